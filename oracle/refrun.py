@@ -1,0 +1,267 @@
+"""TEST INFRASTRUCTURE (oracle harness) -- never imported by the product package.
+
+Runs the UNMODIFIED reference binary built by ``oracle/Makefile.ref`` into
+``oracle/_ref/athena_<cfg>`` and parses its full-precision artefacts:
+
+* ``.rst`` restart dumps  (layout: /root/reference/src/outputs/restart.cpp:42-246)
+* ``.hst`` history files  (layout: /root/reference/src/outputs/history.cpp:376-447)
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference arm may
+use this module.  It reads nothing under /root/reference at run time (the binary is
+self-contained), so it works on the GPU box as well.
+"""
+import os
+import re
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+# cfg name -> make variables (see oracle/Makefile.ref)
+CONFIGS = {
+    "linwave_hydro_hllc": dict(PROB="linear_wave", MHD=0, FLUX="hllc"),
+    "linwave_hydro_roe": dict(PROB="linear_wave", MHD=0, FLUX="roe"),
+    "linwave_hydro_hlle": dict(PROB="linear_wave", MHD=0, FLUX="hlle"),
+    "linwave_mhd_hlld": dict(PROB="linear_wave", MHD=1, FLUX="hlld"),
+    "linwave_mhd_roe": dict(PROB="linear_wave", MHD=1, FLUX="roe"),
+    "linwave_mhd_hlle": dict(PROB="linear_wave", MHD=1, FLUX="hlle"),
+    "blast_mhd_hlld": dict(PROB="blast", MHD=1, FLUX="hlld"),
+    "blast_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc"),
+    "ot_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld"),
+    "kh_hydro_hllc_s1g3": dict(PROB="kh", MHD=0, FLUX="hllc", NGHOST=3, NSCALARS=1),
+    "linwave_hydro_hllc_g3": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=3),
+    "linwave_mhd_hlld_g3": dict(PROB="linear_wave", MHD=1, FLUX="hlld", NGHOST=3),
+}
+
+
+def ref_binary(cfg):
+    return os.path.join(REF_DIR, "athena_" + cfg)
+
+
+def have_ref(cfg):
+    return os.access(ref_binary(cfg), os.X_OK)
+
+
+def build_ref(cfg, jobs=None, quiet=True):
+    """Compile the reference for ``cfg`` (needs /root/reference; no-op if already built)."""
+    if have_ref(cfg):
+        return True
+    if not os.path.isdir("/root/reference/src"):
+        return False
+    mk = CONFIGS[cfg]
+    args = ["make", "-f", os.path.join(HERE, "Makefile.ref"), "CFG=" + cfg,
+            "OUT=" + REF_DIR, "-j%d" % (jobs or os.cpu_count() or 4)]
+    args += ["%s=%s" % (k, v) for k, v in mk.items()]
+    r = subprocess.run(args, cwd=os.path.dirname(HERE), capture_output=quiet, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference build failed for %s:\n%s" % (cfg, (r.stderr or "")[-4000:]))
+    # intermediates are not needed once linked
+    subprocess.run(["rm", "-rf", os.path.join(REF_DIR, cfg)])
+    return have_ref(cfg)
+
+
+def format_athinput(blocks):
+    """blocks: dict name -> dict(param -> value) in the reference's <block> grammar
+    (/root/reference/src/parameter_input.cpp)."""
+    out = []
+    for bname, params in blocks.items():
+        out.append("<%s>" % bname)
+        for k, v in params.items():
+            if isinstance(v, bool):
+                v = "true" if v else "false"
+            elif isinstance(v, float):
+                v = repr(v)
+            out.append("%-14s = %s" % (k, v))
+        out.append("")
+    return "\n".join(out)
+
+
+def run_reference(cfg, blocks, workdir=None, threads=1, timeout=3600):
+    """Run the reference binary on an athinput given as nested dicts. Returns (workdir, stdout)."""
+    exe = ref_binary(cfg)
+    if not have_ref(cfg):
+        raise FileNotFoundError(exe + " (build it here with oracle/Makefile.ref)")
+    workdir = workdir or tempfile.mkdtemp(prefix="athref_")
+    os.makedirs(workdir, exist_ok=True)
+    blocks = {k: dict(v) for k, v in blocks.items()}
+    blocks.setdefault("mesh", {})["num_threads"] = threads
+    inp = os.path.join(workdir, "athinput.ref")
+    with open(inp, "w") as f:
+        f.write(format_athinput(blocks))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    r = subprocess.run([exe, "-i", inp, "-d", workdir], capture_output=True, text=True,
+                       timeout=timeout, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("reference run failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return workdir, r.stdout
+
+
+def parse_zone_cycles(stdout):
+    """Extract the reference's own throughput line (/root/reference/src/main.cpp:639-651)."""
+    out = {}
+    for key in ("zone-cycles/cpu_second", "zone-cycles/omp_wsecond", "cpu time used",
+                "omp wtime used", "zone-cycles"):
+        m = re.search(re.escape(key) + r"\s*=\s*([0-9.eE+-]+)", stdout)
+        if m:
+            out[key] = float(m.group(1))
+    m = re.search(r"cycle=(\d+)\s+time=", stdout[::-1][::-1].rsplit("cycle=", 1)[-1] and stdout)
+    return out
+
+
+def read_rst(path):
+    """Parse a restart dump. Returns dict(params=str, nb, root_level, mesh_size, time, dt, ncycle,
+    nx=(nx1,nx2,nx3) of the MeshBlock, ng, loc=[(lx1,lx2,lx3,level)], u=[...], b1=[...], ...)."""
+    raw = open(path, "rb").read()
+    end = raw.index(b"<par_end>\n") + len(b"<par_end>\n")
+    params = raw[:end].decode()
+    off = end
+    nbtotal, root_level = struct.unpack_from("ii", raw, off)
+    off += 8
+    # RegionSize: 9 doubles (x1min,x2min,x3min,x1max,x2max,x3max,x1rat,x2rat,x3rat) + 3 ints + pad
+    rs = struct.unpack_from("9d3i", raw, off)
+    off += 88
+    time, dt = struct.unpack_from("dd", raw, off)
+    off += 16
+    (ncycle,) = struct.unpack_from("i", raw, off)
+    off += 4
+    (datasize,) = struct.unpack_from("Q", raw, off)
+    off += 8
+
+    def par(block, name, default=None):
+        m = re.search(r"<%s>(.*?)(?=\n<|\Z)" % block, params, re.S)
+        if not m:
+            return default
+        mm = re.search(r"^\s*%s\s*=\s*([^#\n]+)" % name, m.group(1), re.M)
+        return mm.group(1).strip() if mm else default
+
+    mnx = [int(par("mesh", "nx%d" % d)) for d in (1, 2, 3)]
+    bnx = [int(par("meshblock", "nx%d" % d, mnx[d - 1])) for d in (1, 2, 3)]
+    locs = []
+    for _ in range(nbtotal):
+        lx1, lx2, lx3, lev = struct.unpack_from("qqqi", raw, off)
+        off += 32
+        off += 8  # cost
+        locs.append((lx1, lx2, lx3, lev))
+    # infer NGHOST, MHD and NSCALARS from datasize
+    nd = datasize // 8
+    found = None
+    for ng in (2, 3, 4):
+        nc = [n + 2 * ng if n > 1 else 1 for n in bnx]
+        cells = nc[0] * nc[1] * nc[2]
+        faces = ((nc[0] + 1) * nc[1] * nc[2] + nc[0] * (nc[1] + (1 if bnx[1] > 1 else 0)) * nc[2]
+                 + nc[0] * nc[1] * (nc[2] + (1 if bnx[2] > 1 else 0)))
+        for mhd in (0, 1):
+            rest = nd - 5 * cells - mhd * faces
+            if rest >= 0 and rest % cells == 0 and rest // cells <= 8:
+                found = (ng, mhd, rest // cells, nc)
+                break
+        if found:
+            break
+    if not found:
+        raise ValueError("cannot infer restart layout (datasize=%d)" % datasize)
+    ng, mhd, nscal, nc = found
+    out = dict(params=params, nb=nbtotal, root_level=root_level, mesh_size=rs, time=time, dt=dt,
+               ncycle=ncycle, nx=tuple(bnx), mesh_nx=tuple(mnx), ng=ng, mhd=bool(mhd),
+               nscalars=nscal, loc=locs, u=[], b1=[], b2=[], b3=[], s=[])
+    f2 = 1 if bnx[1] > 1 else 0
+    f3 = 1 if bnx[2] > 1 else 0
+    for _ in range(nbtotal):
+        a = np.frombuffer(raw, dtype=np.float64, count=nd, offset=off)
+        off += datasize
+        p = 0
+        n = 5 * nc[2] * nc[1] * nc[0]
+        out["u"].append(a[p:p + n].reshape(5, nc[2], nc[1], nc[0]).copy())
+        p += n
+        if mhd:
+            n = nc[2] * nc[1] * (nc[0] + 1)
+            out["b1"].append(a[p:p + n].reshape(nc[2], nc[1], nc[0] + 1).copy())
+            p += n
+            n = nc[2] * (nc[1] + f2) * nc[0]
+            out["b2"].append(a[p:p + n].reshape(nc[2], nc[1] + f2, nc[0]).copy())
+            p += n
+            n = (nc[2] + f3) * nc[1] * nc[0]
+            out["b3"].append(a[p:p + n].reshape(nc[2] + f3, nc[1], nc[0]).copy())
+            p += n
+        if nscal:
+            n = nscal * nc[2] * nc[1] * nc[0]
+            out["s"].append(a[p:p + n].reshape(nscal, nc[2], nc[1], nc[0]).copy())
+            p += n
+    return out
+
+
+def assemble(rst):
+    """Re-assemble block interiors into global arrays. Returns dict(u, b1, b2, b3, s) where face
+    arrays have the +1 extent of the global mesh."""
+    ng = rst["ng"]
+    nx1, nx2, nx3 = rst["nx"]
+    M1, M2, M3 = rst["mesh_nx"]
+    U = np.empty((5, M3, M2, M1))
+    S = np.empty((rst["nscalars"], M3, M2, M1)) if rst["nscalars"] else None
+    B1 = B2 = B3 = None
+    if rst["mhd"]:
+        B1 = np.empty((M3, M2, M1 + 1))
+        B2 = np.empty((M3, M2 + 1, M1))
+        B3 = np.empty((M3 + 1, M2, M1))
+    g1 = ng
+    g2 = ng if nx2 > 1 else 0
+    g3 = ng if nx3 > 1 else 0
+    for b, (lx1, lx2, lx3, _) in enumerate(rst["loc"]):
+        o1, o2, o3 = lx1 * nx1, lx2 * nx2, lx3 * nx3
+        U[:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1] = \
+            rst["u"][b][:, g3:g3 + nx3, g2:g2 + nx2, g1:g1 + nx1]
+        if S is not None:
+            S[:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1] = \
+                rst["s"][b][:, g3:g3 + nx3, g2:g2 + nx2, g1:g1 + nx1]
+        if rst["mhd"]:
+            B1[o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1 + 1] = \
+                rst["b1"][b][g3:g3 + nx3, g2:g2 + nx2, g1:g1 + nx1 + 1]
+            B2[o3:o3 + nx3, o2:o2 + nx2 + 1, o1:o1 + nx1] = \
+                rst["b2"][b][g3:g3 + nx3, g2:g2 + nx2 + 1, g1:g1 + nx1]
+            B3[o3:o3 + nx3 + 1, o2:o2 + nx2, o1:o1 + nx1] = \
+                rst["b3"][b][g3:g3 + nx3 + 1, g2:g2 + nx2, g1:g1 + nx1]
+    return dict(u=U, b1=B1, b2=B2, b3=B3, s=S)
+
+
+def read_hst(path):
+    """History file -> (column names, 2-D array)."""
+    names = None
+    rows = []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                if "[1]" in line:
+                    names = re.findall(r"\[\d+\]=(\S+)", line)
+                continue
+            if line.strip():
+                rows.append([float(x) for x in line.split()])
+    return names, np.array(rows)
+
+
+def linwave_blocks(mhd, mesh=(32, 16, 16), block=None, tlim=0.1, nlim=-1, wave_flag=0,
+                   integrator="vl2", xorder=2, cfl=0.3, amp=1.0e-6, rst_dt=None,
+                   vflow=0.0, problem_id="LinWave"):
+    """athinput for the linear-wave problem (inputs/{hydro,mhd}/athinput.linear_wave3d shape)."""
+    block = block or mesh
+    b = {
+        "job": {"problem_id": problem_id},
+        "output1": {"file_type": "hst", "dt": 1.0e-9 if rst_dt is None else rst_dt,
+                    "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 1.0e30 if rst_dt is None else rst_dt},
+        "time": {"cfl_number": cfl, "nlim": nlim, "tlim": tlim, "integrator": integrator,
+                 "xorder": xorder, "ncycle_out": 1},
+        "mesh": {"nx1": mesh[0], "x1min": 0.0, "x1max": 3.0, "ix1_bc": "periodic",
+                 "ox1_bc": "periodic",
+                 "nx2": mesh[1], "x2min": 0.0, "x2max": 1.5, "ix2_bc": "periodic",
+                 "ox2_bc": "periodic",
+                 "nx3": mesh[2], "x3min": 0.0, "x3max": 1.5, "ix3_bc": "periodic",
+                 "ox3_bc": "periodic", "num_threads": 1, "refinement": "none"},
+        "meshblock": {"nx1": block[0], "nx2": block[1], "nx3": block[2]},
+        "hydro": {"gamma": 1.666666666666667, "iso_sound_speed": 1.0},
+        "problem": {"compute_error": "false", "wave_flag": wave_flag, "amp": amp,
+                    "vflow": vflow, "ang_2_vert": "false", "ang_3_vert": "false"},
+    }
+    return b
