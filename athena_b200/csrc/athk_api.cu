@@ -1,0 +1,668 @@
+// athk_api.cu -- context, memory and the C ABI (include/athk.h) of libathk.so.
+// Product build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see athk_physics.h).
+#include "../../include/athk.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+
+#include <string>
+#include <vector>
+
+#include "athk_backend.h"
+#include "athk_ops.h"
+
+using namespace athk;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(ATHK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+struct athk_ctx {
+  athk_config cfg;
+  Grid g;
+  Geom geo;
+  EosParams eos;
+  EmfSurf sf;
+  cudaStream_t stream;
+  long long launches;
+  bool coords_set, nbr_set;
+  int nremote;
+  // storage
+  Real *u[3];       // hydro registers [nb][5][sn]
+  Real *w;          // [nb][5][sn]
+  Real *bcc;        // [nb][3][sn]
+  Real *b[3];       // field registers [nb][3][sn]
+  Real *flux[3];    // [nb][5][sn]
+  Real *ef;         // [nb][6][sn]
+  Real *wct;        // [nb][3][sn]
+  Real *e;          // [nb][3][sn]
+  Real *s[3];       // scalar registers [nb][ns][sn]
+  Real *r;          // [nb][ns][sn]
+  Real *sflux[3];   // [nb][ns][sn]
+  Real *emfbuf;     // [nb][sf.per_block]
+  Real *remfbuf;    // remote EMF surfaces
+  Real *geo_store;  // 9 arrays [nb][PG]
+  int *nbr;         // [nb][27]
+  Real *dt_blocks;  // [nb]
+  std::vector<int> h_nbr;
+  std::vector<Real> h_geo;   // host mirror of geo_store
+};
+
+static size_t cc_elems(const athk_ctx *c, int nvar) { return (size_t)c->g.nb * nvar * c->g.sn; }
+
+template <class T>
+static int dev_alloc(T **p, size_t n, cudaStream_t st) {
+  *p = nullptr;
+  if (n == 0) return 0;
+  CU(cudaMalloc((void **)p, n * sizeof(T)));
+  CU(cudaMemsetAsync(*p, 0, n * sizeof(T), st));
+  return 0;
+}
+
+extern "C" const char *athk_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
+  if (!cfg || !out) return fail(ATHK_ERR_ARG, "athk_create: null argument");
+  *out = nullptr;
+  if (cfg->nx1 < 4 || cfg->nx2 < 4 || cfg->nx3 < 4)
+    return fail(ATHK_ERR_ARG, "athk_create: only 3-D MeshBlocks with nx>=4 are supported "
+                              "(got %d x %d x %d)", cfg->nx1, cfg->nx2, cfg->nx3);
+  if (cfg->nghost < 2 || cfg->nghost > 4)
+    return fail(ATHK_ERR_ARG, "athk_create: nghost must be 2..4 (got %d)", cfg->nghost);
+  if (cfg->nblocks < 1) return fail(ATHK_ERR_ARG, "athk_create: nblocks must be >= 1");
+  if (cfg->nscalars < 0 || cfg->nscalars > 8)
+    return fail(ATHK_ERR_ARG, "athk_create: nscalars must be 0..8");
+  if (cfg->mhd && cfg->rsolver != ATHK_RS_HLLD)
+    return fail(ATHK_ERR_ARG, "athk_create: MHD path implements rsolver HLLD only (got %d)",
+                cfg->rsolver);
+  if (!cfg->mhd && cfg->rsolver != ATHK_RS_HLLC)
+    return fail(ATHK_ERR_ARG, "athk_create: hydro path implements rsolver HLLC only (got %d)",
+                cfg->rsolver);
+  if (!(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(ATHK_ERR_NODEVICE, "athk_create: no CUDA device visible; libathk has no CPU path");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(ATHK_ERR_ARG, "athk_create: device %d out of range (%d visible)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+
+  athk_ctx *c = new athk_ctx();
+  c->cfg = *cfg;
+  Grid &g = c->g;
+  g.nx1 = cfg->nx1; g.nx2 = cfg->nx2; g.nx3 = cfg->nx3; g.ng = cfg->nghost;
+  g.nc1 = g.nx1 + 2 * g.ng; g.nc2 = g.nx2 + 2 * g.ng; g.nc3 = g.nx3 + 2 * g.ng;
+  g.is = g.ng; g.ie = g.is + g.nx1 - 1;
+  g.js = g.ng; g.je = g.js + g.nx2 - 1;
+  g.ks = g.ng; g.ke = g.ks + g.nx3 - 1;
+  g.P1 = ((g.nc1 + 1 + 3) / 4) * 4;
+  g.P2 = g.nc2 + 1;
+  g.P3 = g.nc3 + 1;
+  g.nb = cfg->nblocks;
+  g.sj = g.P1;
+  g.sk = (idx_t)g.P1 * g.P2;
+  g.sn = g.sk * g.P3;
+  const Real fmin_default = sqrt(1024 * (Real)FLT_MIN);   // eos.hpp:161, adiabatic_mhd.cpp:29-31
+  c->eos = make_eos(cfg->gamma, cfg->dfloor > 0 ? cfg->dfloor : fmin_default,
+                    cfg->pfloor > 0 ? cfg->pfloor : fmin_default,
+                    cfg->sfloor > 0 ? cfg->sfloor : fmin_default);
+  c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
+  c->launches = 0;
+  c->coords_set = c->nbr_set = false;
+  c->nremote = 0;
+  c->remfbuf = nullptr;
+  CU(cudaStreamCreate(&c->stream));
+  cudaStream_t st = c->stream;
+  const int ns = cfg->nscalars;
+  int rc = 0;
+  for (int r = 0; r < 3 && !rc; ++r) rc = dev_alloc(&c->u[r], r < 2 ? cc_elems(c, 5) : 0, st);
+  if (!rc) rc = dev_alloc(&c->w, cc_elems(c, 5), st);
+  for (int d = 0; d < 3 && !rc; ++d) rc = dev_alloc(&c->flux[d], cc_elems(c, 5), st);
+  const size_t mh = cfg->mhd ? 1 : 0;
+  if (!rc) rc = dev_alloc(&c->bcc, mh * cc_elems(c, 3), st);
+  for (int r = 0; r < 3 && !rc; ++r) rc = dev_alloc(&c->b[r], (r < 2 ? mh : 0) * cc_elems(c, 3), st);
+  if (!rc) rc = dev_alloc(&c->ef, mh * cc_elems(c, 6), st);
+  if (!rc) rc = dev_alloc(&c->wct, mh * cc_elems(c, 3), st);
+  if (!rc) rc = dev_alloc(&c->e, mh * cc_elems(c, 3), st);
+  if (!rc) rc = dev_alloc(&c->emfbuf, mh * (size_t)g.nb * c->sf.per_block(), st);
+  for (int r = 0; r < 3 && !rc; ++r) rc = dev_alloc(&c->s[r], (r < 2 && ns) ? cc_elems(c, ns) : 0, st);
+  if (!rc) rc = dev_alloc(&c->r, ns ? cc_elems(c, ns) : 0, st);
+  for (int d = 0; d < 3 && !rc; ++d) rc = dev_alloc(&c->sflux[d], ns ? cc_elems(c, ns) : 0, st);
+  int PG = g.P1 > g.P2 ? g.P1 : g.P2;
+  if (g.P3 > PG) PG = g.P3;
+  c->geo.PG = PG;
+  if (!rc) rc = dev_alloc(&c->geo_store, (size_t)9 * g.nb * PG, st);
+  if (!rc) rc = dev_alloc(&c->nbr, (size_t)g.nb * 27, st);
+  if (!rc) rc = dev_alloc(&c->dt_blocks, (size_t)g.nb, st);
+  if (rc) {
+    athk_destroy(c);
+    return rc;
+  }
+  for (int d = 0; d < 3; ++d) {
+    c->geo.dxf[d] = c->geo_store + (size_t)(0 + d) * g.nb * PG;
+    c->geo.cp[d] = c->geo_store + (size_t)(3 + d) * g.nb * PG;
+    c->geo.cm[d] = c->geo_store + (size_t)(6 + d) * g.nb * PG;
+  }
+  c->h_geo.assign((size_t)9 * g.nb * PG, 0.0);
+  c->h_nbr.assign((size_t)g.nb * 27, -1);
+  CU(cudaStreamSynchronize(st));
+  *out = c;
+  return ATHK_OK;
+}
+
+extern "C" void athk_destroy(athk_ctx *c) {
+  if (!c) return;
+  for (int r = 0; r < 3; ++r) { cudaFree(c->u[r]); cudaFree(c->b[r]); cudaFree(c->s[r]); }
+  for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
+  cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
+  cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
+  cudaFree(c->dt_blocks);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int athk_sync(athk_ctx *c) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  CU(cudaStreamSynchronize(c->stream));
+  return ATHK_OK;
+}
+
+extern "C" long long athk_launch_count(const athk_ctx *c) { return c ? c->launches : 0; }
+extern "C" void *athk_stream(athk_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+//----------------------------------------------------------------------------------------
+extern "C" int athk_set_block_coords(athk_ctx *c, int lb, const double *x1f, const double *x1v,
+                                     const double *dx1f, const double *x2f, const double *x2v,
+                                     const double *dx2f, const double *x3f, const double *x3v,
+                                     const double *dx3f) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "set_block_coords: block %d out of range", lb);
+  const double *xf[3] = {x1f, x2f, x3f}, *xv[3] = {x1v, x2v, x3v}, *dxf[3] = {dx1f, dx2f, dx3f};
+  const int nc[3] = {c->g.nc1, c->g.nc2, c->g.nc3};
+  const int PG = c->geo.PG;
+  const size_t per = (size_t)c->g.nb * PG;
+  for (int d = 0; d < 3; ++d) {
+    if (!xf[d] || !xv[d] || !dxf[d]) return fail(ATHK_ERR_ARG, "set_block_coords: null array");
+    Real *hd = &c->h_geo[(0 + d) * per + (size_t)lb * PG];
+    Real *hp = &c->h_geo[(3 + d) * per + (size_t)lb * PG];
+    Real *hm = &c->h_geo[(6 + d) * per + (size_t)lb * PG];
+    for (int n = 0; n < nc[d]; ++n) {
+      hd[n] = dxf[d][n];
+      // plm.cpp:152-153 -- the geometric factors are ~0.5 but not exactly; keep the same ops
+      hp[n] = (xf[d][n + 1] - xv[d][n]) / dxf[d][n];
+      hm[n] = (xv[d][n] - xf[d][n]) / dxf[d][n];
+    }
+  }
+  for (int a = 0; a < 9; ++a)
+    CU(cudaMemcpyAsync(c->geo_store + a * per + (size_t)lb * PG, &c->h_geo[a * per + (size_t)lb * PG],
+                       PG * sizeof(Real), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->coords_set = true;
+  return ATHK_OK;
+}
+
+extern "C" int athk_set_neighbors(athk_ctx *c, const int *nbr) {
+  if (!c || !nbr) return fail(ATHK_ERR_ARG, "set_neighbors: null argument");
+  const int n = c->g.nb * 27;
+  for (int q = 0; q < n; ++q) {
+    if (nbr[q] >= c->g.nb) return fail(ATHK_ERR_ARG, "set_neighbors: entry %d = %d out of range", q, nbr[q]);
+    c->h_nbr[q] = nbr[q];
+  }
+  CU(cudaMemcpyAsync(c->nbr, c->h_nbr.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->nbr_set = true;
+  return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+// array table: device base, component offset, nvar, extra extent per direction
+struct ArrDesc {
+  Real *base;
+  int ncomp_total;   // components in the device array per block
+  int comp0;         // first component
+  int nvar;          // components exposed
+  int a1, a2, a3;    // host dims = (nc3+a3, nc2+a2, nc1+a1)
+};
+
+static bool describe(athk_ctx *c, int array, ArrDesc *d) {
+  const int ns = c->cfg.nscalars;
+  switch (array) {
+    case ATHK_U: case ATHK_U1: case ATHK_U2:
+      *d = {c->u[array - ATHK_U], 5, 0, 5, 0, 0, 0}; break;
+    case ATHK_W: *d = {c->w, 5, 0, 5, 0, 0, 0}; break;
+    case ATHK_BCC: *d = {c->bcc, 3, 0, 3, 0, 0, 0}; break;
+    case ATHK_B_X1F: case ATHK_B_X2F: case ATHK_B_X3F: {
+      const int q = array - ATHK_B_X1F;
+      *d = {c->b[0], 3, q, 1, q == 0, q == 1, q == 2}; break; }
+    case ATHK_B1_X1F: case ATHK_B1_X2F: case ATHK_B1_X3F: {
+      const int q = array - ATHK_B1_X1F;
+      *d = {c->b[1], 3, q, 1, q == 0, q == 1, q == 2}; break; }
+    case ATHK_B2_X1F: case ATHK_B2_X2F: case ATHK_B2_X3F: {
+      const int q = array - ATHK_B2_X1F;
+      *d = {c->b[2], 3, q, 1, q == 0, q == 1, q == 2}; break; }
+    case ATHK_FLUX_X1: case ATHK_FLUX_X2: case ATHK_FLUX_X3: {
+      const int q = array - ATHK_FLUX_X1;
+      *d = {c->flux[q], 5, 0, 5, q == 0, q == 1, q == 2}; break; }
+    case ATHK_E_X1E: *d = {c->e, 3, 0, 1, 0, 1, 1}; break;
+    case ATHK_E_X2E: *d = {c->e, 3, 1, 1, 1, 0, 1}; break;
+    case ATHK_E_X3E: *d = {c->e, 3, 2, 1, 1, 1, 0}; break;
+    case ATHK_E3_X1F: *d = {c->ef, 6, 0, 1, 1, 0, 0}; break;
+    case ATHK_E2_X1F: *d = {c->ef, 6, 1, 1, 1, 0, 0}; break;
+    case ATHK_E1_X2F: *d = {c->ef, 6, 2, 1, 0, 1, 0}; break;
+    case ATHK_E3_X2F: *d = {c->ef, 6, 3, 1, 0, 1, 0}; break;
+    case ATHK_E2_X3F: *d = {c->ef, 6, 4, 1, 0, 0, 1}; break;
+    case ATHK_E1_X3F: *d = {c->ef, 6, 5, 1, 0, 0, 1}; break;
+    case ATHK_WGHT_X1F: *d = {c->wct, 3, 0, 1, 1, 0, 0}; break;
+    case ATHK_WGHT_X2F: *d = {c->wct, 3, 1, 1, 0, 1, 0}; break;
+    case ATHK_WGHT_X3F: *d = {c->wct, 3, 2, 1, 0, 0, 1}; break;
+    case ATHK_S: case ATHK_S1: case ATHK_S2:
+      *d = {c->s[array - ATHK_S], ns, 0, ns, 0, 0, 0}; break;
+    case ATHK_R: *d = {c->r, ns, 0, ns, 0, 0, 0}; break;
+    case ATHK_SFLUX_X1: case ATHK_SFLUX_X2: case ATHK_SFLUX_X3: {
+      const int q = array - ATHK_SFLUX_X1;
+      *d = {c->sflux[q], ns, 0, ns, q == 0, q == 1, q == 2}; break; }
+    default: return false;
+  }
+  return d->base != nullptr && d->nvar > 0;
+}
+
+static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_device,
+                      bool sync_after = true) {
+  if (!c || !host) return fail(ATHK_ERR_ARG, "upload/download: null argument");
+  if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "upload/download: block %d out of range", lb);
+  ArrDesc d;
+  if (!describe(c, array, &d))
+    return fail(ATHK_ERR_ARG, "upload/download: array %d not allocated in this configuration", array);
+  const Grid &g = c->g;
+  const int n1 = g.nc1 + d.a1, n2 = g.nc2 + d.a2, n3 = g.nc3 + d.a3;
+  for (int n = 0; n < d.nvar; ++n) {
+    Real *dev = d.base + ((idx_t)lb * d.ncomp_total + d.comp0 + n) * g.sn;
+    double *h = host + (size_t)n * n3 * n2 * n1;
+#ifndef ATHK_EMULATE
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr((void *)h, (size_t)n1 * sizeof(Real), n1, n2);
+    cudaPitchedPtr dp = make_cudaPitchedPtr((void *)dev, (size_t)g.P1 * sizeof(Real), g.P1, g.P2);
+    p.srcPtr = to_device ? hp : dp;
+    p.dstPtr = to_device ? dp : hp;
+    p.extent = make_cudaExtent((size_t)n1 * sizeof(Real), n2, n3);
+    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&p, c->stream));
+#else
+    for (int k = 0; k < n3; ++k)
+      for (int j = 0; j < n2; ++j) {
+        Real *dr = dev + gidx(g, k, j, 0);
+        double *hr = h + ((size_t)k * n2 + j) * n1;
+        if (to_device) memcpy(dr, hr, n1 * sizeof(Real));
+        else memcpy(hr, dr, n1 * sizeof(Real));
+      }
+#endif
+  }
+  if (!to_device && sync_after) CU(cudaStreamSynchronize(c->stream));
+  return ATHK_OK;
+}
+
+extern "C" int athk_download_async(athk_ctx *c, int array, int lb, double *host) {
+  return copy_array(c, array, lb, host, false, false);
+}
+
+extern "C" int athk_upload(athk_ctx *c, int array, int lb, const double *host) {
+  return copy_array(c, array, lb, const_cast<double *>(host), true);
+}
+extern "C" int athk_download(athk_ctx *c, int array, int lb, double *host) {
+  return copy_array(c, array, lb, host, false);
+}
+
+extern "C" int athk_device_array(athk_ctx *c, int array, void **dptr, long long *stride_block,
+                                 long long *stride_var, long long *stride_k, long long *stride_j) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  ArrDesc d;
+  if (!describe(c, array, &d)) return fail(ATHK_ERR_ARG, "device_array: array %d not allocated", array);
+  if (dptr) *dptr = d.base + (idx_t)d.comp0 * c->g.sn;
+  if (stride_block) *stride_block = (long long)d.ncomp_total * c->g.sn;
+  if (stride_var) *stride_var = c->g.sn;
+  if (stride_k) *stride_k = c->g.sk;
+  if (stride_j) *stride_j = c->g.sj;
+  return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+#define NEED_READY(c)                                                                      \
+  do {                                                                                     \
+    if (!(c)) return fail(ATHK_ERR_ARG, "null context");                                   \
+    if (!(c)->coords_set || !(c)->nbr_set)                                                 \
+      return fail(ATHK_ERR_STATE, "%s: call athk_set_block_coords and athk_set_neighbors " \
+                                  "first", __func__);                                      \
+  } while (0)
+
+#define LAUNCH(c, range, functor)                               \
+  do {                                                          \
+    CU(launch_points((c)->stream, (c)->g.nb, (range), (functor))); \
+    (c)->launches++;                                            \
+  } while (0)
+
+static bool bad_reg(int r) { return r < 0 || r > 2; }
+
+extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
+  NEED_READY(c);
+  if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "cons2prim: register %d not allocated", reg);
+  const Grid &g = c->g;
+  Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+  if (c->cfg.mhd) {
+    Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr};
+    LAUNCH(c, r, f);
+  } else {
+    Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr};
+    LAUNCH(c, r, f);
+  }
+  return ATHK_OK;
+}
+
+template <int DIR, int ORDER, bool MHD>
+static int launch_flux(athk_ctx *c, double dt, int breg) {
+  const Grid &g = c->g;
+  // loop limits of calculate_fluxes.cpp:68-76,176-182,299-302 (3-D)
+  Range3 r;
+  if (DIR == 0) {
+    r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
+    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
+  } else if (DIR == 1) {
+    r = {g.ks, g.ke, g.js, g.je + 1, g.is - 1, g.ie + 1};
+    if (MHD) { r.kl--; r.ku++; }
+  } else {
+    r = {g.ks, g.ke + 1, g.js, g.je, g.is, g.ie};
+    if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
+  }
+  FluxPoint<DIR, ORDER, MHD> f = {g, c->eos, c->geo, c->w, c->bcc, MHD ? c->b[breg] : nullptr,
+                                  c->flux[DIR], c->ef, c->wct, dt};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+template <int ORDER, bool MHD>
+static int launch_flux3(athk_ctx *c, double dt, int breg) {
+  int rc = launch_flux<0, ORDER, MHD>(c, dt, breg);
+  if (!rc) rc = launch_flux<1, ORDER, MHD>(c, dt, breg);
+  if (!rc) rc = launch_flux<2, ORDER, MHD>(c, dt, breg);
+  return rc;
+}
+
+extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int breg) {
+  NEED_READY(c);
+  if (c->cfg.mhd && (bad_reg(breg) || !c->b[breg]))
+    return fail(ATHK_ERR_ARG, "calculate_fluxes: field register %d not allocated", breg);
+  if (order == 1) return c->cfg.mhd ? launch_flux3<1, true>(c, dt_mesh, breg) : launch_flux3<1, false>(c, dt_mesh, breg);
+  if (order == 2) return c->cfg.mhd ? launch_flux3<2, true>(c, dt_mesh, breg) : launch_flux3<2, false>(c, dt_mesh, breg);
+  return fail(ATHK_ERR_ARG, "calculate_fluxes: xorder %d not implemented (1 = donor cell, 2 = PLM)", order);
+}
+
+extern "C" int athk_compute_corner_e(athk_ctx *c) {
+  NEED_READY(c);
+  if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "compute_corner_e: context is not MHD");
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  CornerEPoint f = {g, c->w, c->bcc, c->ef, c->wct, c->e};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+extern "C" int athk_send_flux_correction(athk_ctx *c) {
+  NEED_READY(c);
+  if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "send_flux_correction: context is not MHD");
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  EmfPackPoint f = {g, c->sf, c->e, c->emfbuf};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+extern "C" int athk_recv_flux_correction(athk_ctx *c) {
+  NEED_READY(c);
+  if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "recv_flux_correction: context is not MHD");
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  EmfApplyPoint f = {g, c->sf, c->e, c->emfbuf, c->nbr, c->remfbuf};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+// weighted_ave.cpp branch structure -> kernel mode (see WeightedAvePoint)
+static int wa_mode(const double w[5], int *mode) {
+  if (w[3] != 0.0 || w[4] != 0.0) return -1;
+  if (w[0] == 1.0) {
+    if (w[2] != 0.0) *mode = 0;
+    else if (w[1] != 0.0) *mode = 1;
+    else *mode = -2;   // nothing to do
+  } else if (w[0] == 0.0) {
+    if (w[2] != 0.0) *mode = 2;
+    else if (w[1] != 0.0) *mode = 3;
+    else *mode = 7;    // ZeroClear
+  } else {
+    if (w[2] != 0.0) *mode = 4;
+    else if (w[1] != 0.0) *mode = 5;
+    else *mode = 6;
+  }
+  return 0;
+}
+
+static int weighted_ave(athk_ctx *c, Real *out, const Real *in1, const Real *in2, int nvar, int fc,
+                        const double w[5]) {
+  int mode;
+  if (wa_mode(w, &mode))
+    return fail(ATHK_ERR_ARG, "weighted_ave: wght[3], wght[4] != 0 (3S*/ssprk5_4 registers) not implemented");
+  if (mode == -2) return ATHK_OK;
+  const Grid &g = c->g;
+  if ((mode == 0 || mode == 2 || mode == 4) && !in2) return fail(ATHK_ERR_ARG, "weighted_ave: in2 register not allocated");
+  if (mode != 6 && mode != 7 && !in1) return fail(ATHK_ERR_ARG, "weighted_ave: in1 register not allocated");
+  Range3 r = {g.ks, g.ke + fc, g.js, g.je + fc, g.is, g.ie + fc};
+  if (mode == 7) {   // out = 0*out + 0: the reference zeroes through the (w0==0,w1==0) branch
+    WeightedAvePoint f = {g, nvar, fc, 6, 0.0, 0.0, 0.0, out, out, out};
+    // weighted_ave.cpp: with w0==0 and all other weights 0 nothing is executed in the reference
+    (void)f;
+    return ATHK_OK;
+  }
+  WeightedAvePoint f = {g, nvar, fc, mode, w[0], w[1], w[2], out, in1 ? in1 : out, in2 ? in2 : out};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+extern "C" int athk_weighted_ave_cc(athk_ctx *c, int what, int out_reg, int in1_reg, int in2_reg,
+                                    const double wght[5]) {
+  NEED_READY(c);
+  if (bad_reg(out_reg) || bad_reg(in1_reg) || bad_reg(in2_reg) || !wght)
+    return fail(ATHK_ERR_ARG, "weighted_ave_cc: bad register or null weights");
+  Real **regs = (what == 0) ? c->u : c->s;
+  const int nvar = (what == 0) ? 5 : c->cfg.nscalars;
+  if (what != 0 && what != 1) return fail(ATHK_ERR_ARG, "weighted_ave_cc: what must be 0 (u) or 1 (s)");
+  if (!regs[out_reg]) return fail(ATHK_ERR_ARG, "weighted_ave_cc: out register %d not allocated", out_reg);
+  return weighted_ave(c, regs[out_reg], regs[in1_reg], regs[in2_reg], nvar, 0, wght);
+}
+
+extern "C" int athk_weighted_ave_fc(athk_ctx *c, int out_reg, int in1_reg, int in2_reg,
+                                    const double wght[5]) {
+  NEED_READY(c);
+  if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "weighted_ave_fc: context is not MHD");
+  if (bad_reg(out_reg) || bad_reg(in1_reg) || bad_reg(in2_reg) || !wght)
+    return fail(ATHK_ERR_ARG, "weighted_ave_fc: bad register or null weights");
+  if (!c->b[out_reg]) return fail(ATHK_ERR_ARG, "weighted_ave_fc: out register %d not allocated", out_reg);
+  return weighted_ave(c, c->b[out_reg], c->b[in1_reg], c->b[in2_reg], 3, 1, wght);
+}
+
+extern "C" int athk_swap_registers(athk_ctx *c, int what, int a, int b) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  if (bad_reg(a) || bad_reg(b)) return fail(ATHK_ERR_ARG, "swap_registers: bad register");
+  Real **regs = (what == 0) ? c->u : (what == 1 ? c->b : (what == 2 ? c->s : nullptr));
+  if (!regs) return fail(ATHK_ERR_ARG, "swap_registers: what must be 0 (u), 1 (b) or 2 (s)");
+  Real *t = regs[a];
+  regs[a] = regs[b];
+  regs[b] = t;
+  return ATHK_OK;
+}
+
+extern "C" int athk_zero_register(athk_ctx *c, int what, int reg) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "zero_register: bad register");
+  Real *p = (what == 0) ? c->u[reg] : (what == 1 ? c->b[reg] : (what == 2 ? c->s[reg] : nullptr));
+  const int nvar = (what == 0) ? 5 : (what == 1 ? 3 : c->cfg.nscalars);
+  if (!p) return fail(ATHK_ERR_ARG, "zero_register: register not allocated");
+  CU(cudaMemsetAsync(p, 0, cc_elems(c, nvar) * sizeof(Real), c->stream));
+  return ATHK_OK;
+}
+
+extern "C" int athk_add_flux_divergence(athk_ctx *c, double wght, int reg) {
+  NEED_READY(c);
+  if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "add_flux_divergence: register %d not allocated", reg);
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
+  FluxDivPoint f = {g, c->geo, 5, wght, c->flux[0], c->flux[1], c->flux[2], c->u[reg]};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+extern "C" int athk_ct(athk_ctx *c, double wght, int reg) {
+  NEED_READY(c);
+  if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "ct: context is not MHD");
+  if (bad_reg(reg) || !c->b[reg]) return fail(ATHK_ERR_ARG, "ct: register %d not allocated", reg);
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  CTPoint f = {g, c->geo, wght, c->e, c->b[reg]};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
+  NEED_READY(c);
+  if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "exchange_ghosts: bad register");
+  const Grid &g = c->g;
+  if (what_mask & 1) {
+    if (!c->u[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: u register %d not allocated", reg);
+    Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+    GhostFillCC f = {g, 5, c->u[reg], c->nbr};
+    LAUNCH(c, r, f);
+  }
+  if (what_mask & 2) {
+    if (!c->cfg.mhd || !c->b[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: b register %d not allocated", reg);
+    Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
+    GhostFillFC f = {g, c->b[reg], c->nbr};
+    LAUNCH(c, r, f);
+  }
+  if (what_mask & 4) {
+    if (!c->s[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: s register %d not allocated", reg);
+    Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+    GhostFillCC f = {g, c->cfg.nscalars, c->s[reg], c->nbr};
+    LAUNCH(c, r, f);
+  }
+  return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+// Hydro::NewBlockTimeStep: block-wide min reduction.  min() is exact and order independent,
+// so a tree reduction gives the reference's serial result bit for bit.
+#ifndef ATHK_EMULATE
+template <bool MHD>
+__global__ void __launch_bounds__(256) k_block_dt(const CellDt<MHD> f, Real *dt_blocks) {
+  const Grid &g = f.g;
+  const int blk = blockIdx.y;
+  const int ncell = g.nx1 * g.nx2 * g.nx3;
+  Real m = DBL_MAX;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
+    const int i = q % g.nx1;
+    const int t = q / g.nx1;
+    const int j = t % g.nx2;
+    const int k = t / g.nx2;
+    m = min_std(m, f(blk, g.ks + k, g.js + j, g.is + i));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = min_std(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ Real sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = sm[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) m = min_std(m, __shfl_xor_sync(0xffu, m, o));
+    // positive doubles order like their bit patterns
+    if (threadIdx.x == 0)
+      atomicMin((unsigned long long *)&dt_blocks[blk], (unsigned long long)__double_as_longlong(m));
+  }
+}
+__global__ void k_fill(Real *p, int n, Real v) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) p[q] = v;
+}
+#endif
+
+extern "C" int athk_new_block_dt(athk_ctx *c, double cfl_number, double *dt_blocks, double *dt_min) {
+  NEED_READY(c);
+  const Grid &g = c->g;
+  std::vector<Real> h(g.nb);
+#ifndef ATHK_EMULATE
+  k_fill<<<(g.nb + 255) / 256, 256, 0, c->stream>>>(c->dt_blocks, g.nb, DBL_MAX);
+  const int ncell = g.nx1 * g.nx2 * g.nx3;
+  int gx = (ncell + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, g.nb);
+  if (c->cfg.mhd) {
+    CellDt<true> f = {g, c->eos, c->geo, c->w, c->bcc, c->b[0]};
+    k_block_dt<true><<<grid, 256, 0, c->stream>>>(f, c->dt_blocks);
+  } else {
+    CellDt<false> f = {g, c->eos, c->geo, c->w, nullptr, nullptr};
+    k_block_dt<false><<<grid, 256, 0, c->stream>>>(f, c->dt_blocks);
+  }
+  CU(cudaGetLastError());
+  c->launches += 2;
+  CU(cudaMemcpyAsync(h.data(), c->dt_blocks, g.nb * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+#else
+  for (int b = 0; b < g.nb; ++b) {
+    Real m = DBL_MAX;
+    for (int k = g.ks; k <= g.ke; ++k)
+      for (int j = g.js; j <= g.je; ++j)
+        for (int i = g.is; i <= g.ie; ++i) {
+          if (c->cfg.mhd) {
+            CellDt<true> f = {g, c->eos, c->geo, c->w, c->bcc, c->b[0]};
+            m = min_std(m, f(b, k, j, i));
+          } else {
+            CellDt<false> f = {g, c->eos, c->geo, c->w, nullptr, nullptr};
+            m = min_std(m, f(b, k, j, i));
+          }
+        }
+    h[b] = m;
+  }
+#endif
+  Real mn = DBL_MAX;
+  for (int b = 0; b < g.nb; ++b) {
+    h[b] *= cfl_number;   // new_blockdt.cpp:191
+    if (dt_blocks) dt_blocks[b] = h[b];
+    mn = min_std(mn, h[b]);
+  }
+  if (dt_min) *dt_min = mn;
+  return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+// not yet implemented entry points (declared in athk.h; exported so the ABI is complete)
+extern "C" int athk_calculate_scalar_fluxes(athk_ctx *, int) { return fail(ATHK_ERR_ARG, "calculate_scalar_fluxes: not implemented yet"); }
+extern "C" int athk_add_scalar_flux_divergence(athk_ctx *, double, int) { return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: not implemented yet"); }
+extern "C" int athk_history(athk_ctx *, double *, int) { return fail(ATHK_ERR_ARG, "history: not implemented yet"); }
+extern "C" int athk_stage(athk_ctx *, int, int, const athk_stage_wghts *, double) { return fail(ATHK_ERR_ARG, "stage: not implemented yet"); }
+extern "C" int athk_remote_configure(athk_ctx *, int, const int *, const int *, const int *, const int *) { return fail(ATHK_ERR_ARG, "remote_configure: not implemented yet"); }
+extern "C" long long athk_remote_ghost_count(athk_ctx *, int, int) { return -1; }
+extern "C" long long athk_remote_emf_count(athk_ctx *, int) { return -1; }
+extern "C" int athk_remote_set_buffers(athk_ctx *, double *, double *, const long long *, double *, double *, const long long *) { return fail(ATHK_ERR_ARG, "remote_set_buffers: not implemented yet"); }
+extern "C" int athk_remote_pack_ghosts(athk_ctx *, int, int) { return fail(ATHK_ERR_ARG, "remote_pack_ghosts: not implemented yet"); }
+extern "C" int athk_remote_pack_emf(athk_ctx *) { return fail(ATHK_ERR_ARG, "remote_pack_emf: not implemented yet"); }

@@ -1,0 +1,582 @@
+// athk_ops.h -- per-point operator bodies of the MeshBlock update ("one thread = one zone / face /
+// edge").  Each functor is a POD of raw pointers + sizes with
+//     void operator()(int blk, int k, int j, int i) const
+// so that the CUDA launcher (athk_api.cu: one thread per point, i fastest => coalesced rows) and
+// the index-logic harness under tests/emul (plain loops, test infrastructure only) execute the
+// SAME body.  Arithmetic lives in athk_physics.h; this file is extents, stencils and layout.
+//
+// Device layout ("padded box"): every 3-D array of every kind (cell, face, edge) of a MeshBlock
+// uses the same strides  idx(k,j,i) = k*sk + j*sj + i  with sj = P1 >= nc1+1 (rounded up to a
+// multiple of 4 doubles = one 32-byte sector), sk = P1*(nc2+1), plane size sn = sk*(nc3+1).
+// A multi-component array of block b is [b][n][sn].  One index computation serves all arrays.
+#ifndef ATHK_OPS_H_
+#define ATHK_OPS_H_
+
+#include "athk_physics.h"
+
+namespace athk {
+
+typedef long long idx_t;
+
+struct Grid {
+  int nx1, nx2, nx3, ng;
+  int nc1, nc2, nc3;            // cells including ghosts
+  int is, ie, js, je, ks, ke;   // active range (AthenaArray indexing: is = ng)
+  int P1, P2, P3;               // padded extents
+  int nb;                       // MeshBlocks in this context
+  idx_t sj, sk, sn;             // strides (elements)
+};
+
+ATHK_HD idx_t gidx(const Grid &g, int k, int j, int i) { return (idx_t)k * g.sk + (idx_t)j * g.sj + i; }
+
+// per-block 1-D geometry, each [nb][PG] with PG = max(P1,P2,P3)
+struct Geom {
+  int PG;
+  const Real *dxf[3];   // dx1f(i), dx2f(j), dx3f(k)
+  const Real *cp[3];    // (xf(n+1) - xv(n)) / dxf(n)   plm.cpp:152
+  const Real *cm[3];    // (xv(n) - xf(n)) / dxf(n)     plm.cpp:153
+};
+
+// neighbour table entry for offsets (ox1,ox2,ox3) in {-1,0,1}
+ATHK_HD int nbr_slot(int ox1, int ox2, int ox3) { return (ox3 + 1) * 9 + (ox2 + 1) * 3 + (ox1 + 1); }
+
+//========================================================================================
+// EquationOfState::ConservedToPrimitive for one cell (+ CalculateCellCenteredField for MHD)
+template <bool MHD>
+struct Cons2PrimPoint {
+  Grid g;
+  EosParams eos;
+  Real *u;          // [nb][5][sn]   in/out (floors written back)
+  const Real *b;    // [nb][3][sn]   face fields (x1f,x2f,x3f)
+  Real *w;          // [nb][5][sn]
+  Real *bcc;        // [nb][3][sn]
+  const int *nbr;   // [nb][27]
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    // range: interior plus ghost sides with a neighbour (time_integrator.cpp:2206-2212)
+    const int *nb = nbr + blk * 27;
+    if (i < g.is && nb[nbr_slot(-1, 0, 0)] == -1) return;
+    if (i > g.ie && nb[nbr_slot(1, 0, 0)] == -1) return;
+    if (j < g.js && nb[nbr_slot(0, -1, 0)] == -1) return;
+    if (j > g.je && nb[nbr_slot(0, 1, 0)] == -1) return;
+    if (k < g.ks && nb[nbr_slot(0, 0, -1)] == -1) return;
+    if (k > g.ke && nb[nbr_slot(0, 0, 1)] == -1) return;
+    const idx_t c = gidx(g, k, j, i);
+    Real *ub = u + (idx_t)blk * 5 * g.sn + c;
+    Real *wb = w + (idx_t)blk * 5 * g.sn + c;
+    Real uc[5], wc[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) uc[n] = ub[n * g.sn];
+    const Real d0 = uc[IDN], e0 = uc[IEN];
+    if (MHD) {
+      const Real *bb = b + (idx_t)blk * 3 * g.sn + c;
+      Real *bc = bcc + (idx_t)blk * 3 * g.sn + c;
+      // uniform Cartesian: unweighted average of the two faces (field.cpp:139-142)
+      Real bc1 = 0.5 * bb[0] + 0.5 * bb[1];
+      Real bc2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj];
+      Real bc3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
+      bc[0] = bc1;
+      bc[g.sn] = bc2;
+      bc[2 * g.sn] = bc3;
+      cons2prim_mhd(eos, uc, bc1, bc2, bc3, wc);
+    } else {
+      cons2prim_hydro(eos, uc, wc);
+    }
+    if (uc[IDN] != d0) ub[IDN * g.sn] = uc[IDN];
+    if (uc[IEN] != e0) ub[IEN * g.sn] = uc[IEN];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) wb[n * g.sn] = wc[n];
+  }
+};
+
+//========================================================================================
+// One face of Hydro::CalculateFluxes: reconstruct L/R (donor cell or PLM) + Riemann solve.
+// DIR 0/1/2 = x1/x2/x3 sweep.  The face (k,j,i) lies between cell c-s (left) and c (right).
+// RS: 0 = HLLC (hydro), 1 = HLLD (MHD)
+template <int DIR, int ORDER, bool MHD>
+struct FluxPoint {
+  Grid g;
+  EosParams eos;
+  Geom geo;
+  const Real *w, *bcc, *b;
+  Real *flx;      // flux[DIR]: [nb][5][sn]
+  Real *ef;       // face EMFs: [nb][6][sn], components 2*DIR (ey) and 2*DIR+1 (ez)
+  Real *wct;      // wght: [nb][3][sn], component DIR
+  Real dt;        // pmy_mesh->dt, full step
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const int NW = MHD ? 7 : 5;
+    const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
+    const idx_t c = gidx(g, k, j, i);
+    const int n_dir = (DIR == 0) ? i : (DIR == 1 ? j : k);   // index along the sweep
+    const Real *wb = w + (idx_t)blk * 5 * g.sn + c;
+    // rotated variable map: (d, v_n, v_t1, v_t2, p)
+    const int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
+    const idx_t voff[5] = {(idx_t)IDN * g.sn, (idx_t)ivx * g.sn, (idx_t)ivy * g.sn,
+                           (idx_t)ivz * g.sn, (idx_t)IPR * g.sn};
+    Real wl[7], wr[7];
+    Real cpl = 0.0, cmr = 0.0;
+    if (ORDER == 2) {
+      cpl = geo.cp[DIR][blk * geo.PG + n_dir - 1];
+      cmr = geo.cm[DIR][blk * geo.PG + n_dir];
+    }
+#pragma unroll
+    for (int n = 0; n < NW; ++n) {
+      const Real *q;
+      if (n < 5) {
+        q = wb + voff[n];
+      } else {
+        const int ib = (n == 5) ? (DIR + 1) % 3 : (DIR + 2) % 3;
+        q = bcc + ((idx_t)blk * 3 + ib) * g.sn + c;
+      }
+      if (ORDER == 1) {
+        wl[n] = q[-s];
+        wr[n] = q[0];
+      } else {
+        const Real q0 = q[-2 * s], q1 = q[-s], q2 = q[0], q3 = q[s];
+        const Real d01 = q1 - q0, d12 = q2 - q1, d23 = q3 - q2;
+        wl[n] = q1 + cpl * vl_slope(d01, d12);
+        wr[n] = q2 - cmr * vl_slope(d12, d23);
+      }
+    }
+    Real f[7];
+    Real *fb = flx + (idx_t)blk * 5 * g.sn + c;
+    if (MHD) {
+      const Real bxi = b[((idx_t)blk * 3 + DIR) * g.sn + c];
+      hlld_flux(eos, wl, wr, bxi, f);
+      Real *eb = ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
+      eb[0] = -f[IBY];
+      eb[g.sn] = f[IBZ];
+      const Real dxw = geo.dxf[DIR][blk * geo.PG + n_dir];
+      wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, dt);
+    } else {
+      hllc_flux(eos, wl, wr, f);
+    }
+    fb[voff[0]] = f[IDN];
+    fb[voff[1]] = f[IVX];
+    fb[voff[2]] = f[IVY];
+    fb[voff[3]] = f[IVZ];
+    fb[(idx_t)IEN * g.sn] = f[IEN];
+  }
+};
+
+//========================================================================================
+// Field::ComputeCornerE, 3-D branch (calculate_corner_e.cpp:130-229): cell-centred -(v x B)
+// is evaluated on the fly (same bits as the reference's cc_e_ scratch array).
+struct CornerEPoint {
+  Grid g;
+  const Real *w, *bcc;
+  const Real *ef;    // [nb][6][sn]: 0 e3_x1f, 1 e2_x1f, 2 e1_x2f, 3 e3_x2f, 4 e2_x3f, 5 e1_x3f
+  const Real *wct;   // [nb][3][sn]
+  Real *e;           // [nb][3][sn]: x1e,x2e,x3e
+  ATHK_HD Real cce(const Real *wb, const Real *bc, idx_t c, int comp) const {
+    // comp 0: vz*by - vy*bz ; 1: vx*bz - vz*bx ; 2: vy*bx - vx*by
+    const Real v1 = wb[IVX * g.sn + c], v2 = wb[IVY * g.sn + c], v3 = wb[IVZ * g.sn + c];
+    const Real b1 = bc[c], b2 = bc[g.sn + c], b3 = bc[2 * g.sn + c];
+    if (comp == 0) return v3 * b2 - v2 * b3;
+    if (comp == 1) return v1 * b3 - v3 * b1;
+    return v2 * b1 - v1 * b2;
+  }
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const idx_t si = 1, sj = g.sj, sk = g.sk;
+    const Real *wb = w + (idx_t)blk * 5 * g.sn;
+    const Real *bc = bcc + (idx_t)blk * 3 * g.sn;
+    const Real *efb = ef + (idx_t)blk * 6 * g.sn;
+    const Real *e3_x1f = efb, *e2_x1f = efb + g.sn, *e1_x2f = efb + 2 * g.sn,
+               *e3_x2f = efb + 3 * g.sn, *e2_x3f = efb + 4 * g.sn, *e1_x3f = efb + 5 * g.sn;
+    const Real *w_x1f = wct + (idx_t)blk * 3 * g.sn, *w_x2f = w_x1f + g.sn,
+               *w_x3f = w_x1f + 2 * g.sn;
+    Real *eb = e + (idx_t)blk * 3 * g.sn;
+    {
+      const Real cc00 = cce(wb, bc, c, 0), cc0m = cce(wb, bc, c - sj, 0),
+                 ccm0 = cce(wb, bc, c - sk, 0), ccmm = cce(wb, bc, c - sk - sj, 0);
+      Real de1_l3 = (1.0 - w_x2f[c - sk]) * (e1_x3f[c] - ccm0) +
+                    (w_x2f[c - sk]) * (e1_x3f[c - sj] - ccmm);
+      Real de1_r3 = (1.0 - w_x2f[c]) * (e1_x3f[c] - cc00) + (w_x2f[c]) * (e1_x3f[c - sj] - cc0m);
+      Real de1_l2 = (1.0 - w_x3f[c - sj]) * (e1_x2f[c] - cc0m) +
+                    (w_x3f[c - sj]) * (e1_x2f[c - sk] - ccmm);
+      Real de1_r2 = (1.0 - w_x3f[c]) * (e1_x2f[c] - cc00) + (w_x3f[c]) * (e1_x2f[c - sk] - ccm0);
+      eb[c] = 0.25 * (de1_l3 + de1_r3 + de1_l2 + de1_r2 + e1_x2f[c - sk] + e1_x2f[c] +
+                      e1_x3f[c - sj] + e1_x3f[c]);
+    }
+    {
+      const Real cc00 = cce(wb, bc, c, 1), cc0m = cce(wb, bc, c - si, 1),
+                 ccm0 = cce(wb, bc, c - sk, 1), ccmm = cce(wb, bc, c - sk - si, 1);
+      Real de2_l3 = (1.0 - w_x1f[c - sk]) * (e2_x3f[c] - ccm0) +
+                    (w_x1f[c - sk]) * (e2_x3f[c - si] - ccmm);
+      Real de2_r3 = (1.0 - w_x1f[c]) * (e2_x3f[c] - cc00) + (w_x1f[c]) * (e2_x3f[c - si] - cc0m);
+      Real de2_l1 = (1.0 - w_x3f[c - si]) * (e2_x1f[c] - cc0m) +
+                    (w_x3f[c - si]) * (e2_x1f[c - sk] - ccmm);
+      Real de2_r1 = (1.0 - w_x3f[c]) * (e2_x1f[c] - cc00) + (w_x3f[c]) * (e2_x1f[c - sk] - ccm0);
+      eb[g.sn + c] = 0.25 * (de2_l3 + de2_r3 + de2_l1 + de2_r1 + e2_x3f[c - si] + e2_x3f[c] +
+                             e2_x1f[c - sk] + e2_x1f[c]);
+    }
+    {
+      const Real cc00 = cce(wb, bc, c, 2), cc0m = cce(wb, bc, c - si, 2),
+                 ccm0 = cce(wb, bc, c - sj, 2), ccmm = cce(wb, bc, c - sj - si, 2);
+      Real de3_l2 = (1.0 - w_x1f[c - sj]) * (e3_x2f[c] - ccm0) +
+                    (w_x1f[c - sj]) * (e3_x2f[c - si] - ccmm);
+      Real de3_r2 = (1.0 - w_x1f[c]) * (e3_x2f[c] - cc00) + (w_x1f[c]) * (e3_x2f[c - si] - cc0m);
+      Real de3_l1 = (1.0 - w_x2f[c - si]) * (e3_x1f[c] - cc0m) +
+                    (w_x2f[c - si]) * (e3_x1f[c - sj] - ccmm);
+      Real de3_r1 = (1.0 - w_x2f[c]) * (e3_x1f[c] - cc00) + (w_x2f[c]) * (e3_x1f[c - sj] - ccm0);
+      eb[2 * g.sn + c] = 0.25 * (de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[c - si] + e3_x2f[c] +
+                                 e3_x1f[c - sj] + e3_x1f[c]);
+    }
+  }
+};
+
+//========================================================================================
+// EMF correction, same-level neighbours (flux_correction_fc.cpp:51-300, 689-940, 1355-1541).
+// Per-block surface buffer: the six boundary planes of (e1,e2,e3).
+struct EmfSurf {
+  int nx1, nx2, nx3;
+  // section sizes
+  ATHK_HD idx_t n_x1_e2() const { return (idx_t)(nx3 + 1) * nx2; }
+  ATHK_HD idx_t n_x1_e3() const { return (idx_t)nx3 * (nx2 + 1); }
+  ATHK_HD idx_t n_x2_e1() const { return (idx_t)(nx3 + 1) * nx1; }
+  ATHK_HD idx_t n_x2_e3() const { return (idx_t)nx3 * (nx1 + 1); }
+  ATHK_HD idx_t n_x3_e1() const { return (idx_t)(nx2 + 1) * nx1; }
+  ATHK_HD idx_t n_x3_e2() const { return (idx_t)nx2 * (nx1 + 1); }
+  ATHK_HD idx_t n_x1() const { return n_x1_e2() + n_x1_e3(); }
+  ATHK_HD idx_t n_x2() const { return n_x2_e1() + n_x2_e3(); }
+  ATHK_HD idx_t n_x3() const { return n_x3_e1() + n_x3_e2(); }
+  ATHK_HD idx_t per_block() const { return 2 * (n_x1() + n_x2() + n_x3()); }
+  // offsets of a face section: dir 0..2, side 0 (inner) / 1 (outer)
+  ATHK_HD idx_t face_off(int dir, int side) const {
+    idx_t o = 0;
+    if (dir >= 1) o += 2 * n_x1();
+    if (dir >= 2) o += 2 * n_x2();
+    const idx_t n = (dir == 0) ? n_x1() : (dir == 1 ? n_x2() : n_x3());
+    return o + side * n;
+  }
+  // element offsets inside a face section (kk,jj,ii are zero-based from ks,js,is)
+  ATHK_HD idx_t x1_e2(int kk, int jj) const { return (idx_t)kk * nx2 + jj; }
+  ATHK_HD idx_t x1_e3(int kk, int jj) const { return n_x1_e2() + (idx_t)kk * (nx2 + 1) + jj; }
+  ATHK_HD idx_t x2_e1(int kk, int ii) const { return (idx_t)kk * nx1 + ii; }
+  ATHK_HD idx_t x2_e3(int kk, int ii) const { return n_x2_e1() + (idx_t)kk * (nx1 + 1) + ii; }
+  ATHK_HD idx_t x3_e1(int jj, int ii) const { return (idx_t)jj * nx1 + ii; }
+  ATHK_HD idx_t x3_e2(int jj, int ii) const { return n_x3_e1() + (idx_t)jj * (nx1 + 1) + ii; }
+};
+
+// LoadFluxBoundaryBufferSameLevel for all six faces of a block at once
+struct EmfPackPoint {
+  Grid g;
+  EmfSurf sf;
+  const Real *e;   // [nb][3][sn]
+  Real *buf;       // [nb][per_block]
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real *eb = e + (idx_t)blk * 3 * g.sn;
+    Real *bb = buf + (idx_t)blk * sf.per_block();
+    const int kk = k - g.ks, jj = j - g.js, ii = i - g.is;
+    const bool i_ok = (i <= g.ie), j_ok = (j <= g.je), k_ok = (k <= g.ke);
+    if (i == g.is || i == g.ie + 1) {
+      Real *s = bb + sf.face_off(0, i == g.is ? 0 : 1);
+      if (j_ok) s[sf.x1_e2(kk, jj)] = eb[g.sn + c];
+      if (k_ok) s[sf.x1_e3(kk, jj)] = eb[2 * g.sn + c];
+    }
+    if (j == g.js || j == g.je + 1) {
+      Real *s = bb + sf.face_off(1, j == g.js ? 0 : 1);
+      if (i_ok) s[sf.x2_e1(kk, ii)] = eb[c];
+      if (k_ok) s[sf.x2_e3(kk, ii)] = eb[2 * g.sn + c];
+    }
+    if (k == g.ks || k == g.ke + 1) {
+      Real *s = bb + sf.face_off(2, k == g.ks ? 0 : 1);
+      if (i_ok) s[sf.x3_e1(jj, ii)] = eb[c];
+      if (j_ok) s[sf.x3_e2(jj, ii)] = eb[g.sn + c];
+    }
+  }
+};
+
+// SetFluxBoundarySameLevel (+=) followed by AverageFluxBoundary, per boundary edge point.
+// Accumulation order = neighbour enumeration order of bvals_base.cpp:326-372: faces (x1,x2,x3),
+// then edges.  Remote neighbours (<= -2) read from rbuf, a buffer with the same section layout
+// filled by the inter-GPU transport.
+struct EmfApplyPoint {
+  Grid g;
+  EmfSurf sf;
+  Real *e;
+  const Real *buf;       // local blocks' packed surfaces
+  const int *nbr;        // [nb][27]
+  const Real *rbuf;      // remote surfaces [nremote][per_block] (may be null)
+  ATHK_HD const Real *surf_of(int id) const {
+    if (id >= 0) return buf + (idx_t)id * sf.per_block();
+    return rbuf + (idx_t)(-id - 2) * sf.per_block();
+  }
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const int a = (i == g.is) ? -1 : (i == g.ie + 1 ? 1 : 0);
+    const int bq = (j == g.js) ? -1 : (j == g.je + 1 ? 1 : 0);
+    const int cq = (k == g.ks) ? -1 : (k == g.ke + 1 ? 1 : 0);
+    if (a == 0 && bq == 0 && cq == 0) return;
+    const idx_t c = gidx(g, k, j, i);
+    Real *eb = e + (idx_t)blk * 3 * g.sn;
+    const int *nb = nbr + blk * 27;
+    const int kk = k - g.ks, jj = j - g.js, ii = i - g.is;
+    // ---- e1(k,j,i): i in [is,ie]; boundaries in x2 (bq) and x3 (cq)
+    if (i <= g.ie && (bq != 0 || cq != 0)) {
+      Real v = eb[c];
+      int cnt = 1;
+      if (bq != 0) {
+        const int id = nb[nbr_slot(0, bq, 0)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e1(kk, ii)]; ++cnt; }
+      }
+      if (cq != 0) {
+        const int id = nb[nbr_slot(0, 0, cq)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e1(jj, ii)]; ++cnt; }
+      }
+      if (bq != 0 && cq != 0) {
+        const int id = nb[nbr_slot(0, bq, cq)];
+        if (id != -1) {
+          v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e1(kk - cq * g.nx3, ii)];
+          ++cnt;
+        }
+        if (cnt > 1) v *= (1.0 / (Real)cnt);
+      } else if (cnt > 1) {
+        v *= 0.5;
+      }
+      eb[c] = v;
+    }
+    // ---- e2(k,j,i): j in [js,je]; boundaries in x1 (a) and x3 (cq)
+    if (j <= g.je && (a != 0 || cq != 0)) {
+      Real v = eb[g.sn + c];
+      int cnt = 1;
+      if (a != 0) {
+        const int id = nb[nbr_slot(a, 0, 0)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e2(kk, jj)]; ++cnt; }
+      }
+      if (cq != 0) {
+        const int id = nb[nbr_slot(0, 0, cq)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e2(jj, ii)]; ++cnt; }
+      }
+      if (a != 0 && cq != 0) {
+        const int id = nb[nbr_slot(a, 0, cq)];
+        if (id != -1) {
+          v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e2(kk - cq * g.nx3, jj)];
+          ++cnt;
+        }
+        if (cnt > 1) v *= (1.0 / (Real)cnt);
+      } else if (cnt > 1) {
+        v *= 0.5;
+      }
+      eb[g.sn + c] = v;
+    }
+    // ---- e3(k,j,i): k in [ks,ke]; boundaries in x1 (a) and x2 (bq)
+    if (k <= g.ke && (a != 0 || bq != 0)) {
+      Real v = eb[2 * g.sn + c];
+      int cnt = 1;
+      if (a != 0) {
+        const int id = nb[nbr_slot(a, 0, 0)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e3(kk, jj)]; ++cnt; }
+      }
+      if (bq != 0) {
+        const int id = nb[nbr_slot(0, bq, 0)];
+        if (id != -1) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e3(kk, ii)]; ++cnt; }
+      }
+      if (a != 0 && bq != 0) {
+        const int id = nb[nbr_slot(a, bq, 0)];
+        if (id != -1) {
+          v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e3(kk, jj - bq * g.nx2)];
+          ++cnt;
+        }
+        if (cnt > 1) v *= (1.0 / (Real)cnt);
+      } else if (cnt > 1) {
+        v *= 0.5;
+      }
+      eb[2 * g.sn + c] = v;
+    }
+  }
+};
+
+//========================================================================================
+// MeshBlock::WeightedAve (mesh/weighted_ave.cpp:35-230 and :366-520), 2-input form used by
+// vl2/rk2/rk3 (wght[3]=wght[4]=0).  The branch on zero weights is resolved on the host; MODE:
+//   0: out += w1*in1 + w2*in2     1: out += w1*in1
+//   2: out  = w1*in1 + w2*in2     3: out  = w1*in1
+//   4: out  = w0*out + w1*in1 + w2*in2    5: out = w0*out + w1*in1    6: out *= w0
+struct WeightedAvePoint {
+  Grid g;
+  int nvar;     // components handled per point
+  int fc;       // 1: face-centred extents (x1f to ie+1, x2f to je+1, x3f to ke+1)
+  int mode;
+  Real w0, w1, w2;
+  Real *out;
+  const Real *in1, *in2;
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    for (int n = 0; n < nvar; ++n) {
+      if (fc) {
+        const bool ok = (n == 0) ? (j <= g.je && k <= g.ke)
+                                 : (n == 1 ? (i <= g.ie && k <= g.ke) : (i <= g.ie && j <= g.je));
+        if (!ok) continue;
+      }
+      const idx_t o = ((idx_t)blk * nvar + n) * g.sn + c;
+      Real r;
+      switch (mode) {
+        case 0: r = out[o]; r += w1 * in1[o] + w2 * in2[o]; break;
+        case 1: r = out[o]; r += w1 * in1[o]; break;
+        case 2: r = w1 * in1[o] + w2 * in2[o]; break;
+        case 3: r = w1 * in1[o]; break;
+        case 4: r = w0 * out[o] + w1 * in1[o] + w2 * in2[o]; break;
+        case 5: r = w0 * out[o] + w1 * in1[o]; break;
+        default: r = out[o]; r *= w0; break;
+      }
+      out[o] = r;
+    }
+  }
+};
+
+//========================================================================================
+// Hydro::AddFluxDivergence (add_flux_divergence.cpp:39-96), Cartesian areas/volume
+// (coordinates.cpp:448-545): A1 = dx2f*dx3f, A2 = dx1f*dx3f, A3 = dx1f*dx2f, V = dx1f*dx2f*dx3f
+struct FluxDivPoint {
+  Grid g;
+  Geom geo;
+  int nvar;
+  Real wght;
+  const Real *f1, *f2, *f3;   // [nb][nvar][sn]
+  Real *u;                    // [nb][nvar][sn]
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real dx1 = geo.dxf[0][blk * geo.PG + i], dx2 = geo.dxf[1][blk * geo.PG + j],
+               dx3 = geo.dxf[2][blk * geo.PG + k];
+    const Real a1 = dx2 * dx3, a2 = dx1 * dx3, a3 = dx1 * dx2;
+    const Real vol = dx1 * dx2 * dx3;
+    for (int n = 0; n < nvar; ++n) {
+      const idx_t o = ((idx_t)blk * nvar + n) * g.sn + c;
+      Real dflx = (a1 * f1[o + 1] - a1 * f1[o]);
+      dflx += (a2 * f2[o + g.sj] - a2 * f2[o]);
+      dflx += (a3 * f3[o + g.sk] - a3 * f3[o]);
+      u[o] -= wght * dflx / vol;
+    }
+  }
+};
+
+//========================================================================================
+// Field::CT (field/ct.cpp:31-116): launched over k in [ks,ke+1], j in [js,je+1], i in [is,ie+1]
+struct CTPoint {
+  Grid g;
+  Geom geo;
+  Real wght;
+  const Real *e;   // [nb][3][sn]
+  Real *b;         // [nb][3][sn]
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real *e1 = e + (idx_t)blk * 3 * g.sn, *e2 = e1 + g.sn, *e3 = e1 + 2 * g.sn;
+    Real *bb = b + (idx_t)blk * 3 * g.sn;
+    const Real dx1 = geo.dxf[0][blk * geo.PG + i], dx2 = geo.dxf[1][blk * geo.PG + j],
+               dx3 = geo.dxf[2][blk * geo.PG + k];
+    if (k <= g.ke && j <= g.je) {   // B1 at x1-face i
+      const Real area = dx2 * dx3;
+      Real v = bb[c];
+      v -= (wght / area) * (dx3 * e3[c + g.sj] - dx3 * e3[c]);
+      v += (wght / area) * (dx2 * e2[c + g.sk] - dx2 * e2[c]);
+      bb[c] = v;
+    }
+    if (k <= g.ke && i <= g.ie) {   // B2 at x2-face j
+      const Real area = dx1 * dx3;
+      Real v = bb[g.sn + c];
+      v += (wght / area) * (dx3 * e3[c + 1] - dx3 * e3[c]);
+      v -= (wght / area) * (dx1 * e1[c + g.sk] - dx1 * e1[c]);
+      bb[g.sn + c] = v;
+    }
+    if (j <= g.je && i <= g.ie) {   // B3 at x3-face k
+      const Real area = dx1 * dx2;
+      Real v = bb[2 * g.sn + c];
+      v -= (wght / area) * (dx2 * e2[c + 1] - dx2 * e2[c]);
+      v += (wght / area) * (dx1 * e1[c + g.sj] - dx1 * e1[c]);
+      bb[2 * g.sn + c] = v;
+    }
+  }
+};
+
+//========================================================================================
+// Same-level ghost fill for neighbours on the same GPU: the ghost zone reads straight from
+// the neighbour block's active zone (what LoadBoundaryBufferSameLevel + CopyVariableBuffer
+// SameProcess + SetBoundarySameLevel move through a staging buffer; bvals_cc.cpp:287-302,
+// 386-420, bvals_var.cpp:108-119).  Launched over the full box k in [0,nc3-1] etc.
+struct GhostFillCC {
+  Grid g;
+  int nvar;
+  Real *u;          // [nb][nvar][sn]
+  const int *nbr;
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const int o1 = (i < g.is) ? -1 : (i > g.ie ? 1 : 0);
+    const int o2 = (j < g.js) ? -1 : (j > g.je ? 1 : 0);
+    const int o3 = (k < g.ks) ? -1 : (k > g.ke ? 1 : 0);
+    if (o1 == 0 && o2 == 0 && o3 == 0) return;
+    const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
+    if (id < 0) return;   // physical boundary or remote neighbour (unpacked separately)
+    const idx_t dst = gidx(g, k, j, i);
+    const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
+    for (int n = 0; n < nvar; ++n)
+      u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
+  }
+};
+
+// Face-centred version (bvals_fc.cpp:344-397 load, 583-680 set): along its own direction a
+// face array has nc+1 entries and the shared face [s] / [e+1] is NOT overwritten (:591-593).
+// Launched over k in [0,nc3], j in [0,nc2], i in [0,nc1].
+struct GhostFillFC {
+  Grid g;
+  Real *b;          // [nb][3][sn]
+  const int *nbr;
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      // validity of (k,j,i) for component d
+      if (i > g.nc1 - (d == 0 ? 0 : 1)) continue;
+      if (j > g.nc2 - (d == 1 ? 0 : 1)) continue;
+      if (k > g.nc3 - (d == 2 ? 0 : 1)) continue;
+      const int o1 = (i < g.is) ? -1 : (i > g.ie + (d == 0 ? 1 : 0) ? 1 : 0);
+      const int o2 = (j < g.js) ? -1 : (j > g.je + (d == 1 ? 1 : 0) ? 1 : 0);
+      const int o3 = (k < g.ks) ? -1 : (k > g.ke + (d == 2 ? 1 : 0) ? 1 : 0);
+      if (o1 == 0 && o2 == 0 && o3 == 0) continue;
+      const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
+      if (id < 0) continue;
+      const idx_t dst = gidx(g, k, j, i);
+      const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
+      b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
+    }
+  }
+};
+
+//========================================================================================
+// Hydro::NewBlockTimeStep, one cell (new_blockdt.cpp:72-124): returns min(dt1,dt2,dt3)
+template <bool MHD>
+struct CellDt {
+  Grid g;
+  EosParams eos;
+  Geom geo;
+  const Real *w, *bcc, *b;
+  ATHK_HD Real operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real *wb = w + (idx_t)blk * 5 * g.sn + c;
+    const Real d = wb[0], vx = wb[IVX * g.sn], vy = wb[IVY * g.sn], vz = wb[IVZ * g.sn],
+               p = wb[IPR * g.sn];
+    Real dt1 = geo.dxf[0][blk * geo.PG + i], dt2 = geo.dxf[1][blk * geo.PG + j],
+         dt3 = geo.dxf[2][blk * geo.PG + k];
+    if (MHD) {
+      const Real *bc = bcc + (idx_t)blk * 3 * g.sn + c;
+      const Real *bf = b + (idx_t)blk * 3 * g.sn + c;
+      const Real b1 = bc[0], b2 = bc[g.sn], b3 = bc[2 * g.sn];
+      Real bx = b1 + fabs(bf[0] - b1);
+      Real cf = fast_speed(eos, d, p, b2, b3, bx);
+      dt1 /= max_std(0.0, (fabs(vx) + cf));
+      bx = b2 + fabs(bf[g.sn] - b2);
+      cf = fast_speed(eos, d, p, b3, b1, bx);
+      dt2 /= max_std(0.0, (fabs(vy) + cf));
+      bx = b3 + fabs(bf[2 * g.sn] - b3);
+      cf = fast_speed(eos, d, p, b1, b2, bx);
+      dt3 /= max_std(0.0, (fabs(vz) + cf));
+    } else {
+      const Real cs = sound_speed(eos, d, p);
+      dt1 /= max_std(0.0, (fabs(vx) + cs));
+      dt2 /= max_std(0.0, (fabs(vy) + cs));
+      dt3 /= max_std(0.0, (fabs(vz) + cs));
+    }
+    return min_std(min_std(dt1, dt2), dt3);
+  }
+};
+
+}  // namespace athk
+#endif  // ATHK_OPS_H_

@@ -1,0 +1,440 @@
+// athk_physics.h -- point-wise FP64 physics of the hydro/MHD finite-volume update.
+//
+// Every function here is pure (registers in, registers out), marked __host__ __device__ so the
+// identical arithmetic can be exercised by the GPU kernels and by the pre-GPU index-logic harness
+// under tests/emul (test infrastructure, never a product path).
+//
+// PARITY CONTRACT: results must be bit-identical to the reference's double-precision CPU build
+// (g++ -O3, no fast-math, no FMA contraction).  Hence:
+//   * this translation unit is compiled with --fmad=false;
+//   * every expression keeps the reference's association order (C++ evaluates + - * / left to
+//     right; parentheses are reproduced where the reference groups terms);
+//   * min/max follow std::min/std::max tie semantics (return the first argument on ties).
+// Reference sources followed (file:line under /root/reference/src):
+//   eos/adiabatic_hydro.cpp:38-80, eos/adiabatic_mhd.cpp:41-90,149-156 (W(U), sound/fast speed)
+//   reconstruct/plm.cpp:104-112,149-154 (van Leer slope, uniform Cartesian branch)
+//   hydro/rsolvers/hydro/hllc.cpp:32-179, hydro/rsolvers/mhd/hlld.cpp:36-376
+//   hydro/hydro.cpp:154-158 (CT upwind weight)
+#ifndef ATHK_PHYSICS_H_
+#define ATHK_PHYSICS_H_
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ATHK_HD __host__ __device__ __forceinline__
+#else
+#define ATHK_HD inline
+#endif
+
+namespace athk {
+
+typedef double Real;
+
+// variable indices, as src/athena.hpp:169-192
+enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4 };
+enum { IVX = 1, IVY = 2, IVZ = 3, IPR = 4, IBY = 5, IBZ = 6 };
+enum { IB1 = 0, IB2 = 1, IB3 = 2 };
+
+#define ATHK_TINY_NUMBER 1.0e-20
+
+ATHK_HD Real sqr(Real x) { return x * x; }
+// std::min(a,b) == (b < a) ? b : a ; std::max(a,b) == (a < b) ? b : a
+ATHK_HD Real min_std(Real a, Real b) { return (b < a) ? b : a; }
+ATHK_HD Real max_std(Real a, Real b) { return (a < b) ? b : a; }
+
+struct EosParams {
+  Real gamma, gm1, igm1;   // igm1 = 1.0/(gamma-1.0)
+  Real dfloor, pfloor, sfloor;
+};
+
+ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
+  EosParams e;
+  e.gamma = gamma;
+  e.gm1 = gamma - 1.0;
+  e.igm1 = 1.0 / (gamma - 1.0);
+  e.dfloor = dfloor;
+  e.pfloor = pfloor;
+  e.sfloor = sfloor;
+  return e;
+}
+
+//----------------------------------------------------------------------------------------
+// EquationOfState::ConservedToPrimitive, one cell.  u[] is updated in place when a floor
+// fires (density floor / energy write-back), exactly as the reference does.
+// eos/adiabatic_hydro.cpp:58-72
+ATHK_HD void cons2prim_hydro(const EosParams &eos, Real u[5], Real w[5]) {
+  u[IDN] = (u[IDN] > eos.dfloor) ? u[IDN] : eos.dfloor;
+  w[IDN] = u[IDN];
+  Real di = 1.0 / u[IDN];
+  w[IVX] = u[IM1] * di;
+  w[IVY] = u[IM2] * di;
+  w[IVZ] = u[IM3] * di;
+  Real e_k = 0.5 * di * (sqr(u[IM1]) + sqr(u[IM2]) + sqr(u[IM3]));
+  Real p = eos.gm1 * (u[IEN] - e_k);
+  u[IEN] = (p > eos.pfloor) ? u[IEN] : ((eos.pfloor / eos.gm1) + e_k);
+  w[IPR] = (p > eos.pfloor) ? p : eos.pfloor;
+}
+
+// eos/adiabatic_mhd.cpp:63-84 (bcc already interpolated by the caller, field/field.cpp:112-180)
+ATHK_HD void cons2prim_mhd(const EosParams &eos, Real u[5], Real bc1, Real bc2, Real bc3,
+                           Real w[5]) {
+  u[IDN] = (u[IDN] > eos.dfloor) ? u[IDN] : eos.dfloor;
+  w[IDN] = u[IDN];
+  Real di = 1.0 / u[IDN];
+  w[IVX] = u[IM1] * di;
+  w[IVY] = u[IM2] * di;
+  w[IVZ] = u[IM3] * di;
+  Real pb = 0.5 * (sqr(bc1) + sqr(bc2) + sqr(bc3));
+  Real e_k = 0.5 * di * (sqr(u[IM1]) + sqr(u[IM2]) + sqr(u[IM3]));
+  Real p = eos.gm1 * (u[IEN] - e_k - pb);
+  u[IEN] = (p > eos.pfloor) ? u[IEN] : ((eos.pfloor / eos.gm1) + e_k + pb);
+  w[IPR] = (p > eos.pfloor) ? p : eos.pfloor;
+}
+
+// eos/adiabatic_hydro.cpp SoundSpeed ; eos/adiabatic_mhd.cpp:149-156 FastMagnetosonicSpeed
+ATHK_HD Real sound_speed(const EosParams &eos, Real d, Real p) { return sqrt(eos.gamma * p / d); }
+
+ATHK_HD Real fast_speed(const EosParams &eos, Real d, Real p, Real by, Real bz, Real bx) {
+  Real asq = eos.gamma * p;
+  Real vaxsq = bx * bx;
+  Real ct2 = (by * by + bz * bz);
+  Real qsq = vaxsq + ct2 + asq;
+  Real tmp = vaxsq + ct2 - asq;
+  return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
+}
+
+//----------------------------------------------------------------------------------------
+// PLM, uniform-Cartesian van Leer limiter (reconstruct/plm.cpp:104-112): limited slope of one
+// variable from its left/right one-sided differences.
+ATHK_HD Real vl_slope(Real dwl, Real dwr) {
+  Real dw2 = dwl * dwr;
+  Real dwm = 2.0 * dw2 / (dwl + dwr);
+  if (dw2 <= 0.0) dwm = 0.0;
+  return dwm;
+}
+
+//----------------------------------------------------------------------------------------
+// Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
+ATHK_HD Real ct_weight(Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
+  Real v_over_c = (1024.0) * dt * dflx / (dx * (rhol + rhor));
+  Real tmp_min = min_std(0.5, v_over_c);
+  return 0.5 + max_std(-0.5, tmp_min);
+}
+
+//----------------------------------------------------------------------------------------
+// HLLC (hydro/rsolvers/hydro/hllc.cpp:53-175).  wl/wr = (d, vx, vy, vz, p) with vx the
+// sweep-normal velocity; f = (mass, mom-x, mom-y, mom-z, energy) in the same rotated frame.
+ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real gamma = eos.gamma;
+  const Real igm1 = 1.0 / eos.gm1;
+
+  Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
+  Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+  Real el = wl[IPR] * igm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
+  Real er = wr[IPR] * igm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
+  Real rhoa = .5 * (wl[IDN] + wr[IDN]);
+  Real ca = .5 * (cl + cr);
+  Real pmid = .5 * (wl[IPR] + wr[IPR] + (wl[IVX] - wr[IVX]) * rhoa * ca);
+  // umid, rhol, rhor are computed by the reference but never reach the flux (PVRS leftovers)
+
+  Real ql = (pmid <= wl[IPR]) ? 1.0
+            : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wl[IPR] - 1.0));
+  Real qr = (pmid <= wr[IPR]) ? 1.0
+            : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wr[IPR] - 1.0));
+
+  Real al = wl[IVX] - cl * ql;
+  Real ar = wr[IVX] + cr * qr;
+
+  Real bp = ar > 0.0 ? ar : (ATHK_TINY_NUMBER);
+  Real bm = al < 0.0 ? al : -(ATHK_TINY_NUMBER);
+
+  Real vxl = wl[IVX] - al;
+  Real vxr = wr[IVX] - ar;
+
+  Real tl = wl[IPR] + vxl * wl[IDN] * wl[IVX];
+  Real tr = wr[IPR] + vxr * wr[IDN] * wr[IVX];
+
+  Real ml = wl[IDN] * vxl;
+  Real mr = -(wr[IDN] * vxr);
+
+  Real am = (tl - tr) / (ml + mr);
+  Real cp = (ml * tr + mr * tl) / (ml + mr);
+  cp = cp > 0.0 ? cp : 0.0;
+
+  vxl = wl[IVX] - bm;
+  vxr = wr[IVX] - bp;
+
+  Real fl[5], fr[5];
+  fl[IDN] = wl[IDN] * vxl;
+  fr[IDN] = wr[IDN] * vxr;
+  fl[IVX] = wl[IDN] * wl[IVX] * vxl + wl[IPR];
+  fr[IVX] = wr[IDN] * wr[IVX] * vxr + wr[IPR];
+  fl[IVY] = wl[IDN] * wl[IVY] * vxl;
+  fr[IVY] = wr[IDN] * wr[IVY] * vxr;
+  fl[IVZ] = wl[IDN] * wl[IVZ] * vxl;
+  fr[IVZ] = wr[IDN] * wr[IVZ] * vxr;
+  fl[IEN] = el * vxl + wl[IPR] * wl[IVX];
+  fr[IEN] = er * vxr + wr[IPR] * wr[IVX];
+
+  Real sl, sr, sm;
+  if (am >= 0.0) {
+    sl = am / (am - bm);
+    sr = 0.0;
+    sm = -bm / (am - bm);
+  } else {
+    sl = 0.0;
+    sr = -am / (bp - am);
+    sm = bp / (bp - am);
+  }
+
+  f[IDN] = sl * fl[IDN] + sr * fr[IDN];
+  f[IVX] = sl * fl[IVX] + sr * fr[IVX] + sm * cp;
+  f[IVY] = sl * fl[IVY] + sr * fr[IVY];
+  f[IVZ] = sl * fl[IVZ] + sr * fr[IVZ];
+  f[IEN] = sl * fl[IEN] + sr * fr[IEN] + sm * cp * am;
+}
+
+//----------------------------------------------------------------------------------------
+// HLLD (hydro/rsolvers/mhd/hlld.cpp:56-365).  wl/wr = (d, vx, vy, vz, p, by, bz) in the sweep
+// frame, bxi = normal face field.  f = (mass, mx, my, mz, E, by-flux, bz-flux).
+struct Cons7 {
+  Real d, mx, my, mz, e, by, bz;
+};
+
+ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                       Real f[7]) {
+  const Real SMALL_NUMBER = 1.0e-4;
+  const Real igm1 = eos.igm1;
+  Real spd[5];
+  Cons7 ul, ur, ulst, uldst, urdst, urst, fl, fr;
+
+  Real bxsq = bxi * bxi;
+  Real pbl = 0.5 * (bxsq + (sqr(wl[IBY]) + sqr(wl[IBZ])));
+  Real pbr = 0.5 * (bxsq + (sqr(wr[IBY]) + sqr(wr[IBZ])));
+  Real kel = 0.5 * wl[IDN] * (sqr(wl[IVX]) + (sqr(wl[IVY]) + sqr(wl[IVZ])));
+  Real ker = 0.5 * wr[IDN] * (sqr(wr[IVX]) + (sqr(wr[IVY]) + sqr(wr[IVZ])));
+
+  ul.d = wl[IDN];
+  ul.mx = wl[IVX] * ul.d;
+  ul.my = wl[IVY] * ul.d;
+  ul.mz = wl[IVZ] * ul.d;
+  ul.e = wl[IPR] * igm1 + kel + pbl;
+  ul.by = wl[IBY];
+  ul.bz = wl[IBZ];
+
+  ur.d = wr[IDN];
+  ur.mx = wr[IVX] * ur.d;
+  ur.my = wr[IVY] * ur.d;
+  ur.mz = wr[IVZ] * ur.d;
+  ur.e = wr[IPR] * igm1 + ker + pbr;
+  ur.by = wr[IBY];
+  ur.bz = wr[IBZ];
+
+  // outer wave speeds, Miyoshi & Kusano eq. 67
+  Real cfl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cfr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  spd[0] = min_std(wl[IVX] - cfl, wr[IVX] - cfr);
+  spd[4] = max_std(wl[IVX] + cfl, wr[IVX] + cfr);
+
+  Real ptl = wl[IPR] + pbl;
+  Real ptr = wr[IPR] + pbr;
+
+  fl.d = ul.mx;
+  fl.mx = ul.mx * wl[IVX] + ptl - bxsq;
+  fl.my = ul.my * wl[IVX] - bxi * ul.by;
+  fl.mz = ul.mz * wl[IVX] - bxi * ul.bz;
+  fl.e = wl[IVX] * (ul.e + ptl - bxsq) - bxi * (wl[IVY] * ul.by + wl[IVZ] * ul.bz);
+  fl.by = ul.by * wl[IVX] - bxi * wl[IVY];
+  fl.bz = ul.bz * wl[IVX] - bxi * wl[IVZ];
+
+  fr.d = ur.mx;
+  fr.mx = ur.mx * wr[IVX] + ptr - bxsq;
+  fr.my = ur.my * wr[IVX] - bxi * ur.by;
+  fr.mz = ur.mz * wr[IVX] - bxi * ur.bz;
+  fr.e = wr[IVX] * (ur.e + ptr - bxsq) - bxi * (wr[IVY] * ur.by + wr[IVZ] * ur.bz);
+  fr.by = ur.by * wr[IVX] - bxi * wr[IVY];
+  fr.bz = ur.bz * wr[IVX] - bxi * wr[IVZ];
+
+  Real sdl = spd[0] - wl[IVX];
+  Real sdr = spd[4] - wr[IVX];
+
+  // S_M, eq. 38
+  spd[2] = (sdr * ur.mx - sdl * ul.mx + (ptl - ptr)) / (sdr * ur.d - sdl * ul.d);
+
+  Real sdml = spd[0] - spd[2];
+  Real sdmr = spd[4] - spd[2];
+  Real sdml_inv = 1.0 / sdml;
+  Real sdmr_inv = 1.0 / sdmr;
+  // eq. 43
+  ulst.d = ul.d * sdl * sdml_inv;
+  urst.d = ur.d * sdr * sdmr_inv;
+  Real ulst_d_inv = 1.0 / ulst.d;
+  Real urst_d_inv = 1.0 / urst.d;
+  Real sqrtdl = sqrt(ulst.d);
+  Real sqrtdr = sqrt(urst.d);
+
+  // eq. 51
+  spd[1] = spd[2] - fabs(bxi) / sqrtdl;
+  spd[3] = spd[2] + fabs(bxi) / sqrtdr;
+
+  // eq. 41
+  Real ptstl = ptl + ul.d * sdl * (spd[2] - wl[IVX]);
+  Real ptstr = ptr + ur.d * sdr * (spd[2] - wr[IVX]);
+  Real ptst = 0.5 * (ptstr + ptstl);
+
+  // left star state, eqs. 39, 44-47
+  ulst.mx = ulst.d * spd[2];
+  if (fabs(ul.d * sdl * sdml - bxsq) < (SMALL_NUMBER)*ptst) {
+    ulst.my = ulst.d * wl[IVY];
+    ulst.mz = ulst.d * wl[IVZ];
+    ulst.by = ul.by;
+    ulst.bz = ul.bz;
+  } else {
+    Real tmp = bxi * (sdl - sdml) / (ul.d * sdl * sdml - bxsq);
+    ulst.my = ulst.d * (wl[IVY] - ul.by * tmp);
+    ulst.mz = ulst.d * (wl[IVZ] - ul.bz * tmp);
+    tmp = (ul.d * sqr(sdl) - bxsq) / (ul.d * sdl * sdml - bxsq);
+    ulst.by = ul.by * tmp;
+    ulst.bz = ul.bz * tmp;
+  }
+  Real vbstl = (ulst.mx * bxi + (ulst.my * ulst.by + ulst.mz * ulst.bz)) * ulst_d_inv;
+  // eq. 48
+  ulst.e = (sdl * ul.e - ptl * wl[IVX] + ptst * spd[2] +
+            bxi * (wl[IVX] * bxi + (wl[IVY] * ul.by + wl[IVZ] * ul.bz) - vbstl)) * sdml_inv;
+
+  // right star state
+  urst.mx = urst.d * spd[2];
+  if (fabs(ur.d * sdr * sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+    urst.my = urst.d * wr[IVY];
+    urst.mz = urst.d * wr[IVZ];
+    urst.by = ur.by;
+    urst.bz = ur.bz;
+  } else {
+    Real tmp = bxi * (sdr - sdmr) / (ur.d * sdr * sdmr - bxsq);
+    urst.my = urst.d * (wr[IVY] - ur.by * tmp);
+    urst.mz = urst.d * (wr[IVZ] - ur.bz * tmp);
+    tmp = (ur.d * sqr(sdr) - bxsq) / (ur.d * sdr * sdmr - bxsq);
+    urst.by = ur.by * tmp;
+    urst.bz = ur.bz * tmp;
+  }
+  Real vbstr = (urst.mx * bxi + (urst.my * urst.by + urst.mz * urst.bz)) * urst_d_inv;
+  urst.e = (sdr * ur.e - ptr * wr[IVX] + ptst * spd[2] +
+            bxi * (wr[IVX] * bxi + (wr[IVY] * ur.by + wr[IVZ] * ur.bz) - vbstr)) * sdmr_inv;
+
+  // double-star states, eqs. 59-63
+  Real invsumd = 1.0 / (sqrtdl + sqrtdr);
+  Real bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+
+  uldst.d = ulst.d;
+  urdst.d = urst.d;
+  uldst.mx = ulst.mx;
+  urdst.mx = urst.mx;
+
+  Real tmp = invsumd * (sqrtdl * (ulst.my * ulst_d_inv) + sqrtdr * (urst.my * urst_d_inv) +
+                        bxsig * (urst.by - ulst.by));
+  uldst.my = uldst.d * tmp;
+  urdst.my = urdst.d * tmp;
+
+  tmp = invsumd * (sqrtdl * (ulst.mz * ulst_d_inv) + sqrtdr * (urst.mz * urst_d_inv) +
+                   bxsig * (urst.bz - ulst.bz));
+  uldst.mz = uldst.d * tmp;
+  urdst.mz = urdst.d * tmp;
+
+  tmp = invsumd * (sqrtdl * urst.by + sqrtdr * ulst.by +
+                   bxsig * sqrtdl * sqrtdr * ((urst.my * urst_d_inv) - (ulst.my * ulst_d_inv)));
+  uldst.by = urdst.by = tmp;
+
+  tmp = invsumd * (sqrtdl * urst.bz + sqrtdr * ulst.bz +
+                   bxsig * sqrtdl * sqrtdr * ((urst.mz * urst_d_inv) - (ulst.mz * ulst_d_inv)));
+  uldst.bz = urdst.bz = tmp;
+
+  tmp = spd[2] * bxi + (uldst.my * uldst.by + uldst.mz * uldst.bz) / uldst.d;
+  uldst.e = ulst.e - sqrtdl * bxsig * (vbstl - tmp);
+  urdst.e = urst.e + sqrtdr * bxsig * (vbstr - tmp);
+
+  // jump terms S*(U_a - U_b); the reference overwrites the state structs the same way
+  uldst.d = spd[1] * (uldst.d - ulst.d);
+  uldst.mx = spd[1] * (uldst.mx - ulst.mx);
+  uldst.my = spd[1] * (uldst.my - ulst.my);
+  uldst.mz = spd[1] * (uldst.mz - ulst.mz);
+  uldst.e = spd[1] * (uldst.e - ulst.e);
+  uldst.by = spd[1] * (uldst.by - ulst.by);
+  uldst.bz = spd[1] * (uldst.bz - ulst.bz);
+
+  ulst.d = spd[0] * (ulst.d - ul.d);
+  ulst.mx = spd[0] * (ulst.mx - ul.mx);
+  ulst.my = spd[0] * (ulst.my - ul.my);
+  ulst.mz = spd[0] * (ulst.mz - ul.mz);
+  ulst.e = spd[0] * (ulst.e - ul.e);
+  ulst.by = spd[0] * (ulst.by - ul.by);
+  ulst.bz = spd[0] * (ulst.bz - ul.bz);
+
+  urdst.d = spd[3] * (urdst.d - urst.d);
+  urdst.mx = spd[3] * (urdst.mx - urst.mx);
+  urdst.my = spd[3] * (urdst.my - urst.my);
+  urdst.mz = spd[3] * (urdst.mz - urst.mz);
+  urdst.e = spd[3] * (urdst.e - urst.e);
+  urdst.by = spd[3] * (urdst.by - urst.by);
+  urdst.bz = spd[3] * (urdst.bz - urst.bz);
+
+  urst.d = spd[4] * (urst.d - ur.d);
+  urst.mx = spd[4] * (urst.mx - ur.mx);
+  urst.my = spd[4] * (urst.my - ur.my);
+  urst.mz = spd[4] * (urst.mz - ur.mz);
+  urst.e = spd[4] * (urst.e - ur.e);
+  urst.by = spd[4] * (urst.by - ur.by);
+  urst.bz = spd[4] * (urst.bz - ur.bz);
+
+  if (spd[0] >= 0.0) {
+    f[IDN] = fl.d;
+    f[IVX] = fl.mx;
+    f[IVY] = fl.my;
+    f[IVZ] = fl.mz;
+    f[IEN] = fl.e;
+    f[IBY] = fl.by;
+    f[IBZ] = fl.bz;
+  } else if (spd[4] <= 0.0) {
+    f[IDN] = fr.d;
+    f[IVX] = fr.mx;
+    f[IVY] = fr.my;
+    f[IVZ] = fr.mz;
+    f[IEN] = fr.e;
+    f[IBY] = fr.by;
+    f[IBZ] = fr.bz;
+  } else if (spd[1] >= 0.0) {
+    f[IDN] = fl.d + ulst.d;
+    f[IVX] = fl.mx + ulst.mx;
+    f[IVY] = fl.my + ulst.my;
+    f[IVZ] = fl.mz + ulst.mz;
+    f[IEN] = fl.e + ulst.e;
+    f[IBY] = fl.by + ulst.by;
+    f[IBZ] = fl.bz + ulst.bz;
+  } else if (spd[3] <= 0.0) {
+    f[IDN] = fr.d + urst.d;
+    f[IVX] = fr.mx + urst.mx;
+    f[IVY] = fr.my + urst.my;
+    f[IVZ] = fr.mz + urst.mz;
+    f[IEN] = fr.e + urst.e;
+    f[IBY] = fr.by + urst.by;
+    f[IBZ] = fr.bz + urst.bz;
+  } else if (spd[2] >= 0.0) {
+    f[IDN] = fl.d + ulst.d + uldst.d;
+    f[IVX] = fl.mx + ulst.mx + uldst.mx;
+    f[IVY] = fl.my + ulst.my + uldst.my;
+    f[IVZ] = fl.mz + ulst.mz + uldst.mz;
+    f[IEN] = fl.e + ulst.e + uldst.e;
+    f[IBY] = fl.by + ulst.by + uldst.by;
+    f[IBZ] = fl.bz + ulst.bz + uldst.bz;
+  } else {
+    f[IDN] = fr.d + urst.d + urdst.d;
+    f[IVX] = fr.mx + urst.mx + urdst.mx;
+    f[IVY] = fr.my + urst.my + urdst.my;
+    f[IVZ] = fr.mz + urst.mz + urdst.mz;
+    f[IEN] = fr.e + urst.e + urdst.e;
+    f[IBY] = fr.by + urst.by + urdst.by;
+    f[IBZ] = fr.bz + urst.bz + urdst.bz;
+  }
+}
+
+}  // namespace athk
+#endif  // ATHK_PHYSICS_H_

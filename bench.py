@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- zone-cycles/sec of the 3-D MHD VL2+PLM+HLLD+CT MeshBlock update on B200.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1 under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+
+Workload: BASELINE.json configs[2] weak-scaled -- MHD blast wave, 256^3 zones per GPU in 64^3
+MeshBlocks (64 blocks per GPU), periodic, gamma=5/3, cfl 0.3; a "step" is one full VL2 cycle
+(2 stages: donor-cell predictor + PLM corrector, HLLD, corner-E, EMF correction, CT, ghost
+exchange, W(U), new dt) over every MeshBlock.  Metric as the reference prints it
+(/root/reference/src/main.cpp:536,639-651): zone-cycles / second.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG_MHD_VL2 = 320.0   # algorithmic bytes per zone-cycle, SURVEY.md section 8(d)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev = dev
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True,
+                                   text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def weak_mesh(ngpu, per_gpu):
+    """256^3 per GPU: 1 -> 256^3, 2 -> 512x256x256, 4 -> 512x512x256, 8 -> 512^3."""
+    f = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[ngpu]
+    return tuple(per_gpu * x for x in f), f
+
+
+def zorder_partition(nbtotal, nranks):
+    """Contiguous Z-order ranges per rank (mesh/amr_loadbalance.cpp:73-131, equal costs)."""
+    base, rem = divmod(nbtotal, nranks)
+    out, s = [], 0
+    for r in range(nranks):
+        n = base + (1 if r >= nranks - rem else 0)   # remainder assigned from the end
+        out.append(list(range(s, s + n)))
+        s += n
+    return out
+
+
+def run_reference(args):
+    """Reference arm: the UNMODIFIED reference binary (oracle/_ref) on the host cores, a bounded
+    sample of the same workload (same physics/config; smaller mesh so it ends in minutes)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refrun
+    cfg = "blast_mhd_hlld"
+    cores = os.cpu_count() or 1
+    n = args.ref_mesh
+    blk = args.ref_block
+    nblocks = (n // blk) ** 3
+    threads = max(1, min(cores, nblocks))
+    blocks = blast_athinput(n, blk, nlim=1)
+    vals = []
+    t0 = time.time()
+    nrun = args.warmup + args.steps
+    # each "step" of the reference arm is a bounded sample: ref_cycles cycles of the n^3 mesh
+    for it in range(nrun):
+        blocks["time"]["nlim"] = args.ref_cycles
+        wd, out = refrun.run_reference(cfg, blocks, threads=threads)
+        zc = refrun.parse_zone_cycles(out)
+        subprocess.run(["rm", "-rf", wd])
+        if it >= args.warmup:
+            vals.append(zc["zone-cycles/omp_wsecond"])
+        if time.time() - t0 > 240 and vals:
+            break
+    v = sorted(vals)[len(vals) // 2]
+    sample = "%d^3 mesh, %d^3 MeshBlocks, %d cycles per step, %d OpenMP threads" % (
+        n, blk, args.ref_cycles, threads)
+    line = {"impl": "reference", "metric": "zone-cycles/sec (3D MHD VL2+PLM+HLLD+CT)", "value": v,
+            "unit": "zone-cycles/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+            "ms_per_step": 1e3 * (n ** 3) * args.ref_cycles / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "zone-cycles/s", "cores": threads,
+                             "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def blast_athinput(n, blk, nlim):
+    return {
+        "job": {"problem_id": "Blast"},
+        "output1": {"file_type": "hst", "dt": 1.0e30},
+        "time": {"cfl_number": 0.3, "nlim": nlim, "tlim": 1.0, "integrator": "vl2", "xorder": 2,
+                 "ncycle_out": 1000},
+        "mesh": {"nx1": n, "x1min": -1.0, "x1max": 1.0, "ix1_bc": "periodic", "ox1_bc": "periodic",
+                 "nx2": n, "x2min": -1.0, "x2max": 1.0, "ix2_bc": "periodic", "ox2_bc": "periodic",
+                 "nx3": n, "x3min": -1.0, "x3max": 1.0, "ix3_bc": "periodic", "ox3_bc": "periodic",
+                 "num_threads": 1},
+        "meshblock": {"nx1": blk, "nx2": blk, "nx3": blk},
+        "hydro": {"gamma": 1.666666666667, "iso_sound_speed": 0.4082482905},
+        "problem": {"pamb": 0.1, "prat": 100.0, "radius": 0.1, "damb": 1.0, "drat": 1.0,
+                    "ramp": 0.0, "b0": 1.0, "angle": 30},
+    }
+
+
+def workload_config(args):
+    return {"workload": "mhd_blast %d^3 zones per GPU, %d^3 MeshBlocks, VL2+PLM+HLLD+CT, periodic "
+                        "(BASELINE configs[2], weak-scaled)" % (args.per_gpu, args.block),
+            "zones_per_gpu": args.per_gpu ** 3, "meshblock": args.block, "integrator": "vl2",
+            "xorder": 2, "rsolver": "hlld", "nghost": 2, "gamma": 1.666666666667,
+            "cfl_number": 0.3, "l2_policy": "inputs larger than L2 (state >= 1 GB per GPU)",
+            "parallelism": "meshblock-z-order x%d" % args.gpus}
+
+
+def cpu_baseline_sample(args):
+    """Rank 0, N=1: the reference binary on the box's host cores for ~10-30 s of CPU work."""
+    from oracle import refrun
+    cfg = "blast_mhd_hlld"
+    if not refrun.have_ref(cfg):
+        return None
+    cores = os.cpu_count() or 1
+    n, blk = args.ref_mesh, args.ref_block
+    threads = max(1, min(cores, (n // blk) ** 3))
+    # aim for ~15 s: the reference does ~0.6e6 zone-cycles/s/core
+    cyc = max(2, min(40, int(15.0 * 0.6e6 * threads / n ** 3)))
+    blocks = blast_athinput(n, blk, nlim=cyc)
+    wd, out = refrun.run_reference(cfg, blocks, threads=threads)
+    subprocess.run(["rm", "-rf", wd])
+    zc = refrun.parse_zone_cycles(out)
+    return {"value": zc["zone-cycles/omp_wsecond"], "unit": "zone-cycles/s", "cores": threads,
+            "kind": "reference",
+            "sample": "%d^3 mesh, %d^3 MeshBlocks, %d cycles, %d OpenMP threads, g++ -O3" % (
+                n, blk, cyc, threads)}
+
+
+def run_ours(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from athena_b200 import capi, problems, pyhost
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = capi.load()
+    mesh_nx, _ = weak_mesh(world, args.per_gpu)
+    mesh = pyhost.UniformMesh(mesh_nx, (args.block,) * 3, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), ng=2)
+    parts = zorder_partition(mesh.nbtotal, world)
+    rank_of = {}
+    for r, gl in enumerate(parts):
+        for g in gl:
+            rank_of[g] = r
+    gids = parts[rank]
+    gamma = 1.666666666667
+    ctx = pyhost.Context(mesh, True, gamma, device=local_rank, gids=gids, rank_of=rank_of,
+                         my_rank=rank, lib=lib)
+    if world > 1:
+        from athena_b200 import multigpu
+        multigpu.attach(ctx, dist, rank, world)
+
+    # ---- synthetic ICs on the host (pinned), reference pgen formulas --------------------------
+    nb = len(gids)
+    shp = {k: ctx.shape(k) for k in ("U", "B_X1F", "B_X2F", "B_X3F")}
+    host = {k: torch.empty((nb,) + shp[k], dtype=torch.float64, pin_memory=True) for k in shp}
+    hnp = {k: v.numpy() for k, v in host.items()}
+    for lb, g in enumerate(gids):
+        ic = problems.blast_block(mesh, mesh.loc[g], True, gamma)
+        hnp["U"][lb] = ic["u"]
+        hnp["B_X1F"][lb] = ic["b1"]
+        hnp["B_X2F"][lb] = ic["b2"]
+        hnp["B_X3F"][lb] = ic["b3"]
+    state_bytes = sum(v.numel() * 8 for v in host.values())
+
+    dp = C.POINTER(C.c_double)
+
+    def h2d():
+        for k in hnp:
+            for lb in range(nb):
+                ctx.call("athk_upload", capi.ARRAYS[k], lb, hnp[k][lb].ctypes.data_as(dp))
+
+    def d2h():
+        for k in hnp:
+            for lb in range(nb):
+                ctx.call("athk_download_async", capi.ARRAYS[k], lb, hnp[k][lb].ctypes.data_as(dp))
+        ctx.sync()
+
+    h2d()
+    reduce_min = None
+    if world > 1:
+        def reduce_min(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item())
+    ti = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=not args.unfused)
+    ti.initialize(reduce_min=reduce_min)
+
+    stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
+    zones = args.per_gpu ** 3 * world
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    step = lambda: ti.step(reduce_min=reduce_min)   # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launches()
+    ms = timed(step, args.steps)
+    launches = ctx.launches() - l0
+    sampler.stop_flag = True
+    value = zones * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel breakdown (CUDA events around every operator call, 2 extra cycles) --------
+    breakdown = {}
+    if rank == 0:
+        orig_call = ctx.call
+        evs = []
+
+        def timed_call(name, *a):
+            if name in ("athk_sync", "athk_new_block_dt", "athk_swap_registers"):
+                return orig_call(name, *a)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            orig_call(name, *a)
+            e.record(stream)
+            evs.append((name, s, e))
+        ctx.call = timed_call
+    for _ in range(2):
+        step()
+    if rank == 0:
+        ctx.call = orig_call
+        ctx.sync()
+        torch.cuda.synchronize()
+        for name, s, e in evs:
+            breakdown[name] = breakdown.get(name, 0.0) + s.elapsed_time(e) / 2.0
+    barrier()
+
+    # ---- e2e: host buffers in, host buffers out, every step ---------------------------------
+    def e2e_step():
+        h2d()
+        # the state came from the host: redo the start-of-cycle exchange + W(U) the way
+        # Mesh::Initialize does after a restart, then one full cycle, then read everything back
+        ctx.call("athk_exchange_ghosts", 3, 0)
+        ctx.call("athk_cons2prim", 0)
+        ti.step(reduce_min=reduce_min)
+        d2h()
+    d2h()   # make the host copy the current state so that repeated e2e steps stay physical
+    e2e_step()
+    e2e_n = max(2, min(args.steps, 5))
+    ms_e2e = timed(e2e_step, e2e_n)
+    e2e_value = zones * e2e_n / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per_gpu_value = value / world
+        achieved = per_gpu_value * B_ALG_MHD_VL2 / 1e9
+        tot = sum(breakdown.values()) or 1.0
+        top = max(breakdown, key=breakdown.get) if breakdown else None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "whole VL2 cycle (all kernels of the step), %g algorithmic B/zone-cycle"
+                          % B_ALG_MHD_VL2,
+                "peak_source": peak_src,
+                "breakdown_ms_per_cycle": {k: round(v, 4) for k, v in sorted(
+                    breakdown.items(), key=lambda kv: -kv[1])},
+                "top_operator": top, "top_share": (breakdown[top] / tot) if top else None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_sample(args)
+            except Exception as ex:   # the bench line must still be printed
+                cpu = {"error": str(ex)[:200]}
+        line = {"metric": "zone-cycles/sec (3D MHD VL2+PLM+HLLD+CT)", "value": value,
+                "unit": "zone-cycles/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args), "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "zone-cycles/s",
+                        "h2d_bytes_per_step": state_bytes * world,
+                        "d2h_bytes_per_step": state_bytes * world + 8 * mesh.nbtotal,
+                        "what": "per step: pinned-host (u,b) of every MeshBlock -> device, ghost "
+                                "exchange + W(U), one VL2 cycle, (u,b) + block dt -> host"},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "final_dt": ti.dt, "cycles_run": ti.ncycle}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--per-gpu", type=int, default=256, help="zones per side per GPU")
+    ap.add_argument("--block", type=int, default=64, help="MeshBlock size")
+    ap.add_argument("--unfused", action="store_true", help="operator-per-kernel path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-mesh", type=int, default=128)
+    ap.add_argument("--ref-block", type=int, default=32)
+    ap.add_argument("--ref-cycles", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/* athk.h -- C ABI of the B200 (sm_100a) hydro/MHD MeshBlock-update library (libathk.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of Athena++ (v24.0): the per-MeshBlock
+ * finite-volume update.  Athena++ has no FFI/plugin layer; its physics operators are C++ member
+ * functions called from TimeIntegratorTaskList task bodies (src/task_list/time_integrator.cpp:
+ * 1606-2318).  Each entry point below replaces one such member function and cites it.  All
+ * signatures are plain C: pointers, sizes, scalars.  No torch/CUDA types appear.
+ *
+ * Execution model: one context == one GPU == the MeshBlocks of one rank.  An operator call acts
+ * on ALL local MeshBlocks in one launch (the reference loops blocks on the host); calls are
+ * enqueued on the context's stream and return immediately; only athk_sync, athk_download*,
+ * athk_new_block_dt and athk_history synchronise.  Every function returns 0 on success, a
+ * negative athk_status otherwise; athk_last_error() gives the message (the host side raises it
+ * the way ATHENA_ERROR does, src/defs.hpp.in:155-159).  There is no CPU fallback: without a
+ * CUDA device athk_create fails.
+ *
+ * Host array layout is AthenaArray's (src/athena_arrays.hpp:11-14): dense (n,k,j,i), i fastest,
+ * ghost zones included: cell arrays (nvar, nc3, nc2, nc1); faces x1f (nc3,nc2,nc1+1),
+ * x2f (nc3,nc2+1,nc1), x3f (nc3+1,nc2,nc1); edges x1e (nc3+1,nc2+1,nc1), x2e (nc3+1,nc2,nc1+1),
+ * x3e (nc3,nc2+1,nc1+1), with nc = nx + 2*nghost.
+ */
+#ifndef ATHK_H_
+#define ATHK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct athk_ctx athk_ctx;
+
+enum athk_status {
+  ATHK_OK = 0,
+  ATHK_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+  ATHK_ERR_CUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+  ATHK_ERR_NODEVICE = -3, /* no CUDA device: the library never falls back to the CPU */
+  ATHK_ERR_STATE = -4     /* call out of order (e.g. geometry not set) */
+};
+
+/* Riemann solvers: one is linked per build in the reference (Makefile.in:73) */
+enum athk_rsolver { ATHK_RS_HLLC = 0, ATHK_RS_HLLD = 1, ATHK_RS_ROE = 2, ATHK_RS_HLLE = 3, ATHK_RS_LLF = 4 };
+
+/* what the reference fixes at configure time (configure.py) plus <hydro> runtime parameters */
+typedef struct athk_config {
+  int nx1, nx2, nx3;   /* active zones per MeshBlock (<meshblock> nx1..3)          */
+  int nghost;          /* NGHOST                                                  */
+  int nblocks;         /* MeshBlocks owned by this context (this GPU)             */
+  int mhd;             /* MAGNETIC_FIELDS_ENABLED                                 */
+  int nscalars;        /* NSCALARS                                                */
+  int rsolver;         /* enum athk_rsolver                                       */
+  int device;          /* CUDA device ordinal                                     */
+  int reserved;
+  double gamma;        /* <hydro> gamma                                           */
+  double dfloor, pfloor, sfloor; /* floors; <=0 selects sqrt(1024*FLT_MIN) (eos.hpp:161) */
+} athk_config;
+
+/* device-resident arrays addressable through upload/download */
+enum athk_array {
+  ATHK_U = 0, ATHK_U1 = 1, ATHK_U2 = 2,   /* Hydro::u,u1,u2   (5, nc3,nc2,nc1)  hydro.hpp:43-51 */
+  ATHK_W = 3,                             /* Hydro::w                                            */
+  ATHK_BCC = 4,                           /* Field::bcc       (3, nc3,nc2,nc1)  field.hpp:38-51  */
+  ATHK_B_X1F = 5, ATHK_B_X2F = 6, ATHK_B_X3F = 7,       /* Field::b                               */
+  ATHK_B1_X1F = 8, ATHK_B1_X2F = 9, ATHK_B1_X3F = 10,   /* Field::b1                              */
+  ATHK_B2_X1F = 11, ATHK_B2_X2F = 12, ATHK_B2_X3F = 13, /* Field::b2                              */
+  ATHK_FLUX_X1 = 14, ATHK_FLUX_X2 = 15, ATHK_FLUX_X3 = 16, /* Hydro::flux[3] (5, face shape)      */
+  ATHK_E_X1E = 17, ATHK_E_X2E = 18, ATHK_E_X3E = 19,    /* Field::e (edge shapes)                 */
+  ATHK_E3_X1F = 20, ATHK_E2_X1F = 21, ATHK_E1_X2F = 22, /* face EMFs written by RiemannSolver     */
+  ATHK_E3_X2F = 23, ATHK_E2_X3F = 24, ATHK_E1_X3F = 25,
+  ATHK_WGHT_X1F = 26, ATHK_WGHT_X2F = 27, ATHK_WGHT_X3F = 28, /* Field::wght                      */
+  ATHK_S = 29, ATHK_S1 = 30, ATHK_S2 = 31, ATHK_R = 32, /* PassiveScalars::s,s1,s2,r              */
+  ATHK_SFLUX_X1 = 33, ATHK_SFLUX_X2 = 34, ATHK_SFLUX_X3 = 35,
+  ATHK_NARRAYS = 36
+};
+
+/* time-integrator registers (u,b,s move together only if the caller says so) */
+enum athk_reg { ATHK_REG0 = 0, ATHK_REG1 = 1, ATHK_REG2 = 2 };
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int athk_create(const athk_config *cfg, athk_ctx **out);
+void athk_destroy(athk_ctx *ctx);
+const char *athk_last_error(void);
+int athk_sync(athk_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+long long athk_launch_count(const athk_ctx *ctx);
+/* raw CUDA stream handle (cudaStream_t) so a host framework can order its own work after ours */
+void *athk_stream(athk_ctx *ctx);
+
+/* ---- geometry and topology -------------------------------------------------------------
+ * Coordinates::x1f/x1v/dx1f... of block lb, host-computed and used verbatim
+ * (src/coordinates/coordinates.cpp:100-324, cartesian.cpp:24-60).  xNf has ncN+1 entries,
+ * xNv and dxNf have ncN entries. */
+int athk_set_block_coords(athk_ctx *ctx, int lb,
+                          const double *x1f, const double *x1v, const double *dx1f,
+                          const double *x2f, const double *x2v, const double *dx2f,
+                          const double *x3f, const double *x3v, const double *dx3f);
+/* Same-level neighbour table, the result of BoundaryBase::SearchAndSetNeighbors
+ * (src/bvals/bvals_base.cpp:301).  nbr[lb*27 + (ox3+1)*9 + (ox2+1)*3 + (ox1+1)] is
+ *   >= 0   local block index on this context,
+ *   -1     no neighbour (physical boundary),
+ *   <= -2  remote neighbour: -(2 + remote slot), data arrives through athk_remote_* (multi-GPU). */
+int athk_set_neighbors(athk_ctx *ctx, const int *nbr);
+
+/* ---- data movement (Mesh::Initialize after pgen, outputs, restart) ---------------------- */
+int athk_upload(athk_ctx *ctx, int array, int lb, const double *host);
+int athk_download(athk_ctx *ctx, int array, int lb, double *host);
+/* as athk_download but stream-ordered: host (pinned) is valid only after athk_sync */
+int athk_download_async(athk_ctx *ctx, int array, int lb, double *host);
+/* raw device pointer + padded strides of an array (for zero-copy consumers; elements) */
+int athk_device_array(athk_ctx *ctx, int array, void **dptr, long long *stride_block,
+                      long long *stride_var, long long *stride_k, long long *stride_j);
+
+/* ---- operators (each acts on every local MeshBlock) ------------------------------------- */
+/* EquationOfState::ConservedToPrimitive (eos/adiabatic_hydro.cpp:38, adiabatic_mhd.cpp:41; MHD
+ * also Field::CalculateCellCenteredField field.cpp:112) from register `reg` into w/bcc, over the
+ * interior plus every ghost side that has a neighbour (time_integrator.cpp:2206-2212); floors
+ * are written back into the conserved register.  Scalars: eos_scalars.cpp:31. */
+int athk_cons2prim(athk_ctx *ctx, int reg);
+/* Hydro::CalculateFluxes(w,b,bcc,order) (hydro/calculate_fluxes.cpp:38): order 1 donor cell,
+ * 2 PLM, 3 PPM; writes flux[3] and, for MHD, face EMFs + CT weights.  dt_mesh is
+ * pmy_mesh->dt (the FULL step, hlld.cpp:52,373).  b is taken from register breg. */
+int athk_calculate_fluxes(athk_ctx *ctx, int order, double dt_mesh, int breg);
+/* PassiveScalars::CalculateFluxes (scalars/calculate_scalar_fluxes.cpp:41) */
+int athk_calculate_scalar_fluxes(athk_ctx *ctx, int order);
+/* Field::ComputeCornerE(w,bcc) (field/calculate_corner_e.cpp:28, 3-D branch 130-229) */
+int athk_compute_corner_e(athk_ctx *ctx);
+/* FaceCenteredBoundaryVariable::SendFluxCorrection / ReceiveFluxCorrection (+SetFluxBoundary
+ * SameLevel + AverageFluxBoundary), bvals/fc/flux_correction_fc.cpp:51,623,689,1355,1610 */
+int athk_send_flux_correction(athk_ctx *ctx);
+int athk_recv_flux_correction(athk_ctx *ctx);
+/* MeshBlock::WeightedAve (mesh/weighted_ave.cpp:35 cell-centred, :366 face-centred):
+ * out = w0*out + w1*in1 + w2*in2 (+w3,w4 unused by vl2/rk2/rk3) with the zero-weight branches */
+int athk_weighted_ave_cc(athk_ctx *ctx, int what /*0=hydro u,1=scalars s*/, int out_reg,
+                         int in1_reg, int in2_reg, const double wght[5]);
+int athk_weighted_ave_fc(athk_ctx *ctx, int out_reg, int in1_reg, int in2_reg,
+                         const double wght[5]);
+/* AthenaArray::SwapAthenaArray on the register pointers (athena_arrays.hpp:470) */
+int athk_swap_registers(athk_ctx *ctx, int what /*0=u,1=b,2=s*/, int reg_a, int reg_b);
+/* AthenaArray::ZeroClear on a register (time_integrator.cpp:1608-1619) */
+int athk_zero_register(athk_ctx *ctx, int what, int reg);
+/* Hydro::AddFluxDivergence(wght,u_out) (hydro/add_flux_divergence.cpp:39) */
+int athk_add_flux_divergence(athk_ctx *ctx, double wght, int reg);
+int athk_add_scalar_flux_divergence(athk_ctx *ctx, double wght, int reg);
+/* Field::CT(wght,b_out) (field/ct.cpp:31) */
+int athk_ct(athk_ctx *ctx, double wght, int reg);
+/* BoundaryVariable::SendBoundaryBuffers+ReceiveBoundaryBuffers+SetBoundaries for same-level
+ * neighbours (bvals/bvals_var.cpp:212-326, cc/bvals_cc.cpp:287-420, fc/bvals_fc.cpp:344-680);
+ * what: bit0 hydro u, bit1 field b, bit2 scalars s; taken from register reg. */
+int athk_exchange_ghosts(athk_ctx *ctx, int what_mask, int reg);
+/* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:45): per-block min dt * cfl, blocks 0..nblocks-1
+ * into dt_blocks (may be NULL), returns the min over local blocks in *dt_min. Synchronises. */
+int athk_new_block_dt(athk_ctx *ctx, double cfl_number, double *dt_blocks, double *dt_min);
+/* History sums (outputs/history.cpp:196-248): mass, 3 momenta, 3 KE, tot-E, [3 ME], [scalars];
+ * sums[] accumulates over local blocks (volume weighted). Synchronises. */
+int athk_history(athk_ctx *ctx, double *sums, int nsums);
+
+/* ---- fused stage (same results, fewer passes over HBM) ---------------------------------- */
+/* One full integrator stage for every local block, equivalent to the task sequence
+ * CALC_HYDFLX, CALC_FLDFLX, SEND/RECV_FLDFLX, INT_HYD, INT_FLD, SEND/RECV/SETB_HYD/FLD,
+ * CONS2PRIM (time_integrator.cpp:905-1206) with the weights of stage_wghts[stage-1]:
+ *   delta, gamma_1..3, beta (time_integrator.cpp:111-606).  order as athk_calculate_fluxes. */
+typedef struct athk_stage_wghts {
+  double delta, gamma_1, gamma_2, gamma_3, beta;
+} athk_stage_wghts;
+int athk_stage(athk_ctx *ctx, int stage, int order, const athk_stage_wghts *sw, double dt_mesh);
+
+/* ---- multi-GPU surface exchange (buffers packed per remote neighbour slot) ---------------- */
+/* Sizes (doubles) of one remote ghost message for the given quantity mask and offsets, and of
+ * one remote EMF message; pack into / unpack from device buffers owned by the caller. */
+int athk_remote_configure(athk_ctx *ctx, int nremote, const int *lb, const int *ox1,
+                          const int *ox2, const int *ox3);
+long long athk_remote_ghost_count(athk_ctx *ctx, int slot, int what_mask);
+long long athk_remote_emf_count(athk_ctx *ctx, int slot);
+int athk_remote_set_buffers(athk_ctx *ctx, double *send_ghost, double *recv_ghost,
+                            const long long *ghost_off, double *send_emf, double *recv_emf,
+                            const long long *emf_off);
+int athk_remote_pack_ghosts(athk_ctx *ctx, int what_mask, int reg);
+int athk_remote_pack_emf(athk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATHK_H_ */

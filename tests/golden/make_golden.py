@@ -1,0 +1,74 @@
+"""Generates the golden fixtures under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE
+(oracle/_ref/athena_<cfg>, built from /root/reference by oracle/Makefile.ref).  The reference has
+no golden vectors for Newtonian hydro/MHD, so its own outputs are the
+vectors.  Run from the repo root:  python tests/golden/make_golden.py [case ...]
+
+Each fixture is an .npz holding the initial state (reference pgen output, cycle 0 restart dump),
+the final state (final restart dump), both re-assembled to global arrays, the .hst rows printed
+with %24.16e, and the run parameters.
+"""
+import glob
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refrun  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # BASELINE configs[1] shape at parity size: MHD VL2+PLM+HLLD+CT, 8 MeshBlocks
+    "mhd_linwave_vl2_plm_hlld": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
+                                     block=(16, 8, 8), tlim=0.1, integrator="vl2", xorder=2),
+    # BASELINE configs[0] shape at parity size: hydro VL2+PLM+HLLC
+    "hydro_linwave_vl2_plm_hllc": dict(cfg="linwave_hydro_hllc", mhd=False, mesh=(32, 16, 16),
+                                       block=(16, 8, 8), tlim=0.1, integrator="vl2", xorder=2),
+    "mhd_linwave_rk2_plm_hlld": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
+                                     block=(16, 16, 16), tlim=0.05, integrator="rk2", xorder=2),
+    "mhd_linwave_rk3_plm_hlld": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
+                                     block=(32, 16, 16), tlim=0.05, integrator="rk3", xorder=2),
+    "hydro_linwave_rk3_plm_hllc": dict(cfg="linwave_hydro_hllc", mhd=False, mesh=(32, 16, 16),
+                                       block=(16, 8, 8), tlim=0.1, integrator="rk3", xorder=2,
+                                       wave_flag=4, vflow=0.5),
+    "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
+                                   block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
+                                   wave_flag=1, amp=1.0e-2),
+}
+
+
+def make(name):
+    c = CASES[name]
+    if not refrun.build_ref(c["cfg"]):
+        raise SystemExit("reference binary for %s unavailable" % c["cfg"])
+    blocks = refrun.linwave_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                   integrator=c["integrator"], xorder=c["xorder"],
+                                   wave_flag=c.get("wave_flag", 0), amp=c.get("amp", 1.0e-6),
+                                   vflow=c.get("vflow", 0.0))
+    wd, out = refrun.run_reference(c["cfg"], blocks)
+    r0 = refrun.read_rst(glob.glob(wd + "/*.00000.rst")[0])
+    rf = refrun.read_rst(glob.glob(wd + "/*.final.rst")[0])
+    a0, af = refrun.assemble(r0), refrun.assemble(rf)
+    names, hst = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
+    meta = dict(c, name=name, ng=r0["ng"], ncycle=rf["ncycle"], time=rf["time"], dt_final=rf["dt"],
+                dt0=r0["dt"], xmin=[0.0, 0.0, 0.0], xmax=[3.0, 1.5, 1.5], gamma=1.666666666666667,
+                cfl=0.3, loc=[list(l) for l in r0["loc"]], hst_names=names,
+                reference="Athena++ v24.0, g++ -O3 -std=c++11 -fopenmp, oracle/Makefile.ref")
+    arrs = dict(meta=np.array(json.dumps(meta)), hst=hst, u0=a0["u"], uf=af["u"])
+    if c["mhd"]:
+        for k in ("b1", "b2", "b3"):
+            arrs[k + "_0"] = a0[k]
+            arrs[k + "_f"] = af[k]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    shutil.rmtree(wd, ignore_errors=True)
+    print("wrote", name, "cycles", rf["ncycle"], "size",
+          os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    for n in (sys.argv[1:] or CASES):
+        make(n)

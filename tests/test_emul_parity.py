@@ -1,0 +1,24 @@
+"""CPU-side check of the operator bodies' index logic (tests/emul host build of the SAME functors
+the CUDA kernels run) against the reference's golden vectors.  This is debugging infrastructure
+for a container without a GPU; the GPU parity tests proper are in test_gpu_parity.py."""
+import pytest
+
+import util
+
+CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_rk2_plm_hlld",
+         "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emul_matches_reference_bitwise(emul_lib, name):
+    meta, z, ctx, ti = util.run_golden_case(emul_lib, name)
+    util.assert_matches_golden(meta, z, ctx, ti)
+    ctx.close()
+
+
+@pytest.mark.parametrize("block", [(32, 16, 16), (8, 8, 8), (16, 16, 8)])
+def test_emul_decomposition_invariance(emul_lib, block):
+    # the reference result depends on the global mesh only
+    meta, z, ctx, ti = util.run_golden_case(emul_lib, "mhd_linwave_vl2_plm_hlld", block=block)
+    util.assert_matches_golden(meta, z, ctx, ti)
+    ctx.close()
