@@ -11,6 +11,7 @@
 
 #include "athk_backend.h"
 #include "athk_ops.h"
+#include "athk_sweep.h"
 
 using namespace athk;
 
@@ -659,7 +660,88 @@ extern "C" int athk_new_block_dt(athk_ctx *c, double cfl_number, double *dt_bloc
 extern "C" int athk_calculate_scalar_fluxes(athk_ctx *, int) { return fail(ATHK_ERR_ARG, "calculate_scalar_fluxes: not implemented yet"); }
 extern "C" int athk_add_scalar_flux_divergence(athk_ctx *, double, int) { return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: not implemented yet"); }
 extern "C" int athk_history(athk_ctx *, double *, int) { return fail(ATHK_ERR_ARG, "history: not implemented yet"); }
-extern "C" int athk_stage(athk_ctx *, int, int, const athk_stage_wghts *, double) { return fail(ATHK_ERR_ARG, "stage: not implemented yet"); }
+//----------------------------------------------------------------------------------------
+// Fused stage: same task sequence, fewer passes over HBM (see athk_sweep.h).
+template <int ORDER, bool MHD>
+static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
+  const Grid &g = c->g;
+  {   // x1: calculate_fluxes.cpp:68-76
+    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
+    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
+    SweepX1<ORDER, MHD> f = {a};
+    CU(launch_sweep_x1(c->stream, g.nb, r, f));
+    c->launches++;
+  }
+  {   // x2 columns (i,k), marching j: calculate_fluxes.cpp:176-182
+    Range3 r = {g.ks, g.ke, 0, 0, g.is - 1, g.ie + 1};
+    if (MHD) { r.kl--; r.ku++; }
+    SweepMarch<1, ORDER, MHD> f = {a};
+    CU(launch_points(c->stream, g.nb, r, f, 128));
+    c->launches++;
+  }
+  {   // x3 columns (i,j), marching k: calculate_fluxes.cpp:299-302
+    Range3 r = {0, 0, g.js, g.je, g.is, g.ie};
+    if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
+    SweepMarch<2, ORDER, MHD> f = {a};
+    CU(launch_points(c->stream, g.nb, r, f, 128));
+    c->launches++;
+  }
+  return ATHK_OK;
+}
+
+extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wghts *sw,
+                          double dt_mesh) {
+  NEED_READY(c);
+  if (!sw) return fail(ATHK_ERR_ARG, "stage: null weights");
+  if (sw->gamma_3 != 0.0) return fail(ATHK_ERR_ARG, "stage: gamma_3 != 0 (3-register integrators) not implemented");
+  if (order != 1 && order != 2) return fail(ATHK_ERR_ARG, "stage: xorder %d not implemented in the fused path", order);
+  if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "stage: passive scalars not implemented in the fused path");
+  const Grid &g = c->g;
+  const bool mhd = c->cfg.mhd != 0;
+  const int swap = (sw->gamma_1 == 0.0 && sw->gamma_2 == 1.0 && sw->gamma_3 == 0.0) ? 1 : 0;
+  int wa = -2;
+  if (!swap) {
+    const double w[5] = {sw->gamma_1, sw->gamma_2, 0.0, 0.0, 0.0};
+    wa_mode(w, &wa);
+  }
+  SweepArgs a;
+  a.g = g; a.eos = c->eos; a.geo = c->geo;
+  a.w = c->w; a.bcc = c->bcc; a.b = mhd ? c->b[0] : nullptr;
+  a.flx[0] = a.flx[1] = a.flx[2] = nullptr;
+  a.ef = c->ef; a.wct = c->wct;
+  a.dflx = c->flux[0];   // the x1-flux array doubles as the flux-divergence scratch
+  a.dt = dt_mesh;
+  HydroIntegrate &h = a.hi;
+  h.u = c->u[0]; h.u1 = c->u[1];
+  h.u_out = swap ? c->u[1] : c->u[0];
+  h.u1_out = c->u[1];
+  h.delta = sw->delta; h.g1 = sw->gamma_1; h.g2 = sw->gamma_2;
+  h.wght = sw->beta * dt_mesh;
+  h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
+  int rc;
+  if (order == 1) rc = mhd ? launch_sweeps<1, true>(c, a) : launch_sweeps<1, false>(c, a);
+  else rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
+  if (rc) return rc;
+  if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
+  if (mhd) {
+    if ((rc = athk_compute_corner_e(c))) return rc;
+    if ((rc = athk_send_flux_correction(c))) return rc;
+    if ((rc = athk_recv_flux_correction(c))) return rc;
+    FieldIntegrate fi;
+    fi.b = c->b[0]; fi.b1 = c->b[1];
+    fi.b_out = swap ? c->b[1] : c->b[0];
+    fi.b1_out = c->b[1];
+    fi.delta = sw->delta; fi.g1 = sw->gamma_1; fi.g2 = sw->gamma_2;
+    fi.wght = sw->beta * dt_mesh;
+    fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
+    Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+    CTIntegratePoint f = {g, c->geo, c->e, fi};
+    LAUNCH(c, r, f);
+    if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
+  }
+  if ((rc = athk_exchange_ghosts(c, mhd ? 3 : 1, 0))) return rc;
+  return athk_cons2prim(c, 0);
+}
 extern "C" int athk_remote_configure(athk_ctx *, int, const int *, const int *, const int *, const int *) { return fail(ATHK_ERR_ARG, "remote_configure: not implemented yet"); }
 extern "C" long long athk_remote_ghost_count(athk_ctx *, int, int) { return -1; }
 extern "C" long long athk_remote_emf_count(athk_ctx *, int) { return -1; }

@@ -42,44 +42,91 @@ struct Range3 {
 };
 
 #ifndef ATHK_EMULATE
-// One thread per point; x covers i (unit stride => coalesced 128-byte rows), y covers j,
-// z covers (block, k).  Grid sized to the exact point count; blocks of 256 threads.
+// One thread per point of the (blk,k,j,i) box, flattened with i fastest so that consecutive
+// lanes touch consecutive addresses (rows of 64-70 doubles would leave half of a 2-D thread
+// block idle).  256-thread CTAs; the grid is sized to the exact point count.
 template <class F>
 __global__ void __launch_bounds__(256) k_points(const F f, const int nb, const int kl, const int nk,
                                                 const int jl, const int nj, const int il,
                                                 const int ni) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int kz = blockIdx.z * blockDim.z + threadIdx.z;
-  if (i >= ni || j >= nj || kz >= nk * nb) return;
-  const int blk = kz / nk;
-  const int k = kz - blk * nk;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nb * nk * nj * ni;
+  if (t >= total) return;
+  const int row = (int)(t / ni);
+  const int i = (int)(t - (long long)row * ni);
+  const int pl = row / nj;
+  const int j = row - pl * nj;
+  const int blk = pl / nk;
+  const int k = pl - blk * nk;
   f(blk, kl + k, jl + j, il + i);
 }
 
 template <class F>
-static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f) {
+static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f,
+                                        int threads = 256) {
   const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
-  int bx = 32;
-  while (bx < ni && bx < 128) bx <<= 1;   // 32, 64 or 128 threads along i
-  int by = 256 / bx;
-  if (by > nj) by = nj;
-  int bz = 256 / (bx * by);
-  if (bz < 1) bz = 1;
-  dim3 block(bx, by, bz);
-  dim3 grid((ni + bx - 1) / bx, (nj + by - 1) / by, (nk * nb + bz - 1) / bz);
-  k_points<F><<<grid, block, 0, st>>>(f, nb, r.kl, nk, r.jl, nj, r.il, ni);
+  const long long total = (long long)nb * nk * nj * ni;
+  const long long grid = (total + threads - 1) / threads;
+  k_points<F><<<(unsigned)grid, threads, 0, st>>>(f, nb, r.kl, nk, r.jl, nj, r.il, ni);
+  return cudaGetLastError();
+}
+
+// x1 sweep: one lane per face, warps advance by 31 faces so that lane L+1 always holds the
+// flux of the next face of lane L's cell (one redundant face per warp, 3%).
+template <class F>
+__global__ void __launch_bounds__(128) k_sweep_x1(const F f, const int nb, const int kl,
+                                                  const int nk, const int jl, const int nj,
+                                                  const int il, const int nif) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)nb * nk * nj * nif;
+  const long long s = warp * 31 + lane;
+  const bool valid = s < total;
+  int blk = 0, k = 0, j = 0, fi = 0;
+  double fl[7];
+#pragma unroll
+  for (int v = 0; v < 7; ++v) fl[v] = 0.0;
+  if (valid) {
+    const long long row = s / nif;
+    fi = (int)(s - row * nif);
+    const int pl = (int)(row / nj);
+    j = (int)(row - (long long)pl * nj);
+    blk = pl / nk;
+    k = pl - blk * nk;
+    f.compute(blk, kl + k, jl + j, il + fi, fl, lane < 31 || s == total - 1);
+  }
+  double fn[7];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) fn[v] = __shfl_down_sync(0xffffffffu, fl[v], 1);
+  if (valid && lane < 31 && fi + 1 < nif && f.cell_active(kl + k, jl + j, il + fi))
+    f.store_d1(blk, kl + k, jl + j, il + fi, fl, fn);
+}
+
+template <class F>
+static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
+  const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
+  const long long total = (long long)nb * nk * nj * nif;
+  if (total <= 0) return cudaSuccess;
+  long long nwarps = (total - 1 + 30) / 31;
+  if (nwarps < 1) nwarps = 1;
+  const long long grid = (nwarps + 3) / 4;
+  k_sweep_x1<F><<<(unsigned)grid, 128, 0, st>>>(f, nb, r.kl, nk, r.jl, nj, r.il, nif);
   return cudaGetLastError();
 }
 #else
 template <class F>
-static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, const F &f) {
+static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, const F &f,
+                                        int = 256) {
   for (int b = 0; b < nb; ++b)
     for (int k = r.kl; k <= r.ku; ++k)
       for (int j = r.jl; j <= r.ju; ++j)
         for (int i = r.il; i <= r.iu; ++i) f(b, k, j, i);
   return 0;
+}
+template <class F>
+static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
+  return launch_points(st, nb, r, f);
 }
 #endif
 

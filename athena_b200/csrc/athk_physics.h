@@ -106,10 +106,13 @@ ATHK_HD Real fast_speed(const EosParams &eos, Real d, Real p, Real by, Real bz, 
 //----------------------------------------------------------------------------------------
 // PLM, uniform-Cartesian van Leer limiter (reconstruct/plm.cpp:104-112): limited slope of one
 // variable from its left/right one-sided differences.
+// The reference evaluates 2*dw2/(dwl+dwr) unconditionally and then overwrites it with 0 when
+// dw2 <= 0; skipping the division in that case gives the same bits and keeps 0/0 (uniform
+// regions) off the FP64 division slow path.  !(dw2 <= 0) keeps NaN inputs on the division.
 ATHK_HD Real vl_slope(Real dwl, Real dwr) {
   Real dw2 = dwl * dwr;
-  Real dwm = 2.0 * dw2 / (dwl + dwr);
-  if (dw2 <= 0.0) dwm = 0.0;
+  Real dwm = 0.0;
+  if (!(dw2 <= 0.0)) dwm = 2.0 * dw2 / (dwl + dwr);
   return dwm;
 }
 

@@ -1,0 +1,332 @@
+// athk_sweep.h -- fused directional sweeps of Hydro::CalculateFluxes + AddFluxDivergence +
+// the integrator's WeightedAve (the "stage" fast path behind athk_stage()).
+//
+// Same arithmetic as the per-operator kernels (athk_ops.h) -- bit-identical results -- but laid
+// out for the B200: FP64 issue is the binding resource of HLLD+PLM, HBM the second, so
+//   * every cell's PLM slopes are computed once per direction (x2/x3 sweeps march along the
+//     sweep direction with the previous cell's left state held in registers; the CPU code's
+//     wl_/wlb_ pencil swap, calculate_fluxes.cpp:236,355, becomes a register rotation);
+//   * each primitive is loaded once per sweep as a coalesced row (threads along i);
+//   * fluxes never go to HBM: each sweep folds (A F)_+ - (A F)_- into a 5-component scratch
+//     "dflx" (add_flux_divergence.cpp:57-83 accumulation order x1, x2, x3), and the x3 sweep
+//     applies  u_out = WeightedAve(...) - wght*dflx/vol  (time_integrator.cpp:1797-1824).
+// Only the face EMFs + CT weights (needed one cell outside the block by ComputeCornerE) are
+// written out.
+#ifndef ATHK_SWEEP_H_
+#define ATHK_SWEEP_H_
+
+#include "athk_ops.h"
+
+namespace athk {
+
+// how the x3 sweep finishes the hydro update for an interior cell
+struct HydroIntegrate {
+  // registers after the host-side pointer bookkeeping: see athk_stage() in athk_api.cu
+  const Real *u;      // "u"  on entry  [nb][5][sn]
+  const Real *u1;     // "u1" on entry (may be null when u1_zero)
+  Real *u_out;        // array that holds "u" after the stage
+  Real *u1_out;       // array that holds "u1" after the stage (written only if delta != 0 and no swap)
+  Real delta, g1, g2; // stage weights (gamma_3 = 0 for vl2/rk2/rk3)
+  Real wght;          // beta*dt
+  int swap;           // gamma = (0,1,0): SwapAthenaArray instead of averaging
+  int u1_zero;        // stage 1: u1 was ZeroClear'ed (value known, no need to read it)
+  int wa_mode;        // WeightedAvePoint mode for the (g1,g2) average when !swap
+};
+
+struct SweepArgs {
+  Grid g;
+  EosParams eos;
+  Geom geo;
+  const Real *w, *bcc, *b;   // primitives, cell-centred field, face field of the stage input
+  Real *flx[3];              // optional flux arrays (null = do not store)
+  Real *ef;                  // [nb][6][sn]
+  Real *wct;                 // [nb][3][sn]
+  Real *dflx;                // [nb][5][sn] scratch
+  Real dt;                   // pmy_mesh->dt
+  HydroIntegrate hi;
+};
+
+// rotated primitive vector of one cell: (d, v_n, v_t1, v_t2, p, b_t1, b_t2)
+template <int DIR, bool MHD>
+ATHK_HD void load_q(const SweepArgs &a, int blk, idx_t c, Real q[7]) {
+  const Grid &g = a.g;
+  const Real *wb = a.w + (idx_t)blk * 5 * g.sn + c;
+  q[0] = wb[0];
+  q[1] = wb[(idx_t)(IVX + DIR) * g.sn];
+  q[2] = wb[(idx_t)(IVX + (DIR + 1) % 3) * g.sn];
+  q[3] = wb[(idx_t)(IVX + (DIR + 2) % 3) * g.sn];
+  q[4] = wb[(idx_t)IPR * g.sn];
+  if (MHD) {
+    const Real *bc = a.bcc + (idx_t)blk * 3 * g.sn + c;
+    q[5] = bc[(idx_t)((DIR + 1) % 3) * g.sn];
+    q[6] = bc[(idx_t)((DIR + 2) % 3) * g.sn];
+  }
+}
+
+// Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
+template <int DIR, bool MHD>
+ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
+                        const Real wr[7], Real f[7], bool store) {
+  const Grid &g = a.g;
+  if (MHD) {
+    const Real bxi = a.b[((idx_t)blk * 3 + DIR) * g.sn + c];
+    hlld_flux(a.eos, wl, wr, bxi, f);
+    if (store) {
+      Real *eb = a.ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
+      eb[0] = -f[IBY];
+      eb[g.sn] = f[IBZ];
+      const Real dxw = a.geo.dxf[DIR][blk * a.geo.PG + n_dir];
+      a.wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, a.dt);
+    }
+  } else {
+    hllc_flux(a.eos, wl, wr, f);
+  }
+  if (store && a.flx[DIR]) {
+    Real *fb = a.flx[DIR] + (idx_t)blk * 5 * g.sn + c;
+    fb[0] = f[IDN];
+    fb[(idx_t)(IVX + DIR) * g.sn] = f[IVX];
+    fb[(idx_t)(IVX + (DIR + 1) % 3) * g.sn] = f[IVY];
+    fb[(idx_t)(IVX + (DIR + 2) % 3) * g.sn] = f[IVZ];
+    fb[(idx_t)IEN * g.sn] = f[IEN];
+  }
+}
+
+// PLM (or donor cell) of one cell from its two neighbours: left state of the upper face and
+// right state of the lower face (plm.cpp:104-112,149-154 / dc.cpp)
+template <int ORDER, bool MHD>
+ATHK_HD void recon_cell(const Real qm[7], const Real q0[7], const Real qp[7], Real cp, Real cm,
+                        Real wl_up[7], Real wr_lo[7]) {
+  const int NW = MHD ? 7 : 5;
+#pragma unroll
+  for (int n = 0; n < NW; ++n) {
+    if (ORDER == 1) {
+      wl_up[n] = q0[n];
+      wr_lo[n] = q0[n];
+    } else {
+      const Real dwm = vl_slope(q0[n] - qm[n], qp[n] - q0[n]);
+      wl_up[n] = q0[n] + cp * dwm;
+      wr_lo[n] = q0[n] - cm * dwm;
+    }
+  }
+}
+
+// finish the hydro update of one interior cell (all 5 variables): dflx already holds the
+// x1+x2 contributions, d3[] is this sweep's; then WeightedAve + flux divergence.
+ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsum[5], Real vol) {
+  const Grid &g = a.g;
+  const HydroIntegrate &h = a.hi;
+#pragma unroll
+  for (int n = 0; n < 5; ++n) {
+    const idx_t o = ((idx_t)blk * 5 + n) * g.sn + c;
+    const Real un = h.u[o];
+    Real u1n = h.u1_zero ? 0.0 : h.u1[o];
+    if (h.delta != 0.0) u1n += h.delta * un;          // WeightedAve(u1,u,..,{1,delta,0,0,0})
+    Real r;
+    if (h.swap) {
+      r = u1n;                                        // u <-> u1
+    } else {
+      switch (h.wa_mode) {                            // WeightedAve(u,u1,..,{g1,g2,0,0,0})
+        case 1: r = un; r += h.g2 * u1n; break;
+        case 3: r = h.g2 * u1n; break;
+        case 5: r = h.g1 * un + h.g2 * u1n; break;
+        case 6: r = un; r *= h.g1; break;
+        default: r = un; break;
+      }
+      if (h.delta != 0.0) h.u1_out[o] = u1n;
+    }
+    r -= h.wght * dsum[n] / vol;                      // AddFluxDivergence
+    h.u_out[o] = r;
+  }
+}
+
+//========================================================================================
+// x2 / x3 sweep: one thread owns one column along the sweep direction.
+//   DIR=1: column (i,k), marches j ; DIR=2: column (i,j), marches k.
+// Column extents follow calculate_fluxes.cpp:176-182,299-302; faces s..e+1 along the sweep.
+template <int DIR, int ORDER, bool MHD>
+struct SweepMarch {
+  SweepArgs a;
+  // (blk, k, j, i): for DIR=1 the j argument is ignored, for DIR=2 the k argument is ignored
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const Grid &g = a.g;
+    const idx_t s = (DIR == 1) ? g.sj : g.sk;
+    const int n_s = (DIR == 1) ? g.js : g.ks;        // first active index along the sweep
+    const int n_e = (DIR == 1) ? g.je : g.ke;
+    idx_t c = (DIR == 1) ? gidx(g, k, n_s - 1, i) : gidx(g, n_s - 1, j, i);   // cell n_s-1
+    // is this column part of the active zone (gets a flux divergence)?
+    const bool interior = (i >= g.is && i <= g.ie) &&
+                          ((DIR == 1) ? (k >= g.ks && k <= g.ke) : (j >= g.js && j <= g.je));
+    const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
+    const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
+    Real area = 0.0, vol = 0.0;
+    if (interior) {
+      const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
+      if (DIR == 1) {
+        const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
+        area = dx1 * dx3;                              // Face2Area
+      } else {
+        const Real dx2 = a.geo.dxf[1][blk * a.geo.PG + j];
+        area = dx1 * dx2;                              // Face3Area
+        vol = dx1 * dx2;                               // * dx3(k) below (CellVolume order)
+      }
+    }
+    Real qm[7], q0[7], qp[7], wl[7], wl_up[7], wr[7], f[7], fprev[5];
+    load_q<DIR, MHD>(a, blk, c - s, qm);
+    load_q<DIR, MHD>(a, blk, c, q0);
+    // cell n_s-1: only its upper-face left state is needed
+    load_q<DIR, MHD>(a, blk, c + s, qp);
+    recon_cell<ORDER, MHD>(qm, q0, qp, ORDER == 2 ? cpv[n_s - 1] : 0.0,
+                           ORDER == 2 ? cmv[n_s - 1] : 0.0, wl, wr);
+    for (int n = n_s; n <= n_e + 1; ++n) {
+      c += s;
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
+      load_q<DIR, MHD>(a, blk, c + s, qp);
+      recon_cell<ORDER, MHD>(qm, q0, qp, ORDER == 2 ? cpv[n] : 0.0, ORDER == 2 ? cmv[n] : 0.0,
+                             wl_up, wr);
+      solve_face<DIR, MHD>(a, blk, c, n, wl, wr, f, true);   // face n: L from cell n-1, R from cell n
+      if (interior && n > n_s) {
+        // cell n-1: (A F)(n) - (A F)(n-1)
+        const idx_t cc = c - s;
+        Real dsum[5];
+        const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
+        const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
+#pragma unroll
+        for (int v = 0; v < 5; ++v) {
+          const idx_t o = ((idx_t)blk * 5 + vmap[v]) * g.sn + cc;
+          Real d = a.dflx[o];
+          d += (area * fcur[v] - area * fprev[v]);
+          if (DIR == 1) a.dflx[o] = d;
+          else dsum[vmap[v]] = d;
+        }
+        if (DIR == 2) {
+          const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + (n - 1)];
+          integrate_cell(a, blk, cc, dsum, vol * dx3);
+        }
+      }
+      fprev[0] = f[IDN]; fprev[1] = f[IVX]; fprev[2] = f[IVY]; fprev[3] = f[IVZ]; fprev[4] = f[IEN];
+#pragma unroll
+      for (int v = 0; v < 7; ++v) wl[v] = wl_up[v];
+    }
+  }
+};
+
+//========================================================================================
+// x1 sweep: one thread per face (coalesced along i).  compute() is the face solve; the GPU
+// kernel passes the flux of face i+1 to the owner of cell i with a warp shuffle, the host
+// harness (tests/emul) simply solves face i+1 again.
+template <int ORDER, bool MHD>
+struct SweepX1 {
+  SweepArgs a;
+  ATHK_HD void compute(int blk, int k, int j, int i, Real f[7], bool store) const {
+    const Grid &g = a.g;
+    const idx_t c = gidx(g, k, j, i);
+    Real q0[7], q1[7], q2[7], q3[7], wl[7], wr[7], t0[7], t1[7];
+    load_q<0, MHD>(a, blk, c - 1, q1);
+    load_q<0, MHD>(a, blk, c, q2);
+    if (ORDER == 2) {
+      load_q<0, MHD>(a, blk, c - 2, q0);
+      load_q<0, MHD>(a, blk, c + 1, q3);
+      const Real *cpv = a.geo.cp[0] + blk * a.geo.PG;
+      const Real *cmv = a.geo.cm[0] + blk * a.geo.PG;
+      recon_cell<ORDER, MHD>(q0, q1, q2, cpv[i - 1], cmv[i - 1], wl, t0);   // cell i-1 -> L state
+      recon_cell<ORDER, MHD>(q1, q2, q3, cpv[i], cmv[i], t1, wr);           // cell i   -> R state
+    } else {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { wl[v] = q1[v]; wr[v] = q2[v]; }
+    }
+    solve_face<0, MHD>(a, blk, c, i, wl, wr, f, store);
+  }
+  // cell (k,j,i) of the active zone: dflx = A1*F(i+1) - A1*F(i)   (first term of the sum)
+  ATHK_HD void store_d1(int blk, int k, int j, int i, const Real f[7], const Real fnext[7]) const {
+    const Grid &g = a.g;
+    const idx_t c = gidx(g, k, j, i);
+    const Real dx2 = a.geo.dxf[1][blk * a.geo.PG + j], dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
+    const Real area = dx2 * dx3;   // Face1Area
+    const int src[5] = {IDN, IVX, IVY, IVZ, IEN};
+#pragma unroll
+    for (int v = 0; v < 5; ++v)   // DIR=0: rotated index == variable index
+      a.dflx[((idx_t)blk * 5 + src[v]) * g.sn + c] = (area * fnext[src[v]] - area * f[src[v]]);
+  }
+  ATHK_HD bool cell_active(int k, int j, int i) const {
+    const Grid &g = a.g;
+    return i <= g.ie && j >= g.js && j <= g.je && k >= g.ks && k <= g.ke;
+  }
+  // host harness path
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    Real f[7], fn[7];
+    compute(blk, k, j, i, f, true);
+    if (cell_active(k, j, i)) {
+      compute(blk, k, j, i + 1, fn, false);
+      store_d1(blk, k, j, i, f, fn);
+    }
+  }
+};
+
+//========================================================================================
+// Field::CT fused with the integrator's face-centred WeightedAve (time_integrator.cpp:
+// 1853-1885, field/ct.cpp:31-116, mesh/weighted_ave.cpp:366-520).  Same launch domain as CTPoint.
+struct FieldIntegrate {
+  const Real *b, *b1;
+  Real *b_out, *b1_out;
+  Real delta, g1, g2, wght;
+  int swap, b1_zero, wa_mode;
+};
+
+struct CTIntegratePoint {
+  Grid g;
+  Geom geo;
+  const Real *e;
+  FieldIntegrate fi;
+  ATHK_HD Real averaged(idx_t o) const {
+    const Real bn = fi.b[o];
+    Real b1n = fi.b1_zero ? 0.0 : fi.b1[o];
+    if (fi.delta != 0.0) b1n += fi.delta * bn;
+    Real r;
+    if (fi.swap) {
+      r = b1n;
+    } else {
+      switch (fi.wa_mode) {
+        case 1: r = bn; r += fi.g2 * b1n; break;
+        case 3: r = fi.g2 * b1n; break;
+        case 5: r = fi.g1 * bn + fi.g2 * b1n; break;
+        case 6: r = bn; r *= fi.g1; break;
+        default: r = bn; break;
+      }
+      if (fi.delta != 0.0) fi.b1_out[o] = b1n;
+    }
+    return r;
+  }
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real *e1 = e + (idx_t)blk * 3 * g.sn, *e2 = e1 + g.sn, *e3 = e1 + 2 * g.sn;
+    const idx_t o = (idx_t)blk * 3 * g.sn + c;
+    const Real dx1 = geo.dxf[0][blk * geo.PG + i], dx2 = geo.dxf[1][blk * geo.PG + j],
+               dx3 = geo.dxf[2][blk * geo.PG + k];
+    const Real wght = fi.wght;
+    if (k <= g.ke && j <= g.je) {
+      const Real area = dx2 * dx3;
+      Real v = averaged(o);
+      v -= (wght / area) * (dx3 * e3[c + g.sj] - dx3 * e3[c]);
+      v += (wght / area) * (dx2 * e2[c + g.sk] - dx2 * e2[c]);
+      fi.b_out[o] = v;
+    }
+    if (k <= g.ke && i <= g.ie) {
+      const Real area = dx1 * dx3;
+      Real v = averaged(o + g.sn);
+      v += (wght / area) * (dx3 * e3[c + 1] - dx3 * e3[c]);
+      v -= (wght / area) * (dx1 * e1[c + g.sk] - dx1 * e1[c]);
+      fi.b_out[o + g.sn] = v;
+    }
+    if (j <= g.je && i <= g.ie) {
+      const Real area = dx1 * dx2;
+      Real v = averaged(o + 2 * g.sn);
+      v -= (wght / area) * (dx2 * e2[c + 1] - dx2 * e2[c]);
+      v += (wght / area) * (dx1 * e1[c + g.sj] - dx1 * e1[c]);
+      fi.b_out[o + 2 * g.sn] = v;
+    }
+  }
+};
+
+}  // namespace athk
+#endif  // ATHK_SWEEP_H_

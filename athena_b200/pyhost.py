@@ -260,6 +260,11 @@ class TimeIntegrator:
         delta, g1, g2, g3, beta = self.stages[stage - 1]
         dt = self.dt
         mhd = c.mhd
+        order = 1 if (self.integrator == "vl2" and stage == 1) else self.xorder
+        if self.fused:
+            sw = capi.StageWghts(delta, g1, g2, g3, beta)
+            c.call("athk_stage", stage, order, C.byref(sw), dt)
+            return
         if stage == 1:   # StartupTaskList, time_integrator.cpp:1608-1619
             c.call("athk_zero_register", 0, 1)
             if mhd:

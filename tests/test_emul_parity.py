@@ -22,3 +22,11 @@ def test_emul_decomposition_invariance(emul_lib, block):
     meta, z, ctx, ti = util.run_golden_case(emul_lib, "mhd_linwave_vl2_plm_hlld", block=block)
     util.assert_matches_golden(meta, z, ctx, ti)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emul_fused_stage_matches_reference_bitwise(emul_lib, name):
+    # athk_stage(): fused sweeps + integrate, must give the same bits as the operator sequence
+    meta, z, ctx, ti = util.run_golden_case(emul_lib, name, fused=True)
+    util.assert_matches_golden(meta, z, ctx, ti)
+    ctx.close()
