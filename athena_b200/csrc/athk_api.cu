@@ -12,6 +12,9 @@
 #include "athk_backend.h"
 #include "athk_ops.h"
 #include "athk_sweep.h"
+#ifndef ATHK_EMULATE
+#include "athk_sweep_kernels.cuh"
+#endif
 
 using namespace athk;
 
@@ -672,20 +675,29 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
     CU(launch_sweep_x1(c->stream, g.nb, r, f));
     c->launches++;
   }
-  {   // x2 columns (i,k), marching j: calculate_fluxes.cpp:176-182
+#ifndef ATHK_EMULATE
+  // x2 columns (i,k) / x3 columns (i,j): CTA-marching tiles (athk_sweep_kernels.cuh);
+  // extents of calculate_fluxes.cpp:176-182,299-302
+  CU((launch_sweep_tile<1, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.ks - 1 : g.ks,
+                                       MHD ? g.ke + 1 : g.ke, g.is - 1, g.ie + 1)));
+  CU((launch_sweep_tile<2, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.js - 1 : g.js,
+                                       MHD ? g.je + 1 : g.je, MHD ? g.is - 1 : g.is,
+                                       MHD ? g.ie + 1 : g.ie)));
+  c->launches += 2;
+#else
+  {   // host harness: the same sweeps as per-thread marches
     Range3 r = {g.ks, g.ke, 0, 0, g.is - 1, g.ie + 1};
     if (MHD) { r.kl--; r.ku++; }
     SweepMarch<1, ORDER, MHD> f = {a};
     CU(launch_points(c->stream, g.nb, r, f, 128));
-    c->launches++;
   }
-  {   // x3 columns (i,j), marching k: calculate_fluxes.cpp:299-302
+  {
     Range3 r = {0, 0, g.js, g.je, g.is, g.ie};
     if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
     SweepMarch<2, ORDER, MHD> f = {a};
     CU(launch_points(c->stream, g.nb, r, f, 128));
-    c->launches++;
   }
+#endif
   return ATHK_OK;
 }
 

@@ -45,8 +45,14 @@ struct Range3 {
 // One thread per point of the (blk,k,j,i) box, flattened with i fastest so that consecutive
 // lanes touch consecutive addresses (rows of 64-70 doubles would leave half of a 2-D thread
 // block idle).  256-thread CTAs; the grid is sized to the exact point count.
+#ifndef ATHK_KP_THREADS
+#define ATHK_KP_THREADS 128
+#endif
+#ifndef ATHK_KP_MINB
+#define ATHK_KP_MINB 5
+#endif
 template <class F>
-__global__ void __launch_bounds__(256) k_points(const F f, const int nb, const int kl, const int nk,
+__global__ void __launch_bounds__(ATHK_KP_THREADS, ATHK_KP_MINB) k_points(const F f, const int nb, const int kl, const int nk,
                                                 const int jl, const int nj, const int il,
                                                 const int ni) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +69,8 @@ __global__ void __launch_bounds__(256) k_points(const F f, const int nb, const i
 
 template <class F>
 static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f,
-                                        int threads = 256) {
+                                        int threads = ATHK_KP_THREADS) {
+  if (threads > ATHK_KP_THREADS) threads = ATHK_KP_THREADS;
   const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
   const long long total = (long long)nb * nk * nj * ni;
@@ -74,8 +81,11 @@ static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r
 
 // x1 sweep: one lane per face, warps advance by 31 faces so that lane L+1 always holds the
 // flux of the next face of lane L's cell (one redundant face per warp, 3%).
+#ifndef ATHK_X1_MINB
+#define ATHK_X1_MINB 5
+#endif
 template <class F>
-__global__ void __launch_bounds__(128) k_sweep_x1(const F f, const int nb, const int kl,
+__global__ void __launch_bounds__(128, ATHK_X1_MINB) k_sweep_x1(const F f, const int nb, const int kl,
                                                   const int nk, const int jl, const int nj,
                                                   const int il, const int nif) {
   const int lane = threadIdx.x & 31;

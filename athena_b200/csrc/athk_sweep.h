@@ -212,6 +212,30 @@ struct SweepMarch {
 };
 
 //========================================================================================
+// One face of a DIR-sweep, self-contained: reconstruct both adjacent cells, then Riemann solve.
+// c = index of the cell above the face, n_dir = its index along the sweep.
+template <int DIR, int ORDER, bool MHD>
+ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
+  const Grid &g = a.g;
+  const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
+  Real q0[7], q1[7], q2[7], q3[7], wl[7], wr[7], t0[7], t1[7];
+  load_q<DIR, MHD>(a, blk, c - s, q1);
+  load_q<DIR, MHD>(a, blk, c, q2);
+  if (ORDER == 2) {
+    load_q<DIR, MHD>(a, blk, c - 2 * s, q0);
+    load_q<DIR, MHD>(a, blk, c + s, q3);
+    const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
+    const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
+    recon_cell<ORDER, MHD>(q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
+    recon_cell<ORDER, MHD>(q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
+  } else {
+#pragma unroll
+    for (int v = 0; v < 7; ++v) { wl[v] = q1[v]; wr[v] = q2[v]; }
+  }
+  solve_face<DIR, MHD>(a, blk, c, n_dir, wl, wr, f, store);
+}
+
+//========================================================================================
 // x1 sweep: one thread per face (coalesced along i).  compute() is the face solve; the GPU
 // kernel passes the flux of face i+1 to the owner of cell i with a warp shuffle, the host
 // harness (tests/emul) simply solves face i+1 again.

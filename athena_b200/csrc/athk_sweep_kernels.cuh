@@ -1,0 +1,113 @@
+// athk_sweep_kernels.cuh -- CUDA-only launch shapes of the fused x2/x3 sweeps (athk_sweep.h holds
+// the arithmetic, shared with the host harness).
+//
+// HLLD in FP64 needs ~100-150 registers, so resident warps -- not HBM -- bound these kernels
+// (ncu, profiles/): the per-thread "march" of SweepMarch carries its rolling stencil in
+// registers and drops to 8 warps/SM.  Here the CTA marches instead of the thread:
+//   CTA = 32 columns (lanes, consecutive i => coalesced rows) x R faces along the sweep.
+//   Each step every thread solves ONE face (no loop-carried registers), parks its 5 hydro fluxes
+//   in shared memory, and after one __syncthreads the thread owning cell n-1 forms
+//   (A F)(n) - (A F)(n-1) from its own flux and the row below (the previous step's top row for
+//   r == 0: triple-buffered, so one barrier per step suffices and no face is solved twice).
+#ifndef ATHK_SWEEP_KERNELS_CUH_
+#define ATHK_SWEEP_KERNELS_CUH_
+
+#include "athk_sweep.h"
+
+namespace athk {
+
+#ifndef ATHK_TILE_R
+#define ATHK_TILE_R 5
+#endif
+#ifndef ATHK_TILE_MINB
+#define ATHK_TILE_MINB 4
+#endif
+
+template <int DIR, int ORDER, bool MHD>
+__global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
+k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il,
+             const int ni) {
+  constexpr int R = ATHK_TILE_R;
+  __shared__ Real sF[3][R][5][32];
+  const Grid &g = a.g;
+  const int lane = threadIdx.x, r = threadIdx.y;
+  const long long col = (long long)blockIdx.x * 32 + lane;
+  const long long ncol = (long long)nb * n_o * ni;
+  const bool colvalid = col < ncol;
+  int blk = 0, o = o_lo, i = il;
+  if (colvalid) {
+    const int row = (int)(col / ni);
+    i = il + (int)(col - (long long)row * ni);
+    blk = row / n_o;
+    o = o_lo + (row - blk * n_o);
+  }
+  const idx_t s = (DIR == 1) ? g.sj : g.sk;
+  const int n_s = (DIR == 1) ? g.js : g.ks;
+  const int n_e = (DIR == 1) ? g.je : g.ke;
+  const int k0 = (DIR == 1) ? o : 0, j0 = (DIR == 1) ? 0 : o;
+  const bool interior = colvalid && (i >= g.is && i <= g.ie) &&
+                        ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
+  Real area = 0.0, vol12 = 0.0;
+  if (interior) {
+    const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
+    if (DIR == 1) {
+      area = dx1 * a.geo.dxf[2][blk * a.geo.PG + o];   // Face2Area = dx1f*dx3f
+    } else {
+      area = dx1 * a.geo.dxf[1][blk * a.geo.PG + o];   // Face3Area = dx1f*dx2f
+      vol12 = area;                                    // CellVolume = (dx1f*dx2f)*dx3f
+    }
+  }
+  const int nf = n_e + 1 - n_s + 1;            // faces n_s .. n_e+1
+  const int nsteps = (nf + R - 1) / R;
+  const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
+  for (int step = 0; step < nsteps; ++step) {
+    const int n = n_s + step * R + r;
+    const bool fvalid = colvalid && n <= n_e + 1;
+    const int buf = step % 3;
+    Real f[7];
+    idx_t c = 0;
+    if (fvalid) {
+      c = (DIR == 1) ? gidx(g, k0, n, i) : gidx(g, n, j0, i);
+      face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
+      sF[buf][r][0][lane] = f[IDN];
+      sF[buf][r][1][lane] = f[IVX];
+      sF[buf][r][2][lane] = f[IVY];
+      sF[buf][r][3][lane] = f[IVZ];
+      sF[buf][r][4][lane] = f[IEN];
+    }
+    __syncthreads();
+    if (fvalid && interior && n > n_s) {
+      const Real(*below)[32] = (r > 0) ? sF[buf][r - 1] : sF[(step + 2) % 3][R - 1];
+      const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
+      const idx_t cc = c - s;   // cell n-1
+      Real dsum[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const idx_t oo = ((idx_t)blk * 5 + vmap[v]) * g.sn + cc;
+        Real d = a.dflx[oo];
+        d += (area * fcur[v] - area * below[v][lane]);
+        if (DIR == 1) a.dflx[oo] = d;
+        else dsum[vmap[v]] = d;
+      }
+      if (DIR == 2) {
+        const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + (n - 1)];
+        integrate_cell(a, blk, cc, dsum, vol12 * dx3);
+      }
+    }
+  }
+}
+
+template <int DIR, int ORDER, bool MHD>
+static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a, int nb, int o_lo,
+                                            int o_hi, int il, int iu) {
+  const int n_o = o_hi - o_lo + 1, ni = iu - il + 1;
+  const long long ncol = (long long)nb * n_o * ni;
+  if (ncol <= 0) return cudaSuccess;
+  dim3 block(32, ATHK_TILE_R);
+  const unsigned grid = (unsigned)((ncol + 31) / 32);
+  k_sweep_tile<DIR, ORDER, MHD><<<grid, block, 0, st>>>(a, nb, o_lo, n_o, il, ni);
+  return cudaGetLastError();
+}
+
+}  // namespace athk
+#endif  // ATHK_SWEEP_KERNELS_CUH_
