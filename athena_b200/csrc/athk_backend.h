@@ -42,29 +42,28 @@ struct Range3 {
 };
 
 #ifndef ATHK_EMULATE
-// One thread per point of the (blk,k,j,i) box, flattened with i fastest so that consecutive
-// lanes touch consecutive addresses (rows of 64-70 doubles would leave half of a 2-D thread
-// block idle).  256-thread CTAs; the grid is sized to the exact point count.
+// One thread per point of the (blk,k,j,i) box.  grid.x covers one (j,i) plane flattened with i
+// fastest (consecutive lanes -> consecutive addresses; rows of 64-70 doubles would leave a 2-D
+// thread block half idle), grid.y = k, grid.z = MeshBlock: the plane decode is block-uniform and
+// the single per-thread division t / ni is a multiply-high by a host-computed reciprocal
+// (exact for t*ni < 2^32).
 #ifndef ATHK_KP_THREADS
 #define ATHK_KP_THREADS 128
 #endif
 #ifndef ATHK_KP_MINB
 #define ATHK_KP_MINB 5
 #endif
+static inline unsigned magic_u32(int d) { return (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
+
 template <class F>
-__global__ void __launch_bounds__(ATHK_KP_THREADS, ATHK_KP_MINB) k_points(const F f, const int nb, const int kl, const int nk,
-                                                const int jl, const int nj, const int il,
-                                                const int ni) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)nb * nk * nj * ni;
-  if (t >= total) return;
-  const int row = (int)(t / ni);
-  const int i = (int)(t - (long long)row * ni);
-  const int pl = row / nj;
-  const int j = row - pl * nj;
-  const int blk = pl / nk;
-  const int k = pl - blk * nk;
-  f(blk, kl + k, jl + j, il + i);
+__global__ void __launch_bounds__(ATHK_KP_THREADS, ATHK_KP_MINB)
+k_points(const F f, const int kl, const int jl, const int nj, const int il, const int ni,
+         const unsigned ni_magic) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(nj * ni)) return;
+  const unsigned j = (ni == 1) ? t : __umulhi(t, ni_magic);
+  const unsigned i = t - j * (unsigned)ni;
+  f((int)blockIdx.z, kl + (int)blockIdx.y, jl + (int)j, il + (int)i);
 }
 
 template <class F>
@@ -73,55 +72,52 @@ static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r
   if (threads > ATHK_KP_THREADS) threads = ATHK_KP_THREADS;
   const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
-  const long long total = (long long)nb * nk * nj * ni;
-  const long long grid = (total + threads - 1) / threads;
-  k_points<F><<<(unsigned)grid, threads, 0, st>>>(f, nb, r.kl, nk, r.jl, nj, r.il, ni);
+  dim3 grid((unsigned)((nj * ni + threads - 1) / threads), (unsigned)nk, (unsigned)nb);
+  k_points<F><<<grid, threads, 0, st>>>(f, r.kl, r.jl, nj, r.il, ni, magic_u32(ni));
   return cudaGetLastError();
 }
 
-// x1 sweep: one lane per face, warps advance by 31 faces so that lane L+1 always holds the
-// flux of the next face of lane L's cell (one redundant face per warp, 3%).
+// x1 sweep: one lane per face; within a (k, MeshBlock) plane the faces form a stream and warps
+// advance by 31 so that lane L+1 always holds the flux of the upper face of lane L's cell (one
+// redundant face per warp, 3%).
 #ifndef ATHK_X1_MINB
 #define ATHK_X1_MINB 5
 #endif
 template <class F>
-__global__ void __launch_bounds__(128, ATHK_X1_MINB) k_sweep_x1(const F f, const int nb, const int kl,
-                                                  const int nk, const int jl, const int nj,
-                                                  const int il, const int nif) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)nb * nk * nj * nif;
-  const long long s = warp * 31 + lane;
+__global__ void __launch_bounds__(128, ATHK_X1_MINB)
+k_sweep_x1(const F f, const int kl, const int jl, const int nj, const int il, const int nif,
+           const unsigned nif_magic) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned total = (unsigned)(nj * nif);
+  const unsigned s = warp * 31 + lane;
   const bool valid = s < total;
-  int blk = 0, k = 0, j = 0, fi = 0;
+  const int blk = (int)blockIdx.z, k = kl + (int)blockIdx.y;
+  int j = 0, fi = 0;
   double fl[7];
 #pragma unroll
   for (int v = 0; v < 7; ++v) fl[v] = 0.0;
   if (valid) {
-    const long long row = s / nif;
-    fi = (int)(s - row * nif);
-    const int pl = (int)(row / nj);
-    j = (int)(row - (long long)pl * nj);
-    blk = pl / nk;
-    k = pl - blk * nk;
-    f.compute(blk, kl + k, jl + j, il + fi, fl, lane < 31 || s == total - 1);
+    const unsigned row = __umulhi(s, nif_magic);
+    fi = (int)(s - row * (unsigned)nif);
+    j = jl + (int)row;
+    f.compute(blk, k, j, il + fi, fl, lane < 31 || s == total - 1);
   }
   double fn[7];
 #pragma unroll
   for (int v = 0; v < 5; ++v) fn[v] = __shfl_down_sync(0xffffffffu, fl[v], 1);
-  if (valid && lane < 31 && fi + 1 < nif && f.cell_active(kl + k, jl + j, il + fi))
-    f.store_d1(blk, kl + k, jl + j, il + fi, fl, fn);
+  if (valid && lane < 31 && fi + 1 < nif && f.cell_active(k, j, il + fi))
+    f.store_d1(blk, k, j, il + fi, fl, fn);
 }
 
 template <class F>
 static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
   const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
-  const long long total = (long long)nb * nk * nj * nif;
-  if (total <= 0) return cudaSuccess;
-  long long nwarps = (total - 1 + 30) / 31;
-  if (nwarps < 1) nwarps = 1;
-  const long long grid = (nwarps + 3) / 4;
-  k_sweep_x1<F><<<(unsigned)grid, 128, 0, st>>>(f, nb, r.kl, nk, r.jl, nj, r.il, nif);
+  if (nif <= 1 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
+  const int total = nj * nif;
+  const int nwarps = (total - 1 + 30) / 31;
+  dim3 grid((unsigned)((nwarps + 3) / 4), (unsigned)nk, (unsigned)nb);
+  k_sweep_x1<F><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il, nif, magic_u32(nif));
   return cudaGetLastError();
 }
 #else

@@ -42,6 +42,17 @@ ATHK_HD Real sqr(Real x) { return x * x; }
 ATHK_HD Real min_std(Real a, Real b) { return (b < a) ? b : a; }
 ATHK_HD Real max_std(Real a, Real b) { return (a < b) ? b : a; }
 
+// IEEE division a/b with a shortcut for an exactly-zero numerator: 0/b == 0*b (signed zero,
+// same bits) for every finite non-zero b.  Static uniform regions (v = 0, equal pressures) make
+// several HLLD/HLLC numerators exactly 0, which sends the GPU's FP64 division into its
+// ~100-instruction slow path; the shortcut returns the identical result in 3 instructions.
+ATHK_HD Real fdiv(Real a, Real b) {
+#if defined(__CUDA_ARCH__)
+  if (a == 0.0 && b != 0.0 && fabs(b) <= 1.7976931348623157e308) return a * b;
+#endif
+  return a / b;
+}
+
 struct EosParams {
   Real gamma, gm1, igm1;   // igm1 = 1.0/(gamma-1.0)
   Real dfloor, pfloor, sfloor;
@@ -119,7 +130,7 @@ ATHK_HD Real vl_slope(Real dwl, Real dwr) {
 //----------------------------------------------------------------------------------------
 // Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
 ATHK_HD Real ct_weight(Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
-  Real v_over_c = (1024.0) * dt * dflx / (dx * (rhol + rhor));
+  Real v_over_c = fdiv((1024.0) * dt * dflx, (dx * (rhol + rhor)));
   Real tmp_min = min_std(0.5, v_over_c);
   return 0.5 + max_std(-0.5, tmp_min);
 }
@@ -160,7 +171,7 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
   Real ml = wl[IDN] * vxl;
   Real mr = -(wr[IDN] * vxr);
 
-  Real am = (tl - tr) / (ml + mr);
+  Real am = fdiv((tl - tr), (ml + mr));
   Real cp = (ml * tr + mr * tl) / (ml + mr);
   cp = cp > 0.0 ? cp : 0.0;
 
@@ -181,12 +192,12 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
 
   Real sl, sr, sm;
   if (am >= 0.0) {
-    sl = am / (am - bm);
+    sl = fdiv(am, (am - bm));
     sr = 0.0;
     sm = -bm / (am - bm);
   } else {
     sl = 0.0;
-    sr = -am / (bp - am);
+    sr = fdiv(-am, (bp - am));
     sm = bp / (bp - am);
   }
 
@@ -262,7 +273,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   Real sdr = spd[4] - wr[IVX];
 
   // S_M, eq. 38
-  spd[2] = (sdr * ur.mx - sdl * ul.mx + (ptl - ptr)) / (sdr * ur.d - sdl * ul.d);
+  spd[2] = fdiv((sdr * ur.mx - sdl * ul.mx + (ptl - ptr)), (sdr * ur.d - sdl * ul.d));
 
   Real sdml = spd[0] - spd[2];
   Real sdmr = spd[4] - spd[2];
@@ -293,7 +304,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     ulst.by = ul.by;
     ulst.bz = ul.bz;
   } else {
-    Real tmp = bxi * (sdl - sdml) / (ul.d * sdl * sdml - bxsq);
+    Real tmp = fdiv(bxi * (sdl - sdml), (ul.d * sdl * sdml - bxsq));
     ulst.my = ulst.d * (wl[IVY] - ul.by * tmp);
     ulst.mz = ulst.d * (wl[IVZ] - ul.bz * tmp);
     tmp = (ul.d * sqr(sdl) - bxsq) / (ul.d * sdl * sdml - bxsq);
@@ -313,7 +324,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     urst.by = ur.by;
     urst.bz = ur.bz;
   } else {
-    Real tmp = bxi * (sdr - sdmr) / (ur.d * sdr * sdmr - bxsq);
+    Real tmp = fdiv(bxi * (sdr - sdmr), (ur.d * sdr * sdmr - bxsq));
     urst.my = urst.d * (wr[IVY] - ur.by * tmp);
     urst.mz = urst.d * (wr[IVZ] - ur.bz * tmp);
     tmp = (ur.d * sqr(sdr) - bxsq) / (ur.d * sdr * sdmr - bxsq);
@@ -351,7 +362,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
                    bxsig * sqrtdl * sqrtdr * ((urst.mz * urst_d_inv) - (ulst.mz * ulst_d_inv)));
   uldst.bz = urdst.bz = tmp;
 
-  tmp = spd[2] * bxi + (uldst.my * uldst.by + uldst.mz * uldst.bz) / uldst.d;
+  tmp = spd[2] * bxi + fdiv((uldst.my * uldst.by + uldst.mz * uldst.bz), uldst.d);
   uldst.e = ulst.e - sqrtdl * bxsig * (vbstl - tmp);
   urdst.e = urst.e + sqrtdr * bxsig * (vbstr - tmp);
 

@@ -118,7 +118,8 @@ ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsu
 #pragma unroll
   for (int n = 0; n < 5; ++n) {
     const idx_t o = ((idx_t)blk * 5 + n) * g.sn + c;
-    const Real un = h.u[o];
+    // load only what the stage's weights use (vl2 stage 2 never reads u, stage 1 never reads u1)
+    const Real un = (h.delta != 0.0 || !h.swap) ? h.u[o] : 0.0;
     Real u1n = h.u1_zero ? 0.0 : h.u1[o];
     if (h.delta != 0.0) u1n += h.delta * un;          // WeightedAve(u1,u,..,{1,delta,0,0,0})
     Real r;

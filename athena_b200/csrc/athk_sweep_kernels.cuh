@@ -66,8 +66,14 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
     const int buf = step % 3;
     Real f[7];
     idx_t c = 0;
+    const bool upd = fvalid && interior && n > n_s;   // this thread finishes cell n-1
+    Real dpre[5];
     if (fvalid) {
       c = (DIR == 1) ? gidx(g, k0, n, i) : gidx(g, n, j0, i);
+      if (upd) {   // issue the scratch loads now; they complete under the Riemann solve
+#pragma unroll
+        for (int v = 0; v < 5; ++v) dpre[v] = a.dflx[((idx_t)blk * 5 + vmap[v]) * g.sn + (c - s)];
+      }
       face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
       sF[buf][r][0][lane] = f[IDN];
       sF[buf][r][1][lane] = f[IVX];
@@ -76,17 +82,16 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
       sF[buf][r][4][lane] = f[IEN];
     }
     __syncthreads();
-    if (fvalid && interior && n > n_s) {
+    if (upd) {
       const Real(*below)[32] = (r > 0) ? sF[buf][r - 1] : sF[(step + 2) % 3][R - 1];
       const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
       const idx_t cc = c - s;   // cell n-1
       Real dsum[5];
 #pragma unroll
       for (int v = 0; v < 5; ++v) {
-        const idx_t oo = ((idx_t)blk * 5 + vmap[v]) * g.sn + cc;
-        Real d = a.dflx[oo];
+        Real d = dpre[v];
         d += (area * fcur[v] - area * below[v][lane]);
-        if (DIR == 1) a.dflx[oo] = d;
+        if (DIR == 1) a.dflx[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = d;
         else dsum[vmap[v]] = d;
       }
       if (DIR == 2) {
