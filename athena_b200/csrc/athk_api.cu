@@ -668,13 +668,6 @@ extern "C" int athk_history(athk_ctx *, double *, int) { return fail(ATHK_ERR_AR
 template <int ORDER, bool MHD>
 static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
   const Grid &g = c->g;
-  {   // x1: calculate_fluxes.cpp:68-76
-    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
-    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
-    SweepX1<ORDER, MHD> f = {a};
-    CU(launch_sweep_x1(c->stream, g.nb, r, f));
-    c->launches++;
-  }
 #ifndef ATHK_EMULATE
   // x2 columns (i,k) / x3 columns (i,j): CTA-marching tiles (athk_sweep_kernels.cuh);
   // extents of calculate_fluxes.cpp:176-182,299-302
@@ -698,6 +691,13 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
     CU(launch_points(c->stream, g.nb, r, f, 128));
   }
 #endif
+  {   // x1 last (calculate_fluxes.cpp:68-76): sums d1+d2+d3 and integrates
+    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
+    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
+    SweepX1<ORDER, MHD> f = {a};
+    CU(launch_sweep_x1(c->stream, g.nb, r, f));
+    c->launches++;
+  }
   return ATHK_OK;
 }
 
@@ -721,7 +721,8 @@ extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wg
   a.w = c->w; a.bcc = c->bcc; a.b = mhd ? c->b[0] : nullptr;
   a.flx[0] = a.flx[1] = a.flx[2] = nullptr;
   a.ef = c->ef; a.wct = c->wct;
-  a.dflx = c->flux[0];   // the x1-flux array doubles as the flux-divergence scratch
+  a.d2 = c->flux[1];   // the x2/x3 flux arrays double as the flux-divergence scratch terms
+  a.d3 = c->flux[2];
   a.dt = dt_mesh;
   HydroIntegrate &h = a.hi;
   h.u = c->u[0]; h.u1 = c->u[1];

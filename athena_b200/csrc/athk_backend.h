@@ -101,6 +101,7 @@ k_sweep_x1(const F f, const int kl, const int jl, const int nj, const int il, co
     const unsigned row = __umulhi(s, nif_magic);
     fi = (int)(s - row * (unsigned)nif);
     j = jl + (int)row;
+    if (lane < 31 && fi + 1 < nif && f.cell_active(k, j, il + fi)) f.prefetch_cell(blk, k, j, il + fi);
     f.compute(blk, k, j, il + fi, fl, lane < 31 || s == total - 1);
   }
   double fn[7];

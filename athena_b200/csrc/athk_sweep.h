@@ -41,7 +41,7 @@ struct SweepArgs {
   Real *flx[3];              // optional flux arrays (null = do not store)
   Real *ef;                  // [nb][6][sn]
   Real *wct;                 // [nb][3][sn]
-  Real *dflx;                // [nb][5][sn] scratch
+  Real *d2, *d3;             // [nb][5][sn] scratch: x2 / x3 terms of the flux divergence
   Real dt;                   // pmy_mesh->dt
   HydroIntegrate hi;
 };
@@ -159,17 +159,11 @@ struct SweepMarch {
                           ((DIR == 1) ? (k >= g.ks && k <= g.ke) : (j >= g.js && j <= g.je));
     const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
     const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
-    Real area = 0.0, vol = 0.0;
+    Real area = 0.0;
     if (interior) {
       const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
-      if (DIR == 1) {
-        const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
-        area = dx1 * dx3;                              // Face2Area
-      } else {
-        const Real dx2 = a.geo.dxf[1][blk * a.geo.PG + j];
-        area = dx1 * dx2;                              // Face3Area
-        vol = dx1 * dx2;                               // * dx3(k) below (CellVolume order)
-      }
+      if (DIR == 1) area = dx1 * a.geo.dxf[2][blk * a.geo.PG + k];   // Face2Area
+      else area = dx1 * a.geo.dxf[1][blk * a.geo.PG + j];            // Face3Area
     }
     Real qm[7], q0[7], qp[7], wl[7], wl_up[7], wr[7], f[7], fprev[5];
     load_q<DIR, MHD>(a, blk, c - s, qm);
@@ -189,21 +183,12 @@ struct SweepMarch {
       if (interior && n > n_s) {
         // cell n-1: (A F)(n) - (A F)(n-1)
         const idx_t cc = c - s;
-        Real dsum[5];
         const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
         const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
+        Real *dst = (DIR == 1) ? a.d2 : a.d3;
 #pragma unroll
-        for (int v = 0; v < 5; ++v) {
-          const idx_t o = ((idx_t)blk * 5 + vmap[v]) * g.sn + cc;
-          Real d = a.dflx[o];
-          d += (area * fcur[v] - area * fprev[v]);
-          if (DIR == 1) a.dflx[o] = d;
-          else dsum[vmap[v]] = d;
-        }
-        if (DIR == 2) {
-          const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + (n - 1)];
-          integrate_cell(a, blk, cc, dsum, vol * dx3);
-        }
+        for (int v = 0; v < 5; ++v)
+          dst[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = (area * fcur[v] - area * fprev[v]);
       }
       fprev[0] = f[IDN]; fprev[1] = f[IVX]; fprev[2] = f[IVY]; fprev[3] = f[IVZ]; fprev[4] = f[IEN];
 #pragma unroll
@@ -262,16 +247,43 @@ struct SweepX1 {
     }
     solve_face<0, MHD>(a, blk, c, i, wl, wr, f, store);
   }
-  // cell (k,j,i) of the active zone: dflx = A1*F(i+1) - A1*F(i)   (first term of the sum)
+  // cell (k,j,i) of the active zone.  The x1 sweep runs LAST: it forms
+  //   dflx = (A1 F(i+1) - A1 F(i)); dflx += d2; dflx += d3     (add_flux_divergence.cpp:57-83)
+  // from the x2/x3 sweeps' scratch terms and finishes the update (integrate_cell).
   ATHK_HD void store_d1(int blk, int k, int j, int i, const Real f[7], const Real fnext[7]) const {
     const Grid &g = a.g;
     const idx_t c = gidx(g, k, j, i);
-    const Real dx2 = a.geo.dxf[1][blk * a.geo.PG + j], dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
+    const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i], dx2 = a.geo.dxf[1][blk * a.geo.PG + j],
+               dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
     const Real area = dx2 * dx3;   // Face1Area
     const int src[5] = {IDN, IVX, IVY, IVZ, IEN};
+    Real dsum[5];
 #pragma unroll
-    for (int v = 0; v < 5; ++v)   // DIR=0: rotated index == variable index
-      a.dflx[((idx_t)blk * 5 + src[v]) * g.sn + c] = (area * fnext[src[v]] - area * f[src[v]]);
+    for (int v = 0; v < 5; ++v) {   // DIR=0: rotated index == variable index
+      const idx_t o = ((idx_t)blk * 5 + src[v]) * g.sn + c;
+      Real d = (area * fnext[src[v]] - area * f[src[v]]);
+      d += a.d2[o];
+      d += a.d3[o];
+      dsum[src[v]] = d;
+    }
+    integrate_cell(a, blk, c, dsum, dx1 * dx2 * dx3);
+  }
+  // L2 prefetch of what store_d1 will read (d2, d3 and the register it averages), issued before
+  // the Riemann solve: no registers held, and the final loads hit L2 instead of HBM.
+  ATHK_HD void prefetch_cell(int blk, int k, int j, int i) const {
+#if defined(__CUDA_ARCH__)
+    const Grid &g = a.g;
+    const idx_t c = gidx(g, k, j, i);
+    const HydroIntegrate &h = a.hi;
+    const Real *ureg = (h.delta != 0.0 || !h.swap) ? h.u : h.u1;
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const idx_t o = ((idx_t)blk * 5 + v) * g.sn + c;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d2 + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d3 + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ureg + o));
+    }
+#endif
   }
   ATHK_HD bool cell_active(int k, int j, int i) const {
     const Grid &g = a.g;

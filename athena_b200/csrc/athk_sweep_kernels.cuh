@@ -6,9 +6,11 @@
 // registers and drops to 8 warps/SM.  Here the CTA marches instead of the thread:
 //   CTA = 32 columns (lanes, consecutive i => coalesced rows) x R faces along the sweep.
 //   Each step every thread solves ONE face (no loop-carried registers), parks its 5 hydro fluxes
-//   in shared memory, and after one __syncthreads the thread owning cell n-1 forms
+//   in shared memory, and after one __syncthreads the thread owning cell n-1 stores
 //   (A F)(n) - (A F)(n-1) from its own flux and the row below (the previous step's top row for
-//   r == 0: triple-buffered, so one barrier per step suffices and no face is solved twice).
+//   r == 0: triple-buffered, so one barrier per step suffices and no face is solved twice)
+//   into the sweep's scratch term d2 / d3.  The x1 sweep (warp shuffles, no barrier) runs last,
+//   sums d1 + d2 + d3 in the reference's order and applies the integrator update.
 #ifndef ATHK_SWEEP_KERNELS_CUH_
 #define ATHK_SWEEP_KERNELS_CUH_
 
@@ -47,16 +49,12 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
   const int k0 = (DIR == 1) ? o : 0, j0 = (DIR == 1) ? 0 : o;
   const bool interior = colvalid && (i >= g.is && i <= g.ie) &&
                         ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
-  Real area = 0.0, vol12 = 0.0;
+  Real area = 0.0;
   if (interior) {
     const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
-    if (DIR == 1) {
-      area = dx1 * a.geo.dxf[2][blk * a.geo.PG + o];   // Face2Area = dx1f*dx3f
-    } else {
-      area = dx1 * a.geo.dxf[1][blk * a.geo.PG + o];   // Face3Area = dx1f*dx2f
-      vol12 = area;                                    // CellVolume = (dx1f*dx2f)*dx3f
-    }
+    area = dx1 * a.geo.dxf[(DIR == 1) ? 2 : 1][blk * a.geo.PG + o];   // Face2Area / Face3Area
   }
+  Real *dst = (DIR == 1) ? a.d2 : a.d3;
   const int nf = n_e + 1 - n_s + 1;            // faces n_s .. n_e+1
   const int nsteps = (nf + R - 1) / R;
   const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
@@ -66,14 +64,8 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
     const int buf = step % 3;
     Real f[7];
     idx_t c = 0;
-    const bool upd = fvalid && interior && n > n_s;   // this thread finishes cell n-1
-    Real dpre[5];
     if (fvalid) {
       c = (DIR == 1) ? gidx(g, k0, n, i) : gidx(g, n, j0, i);
-      if (upd) {   // issue the scratch loads now; they complete under the Riemann solve
-#pragma unroll
-        for (int v = 0; v < 5; ++v) dpre[v] = a.dflx[((idx_t)blk * 5 + vmap[v]) * g.sn + (c - s)];
-      }
       face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
       sF[buf][r][0][lane] = f[IDN];
       sF[buf][r][1][lane] = f[IVX];
@@ -82,22 +74,13 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
       sF[buf][r][4][lane] = f[IEN];
     }
     __syncthreads();
-    if (upd) {
+    if (fvalid && interior && n > n_s) {   // this thread owns cell n-1: pure store, no RMW
       const Real(*below)[32] = (r > 0) ? sF[buf][r - 1] : sF[(step + 2) % 3][R - 1];
       const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
-      const idx_t cc = c - s;   // cell n-1
-      Real dsum[5];
+      const idx_t cc = c - s;
 #pragma unroll
-      for (int v = 0; v < 5; ++v) {
-        Real d = dpre[v];
-        d += (area * fcur[v] - area * below[v][lane]);
-        if (DIR == 1) a.dflx[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = d;
-        else dsum[vmap[v]] = d;
-      }
-      if (DIR == 2) {
-        const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + (n - 1)];
-        integrate_cell(a, blk, cc, dsum, vol12 * dx3);
-      }
+      for (int v = 0; v < 5; ++v)
+        dst[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = (area * fcur[v] - area * below[v][lane]);
     }
   }
 }
