@@ -85,11 +85,12 @@ PROTOTYPES = {
     "athk_new_block_dt": (C.c_int, [_P, C.c_double, _D, _D]),
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_stage": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StageWghts), C.c_double]),
-    "athk_remote_configure": (C.c_int, [_P, C.c_int, _I, _I, _I, _I]),
-    "athk_remote_ghost_count": (C.c_longlong, [_P, C.c_int, C.c_int]),
-    "athk_remote_emf_count": (C.c_longlong, [_P, C.c_int]),
-    "athk_remote_set_buffers": (C.c_int, [_P, _D, _D, _LL, _D, _D, _LL]),
-    "athk_remote_pack_ghosts": (C.c_int, [_P, C.c_int, C.c_int]),
+    "athk_stage_phase": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(StageWghts), C.c_double]),
+    "athk_remote_ghost_count": (C.c_longlong, [_P, C.c_int, C.c_int, C.c_int]),
+    "athk_remote_emf_count": (C.c_longlong, [_P, C.c_int, C.c_int, C.c_int]),
+    "athk_remote_configure": (C.c_int, [_P, C.c_int, _I, _I, _I, _I, _LL, _LL, _LL, _LL]),
+    "athk_remote_set_buffers": (C.c_int, [_P, _P, _P, _P, _P]),
+    "athk_remote_pack_ghosts": (C.c_int, [_P, C.c_int]),
     "athk_remote_pack_emf": (C.c_int, [_P]),
 }
 

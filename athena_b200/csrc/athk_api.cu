@@ -61,7 +61,13 @@ struct athk_ctx {
   Real *r;          // [nb][ns][sn]
   Real *sflux[3];   // [nb][ns][sn]
   Real *emfbuf;     // [nb][sf.per_block]
-  Real *remfbuf;    // remote EMF surfaces
+  // remote (other-GPU) neighbour links
+  RemoteLinks rl;
+  int *rl_int;        // device [4][n]: lb,o1,o2,o3
+  idx_t *rl_off;      // device [5][n]: gsend,grecv,esend,erecv,ebase
+  std::vector<int> h_rl_int;
+  std::vector<idx_t> h_rl_off;
+  idx_t max_ghost_count, max_emf_count;
   Real *geo_store;  // 9 arrays [nb][PG]
   int *nbr;         // [nb][27]
   Real *dt_blocks;  // [nb]
@@ -130,7 +136,9 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->launches = 0;
   c->coords_set = c->nbr_set = false;
   c->nremote = 0;
-  c->remfbuf = nullptr;
+  memset(&c->rl, 0, sizeof(c->rl));
+  c->rl_int = nullptr; c->rl_off = nullptr;
+  c->max_ghost_count = c->max_emf_count = 0;
   CU(cudaStreamCreate(&c->stream));
   cudaStream_t st = c->stream;
   const int ns = cfg->nscalars;
@@ -177,6 +185,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
+  cudaFree(c->rl_int); cudaFree(c->rl_off);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -441,7 +450,7 @@ extern "C" int athk_recv_flux_correction(athk_ctx *c) {
   if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "recv_flux_correction: context is not MHD");
   const Grid &g = c->g;
   Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
-  EmfApplyPoint f = {g, c->sf, c->e, c->emfbuf, c->nbr, c->remfbuf};
+  EmfApplyPoint f = {g, c->sf, c->e, c->emfbuf, c->nbr, c->rl.erbuf, c->rl.ebase};
   LAUNCH(c, r, f);
   return ATHK_OK;
 }
@@ -557,19 +566,19 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
   if (what_mask & 1) {
     if (!c->u[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: u register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
-    GhostFillCC f = {g, 5, c->u[reg], c->nbr};
+    GhostFillCC f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
     LAUNCH(c, r, f);
   }
   if (what_mask & 2) {
     if (!c->cfg.mhd || !c->b[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: b register %d not allocated", reg);
     Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
-    GhostFillFC f = {g, c->b[reg], c->nbr};
+    GhostFillFC f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
     LAUNCH(c, r, f);
   }
   if (what_mask & 4) {
     if (!c->s[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: s register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
-    GhostFillCC f = {g, c->cfg.nscalars, c->s[reg], c->nbr};
+    GhostFillCC f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
     LAUNCH(c, r, f);
   }
   return ATHK_OK;
@@ -703,7 +712,16 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
 
 extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wghts *sw,
                           double dt_mesh) {
+  int rc = athk_stage_phase(c, 0, stage, order, sw, dt_mesh);
+  if (!rc) rc = athk_stage_phase(c, 1, stage, order, sw, dt_mesh);
+  if (!rc) rc = athk_stage_phase(c, 2, stage, order, sw, dt_mesh);
+  return rc;
+}
+
+extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
+                                const athk_stage_wghts *sw, double dt_mesh) {
   NEED_READY(c);
+  if (phase < 0 || phase > 2) return fail(ATHK_ERR_ARG, "stage_phase: phase must be 0, 1 or 2");
   if (!sw) return fail(ATHK_ERR_ARG, "stage: null weights");
   if (sw->gamma_3 != 0.0) return fail(ATHK_ERR_ARG, "stage: gamma_3 != 0 (3-register integrators) not implemented");
   if (order != 1 && order != 2) return fail(ATHK_ERR_ARG, "stage: xorder %d not implemented in the fused path", order);
@@ -716,48 +734,144 @@ extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wg
     const double w[5] = {sw->gamma_1, sw->gamma_2, 0.0, 0.0, 0.0};
     wa_mode(w, &wa);
   }
-  SweepArgs a;
-  a.g = g; a.eos = c->eos; a.geo = c->geo;
-  a.w = c->w; a.bcc = c->bcc; a.b = mhd ? c->b[0] : nullptr;
-  a.flx[0] = a.flx[1] = a.flx[2] = nullptr;
-  a.ef = c->ef; a.wct = c->wct;
-  a.d2 = c->flux[1];   // the x2/x3 flux arrays double as the flux-divergence scratch terms
-  a.d3 = c->flux[2];
-  a.dt = dt_mesh;
-  HydroIntegrate &h = a.hi;
-  h.u = c->u[0]; h.u1 = c->u[1];
-  h.u_out = swap ? c->u[1] : c->u[0];
-  h.u1_out = c->u[1];
-  h.delta = sw->delta; h.g1 = sw->gamma_1; h.g2 = sw->gamma_2;
-  h.wght = sw->beta * dt_mesh;
-  h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
   int rc;
-  if (order == 1) rc = mhd ? launch_sweeps<1, true>(c, a) : launch_sweeps<1, false>(c, a);
-  else rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
-  if (rc) return rc;
-  if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
-  if (mhd) {
-    if ((rc = athk_compute_corner_e(c))) return rc;
-    if ((rc = athk_send_flux_correction(c))) return rc;
-    if ((rc = athk_recv_flux_correction(c))) return rc;
-    FieldIntegrate fi;
-    fi.b = c->b[0]; fi.b1 = c->b[1];
-    fi.b_out = swap ? c->b[1] : c->b[0];
-    fi.b1_out = c->b[1];
-    fi.delta = sw->delta; fi.g1 = sw->gamma_1; fi.g2 = sw->gamma_2;
-    fi.wght = sw->beta * dt_mesh;
-    fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
-    Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
-    CTIntegratePoint f = {g, c->geo, c->e, fi};
-    LAUNCH(c, r, f);
-    if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
+  if (phase == 0) {
+    SweepArgs a;
+    a.g = g; a.eos = c->eos; a.geo = c->geo;
+    a.w = c->w; a.bcc = c->bcc; a.b = mhd ? c->b[0] : nullptr;
+    a.flx[0] = a.flx[1] = a.flx[2] = nullptr;
+    a.ef = c->ef; a.wct = c->wct;
+    a.d2 = c->flux[1];   // the x2/x3 flux arrays double as the flux-divergence scratch terms
+    a.d3 = c->flux[2];
+    a.dt = dt_mesh;
+    HydroIntegrate &h = a.hi;
+    h.u = c->u[0]; h.u1 = c->u[1];
+    h.u_out = swap ? c->u[1] : c->u[0];
+    h.u1_out = c->u[1];
+    h.delta = sw->delta; h.g1 = sw->gamma_1; h.g2 = sw->gamma_2;
+    h.wght = sw->beta * dt_mesh;
+    h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
+    if (order == 1) rc = mhd ? launch_sweeps<1, true>(c, a) : launch_sweeps<1, false>(c, a);
+    else rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
+    if (rc) return rc;
+    if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
+    if (mhd) {
+      if ((rc = athk_compute_corner_e(c))) return rc;
+      if ((rc = athk_send_flux_correction(c))) return rc;
+      if ((rc = athk_remote_pack_emf(c))) return rc;
+    }
+    return ATHK_OK;
+  }
+  if (phase == 1) {
+    if (mhd) {
+      if ((rc = athk_recv_flux_correction(c))) return rc;
+      FieldIntegrate fi;
+      fi.b = c->b[0]; fi.b1 = c->b[1];
+      fi.b_out = swap ? c->b[1] : c->b[0];
+      fi.b1_out = c->b[1];
+      fi.delta = sw->delta; fi.g1 = sw->gamma_1; fi.g2 = sw->gamma_2;
+      fi.wght = sw->beta * dt_mesh;
+      fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
+      Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+      CTIntegratePoint f = {g, c->geo, c->e, fi};
+      LAUNCH(c, r, f);
+      if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
+    }
+    return athk_remote_pack_ghosts(c, 0);
   }
   if ((rc = athk_exchange_ghosts(c, mhd ? 3 : 1, 0))) return rc;
   return athk_cons2prim(c, 0);
 }
-extern "C" int athk_remote_configure(athk_ctx *, int, const int *, const int *, const int *, const int *) { return fail(ATHK_ERR_ARG, "remote_configure: not implemented yet"); }
-extern "C" long long athk_remote_ghost_count(athk_ctx *, int, int) { return -1; }
-extern "C" long long athk_remote_emf_count(athk_ctx *, int) { return -1; }
-extern "C" int athk_remote_set_buffers(athk_ctx *, double *, double *, const long long *, double *, double *, const long long *) { return fail(ATHK_ERR_ARG, "remote_set_buffers: not implemented yet"); }
-extern "C" int athk_remote_pack_ghosts(athk_ctx *, int, int) { return fail(ATHK_ERR_ARG, "remote_pack_ghosts: not implemented yet"); }
-extern "C" int athk_remote_pack_emf(athk_ctx *) { return fail(ATHK_ERR_ARG, "remote_pack_emf: not implemented yet"); }
+//----------------------------------------------------------------------------------------
+// Remote links (neighbours that live on another GPU).  The transport itself (NCCL send/recv or
+// peer copies over NVLink) is done by the host framework between pack and unpack; this library
+// packs messages into / reads them from device buffers the caller owns.
+extern "C" long long athk_remote_ghost_count(athk_ctx *c, int ox1, int ox2, int ox3) {
+  if (!c) return -1;
+  return ghost_section_off(c->g, c->cfg.mhd != 0, c->cfg.nscalars, ox1, ox2, ox3, 5);
+}
+
+extern "C" long long athk_remote_emf_count(athk_ctx *c, int ox1, int ox2, int ox3) {
+  if (!c || !c->cfg.mhd) return 0;
+  int dir, od;
+  if (!emf_link_section(ox1, ox2, ox3, &dir, &od)) return 0;
+  return dir == 0 ? c->sf.n_x1() : (dir == 1 ? c->sf.n_x2() : c->sf.n_x3());
+}
+
+extern "C" int athk_remote_configure(athk_ctx *c, int nlinks, const int *lb, const int *ox1,
+                                     const int *ox2, const int *ox3,
+                                     const long long *ghost_send_off,
+                                     const long long *ghost_recv_off,
+                                     const long long *emf_send_off, const long long *emf_recv_off) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  if (nlinks < 0) return fail(ATHK_ERR_ARG, "remote_configure: nlinks < 0");
+  cudaFree(c->rl_int); cudaFree(c->rl_off);
+  c->rl_int = nullptr; c->rl_off = nullptr;
+  memset(&c->rl, 0, sizeof(c->rl));
+  c->max_ghost_count = c->max_emf_count = 0;
+  if (nlinks == 0) return ATHK_OK;
+  if (!lb || !ox1 || !ox2 || !ox3 || !ghost_send_off || !ghost_recv_off)
+    return fail(ATHK_ERR_ARG, "remote_configure: null array");
+  const size_t n = nlinks;
+  c->h_rl_int.assign(4 * n, 0);
+  c->h_rl_off.assign(5 * n, 0);
+  for (size_t q = 0; q < n; ++q) {
+    if (lb[q] < 0 || lb[q] >= c->g.nb) return fail(ATHK_ERR_ARG, "remote_configure: block out of range");
+    c->h_rl_int[q] = lb[q]; c->h_rl_int[n + q] = ox1[q];
+    c->h_rl_int[2 * n + q] = ox2[q]; c->h_rl_int[3 * n + q] = ox3[q];
+    c->h_rl_off[q] = ghost_send_off[q]; c->h_rl_off[n + q] = ghost_recv_off[q];
+    c->h_rl_off[2 * n + q] = emf_send_off ? emf_send_off[q] : 0;
+    c->h_rl_off[3 * n + q] = emf_recv_off ? emf_recv_off[q] : 0;
+    idx_t ebase = 0;
+    int dir, od;
+    if (c->cfg.mhd && emf_link_section(ox1[q], ox2[q], ox3[q], &dir, &od))
+      // the neighbour's side that faces this block: neighbour at -1 -> its outer side
+      ebase = c->h_rl_off[3 * n + q] - c->sf.face_off(dir, od < 0 ? 1 : 0);
+    c->h_rl_off[4 * n + q] = ebase;
+    const idx_t gc = athk_remote_ghost_count(c, ox1[q], ox2[q], ox3[q]);
+    const idx_t ec = athk_remote_emf_count(c, ox1[q], ox2[q], ox3[q]);
+    if (gc > c->max_ghost_count) c->max_ghost_count = gc;
+    if (ec > c->max_emf_count) c->max_emf_count = ec;
+  }
+  int rc = dev_alloc(&c->rl_int, 4 * n, c->stream);
+  if (!rc) rc = dev_alloc(&c->rl_off, 5 * n, c->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->rl_int, c->h_rl_int.data(), 4 * n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->rl_off, c->h_rl_off.data(), 5 * n * sizeof(idx_t), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->rl.n = nlinks;
+  c->rl.lb = c->rl_int; c->rl.o1 = c->rl_int + n; c->rl.o2 = c->rl_int + 2 * n; c->rl.o3 = c->rl_int + 3 * n;
+  c->rl.gsend = c->rl_off; c->rl.grecv = c->rl_off + n; c->rl.esend = c->rl_off + 2 * n;
+  c->rl.erecv = c->rl_off + 3 * n; c->rl.ebase = c->rl_off + 4 * n;
+  return ATHK_OK;
+}
+
+extern "C" int athk_remote_set_buffers(athk_ctx *c, double *send_ghost, double *recv_ghost,
+                                       double *send_emf, double *recv_emf) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  c->rl.gsbuf = send_ghost; c->rl.grbuf = recv_ghost;
+  c->rl.esbuf = send_emf; c->rl.erbuf = recv_emf;
+  return ATHK_OK;
+}
+
+extern "C" int athk_remote_pack_ghosts(athk_ctx *c, int reg) {
+  NEED_READY(c);
+  if (c->rl.n == 0) return ATHK_OK;
+  if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "remote_pack_ghosts: register %d not allocated", reg);
+  if (!c->rl.gsbuf) return fail(ATHK_ERR_STATE, "remote_pack_ghosts: call athk_remote_set_buffers first");
+  RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, c->rl, c->u[reg],
+                       c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr};
+  CU(launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
+  c->launches++;
+  return ATHK_OK;
+}
+
+extern "C" int athk_remote_pack_emf(athk_ctx *c) {
+  NEED_READY(c);
+  if (c->rl.n == 0 || !c->cfg.mhd) return ATHK_OK;
+  if (!c->rl.esbuf) return fail(ATHK_ERR_STATE, "remote_pack_emf: call athk_remote_set_buffers first");
+  RemoteEmfPack f = {c->sf, c->rl, c->emfbuf};
+  CU(launch_links(c->stream, c->rl.n, c->max_emf_count, f));
+  c->launches++;
+  return ATHK_OK;
+}

@@ -121,7 +121,26 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
   k_sweep_x1<F><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il, nif, magic_u32(nif));
   return cudaGetLastError();
 }
+// (link, element) launcher for the variable-length remote messages
+template <class F>
+__global__ void __launch_bounds__(256) k_links(const F f, const long long maxcount) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < maxcount) f((int)blockIdx.y, e);
+}
+template <class F>
+static inline cudaError_t launch_links(cudaStream_t st, int nlinks, long long maxcount, const F &f) {
+  if (nlinks <= 0 || maxcount <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((maxcount + 255) / 256), (unsigned)nlinks);
+  k_links<F><<<grid, 256, 0, st>>>(f, maxcount);
+  return cudaGetLastError();
+}
 #else
+template <class F>
+static inline cudaError_t launch_links(cudaStream_t, int nlinks, long long maxcount, const F &f) {
+  for (int l = 0; l < nlinks; ++l)
+    for (long long e = 0; e < maxcount; ++e) f(l, e);
+  return 0;
+}
 template <class F>
 static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, const F &f,
                                         int = 256) {

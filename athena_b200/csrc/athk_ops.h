@@ -290,18 +290,19 @@ struct EmfPackPoint {
 
 // SetFluxBoundarySameLevel (+=) followed by AverageFluxBoundary, per boundary edge point.
 // Accumulation order = neighbour enumeration order of bvals_base.cpp:326-372: faces (x1,x2,x3),
-// then edges.  Remote neighbours (<= -2) read from rbuf, a buffer with the same section layout
-// filled by the inter-GPU transport.
+// then edges.  Remote neighbours (<= -2) read the received message of their link; it holds the
+// one face section this kernel indexes for that neighbour (see emf_link_section).
 struct EmfApplyPoint {
   Grid g;
   EmfSurf sf;
   Real *e;
   const Real *buf;       // local blocks' packed surfaces
   const int *nbr;        // [nb][27]
-  const Real *rbuf;      // remote surfaces [nremote][per_block] (may be null)
+  const Real *rbuf;      // received EMF messages of remote links (may be null)
+  const idx_t *rbase;    // [nlinks] message offset minus the face-section offset it stands for
   ATHK_HD const Real *surf_of(int id) const {
     if (id >= 0) return buf + (idx_t)id * sf.per_block();
-    return rbuf + (idx_t)(-id - 2) * sf.per_block();
+    return rbuf + rbase[-id - 2];
   }
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const int a = (i == g.is) ? -1 : (i == g.ie + 1 ? 1 : 0);
@@ -490,36 +491,183 @@ struct CTPoint {
 };
 
 //========================================================================================
-// Same-level ghost fill for neighbours on the same GPU: the ghost zone reads straight from
-// the neighbour block's active zone (what LoadBoundaryBufferSameLevel + CopyVariableBuffer
-// SameProcess + SetBoundarySameLevel move through a staging buffer; bvals_cc.cpp:287-302,
-// 386-420, bvals_var.cpp:108-119).  Launched over the full box k in [0,nc3-1] etc.
+// Slab geometry of one same-level boundary message (bvals_cc.cpp:287-302,386-420 for cell-
+// centred data, bvals_fc.cpp:344-397,583-680 for face fields).  For neighbour offset o along a
+// direction: dim = extent, ss = first index the sender packs, rs = first ghost index the
+// receiver fills.  A face field has nx+1 entries along its own direction and the shared face
+// is neither sent nor overwritten (bvals_fc.cpp:591-593).
+struct Slab {
+  int d1, d2, d3;      // extents (i,j,k)
+  int s1, s2, s3;      // sender start
+  int r1, r2, r3;      // receiver start
+  ATHK_HD idx_t count() const { return (idx_t)d1 * d2 * d3; }
+};
+
+ATHK_HD void slab_axis(int o, int s, int e, int nx, int ng, bool own_dir, int *d, int *ss, int *rs) {
+  if (o == 0) { *d = nx + (own_dir ? 1 : 0); *ss = s; *rs = s; }
+  else if (o > 0) { *d = ng; *ss = e - ng + 1; *rs = e + (own_dir ? 2 : 1); }
+  else { *d = ng; *ss = s + (own_dir ? 1 : 0); *rs = s - ng; }
+}
+
+// comp < 0: cell-centred; comp = 0,1,2: face field x1f,x2f,x3f
+ATHK_HD Slab make_slab(const Grid &g, int comp, int o1, int o2, int o3) {
+  Slab sl;
+  slab_axis(o1, g.is, g.ie, g.nx1, g.ng, comp == 0, &sl.d1, &sl.s1, &sl.r1);
+  slab_axis(o2, g.js, g.je, g.nx2, g.ng, comp == 1, &sl.d2, &sl.s2, &sl.r2);
+  slab_axis(o3, g.ks, g.ke, g.nx3, g.ng, comp == 2, &sl.d3, &sl.s3, &sl.r3);
+  return sl;
+}
+
+// one link = (local block, neighbour offset) whose neighbour lives on another GPU.  Messages of
+// all links are concatenated in per-peer send / receive buffers; the element layout of one ghost
+// message is [u: nvar_u][x1f][x2f][x3f][s: nvar_s], each section dense (k,j,i).
+struct RemoteLinks {
+  int n;
+  const int *lb, *o1, *o2, *o3;          // [n]
+  const idx_t *gsend, *grecv;            // [n] element offsets of the ghost message
+  const idx_t *esend, *erecv;            // [n] element offsets of the EMF message
+  const idx_t *ebase;                    // [n] erecv - face_off(dir,side) the apply kernel expects
+  Real *gsbuf;                           // ghost send buffer
+  const Real *grbuf;                     // ghost receive buffer
+  Real *esbuf;
+  const Real *erbuf;
+};
+
+ATHK_HD idx_t ghost_section_off(const Grid &g, bool mhd, int nscal, int o1, int o2, int o3,
+                                int section /*0 u, 1..3 faces, 4 scalars, 5 = total*/) {
+  idx_t off = 0;
+  if (section == 0) return off;
+  off += 5 * make_slab(g, -1, o1, o2, o3).count();
+  for (int d = 0; d < 3; ++d) {
+    if (section == 1 + d) return off;
+    if (mhd) off += make_slab(g, d, o1, o2, o3).count();
+  }
+  if (section == 4) return off;
+  off += (idx_t)nscal * make_slab(g, -1, o1, o2, o3).count();
+  return off;
+}
+
+// LoadBoundaryBufferSameLevel for every remote link: one thread per message element
+struct RemoteGhostPack {
+  Grid g;
+  int mhd, nscal;
+  RemoteLinks rl;
+  const Real *u, *b, *s;
+  // (link, e): e = element index inside the link's message
+  ATHK_HD void operator()(int link, idx_t e) const {
+    const int o1 = rl.o1[link], o2 = rl.o2[link], o3 = rl.o3[link], blk = rl.lb[link];
+    Real *dst = rl.gsbuf + rl.gsend[link] + e;
+    const Slab cc = make_slab(g, -1, o1, o2, o3);
+    idx_t base = 0;
+    const idx_t ncc = cc.count();
+    if (e < 5 * ncc) {
+      const int n = (int)(e / ncc);
+      idx_t q = e - n * ncc;
+      const int li = (int)(q % cc.d1); q /= cc.d1;
+      const int lj = (int)(q % cc.d2);
+      const int lk = (int)(q / cc.d2);
+      *dst = u[((idx_t)blk * 5 + n) * g.sn + gidx(g, cc.s3 + lk, cc.s2 + lj, cc.s1 + li)];
+      return;
+    }
+    base = 5 * ncc;
+    if (mhd) {
+      for (int d = 0; d < 3; ++d) {
+        const Slab f = make_slab(g, d, o1, o2, o3);
+        const idx_t nf = f.count();
+        if (e < base + nf) {
+          idx_t q = e - base;
+          const int li = (int)(q % f.d1); q /= f.d1;
+          const int lj = (int)(q % f.d2);
+          const int lk = (int)(q / f.d2);
+          *dst = b[((idx_t)blk * 3 + d) * g.sn + gidx(g, f.s3 + lk, f.s2 + lj, f.s1 + li)];
+          return;
+        }
+        base += nf;
+      }
+    }
+    if (nscal > 0 && e < base + nscal * ncc) {
+      idx_t q = e - base;
+      const int n = (int)(q / ncc);
+      q -= n * ncc;
+      const int li = (int)(q % cc.d1); q /= cc.d1;
+      const int lj = (int)(q % cc.d2);
+      const int lk = (int)(q / cc.d2);
+      *dst = s[((idx_t)blk * nscal + n) * g.sn + gidx(g, cc.s3 + lk, cc.s2 + lj, cc.s1 + li)];
+    }
+  }
+};
+
+// EMF message of a remote link: the packed face section the receiver's EmfApplyPoint indexes
+// (face links: that face; x1x2 / x1x3 edge links: the X1 face section; x2x3 edges: X2 section)
+ATHK_HD bool emf_link_section(int o1, int o2, int o3, int *dir, int *o_dir) {
+  const int nz = (o1 != 0) + (o2 != 0) + (o3 != 0);
+  if (nz == 3 || nz == 0) return false;   // corners exchange no EMF
+  if (o1 != 0) { *dir = 0; *o_dir = o1; }
+  else if (o2 != 0) { *dir = 1; *o_dir = o2; }
+  else { *dir = 2; *o_dir = o3; }
+  return true;
+}
+
+struct RemoteEmfPack {
+  EmfSurf sf;
+  RemoteLinks rl;
+  const Real *buf;   // local packed surfaces [nb][per_block]
+  ATHK_HD void operator()(int link, idx_t e) const {
+    int dir, od;
+    if (!emf_link_section(rl.o1[link], rl.o2[link], rl.o3[link], &dir, &od)) return;
+    const idx_t n = (dir == 0) ? sf.n_x1() : (dir == 1 ? sf.n_x2() : sf.n_x3());
+    if (e >= n) return;
+    // my boundary facing the neighbour: neighbour at +1 -> my outer side
+    rl.esbuf[rl.esend[link] + e] =
+        buf[(idx_t)rl.lb[link] * sf.per_block() + sf.face_off(dir, od > 0 ? 1 : 0) + e];
+  }
+};
+
+//========================================================================================
+// Same-level ghost fill.  Neighbour on the same GPU: the ghost zone reads straight from the
+// neighbour block's active zone (what LoadBoundaryBufferSameLevel + CopyVariableBufferSame
+// Process + SetBoundarySameLevel move through a staging buffer; bvals_cc.cpp:287-302,386-420,
+// bvals_var.cpp:108-119).  Neighbour on another GPU (table entry <= -2): read the received
+// message.  Launched over the full box k in [0,nc3-1] etc.
 struct GhostFillCC {
   Grid g;
   int nvar;
   Real *u;          // [nb][nvar][sn]
   const int *nbr;
+  int mhd, nscal, section;   // section 0 = hydro u, 4 = scalars (remote message layout)
+  RemoteLinks rl;
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const int o1 = (i < g.is) ? -1 : (i > g.ie ? 1 : 0);
     const int o2 = (j < g.js) ? -1 : (j > g.je ? 1 : 0);
     const int o3 = (k < g.ks) ? -1 : (k > g.ke ? 1 : 0);
     if (o1 == 0 && o2 == 0 && o3 == 0) return;
     const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
-    if (id < 0) return;   // physical boundary or remote neighbour (unpacked separately)
+    if (id == -1) return;   // physical boundary
     const idx_t dst = gidx(g, k, j, i);
-    const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
-    for (int n = 0; n < nvar; ++n)
-      u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
+    if (id >= 0) {
+      const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
+      for (int n = 0; n < nvar; ++n)
+        u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
+    } else {
+      const int link = -id - 2;
+      const Slab cc = make_slab(g, -1, o1, o2, o3);
+      const idx_t e = ((idx_t)(k - cc.r3) * cc.d2 + (j - cc.r2)) * cc.d1 + (i - cc.r1);
+      const Real *src = rl.grbuf + rl.grecv[link] +
+                        ghost_section_off(g, mhd != 0, nscal, o1, o2, o3, section) + e;
+      const idx_t ncc = cc.count();
+      for (int n = 0; n < nvar; ++n) u[((idx_t)blk * nvar + n) * g.sn + dst] = src[n * ncc];
+    }
   }
 };
 
-// Face-centred version (bvals_fc.cpp:344-397 load, 583-680 set): along its own direction a
-// face array has nc+1 entries and the shared face [s] / [e+1] is NOT overwritten (:591-593).
+// Face-centred version (bvals_fc.cpp:344-397 load, 583-680 set).
 // Launched over k in [0,nc3], j in [0,nc2], i in [0,nc1].
 struct GhostFillFC {
   Grid g;
   Real *b;          // [nb][3][sn]
   const int *nbr;
+  int nscal;
+  RemoteLinks rl;
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -532,10 +680,18 @@ struct GhostFillFC {
       const int o3 = (k < g.ks) ? -1 : (k > g.ke + (d == 2 ? 1 : 0) ? 1 : 0);
       if (o1 == 0 && o2 == 0 && o3 == 0) continue;
       const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
-      if (id < 0) continue;
+      if (id == -1) continue;
       const idx_t dst = gidx(g, k, j, i);
-      const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
-      b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
+      if (id >= 0) {
+        const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
+        b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
+      } else {
+        const int link = -id - 2;
+        const Slab f = make_slab(g, d, o1, o2, o3);
+        const idx_t e = ((idx_t)(k - f.r3) * f.d2 + (j - f.r2)) * f.d1 + (i - f.r1);
+        b[((idx_t)blk * 3 + d) * g.sn + dst] =
+            rl.grbuf[rl.grecv[link] + ghost_section_off(g, true, nscal, o1, o2, o3, 1 + d) + e];
+      }
     }
   }
 };

@@ -1,0 +1,122 @@
+"""Inter-GPU boundary exchange for MeshBlocks partitioned across ranks (one process per GPU).
+
+Mirrors the rank-crossing half of the reference's BoundaryVariable machinery
+(/root/reference/src/bvals/bvals_var.cpp:212-262 Send/ReceiveBoundaryBuffers, cc/bvals_cc.cpp:
+614-663 persistent MPI requests, fc/flux_correction_fc.cpp:623-654,1610-1749 EMF correction):
+every (block, neighbour) pair whose neighbour lives on another rank is a "remote link".  Where
+the reference posts one MPI message per link, all links towards the same peer are coalesced here
+into ONE message per peer and quantity (ghost zones of u+b; EMF surfaces), packed by a single
+kernel launch and moved with NCCL send/recv over NVLink (torch.distributed is the plumbing; gloo
+on CPU tensors for the world_size-2 tests).  There is no collective on the data path: the only
+reduction is the global min of dt (Mesh::NewTimeStep, mesh.cpp:1263).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _slot(o):
+    return (o[2] + 1) * 9 + (o[1] + 1) * 3 + (o[0] + 1)
+
+
+class RemoteExchange:
+    def __init__(self, ctx, rank, world, device, stream=None):
+        self.ctx = ctx
+        self.rank = rank
+        self.world = world
+        self.stream = stream
+        lib, h = ctx.lib, ctx.h
+        links = ctx.remote          # [(lb, (o1,o2,o3), remote gid, remote rank)], index = link id
+        n = len(links)
+        self.nlinks = n
+        gcount = [lib.athk_remote_ghost_count(h, *l[1]) for l in links]
+        ecount = [lib.athk_remote_emf_count(h, *l[1]) for l in links]
+        peers = sorted(set(l[3] for l in links))
+        self.peers = peers
+        gs = np.zeros(n, dtype=np.int64)
+        gr = np.zeros(n, dtype=np.int64)
+        es = np.zeros(n, dtype=np.int64)
+        er = np.zeros(n, dtype=np.int64)
+        self.gseg, self.eseg = {}, {}   # peer -> (send start, send end, recv start, recv end)
+        g_s = g_r = e_s = e_r = 0
+        for p in peers:
+            mine = [q for q in range(n) if links[q][3] == p]
+            # canonical order of messages between two ranks: (receiver's block gid, offset as the
+            # receiver sees it).  Sender side: receiver block = remote gid, offset = -ox.
+            send_order = sorted(mine, key=lambda q: (links[q][2], _slot(tuple(-x for x in links[q][1]))))
+            recv_order = sorted(mine, key=lambda q: (ctx.gids[links[q][0]], _slot(links[q][1])))
+            gs0, gr0, es0, er0 = g_s, g_r, e_s, e_r
+            for q in send_order:
+                gs[q] = g_s
+                g_s += gcount[q]
+                es[q] = e_s
+                e_s += ecount[q]
+            for q in recv_order:
+                gr[q] = g_r
+                g_r += gcount[q]
+                er[q] = e_r
+                e_r += ecount[q]
+            self.gseg[p] = (gs0, g_s, gr0, g_r)
+            self.eseg[p] = (es0, e_s, er0, e_r)
+        kw = dict(dtype=torch.float64, device=device)
+        self.gsbuf = torch.zeros(max(g_s, 1), **kw)
+        self.grbuf = torch.zeros(max(g_r, 1), **kw)
+        self.esbuf = torch.zeros(max(e_s, 1), **kw)
+        self.erbuf = torch.zeros(max(e_r, 1), **kw)
+        self.ghost_bytes = 8 * g_s
+        self.emf_bytes = 8 * e_s
+        ia = lambda v: np.ascontiguousarray(v, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int))   # noqa: E731
+        la = lambda v: v.ctypes.data_as(C.POINTER(C.c_longlong))                                      # noqa: E731
+        lb = [l[0] for l in links]
+        o1 = [l[1][0] for l in links]
+        o2 = [l[1][1] for l in links]
+        o3 = [l[1][2] for l in links]
+        self._keep = (gs, gr, es, er)
+        ctx.call("athk_remote_configure", n, ia(lb), ia(o1), ia(o2), ia(o3), la(gs), la(gr), la(es), la(er))
+        ctx.call("athk_remote_set_buffers", self.gsbuf.data_ptr(), self.grbuf.data_ptr(),
+                 self.esbuf.data_ptr(), self.erbuf.data_ptr())
+
+    def _exchange(self, sbuf, rbuf, seg):
+        if not self.peers:
+            return
+        ops = []
+        for p in self.peers:
+            s0, s1, r0, r1 = seg[p]
+            if s1 > s0:
+                ops.append(dist.P2POp(dist.isend, sbuf[s0:s1], p))
+            if r1 > r0:
+                ops.append(dist.P2POp(dist.irecv, rbuf[r0:r1], p))
+        if not ops:
+            return
+        if self.stream is not None:
+            # NCCL work is ordered after the pack kernels on the context's stream, and the stream
+            # waits for the transfers before the unpack kernels that follow
+            with torch.cuda.stream(self.stream):
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def exchange_ghosts(self):
+        self._exchange(self.gsbuf, self.grbuf, self.gseg)
+
+    def exchange_emf(self):
+        if self.ctx.mhd:
+            self._exchange(self.esbuf, self.erbuf, self.eseg)
+
+
+def attach(ctx, rank, world, device="cuda", stream=None):
+    """Create the exchange object for a context whose neighbour table has remote links."""
+    ctx.xch = RemoteExchange(ctx, rank, world, device, stream)
+    return ctx.xch
+
+
+def reduce_min_fn(device):
+    def f(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+    return f

@@ -234,10 +234,17 @@ class TimeIntegrator:
 
     # Mesh::Initialize after the problem generator (mesh.cpp:1686-1965)
     def initialize(self, tlim=None, reduce_min=None):
+        self.refresh_ghosts_and_primitives()
+        self.new_time_step(tlim, reduce_min)
+
+    def refresh_ghosts_and_primitives(self):
         c = self.ctx
+        xch = getattr(c, "xch", None)
+        if xch is not None:   # neighbours on other GPUs: pack, send/recv, then fill
+            c.call("athk_remote_pack_ghosts", 0)
+            xch.exchange_ghosts()
         c.call("athk_exchange_ghosts", 1 | (2 if c.mhd else 0) | (4 if c.nscalars else 0), 0)
         c.call("athk_cons2prim", 0)
-        self.new_time_step(tlim, reduce_min)
 
     def new_block_dt(self):
         m = C.c_double()
@@ -261,9 +268,17 @@ class TimeIntegrator:
         dt = self.dt
         mhd = c.mhd
         order = 1 if (self.integrator == "vl2" and stage == 1) else self.xorder
+        xch = getattr(c, "xch", None)
         if self.fused:
             sw = capi.StageWghts(delta, g1, g2, g3, beta)
-            c.call("athk_stage", stage, order, C.byref(sw), dt)
+            if xch is None:
+                c.call("athk_stage", stage, order, C.byref(sw), dt)
+            else:
+                c.call("athk_stage_phase", 0, stage, order, C.byref(sw), dt)
+                xch.exchange_emf()
+                c.call("athk_stage_phase", 1, stage, order, C.byref(sw), dt)
+                xch.exchange_ghosts()
+                c.call("athk_stage_phase", 2, stage, order, C.byref(sw), dt)
             return
         if stage == 1:   # StartupTaskList, time_integrator.cpp:1608-1619
             c.call("athk_zero_register", 0, 1)
@@ -275,6 +290,9 @@ class TimeIntegrator:
         if mhd:
             c.call("athk_compute_corner_e")          # CALC_FLDFLX
             c.call("athk_send_flux_correction")      # SEND_FLDFLX
+            if xch is not None:
+                c.call("athk_remote_pack_emf")
+                xch.exchange_emf()
             c.call("athk_recv_flux_correction")      # RECV_FLDFLX
         # INT_HYD (time_integrator.cpp:1797-1847)
         w1 = (C.c_double * 5)(1.0, delta, 0.0, 0.0, 0.0)
@@ -294,6 +312,9 @@ class TimeIntegrator:
                 c.call("athk_weighted_ave_fc", 0, 1, 2, w2)
             c.call("athk_ct", beta * dt, 0)
         # SEND/RECV/SETB_HYD, _FLD ; CONS2PRIM
+        if xch is not None:
+            c.call("athk_remote_pack_ghosts", 0)
+            xch.exchange_ghosts()
         c.call("athk_exchange_ghosts", 1 | (2 if mhd else 0), 0)
         c.call("athk_cons2prim", 0)
 

@@ -210,9 +210,10 @@ def run_ours(args):
     gamma = 1.666666666667
     ctx = pyhost.Context(mesh, True, gamma, device=local_rank, gids=gids, rank_of=rank_of,
                          my_rank=rank, lib=lib)
+    stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
     if world > 1:
         from athena_b200 import multigpu
-        multigpu.attach(ctx, dist, rank, world)
+        multigpu.attach(ctx, rank, world, device="cuda", stream=stream)
 
     # ---- synthetic ICs on the host (pinned), reference pgen formulas --------------------------
     nb = len(gids)
@@ -241,16 +242,10 @@ def run_ours(args):
         ctx.sync()
 
     h2d()
-    reduce_min = None
-    if world > 1:
-        def reduce_min(x):
-            t = torch.tensor([x], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            return float(t.item())
+    reduce_min = multigpu.reduce_min_fn("cuda") if world > 1 else None
     ti = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=not args.unfused)
     ti.initialize(reduce_min=reduce_min)
 
-    stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
     zones = args.per_gpu ** 3 * world
 
     def barrier():
@@ -317,8 +312,7 @@ def run_ours(args):
         h2d()
         # the state came from the host: redo the start-of-cycle exchange + W(U) the way
         # Mesh::Initialize does after a restart, then one full cycle, then read everything back
-        ctx.call("athk_exchange_ghosts", 3, 0)
-        ctx.call("athk_cons2prim", 0)
+        ti.refresh_ghosts_and_primitives()
         ti.step(reduce_min=reduce_min)
         d2h()
     d2h()   # make the host copy the current state so that repeated e2e steps stay physical

@@ -162,17 +162,34 @@ typedef struct athk_stage_wghts {
 } athk_stage_wghts;
 int athk_stage(athk_ctx *ctx, int stage, int order, const athk_stage_wghts *sw, double dt_mesh);
 
-/* ---- multi-GPU surface exchange (buffers packed per remote neighbour slot) ---------------- */
-/* Sizes (doubles) of one remote ghost message for the given quantity mask and offsets, and of
- * one remote EMF message; pack into / unpack from device buffers owned by the caller. */
-int athk_remote_configure(athk_ctx *ctx, int nremote, const int *lb, const int *ox1,
-                          const int *ox2, const int *ox3);
-long long athk_remote_ghost_count(athk_ctx *ctx, int slot, int what_mask);
-long long athk_remote_emf_count(athk_ctx *ctx, int slot);
+/* The same stage split at the two points where data of other GPUs is needed, so that the host
+ * can run the transport (NCCL send/recv over NVLink) in between:
+ *   phase 0: sweeps, corner E, pack EMF surfaces (local + remote links)      -> send/recv EMF
+ *   phase 1: EMF correction, CT, pack ghost messages of remote links         -> send/recv ghosts
+ *   phase 2: ghost fill (local neighbours + received messages), W(U)
+ * athk_stage == phases 0,1,2 back to back (single GPU, or no remote links). */
+int athk_stage_phase(athk_ctx *ctx, int phase, int stage, int order, const athk_stage_wghts *sw,
+                     double dt_mesh);
+
+/* ---- multi-GPU: neighbours on another GPU ("remote links") ---------------------------------
+ * BoundaryVariable::SendBoundaryBuffers / ReceiveBoundaryBuffers across ranks (bvals_var.cpp:
+ * 212-262; MPI persistent requests in the reference, bvals_cc.cpp:614-663).  A link is
+ * (local block lb, neighbour offset ox1..3); entry -(2+link) in the neighbour table refers to it.
+ * The caller owns four device buffers (ghost send/recv, EMF send/recv) and assigns every link an
+ * element offset in each, normally grouping links per peer rank so that one message per peer and
+ * quantity crosses NVLink.  Message sizes: */
+long long athk_remote_ghost_count(athk_ctx *ctx, int ox1, int ox2, int ox3); /* u (+b) (+s) slab */
+long long athk_remote_emf_count(athk_ctx *ctx, int ox1, int ox2, int ox3);   /* 0 for corners   */
+int athk_remote_configure(athk_ctx *ctx, int nlinks, const int *lb, const int *ox1,
+                          const int *ox2, const int *ox3, const long long *ghost_send_off,
+                          const long long *ghost_recv_off, const long long *emf_send_off,
+                          const long long *emf_recv_off);
 int athk_remote_set_buffers(athk_ctx *ctx, double *send_ghost, double *recv_ghost,
-                            const long long *ghost_off, double *send_emf, double *recv_emf,
-                            const long long *emf_off);
-int athk_remote_pack_ghosts(athk_ctx *ctx, int what_mask, int reg);
+                            double *send_emf, double *recv_emf);
+/* LoadBoundaryBufferSameLevel for every remote link (cc/bvals_cc.cpp:287, fc/bvals_fc.cpp:344) */
+int athk_remote_pack_ghosts(athk_ctx *ctx, int reg);
+/* LoadFluxBoundaryBufferSameLevel for every remote link (fc/flux_correction_fc.cpp:51);
+ * call after athk_send_flux_correction */
 int athk_remote_pack_emf(athk_ctx *ctx);
 
 #ifdef __cplusplus

@@ -1,0 +1,60 @@
+"""Run under torchrun on N GPUs: golden case split across ranks (NCCL), fields must match the
+reference bit for bit.  usage: torchrun --nproc-per-node N tools/multi_check.py [case] [--unfused]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import util  # noqa: E402
+from athena_b200 import capi, multigpu, pyhost  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "mhd_linwave_vl2_plm_hlld"
+fused = "--unfused" not in sys.argv
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+lib = capi.load()
+meta, z = util.load_golden(name)
+mesh = pyhost.UniformMesh(meta["mesh"], meta["block"], meta["xmin"], meta["xmax"], ng=meta["ng"])
+nb = mesh.nbtotal
+per = nb // world
+parts = [list(range(r * per, (r + 1) * per if r < world - 1 else nb)) for r in range(world)]
+rank_of = {g: r for r, gl in enumerate(parts) for g in gl}
+mhd = meta["mhd"]
+ctx = pyhost.Context(mesh, mhd, meta["gamma"], device=lr, gids=parts[rank], rank_of=rank_of, my_rank=rank, lib=lib)
+stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
+multigpu.attach(ctx, rank, world, device="cuda", stream=stream)
+B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
+blocks = util.split_to_blocks(mesh, z["u0"], *B)
+for lb, g in enumerate(ctx.gids):
+    ctx.upload("U", lb, blocks[g]["u"])
+    if mhd:
+        ctx.upload("B_X1F", lb, blocks[g]["b1"])
+        ctx.upload("B_X2F", lb, blocks[g]["b2"])
+        ctx.upload("B_X3F", lb, blocks[g]["b3"])
+rmin = multigpu.reduce_min_fn("cuda")
+ti = pyhost.TimeIntegrator(ctx, meta["integrator"], meta["xorder"], meta["cfl"], fused=fused)
+ti.initialize(tlim=meta["tlim"], reduce_min=rmin)
+while ti.time < meta["tlim"]:
+    ti.step(meta["tlim"], reduce_min=rmin)
+ok = ti.ncycle == meta["ncycle"] and ti.dt == meta["dt_final"]
+ng = meta["ng"]
+nx1, nx2, nx3 = mesh.block_nx
+for lb, g in enumerate(ctx.gids):
+    l1, l2, l3 = mesh.loc[g]
+    o1, o2, o3 = l1 * nx1, l2 * nx2, l3 * nx3
+    u = ctx.download("U", lb)[:, ng:ng + nx3, ng:ng + nx2, ng:ng + nx1]
+    ok = ok and np.array_equal(u, z["uf"][:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1])
+    if mhd:
+        b2 = ctx.download("B_X2F", lb)[ng:ng + nx3, ng:ng + nx2 + 1, ng:ng + nx1]
+        ok = ok and np.array_equal(b2, z["b2_f"][o3:o3 + nx3, o2:o2 + nx2 + 1, o1:o1 + nx1])
+print("rank %d/%d %s fused=%s cycles=%d links=%d bitwise_equal_to_reference=%s" % (
+    rank, world, name, fused, ti.ncycle, len(ctx.remote), ok), flush=True)
+ctx.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
