@@ -83,6 +83,7 @@ PROTOTYPES = {
     "athk_ct": (C.c_int, [_P, C.c_double, C.c_int]),
     "athk_exchange_ghosts": (C.c_int, [_P, C.c_int, C.c_int]),
     "athk_new_block_dt": (C.c_int, [_P, C.c_double, _D, _D]),
+    "athk_request_block_dt": (C.c_int, [_P]),
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_stage": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StageWghts), C.c_double]),
     "athk_stage_phase": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(StageWghts), C.c_double]),

@@ -68,6 +68,8 @@ struct athk_ctx {
   std::vector<int> h_rl_int;
   std::vector<idx_t> h_rl_off;
   idx_t max_ghost_count, max_emf_count;
+  SlabTable *slab_tab;   // device
+  bool dt_requested, dt_valid;   // NewBlockTimeStep fused into the next / last W(U)
   Real *geo_store;  // 9 arrays [nb][PG]
   int *nbr;         // [nb][27]
   Real *dt_blocks;  // [nb]
@@ -134,6 +136,7 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
                     cfg->sfloor > 0 ? cfg->sfloor : fmin_default);
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
+  c->dt_requested = c->dt_valid = false;
   c->coords_set = c->nbr_set = false;
   c->nremote = 0;
   memset(&c->rl, 0, sizeof(c->rl));
@@ -171,6 +174,22 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     c->geo.cp[d] = c->geo_store + (size_t)(3 + d) * g.nb * PG;
     c->geo.cm[d] = c->geo_store + (size_t)(6 + d) * g.nb * PG;
   }
+  {   // slab geometry table for the remote-link kernels
+    SlabTable *ht = new SlabTable();
+    for (int o3 = -1; o3 <= 1; ++o3)
+      for (int o2 = -1; o2 <= 1; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          const int os = nbr_slot(o1, o2, o3);
+          for (int q = 0; q < 4; ++q) ht->slab[os][q] = make_slab(g, q - 1, o1, o2, o3);
+          for (int sct = 0; sct < 6; ++sct)
+            ht->sec[os][sct] = ghost_section_off(g, cfg->mhd != 0, cfg->nscalars, o1, o2, o3, sct);
+        }
+    c->slab_tab = nullptr;
+    if (cudaMalloc((void **)&c->slab_tab, sizeof(SlabTable)) == cudaSuccess)
+      cudaMemcpy(c->slab_tab, ht, sizeof(SlabTable), cudaMemcpyHostToDevice);
+    delete ht;
+    c->rl.tab = c->slab_tab;
+  }
   c->h_geo.assign((size_t)9 * g.nb * PG, 0.0);
   c->h_nbr.assign((size_t)g.nb * 27, -1);
   CU(cudaStreamSynchronize(st));
@@ -185,7 +204,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
-  cudaFree(c->rl_int); cudaFree(c->rl_off);
+  cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -372,18 +391,50 @@ extern "C" int athk_device_array(athk_ctx *c, int array, void **dptr, long long 
 
 static bool bad_reg(int r) { return r < 0 || r > 2; }
 
+#ifndef ATHK_EMULATE
+__global__ void k_fill(Real *p, int n, Real v) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) p[q] = v;
+}
+#endif
+
+static int fill_dt_blocks(athk_ctx *c) {
+#ifndef ATHK_EMULATE
+  k_fill<<<(c->g.nb + 255) / 256, 256, 0, c->stream>>>(c->dt_blocks, c->g.nb, DBL_MAX);
+  CU(cudaGetLastError());
+  c->launches++;
+#else
+  for (int b = 0; b < c->g.nb; ++b) c->dt_blocks[b] = DBL_MAX;
+#endif
+  return ATHK_OK;
+}
+
+extern "C" int athk_request_block_dt(athk_ctx *c) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  c->dt_requested = true;
+  return ATHK_OK;
+}
+
 extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   NEED_READY(c);
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "cons2prim: register %d not allocated", reg);
   const Grid &g = c->g;
   Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+  Real *dt_out = nullptr;
+  c->dt_valid = false;
+  if (c->dt_requested) {
+    int rc = fill_dt_blocks(c);
+    if (rc) return rc;
+    dt_out = c->dt_blocks;
+  }
   if (c->cfg.mhd) {
-    Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr};
+    Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr, dt_out, c->geo};
     LAUNCH(c, r, f);
   } else {
-    Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr};
+    Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo};
     LAUNCH(c, r, f);
   }
+  if (c->dt_requested) { c->dt_valid = true; c->dt_requested = false; }
   return ATHK_OK;
 }
 
@@ -613,16 +664,17 @@ __global__ void __launch_bounds__(256) k_block_dt(const CellDt<MHD> f, Real *dt_
       atomicMin((unsigned long long *)&dt_blocks[blk], (unsigned long long)__double_as_longlong(m));
   }
 }
-__global__ void k_fill(Real *p, int n, Real v) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < n) p[q] = v;
-}
 #endif
 
 extern "C" int athk_new_block_dt(athk_ctx *c, double cfl_number, double *dt_blocks, double *dt_min) {
   NEED_READY(c);
   const Grid &g = c->g;
   std::vector<Real> h(g.nb);
+  if (c->dt_valid) {   // already folded by the last W(U) (athk_request_block_dt)
+    CU(cudaMemcpyAsync(h.data(), c->dt_blocks, g.nb * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->dt_valid = false;
+  } else {
 #ifndef ATHK_EMULATE
   k_fill<<<(g.nb + 255) / 256, 256, 0, c->stream>>>(c->dt_blocks, g.nb, DBL_MAX);
   const int ncell = g.nx1 * g.nx2 * g.nx3;
@@ -657,6 +709,7 @@ extern "C" int athk_new_block_dt(athk_ctx *c, double cfl_number, double *dt_bloc
     h[b] = m;
   }
 #endif
+  }
   Real mn = DBL_MAX;
   for (int b = 0; b < g.nb; ++b) {
     h[b] *= cfl_number;   // new_blockdt.cpp:191
@@ -808,6 +861,7 @@ extern "C" int athk_remote_configure(athk_ctx *c, int nlinks, const int *lb, con
   cudaFree(c->rl_int); cudaFree(c->rl_off);
   c->rl_int = nullptr; c->rl_off = nullptr;
   memset(&c->rl, 0, sizeof(c->rl));
+  c->rl.tab = c->slab_tab;
   c->max_ghost_count = c->max_emf_count = 0;
   if (nlinks == 0) return ATHK_OK;
   if (!lb || !ox1 || !ox2 || !ox3 || !ghost_send_off || !ghost_recv_off)

@@ -51,6 +51,19 @@ struct Cons2PrimPoint {
   Real *w;          // [nb][5][sn]
   Real *bcc;        // [nb][3][sn]
   const int *nbr;   // [nb][27]
+  // optional fusion of Hydro::NewBlockTimeStep (new_blockdt.cpp:72-124) into the last stage's
+  // W(U): active cells also fold min(dx/(|v|+c)) into dt_out[blk] (null = off)
+  Real *dt_out;
+  Geom geo;
+  ATHK_HD void fold_dt(int blk, Real dtc) const {
+#if defined(__CUDA_ARCH__)
+    // positive doubles order like their bit patterns; the racy pre-read only filters
+    if (dtc < dt_out[blk])
+      atomicMin((unsigned long long *)&dt_out[blk], (unsigned long long)__double_as_longlong(dtc));
+#else
+    if (dtc < dt_out[blk]) dt_out[blk] = dtc;
+#endif
+  }
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     // range: interior plus ghost sides with a neighbour (time_integrator.cpp:2206-2212)
     const int *nb = nbr + blk * 27;
@@ -85,6 +98,28 @@ struct Cons2PrimPoint {
     if (uc[IEN] != e0) ub[IEN * g.sn] = uc[IEN];
 #pragma unroll
     for (int n = 0; n < 5; ++n) wb[n * g.sn] = wc[n];
+    if (dt_out != nullptr && i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks &&
+        k <= g.ke) {
+      Real dt1 = geo.dxf[0][blk * geo.PG + i], dt2 = geo.dxf[1][blk * geo.PG + j],
+           dt3 = geo.dxf[2][blk * geo.PG + k];
+      if (MHD) {
+        const Real *bb = b + (idx_t)blk * 3 * g.sn + c;
+        const Real b1 = 0.5 * bb[0] + 0.5 * bb[1], b2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj],
+                   b3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
+        Real bx = b1 + fabs(bb[0] - b1);
+        dt1 /= max_std(0.0, (fabs(wc[IVX]) + fast_speed(eos, wc[IDN], wc[IPR], b2, b3, bx)));
+        bx = b2 + fabs(bb[g.sn] - b2);
+        dt2 /= max_std(0.0, (fabs(wc[IVY]) + fast_speed(eos, wc[IDN], wc[IPR], b3, b1, bx)));
+        bx = b3 + fabs(bb[2 * g.sn] - b3);
+        dt3 /= max_std(0.0, (fabs(wc[IVZ]) + fast_speed(eos, wc[IDN], wc[IPR], b1, b2, bx)));
+      } else {
+        const Real cs = sound_speed(eos, wc[IDN], wc[IPR]);
+        dt1 /= max_std(0.0, (fabs(wc[IVX]) + cs));
+        dt2 /= max_std(0.0, (fabs(wc[IVY]) + cs));
+        dt3 /= max_std(0.0, (fabs(wc[IVZ]) + cs));
+      }
+      fold_dt(blk, min_std(min_std(dt1, dt2), dt3));
+    }
   }
 };
 
@@ -521,8 +556,16 @@ ATHK_HD Slab make_slab(const Grid &g, int comp, int o1, int o2, int o3) {
 // one link = (local block, neighbour offset) whose neighbour lives on another GPU.  Messages of
 // all links are concatenated in per-peer send / receive buffers; the element layout of one ghost
 // message is [u: nvar_u][x1f][x2f][x3f][s: nvar_s], each section dense (k,j,i).
+// slab geometry depends on the neighbour offset only: 27 offsets x {cc, x1f, x2f, x3f}, plus the
+// section offsets of the ghost message; built once on the host (athk_create)
+struct SlabTable {
+  Slab slab[27][4];     // [nbr_slot][comp+1]
+  idx_t sec[27][6];     // [nbr_slot][section]: 0 u, 1..3 faces, 4 scalars, 5 total
+};
+
 struct RemoteLinks {
   int n;
+  const SlabTable *tab;
   const int *lb, *o1, *o2, *o3;          // [n]
   const idx_t *gsend, *grecv;            // [n] element offsets of the ghost message
   const idx_t *esend, *erecv;            // [n] element offsets of the EMF message
@@ -557,7 +600,9 @@ struct RemoteGhostPack {
   ATHK_HD void operator()(int link, idx_t e) const {
     const int o1 = rl.o1[link], o2 = rl.o2[link], o3 = rl.o3[link], blk = rl.lb[link];
     Real *dst = rl.gsbuf + rl.gsend[link] + e;
-    const Slab cc = make_slab(g, -1, o1, o2, o3);
+    const int os = nbr_slot(o1, o2, o3);
+    if (e >= rl.tab->sec[os][5]) return;
+    const Slab cc = rl.tab->slab[os][0];
     idx_t base = 0;
     const idx_t ncc = cc.count();
     if (e < 5 * ncc) {
@@ -572,7 +617,7 @@ struct RemoteGhostPack {
     base = 5 * ncc;
     if (mhd) {
       for (int d = 0; d < 3; ++d) {
-        const Slab f = make_slab(g, d, o1, o2, o3);
+        const Slab f = rl.tab->slab[os][1 + d];
         const idx_t nf = f.count();
         if (e < base + nf) {
           idx_t q = e - base;
@@ -650,10 +695,10 @@ struct GhostFillCC {
         u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
     } else {
       const int link = -id - 2;
-      const Slab cc = make_slab(g, -1, o1, o2, o3);
+      const int os = nbr_slot(o1, o2, o3);
+      const Slab cc = rl.tab->slab[os][0];
       const idx_t e = ((idx_t)(k - cc.r3) * cc.d2 + (j - cc.r2)) * cc.d1 + (i - cc.r1);
-      const Real *src = rl.grbuf + rl.grecv[link] +
-                        ghost_section_off(g, mhd != 0, nscal, o1, o2, o3, section) + e;
+      const Real *src = rl.grbuf + rl.grecv[link] + rl.tab->sec[os][section] + e;
       const idx_t ncc = cc.count();
       for (int n = 0; n < nvar; ++n) u[((idx_t)blk * nvar + n) * g.sn + dst] = src[n * ncc];
     }
@@ -687,10 +732,10 @@ struct GhostFillFC {
         b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
       } else {
         const int link = -id - 2;
-        const Slab f = make_slab(g, d, o1, o2, o3);
+        const int os = nbr_slot(o1, o2, o3);
+        const Slab f = rl.tab->slab[os][1 + d];
         const idx_t e = ((idx_t)(k - f.r3) * f.d2 + (j - f.r2)) * f.d1 + (i - f.r1);
-        b[((idx_t)blk * 3 + d) * g.sn + dst] =
-            rl.grbuf[rl.grecv[link] + ghost_section_off(g, true, nscal, o1, o2, o3, 1 + d) + e];
+        b[((idx_t)blk * 3 + d) * g.sn + dst] = rl.grbuf[rl.grecv[link] + rl.tab->sec[os][1 + d] + e];
       }
     }
   }

@@ -319,7 +319,10 @@ class TimeIntegrator:
         c.call("athk_cons2prim", 0)
 
     def step(self, tlim=None, reduce_min=None):
-        for stage in range(1, len(self.stages) + 1):
+        nst = len(self.stages)
+        for stage in range(1, nst + 1):
+            if stage == nst:   # NEW_DT runs on the last stage only (time_integrator.cpp:2313)
+                self.ctx.call("athk_request_block_dt")
             self.one_stage(stage)
         self.ncycle += 1
         self.time += self.dt

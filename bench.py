@@ -126,7 +126,7 @@ def run_reference(args):
                              "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def blast_athinput(n, blk, nlim):
@@ -295,12 +295,28 @@ def run_ours(args):
             s.record(stream)
             orig_call(name, *a)
             e.record(stream)
-            evs.append((name, s, e))
+            key = name + (":phase%d" % a[0] if name == "athk_stage_phase" else "")
+            evs.append((key, s, e))
         ctx.call = timed_call
+        xch = getattr(ctx, "xch", None)
+        if xch is not None:
+            def wrap(fn, key):
+                def g():
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(stream)
+                    fn()
+                    e.record(stream)
+                    evs.append((key, s, e))
+                return g
+            orig_xg, orig_xe = xch.exchange_ghosts, xch.exchange_emf
+            xch.exchange_ghosts = wrap(orig_xg, "nccl_exchange_ghosts")
+            xch.exchange_emf = wrap(orig_xe, "nccl_exchange_emf")
     for _ in range(2):
         step()
     if rank == 0:
         ctx.call = orig_call
+        if getattr(ctx, "xch", None) is not None:
+            ctx.xch.exchange_ghosts, ctx.xch.exchange_emf = orig_xg, orig_xe
         ctx.sync()
         torch.cuda.synchronize()
         for name, s, e in evs:
@@ -353,13 +369,33 @@ def run_ours(args):
                                 "exchange + W(U), one VL2 cycle, (u,b) + block dt -> host"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "final_dt": ti.dt, "cycles_run": ti.ncycle}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL version banner, torch warnings) may write to fd 1; the contract is ONE JSON
+    line on stdout, so fd 1 is pointed at stderr and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

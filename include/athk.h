@@ -148,6 +148,9 @@ int athk_exchange_ghosts(athk_ctx *ctx, int what_mask, int reg);
 /* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:45): per-block min dt * cfl, blocks 0..nblocks-1
  * into dt_blocks (may be NULL), returns the min over local blocks in *dt_min. Synchronises. */
 int athk_new_block_dt(athk_ctx *ctx, double cfl_number, double *dt_blocks, double *dt_min);
+/* Ask the NEXT athk_cons2prim (the last stage's W(U)) to fold Hydro::NewBlockTimeStep into the
+ * same pass over w; the following athk_new_block_dt then only reads the per-block minima. */
+int athk_request_block_dt(athk_ctx *ctx);
 /* History sums (outputs/history.cpp:196-248): mass, 3 momenta, 3 KE, tot-E, [3 ME], [scalars];
  * sums[] accumulates over local blocks (volume weighted). Synchronises. */
 int athk_history(athk_ctx *ctx, double *sums, int nsums);
