@@ -1,0 +1,590 @@
+"""TEST INFRASTRUCTURE (oracle) -- numpy restatement of the reference's per-MeshBlock
+finite-volume update (Athena++ v24.0, 3-D Cartesian uniform periodic mesh, adiabatic EOS).
+
+Independent of the CUDA sources: written from the reference alone, operation for operation
+(same association order, no FMA: numpy evaluates each binary op separately in IEEE double), so
+its results are expected to be BIT-IDENTICAL to the reference binary.  It is pinned against the
+golden vectors in tests/golden (outputs of the unmodified reference, tests/test_oracle.py).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+
+It works on the GLOBAL mesh with periodic wrap (np.roll): the reference result on a uniform
+periodic mesh does not depend on the MeshBlock decomposition.
+
+Reference sources followed (file:line under /root/reference/src):
+  eos/adiabatic_hydro.cpp:38-80, eos/adiabatic_mhd.cpp:41-90,149-156   cons2prim, sound/fast speed
+  field/field.cpp:112-180                                              cell-centred field
+  reconstruct/dc.cpp:24-110, reconstruct/plm.cpp:27-175                donor cell, PLM (van Leer)
+  hydro/rsolvers/hydro/hllc.cpp:32-179, hydro/rsolvers/mhd/hlld.cpp:36-376
+  hydro/hydro.cpp:154-158                                              CT weight
+  hydro/calculate_fluxes.cpp:38-415                                    sweeps, rotations
+  field/calculate_corner_e.cpp:130-229, field/ct.cpp:31-116            corner EMF, CT
+  bvals/fc/flux_correction_fc.cpp:689-760,1355-1541                    EMF correction (averaging)
+  hydro/add_flux_divergence.cpp:39-96, mesh/weighted_ave.cpp:35-230    update
+  hydro/new_blockdt.cpp:45-230, mesh/mesh.cpp:1236-1282                time step
+  task_list/time_integrator.cpp:111-606,1694-1885                      stage weights / order
+"""
+import sys
+
+import numpy as np
+
+IDN, IM1, IM2, IM3, IEN = 0, 1, 2, 3, 4
+IVX, IVY, IVZ, IPR, IBY, IBZ = 1, 2, 3, 4, 5, 6
+TINY_NUMBER = 1.0e-20
+FLOOR = np.sqrt(1024 * np.float64(np.finfo(np.float32).tiny))   # eos.hpp:161
+TWO_3RD = 0.66666666666666667
+ONE_3RD = 0.33333333333333333
+INTEGRATORS = {   # (delta, gamma_1, gamma_2, gamma_3, beta)
+    "vl2": [(1.0, 0.0, 1.0, 0.0, 0.5), (0.0, 0.0, 1.0, 0.0, 1.0)],
+    "rk2": [(1.0, 0.0, 1.0, 0.0, 1.0), (0.0, 0.5, 0.5, 0.0, 0.5)],
+    "rk3": [(1.0, 0.0, 1.0, 0.0, 1.0), (0.0, 0.25, 0.75, 0.0, 0.25),
+            (0.0, TWO_3RD, ONE_3RD, 0.0, TWO_3RD)],
+}
+CFL_LIMIT = {"vl2": 0.5, "rk2": 1.0, "rk3": 1.0}
+
+AX = {0: -1, 1: -2, 2: -3}   # sweep direction -> numpy axis of a (k,j,i) array
+
+
+def sh(a, d, n):
+    """value at index+n along direction d (periodic)."""
+    return np.roll(a, -n, axis=AX[d])
+
+
+def mesh_gen_x(index, nrange):   # mesh.hpp:457-473 (sym_interval = true)
+    noffset = index - nrange // 2
+    noffset_ceil = index - (nrange + 1) // 2
+    return float(noffset + noffset_ceil) / (2.0 * nrange)
+
+
+def uniform_gen(x, xmin, xmax):   # mesh.hpp:535-538
+    return 0.5 * (xmin + xmax) + (x * xmax - x * xmin)
+
+
+NG = 2
+
+
+class Mesh:
+    """Global uniform mesh treated as ONE MeshBlock with NG ghost zones; 1-D coordinate arrays as
+    Coordinates builds them (coordinates.cpp:100-324, cartesian.cpp:24-60).  Every 3-D array of
+    the oracle lives in the same padded box (nc3+1, nc2+1, nc1+1) so that cell, face and edge
+    data share one index space (index ng = first active cell / face)."""
+
+    def __init__(self, nx, xmin, xmax, ng=NG):
+        self.nx = tuple(nx)
+        self.ng = ng
+        self.nc = tuple(n + 2 * ng for n in nx)
+        self.shape = tuple(n + 1 for n in self.nc[::-1])   # (k,j,i) padded box
+        self.dxf, self.cp, self.cm = [], [], []
+        for d in range(3):
+            n, nc = nx[d], self.nc[d]
+            xf = np.array([uniform_gen(mesh_gen_x(i - ng, n), xmin[d], xmax[d]) for i in range(nc + 1)])
+            xf[ng] = xmin[d]
+            xf[ng + n] = xmax[d]
+            dx = (xmax[d] - xmin[d]) / n
+            dxf = np.full(nc + 1, dx)
+            xv = 0.5 * (xf[1:] + xf[:-1])
+            cp = np.ones(nc + 1)
+            cm = np.ones(nc + 1)
+            cp[:nc] = (xf[1:] - xv) / dxf[:nc]    # plm.cpp:152
+            cm[:nc] = (xv - xf[:-1]) / dxf[:nc]   # plm.cpp:153
+            self.dxf.append(dxf)
+            self.cp.append(cp)
+            self.cm.append(cm)
+
+    def along(self, arr1d, d):
+        shape = [1, 1, 1]
+        shape[AX[d]] = -1
+        return arr1d.reshape(shape)
+
+    def idx(self, d):
+        """index array along direction d, broadcastable over the padded box"""
+        return self.along(np.arange(self.nc[d] + 1), d)
+
+    def active(self, d, extra=0):
+        """mask of active indices [ng, ng+n-1+extra] along d"""
+        i = self.idx(d)
+        return (i >= self.ng) & (i <= self.ng + self.nx[d] - 1 + extra)
+
+    def pad_cc(self, a):
+        """global interior (…,n3,n2,n1) -> padded box with zero ghosts"""
+        ng = self.ng
+        out = np.zeros(a.shape[:-3] + self.shape)
+        out[..., ng:ng + self.nx[2], ng:ng + self.nx[1], ng:ng + self.nx[0]] = a
+        return out
+
+    def pad_fc(self, a, d):
+        ng = self.ng
+        n = [self.nx[2], self.nx[1], self.nx[0]]
+        n[2 - d] += 1
+        out = np.zeros(self.shape)
+        out[ng:ng + n[0], ng:ng + n[1], ng:ng + n[2]] = a
+        return out
+
+    def unpad(self, a, d=None):
+        ng = self.ng
+        n = [self.nx[2], self.nx[1], self.nx[0]]
+        if d is not None:
+            n[2 - d] += 1
+        return a[..., ng:ng + n[0], ng:ng + n[1], ng:ng + n[2]]
+
+    def fill_ghosts_cc(self, a):
+        """periodic self-exchange of a cell-centred array (bvals_cc.cpp:287-302,386-420)"""
+        for d in range(3):
+            i = self.idx(d)
+            n, ng = self.nx[d], self.ng
+            lo = np.roll(a, n, axis=AX[d])    # value at index - n ... placed at index
+            hi = np.roll(a, -n, axis=AX[d])
+            a = np.where(i < ng, hi, np.where(i > ng + n - 1, lo, a))
+        return a
+
+    def fill_ghosts_fc(self, a, comp):
+        """face field: along its own direction the shared faces ng and ng+n are kept
+        (bvals_fc.cpp:591-593)"""
+        for d in range(3):
+            i = self.idx(d)
+            n, ng = self.nx[d], self.ng
+            top = ng + n - 1 + (1 if d == comp else 0)
+            lo = np.roll(a, n, axis=AX[d])
+            hi = np.roll(a, -n, axis=AX[d])
+            a = np.where(i < ng, hi, np.where(i > top, lo, a))
+        return a
+
+
+def cell_centered_b(b1, b2, b3):   # field.cpp:139-170, uniform
+    return (0.5 * b1 + 0.5 * sh(b1, 0, 1), 0.5 * b2 + 0.5 * sh(b2, 1, 1), 0.5 * b3 + 0.5 * sh(b3, 2, 1))
+
+
+def cons2prim(u, gamma, bcc=None, dfloor=FLOOR, pfloor=FLOOR):
+    """Returns w; u is modified in place where floors fire (adiabatic_*.cpp)."""
+    gm1 = gamma - 1.0
+    u[IDN] = np.where(u[IDN] > dfloor, u[IDN], dfloor)
+    w = np.empty_like(u)
+    w[IDN] = u[IDN]
+    di = 1.0 / u[IDN]
+    w[IVX] = u[IM1] * di
+    w[IVY] = u[IM2] * di
+    w[IVZ] = u[IM3] * di
+    e_k = 0.5 * di * (u[IM1] * u[IM1] + u[IM2] * u[IM2] + u[IM3] * u[IM3])
+    if bcc is not None:
+        pb = 0.5 * (bcc[0] * bcc[0] + bcc[1] * bcc[1] + bcc[2] * bcc[2])
+        p = gm1 * (u[IEN] - e_k - pb)
+        u[IEN] = np.where(p > pfloor, u[IEN], (pfloor / gm1) + e_k + pb)
+    else:
+        p = gm1 * (u[IEN] - e_k)
+        u[IEN] = np.where(p > pfloor, u[IEN], (pfloor / gm1) + e_k)
+    w[IPR] = np.where(p > pfloor, p, pfloor)
+    return w
+
+
+def fast_speed(gamma, d, p, by, bz, bx):   # adiabatic_mhd.cpp:149-156
+    asq = gamma * p
+    vaxsq = bx * bx
+    ct2 = (by * by + bz * bz)
+    qsq = vaxsq + ct2 + asq
+    tmp = vaxsq + ct2 - asq
+    return np.sqrt(0.5 * (qsq + np.sqrt(tmp * tmp + 4.0 * asq * ct2)) / d)
+
+
+def reconstruct(q, d, order, mesh):
+    """q: list of (k,j,i) arrays. Returns (wl, wr) at face n (between cells n-1 and n)."""
+    wl, wr = [], []
+    cp = mesh.along(mesh.cp[d], d)
+    cm = mesh.along(mesh.cm[d], d)
+    with np.errstate(all="ignore"):
+        for a in q:
+            if order == 1:
+                up, lo = a, a
+            else:
+                dwl = a - sh(a, d, -1)
+                dwr = sh(a, d, 1) - a
+                dw2 = dwl * dwr
+                dwm = 2.0 * dw2 / (dwl + dwr)
+                dwm = np.where(dw2 <= 0.0, 0.0, dwm)
+                up = a + cp * dwm      # L state of face n+1
+                lo = a - cm * dwm      # R state of face n
+            wl.append(sh(up, d, -1))
+            wr.append(lo)
+    return wl, wr
+
+
+def hllc(wl, wr, gamma):   # hllc.cpp:53-175
+    gm1 = gamma - 1.0
+    igm1 = 1.0 / gm1
+    with np.errstate(all="ignore"):
+        cl = np.sqrt(gamma * wl[IPR] / wl[IDN])
+        cr = np.sqrt(gamma * wr[IPR] / wr[IDN])
+        el = wl[IPR] * igm1 + 0.5 * wl[IDN] * (wl[IVX] * wl[IVX] + wl[IVY] * wl[IVY] + wl[IVZ] * wl[IVZ])
+        er = wr[IPR] * igm1 + 0.5 * wr[IDN] * (wr[IVX] * wr[IVX] + wr[IVY] * wr[IVY] + wr[IVZ] * wr[IVZ])
+        rhoa = .5 * (wl[IDN] + wr[IDN])
+        ca = .5 * (cl + cr)
+        pmid = .5 * (wl[IPR] + wr[IPR] + (wl[IVX] - wr[IVX]) * rhoa * ca)
+        ql = np.where(pmid <= wl[IPR], 1.0, np.sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wl[IPR] - 1.0)))
+        qr = np.where(pmid <= wr[IPR], 1.0, np.sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wr[IPR] - 1.0)))
+        al = wl[IVX] - cl * ql
+        ar = wr[IVX] + cr * qr
+        bp = np.where(ar > 0.0, ar, TINY_NUMBER)
+        bm = np.where(al < 0.0, al, -TINY_NUMBER)
+        vxl = wl[IVX] - al
+        vxr = wr[IVX] - ar
+        tl = wl[IPR] + vxl * wl[IDN] * wl[IVX]
+        tr = wr[IPR] + vxr * wr[IDN] * wr[IVX]
+        ml = wl[IDN] * vxl
+        mr = -(wr[IDN] * vxr)
+        am = (tl - tr) / (ml + mr)
+        cp = (ml * tr + mr * tl) / (ml + mr)
+        cp = np.where(cp > 0.0, cp, 0.0)
+        vxl = wl[IVX] - bm
+        vxr = wr[IVX] - bp
+        fl = [wl[IDN] * vxl, wl[IDN] * wl[IVX] * vxl + wl[IPR], wl[IDN] * wl[IVY] * vxl,
+              wl[IDN] * wl[IVZ] * vxl, el * vxl + wl[IPR] * wl[IVX]]
+        fr = [wr[IDN] * vxr, wr[IDN] * wr[IVX] * vxr + wr[IPR], wr[IDN] * wr[IVY] * vxr,
+              wr[IDN] * wr[IVZ] * vxr, er * vxr + wr[IPR] * wr[IVX]]
+        pos = am >= 0.0
+        sl = np.where(pos, am / (am - bm), 0.0)
+        sr = np.where(pos, 0.0, -am / (bp - am))
+        sm = np.where(pos, -bm / (am - bm), bp / (bp - am))
+        f = [sl * fl[n] + sr * fr[n] for n in range(5)]
+        f[IVX] = sl * fl[IVX] + sr * fr[IVX] + sm * cp
+        f[IEN] = sl * fl[IEN] + sr * fr[IEN] + sm * cp * am
+    return f
+
+
+def hlld(wl, wr, bxi, gamma):   # hlld.cpp:56-365 ; returns 7 flux components
+    SMALL = 1.0e-4
+    igm1 = 1.0 / (gamma - 1.0)
+    with np.errstate(all="ignore"):
+        bxsq = bxi * bxi
+        pbl = 0.5 * (bxsq + (wl[IBY] * wl[IBY] + wl[IBZ] * wl[IBZ]))
+        pbr = 0.5 * (bxsq + (wr[IBY] * wr[IBY] + wr[IBZ] * wr[IBZ]))
+        kel = 0.5 * wl[IDN] * (wl[IVX] * wl[IVX] + (wl[IVY] * wl[IVY] + wl[IVZ] * wl[IVZ]))
+        ker = 0.5 * wr[IDN] * (wr[IVX] * wr[IVX] + (wr[IVY] * wr[IVY] + wr[IVZ] * wr[IVZ]))
+        # conserved L/R: d, mx, my, mz, e, by, bz
+        ul = [wl[IDN], wl[IVX] * wl[IDN], wl[IVY] * wl[IDN], wl[IVZ] * wl[IDN],
+              wl[IPR] * igm1 + kel + pbl, wl[IBY], wl[IBZ]]
+        ur = [wr[IDN], wr[IVX] * wr[IDN], wr[IVY] * wr[IDN], wr[IVZ] * wr[IDN],
+              wr[IPR] * igm1 + ker + pbr, wr[IBY], wr[IBZ]]
+        cfl = fast_speed(gamma, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi)
+        cfr = fast_speed(gamma, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi)
+        a0, b0 = wl[IVX] - cfl, wr[IVX] - cfr
+        s0 = np.where(b0 < a0, b0, a0)                 # std::min
+        a4, b4 = wl[IVX] + cfl, wr[IVX] + cfr
+        s4 = np.where(a4 < b4, b4, a4)                 # std::max
+        ptl = wl[IPR] + pbl
+        ptr = wr[IPR] + pbr
+        fl = [ul[1], ul[1] * wl[IVX] + ptl - bxsq, ul[2] * wl[IVX] - bxi * ul[5],
+              ul[3] * wl[IVX] - bxi * ul[6],
+              wl[IVX] * (ul[4] + ptl - bxsq) - bxi * (wl[IVY] * ul[5] + wl[IVZ] * ul[6]),
+              ul[5] * wl[IVX] - bxi * wl[IVY], ul[6] * wl[IVX] - bxi * wl[IVZ]]
+        fr = [ur[1], ur[1] * wr[IVX] + ptr - bxsq, ur[2] * wr[IVX] - bxi * ur[5],
+              ur[3] * wr[IVX] - bxi * ur[6],
+              wr[IVX] * (ur[4] + ptr - bxsq) - bxi * (wr[IVY] * ur[5] + wr[IVZ] * ur[6]),
+              ur[5] * wr[IVX] - bxi * wr[IVY], ur[6] * wr[IVX] - bxi * wr[IVZ]]
+        sdl = s0 - wl[IVX]
+        sdr = s4 - wr[IVX]
+        s2 = (sdr * ur[1] - sdl * ul[1] + (ptl - ptr)) / (sdr * ur[0] - sdl * ul[0])
+        sdml = s0 - s2
+        sdmr = s4 - s2
+        sdml_inv = 1.0 / sdml
+        sdmr_inv = 1.0 / sdmr
+        ulst_d = ul[0] * sdl * sdml_inv
+        urst_d = ur[0] * sdr * sdmr_inv
+        ulst_d_inv = 1.0 / ulst_d
+        urst_d_inv = 1.0 / urst_d
+        sqrtdl = np.sqrt(ulst_d)
+        sqrtdr = np.sqrt(urst_d)
+        s1 = s2 - np.abs(bxi) / sqrtdl
+        s3 = s2 + np.abs(bxi) / sqrtdr
+        ptstl = ptl + ul[0] * sdl * (s2 - wl[IVX])
+        ptstr = ptr + ur[0] * sdr * (s2 - wr[IVX])
+        ptst = 0.5 * (ptstr + ptstl)
+
+        def star(u, w, sd, sdm, sdm_inv, ust_d, ust_d_inv, pt):
+            mx = ust_d * s2
+            den = u[0] * sd * sdm - bxsq
+            degen = np.abs(den) < SMALL * ptst
+            tmp = bxi * (sd - sdm) / den
+            my = np.where(degen, ust_d * w[IVY], ust_d * (w[IVY] - u[5] * tmp))
+            mz = np.where(degen, ust_d * w[IVZ], ust_d * (w[IVZ] - u[6] * tmp))
+            tmp2 = (u[0] * (sd * sd) - bxsq) / den
+            by = np.where(degen, u[5], u[5] * tmp2)
+            bz = np.where(degen, u[6], u[6] * tmp2)
+            vbst = (mx * bxi + (my * by + mz * bz)) * ust_d_inv
+            e = (sd * u[4] - pt * w[IVX] + ptst * s2 +
+                 bxi * (w[IVX] * bxi + (w[IVY] * u[5] + w[IVZ] * u[6]) - vbst)) * sdm_inv
+            return [ust_d, mx, my, mz, e, by, bz], vbst
+
+        ulst, vbstl = star(ul, wl, sdl, sdml, sdml_inv, ulst_d, ulst_d_inv, ptl)
+        urst, vbstr = star(ur, wr, sdr, sdmr, sdmr_inv, urst_d, urst_d_inv, ptr)
+        invsumd = 1.0 / (sqrtdl + sqrtdr)
+        bxsig = np.where(bxi > 0.0, 1.0, -1.0)
+        tmp = invsumd * (sqrtdl * (ulst[2] * ulst_d_inv) + sqrtdr * (urst[2] * urst_d_inv) +
+                         bxsig * (urst[5] - ulst[5]))
+        uld_my, urd_my = ulst[0] * tmp, urst[0] * tmp
+        tmp = invsumd * (sqrtdl * (ulst[3] * ulst_d_inv) + sqrtdr * (urst[3] * urst_d_inv) +
+                         bxsig * (urst[6] - ulst[6]))
+        uld_mz, urd_mz = ulst[0] * tmp, urst[0] * tmp
+        d_by = invsumd * (sqrtdl * urst[5] + sqrtdr * ulst[5] +
+                          bxsig * sqrtdl * sqrtdr * ((urst[2] * urst_d_inv) - (ulst[2] * ulst_d_inv)))
+        d_bz = invsumd * (sqrtdl * urst[6] + sqrtdr * ulst[6] +
+                          bxsig * sqrtdl * sqrtdr * ((urst[3] * urst_d_inv) - (ulst[3] * ulst_d_inv)))
+        tmp = s2 * bxi + (uld_my * d_by + uld_mz * d_bz) / ulst[0]
+        uld_e = ulst[4] - sqrtdl * bxsig * (vbstl - tmp)
+        urd_e = urst[4] + sqrtdr * bxsig * (vbstr - tmp)
+        uldst = [ulst[0], ulst[1], uld_my, uld_mz, uld_e, d_by, d_bz]
+        urdst = [urst[0], urst[1], urd_my, urd_mz, urd_e, d_by, d_bz]
+        jl2 = [s1 * (uldst[n] - ulst[n]) for n in range(7)]
+        jl1 = [s0 * (ulst[n] - ul[n]) for n in range(7)]
+        jr2 = [s3 * (urdst[n] - urst[n]) for n in range(7)]
+        jr1 = [s4 * (urst[n] - ur[n]) for n in range(7)]
+        f = []
+        for n in range(7):
+            val = fr[n] + jr1[n] + jr2[n]                             # Fr**
+            val = np.where(s2 >= 0.0, fl[n] + jl1[n] + jl2[n], val)   # Fl**
+            val = np.where(s3 <= 0.0, fr[n] + jr1[n], val)            # Fr*
+            val = np.where(s1 >= 0.0, fl[n] + jl1[n], val)            # Fl*
+            val = np.where(s4 <= 0.0, fr[n], val)
+            val = np.where(s0 >= 0.0, fl[n], val)
+            f.append(val)
+    return f
+
+
+def ct_weight(dflx, rhol, rhor, dx, dt):   # hydro.cpp:154-158
+    v_over_c = (1024.0) * dt * dflx / (dx * (rhol + rhor))
+    tmp_min = np.where(v_over_c < 0.5, v_over_c, 0.5)
+    return 0.5 + np.where(-0.5 < tmp_min, tmp_min, -0.5)
+
+
+class State:
+    """u: global interior (5,n3,n2,n1); b: global face arrays with the +1 extent of their own
+    direction (the faces on the periodic seam are distinct arrays entries, as in the reference
+    where each MeshBlock keeps its own copy of a shared face)."""
+
+    def __init__(self, mesh, gamma, u, b=None):
+        self.mesh, self.gamma = mesh, gamma
+        self.mhd = b is not None
+        self.u = mesh.fill_ghosts_cc(mesh.pad_cc(u))
+        self.b = [mesh.fill_ghosts_fc(mesh.pad_fc(b[d], d), d) for d in range(3)] if self.mhd else None
+        self.prim()
+
+    def prim(self):
+        self.bcc = cell_centered_b(*self.b) if self.mhd else None
+        with np.errstate(all="ignore"):
+            self.w = cons2prim(self.u, self.gamma, self.bcc)
+
+    def interior_u(self):
+        return self.mesh.unpad(self.u)
+
+    def interior_b(self, d):
+        return self.mesh.unpad(self.b[d], d)
+
+
+def fluxes(st, order, dt_mesh):
+    """CalculateFluxes: returns flux[d] (5 arrays, variable-indexed) and, for MHD, face EMFs and
+    CT weights, all at face n of direction d (between cells n-1 and n)."""
+    mesh, g = st.mesh, st.gamma
+    out = []
+    for d in range(3):
+        ivx, ivy, ivz = IVX + d, IVX + (d + 1) % 3, IVX + (d + 2) % 3
+        q = [st.w[IDN], st.w[ivx], st.w[ivy], st.w[ivz], st.w[IPR]]
+        if st.mhd:
+            q += [st.bcc[(d + 1) % 3], st.bcc[(d + 2) % 3]]
+        wl, wr = reconstruct(q, d, order, mesh)
+        if st.mhd:
+            f = hlld(wl, wr, st.b[d], g)
+            flx = [None] * 5
+            flx[IDN], flx[ivx], flx[ivy], flx[ivz], flx[IEN] = f[0], f[1], f[2], f[3], f[4]
+            dxw = mesh.along(mesh.dxf[d], d)
+            wct = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, dt_mesh)
+            out.append((flx, -f[IBY], f[IBZ], wct))
+        else:
+            f = hllc(wl, wr, g)
+            flx = [None] * 5
+            flx[IDN], flx[ivx], flx[ivy], flx[ivz], flx[IEN] = f[0], f[1], f[2], f[3], f[4]
+            out.append((flx, None, None, None))
+    return out
+
+
+def corner_e(st, fx):
+    """ComputeCornerE (3-D) + same-level EMF correction for a periodic uniform mesh.  On the
+    global mesh every edge is interior, so the correction (own + bit-equal neighbour copies,
+    then *0.5 or *0.25) is the identity except for rounding of ((a+a)+a)+a; the reference applies
+    it only on MeshBlock boundaries, where it is exact as well -- see apply_emf_correction."""
+    w, bcc = st.w, st.bcc
+    cc1 = w[IVZ] * bcc[1] - w[IVY] * bcc[2]
+    cc2 = w[IVX] * bcc[2] - w[IVZ] * bcc[0]
+    cc3 = w[IVY] * bcc[0] - w[IVX] * bcc[1]
+    (_, e3_x1f, e2_x1f, w_x1f), (_, e1_x2f, e3_x2f, w_x2f), (_, e2_x3f, e1_x3f, w_x3f) = fx
+    S = sh
+
+    def K(a, n=-1):
+        return S(a, 2, n)
+
+    def J(a, n=-1):
+        return S(a, 1, n)
+
+    def I(a, n=-1):
+        return S(a, 0, n)
+    de1_l3 = (1.0 - K(w_x2f)) * (e1_x3f - K(cc1)) + (K(w_x2f)) * (J(e1_x3f) - K(J(cc1)))
+    de1_r3 = (1.0 - w_x2f) * (e1_x3f - cc1) + (w_x2f) * (J(e1_x3f) - J(cc1))
+    de1_l2 = (1.0 - J(w_x3f)) * (e1_x2f - J(cc1)) + (J(w_x3f)) * (K(e1_x2f) - K(J(cc1)))
+    de1_r2 = (1.0 - w_x3f) * (e1_x2f - cc1) + (w_x3f) * (K(e1_x2f) - K(cc1))
+    e1 = 0.25 * (de1_l3 + de1_r3 + de1_l2 + de1_r2 + K(e1_x2f) + e1_x2f + J(e1_x3f) + e1_x3f)
+    de2_l3 = (1.0 - K(w_x1f)) * (e2_x3f - K(cc2)) + (K(w_x1f)) * (I(e2_x3f) - K(I(cc2)))
+    de2_r3 = (1.0 - w_x1f) * (e2_x3f - cc2) + (w_x1f) * (I(e2_x3f) - I(cc2))
+    de2_l1 = (1.0 - I(w_x3f)) * (e2_x1f - I(cc2)) + (I(w_x3f)) * (K(e2_x1f) - K(I(cc2)))
+    de2_r1 = (1.0 - w_x3f) * (e2_x1f - cc2) + (w_x3f) * (K(e2_x1f) - K(cc2))
+    e2 = 0.25 * (de2_l3 + de2_r3 + de2_l1 + de2_r1 + I(e2_x3f) + e2_x3f + K(e2_x1f) + e2_x1f)
+    de3_l2 = (1.0 - J(w_x1f)) * (e3_x2f - J(cc3)) + (J(w_x1f)) * (I(e3_x2f) - J(I(cc3)))
+    de3_r2 = (1.0 - w_x1f) * (e3_x2f - cc3) + (w_x1f) * (I(e3_x2f) - I(cc3))
+    de3_l1 = (1.0 - I(w_x2f)) * (e3_x1f - I(cc3)) + (I(w_x2f)) * (J(e3_x1f) - J(I(cc3)))
+    de3_r1 = (1.0 - w_x2f) * (e3_x1f - cc3) + (w_x2f) * (J(e3_x1f) - J(cc3))
+    e3 = 0.25 * (de3_l1 + de3_r1 + de3_l2 + de3_r2 + I(e3_x2f) + e3_x2f + J(e3_x1f) + e3_x1f)
+    return [e1, e2, e3]
+
+
+def apply_emf_correction(e, mesh, block_nx):
+    """SetFluxBoundarySameLevel + AverageFluxBoundary on MeshBlock boundaries
+    (flux_correction_fc.cpp:689-760,1355-1541): every block adds its neighbours' copies of a
+    shared edge EMF to its own (face neighbours in x1,x2,x3 order, then the edge neighbour),
+    then scales faces by 0.5 and block edges by 0.25.  Inside the mesh all copies are the same
+    array entry; across the periodic seam the partner copy is the entry at the opposite seam
+    index (it was computed from that side's own copy of the seam face field, so it may differ in
+    the last bits)."""
+    ng = mesh.ng
+
+    def partner(a, d):
+        i, n = mesh.idx(d), mesh.nx[d]
+        return np.where(i == ng, np.roll(a, -n, axis=AX[d]),
+                        np.where(i == ng + n, np.roll(a, n, axis=AX[d]), a))
+    on = []
+    for d in range(3):
+        i = mesh.idx(d) - ng
+        on.append((i >= 0) & (i <= mesh.nx[d]) & (i % block_nx[d] == 0))
+    out = []
+    for comp, (da, db) in enumerate(((1, 2), (0, 2), (0, 1))):
+        a = e[comp]
+        pa, pb = on[da], on[db]
+        fa = partner(a, da)
+        fb = partner(a, db)
+        fe = partner(fa, db)
+        v_a = (a + fa) * 0.5
+        v_b = (a + fb) * 0.5
+        v_edge = (((a + fa) + fb) + fe) * 0.25
+        out.append(np.where(pa & pb, v_edge, np.where(pa, v_a, np.where(pb, v_b, a))))
+    return out
+
+
+def weighted_ave(out, in1, in2, w0, w1, w2):   # weighted_ave.cpp:35-230 (wght[3]=wght[4]=0)
+    if w0 == 1.0:
+        if w2 != 0.0:
+            return out + (w1 * in1 + w2 * in2)
+        if w1 != 0.0:
+            return out + w1 * in1
+        return out
+    if w0 == 0.0:
+        if w2 != 0.0:
+            return w1 * in1 + w2 * in2
+        if w1 != 0.0:
+            return w1 * in1
+        return out
+    if w2 != 0.0:
+        return w0 * out + w1 * in1 + w2 * in2
+    if w1 != 0.0:
+        return w0 * out + w1 * in1
+    return out * w0
+
+
+def block_dt(st, cfl):   # new_blockdt.cpp:72-191
+    w, m = st.w, st.mesh
+    dx = [m.along(m.dxf[d], d) for d in range(3)]
+    with np.errstate(all="ignore"):
+        if st.mhd:
+            bcc, b = st.bcc, st.b
+            dts = []
+            for d in range(3):
+                bx = bcc[d] + np.abs(b[d] - bcc[d])
+                cf = fast_speed(st.gamma, w[IDN], w[IPR], bcc[(d + 1) % 3], bcc[(d + 2) % 3], bx)
+                dts.append(dx[d] / np.maximum(0.0, np.abs(w[IVX + d]) + cf))
+        else:
+            cs = np.sqrt(st.gamma * w[IPR] / w[IDN])
+            dts = [dx[d] / np.maximum(0.0, np.abs(w[IVX + d]) + cs) for d in range(3)]
+    act = m.active(0) & m.active(1) & m.active(2)
+    return min(float(x[np.broadcast_to(act, x.shape)].min()) for x in dts) * cfl
+
+
+class Integrator:
+    def __init__(self, st, integrator="vl2", xorder=2, cfl=0.3, block_nx=None):
+        self.st, self.name, self.xorder = st, integrator, xorder
+        self.stages = INTEGRATORS[integrator]
+        self.cfl = min(cfl, CFL_LIMIT[integrator])
+        self.block_nx = block_nx or st.mesh.nx
+        self.time, self.ncycle = 0.0, 0
+        self.dt = sys.float_info.max
+        self.dt_history = []
+
+    def new_dt(self, tlim):   # mesh.cpp:1236-1282
+        dt = min(2.0 * self.dt, block_dt(self.st, self.cfl))
+        if tlim is not None and self.time < tlim and (tlim - self.time) < dt:
+            dt = tlim - self.time
+        self.dt = dt
+
+    def step(self, tlim=None):
+        st, m = self.st, self.st.mesh
+        dx = [m.along(m.dxf[d], d) for d in range(3)]
+        act = [m.active(d) for d in range(3)]
+        actf = [m.active(d, 1) for d in range(3)]
+        cells = act[0] & act[1] & act[2]
+        # WeightedAve / CT ranges of the face fields (weighted_ave.cpp:383-406, ct.cpp:31-116)
+        faces = [actf[0] & act[1] & act[2], act[0] & actf[1] & act[2], act[0] & act[1] & actf[2]]
+        u1 = np.zeros_like(st.u)
+        b1 = [np.zeros_like(x) for x in st.b] if st.mhd else None
+        for stage, (delta, g1, g2, g3, beta) in enumerate(self.stages, 1):
+            order = 1 if (self.name == "vl2" and stage == 1) else self.xorder
+            with np.errstate(all="ignore"):
+                fx = fluxes(st, order, self.dt)
+                wght = beta * self.dt
+                if st.mhd:
+                    e = apply_emf_correction(corner_e(st, fx), m, self.block_nx)
+                # IntegrateHydro (time_integrator.cpp:1797-1824); only active cells are touched
+                u1 = np.where(cells, weighted_ave(u1, st.u, None, 1.0, delta, 0.0), u1)
+                if g1 == 0.0 and g2 == 1.0 and g3 == 0.0:
+                    st.u, u1 = u1, st.u
+                else:
+                    st.u = np.where(cells, weighted_ave(st.u, u1, None, g1, g2, g3), st.u)
+                a1, a2, a3 = dx[1] * dx[2], dx[0] * dx[2], dx[0] * dx[1]
+                vol = dx[0] * dx[1] * dx[2]
+                unew = st.u.copy()
+                for n in range(5):
+                    dflx = (a1 * sh(fx[0][0][n], 0, 1) - a1 * fx[0][0][n])
+                    dflx = dflx + (a2 * sh(fx[1][0][n], 1, 1) - a2 * fx[1][0][n])
+                    dflx = dflx + (a3 * sh(fx[2][0][n], 2, 1) - a3 * fx[2][0][n])
+                    unew[n] = np.where(cells, st.u[n] - wght * dflx / vol, st.u[n])
+                st.u = unew
+                if st.mhd:   # IntegrateField + CT (ct.cpp:31-116)
+                    for c in range(3):
+                        b1[c] = np.where(faces[c], weighted_ave(b1[c], st.b[c], None, 1.0, delta, 0.0), b1[c])
+                    if g1 == 0.0 and g2 == 1.0 and g3 == 0.0:
+                        st.b, b1 = b1, st.b
+                    else:
+                        st.b = [np.where(faces[c], weighted_ave(st.b[c], b1[c], None, g1, g2, g3), st.b[c])
+                                for c in range(3)]
+                    e1, e2, e3 = e
+                    bx1 = st.b[0] - (wght / a1) * (dx[2] * sh(e3, 1, 1) - dx[2] * e3)
+                    bx1 = bx1 + (wght / a1) * (dx[1] * sh(e2, 2, 1) - dx[1] * e2)
+                    bx2 = st.b[1] + (wght / a2) * (dx[2] * sh(e3, 0, 1) - dx[2] * e3)
+                    bx2 = bx2 - (wght / a2) * (dx[0] * sh(e1, 2, 1) - dx[0] * e1)
+                    bx3 = st.b[2] - (wght / a3) * (dx[1] * sh(e2, 0, 1) - dx[1] * e2)
+                    bx3 = bx3 + (wght / a3) * (dx[0] * sh(e1, 1, 1) - dx[0] * e1)
+                    st.b = [np.where(faces[0], bx1, st.b[0]), np.where(faces[1], bx2, st.b[1]),
+                            np.where(faces[2], bx3, st.b[2])]
+                    st.b = [m.fill_ghosts_fc(st.b[d], d) for d in range(3)]
+                st.u = m.fill_ghosts_cc(st.u)
+            st.prim()
+        self.ncycle += 1
+        self.time += self.dt
+        self.dt_history.append(self.dt)
+        self.new_dt(tlim)
+
+    def run(self, tlim):
+        self.new_dt(tlim)
+        while self.time < tlim:
+            self.step(tlim)
