@@ -62,6 +62,7 @@ PROTOTYPES = {
     "athk_sync": (C.c_int, [_P]),
     "athk_launch_count": (C.c_longlong, [_P]),
     "athk_stream": (_P, [_P]),
+    "athk_profile": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int]),
     "athk_set_block_coords": (C.c_int, [_P, C.c_int] + [_D] * 9),
     "athk_set_neighbors": (C.c_int, [_P, _I]),
     "athk_upload": (C.c_int, [_P, C.c_int, C.c_int, _D]),

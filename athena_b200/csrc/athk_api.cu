@@ -70,6 +70,10 @@ struct athk_ctx {
   idx_t max_ghost_count, max_emf_count;
   SlabTable *slab_tab;   // device
   bool dt_requested, dt_valid;   // NewBlockTimeStep fused into the next / last W(U)
+  // optional per-kernel timing with CUDA events on the launching stream (athk_profile)
+  bool prof_on;
+  struct ProfRec { const char *name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
   Real *geo_store;  // 9 arrays [nb][PG]
   int *nbr;         // [nb][27]
   Real *dt_blocks;  // [nb]
@@ -137,6 +141,7 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
   c->dt_requested = c->dt_valid = false;
+  c->prof_on = false;
   c->coords_set = c->nbr_set = false;
   c->nremote = 0;
   memset(&c->rl, 0, sizeof(c->rl));
@@ -216,6 +221,43 @@ extern "C" int athk_sync(athk_ctx *c) {
 }
 
 extern "C" long long athk_launch_count(const athk_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int athk_profile(athk_ctx *c, int enable, char *report, int report_len) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+#ifndef ATHK_EMULATE
+  if (report && report_len > 0) {
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<std::string> names;
+    std::vector<double> ms;
+    std::vector<int> cnt;
+    for (size_t q = 0; q < c->prof.size(); ++q) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, c->prof[q].a, c->prof[q].b) != cudaSuccess) t = 0.f;
+      size_t k = 0;
+      for (; k < names.size(); ++k) if (names[k] == c->prof[q].name) break;
+      if (k == names.size()) { names.push_back(c->prof[q].name); ms.push_back(0.0); cnt.push_back(0); }
+      ms[k] += t;
+      cnt[k]++;
+      cudaEventDestroy(c->prof[q].a);
+      cudaEventDestroy(c->prof[q].b);
+    }
+    c->prof.clear();
+    std::string out = "{";
+    char line[256];
+    for (size_t k = 0; k < names.size(); ++k) {
+      snprintf(line, sizeof(line), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", k ? ", " : "",
+               names[k].c_str(), ms[k], cnt[k]);
+      out += line;
+    }
+    out += "}";
+    snprintf(report, report_len, "%s", out.c_str());
+  }
+#else
+  if (report && report_len > 0) snprintf(report, report_len, "{}");
+#endif
+  c->prof_on = enable != 0;
+  return ATHK_OK;
+}
 extern "C" void *athk_stream(athk_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 //----------------------------------------------------------------------------------------
@@ -383,11 +425,34 @@ extern "C" int athk_device_array(athk_ctx *c, int array, void **dptr, long long 
                                   "first", __func__);                                      \
   } while (0)
 
-#define LAUNCH(c, range, functor)                               \
-  do {                                                          \
-    CU(launch_points((c)->stream, (c)->g.nb, (range), (functor))); \
-    (c)->launches++;                                            \
+#ifndef ATHK_EMULATE
+static void prof_begin(athk_ctx *c, const char *name) {
+  if (!c->prof_on) return;
+  athk_ctx::ProfRec r;
+  r.name = name;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c->stream);
+  c->prof.push_back(r);
+}
+static void prof_end(athk_ctx *c) {
+  if (c->prof_on && !c->prof.empty()) cudaEventRecord(c->prof.back().b, c->stream);
+}
+#else
+static void prof_begin(athk_ctx *, const char *) {}
+static void prof_end(athk_ctx *) {}
+#endif
+
+// one kernel launch, optionally bracketed by CUDA events; named after the API entry point
+#define LAUNCH_NAMED(c, name, call) \
+  do {                            \
+    prof_begin((c), (name));      \
+    CU(call);                     \
+    prof_end(c);                  \
+    (c)->launches++;              \
   } while (0)
+#define LAUNCH(c, range, functor) \
+  LAUNCH_NAMED(c, __func__, launch_points((c)->stream, (c)->g.nb, (range), (functor)))
 
 static bool bad_reg(int r) { return r < 0 || r > 2; }
 
@@ -617,20 +682,35 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
   if (what_mask & 1) {
     if (!c->u[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: u register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
-    GhostFillCC f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
-    LAUNCH(c, r, f);
+    if (c->rl.n > 0) {
+      GhostFillCC<true> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
+      LAUNCH(c, r, f);
+    } else {
+      GhostFillCC<false> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
+      LAUNCH(c, r, f);
+    }
   }
   if (what_mask & 2) {
     if (!c->cfg.mhd || !c->b[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: b register %d not allocated", reg);
     Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
-    GhostFillFC f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
-    LAUNCH(c, r, f);
+    if (c->rl.n > 0) {
+      GhostFillFC<true> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
+      LAUNCH(c, r, f);
+    } else {
+      GhostFillFC<false> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
+      LAUNCH(c, r, f);
+    }
   }
   if (what_mask & 4) {
     if (!c->s[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: s register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
-    GhostFillCC f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
-    LAUNCH(c, r, f);
+    if (c->rl.n > 0) {
+      GhostFillCC<true> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
+      LAUNCH(c, r, f);
+    } else {
+      GhostFillCC<false> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
+      LAUNCH(c, r, f);
+    }
   }
   return ATHK_OK;
 }
@@ -733,12 +813,13 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
 #ifndef ATHK_EMULATE
   // x2 columns (i,k) / x3 columns (i,j): CTA-marching tiles (athk_sweep_kernels.cuh);
   // extents of calculate_fluxes.cpp:176-182,299-302
-  CU((launch_sweep_tile<1, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.ks - 1 : g.ks,
-                                       MHD ? g.ke + 1 : g.ke, g.is - 1, g.ie + 1)));
-  CU((launch_sweep_tile<2, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.js - 1 : g.js,
-                                       MHD ? g.je + 1 : g.je, MHD ? g.is - 1 : g.is,
-                                       MHD ? g.ie + 1 : g.ie)));
-  c->launches += 2;
+  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x2_donor" : "sweep_x2_plm",
+               (launch_sweep_tile<1, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.ks - 1 : g.ks,
+                                                 MHD ? g.ke + 1 : g.ke, g.is - 1, g.ie + 1)));
+  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x3_donor" : "sweep_x3_plm",
+               (launch_sweep_tile<2, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.js - 1 : g.js,
+                                                 MHD ? g.je + 1 : g.je, MHD ? g.is - 1 : g.is,
+                                                 MHD ? g.ie + 1 : g.ie)));
 #else
   {   // host harness: the same sweeps as per-thread marches
     Range3 r = {g.ks, g.ke, 0, 0, g.is - 1, g.ie + 1};
@@ -757,8 +838,8 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
     Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
     if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
     SweepX1<ORDER, MHD> f = {a};
-    CU(launch_sweep_x1(c->stream, g.nb, r, f));
-    c->launches++;
+    LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x1_donor_integrate" : "sweep_x1_plm_integrate",
+                 launch_sweep_x1(c->stream, g.nb, r, f));
   }
   return ATHK_OK;
 }
@@ -827,7 +908,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
       Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
       CTIntegratePoint f = {g, c->geo, c->e, fi};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, "ct_integrate", launch_points(c->stream, g.nb, r, f));
       if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
     }
     return athk_remote_pack_ghosts(c, 0);
@@ -915,8 +996,7 @@ extern "C" int athk_remote_pack_ghosts(athk_ctx *c, int reg) {
   if (!c->rl.gsbuf) return fail(ATHK_ERR_STATE, "remote_pack_ghosts: call athk_remote_set_buffers first");
   RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, c->rl, c->u[reg],
                        c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr};
-  CU(launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
-  c->launches++;
+  LAUNCH_NAMED(c, __func__, launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
   return ATHK_OK;
 }
 
@@ -925,7 +1005,6 @@ extern "C" int athk_remote_pack_emf(athk_ctx *c) {
   if (c->rl.n == 0 || !c->cfg.mhd) return ATHK_OK;
   if (!c->rl.esbuf) return fail(ATHK_ERR_STATE, "remote_pack_emf: call athk_remote_set_buffers first");
   RemoteEmfPack f = {c->sf, c->rl, c->emfbuf};
-  CU(launch_links(c->stream, c->rl.n, c->max_emf_count, f));
-  c->launches++;
+  LAUNCH_NAMED(c, __func__, launch_links(c->stream, c->rl.n, c->max_emf_count, f));
   return ATHK_OK;
 }

@@ -19,6 +19,7 @@
 // ---- minimal stand-ins for the CUDA runtime calls the API layer uses ----------------------
 typedef int cudaError_t;
 typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
 #define cudaSuccess 0
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }

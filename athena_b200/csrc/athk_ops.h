@@ -674,6 +674,7 @@ struct RemoteEmfPack {
 // Process + SetBoundarySameLevel move through a staging buffer; bvals_cc.cpp:287-302,386-420,
 // bvals_var.cpp:108-119).  Neighbour on another GPU (table entry <= -2): read the received
 // message.  Launched over the full box k in [0,nc3-1] etc.
+template <bool REMOTE>
 struct GhostFillCC {
   Grid g;
   int nvar;
@@ -693,7 +694,7 @@ struct GhostFillCC {
       const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
       for (int n = 0; n < nvar; ++n)
         u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
-    } else {
+    } else if (REMOTE) {
       const int link = -id - 2;
       const int os = nbr_slot(o1, o2, o3);
       const Slab cc = rl.tab->slab[os][0];
@@ -707,6 +708,7 @@ struct GhostFillCC {
 
 // Face-centred version (bvals_fc.cpp:344-397 load, 583-680 set).
 // Launched over k in [0,nc3], j in [0,nc2], i in [0,nc1].
+template <bool REMOTE>
 struct GhostFillFC {
   Grid g;
   Real *b;          // [nb][3][sn]
@@ -730,7 +732,7 @@ struct GhostFillFC {
       if (id >= 0) {
         const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
         b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
-      } else {
+      } else if (REMOTE) {
         const int link = -id - 2;
         const int os = nbr_slot(o1, o2, o3);
         const Slab f = rl.tab->slab[os][1 + d];

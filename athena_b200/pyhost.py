@@ -321,8 +321,8 @@ class TimeIntegrator:
     def step(self, tlim=None, reduce_min=None):
         nst = len(self.stages)
         for stage in range(1, nst + 1):
-            if stage == nst:   # NEW_DT runs on the last stage only (time_integrator.cpp:2313)
-                self.ctx.call("athk_request_block_dt")
+            # (athk_request_block_dt could fold NEW_DT into this stage's W(U); measured slower
+            #  than the separate reduction kernel on B200, so it is not used here)
             self.one_stage(stage)
         self.ncycle += 1
         self.time += self.dt

@@ -23,6 +23,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_ALG_MHD_VL2 = 320.0   # algorithmic bytes per zone-cycle, SURVEY.md section 8(d)
+# algorithmic bytes per zone of ONE launch of the named kernel (kernel table)
+DOMINANT_ALG_BYTES = {"sweep_x1": 31 * 8, "sweep_x2": 16 * 8, "sweep_x3": 16 * 8}
+
+
+def ncu_traffic(kernel):
+    """dram bytes of the kernel from the committed ncu capture (profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    for k, v in d.items():
+        if kernel.startswith(k):
+            return v
+    return None
 
 
 def measured_peaks():
@@ -34,40 +48,61 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled through
+    NVML every few ms (nvidia-smi itself takes ~0.5 s per query, longer than a short timed
+    region); falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, dev):
         super().__init__(daemon=True)
         self.dev = dev
-        self.rows = []
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
         self.stop_flag = False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[dev]) if vis and vis.split(",")[dev].isdigit() else dev
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         while not self.stop_flag:
             try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True,
-                                   text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.005)
 
     def summary(self):
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        if self.h is None or not self.sm:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+                a, b = [float(x) for x in r.stdout.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi (idle)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None,
+                "source": "nvml"}
 
 
 def weak_mesh(ngpu, per_gpu):
@@ -282,23 +317,15 @@ def run_ours(args):
     sampler.stop_flag = True
     value = zones * args.steps / (ms * 1e-3)
 
-    # ---- per-kernel breakdown (CUDA events around every operator call, 2 extra cycles) --------
+    # ---- per-kernel breakdown, measured live with CUDA events on the launching stream --------
+    # (athk_profile brackets every kernel launch inside the library; the NCCL exchanges are
+    # bracketed here).  2 extra cycles after the timed region, so `value` is not perturbed.
     breakdown = {}
+    nprof = 2
+    evs = []
+    xch = getattr(ctx, "xch", None)
     if rank == 0:
-        orig_call = ctx.call
-        evs = []
-
-        def timed_call(name, *a):
-            if name in ("athk_sync", "athk_new_block_dt", "athk_swap_registers"):
-                return orig_call(name, *a)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(stream)
-            orig_call(name, *a)
-            e.record(stream)
-            key = name + (":phase%d" % a[0] if name == "athk_stage_phase" else "")
-            evs.append((key, s, e))
-        ctx.call = timed_call
-        xch = getattr(ctx, "xch", None)
+        ctx.call("athk_profile", 1, None, 0)
         if xch is not None:
             def wrap(fn, key):
                 def g():
@@ -311,16 +338,21 @@ def run_ours(args):
             orig_xg, orig_xe = xch.exchange_ghosts, xch.exchange_emf
             xch.exchange_ghosts = wrap(orig_xg, "nccl_exchange_ghosts")
             xch.exchange_emf = wrap(orig_xe, "nccl_exchange_emf")
-    for _ in range(2):
+    for _ in range(nprof):
         step()
     if rank == 0:
-        ctx.call = orig_call
-        if getattr(ctx, "xch", None) is not None:
-            ctx.xch.exchange_ghosts, ctx.xch.exchange_emf = orig_xg, orig_xe
-        ctx.sync()
-        torch.cuda.synchronize()
-        for name, s, e in evs:
-            breakdown[name] = breakdown.get(name, 0.0) + s.elapsed_time(e) / 2.0
+        buf = C.create_string_buffer(16384)
+        ctx.call("athk_profile", 0, buf, len(buf))
+        rep = json.loads(buf.value.decode() or "{}")
+        for k, v in rep.items():
+            breakdown[k] = {"ms_per_cycle": v["ms"] / nprof, "launches_per_cycle": v["launches"] / nprof}
+        if xch is not None:
+            xch.exchange_ghosts, xch.exchange_emf = orig_xg, orig_xe
+            torch.cuda.synchronize()
+            for name, s_, e_ in evs:
+                d = breakdown.setdefault(name, {"ms_per_cycle": 0.0, "launches_per_cycle": 0.0})
+                d["ms_per_cycle"] += s_.elapsed_time(e_) / nprof
+                d["launches_per_cycle"] += 1.0 / nprof
     barrier()
 
     # ---- e2e: host buffers in, host buffers out, every step ---------------------------------
@@ -341,16 +373,32 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         per_gpu_value = value / world
         achieved = per_gpu_value * B_ALG_MHD_VL2 / 1e9
-        tot = sum(breakdown.values()) or 1.0
-        top = max(breakdown, key=breakdown.get) if breakdown else None
+        tot = sum(v["ms_per_cycle"] for v in breakdown.values()) or 1.0
+        top = max(breakdown, key=lambda k: breakdown[k]["ms_per_cycle"]) if breakdown else None
+        dominant = None
+        if top:
+            t = breakdown[top]
+            ms_launch = t["ms_per_cycle"] / max(t["launches_per_cycle"], 1e-9)
+            # algorithmic bytes of one launch of the final x1 sweep, per zone: reads w(5) + bcc(2)
+            # + b.x1f(1) + d2(5) + d3(5) + u(5), writes u(5) + 2 face EMFs + CT weight = 31 doubles
+            alg = DOMINANT_ALG_BYTES.get(top.split("_plm")[0].split("_donor")[0], None)
+            dominant = {"kernel": top, "ms_per_launch": ms_launch,
+                        "share_of_step": t["ms_per_cycle"] / tot,
+                        "alg_bytes_per_zone": alg}
+            if alg:
+                gbs = alg * args.per_gpu ** 3 / (ms_launch * 1e-3) / 1e9
+                dominant.update({"achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
+            tr = ncu_traffic(top)
+            if tr:
+                dominant.update(tr)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
-                "kernel": "whole VL2 cycle (all kernels of the step), %g algorithmic B/zone-cycle"
-                          % B_ALG_MHD_VL2,
-                "peak_source": peak_src,
-                "breakdown_ms_per_cycle": {k: round(v, 4) for k, v in sorted(
-                    breakdown.items(), key=lambda kv: -kv[1])},
-                "top_operator": top, "top_share": (breakdown[top] / tot) if top else None}
+                "frac": achieved / peak, "traffic": (dominant or {}).get("traffic"),
+                "kernel": "whole VL2 cycle = every kernel of the step; %g algorithmic B/zone-cycle "
+                          "(SURVEY 8d). The sweeps are FP64-issue bound, not HBM bound: see "
+                          "fp64_pipe_pct in profiles/ and DESIGN.md" % B_ALG_MHD_VL2,
+                "peak_source": peak_src, "dominant": dominant,
+                "breakdown_ms_per_cycle": {k: round(v["ms_per_cycle"], 4) for k, v in sorted(
+                    breakdown.items(), key=lambda kv: -kv[1]["ms_per_cycle"])}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:

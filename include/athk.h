@@ -81,6 +81,11 @@ const char *athk_last_error(void);
 int athk_sync(athk_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 long long athk_launch_count(const athk_ctx *ctx);
+/* Per-kernel timing with CUDA events on the context's stream.  enable != 0 starts recording an
+ * event pair around every launch; a non-NULL report receives (after a synchronise) a JSON object
+ * {"<entry point or sweep name>": {"ms": total, "launches": n}, ...} of what was recorded since
+ * the last report.  Used by bench.py for the live roofline numbers. */
+int athk_profile(athk_ctx *ctx, int enable, char *report, int report_len);
 /* raw CUDA stream handle (cudaStream_t) so a host framework can order its own work after ours */
 void *athk_stream(athk_ctx *ctx);
 
