@@ -1,0 +1,285 @@
+// athena.hpp -- C++ host side of athena-b200: the reference's Mesh / MeshBlock / Coordinates /
+// ParameterInput / TimeIntegratorTaskList / pgen API (names, argument meaning, error behaviour)
+// re-implemented as thin glue above the C ABI of libathk.so (include/athk.h).  Field data live in
+// HBM; MeshBlock::phydro->u etc. are HOST arrays used by problem generators and outputs only
+// (uploaded after ProblemGenerator, downloaded at output times), exactly the access pattern the
+// reference's pgens and outputs have.
+//
+// What the reference fixes at configure time (configure.py: --prob, -b, --flux, --nghost,
+// --nscalars) is a run-time choice here (Config), taken from the command line or from the
+// athinput's `<comment> configure = ...` line.
+//
+// Reference: src/athena.hpp, src/athena_arrays.hpp, src/parameter_input.hpp, src/mesh/mesh.hpp,
+// src/coordinates/coordinates.hpp, src/hydro/hydro.hpp, src/field/field.hpp,
+// src/task_list/task_list.hpp (file:line cited at each definition).
+#ifndef ATHENA_B200_HOST_ATHENA_HPP_
+#define ATHENA_B200_HOST_ATHENA_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/athk.h"
+
+using Real = double;   // athena.hpp:39
+
+// athena.hpp:169-192
+enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4 };
+enum { IVX = 1, IVY = 2, IVZ = 3, IPR = 4, IBY = 5, IBZ = 6 };
+enum { IB1 = 0, IB2 = 1, IB3 = 2 };
+enum { X1DIR = 0, X2DIR = 1, X3DIR = 2 };
+constexpr int NHYDRO = 5;
+
+// defs.hpp.in:137-159
+#define PI 3.1415926535897932
+#define TWO_PI 6.2831853071795862
+#define ONE_3RD 0.33333333333333333
+#define TWO_3RD 0.66666666666666667
+#define TINY_NUMBER 1.0e-20
+#define SQR(x) ((x) * (x))
+#define SIGN(x) (((x) < 0.0) ? -1.0 : 1.0)
+#define ATHENA_ERROR(x) throw std::runtime_error(x.str().c_str())
+
+// run-time stand-in for the configure-time macros of src/defs.hpp
+struct Config {
+  std::string problem = "";
+  bool mhd = false;           // MAGNETIC_FIELDS_ENABLED
+  std::string flux = "";      // RIEMANN_SOLVER (default hllc / hlld)
+  int nghost = 2;             // NGHOST
+  int nscalars = 0;           // NSCALARS
+  int nwave() const { return mhd ? 7 : 5; }
+};
+extern Config g_config;
+#define MAGNETIC_FIELDS_ENABLED (g_config.mhd)
+#define NGHOST (g_config.nghost)
+#define NSCALARS (g_config.nscalars)
+#define NWAVE (g_config.nwave())
+#define NON_BAROTROPIC_EOS 1
+
+//----------------------------------------------------------------------------------------
+// AthenaArray (athena_arrays.hpp:25-171): dense, last index fastest
+template <typename T>
+class AthenaArray {
+ public:
+  void NewAthenaArray(int n1) { Alloc(1, 1, 1, n1); }
+  void NewAthenaArray(int n2, int n1) { Alloc(1, 1, n2, n1); }
+  void NewAthenaArray(int n3, int n2, int n1) { Alloc(1, n3, n2, n1); }
+  void NewAthenaArray(int n4, int n3, int n2, int n1) { Alloc(n4, n3, n2, n1); }
+  int GetDim1() const { return n1_; }
+  int GetDim2() const { return n2_; }
+  int GetDim3() const { return n3_; }
+  int GetDim4() const { return n4_; }
+  std::size_t GetSize() const { return d_.size(); }
+  std::size_t GetSizeInBytes() const { return d_.size() * sizeof(T); }
+  bool IsAllocated() const { return !d_.empty(); }
+  T *data() { return d_.data(); }
+  const T *data() const { return d_.data(); }
+  T &operator()(int i) { return d_[i]; }
+  const T &operator()(int i) const { return d_[i]; }
+  T &operator()(int j, int i) { return d_[i + n1_ * j]; }
+  const T &operator()(int j, int i) const { return d_[i + n1_ * j]; }
+  T &operator()(int k, int j, int i) { return d_[i + n1_ * (j + n2_ * (std::size_t)k)]; }
+  const T &operator()(int k, int j, int i) const { return d_[i + n1_ * (j + n2_ * (std::size_t)k)]; }
+  T &operator()(int n, int k, int j, int i) { return d_[i + n1_ * (j + n2_ * (k + n3_ * (std::size_t)n))]; }
+  const T &operator()(int n, int k, int j, int i) const {
+    return d_[i + n1_ * (j + n2_ * (k + n3_ * (std::size_t)n))];
+  }
+  void ZeroClear() { std::fill(d_.begin(), d_.end(), T()); }
+  void SwapAthenaArray(AthenaArray<T> &o) {
+    d_.swap(o.d_);
+    std::swap(n1_, o.n1_); std::swap(n2_, o.n2_); std::swap(n3_, o.n3_); std::swap(n4_, o.n4_);
+  }
+
+ private:
+  void Alloc(int n4, int n3, int n2, int n1) {
+    n1_ = n1; n2_ = n2; n3_ = n3; n4_ = n4;
+    d_.assign((std::size_t)n4 * n3 * n2 * n1, T());
+  }
+  std::vector<T> d_;
+  int n1_ = 0, n2_ = 0, n3_ = 0, n4_ = 0;
+};
+
+struct FaceField { AthenaArray<Real> x1f, x2f, x3f; };   // athena.hpp:128-138
+
+//----------------------------------------------------------------------------------------
+// ParameterInput (parameter_input.hpp:70-119): <block> / name = value # comment
+class ParameterInput {
+ public:
+  struct Line { std::string name, value, comment; };
+  struct Block { std::string name; std::vector<Line> lines; };
+  void LoadFromFile(const std::string &fname);
+  void LoadFromStream(std::istream &is);
+  void ModifyFromCmdline(int argc, char *argv[]);
+  void ParameterDump(std::ostream &os) const;
+  int DoesParameterExist(const std::string &block, const std::string &name) const;
+  bool DoesBlockExist(const std::string &block) const { return Find(block) != nullptr; }
+  int GetInteger(const std::string &block, const std::string &name) const;
+  Real GetReal(const std::string &block, const std::string &name) const;
+  bool GetBoolean(const std::string &block, const std::string &name) const;
+  std::string GetString(const std::string &block, const std::string &name) const;
+  int GetOrAddInteger(const std::string &block, const std::string &name, int def);
+  Real GetOrAddReal(const std::string &block, const std::string &name, Real def);
+  bool GetOrAddBoolean(const std::string &block, const std::string &name, bool def);
+  std::string GetOrAddString(const std::string &block, const std::string &name, const std::string &def);
+  int SetInteger(const std::string &block, const std::string &name, int v);
+  Real SetReal(const std::string &block, const std::string &name, Real v);
+  std::string SetString(const std::string &block, const std::string &name, const std::string &v);
+  const std::vector<Block> &blocks() const { return blocks_; }
+
+ private:
+  const Block *Find(const std::string &b) const;
+  Block *FindOrAdd(const std::string &b);
+  const Line *FindLine(const std::string &b, const std::string &n, const char *who) const;
+  void Add(Block *pb, const std::string &n, const std::string &v, const std::string &c);
+  std::vector<Block> blocks_;
+};
+
+//----------------------------------------------------------------------------------------
+struct RegionSize {   // mesh.hpp / athena.hpp:150-160 (same member order as the reference: the
+  Real x1min, x2min, x3min;   // struct is written raw into restart files)
+  Real x1max, x2max, x3max;
+  Real x1rat, x2rat, x3rat;
+  int nx1, nx2, nx3;
+};
+struct LogicalLocation {   // athena.hpp:104-118
+  std::int64_t lx1, lx2, lx3;
+  int level;
+};
+
+enum class BoundaryFlag { block = -1, undef, reflect, outflow, user, periodic };
+
+class Mesh;
+class MeshBlock;
+
+// Coordinates (coordinates/coordinates.hpp, cartesian.cpp): 1-D arrays, uniform Cartesian
+class Coordinates {
+ public:
+  Coordinates(MeshBlock *pmb, Mesh *pm);
+  AthenaArray<Real> x1f, x2f, x3f, x1v, x2v, x3v, dx1f, dx2f, dx3f, dx1v, dx2v, dx3v;
+  Real GetCellVolume(int k, int j, int i) const { return dx1f(i) * dx2f(j) * dx3f(k); }
+};
+
+class Hydro {   // hydro/hydro.hpp:32-122 (host mirrors only)
+ public:
+  explicit Hydro(MeshBlock *pmb);
+  AthenaArray<Real> u, w;
+};
+class Field {   // field/field.hpp:30-75
+ public:
+  explicit Field(MeshBlock *pmb);
+  FaceField b;
+  AthenaArray<Real> bcc;
+};
+class PassiveScalars {
+ public:
+  explicit PassiveScalars(MeshBlock *pmb);
+  AthenaArray<Real> s, r;
+};
+class EquationOfState {   // eos/eos.hpp:32-181
+ public:
+  explicit EquationOfState(ParameterInput *pin);
+  Real GetGamma() const { return gamma_; }
+  Real GetDensityFloor() const { return dfloor_; }
+  Real GetPressureFloor() const { return pfloor_; }
+ private:
+  Real gamma_, dfloor_, pfloor_;
+};
+
+class MeshBlock {   // mesh/mesh.hpp:75-200
+ public:
+  MeshBlock(int gid, int lid, LogicalLocation loc, RegionSize bs, Mesh *pm, ParameterInput *pin);
+  ~MeshBlock();
+  void ProblemGenerator(ParameterInput *pin);   // dispatches to the selected pgen
+  Mesh *pmy_mesh;
+  LogicalLocation loc;
+  RegionSize block_size;
+  int gid, lid;
+  int is, ie, js, je, ks, ke;
+  int ncells1, ncells2, ncells3;
+  Coordinates *pcoord;
+  Hydro *phydro;
+  Field *pfield;
+  PassiveScalars *pscalars;
+  EquationOfState *peos;
+  Real new_block_dt_;
+};
+
+typedef void (*PgenFn)(MeshBlock *pmb, ParameterInput *pin);
+typedef void (*MeshHookFn)(Mesh *pm, ParameterInput *pin);
+struct ProblemGeneratorEntry {
+  const char *name;
+  MeshHookFn init_user_mesh_data;    // Mesh::InitUserMeshData
+  PgenFn problem_generator;          // MeshBlock::ProblemGenerator
+  MeshHookFn user_work_after_loop;   // Mesh::UserWorkAfterLoop
+};
+const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name);
+
+class Mesh {   // mesh/mesh.hpp:206-447
+ public:
+  Mesh(ParameterInput *pin);
+  ~Mesh();
+  void Initialize(ParameterInput *pin);   // mesh.cpp:1622
+  void NewTimeStep();                     // mesh.cpp:1236
+  void UserWorkAfterLoop(ParameterInput *pin);
+  void OutputCycleDiagnostics();          // mesh.cpp:2304
+  void DownloadAll();                     // device -> host mirrors (outputs)
+  MeshBlock *my_blocks(int b) { return blocks_[b]; }
+  RegionSize mesh_size;
+  BoundaryFlag mesh_bcs[6];
+  bool f2, f3;
+  int ndim;
+  Real start_time, time, tlim, dt, cfl_number;
+  int nlim, ncycle, ncycle_out;
+  int nbtotal, nblocal, root_level;
+  int nrbx1, nrbx2, nrbx3;
+  std::vector<LogicalLocation> loclist;
+  athk_ctx *athk;
+  const ProblemGeneratorEntry *pgen;
+  bool fused_stage;
+  // user history output (mesh.hpp: EnrollUserHistoryOutput)
+  typedef Real (*HistoryFn)(MeshBlock *pmb, int iout);
+  struct UserHistory { HistoryFn fn; std::string name; int op; /*0 sum,1 max,2 min*/ };
+  std::vector<UserHistory> user_history;
+  void EnrollUserHistoryOutput(HistoryFn fn, const char *name, int op) { user_history.push_back({fn, name, op}); }
+
+ private:
+  std::vector<MeshBlock *> blocks_;
+};
+
+void AthkCheck(int rc, const char *where);   // non-zero return -> ATHENA_ERROR(athk_last_error)
+
+// TimeIntegratorTaskList (task_list/time_integrator.cpp:42-1206)
+class TimeIntegratorTaskList {
+ public:
+  TimeIntegratorTaskList(ParameterInput *pin, Mesh *pm);
+  void DoTaskListOneStage(Mesh *pm, int stage);   // task_list.cpp:66
+  std::string integrator;
+  int nstages;
+  Real cfl_limit;
+  struct IntegratorWeight { Real delta, gamma_1, gamma_2, gamma_3, beta; };
+  IntegratorWeight stage_wghts[6];
+  int xorder;
+};
+
+// Outputs (outputs/outputs.hpp): history (.hst) and restart (.rst) writers
+class Outputs {
+ public:
+  Outputs(Mesh *pm, ParameterInput *pin);
+  void MakeOutputs(Mesh *pm, ParameterInput *pin, bool wtflag = false);   // outputs.cpp:1490
+ private:
+  struct OutputParameters {
+    std::string block_name, file_type, file_basename, data_format;
+    Real dt, next_time;
+    int dcycle, file_number;
+  };
+  std::vector<OutputParameters> types_;
+  void WriteHistory(OutputParameters &op, Mesh *pm, ParameterInput *pin);
+  void WriteRestart(OutputParameters &op, Mesh *pm, ParameterInput *pin, bool force);
+};
+
+#endif  // ATHENA_B200_HOST_ATHENA_HPP_

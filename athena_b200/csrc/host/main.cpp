@@ -1,0 +1,117 @@
+// main.cpp -- driver of the B200 host: argv -> ParameterInput -> Mesh -> TimeIntegratorTaskList
+// -> main loop, following src/main.cpp:65-666 (flags :125-203, setup :230-424, loop :457-571,
+// wrap-up :584-652).  Prints the reference's own throughput lines (zone-cycles/...second).
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "athena.hpp"
+
+static void ParseConfigure(const std::string &s) {
+  // the tokens configure.py would take: --prob=<name> -b --flux=<name> --nghost=<n> --nscalars=<n>
+  std::stringstream ss(s);
+  std::string t;
+  while (ss >> t) {
+    if (t.compare(0, 7, "--prob=") == 0) g_config.problem = t.substr(7);
+    else if (t == "-b") g_config.mhd = true;
+    else if (t.compare(0, 7, "--flux=") == 0) g_config.flux = t.substr(7);
+    else if (t.compare(0, 9, "--nghost=") == 0) g_config.nghost = std::atoi(t.c_str() + 9);
+    else if (t.compare(0, 11, "--nscalars=") == 0) g_config.nscalars = std::atoi(t.c_str() + 11);
+  }
+}
+
+int main(int argc, char *argv[]) {
+  std::string input_filename, run_dir;
+  bool narg_flag = false, have_cfg = false;
+  std::string cfg_cmdline;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "-i" && i + 1 < argc) input_filename = argv[++i];
+    else if (a == "-d" && i + 1 < argc) run_dir = argv[++i];
+    else if (a == "-n") narg_flag = true;
+    else if (a == "-h") {
+      std::cout << "Athena++ (B200 path)" << std::endl
+                << "Usage: " << argv[0] << " [options] [block/par=value ...]" << std::endl
+                << "  -i <file>   specify input file [athinput]" << std::endl
+                << "  -d <dir>    specify run dir [current dir]" << std::endl
+                << "  -n          parse input file and quit" << std::endl
+                << "  --prob=<pgen> [-b] [--flux=..] [--nghost=n] [--nscalars=n]  configure-time choices "
+                   "of the reference (default: the athinput's <comment> configure line)" << std::endl;
+      return 0;
+    } else if (a.compare(0, 2, "--") == 0 || a == "-b") {
+      cfg_cmdline += a + " ";
+      have_cfg = true;
+    }
+  }
+  if (input_filename.empty()) {
+    std::cout << "### FATAL ERROR in main" << std::endl << "No input file or restart file is specified." << std::endl;
+    return 1;
+  }
+  try {
+    ParameterInput *pinput = new ParameterInput;
+    pinput->LoadFromFile(input_filename);
+    pinput->ModifyFromCmdline(argc, argv);
+    if (have_cfg) ParseConfigure(cfg_cmdline);
+    else if (pinput->DoesParameterExist("comment", "configure")) ParseConfigure(pinput->GetString("comment", "configure"));
+    if (!run_dir.empty() && chdir(run_dir.c_str()) != 0) {
+      std::stringstream msg;
+      msg << "### FATAL ERROR in function [ChangeRunDir]" << std::endl << "Cannot cd to directory '" << run_dir << "'";
+      ATHENA_ERROR(msg);
+    }
+    Mesh *pmesh = new Mesh(pinput);
+    TimeIntegratorTaskList *ptlist = new TimeIntegratorTaskList(pinput, pmesh);
+    if (narg_flag) {
+      pinput->ParameterDump(std::cout);
+      return 0;
+    }
+    pmesh->Initialize(pinput);
+    Outputs *pouts = new Outputs(pmesh, pinput);
+    pouts->MakeOutputs(pmesh, pinput);
+
+    std::cout << "\nSetup complete, entering main loop...\n" << std::endl;
+    std::uint64_t mbcnt = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while ((pmesh->time < pmesh->tlim) && (pmesh->nlim < 0 || pmesh->ncycle < pmesh->nlim)) {
+      pmesh->OutputCycleDiagnostics();
+      for (int stage = 1; stage <= ptlist->nstages; ++stage) ptlist->DoTaskListOneStage(pmesh, stage);
+      pmesh->ncycle++;
+      pmesh->time += pmesh->dt;
+      mbcnt += pmesh->nbtotal;
+      pmesh->NewTimeStep();
+      if (pmesh->time < pmesh->tlim) pouts->MakeOutputs(pmesh, pinput);   // final output happens later (main.cpp:546)
+    }
+    AthkCheck(athk_sync(pmesh->athk), "main");
+    const double wsec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    pmesh->OutputCycleDiagnostics();
+    pmesh->UserWorkAfterLoop(pinput);
+    pouts->MakeOutputs(pmesh, pinput, true);   // final outputs (main.cpp:589)
+
+    if (pmesh->ncycle == pmesh->nlim) std::cout << std::endl << "Terminating on cycle limit" << std::endl;
+    else std::cout << std::endl << "Terminating on time limit" << std::endl;
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "time=%.16e cycle=%d\ntlim=%.16e nlim=%d\n", pmesh->time, pmesh->ncycle,
+                  pmesh->tlim, pmesh->nlim);
+    std::cout << buf << std::endl;
+    const MeshBlock *pb = pmesh->my_blocks(0);
+    const std::uint64_t zonecycles = mbcnt * static_cast<std::uint64_t>(pb->block_size.nx1) * pb->block_size.nx2 *
+                                     pb->block_size.nx3;   // main.cpp:639-641
+    std::snprintf(buf, sizeof(buf),
+                  "zone-cycles = %llu\ngpu wtime used = %.16e\nzone-cycles/gpu_wsecond = %.16e\n"
+                  "kernel launches = %lld\n",
+                  (unsigned long long)zonecycles, wsec, zonecycles / wsec, athk_launch_count(pmesh->athk));
+    std::cout << buf << std::endl;
+    delete pouts;
+    delete ptlist;
+    delete pmesh;
+    delete pinput;
+  } catch (std::bad_alloc &ba) {
+    std::cout << "### FATAL ERROR in main" << std::endl << "memory allocation failed: " << ba.what() << std::endl;
+    return 1;
+  } catch (std::exception const &ex) {
+    std::cout << ex.what() << std::endl;   // the reference prints the ATHENA_ERROR message and exits(1)
+    return 1;
+  }
+  return 0;
+}

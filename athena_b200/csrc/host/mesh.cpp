@@ -1,0 +1,329 @@
+// mesh.cpp -- Mesh / MeshBlock / Coordinates of the host side.
+// Follows src/mesh/mesh.cpp:72-567 (constructor: <mesh>/<meshblock> parsing, root level, Z-ordered
+// block list), :1622-1967 (Initialize), :1236-1282 (NewTimeStep), :1984-2060
+// (SetBlockSizeAndBoundaries), src/mesh/meshblock.cpp:62-261, src/coordinates/coordinates.cpp:
+// 100-324 + cartesian.cpp:24-60, mesh.hpp:457-473,535-560 (uniform mesh generator).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <limits>
+
+#include "athena.hpp"
+
+Config g_config;
+
+void AthkCheck(int rc, const char *where) {
+  if (rc != 0) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in " << where << std::endl << "libathk: " << athk_last_error();
+    ATHENA_ERROR(msg);
+  }
+}
+
+// mesh.hpp:457-473 (sym_interval = true) and :535-538
+static Real ComputeMeshGeneratorX(std::int64_t index, std::int64_t nrange) {
+  const std::int64_t noffset = index - (nrange) / 2;
+  const std::int64_t noffset_ceil = index - (nrange + 1) / 2;
+  return static_cast<Real>(noffset + noffset_ceil) / (2.0 * nrange);
+}
+static Real UniformMeshGenerator(Real x, Real xmin, Real xmax) {
+  return static_cast<Real>(0.5) * (xmin + xmax) + (x * xmax - x * xmin);
+}
+
+static BoundaryFlag GetBoundaryFlag(const std::string &s) {   // bvals/utils/boundary_flag.cpp
+  if (s == "periodic") return BoundaryFlag::periodic;
+  if (s == "reflecting") return BoundaryFlag::reflect;
+  if (s == "outflow") return BoundaryFlag::outflow;
+  if (s == "user") return BoundaryFlag::user;
+  if (s == "none") return BoundaryFlag::undef;
+  std::stringstream msg;
+  msg << "### FATAL ERROR in GetBoundaryFlag" << std::endl
+      << "Input string=" << s << " is an invalid boundary type";
+  ATHENA_ERROR(msg);
+}
+
+static std::uint64_t MortonKey(const LogicalLocation &l) {
+  std::uint64_t k = 0;
+  for (int bit = 0; bit < 21; ++bit) {
+    k |= ((std::uint64_t)((l.lx1 >> bit) & 1)) << (3 * bit);
+    k |= ((std::uint64_t)((l.lx2 >> bit) & 1)) << (3 * bit + 1);
+    k |= ((std::uint64_t)((l.lx3 >> bit) & 1)) << (3 * bit + 2);
+  }
+  return k;
+}
+
+//----------------------------------------------------------------------------------------
+Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm) {
+  const int ng = NGHOST;
+  const RegionSize &ms = pm->mesh_size;
+  const RegionSize &bs = pmb->block_size;
+  struct Dir { AthenaArray<Real> *xf, *xv, *dxf, *dxv; int nx, nc; std::int64_t lx; Real bmin, bmax, mmin, mmax; int mnx; };
+  Dir dirs[3] = {
+      {&x1f, &x1v, &dx1f, &dx1v, bs.nx1, pmb->ncells1, pmb->loc.lx1, bs.x1min, bs.x1max, ms.x1min, ms.x1max, ms.nx1},
+      {&x2f, &x2v, &dx2f, &dx2v, bs.nx2, pmb->ncells2, pmb->loc.lx2, bs.x2min, bs.x2max, ms.x2min, ms.x2max, ms.nx2},
+      {&x3f, &x3v, &dx3f, &dx3v, bs.nx3, pmb->ncells3, pmb->loc.lx3, bs.x3min, bs.x3max, ms.x3min, ms.x3max, ms.nx3}};
+  for (Dir &d : dirs) {
+    d.xf->NewAthenaArray(d.nc + 1);
+    d.xv->NewAthenaArray(d.nc);
+    d.dxf->NewAthenaArray(d.nc);
+    d.dxv->NewAthenaArray(d.nc);
+    const int il = ng, iu = ng + d.nx - 1;
+    const std::int64_t nrootmesh = d.mnx;   // uniform level
+    // coordinates.cpp:143-152 (uniform mesh generator branch)
+    const Real dx = (d.bmax - d.bmin) / (iu - il + 1);
+    for (int i = il - ng; i <= iu + ng + 1; ++i) {
+      const std::int64_t noffset = static_cast<std::int64_t>(i - il + d.lx * d.nx);
+      const Real rx = ComputeMeshGeneratorX(noffset, nrootmesh);
+      (*d.xf)(i) = UniformMeshGenerator(rx, d.mmin, d.mmax);
+    }
+    (*d.xf)(il) = d.bmin;
+    (*d.xf)(iu + 1) = d.bmax;
+    for (int i = il - ng; i <= iu + ng; ++i) (*d.dxf)(i) = dx;
+    // cartesian.cpp:27-38
+    for (int i = il - ng; i <= iu + ng; ++i) (*d.xv)(i) = 0.5 * ((*d.xf)(i + 1) + (*d.xf)(i));
+    for (int i = il - ng; i <= iu + ng - 1; ++i) (*d.dxv)(i) = (*d.dxf)(i);
+  }
+}
+
+Hydro::Hydro(MeshBlock *pmb) {
+  u.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  w.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+}
+Field::Field(MeshBlock *pmb) {
+  if (!MAGNETIC_FIELDS_ENABLED) return;
+  b.x1f.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1 + 1);
+  b.x2f.NewAthenaArray(pmb->ncells3, pmb->ncells2 + 1, pmb->ncells1);
+  b.x3f.NewAthenaArray(pmb->ncells3 + 1, pmb->ncells2, pmb->ncells1);
+  bcc.NewAthenaArray(3, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+}
+PassiveScalars::PassiveScalars(MeshBlock *pmb) {
+  if (NSCALARS == 0) return;
+  s.NewAthenaArray(NSCALARS, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  r.NewAthenaArray(NSCALARS, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+}
+EquationOfState::EquationOfState(ParameterInput *pin) {   // eos/adiabatic_*.cpp:26-31
+  const Real float_min = std::numeric_limits<float>::min();
+  gamma_ = pin->GetReal("hydro", "gamma");
+  dfloor_ = pin->GetOrAddReal("hydro", "dfloor", std::sqrt(1024 * float_min));
+  pfloor_ = pin->GetOrAddReal("hydro", "pfloor", std::sqrt(1024 * float_min));
+}
+
+MeshBlock::MeshBlock(int igid, int ilid, LogicalLocation iloc, RegionSize bs, Mesh *pm, ParameterInput *pin)
+    : pmy_mesh(pm), loc(iloc), block_size(bs), gid(igid), lid(ilid), new_block_dt_(0.0) {
+  is = NGHOST; ie = is + bs.nx1 - 1;
+  js = NGHOST; je = js + bs.nx2 - 1;
+  ks = NGHOST; ke = ks + bs.nx3 - 1;
+  ncells1 = bs.nx1 + 2 * NGHOST;
+  ncells2 = bs.nx2 + 2 * NGHOST;
+  ncells3 = bs.nx3 + 2 * NGHOST;
+  pcoord = new Coordinates(this, pm);
+  phydro = new Hydro(this);
+  pfield = new Field(this);
+  pscalars = new PassiveScalars(this);
+  peos = new EquationOfState(pin);
+}
+MeshBlock::~MeshBlock() {
+  delete pcoord; delete phydro; delete pfield; delete pscalars; delete peos;
+}
+void MeshBlock::ProblemGenerator(ParameterInput *pin) {
+  if (pmy_mesh->pgen && pmy_mesh->pgen->problem_generator) pmy_mesh->pgen->problem_generator(this, pin);
+}
+
+//----------------------------------------------------------------------------------------
+Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
+  std::stringstream msg;
+  mesh_size.nx1 = pin->GetInteger("mesh", "nx1");
+  mesh_size.nx2 = pin->GetInteger("mesh", "nx2");
+  mesh_size.nx3 = pin->GetInteger("mesh", "nx3");
+  mesh_size.x1min = pin->GetReal("mesh", "x1min"); mesh_size.x1max = pin->GetReal("mesh", "x1max");
+  mesh_size.x2min = pin->GetReal("mesh", "x2min"); mesh_size.x2max = pin->GetReal("mesh", "x2max");
+  mesh_size.x3min = pin->GetReal("mesh", "x3min"); mesh_size.x3max = pin->GetReal("mesh", "x3max");
+  mesh_size.x1rat = pin->GetOrAddReal("mesh", "x1rat", 1.0);
+  mesh_size.x2rat = pin->GetOrAddReal("mesh", "x2rat", 1.0);
+  mesh_size.x3rat = pin->GetOrAddReal("mesh", "x3rat", 1.0);
+  const char *bn[6] = {"ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc"};
+  for (int n = 0; n < 6; ++n) mesh_bcs[n] = GetBoundaryFlag(pin->GetOrAddString("mesh", bn[n], "none"));
+  start_time = pin->GetOrAddReal("time", "start_time", 0.0);
+  time = start_time;
+  tlim = pin->GetReal("time", "tlim");
+  dt = std::numeric_limits<Real>::max();
+  nlim = pin->GetOrAddInteger("time", "nlim", -1);
+  ncycle = 0;
+  ncycle_out = pin->GetOrAddInteger("time", "ncycle_out", 1);
+  f2 = mesh_size.nx2 > 1;
+  f3 = mesh_size.nx3 > 1;
+  ndim = f3 ? 3 : (f2 ? 2 : 1);
+  if (ndim != 3) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "The B200 path implements 3-D MeshBlocks only (nx1,nx2,nx3 > 1)";
+    ATHENA_ERROR(msg);
+  }
+  if (mesh_size.x1rat != 1.0 || mesh_size.x2rat != 1.0 || mesh_size.x3rat != 1.0 ||
+      pin->GetOrAddString("mesh", "refinement", "none") != "none") {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "The B200 path implements uniform Cartesian meshes without refinement";
+    ATHENA_ERROR(msg);
+  }
+  for (int n = 0; n < 6; ++n) {
+    if (mesh_bcs[n] != BoundaryFlag::periodic) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "The B200 path implements periodic mesh boundaries only (" << bn[n] << ")";
+      ATHENA_ERROR(msg);
+    }
+  }
+  RegionSize bs = mesh_size;
+  bs.nx1 = pin->GetOrAddInteger("meshblock", "nx1", mesh_size.nx1);
+  bs.nx2 = pin->GetOrAddInteger("meshblock", "nx2", mesh_size.nx2);
+  bs.nx3 = pin->GetOrAddInteger("meshblock", "nx3", mesh_size.nx3);
+  if (mesh_size.nx1 % bs.nx1 || mesh_size.nx2 % bs.nx2 || mesh_size.nx3 % bs.nx3) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "the Mesh must be evenly divisible by the MeshBlock";   // mesh.cpp:243-248
+    ATHENA_ERROR(msg);
+  }
+  nrbx1 = mesh_size.nx1 / bs.nx1;
+  nrbx2 = mesh_size.nx2 / bs.nx2;
+  nrbx3 = mesh_size.nx3 / bs.nx3;
+  const int nbmax = std::max(nrbx1, std::max(nrbx2, nrbx3));
+  for (root_level = 0; (1 << root_level) < nbmax; root_level++) {}   // mesh.cpp:265
+  // Z-ordered list of the root-level blocks (meshblock_tree.cpp:336-350)
+  for (std::int64_t k = 0; k < nrbx3; ++k)
+    for (std::int64_t j = 0; j < nrbx2; ++j)
+      for (std::int64_t i = 0; i < nrbx1; ++i) loclist.push_back(LogicalLocation{i, j, k, root_level});
+  std::sort(loclist.begin(), loclist.end(),
+            [](const LogicalLocation &a, const LogicalLocation &b) { return MortonKey(a) < MortonKey(b); });
+  nbtotal = static_cast<int>(loclist.size());
+  nblocal = nbtotal;   // one rank / one GPU in this binary
+
+  pgen = FindProblemGenerator(g_config.problem);
+  if (pgen == nullptr) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "problem generator '" << g_config.problem << "' is not built into this binary";
+    ATHENA_ERROR(msg);
+  }
+  fused_stage = pin->GetOrAddBoolean("time", "fused_stage", true);
+
+  for (int n = 0; n < nbtotal; ++n) {
+    const LogicalLocation &l = loclist[n];
+    RegionSize b = bs;
+    // SetBlockSizeAndBoundaries, mesh.cpp:1984-2060
+    struct { std::int64_t lx; int nrb; Real mmin, mmax; Real *bmin, *bmax; } d[3] = {
+        {l.lx1, nrbx1, mesh_size.x1min, mesh_size.x1max, &b.x1min, &b.x1max},
+        {l.lx2, nrbx2, mesh_size.x2min, mesh_size.x2max, &b.x2min, &b.x2max},
+        {l.lx3, nrbx3, mesh_size.x3min, mesh_size.x3max, &b.x3min, &b.x3max}};
+    for (auto &q : d) {
+      *q.bmin = (q.lx == 0) ? q.mmin : UniformMeshGenerator(ComputeMeshGeneratorX(q.lx, q.nrb), q.mmin, q.mmax);
+      *q.bmax = (q.lx == q.nrb - 1) ? q.mmax
+                                    : UniformMeshGenerator(ComputeMeshGeneratorX(q.lx + 1, q.nrb), q.mmin, q.mmax);
+    }
+    blocks_.push_back(new MeshBlock(n, n, l, b, this, pin));
+  }
+
+  // ---- device context: one for all MeshBlocks of this rank --------------------------------
+  athk_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.nx1 = bs.nx1; cfg.nx2 = bs.nx2; cfg.nx3 = bs.nx3;
+  cfg.nghost = NGHOST;
+  cfg.nblocks = nblocal;
+  cfg.mhd = MAGNETIC_FIELDS_ENABLED ? 1 : 0;
+  cfg.nscalars = NSCALARS;
+  const std::string flux = g_config.flux.empty() ? (MAGNETIC_FIELDS_ENABLED ? "hlld" : "hllc") : g_config.flux;
+  if (flux == "hllc") cfg.rsolver = ATHK_RS_HLLC;
+  else if (flux == "hlld") cfg.rsolver = ATHK_RS_HLLD;
+  else if (flux == "roe") cfg.rsolver = ATHK_RS_ROE;
+  else if (flux == "hlle") cfg.rsolver = ATHK_RS_HLLE;
+  else if (flux == "llf") cfg.rsolver = ATHK_RS_LLF;
+  else {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl << "unknown Riemann solver '" << flux << "'";
+    ATHENA_ERROR(msg);
+  }
+  cfg.device = pin->GetOrAddInteger("mesh", "gpu_device", 0);
+  cfg.gamma = blocks_[0]->peos->GetGamma();
+  cfg.dfloor = blocks_[0]->peos->GetDensityFloor();
+  cfg.pfloor = blocks_[0]->peos->GetPressureFloor();
+  AthkCheck(athk_create(&cfg, &athk), "Mesh constructor (athk_create)");
+  for (int n = 0; n < nblocal; ++n) {
+    Coordinates *pc = blocks_[n]->pcoord;
+    AthkCheck(athk_set_block_coords(athk, n, pc->x1f.data(), pc->x1v.data(), pc->dx1f.data(),
+                                    pc->x2f.data(), pc->x2v.data(), pc->dx2f.data(),
+                                    pc->x3f.data(), pc->x3v.data(), pc->dx3f.data()),
+              "Mesh constructor (athk_set_block_coords)");
+  }
+  // same-level neighbour table (BoundaryBase::SearchAndSetNeighbors, bvals_base.cpp:301):
+  // uniform periodic root grid => the neighbour is the block at the wrapped logical location
+  std::map<std::uint64_t, int> gid_of;
+  for (int n = 0; n < nbtotal; ++n) gid_of[MortonKey(loclist[n])] = n;
+  std::vector<int> nbr((std::size_t)nblocal * 27, -1);
+  for (int n = 0; n < nblocal; ++n) {
+    const LogicalLocation &l = loclist[n];
+    for (int o3 = -1; o3 <= 1; ++o3)
+      for (int o2 = -1; o2 <= 1; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          if (o1 == 0 && o2 == 0 && o3 == 0) continue;
+          LogicalLocation q{(l.lx1 + o1 + nrbx1) % nrbx1, (l.lx2 + o2 + nrbx2) % nrbx2,
+                            (l.lx3 + o3 + nrbx3) % nrbx3, l.level};
+          nbr[(std::size_t)n * 27 + (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1)] = gid_of[MortonKey(q)];
+        }
+  }
+  AthkCheck(athk_set_neighbors(athk, nbr.data()), "Mesh constructor (athk_set_neighbors)");
+  if (pgen->init_user_mesh_data) pgen->init_user_mesh_data(this, pin);   // mesh.cpp:601
+}
+
+Mesh::~Mesh() {
+  for (MeshBlock *p : blocks_) delete p;
+  if (athk) athk_destroy(athk);
+}
+
+// Mesh::Initialize for a fresh run (mesh.cpp:1622-1967): pgen on the host, upload, first
+// boundary exchange, W(U) on interior + ghosts, first time step
+void Mesh::Initialize(ParameterInput *pin) {
+  for (int b = 0; b < nblocal; ++b) {
+    MeshBlock *pmb = blocks_[b];
+    pmb->ProblemGenerator(pin);
+    AthkCheck(athk_upload(athk, ATHK_U, b, pmb->phydro->u.data()), "Mesh::Initialize");
+    if (MAGNETIC_FIELDS_ENABLED) {
+      AthkCheck(athk_upload(athk, ATHK_B_X1F, b, pmb->pfield->b.x1f.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::Initialize");
+    }
+  }
+  AthkCheck(athk_sync(athk), "Mesh::Initialize");
+  AthkCheck(athk_exchange_ghosts(athk, 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0), 0), "Mesh::Initialize");
+  AthkCheck(athk_cons2prim(athk, 0), "Mesh::Initialize");
+  NewTimeStep();
+}
+
+void Mesh::NewTimeStep() {   // mesh.cpp:1236-1282
+  std::vector<Real> bdt(nblocal);
+  Real dtmin;
+  AthkCheck(athk_new_block_dt(athk, cfl_number, bdt.data(), &dtmin), "Mesh::NewTimeStep");
+  for (int b = 0; b < nblocal; ++b) blocks_[b]->new_block_dt_ = bdt[b];
+  dt = static_cast<Real>(2.0) * dt;
+  for (int b = 0; b < nblocal; ++b) dt = std::min(dt, blocks_[b]->new_block_dt_);
+  if (time < tlim && (tlim - time) < dt) dt = tlim - time;
+}
+
+void Mesh::DownloadAll() {
+  for (int b = 0; b < nblocal; ++b) {
+    MeshBlock *pmb = blocks_[b];
+    AthkCheck(athk_download(athk, ATHK_U, b, pmb->phydro->u.data()), "Mesh::DownloadAll");
+    AthkCheck(athk_download(athk, ATHK_W, b, pmb->phydro->w.data()), "Mesh::DownloadAll");
+    if (MAGNETIC_FIELDS_ENABLED) {
+      AthkCheck(athk_download(athk, ATHK_B_X1F, b, pmb->pfield->b.x1f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_BCC, b, pmb->pfield->bcc.data()), "Mesh::DownloadAll");
+    }
+  }
+}
+
+void Mesh::UserWorkAfterLoop(ParameterInput *pin) {
+  if (pgen && pgen->user_work_after_loop) pgen->user_work_after_loop(this, pin);
+}
+
+void Mesh::OutputCycleDiagnostics() {   // mesh.cpp:2304-2333
+  if (ncycle_out != 0 && ncycle % ncycle_out == 0) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "cycle=%d time=%.16e dt=%.16e", ncycle, time, dt);
+    std::cout << buf << std::endl;
+  }
+}

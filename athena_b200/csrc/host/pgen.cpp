@@ -1,0 +1,439 @@
+// pgen.cpp -- problem generators of the BASELINE configs behind the reference's user-hook API
+// (Mesh::InitUserMeshData / MeshBlock::ProblemGenerator / Mesh::UserWorkAfterLoop,
+// src/pgen/default_pgen.cpp:42-86).  They run on the HOST, as in the reference, and the state is
+// uploaded afterwards (Mesh::Initialize); using the host libm also keeps sin/cos bit-identical to
+// the reference's initial data.  The reference links one pgen per build; here they are selected
+// by name (--prob=<name>).
+//   linear_wave   src/pgen/linear_wave.cpp:77-188 (setup), :190-427 (errors), :430-570 (ICs),
+//                 :575-620 (vector potential), :640-760,1040-1075 (right eigenvectors)
+//   blast         src/pgen/blast.cpp:52-259
+//   orszag_tang   src/pgen/orszag_tang.cpp:40-110
+//   kh            src/pgen/kh.cpp:159-215 (iprob = 2)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "athena.hpp"
+
+//========================================================================================
+// blast
+static void BlastGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  Real rout = pin->GetReal("problem", "radius");
+  Real rin = rout - pin->GetOrAddReal("problem", "ramp", 0.0);
+  Real pa = pin->GetOrAddReal("problem", "pamb", 1.0);
+  Real da = pin->GetOrAddReal("problem", "damb", 1.0);
+  Real prat = pin->GetReal("problem", "prat");
+  Real drat = pin->GetOrAddReal("problem", "drat", 1.0);
+  Real b0 = 0.0, angle = 0.0;
+  if (MAGNETIC_FIELDS_ENABLED) {
+    b0 = pin->GetReal("problem", "b0");
+    angle = (PI / 180.0) * pin->GetReal("problem", "angle");
+  }
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  const Real x0 = pin->GetOrAddReal("problem", "x1_0", 0.0);
+  const Real y0 = pin->GetOrAddReal("problem", "x2_0", 0.0);
+  const Real z0 = pin->GetOrAddReal("problem", "x3_0", 0.0);
+  AthenaArray<Real> &u = pmb->phydro->u;
+  Coordinates *pc = pmb->pcoord;
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) {
+        const Real x = pc->x1v(i), y = pc->x2v(j), z = pc->x3v(k);
+        const Real rad = std::sqrt(SQR(x - x0) + SQR(y - y0) + SQR(z - z0));
+        Real den = da, pres = pa;
+        if (rad < rout) {
+          if (rad < rin) {
+            den = drat * da;
+            pres = prat * pa;
+          } else {   // smooth ramp
+            const Real f = (rad - rin) / (rout - rin);
+            den = std::exp((1.0 - f) * std::log(drat * da) + f * std::log(da));
+            pres = std::exp((1.0 - f) * std::log(prat * pa) + f * std::log(pa));
+          }
+        }
+        u(IDN, k, j, i) = den;
+        u(IM1, k, j, i) = 0.0;
+        u(IM2, k, j, i) = 0.0;
+        u(IM3, k, j, i) = 0.0;
+        u(IEN, k, j, i) = pres / gm1;
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    FaceField &b = pmb->pfield->b;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie + 1; ++i) b.x1f(k, j, i) = b0 * std::cos(angle);
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je + 1; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x2f(k, j, i) = b0 * std::sin(angle);
+    for (int k = pmb->ks; k <= pmb->ke + 1; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x3f(k, j, i) = 0.0;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) u(IEN, k, j, i) += 0.5 * b0 * b0;
+  }
+}
+
+//========================================================================================
+// orszag_tang (uniform in x3)
+static void OrszagTangGenerator(MeshBlock *pmb, ParameterInput *) {
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  AthenaArray<Real> az;
+  az.NewAthenaArray(pmb->ncells2, pmb->ncells1);
+  const Real B0 = 1.0 / std::sqrt(4.0 * PI);
+  const Real d0 = 25.0 / (36.0 * PI);
+  const Real v0 = 1.0;
+  const Real p0 = 5.0 / (12.0 * PI);
+  Coordinates *pc = pmb->pcoord;
+  AthenaArray<Real> &u = pmb->phydro->u;
+  FaceField &b = pmb->pfield->b;
+  for (int j = pmb->js; j <= pmb->je + 1; ++j)
+    for (int i = pmb->is; i <= pmb->ie + 1; ++i)
+      az(j, i) = B0 / (4.0 * PI) * (std::cos(4.0 * PI * pc->x1f(i)) - 2.0 * std::cos(TWO_PI * pc->x2f(j)));
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) {
+        u(IDN, k, j, i) = d0;
+        u(IM1, k, j, i) = d0 * v0 * std::sin(TWO_PI * pc->x2v(j));
+        u(IM2, k, j, i) = -d0 * v0 * std::sin(TWO_PI * pc->x1v(i));
+        u(IM3, k, j, i) = 0.0;
+      }
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = (az(j + 1, i) - az(j, i)) / pc->dx2f(j);
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je + 1; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) b.x2f(k, j, i) = (az(j, i) - az(j, i + 1)) / pc->dx1f(i);
+  for (int k = pmb->ks; k <= pmb->ke + 1; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) b.x3f(k, j, i) = 0.0;
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++)
+        u(IEN, k, j, i) = p0 / gm1 +
+                          0.5 * (SQR(0.5 * (b.x1f(k, j, i) + b.x1f(k, j, i + 1))) +
+                                 SQR(0.5 * (b.x2f(k, j, i) + b.x2f(k, j + 1, i))) +
+                                 SQR(0.5 * (b.x3f(k, j, i) + b.x3f(k + 1, j, i)))) +
+                          (0.5) * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i))) /
+                              u(IDN, k, j, i);
+}
+
+//========================================================================================
+// kh, iprob = 2 (tanh shear layer, deterministic)
+static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  const int iprob = pin->GetInteger("problem", "iprob");
+  if (iprob != 2) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in kh ProblemGenerator" << std::endl
+        << "iprob=" << iprob << " is not built into the B200 host (iprob=2 is)";
+    ATHENA_ERROR(msg);
+  }
+  const Real vflow = pin->GetReal("problem", "vflow");
+  const Real amp = pin->GetReal("problem", "amp");
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  const Real a = 0.02, sigma = 0.2;
+  Coordinates *pc = pmb->pcoord;
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) {
+        u(IDN, k, j, i) = 1.0;
+        u(IM1, k, j, i) = vflow * std::tanh((pc->x2v(j)) / a);
+        u(IM2, k, j, i) = amp * std::cos(TWO_PI * pc->x1v(i)) * std::exp(-(SQR(pc->x2v(j))) / SQR(sigma));
+        u(IM3, k, j, i) = 0.0;
+        u(IEN, k, j, i) = 1.0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    const Real b0 = pin->GetReal("problem", "b0");
+    FaceField &b = pmb->pfield->b;
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0;
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * b0 * b0;
+  }
+}
+
+//========================================================================================
+// linear_wave
+namespace {
+Real amp, vflow, ang_2, ang_3, sin_a2, cos_a2, sin_a3, cos_a3, lambda, k_par, gam, gm1;
+Real d0, p0, u0, bx0, by0, bz0, dby, dbz;
+int wave_flag;
+bool ang_2_vert, ang_3_vert;
+Real ev[7], rem[7][7];
+
+// right eigenvectors in conserved variables, adiabatic (linear_wave.cpp:640-760, :1040-1075)
+void RightEigensystem(Real d, Real v1, Real v2, Real v3, Real h, Real b1, Real b2, Real b3, Real x, Real y) {
+  if (MAGNETIC_FIELDS_ENABLED) {
+    const Real vsq = v1 * v1 + v2 * v2 + v3 * v3;
+    const Real btsq = b2 * b2 + b3 * b3;
+    const Real bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+    const Real vaxsq = b1 * b1 / d;
+    const Real hp = h - (vaxsq + btsq / d);
+    const Real twid_asq = std::max((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), TINY_NUMBER);
+    const Real ct2 = bt_starsq / d;
+    const Real tsum = vaxsq + ct2 + twid_asq;
+    const Real tdif = vaxsq + ct2 - twid_asq;
+    const Real cf2_cs2 = std::sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+    const Real cfsq = 0.5 * (tsum + cf2_cs2);
+    const Real cf = std::sqrt(cfsq);
+    const Real cssq = twid_asq * vaxsq / cfsq;
+    const Real cs = std::sqrt(cssq);
+    const Real bt = std::sqrt(btsq);
+    const Real bt_star = std::sqrt(bt_starsq);
+    Real bet2, bet3;
+    if (bt == 0.0) { bet2 = 1.0; bet3 = 0.0; } else { bet2 = b2 / bt; bet3 = b3 / bt; }
+    const Real bet2_star = bet2 / std::sqrt(gm1 - (gm1 - 1.0) * y);
+    const Real bet3_star = bet3 / std::sqrt(gm1 - (gm1 - 1.0) * y);
+    const Real bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star;
+    const Real vbet = v2 * bet2_star + v3 * bet3_star;
+    Real alpha_f, alpha_s;
+    if ((cfsq - cssq) == 0.0) { alpha_f = 1.0; alpha_s = 0.0; }
+    else if ((twid_asq - cssq) <= 0.0) { alpha_f = 0.0; alpha_s = 1.0; }
+    else if ((cfsq - twid_asq) <= 0.0) { alpha_f = 1.0; alpha_s = 0.0; }
+    else {
+      alpha_f = std::sqrt((twid_asq - cssq) / (cfsq - cssq));
+      alpha_s = std::sqrt((cfsq - twid_asq) / (cfsq - cssq));
+    }
+    const Real sqrtd = std::sqrt(d);
+    const Real isqrtd = 1.0 / sqrtd;
+    const Real s = SIGN(b1);
+    const Real twid_a = std::sqrt(twid_asq);
+    const Real qf = cf * alpha_f * s;
+    const Real qs = cs * alpha_s * s;
+    const Real af_prime = twid_a * alpha_f * isqrtd;
+    const Real as_prime = twid_a * alpha_s * isqrtd;
+    const Real afpbb = af_prime * bt_star * bet_starsq;
+    const Real aspbb = as_prime * bt_star * bet_starsq;
+    const Real vax = std::sqrt(vaxsq);
+    ev[0] = v1 - cf; ev[1] = v1 - vax; ev[2] = v1 - cs; ev[3] = v1; ev[4] = v1 + cs; ev[5] = v1 + vax; ev[6] = v1 + cf;
+    rem[0][0] = alpha_f; rem[0][1] = 0.0; rem[0][2] = alpha_s; rem[0][3] = 1.0; rem[0][4] = alpha_s; rem[0][5] = 0.0; rem[0][6] = alpha_f;
+    rem[1][0] = alpha_f * ev[0]; rem[1][1] = 0.0; rem[1][2] = alpha_s * ev[2]; rem[1][3] = v1;
+    rem[1][4] = alpha_s * ev[4]; rem[1][5] = 0.0; rem[1][6] = alpha_f * ev[6];
+    Real qa = alpha_f * v2, qb = alpha_s * v2, qc = qs * bet2_star, qd = qf * bet2_star;
+    rem[2][0] = qa + qc; rem[2][1] = -bet3; rem[2][2] = qb - qd; rem[2][3] = v2; rem[2][4] = qb + qd; rem[2][5] = bet3; rem[2][6] = qa - qc;
+    qa = alpha_f * v3; qb = alpha_s * v3; qc = qs * bet3_star; qd = qf * bet3_star;
+    rem[3][0] = qa + qc; rem[3][1] = bet2; rem[3][2] = qb - qd; rem[3][3] = v3; rem[3][4] = qb + qd; rem[3][5] = -bet2; rem[3][6] = qa - qc;
+    rem[4][0] = alpha_f * (hp - v1 * cf) + qs * vbet + aspbb;
+    rem[4][1] = -(v2 * bet3 - v3 * bet2);
+    rem[4][2] = alpha_s * (hp - v1 * cs) - qf * vbet - afpbb;
+    rem[4][3] = 0.5 * vsq + (gm1 - 1.0) * x / gm1;
+    rem[4][4] = alpha_s * (hp + v1 * cs) + qf * vbet - afpbb;
+    rem[4][5] = -rem[4][1];
+    rem[4][6] = alpha_f * (hp + v1 * cf) - qs * vbet + aspbb;
+    rem[5][0] = as_prime * bet2_star; rem[5][1] = -bet3 * s * isqrtd; rem[5][2] = -af_prime * bet2_star; rem[5][3] = 0.0;
+    rem[5][4] = rem[5][2]; rem[5][5] = rem[5][1]; rem[5][6] = rem[5][0];
+    rem[6][0] = as_prime * bet3_star; rem[6][1] = bet2 * s * isqrtd; rem[6][2] = -af_prime * bet3_star; rem[6][3] = 0.0;
+    rem[6][4] = rem[6][2]; rem[6][5] = rem[6][1]; rem[6][6] = rem[6][0];
+  } else {
+    const Real vsq = v1 * v1 + v2 * v2 + v3 * v3;
+    const Real asq = gm1 * std::max((h - 0.5 * vsq), TINY_NUMBER);
+    const Real a = std::sqrt(asq);
+    ev[0] = v1 - a; ev[1] = v1; ev[2] = v1; ev[3] = v1; ev[4] = v1 + a;
+    rem[0][0] = 1.0; rem[1][0] = v1 - a; rem[2][0] = v2; rem[3][0] = v3; rem[4][0] = h - v1 * a;
+    rem[0][1] = 0.0; rem[1][1] = 0.0; rem[2][1] = 1.0; rem[3][1] = 0.0; rem[4][1] = v2;
+    rem[0][2] = 0.0; rem[1][2] = 0.0; rem[2][2] = 0.0; rem[3][2] = 1.0; rem[4][2] = v3;
+    rem[0][3] = 1.0; rem[1][3] = v1; rem[2][3] = v2; rem[3][3] = v3; rem[4][3] = 0.5 * vsq;
+    rem[0][4] = 1.0; rem[1][4] = v1 + a; rem[2][4] = v2; rem[3][4] = v3; rem[4][4] = h + v1 * a;
+  }
+}
+
+// vector potential in the rotated frame (linear_wave.cpp:575-620)
+Real A1(Real x1, Real x2, Real x3) {
+  const Real x = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+  const Real y = -x1 * sin_a3 + x2 * cos_a3;
+  const Real Ay = bz0 * x - (dbz / k_par) * std::cos(k_par * (x));
+  const Real Az = -by0 * x + (dby / k_par) * std::cos(k_par * (x)) + bx0 * y;
+  return -Ay * sin_a3 - Az * sin_a2 * cos_a3;
+}
+Real A2(Real x1, Real x2, Real x3) {
+  const Real x = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+  const Real y = -x1 * sin_a3 + x2 * cos_a3;
+  const Real Ay = bz0 * x - (dbz / k_par) * std::cos(k_par * (x));
+  const Real Az = -by0 * x + (dby / k_par) * std::cos(k_par * (x)) + bx0 * y;
+  return Ay * cos_a3 - Az * sin_a2 * sin_a3;
+}
+Real A3(Real x1, Real x2, Real x3) {
+  const Real x = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+  const Real y = -x1 * sin_a3 + x2 * cos_a3;
+  const Real Az = -by0 * x + (dby / k_par) * std::cos(k_par * (x)) + bx0 * y;
+  return Az * cos_a2;
+}
+
+Real MaxV2(MeshBlock *pmb, int) {   // linear_wave.cpp user history "max-v2"
+  Real max_v2 = 0.0;
+  const AthenaArray<Real> &w = pmb->phydro->w;
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) max_v2 = std::max(std::abs(w(IVY, k, j, i)), max_v2);
+  return max_v2;
+}
+}  // namespace
+
+static void LinearWaveInit(Mesh *pm, ParameterInput *pin) {
+  wave_flag = pin->GetInteger("problem", "wave_flag");
+  amp = pin->GetReal("problem", "amp");
+  vflow = pin->GetOrAddReal("problem", "vflow", 0.0);
+  ang_2 = pin->GetOrAddReal("problem", "ang_2", -999.9);
+  ang_3 = pin->GetOrAddReal("problem", "ang_3", -999.9);
+  ang_2_vert = pin->GetOrAddBoolean("problem", "ang_2_vert", false);
+  ang_3_vert = pin->GetOrAddBoolean("problem", "ang_3_vert", false);
+  gam = pin->GetReal("hydro", "gamma");
+  gm1 = (gam - 1.0);
+  const Real x1size = pm->mesh_size.x1max - pm->mesh_size.x1min;
+  const Real x2size = pm->mesh_size.x2max - pm->mesh_size.x2min;
+  const Real x3size = pm->mesh_size.x3max - pm->mesh_size.x3min;
+  if (ang_3 == -999.9) ang_3 = std::atan(x1size / x2size);
+  sin_a3 = std::sin(ang_3);
+  cos_a3 = std::cos(ang_3);
+  if (ang_3_vert) { sin_a3 = 1.0; cos_a3 = 0.0; ang_3 = 0.5 * M_PI; }
+  if (ang_2 == -999.9) ang_2 = std::atan(0.5 * (x1size * cos_a3 + x2size * sin_a3) / x3size);
+  sin_a2 = std::sin(ang_2);
+  cos_a2 = std::cos(ang_2);
+  if (ang_2_vert) { sin_a2 = 1.0; cos_a2 = 0.0; ang_2 = 0.5 * M_PI; }
+  const Real x1 = x1size * cos_a2 * cos_a3;
+  const Real x2 = x2size * cos_a2 * sin_a3;
+  const Real x3 = x3size * sin_a2;
+  lambda = x1;
+  if (pm->f2 && ang_3 != 0.0) lambda = std::min(lambda, x2);
+  if (pm->f3 && ang_2 != 0.0) lambda = std::min(lambda, x3);
+  if (ang_3_vert) lambda = x2;
+  if (ang_2_vert) lambda = x3;
+  k_par = 2.0 * (PI) / lambda;
+  d0 = 1.0;
+  u0 = vflow;
+  const Real v0 = 0.0, w0 = 0.0;
+  bx0 = 1.0;
+  by0 = std::sqrt(2.0);
+  bz0 = 0.5;
+  const Real xfact = 0.0, yfact = 1.0;
+  p0 = 1.0 / gam;
+  Real h0 = ((p0 / gm1 + 0.5 * d0 * (u0 * u0 + v0 * v0 + w0 * w0)) + p0) / d0;
+  if (MAGNETIC_FIELDS_ENABLED) h0 += (bx0 * bx0 + by0 * by0 + bz0 * bz0) / d0;
+  RightEigensystem(d0, u0, v0, w0, h0, bx0, by0, bz0, xfact, yfact);
+  if (pin->GetOrAddBoolean("problem", "test", false) && pm->ncycle == 0) {
+    const Real ntlim = lambda / std::abs(ev[wave_flag]) * pm->tlim;
+    pm->tlim = ntlim;
+    pin->SetReal("time", "tlim", ntlim);
+  }
+  pm->EnrollUserHistoryOutput(MaxV2, "max-v2", 1);
+}
+
+static void LinearWaveGenerator(MeshBlock *pmb, ParameterInput *) {
+  Coordinates *pc = pmb->pcoord;
+  const int is = pmb->is, ie = pmb->ie, js = pmb->js, je = pmb->je, ks = pmb->ks, ke = pmb->ke;
+  if (MAGNETIC_FIELDS_ENABLED) {
+    AthenaArray<Real> a1, a2, a3;
+    a1.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+    a2.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+    a3.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+    dby = amp * rem[NWAVE - 2][wave_flag];
+    dbz = amp * rem[NWAVE - 1][wave_flag];
+    // uniform level: no finer neighbours, the single-point branches of linear_wave.cpp:449-500
+    for (int k = ks; k <= ke + 1; k++)
+      for (int j = js; j <= je + 1; j++)
+        for (int i = is; i <= ie + 1; i++) {
+          a1(k, j, i) = A1(pc->x1v(i), pc->x2f(j), pc->x3f(k));
+          a2(k, j, i) = A2(pc->x1f(i), pc->x2v(j), pc->x3f(k));
+          a3(k, j, i) = A3(pc->x1f(i), pc->x2f(j), pc->x3v(k));
+        }
+    FaceField &b = pmb->pfield->b;
+    for (int k = ks; k <= ke; k++)
+      for (int j = js; j <= je; j++)
+        for (int i = is; i <= ie + 1; i++)
+          b.x1f(k, j, i) = (a3(k, j + 1, i) - a3(k, j, i)) / pc->dx2f(j) - (a2(k + 1, j, i) - a2(k, j, i)) / pc->dx3f(k);
+    for (int k = ks; k <= ke; k++)
+      for (int j = js; j <= je + 1; j++)
+        for (int i = is; i <= ie; i++)
+          b.x2f(k, j, i) = (a1(k + 1, j, i) - a1(k, j, i)) / pc->dx3f(k) - (a3(k, j, i + 1) - a3(k, j, i)) / pc->dx1f(i);
+    for (int k = ks; k <= ke + 1; k++)
+      for (int j = js; j <= je; j++)
+        for (int i = is; i <= ie; i++)
+          b.x3f(k, j, i) = (a2(k, j, i + 1) - a2(k, j, i)) / pc->dx1f(i) - (a1(k, j + 1, i) - a1(k, j, i)) / pc->dx2f(j);
+  }
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        const Real x = cos_a2 * (pc->x1v(i) * cos_a3 + pc->x2v(j) * sin_a3) + pc->x3v(k) * sin_a2;
+        const Real sn = std::sin(k_par * x);
+        u(IDN, k, j, i) = d0 + amp * sn * rem[0][wave_flag];
+        const Real mx = d0 * vflow + amp * sn * rem[1][wave_flag];
+        const Real my = amp * sn * rem[2][wave_flag];
+        const Real mz = amp * sn * rem[3][wave_flag];
+        u(IM1, k, j, i) = mx * cos_a2 * cos_a3 - my * sin_a3 - mz * sin_a2 * cos_a3;
+        u(IM2, k, j, i) = mx * cos_a2 * sin_a3 + my * cos_a3 - mz * sin_a2 * sin_a3;
+        u(IM3, k, j, i) = mx * sin_a2 + mz * cos_a2;
+        u(IEN, k, j, i) = p0 / gm1 + 0.5 * d0 * u0 * u0 + amp * sn * rem[4][wave_flag];
+        if (MAGNETIC_FIELDS_ENABLED) u(IEN, k, j, i) += 0.5 * (bx0 * bx0 + by0 * by0 + bz0 * bz0);
+      }
+}
+
+// L1 errors against the initial wave (linear_wave.cpp:190-427): written to
+// linearwave-errors.dat in the reference's column format
+static void LinearWaveErrors(Mesh *pm, ParameterInput *pin) {
+  if (!pin->GetOrAddBoolean("problem", "compute_error", false)) return;
+  pm->DownloadAll();
+  const int nv = NHYDRO + (MAGNETIC_FIELDS_ENABLED ? 3 : 0);
+  Real l1_err[8] = {0, 0, 0, 0, 0, 0, 0, 0}, max_err[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < pm->nblocal; ++b) {
+    MeshBlock *pmb = pm->my_blocks(b);
+    Coordinates *pc = pmb->pcoord;
+    const AthenaArray<Real> &u = pmb->phydro->u;
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie; i++) {
+          const Real x = cos_a2 * (pc->x1v(i) * cos_a3 + pc->x2v(j) * sin_a3) + pc->x3v(k) * sin_a2;
+          const Real sn = std::sin(k_par * x);
+          const Real d1 = d0 + amp * sn * rem[0][wave_flag];
+          const Real mx = d0 * vflow + amp * sn * rem[1][wave_flag];
+          const Real my = amp * sn * rem[2][wave_flag];
+          const Real mz = amp * sn * rem[3][wave_flag];
+          const Real m1 = mx * cos_a2 * cos_a3 - my * sin_a3 - mz * sin_a2 * cos_a3;
+          const Real m2 = mx * cos_a2 * sin_a3 + my * cos_a3 - mz * sin_a2 * sin_a3;
+          const Real m3 = mx * sin_a2 + mz * cos_a2;
+          Real e0 = p0 / gm1 + 0.5 * d0 * u0 * u0 + amp * sn * rem[4][wave_flag];
+          if (MAGNETIC_FIELDS_ENABLED) e0 += 0.5 * (bx0 * bx0 + by0 * by0 + bz0 * bz0);
+          const Real vol = pc->GetCellVolume(k, j, i);
+          const Real ref[5] = {d1, m1, m2, m3, e0};
+          for (int n = 0; n < NHYDRO; ++n) {
+            const Real err = std::abs(ref[n] - u(n, k, j, i));
+            l1_err[n] += err * vol;
+            max_err[n] = std::max(err, max_err[n]);
+          }
+        }
+  }
+  const Real vol_tot = (pm->mesh_size.x1max - pm->mesh_size.x1min) * (pm->mesh_size.x2max - pm->mesh_size.x2min) *
+                       (pm->mesh_size.x3max - pm->mesh_size.x3min);
+  Real rms = 0.0, max_max_over_l1 = 0.0;
+  for (int n = 0; n < NHYDRO; ++n) {
+    l1_err[n] /= vol_tot;
+    rms += SQR(l1_err[n]);
+    max_max_over_l1 = std::max(max_max_over_l1, max_err[n] / l1_err[n]);
+  }
+  rms = std::sqrt(rms);
+  FILE *pfile = std::fopen("linearwave-errors.dat", "a");
+  if (pfile == nullptr) return;
+  std::fprintf(pfile, "# Nx1  Nx2  Nx3  Ncycle  RMS-L1-Error  d_L1  M1_L1  M2_L1  M3_L1  E_L1\n");
+  std::fprintf(pfile, "%d  %d  %d  %d  %e", pm->mesh_size.nx1, pm->mesh_size.nx2, pm->mesh_size.nx3, pm->ncycle, rms);
+  for (int n = 0; n < NHYDRO; ++n) std::fprintf(pfile, "  %e", l1_err[n]);
+  std::fprintf(pfile, "  %e\n", max_max_over_l1);
+  std::fclose(pfile);
+  (void)nv;
+}
+
+//========================================================================================
+static const ProblemGeneratorEntry kProblemGenerators[] = {
+    {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
+    {"blast", nullptr, BlastGenerator, nullptr},
+    {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
+    {"kh", nullptr, KHGenerator, nullptr},
+};
+
+const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {
+  for (const ProblemGeneratorEntry &e : kProblemGenerators)
+    if (name == e.name) return &e;
+  return nullptr;
+}

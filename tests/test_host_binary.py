@@ -1,0 +1,132 @@
+"""The C++ host (Mesh / MeshBlock / ParameterInput / TimeIntegratorTaskList / pgen mirror) run the
+way the reference's regression tests run the reference: same athinput -> run the binary -> parse
+its .rst / .hst.  Restart dumps (initial = pgen output, intermediate, final), the dt sequence and
+the history file must be IDENTICAL to the reference binary's (oracle/_ref, built from
+/root/reference by oracle/Makefile.ref).  CPU variant: host linked with the tests/emul harness
+library; GPU variant: the product binary athena_b200/bin/athena_b200 (libathk.so, CUDA)."""
+import glob
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import refrun
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_BIN = os.path.join(ROOT, "tests", "emul", "athena_emul")
+CUDA_BIN = os.path.join(ROOT, "athena_b200", "bin", "athena_b200")
+
+
+def blast_blocks(n=32, blk=16, tlim=0.02):
+    return {
+        "job": {"problem_id": "Blast"},
+        "output1": {"file_type": "hst", "dt": 0.005, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 0.01},
+        "time": {"cfl_number": 0.3, "nlim": -1, "tlim": tlim, "integrator": "vl2", "xorder": 2,
+                 "ncycle_out": 1},
+        "mesh": {"nx1": n, "x1min": -1.0, "x1max": 1.0, "ix1_bc": "periodic", "ox1_bc": "periodic",
+                 "nx2": n, "x2min": -1.0, "x2max": 1.0, "ix2_bc": "periodic", "ox2_bc": "periodic",
+                 "nx3": n, "x3min": -1.0, "x3max": 1.0, "ix3_bc": "periodic", "ox3_bc": "periodic",
+                 "num_threads": 1},
+        "meshblock": {"nx1": blk, "nx2": blk, "nx3": blk},
+        "hydro": {"gamma": 1.666666666667, "iso_sound_speed": 0.4082482905},
+        "problem": {"pamb": 0.1, "prat": 100.0, "radius": 0.1, "damb": 1.0, "drat": 1.0,
+                    "ramp": 0.0, "b0": 1.0, "angle": 30},
+    }
+
+
+CASES = {
+    "mhd_linwave": ("linwave_mhd_hlld", "linear_wave", True,
+                    lambda: dict(refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(16, 8, 8),
+                                                       tlim=0.05, rst_dt=0.02))),
+    "hydro_linwave_rk3": ("linwave_hydro_hllc", "linear_wave", False,
+                          lambda: dict(refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(16, 8, 8),
+                                                             tlim=0.1, rst_dt=0.05, integrator="rk3"))),
+    "mhd_blast": ("blast_mhd_hlld", "blast", True, blast_blocks),
+}
+
+
+def run_host(binary, blocks, prob, mhd, extra=()):
+    wd = tempfile.mkdtemp(prefix="athhost_")
+    inp = os.path.join(wd, "athinput.host")
+    with open(inp, "w") as f:
+        f.write(refrun.format_athinput(blocks))
+    args = [binary, "-i", inp, "-d", wd, "--prob=" + prob] + (["-b"] if mhd else []) + list(extra)
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    return wd, r
+
+
+def compare_with_reference(binary, case):
+    cfg, prob, mhd, mk = CASES[case]
+    if not refrun.have_ref(cfg):
+        pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
+    blocks = mk()
+    wd_ref, _ = refrun.run_reference(cfg, blocks)
+    wd, r = run_host(binary, blocks, prob, mhd)
+    try:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        ref_files = sorted(os.path.basename(f) for f in glob.glob(wd_ref + "/*.rst"))
+        our_files = sorted(os.path.basename(f) for f in glob.glob(wd + "/*.rst"))
+        assert ref_files == our_files and len(ref_files) >= 3
+        for name in ref_files:
+            a, c = refrun.read_rst(os.path.join(wd_ref, name)), refrun.read_rst(os.path.join(wd, name))
+            assert (a["ncycle"], a["time"], a["dt"], a["loc"]) == (c["ncycle"], c["time"], c["dt"], c["loc"]), name
+            for k in ("u", "b1", "b2", "b3"):
+                assert len(a[k]) == len(c[k])
+                for x, y in zip(a[k], c[k]):
+                    np.testing.assert_array_equal(x, y, err_msg="%s %s" % (name, k))
+        n1, h1 = refrun.read_hst(glob.glob(wd_ref + "/*.hst")[0])
+        n2, h2 = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
+        assert n1 == n2
+        # history sums are formed on the host in the reference's serial order: identical digits;
+        # the north-star bar is 1e-10 relative to the column scale
+        scale = np.abs(h1).max(axis=0) + 1e-300
+        assert np.all(np.abs(h1 - h2) <= 1e-10 * scale)
+        np.testing.assert_array_equal(h1[:, :2], h2[:, :2])   # time and dt columns exactly
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+        shutil.rmtree(wd_ref, ignore_errors=True)
+
+
+@pytest.fixture(scope="module")
+def emul_binary(emul_lib):
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "athena_b200", "csrc", "host"), "emul"],
+                   check=True, capture_output=True)
+    return EMUL_BIN
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case):
+    compare_with_reference(emul_binary, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    compare_with_reference(CUDA_BIN, case)
+
+
+def test_parameter_input_error_behaviour(emul_binary):
+    """Missing parameter / unknown cmdline override / non-periodic BC: message + exit status as
+    ATHENA_ERROR does (src/defs.hpp.in:155-159, parameter_input.cpp:352-395)."""
+    blocks = blast_blocks()
+    bad = {k: dict(v) for k, v in blocks.items()}
+    del bad["time"]["tlim"]
+    wd, r = run_host(emul_binary, bad, "blast", True)
+    assert r.returncode != 0 and "Parameter name 'tlim' not found in block 'time'" in r.stdout
+    shutil.rmtree(wd, ignore_errors=True)
+    wd, r = run_host(emul_binary, blocks, "blast", True, extra=["output1/new_param=3"])
+    assert r.returncode != 0 and "on command line not found" in r.stdout
+    shutil.rmtree(wd, ignore_errors=True)
+    bad = {k: dict(v) for k, v in blocks.items()}
+    bad["mesh"]["ix1_bc"] = "outflow"
+    wd, r = run_host(emul_binary, bad, "blast", True)
+    assert r.returncode != 0 and "periodic mesh boundaries only" in r.stdout
+    shutil.rmtree(wd, ignore_errors=True)
+    wd, r = run_host(emul_binary, blocks, "blast", True, extra=["time/tlim=0.004"])
+    assert r.returncode == 0 and "Terminating on time limit" in r.stdout
+    shutil.rmtree(wd, ignore_errors=True)
