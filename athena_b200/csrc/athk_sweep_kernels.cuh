@@ -24,6 +24,9 @@ namespace athk {
 #ifndef ATHK_TILE_MINB
 #define ATHK_TILE_MINB 4
 #endif
+#ifndef ATHK_TILE_PREFETCH
+#define ATHK_TILE_PREFETCH 1   // 1: prefetch.global.L2 of the next step's cell, 2: .L1, 0: off
+#endif
 
 template <int DIR, int ORDER, bool MHD>
 __global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
@@ -66,6 +69,25 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
     idx_t c = 0;
     if (fvalid) {
       c = (DIR == 1) ? gidx(g, k0, n, i) : gidx(g, n, j0, i);
+#if defined(ATHK_TILE_PREFETCH) && ATHK_TILE_PREFETCH > 0
+#if ATHK_TILE_PREFETCH == 2
+#define ATHK_PF "prefetch.global.L1 [%0];"
+#else
+#define ATHK_PF "prefetch.global.L2 [%0];"
+#endif
+      if (n + R <= n_e + 2) {   // next step's cell of this thread: pull its lines towards L2/L1
+        const idx_t cn = c + (idx_t)R * s;
+        const Real *wb = a.w + (idx_t)blk * 5 * g.sn + cn;
+#pragma unroll
+        for (int v = 0; v < 5; ++v) asm volatile(ATHK_PF ::"l"(wb + (idx_t)v * g.sn));
+        if (MHD) {
+          const Real *bc = a.bcc + (idx_t)blk * 3 * g.sn + cn;
+          asm volatile(ATHK_PF ::"l"(bc + (idx_t)((DIR + 1) % 3) * g.sn));
+          asm volatile(ATHK_PF ::"l"(bc + (idx_t)((DIR + 2) % 3) * g.sn));
+          asm volatile(ATHK_PF ::"l"(a.b + ((idx_t)blk * 3 + DIR) * g.sn + cn));
+        }
+      }
+#endif
       face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
       sF[buf][r][0][lane] = f[IDN];
       sF[buf][r][1][lane] = f[IVX];
