@@ -503,8 +503,21 @@ extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   return ATHK_OK;
 }
 
+static SweepArgs make_sweep_args(athk_ctx *c, double dt, int breg, bool store_flux) {
+  SweepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = c->g; a.eos = c->eos; a.geo = c->geo;
+  a.w = c->w; a.bcc = c->bcc; a.b = c->cfg.mhd ? c->b[breg] : nullptr;
+  for (int d = 0; d < 3; ++d) a.flx[d] = store_flux ? c->flux[d] : nullptr;
+  a.ef = c->ef; a.wct = c->wct;
+  a.d2 = c->flux[1];   // fused path only: the x2/x3 flux arrays double as scratch terms
+  a.d3 = c->flux[2];
+  a.dt = dt;
+  return a;
+}
+
 template <int DIR, int ORDER, bool MHD>
-static int launch_flux(athk_ctx *c, double dt, int breg) {
+static int launch_flux(athk_ctx *c, const SweepArgs &a) {
   const Grid &g = c->g;
   // loop limits of calculate_fluxes.cpp:68-76,176-182,299-302 (3-D)
   Range3 r;
@@ -518,27 +531,39 @@ static int launch_flux(athk_ctx *c, double dt, int breg) {
     r = {g.ks, g.ke + 1, g.js, g.je, g.is, g.ie};
     if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
   }
-  FluxPoint<DIR, ORDER, MHD> f = {g, c->eos, c->geo, c->w, c->bcc, MHD ? c->b[breg] : nullptr,
-                                  c->flux[DIR], c->ef, c->wct, dt};
-  LAUNCH(c, r, f);
+  FacePoint<DIR, ORDER, MHD> f = {a};
+  LAUNCH_NAMED(c, DIR == 0 ? "calculate_fluxes_x1" : (DIR == 1 ? "calculate_fluxes_x2" : "calculate_fluxes_x3"),
+               launch_points(c->stream, g.nb, r, f));
   return ATHK_OK;
 }
 
 template <int ORDER, bool MHD>
 static int launch_flux3(athk_ctx *c, double dt, int breg) {
-  int rc = launch_flux<0, ORDER, MHD>(c, dt, breg);
-  if (!rc) rc = launch_flux<1, ORDER, MHD>(c, dt, breg);
-  if (!rc) rc = launch_flux<2, ORDER, MHD>(c, dt, breg);
+  const SweepArgs a = make_sweep_args(c, dt, breg, true);
+  int rc = launch_flux<0, ORDER, MHD>(c, a);
+  if (!rc) rc = launch_flux<1, ORDER, MHD>(c, a);
+  if (!rc) rc = launch_flux<2, ORDER, MHD>(c, a);
   return rc;
+}
+
+static int check_order(athk_ctx *c, int order, const char *who) {
+  if (order < 1 || order > 3)
+    return fail(ATHK_ERR_ARG, "%s: xorder %d not implemented (1 donor cell, 2 PLM, 3 PPM)", who, order);
+  if (order == 3 && c->cfg.nghost < 3)   // reconstruction.cpp:117-127
+    return fail(ATHK_ERR_ARG, "%s: xorder=3 (PPM) needs nghost >= 3 (context has %d)", who, c->cfg.nghost);
+  return ATHK_OK;
 }
 
 extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int breg) {
   NEED_READY(c);
   if (c->cfg.mhd && (bad_reg(breg) || !c->b[breg]))
     return fail(ATHK_ERR_ARG, "calculate_fluxes: field register %d not allocated", breg);
-  if (order == 1) return c->cfg.mhd ? launch_flux3<1, true>(c, dt_mesh, breg) : launch_flux3<1, false>(c, dt_mesh, breg);
-  if (order == 2) return c->cfg.mhd ? launch_flux3<2, true>(c, dt_mesh, breg) : launch_flux3<2, false>(c, dt_mesh, breg);
-  return fail(ATHK_ERR_ARG, "calculate_fluxes: xorder %d not implemented (1 = donor cell, 2 = PLM)", order);
+  int rc = check_order(c, order, "calculate_fluxes");
+  if (rc) return rc;
+  const bool mhd = c->cfg.mhd != 0;
+  if (order == 1) return mhd ? launch_flux3<1, true>(c, dt_mesh, breg) : launch_flux3<1, false>(c, dt_mesh, breg);
+  if (order == 2) return mhd ? launch_flux3<2, true>(c, dt_mesh, breg) : launch_flux3<2, false>(c, dt_mesh, breg);
+  return mhd ? launch_flux3<3, true>(c, dt_mesh, breg) : launch_flux3<3, false>(c, dt_mesh, breg);
 }
 
 extern "C" int athk_compute_corner_e(athk_ctx *c) {
@@ -813,10 +838,10 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
 #ifndef ATHK_EMULATE
   // x2 columns (i,k) / x3 columns (i,j): CTA-marching tiles (athk_sweep_kernels.cuh);
   // extents of calculate_fluxes.cpp:176-182,299-302
-  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x2_donor" : "sweep_x2_plm",
+  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x2_donor" : (ORDER == 2 ? "sweep_x2_plm" : "sweep_x2_ppm"),
                (launch_sweep_tile<1, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.ks - 1 : g.ks,
                                                  MHD ? g.ke + 1 : g.ke, g.is - 1, g.ie + 1)));
-  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x3_donor" : "sweep_x3_plm",
+  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x3_donor" : (ORDER == 2 ? "sweep_x3_plm" : "sweep_x3_ppm"),
                (launch_sweep_tile<2, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.js - 1 : g.js,
                                                  MHD ? g.je + 1 : g.je, MHD ? g.is - 1 : g.is,
                                                  MHD ? g.ie + 1 : g.ie)));
@@ -838,7 +863,7 @@ static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
     Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
     if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
     SweepX1<ORDER, MHD> f = {a};
-    LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x1_donor_integrate" : "sweep_x1_plm_integrate",
+    LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x1_donor_integrate" : (ORDER == 2 ? "sweep_x1_plm_integrate" : "sweep_x1_ppm_integrate"),
                  launch_sweep_x1(c->stream, g.nb, r, f));
   }
   return ATHK_OK;
@@ -858,7 +883,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
   if (phase < 0 || phase > 2) return fail(ATHK_ERR_ARG, "stage_phase: phase must be 0, 1 or 2");
   if (!sw) return fail(ATHK_ERR_ARG, "stage: null weights");
   if (sw->gamma_3 != 0.0) return fail(ATHK_ERR_ARG, "stage: gamma_3 != 0 (3-register integrators) not implemented");
-  if (order != 1 && order != 2) return fail(ATHK_ERR_ARG, "stage: xorder %d not implemented in the fused path", order);
+  { int rco = check_order(c, order, "stage"); if (rco) return rco; }
   if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "stage: passive scalars not implemented in the fused path");
   const Grid &g = c->g;
   const bool mhd = c->cfg.mhd != 0;
@@ -870,14 +895,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
   }
   int rc;
   if (phase == 0) {
-    SweepArgs a;
-    a.g = g; a.eos = c->eos; a.geo = c->geo;
-    a.w = c->w; a.bcc = c->bcc; a.b = mhd ? c->b[0] : nullptr;
-    a.flx[0] = a.flx[1] = a.flx[2] = nullptr;
-    a.ef = c->ef; a.wct = c->wct;
-    a.d2 = c->flux[1];   // the x2/x3 flux arrays double as the flux-divergence scratch terms
-    a.d3 = c->flux[2];
-    a.dt = dt_mesh;
+    SweepArgs a = make_sweep_args(c, dt_mesh, 0, false);
     HydroIntegrate &h = a.hi;
     h.u = c->u[0]; h.u1 = c->u[1];
     h.u_out = swap ? c->u[1] : c->u[0];
@@ -886,7 +904,8 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     h.wght = sw->beta * dt_mesh;
     h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
     if (order == 1) rc = mhd ? launch_sweeps<1, true>(c, a) : launch_sweeps<1, false>(c, a);
-    else rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
+    else if (order == 2) rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
+    else rc = mhd ? launch_sweeps<3, true>(c, a) : launch_sweeps<3, false>(c, a);
     if (rc) return rc;
     if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
     if (mhd) {

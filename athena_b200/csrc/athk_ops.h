@@ -124,76 +124,6 @@ struct Cons2PrimPoint {
 };
 
 //========================================================================================
-// One face of Hydro::CalculateFluxes: reconstruct L/R (donor cell or PLM) + Riemann solve.
-// DIR 0/1/2 = x1/x2/x3 sweep.  The face (k,j,i) lies between cell c-s (left) and c (right).
-// RS: 0 = HLLC (hydro), 1 = HLLD (MHD)
-template <int DIR, int ORDER, bool MHD>
-struct FluxPoint {
-  Grid g;
-  EosParams eos;
-  Geom geo;
-  const Real *w, *bcc, *b;
-  Real *flx;      // flux[DIR]: [nb][5][sn]
-  Real *ef;       // face EMFs: [nb][6][sn], components 2*DIR (ey) and 2*DIR+1 (ez)
-  Real *wct;      // wght: [nb][3][sn], component DIR
-  Real dt;        // pmy_mesh->dt, full step
-  ATHK_HD void operator()(int blk, int k, int j, int i) const {
-    const int NW = MHD ? 7 : 5;
-    const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
-    const idx_t c = gidx(g, k, j, i);
-    const int n_dir = (DIR == 0) ? i : (DIR == 1 ? j : k);   // index along the sweep
-    const Real *wb = w + (idx_t)blk * 5 * g.sn + c;
-    // rotated variable map: (d, v_n, v_t1, v_t2, p)
-    const int ivx = IVX + DIR, ivy = IVX + (DIR + 1) % 3, ivz = IVX + (DIR + 2) % 3;
-    const idx_t voff[5] = {(idx_t)IDN * g.sn, (idx_t)ivx * g.sn, (idx_t)ivy * g.sn,
-                           (idx_t)ivz * g.sn, (idx_t)IPR * g.sn};
-    Real wl[7], wr[7];
-    Real cpl = 0.0, cmr = 0.0;
-    if (ORDER == 2) {
-      cpl = geo.cp[DIR][blk * geo.PG + n_dir - 1];
-      cmr = geo.cm[DIR][blk * geo.PG + n_dir];
-    }
-#pragma unroll
-    for (int n = 0; n < NW; ++n) {
-      const Real *q;
-      if (n < 5) {
-        q = wb + voff[n];
-      } else {
-        const int ib = (n == 5) ? (DIR + 1) % 3 : (DIR + 2) % 3;
-        q = bcc + ((idx_t)blk * 3 + ib) * g.sn + c;
-      }
-      if (ORDER == 1) {
-        wl[n] = q[-s];
-        wr[n] = q[0];
-      } else {
-        const Real q0 = q[-2 * s], q1 = q[-s], q2 = q[0], q3 = q[s];
-        const Real d01 = q1 - q0, d12 = q2 - q1, d23 = q3 - q2;
-        wl[n] = q1 + cpl * vl_slope(d01, d12);
-        wr[n] = q2 - cmr * vl_slope(d12, d23);
-      }
-    }
-    Real f[7];
-    Real *fb = flx + (idx_t)blk * 5 * g.sn + c;
-    if (MHD) {
-      const Real bxi = b[((idx_t)blk * 3 + DIR) * g.sn + c];
-      hlld_flux(eos, wl, wr, bxi, f);
-      Real *eb = ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
-      eb[0] = -f[IBY];
-      eb[g.sn] = f[IBZ];
-      const Real dxw = geo.dxf[DIR][blk * geo.PG + n_dir];
-      wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, dt);
-    } else {
-      hllc_flux(eos, wl, wr, f);
-    }
-    fb[voff[0]] = f[IDN];
-    fb[voff[1]] = f[IVX];
-    fb[voff[2]] = f[IVY];
-    fb[voff[3]] = f[IVZ];
-    fb[(idx_t)IEN * g.sn] = f[IEN];
-  }
-};
-
-//========================================================================================
 // Field::ComputeCornerE, 3-D branch (calculate_corner_e.cpp:130-229): cell-centred -(v x B)
 // is evaluated on the fly (same bits as the reference's cc_e_ scratch array).
 struct CornerEPoint {

@@ -128,6 +128,88 @@ ATHK_HD Real vl_slope(Real dwl, Real dwr) {
 }
 
 //----------------------------------------------------------------------------------------
+// PPM of one variable in one cell, uniform Cartesian branch of reconstruct/ppm.cpp:107-320
+// (4th-order interface values with c1..c4 = 1/2, c5 = 1/6, c6 = -1/6, reconstruction.cpp:494-505;
+// Colella-Dawson interface limiter :139-193; Colella-Sekora / McCorquodale-Colella
+// extremum-preserving limiter :226-279, time/ext_preserving = true, C2 = 1.25).
+// Returns the left state of the upper face (ql_iph) and the right state of the lower face (qr_imh).
+ATHK_HD Real sign_ath(Real x) { return (x < 0.0) ? -1.0 : 1.0; }   // SIGN() of defs.hpp.in:150
+
+ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Real *ql_iph,
+                      Real *qr_imh) {
+  const Real C2 = 1.25;
+  const Real c1 = 0.5, c2 = 0.5, c3 = 0.5, c4 = 0.5, c5 = 1.0 / 6.0, c6 = -1.0 / 6.0;
+  Real qa = (q - q_im1);
+  Real qb = (q_ip1 - q);
+  const Real dd_im1 = c1 * qa + c2 * (q_im1 - q_im2);
+  const Real dd = c1 * qb + c2 * qa;
+  const Real dd_ip1 = c1 * (q_ip2 - q_ip1) + c2 * qb;
+  Real dph = (c3 * q_im1 + c4 * q) + (c5 * dd_im1 + c6 * dd);
+  Real dph_ip1 = (c3 * q + c4 * q_ip1) + (c5 * dd + c6 * dd_ip1);
+  const Real d2qc_im1 = q_im2 + q - 2.0 * q_im1;
+  const Real d2qc = q_im1 + q_ip1 - 2.0 * q;
+  const Real d2qc_ip1 = q + q_ip2 - 2.0 * q_ip1;
+  {   // i-1/2 interface
+    const Real qa_tmp = dph - q_im1;
+    const Real qb_tmp = q - dph;
+    qa = 3.0 * (q_im1 + q - 2.0 * dph);
+    qb = d2qc_im1;
+    const Real qc = d2qc;
+    Real qd = 0.0;
+    if (sign_ath(qa) == sign_ath(qb) && sign_ath(qa) == sign_ath(qc))
+      qd = sign_ath(qa) * min_std(C2 * fabs(qb), min_std(C2 * fabs(qc), fabs(qa)));
+    const Real dph_tmp = 0.5 * (q_im1 + q) - qd / 6.0;
+    if (qa_tmp * qb_tmp < 0.0) dph = dph_tmp;
+  }
+  {   // i+1/2 interface
+    const Real qa_tmp = dph_ip1 - q;
+    const Real qb_tmp = q_ip1 - dph_ip1;
+    qa = 3.0 * (q + q_ip1 - 2.0 * dph_ip1);
+    qb = d2qc;
+    const Real qc = d2qc_ip1;
+    Real qd = 0.0;
+    if (sign_ath(qa) == sign_ath(qb) && sign_ath(qa) == sign_ath(qc))
+      qd = sign_ath(qa) * min_std(C2 * fabs(qb), min_std(C2 * fabs(qc), fabs(qa)));
+    const Real dphip1_tmp = 0.5 * (q + q_ip1) - qd / 6.0;
+    if (qa_tmp * qb_tmp < 0.0) dph_ip1 = dphip1_tmp;
+  }
+  const Real d2qf = 6.0 * (dph + dph_ip1 - 2.0 * q);
+  Real qminus = dph, qplus = dph_ip1;
+  const Real dqf_minus = q - qminus;
+  const Real dqf_plus = qplus - q;
+  {
+    const Real qa_tmp = dqf_minus * dqf_plus;
+    const Real qb_tmp = (q_ip1 - q) * (q - q_im1);
+    qa = d2qc_im1;
+    qb = d2qc;
+    const Real qc = d2qc_ip1;
+    const Real qd = d2qf;
+    Real qe = 0.0;
+    if (sign_ath(qa) == sign_ath(qb) && sign_ath(qa) == sign_ath(qc) && sign_ath(qa) == sign_ath(qd))
+      qe = sign_ath(qd) * min_std(min_std(C2 * fabs(qa), C2 * fabs(qb)), min_std(C2 * fabs(qc), fabs(qd)));
+    qa = max_std(fabs(q_im1), fabs(q_im2));
+    qb = max_std(max_std(fabs(q), fabs(q_ip1)), fabs(q_ip2));
+    Real rho = 0.0;
+    if (fabs(qd) > (1.0e-12) * max_std(qa, qb)) rho = qe / qd;
+    const Real tmp_m = q - rho * dqf_minus;
+    const Real tmp_p = q + rho * dqf_plus;
+    const Real tmp2_m = q - 2.0 * dqf_plus;
+    const Real tmp2_p = q + 2.0 * dqf_minus;
+    if ((qa_tmp <= 0.0 || qb_tmp <= 0.0)) {
+      if (rho <= (1.0 - (1.0e-12))) {
+        qminus = tmp_m;
+        qplus = tmp_p;
+      }
+    } else {
+      if (fabs(dqf_minus) >= 2.0 * fabs(dqf_plus)) qminus = tmp2_m;
+      if (fabs(dqf_plus) >= 2.0 * fabs(dqf_minus)) qplus = tmp2_p;
+    }
+  }
+  *ql_iph = qplus;
+  *qr_imh = qminus;
+}
+
+//----------------------------------------------------------------------------------------
 // Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
 ATHK_HD Real ct_weight(Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
   Real v_over_c = fdiv((1024.0) * dt * dflx, (dx * (rhol + rhor)));

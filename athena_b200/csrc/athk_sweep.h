@@ -141,7 +141,67 @@ ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsu
 }
 
 //========================================================================================
-// x2 / x3 sweep: one thread owns one column along the sweep direction.
+// One face of a DIR-sweep, self-contained: reconstruct both adjacent cells (donor cell, PLM or
+// PPM), then Riemann solve.  c = index of the cell above the face, n_dir = its index along the
+// sweep.
+template <int DIR, int ORDER, bool MHD>
+ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
+  const Grid &g = a.g;
+  const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
+  const int NW = MHD ? 7 : 5;
+  Real wl[7], wr[7];
+  if (ORDER == 3) {
+    // PPM: L state from cell n-1 (stencil n-3..n+1), R state from cell n (stencil n-2..n+2)
+    Real qm3[7], qm2[7], qm1[7], q0[7], qp1[7], qp2[7];
+    load_q<DIR, MHD>(a, blk, c - 3 * s, qm3);
+    load_q<DIR, MHD>(a, blk, c - 2 * s, qm2);
+    load_q<DIR, MHD>(a, blk, c - s, qm1);
+    load_q<DIR, MHD>(a, blk, c, q0);
+    load_q<DIR, MHD>(a, blk, c + s, qp1);
+    load_q<DIR, MHD>(a, blk, c + 2 * s, qp2);
+#pragma unroll
+    for (int v = 0; v < NW; ++v) {
+      Real up, lo;
+      ppm_cell(qm3[v], qm2[v], qm1[v], q0[v], qp1[v], &up, &lo);
+      wl[v] = up;
+      ppm_cell(qm2[v], qm1[v], q0[v], qp1[v], qp2[v], &up, &lo);
+      wr[v] = lo;
+    }
+    // ApplyPrimitiveFloors on both states (ppm.cpp:326-332)
+    wl[IDN] = (wl[IDN] > a.eos.dfloor) ? wl[IDN] : a.eos.dfloor;
+    wl[IPR] = (wl[IPR] > a.eos.pfloor) ? wl[IPR] : a.eos.pfloor;
+    wr[IDN] = (wr[IDN] > a.eos.dfloor) ? wr[IDN] : a.eos.dfloor;
+    wr[IPR] = (wr[IPR] > a.eos.pfloor) ? wr[IPR] : a.eos.pfloor;
+  } else if (ORDER == 2) {
+    Real q0[7], q1[7], q2[7], q3[7], t0[7], t1[7];
+    load_q<DIR, MHD>(a, blk, c - s, q1);
+    load_q<DIR, MHD>(a, blk, c, q2);
+    load_q<DIR, MHD>(a, blk, c - 2 * s, q0);
+    load_q<DIR, MHD>(a, blk, c + s, q3);
+    const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
+    const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
+    recon_cell<ORDER, MHD>(q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
+    recon_cell<ORDER, MHD>(q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
+  } else {
+    load_q<DIR, MHD>(a, blk, c - s, wl);
+    load_q<DIR, MHD>(a, blk, c, wr);
+  }
+  solve_face<DIR, MHD>(a, blk, c, n_dir, wl, wr, f, store);
+}
+
+// Hydro::CalculateFluxes as an operator: one thread per face, fluxes stored (a.flx[DIR] set)
+template <int DIR, int ORDER, bool MHD>
+struct FacePoint {
+  SweepArgs a;
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    Real f[7];
+    face_compute<DIR, ORDER, MHD>(a, blk, gidx(a.g, k, j, i), (DIR == 0) ? i : (DIR == 1 ? j : k), f, true);
+  }
+};
+
+//========================================================================================
+// x2 / x3 sweep as a per-column loop: the host harness (tests/emul) form of the CTA-marching
+// tile kernels in athk_sweep_kernels.cuh -- same faces, same stores.
 //   DIR=1: column (i,k), marches j ; DIR=2: column (i,j), marches k.
 // Column extents follow calculate_fluxes.cpp:176-182,299-302; faces s..e+1 along the sweep.
 template <int DIR, int ORDER, bool MHD>
@@ -153,33 +213,19 @@ struct SweepMarch {
     const idx_t s = (DIR == 1) ? g.sj : g.sk;
     const int n_s = (DIR == 1) ? g.js : g.ks;        // first active index along the sweep
     const int n_e = (DIR == 1) ? g.je : g.ke;
-    idx_t c = (DIR == 1) ? gidx(g, k, n_s - 1, i) : gidx(g, n_s - 1, j, i);   // cell n_s-1
     // is this column part of the active zone (gets a flux divergence)?
     const bool interior = (i >= g.is && i <= g.ie) &&
                           ((DIR == 1) ? (k >= g.ks && k <= g.ke) : (j >= g.js && j <= g.je));
-    const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
-    const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
     Real area = 0.0;
     if (interior) {
       const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
       if (DIR == 1) area = dx1 * a.geo.dxf[2][blk * a.geo.PG + k];   // Face2Area
       else area = dx1 * a.geo.dxf[1][blk * a.geo.PG + j];            // Face3Area
     }
-    Real qm[7], q0[7], qp[7], wl[7], wl_up[7], wr[7], f[7], fprev[5];
-    load_q<DIR, MHD>(a, blk, c - s, qm);
-    load_q<DIR, MHD>(a, blk, c, q0);
-    // cell n_s-1: only its upper-face left state is needed
-    load_q<DIR, MHD>(a, blk, c + s, qp);
-    recon_cell<ORDER, MHD>(qm, q0, qp, ORDER == 2 ? cpv[n_s - 1] : 0.0,
-                           ORDER == 2 ? cmv[n_s - 1] : 0.0, wl, wr);
+    Real f[7], fprev[5];
     for (int n = n_s; n <= n_e + 1; ++n) {
-      c += s;
-#pragma unroll
-      for (int v = 0; v < 7; ++v) { qm[v] = q0[v]; q0[v] = qp[v]; }
-      load_q<DIR, MHD>(a, blk, c + s, qp);
-      recon_cell<ORDER, MHD>(qm, q0, qp, ORDER == 2 ? cpv[n] : 0.0, ORDER == 2 ? cmv[n] : 0.0,
-                             wl_up, wr);
-      solve_face<DIR, MHD>(a, blk, c, n, wl, wr, f, true);   // face n: L from cell n-1, R from cell n
+      const idx_t c = (DIR == 1) ? gidx(g, k, n, i) : gidx(g, n, j, i);
+      face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
       if (interior && n > n_s) {
         // cell n-1: (A F)(n) - (A F)(n-1)
         const idx_t cc = c - s;
@@ -191,35 +237,9 @@ struct SweepMarch {
           dst[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = (area * fcur[v] - area * fprev[v]);
       }
       fprev[0] = f[IDN]; fprev[1] = f[IVX]; fprev[2] = f[IVY]; fprev[3] = f[IVZ]; fprev[4] = f[IEN];
-#pragma unroll
-      for (int v = 0; v < 7; ++v) wl[v] = wl_up[v];
     }
   }
 };
-
-//========================================================================================
-// One face of a DIR-sweep, self-contained: reconstruct both adjacent cells, then Riemann solve.
-// c = index of the cell above the face, n_dir = its index along the sweep.
-template <int DIR, int ORDER, bool MHD>
-ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
-  const Grid &g = a.g;
-  const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
-  Real q0[7], q1[7], q2[7], q3[7], wl[7], wr[7], t0[7], t1[7];
-  load_q<DIR, MHD>(a, blk, c - s, q1);
-  load_q<DIR, MHD>(a, blk, c, q2);
-  if (ORDER == 2) {
-    load_q<DIR, MHD>(a, blk, c - 2 * s, q0);
-    load_q<DIR, MHD>(a, blk, c + s, q3);
-    const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
-    const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
-    recon_cell<ORDER, MHD>(q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
-    recon_cell<ORDER, MHD>(q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
-  } else {
-#pragma unroll
-    for (int v = 0; v < 7; ++v) { wl[v] = q1[v]; wr[v] = q2[v]; }
-  }
-  solve_face<DIR, MHD>(a, blk, c, n_dir, wl, wr, f, store);
-}
 
 //========================================================================================
 // x1 sweep: one thread per face (coalesced along i).  compute() is the face solve; the GPU
@@ -229,23 +249,7 @@ template <int ORDER, bool MHD>
 struct SweepX1 {
   SweepArgs a;
   ATHK_HD void compute(int blk, int k, int j, int i, Real f[7], bool store) const {
-    const Grid &g = a.g;
-    const idx_t c = gidx(g, k, j, i);
-    Real q0[7], q1[7], q2[7], q3[7], wl[7], wr[7], t0[7], t1[7];
-    load_q<0, MHD>(a, blk, c - 1, q1);
-    load_q<0, MHD>(a, blk, c, q2);
-    if (ORDER == 2) {
-      load_q<0, MHD>(a, blk, c - 2, q0);
-      load_q<0, MHD>(a, blk, c + 1, q3);
-      const Real *cpv = a.geo.cp[0] + blk * a.geo.PG;
-      const Real *cmv = a.geo.cm[0] + blk * a.geo.PG;
-      recon_cell<ORDER, MHD>(q0, q1, q2, cpv[i - 1], cmv[i - 1], wl, t0);   // cell i-1 -> L state
-      recon_cell<ORDER, MHD>(q1, q2, q3, cpv[i], cmv[i], t1, wr);           // cell i   -> R state
-    } else {
-#pragma unroll
-      for (int v = 0; v < 7; ++v) { wl[v] = q1[v]; wr[v] = q2[v]; }
-    }
-    solve_face<0, MHD>(a, blk, c, i, wl, wr, f, store);
+    face_compute<0, ORDER, MHD>(a, blk, gidx(a.g, k, j, i), i, f, store);
   }
   // cell (k,j,i) of the active zone.  The x1 sweep runs LAST: it forms
   //   dflx = (A1 F(i+1) - A1 F(i)); dflx += d2; dflx += d3     (add_flux_divergence.cpp:57-83)

@@ -35,6 +35,12 @@ CASES = {
     "hydro_linwave_rk3_plm_hllc": dict(cfg="linwave_hydro_hllc", mhd=False, mesh=(32, 16, 16),
                                        block=(16, 8, 8), tlim=0.1, integrator="rk3", xorder=2,
                                        wave_flag=4, vflow=0.5),
+    # PPM (xorder=3) needs NGHOST >= 3: reference built with --nghost=3
+    "hydro_linwave_rk3_ppm_hllc": dict(cfg="linwave_hydro_hllc_g3", mhd=False, mesh=(32, 16, 16),
+                                       block=(16, 8, 8), tlim=0.1, integrator="rk3", xorder=3),
+    "mhd_linwave_vl2_ppm_hlld": dict(cfg="linwave_mhd_hlld_g3", mhd=True, mesh=(32, 16, 16),
+                                     block=(16, 8, 8), tlim=0.05, integrator="vl2", xorder=3,
+                                     wave_flag=2, amp=1.0e-3),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),

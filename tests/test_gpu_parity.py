@@ -9,7 +9,8 @@ import util
 pytestmark = pytest.mark.gpu
 
 CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_rk2_plm_hlld",
-         "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2"]
+         "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2",
+         "hydro_linwave_rk3_ppm_hllc", "mhd_linwave_vl2_ppm_hlld"]
 
 
 @pytest.mark.parametrize("name", CASES)
