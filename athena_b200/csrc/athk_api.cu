@@ -1,26 +1,21 @@
 // athk_api.cu -- context, memory and the C ABI (include/athk.h) of libathk.so.
 // Product build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false (see athk_physics.h).
-#include "../../include/athk.h"
+#include "athk_ctx.h"
+#include "athk_sweep_launch_impl.h"
 
-#include <float.h>
-#include <math.h>
-#include <stdarg.h>
-
-#include <string>
-#include <vector>
-
-#include "athk_backend.h"
-#include "athk_ops.h"
-#include "athk_sweep.h"
-#ifndef ATHK_EMULATE
-#include "athk_sweep_kernels.cuh"
-#endif
-
-using namespace athk;
+ATHK_INSTANTIATE_RS(athk::RS_HLLC, false)
+ATHK_INSTANTIATE_RS(athk::RS_HLLD, true)
+ATHK_EXTERN_RS(athk::RS_ROE, false)
+ATHK_EXTERN_RS(athk::RS_ROE, true)
+ATHK_EXTERN_RS(athk::RS_HLLE, false)
+ATHK_EXTERN_RS(athk::RS_HLLE, true)
+ATHK_EXTERN_RS(athk::RS_LLF, false)
+ATHK_EXTERN_RS(athk::RS_LLF, true)
 
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char *fmt, ...) {
+#undef fail
+int athk_fail(int code, const char *fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -29,57 +24,8 @@ static int fail(int code, const char *fmt, ...) {
   g_last_error = buf;
   return code;
 }
+#define fail athk_fail
 
-#define CU(call)                                                                           \
-  do {                                                                                     \
-    cudaError_t e_ = (call);                                                               \
-    if (e_ != cudaSuccess)                                                                 \
-      return fail(ATHK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
-                  __FILE__, __LINE__);                                                     \
-  } while (0)
-
-struct athk_ctx {
-  athk_config cfg;
-  Grid g;
-  Geom geo;
-  EosParams eos;
-  EmfSurf sf;
-  cudaStream_t stream;
-  long long launches;
-  bool coords_set, nbr_set;
-  int nremote;
-  // storage
-  Real *u[3];       // hydro registers [nb][5][sn]
-  Real *w;          // [nb][5][sn]
-  Real *bcc;        // [nb][3][sn]
-  Real *b[3];       // field registers [nb][3][sn]
-  Real *flux[3];    // [nb][5][sn]
-  Real *ef;         // [nb][6][sn]
-  Real *wct;        // [nb][3][sn]
-  Real *e;          // [nb][3][sn]
-  Real *s[3];       // scalar registers [nb][ns][sn]
-  Real *r;          // [nb][ns][sn]
-  Real *sflux[3];   // [nb][ns][sn]
-  Real *emfbuf;     // [nb][sf.per_block]
-  // remote (other-GPU) neighbour links
-  RemoteLinks rl;
-  int *rl_int;        // device [4][n]: lb,o1,o2,o3
-  idx_t *rl_off;      // device [5][n]: gsend,grecv,esend,erecv,ebase
-  std::vector<int> h_rl_int;
-  std::vector<idx_t> h_rl_off;
-  idx_t max_ghost_count, max_emf_count;
-  SlabTable *slab_tab;   // device
-  bool dt_requested, dt_valid;   // NewBlockTimeStep fused into the next / last W(U)
-  // optional per-kernel timing with CUDA events on the launching stream (athk_profile)
-  bool prof_on;
-  struct ProfRec { const char *name; cudaEvent_t a, b; };
-  std::vector<ProfRec> prof;
-  Real *geo_store;  // 9 arrays [nb][PG]
-  int *nbr;         // [nb][27]
-  Real *dt_blocks;  // [nb]
-  std::vector<int> h_nbr;
-  std::vector<Real> h_geo;   // host mirror of geo_store
-};
 
 static size_t cc_elems(const athk_ctx *c, int nvar) { return (size_t)c->g.nb * nvar * c->g.sn; }
 
@@ -105,12 +51,13 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   if (cfg->nblocks < 1) return fail(ATHK_ERR_ARG, "athk_create: nblocks must be >= 1");
   if (cfg->nscalars < 0 || cfg->nscalars > 8)
     return fail(ATHK_ERR_ARG, "athk_create: nscalars must be 0..8");
-  if (cfg->mhd && cfg->rsolver != ATHK_RS_HLLD)
-    return fail(ATHK_ERR_ARG, "athk_create: MHD path implements rsolver HLLD only (got %d)",
-                cfg->rsolver);
-  if (!cfg->mhd && cfg->rsolver != ATHK_RS_HLLC)
-    return fail(ATHK_ERR_ARG, "athk_create: hydro path implements rsolver HLLC only (got %d)",
-                cfg->rsolver);
+  // configure.py:376-389: hllc is hydro-only, hlld MHD-only; roe / hlle / llf exist for both
+  if (cfg->rsolver < ATHK_RS_HLLC || cfg->rsolver > ATHK_RS_LLF)
+    return fail(ATHK_ERR_ARG, "athk_create: unknown rsolver %d", cfg->rsolver);
+  if (cfg->mhd && cfg->rsolver == ATHK_RS_HLLC)
+    return fail(ATHK_ERR_ARG, "athk_create: rsolver HLLC is hydro-only (use HLLD, Roe, HLLE or LLF with mhd=1)");
+  if (!cfg->mhd && cfg->rsolver == ATHK_RS_HLLD)
+    return fail(ATHK_ERR_ARG, "athk_create: rsolver HLLD needs mhd=1 (use HLLC, Roe, HLLE or LLF)");
   if (!(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
@@ -426,7 +373,7 @@ extern "C" int athk_device_array(athk_ctx *c, int array, void **dptr, long long 
   } while (0)
 
 #ifndef ATHK_EMULATE
-static void prof_begin(athk_ctx *c, const char *name) {
+void athk_prof_begin(athk_ctx *c, const char *name) {
   if (!c->prof_on) return;
   athk_ctx::ProfRec r;
   r.name = name;
@@ -435,24 +382,14 @@ static void prof_begin(athk_ctx *c, const char *name) {
   cudaEventRecord(r.a, c->stream);
   c->prof.push_back(r);
 }
-static void prof_end(athk_ctx *c) {
+void athk_prof_end(athk_ctx *c) {
   if (c->prof_on && !c->prof.empty()) cudaEventRecord(c->prof.back().b, c->stream);
 }
 #else
-static void prof_begin(athk_ctx *, const char *) {}
-static void prof_end(athk_ctx *) {}
+void athk_prof_begin(athk_ctx *, const char *) {}
+void athk_prof_end(athk_ctx *) {}
 #endif
 
-// one kernel launch, optionally bracketed by CUDA events; named after the API entry point
-#define LAUNCH_NAMED(c, name, call) \
-  do {                            \
-    prof_begin((c), (name));      \
-    CU(call);                     \
-    prof_end(c);                  \
-    (c)->launches++;              \
-  } while (0)
-#define LAUNCH(c, range, functor) \
-  LAUNCH_NAMED(c, __func__, launch_points((c)->stream, (c)->g.nb, (range), (functor)))
 
 static bool bad_reg(int r) { return r < 0 || r > 2; }
 
@@ -503,49 +440,6 @@ extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   return ATHK_OK;
 }
 
-static SweepArgs make_sweep_args(athk_ctx *c, double dt, int breg, bool store_flux) {
-  SweepArgs a;
-  memset(&a, 0, sizeof(a));
-  a.g = c->g; a.eos = c->eos; a.geo = c->geo;
-  a.w = c->w; a.bcc = c->bcc; a.b = c->cfg.mhd ? c->b[breg] : nullptr;
-  for (int d = 0; d < 3; ++d) a.flx[d] = store_flux ? c->flux[d] : nullptr;
-  a.ef = c->ef; a.wct = c->wct;
-  a.d2 = c->flux[1];   // fused path only: the x2/x3 flux arrays double as scratch terms
-  a.d3 = c->flux[2];
-  a.dt = dt;
-  return a;
-}
-
-template <int DIR, int ORDER, bool MHD>
-static int launch_flux(athk_ctx *c, const SweepArgs &a) {
-  const Grid &g = c->g;
-  // loop limits of calculate_fluxes.cpp:68-76,176-182,299-302 (3-D)
-  Range3 r;
-  if (DIR == 0) {
-    r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
-    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
-  } else if (DIR == 1) {
-    r = {g.ks, g.ke, g.js, g.je + 1, g.is - 1, g.ie + 1};
-    if (MHD) { r.kl--; r.ku++; }
-  } else {
-    r = {g.ks, g.ke + 1, g.js, g.je, g.is, g.ie};
-    if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
-  }
-  FacePoint<DIR, ORDER, MHD> f = {a};
-  LAUNCH_NAMED(c, DIR == 0 ? "calculate_fluxes_x1" : (DIR == 1 ? "calculate_fluxes_x2" : "calculate_fluxes_x3"),
-               launch_points(c->stream, g.nb, r, f));
-  return ATHK_OK;
-}
-
-template <int ORDER, bool MHD>
-static int launch_flux3(athk_ctx *c, double dt, int breg) {
-  const SweepArgs a = make_sweep_args(c, dt, breg, true);
-  int rc = launch_flux<0, ORDER, MHD>(c, a);
-  if (!rc) rc = launch_flux<1, ORDER, MHD>(c, a);
-  if (!rc) rc = launch_flux<2, ORDER, MHD>(c, a);
-  return rc;
-}
-
 static int check_order(athk_ctx *c, int order, const char *who) {
   if (order < 1 || order > 3)
     return fail(ATHK_ERR_ARG, "%s: xorder %d not implemented (1 donor cell, 2 PLM, 3 PPM)", who, order);
@@ -561,9 +455,12 @@ extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int
   int rc = check_order(c, order, "calculate_fluxes");
   if (rc) return rc;
   const bool mhd = c->cfg.mhd != 0;
-  if (order == 1) return mhd ? launch_flux3<1, true>(c, dt_mesh, breg) : launch_flux3<1, false>(c, dt_mesh, breg);
-  if (order == 2) return mhd ? launch_flux3<2, true>(c, dt_mesh, breg) : launch_flux3<2, false>(c, dt_mesh, breg);
-  return mhd ? launch_flux3<3, true>(c, dt_mesh, breg) : launch_flux3<3, false>(c, dt_mesh, breg);
+  switch (c->cfg.rsolver) {
+    case ATHK_RS_ROE: return mhd ? athk_flux3_rs<RS_ROE, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_ROE, false>(c, order, dt_mesh, breg);
+    case ATHK_RS_HLLE: return mhd ? athk_flux3_rs<RS_HLLE, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLE, false>(c, order, dt_mesh, breg);
+    case ATHK_RS_LLF: return mhd ? athk_flux3_rs<RS_LLF, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_LLF, false>(c, order, dt_mesh, breg);
+    default: return mhd ? athk_flux3_rs<RS_HLLD, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLC, false>(c, order, dt_mesh, breg);
+  }
 }
 
 extern "C" int athk_compute_corner_e(athk_ctx *c) {
@@ -831,44 +728,7 @@ extern "C" int athk_calculate_scalar_fluxes(athk_ctx *, int) { return fail(ATHK_
 extern "C" int athk_add_scalar_flux_divergence(athk_ctx *, double, int) { return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: not implemented yet"); }
 extern "C" int athk_history(athk_ctx *, double *, int) { return fail(ATHK_ERR_ARG, "history: not implemented yet"); }
 //----------------------------------------------------------------------------------------
-// Fused stage: same task sequence, fewer passes over HBM (see athk_sweep.h).
-template <int ORDER, bool MHD>
-static int launch_sweeps(athk_ctx *c, const SweepArgs &a) {
-  const Grid &g = c->g;
-#ifndef ATHK_EMULATE
-  // x2 columns (i,k) / x3 columns (i,j): CTA-marching tiles (athk_sweep_kernels.cuh);
-  // extents of calculate_fluxes.cpp:176-182,299-302
-  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x2_donor" : (ORDER == 2 ? "sweep_x2_plm" : "sweep_x2_ppm"),
-               (launch_sweep_tile<1, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.ks - 1 : g.ks,
-                                                 MHD ? g.ke + 1 : g.ke, g.is - 1, g.ie + 1)));
-  LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x3_donor" : (ORDER == 2 ? "sweep_x3_plm" : "sweep_x3_ppm"),
-               (launch_sweep_tile<2, ORDER, MHD>(c->stream, a, g.nb, MHD ? g.js - 1 : g.js,
-                                                 MHD ? g.je + 1 : g.je, MHD ? g.is - 1 : g.is,
-                                                 MHD ? g.ie + 1 : g.ie)));
-#else
-  {   // host harness: the same sweeps as per-thread marches
-    Range3 r = {g.ks, g.ke, 0, 0, g.is - 1, g.ie + 1};
-    if (MHD) { r.kl--; r.ku++; }
-    SweepMarch<1, ORDER, MHD> f = {a};
-    CU(launch_points(c->stream, g.nb, r, f, 128));
-  }
-  {
-    Range3 r = {0, 0, g.js, g.je, g.is, g.ie};
-    if (MHD) { r.jl--; r.ju++; r.il--; r.iu++; }
-    SweepMarch<2, ORDER, MHD> f = {a};
-    CU(launch_points(c->stream, g.nb, r, f, 128));
-  }
-#endif
-  {   // x1 last (calculate_fluxes.cpp:68-76): sums d1+d2+d3 and integrates
-    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
-    if (MHD) { r.kl--; r.ku++; r.jl--; r.ju++; }
-    SweepX1<ORDER, MHD> f = {a};
-    LAUNCH_NAMED(c, ORDER == 1 ? "sweep_x1_donor_integrate" : (ORDER == 2 ? "sweep_x1_plm_integrate" : "sweep_x1_ppm_integrate"),
-                 launch_sweep_x1(c->stream, g.nb, r, f));
-  }
-  return ATHK_OK;
-}
-
+// Fused stage: same task sequence, fewer passes over HBM (see athk_sweep.h, athk_sweep_launch_impl.h).
 extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wghts *sw,
                           double dt_mesh) {
   int rc = athk_stage_phase(c, 0, stage, order, sw, dt_mesh);
@@ -903,9 +763,12 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     h.delta = sw->delta; h.g1 = sw->gamma_1; h.g2 = sw->gamma_2;
     h.wght = sw->beta * dt_mesh;
     h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
-    if (order == 1) rc = mhd ? launch_sweeps<1, true>(c, a) : launch_sweeps<1, false>(c, a);
-    else if (order == 2) rc = mhd ? launch_sweeps<2, true>(c, a) : launch_sweeps<2, false>(c, a);
-    else rc = mhd ? launch_sweeps<3, true>(c, a) : launch_sweeps<3, false>(c, a);
+    switch (c->cfg.rsolver) {
+      case ATHK_RS_ROE: rc = mhd ? athk_sweeps_rs<RS_ROE, true>(c, order, a) : athk_sweeps_rs<RS_ROE, false>(c, order, a); break;
+      case ATHK_RS_HLLE: rc = mhd ? athk_sweeps_rs<RS_HLLE, true>(c, order, a) : athk_sweeps_rs<RS_HLLE, false>(c, order, a); break;
+      case ATHK_RS_LLF: rc = mhd ? athk_sweeps_rs<RS_LLF, true>(c, order, a) : athk_sweeps_rs<RS_LLF, false>(c, order, a); break;
+      default: rc = mhd ? athk_sweeps_rs<RS_HLLD, true>(c, order, a) : athk_sweeps_rs<RS_HLLC, false>(c, order, a); break;
+    }
     if (rc) return rc;
     if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
     if (mhd) {

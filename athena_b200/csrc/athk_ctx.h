@@ -1,0 +1,94 @@
+// athk_ctx.h -- the context behind include/athk.h's opaque athk_ctx, error plumbing and the launch
+// macros; shared by the translation units of libathk.so (athk_api.cu and the per-Riemann-solver
+// athk_rs_*.cu, which only hold kernel instantiations).
+#ifndef ATHK_CTX_H_
+#define ATHK_CTX_H_
+#include "../../include/athk.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "athk_backend.h"
+#include "athk_ops.h"
+#include "athk_sweep.h"
+#ifndef ATHK_EMULATE
+#include "athk_sweep_kernels.cuh"
+#endif
+
+using namespace athk;
+
+int athk_fail(int code, const char *fmt, ...);   // records athk_last_error(), returns code
+#define fail athk_fail
+
+#define CU(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(ATHK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+struct athk_ctx {
+  athk_config cfg;
+  Grid g;
+  Geom geo;
+  EosParams eos;
+  EmfSurf sf;
+  cudaStream_t stream;
+  long long launches;
+  bool coords_set, nbr_set;
+  int nremote;
+  // storage
+  Real *u[3];       // hydro registers [nb][5][sn]
+  Real *w;          // [nb][5][sn]
+  Real *bcc;        // [nb][3][sn]
+  Real *b[3];       // field registers [nb][3][sn]
+  Real *flux[3];    // [nb][5][sn]
+  Real *ef;         // [nb][6][sn]
+  Real *wct;        // [nb][3][sn]
+  Real *e;          // [nb][3][sn]
+  Real *s[3];       // scalar registers [nb][ns][sn]
+  Real *r;          // [nb][ns][sn]
+  Real *sflux[3];   // [nb][ns][sn]
+  Real *emfbuf;     // [nb][sf.per_block]
+  // remote (other-GPU) neighbour links
+  RemoteLinks rl;
+  int *rl_int;        // device [4][n]: lb,o1,o2,o3
+  idx_t *rl_off;      // device [5][n]: gsend,grecv,esend,erecv,ebase
+  std::vector<int> h_rl_int;
+  std::vector<idx_t> h_rl_off;
+  idx_t max_ghost_count, max_emf_count;
+  SlabTable *slab_tab;   // device
+  bool dt_requested, dt_valid;   // NewBlockTimeStep fused into the next / last W(U)
+  // optional per-kernel timing with CUDA events on the launching stream (athk_profile)
+  bool prof_on;
+  struct ProfRec { const char *name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  Real *geo_store;  // 9 arrays [nb][PG]
+  int *nbr;         // [nb][27]
+  Real *dt_blocks;  // [nb]
+  std::vector<int> h_nbr;
+  std::vector<Real> h_geo;   // host mirror of geo_store
+};
+
+void athk_prof_begin(athk_ctx *c, const char *name);
+void athk_prof_end(athk_ctx *c);
+#define prof_begin athk_prof_begin
+#define prof_end athk_prof_end
+// one kernel launch, optionally bracketed by CUDA events; named after the API entry point
+#define LAUNCH_NAMED(c, name, call) \
+  do {                            \
+    prof_begin((c), (name));      \
+    CU(call);                     \
+    prof_end(c);                  \
+    (c)->launches++;              \
+  } while (0)
+#define LAUNCH(c, range, functor) \
+  LAUNCH_NAMED(c, __func__, launch_points((c)->stream, (c)->g.nb, (range), (functor)))
+
+#endif  // ATHK_CTX_H_

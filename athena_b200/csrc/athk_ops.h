@@ -12,7 +12,7 @@
 #ifndef ATHK_OPS_H_
 #define ATHK_OPS_H_
 
-#include "athk_physics.h"
+#include "athk_rsolvers.h"
 
 namespace athk {
 

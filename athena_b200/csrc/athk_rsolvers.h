@@ -1,0 +1,583 @@
+// athk_rsolvers.h -- the reference's alternative Riemann solvers (one is linked per build there,
+// Makefile.in:73; selected at run time here through athk_config.rsolver).  Same conventions as
+// hllc_flux / hlld_flux in athk_physics.h: states in the sweep frame, adiabatic EOS, bit-exact
+// association order.
+//   hydro: HLLE  hydro/rsolvers/hydro/hlle.cpp:38-162
+//          LLF   hydro/rsolvers/hydro/llf.cpp:34-123
+//          Roe   hydro/rsolvers/hydro/roe.cpp:43-175 (+ RoeFlux :185-300; LLF fallback when an
+//                intermediate density is negative)
+//   MHD:   HLLE  hydro/rsolvers/mhd/hlle_mhd.cpp:25-182
+//          LLF   hydro/rsolvers/mhd/llf_mhd.cpp
+#ifndef ATHK_RSOLVERS_H_
+#define ATHK_RSOLVERS_H_
+
+#include "athk_physics.h"
+
+namespace athk {
+
+enum { RS_HLLC = 0, RS_HLLD = 1, RS_ROE = 2, RS_HLLE = 3, RS_LLF = 4 };   // == enum athk_rsolver
+
+//----------------------------------------------------------------------------------------
+ATHK_HD void hlle_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real gm1 = eos.gm1;
+  const Real igm1 = 1.0 / gm1;
+  Real wroe[5], fl[5], fr[5];
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl * sqrtdr;
+  wroe[IVX] = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  wroe[IVY] = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  wroe[IVZ] = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  Real el = wl[IPR] * igm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
+  Real er = wr[IPR] * igm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
+  Real hroe = ((el + wl[IPR]) / sqrtdl + (er + wr[IPR]) / sqrtdr) * isdlpdr;
+  Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
+  Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+  Real q = hroe - 0.5 * (sqr(wroe[IVX]) + sqr(wroe[IVY]) + sqr(wroe[IVZ]));
+  Real a = (q < 0.0) ? 0.0 : sqrt(gm1 * q);
+  Real al = min_std((wroe[IVX] - a), (wl[IVX] - cl));
+  Real ar = max_std((wroe[IVX] + a), (wr[IVX] + cr));
+  Real bp = ar > 0.0 ? ar : 0.0;
+  Real bm = al < 0.0 ? al : 0.0;
+  Real vxl = wl[IVX] - bm;
+  Real vxr = wr[IVX] - bp;
+  fl[IDN] = wl[IDN] * vxl;
+  fr[IDN] = wr[IDN] * vxr;
+  fl[IVX] = wl[IDN] * wl[IVX] * vxl;
+  fr[IVX] = wr[IDN] * wr[IVX] * vxr;
+  fl[IVY] = wl[IDN] * wl[IVY] * vxl;
+  fr[IVY] = wr[IDN] * wr[IVY] * vxr;
+  fl[IVZ] = wl[IDN] * wl[IVZ] * vxl;
+  fr[IVZ] = wr[IDN] * wr[IVZ] * vxr;
+  fl[IVX] += wl[IPR];
+  fr[IVX] += wr[IPR];
+  fl[IEN] = el * vxl + wl[IPR] * wl[IVX];
+  fr[IEN] = er * vxr + wr[IPR] * wr[IVX];
+  Real tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+#pragma unroll
+  for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp;
+}
+
+//----------------------------------------------------------------------------------------
+// shared by LLF and Roe: physical fluxes, conserved jump
+ATHK_HD void hydro_lr_fluxes(const EosParams &eos, const Real wl[5], const Real wr[5], Real fl[5],
+                             Real fr[5], Real du[5], Real *pel, Real *per) {
+  const Real gm1 = eos.gm1;
+  Real mxl = wl[IDN] * wl[IVX];
+  Real mxr = wr[IDN] * wr[IVX];
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  fl[IVX] = mxl * wl[IVX];
+  fr[IVX] = mxr * wr[IVX];
+  fl[IVY] = mxl * wl[IVY];
+  fr[IVY] = mxr * wr[IVY];
+  fl[IVZ] = mxl * wl[IVZ];
+  fr[IVZ] = mxr * wr[IVZ];
+  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
+  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
+  fl[IVX] += wl[IPR];
+  fr[IVX] += wr[IPR];
+  fl[IEN] = (el + wl[IPR]) * wl[IVX];
+  fr[IEN] = (er + wr[IPR]) * wr[IVX];
+  du[IDN] = wr[IDN] - wl[IDN];
+  du[IVX] = wr[IDN] * wr[IVX] - wl[IDN] * wl[IVX];
+  du[IVY] = wr[IDN] * wr[IVY] - wl[IDN] * wl[IVY];
+  du[IVZ] = wr[IDN] * wr[IVZ] - wl[IDN] * wl[IVZ];
+  du[IEN] = er - el;
+  *pel = el;
+  *per = er;
+}
+
+ATHK_HD void llf_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  Real fl[5], fr[5], du[5], el, er;
+  Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
+  Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+  Real a = 0.5 * max_std((fabs(wl[IVX]) + cl), (fabs(wr[IVX]) + cr));
+  hydro_lr_fluxes(eos, wl, wr, fl, fr, du, &el, &er);
+#pragma unroll
+  for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
+}
+
+ATHK_HD void roe_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real gm1 = eos.gm1;
+  Real wroe[5], fl[5], fr[5], du[5], ev[5], el, er;
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl * sqrtdr;
+  wroe[IVX] = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  wroe[IVY] = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  wroe[IVZ] = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  hydro_lr_fluxes(eos, wl, wr, fl, fr, du, &el, &er);
+  wroe[IPR] = ((el + wl[IPR]) / sqrtdl + (er + wr[IPR]) / sqrtdr) * isdlpdr;   // Roe enthalpy
+#pragma unroll
+  for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]);
+  int llf_flag = 0;
+  {   // RoeFlux (roe.cpp:185-270)
+    const Real v1 = wroe[IVX], v2 = wroe[IVY], v3 = wroe[IVZ];
+    const Real h = wroe[IPR];
+    Real vsq = v1 * v1 + v2 * v2 + v3 * v3;
+    Real q = h - 0.5 * vsq;
+    Real cs_sq = (q < 0.0) ? (ATHK_TINY_NUMBER) : gm1 * q;
+    Real cs = sqrt(cs_sq);
+    ev[0] = v1 - cs;
+    ev[1] = v1;
+    ev[2] = v1;
+    ev[3] = v1;
+    ev[4] = v1 + cs;
+    Real a[5];
+    Real na = 0.5 / cs_sq;
+    a[0] = du[0] * (0.5 * gm1 * vsq + v1 * cs);
+    a[0] -= du[1] * (gm1 * v1 + cs);
+    a[0] -= du[2] * gm1 * v2;
+    a[0] -= du[3] * gm1 * v3;
+    a[0] += du[4] * gm1;
+    a[0] *= na;
+    a[1] = du[0] * (-v2);
+    a[1] += du[2];
+    a[2] = du[0] * (-v3);
+    a[2] += du[3];
+    Real qa = gm1 / cs_sq;
+    a[3] = du[0] * (1.0 - na * gm1 * vsq);
+    a[3] += du[1] * qa * v1;
+    a[3] += du[2] * qa * v2;
+    a[3] += du[3] * qa * v3;
+    a[3] -= du[4] * qa;
+    a[4] = du[0] * (0.5 * gm1 * vsq - v1 * cs);
+    a[4] -= du[1] * (gm1 * v1 - cs);
+    a[4] -= du[2] * gm1 * v2;
+    a[4] -= du[3] * gm1 * v3;
+    a[4] += du[4] * gm1;
+    a[4] *= na;
+    Real coeff[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) coeff[n] = -0.5 * fabs(ev[n]) * a[n];
+    Real dens = wl[IDN] + a[0];
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3];
+    if (dens < 0.0) llf_flag = 1;
+    f[0] += coeff[0];
+    f[0] += coeff[3];
+    f[0] += coeff[4];
+    f[1] += coeff[0] * (v1 - cs);
+    f[1] += coeff[3] * v1;
+    f[1] += coeff[4] * (v1 + cs);
+    f[2] += coeff[0] * v2;
+    f[2] += coeff[1];
+    f[2] += coeff[3] * v2;
+    f[2] += coeff[4] * v2;
+    f[3] += coeff[0] * v3;
+    f[3] += coeff[2];
+    f[3] += coeff[3] * v3;
+    f[3] += coeff[4] * v3;
+    f[4] += coeff[0] * (h - v1 * cs);
+    f[4] += coeff[1] * v2;
+    f[4] += coeff[2] * v3;
+    f[4] += coeff[3] * 0.5 * vsq;
+    f[4] += coeff[4] * (h + v1 * cs);
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = fl[n];
+  }
+  if (ev[4] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
+    Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+    Real a = 0.5 * max_std((fabs(wl[IVX]) + cl), (fabs(wr[IVX]) + cr));
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
+  }
+}
+
+//========================================================================================
+// MHD.  wl/wr = (d, vx, vy, vz, p, by, bz), bxi = face-normal field; f[IBY], f[IBZ] are the
+// induction fluxes the caller turns into EMFs (-f[IBY] -> ey, f[IBZ] -> ez).
+
+// shared by LLF and Roe (llf_mhd.cpp:78-125 == roe_mhd.cpp:108-160)
+ATHK_HD void mhd_lr_fluxes(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                           Real fl[7], Real fr[7], Real du[7], Real *pel, Real *per, Real *ppbl,
+                           Real *ppbr) {
+  const Real gm1 = eos.gm1;
+  Real mxl = wl[IDN] * wl[IVX];
+  Real mxr = wr[IDN] * wr[IVX];
+  Real pbl = 0.5 * (bxi * bxi + sqr(wl[IBY]) + sqr(wl[IBZ]));
+  Real pbr = 0.5 * (bxi * bxi + sqr(wr[IBY]) + sqr(wr[IBZ]));
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  fl[IVX] = mxl * wl[IVX] + pbl - sqr(bxi);
+  fr[IVX] = mxr * wr[IVX] + pbr - sqr(bxi);
+  fl[IVY] = mxl * wl[IVY] - bxi * wl[IBY];
+  fr[IVY] = mxr * wr[IVY] - bxi * wr[IBY];
+  fl[IVZ] = mxl * wl[IVZ] - bxi * wl[IBZ];
+  fr[IVZ] = mxr * wr[IVZ] - bxi * wr[IBZ];
+  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
+  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
+  fl[IVX] += wl[IPR];
+  fr[IVX] += wr[IPR];
+  fl[IEN] = (el + wl[IPR] + pbl - bxi * bxi) * wl[IVX];
+  fr[IEN] = (er + wr[IPR] + pbr - bxi * bxi) * wr[IVX];
+  fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
+  fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  fl[IBY] = wl[IBY] * wl[IVX] - bxi * wl[IVY];
+  fr[IBY] = wr[IBY] * wr[IVX] - bxi * wr[IVY];
+  fl[IBZ] = wl[IBZ] * wl[IVX] - bxi * wl[IVZ];
+  fr[IBZ] = wr[IBZ] * wr[IVX] - bxi * wr[IVZ];
+  du[IDN] = wr[IDN] - wl[IDN];
+  du[IVX] = wr[IDN] * wr[IVX] - wl[IDN] * wl[IVX];
+  du[IVY] = wr[IDN] * wr[IVY] - wl[IDN] * wl[IVY];
+  du[IVZ] = wr[IDN] * wr[IVZ] - wl[IDN] * wl[IVZ];
+  du[IEN] = er - el;
+  du[IBY] = wr[IBY] - wl[IBY];
+  du[IBZ] = wr[IBZ] - wl[IBZ];
+  *pel = el;
+  *per = er;
+  *ppbl = pbl;
+  *ppbr = pbr;
+}
+
+ATHK_HD void llf_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                          Real f[7]) {
+  Real fl[7], fr[7], du[7], el, er, pbl, pbr;
+  Real cfl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cfr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  Real a = 0.5 * max_std((fabs(wl[IVX]) + cfl), (fabs(wr[IVX]) + cfr));
+  mhd_lr_fluxes(eos, wl, wr, bxi, fl, fr, du, &el, &er, &pbl, &pbr);
+#pragma unroll
+  for (int n = 0; n < 7; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
+}
+
+ATHK_HD void hlle_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                           Real f[7]) {
+  const Real gm1 = eos.gm1;
+  Real wroe[7], fl[7], fr[7];
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl * sqrtdr;
+  wroe[IVX] = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  wroe[IVY] = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  wroe[IVZ] = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  wroe[IBY] = (sqrtdr * wl[IBY] + sqrtdl * wr[IBY]) * isdlpdr;
+  wroe[IBZ] = (sqrtdr * wl[IBZ] + sqrtdl * wr[IBZ]) * isdlpdr;
+  Real x = 0.5 * (sqr(wl[IBY] - wr[IBY]) + sqr(wl[IBZ] - wr[IBZ])) / (sqr(sqrtdl + sqrtdr));
+  Real y = 0.5 * (wl[IDN] + wr[IDN]) / wroe[IDN];
+  Real pbl = 0.5 * (bxi * bxi + sqr(wl[IBY]) + sqr(wl[IBZ]));
+  Real pbr = 0.5 * (bxi * bxi + sqr(wr[IBY]) + sqr(wr[IBZ]));
+  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
+  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
+  Real hroe = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr;
+  Real cl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  Real btsq = sqr(wroe[IBY]) + sqr(wroe[IBZ]);
+  Real vaxsq = bxi * bxi / wroe[IDN];
+  Real bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+  Real hp = hroe - (vaxsq + btsq / wroe[IDN]);
+  Real vsq = sqr(wroe[IVX]) + sqr(wroe[IVY]) + sqr(wroe[IVZ]);
+  Real twid_asq = max_std((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 0.0);
+  Real ct2 = bt_starsq / wroe[IDN];
+  Real tsum = vaxsq + ct2 + twid_asq;
+  Real tdif = vaxsq + ct2 - twid_asq;
+  Real cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  Real cfsq = 0.5 * (tsum + cf2_cs2);
+  Real a = sqrt(cfsq);
+  Real al = min_std((wroe[IVX] - a), (wl[IVX] - cl));
+  Real ar = max_std((wroe[IVX] + a), (wr[IVX] + cr));
+  Real bp = ar > 0.0 ? ar : 0.0;
+  Real bm = al < 0.0 ? al : 0.0;
+  Real vxl = wl[IVX] - bm;
+  Real vxr = wr[IVX] - bp;
+  fl[IDN] = wl[IDN] * vxl;
+  fr[IDN] = wr[IDN] * vxr;
+  fl[IVX] = wl[IDN] * wl[IVX] * vxl + pbl - sqr(bxi);
+  fr[IVX] = wr[IDN] * wr[IVX] * vxr + pbr - sqr(bxi);
+  fl[IVY] = wl[IDN] * wl[IVY] * vxl - bxi * wl[IBY];
+  fr[IVY] = wr[IDN] * wr[IVY] * vxr - bxi * wr[IBY];
+  fl[IVZ] = wl[IDN] * wl[IVZ] * vxl - bxi * wl[IBZ];
+  fr[IVZ] = wr[IDN] * wr[IVZ] * vxr - bxi * wr[IBZ];
+  fl[IVX] += wl[IPR];
+  fr[IVX] += wr[IPR];
+  fl[IEN] = el * vxl + wl[IVX] * (wl[IPR] + pbl - bxi * bxi);
+  fr[IEN] = er * vxr + wr[IVX] * (wr[IPR] + pbr - bxi * bxi);
+  fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
+  fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  fl[IBY] = wl[IBY] * vxl - bxi * wl[IVY];
+  fr[IBY] = wr[IBY] * vxr - bxi * wr[IVY];
+  fl[IBZ] = wl[IBZ] * vxl - bxi * wl[IVZ];
+  fr[IBZ] = wr[IBZ] * vxr - bxi * wr[IVZ];
+  Real tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+#pragma unroll
+  for (int n = 0; n < 7; ++n) f[n] = 0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp;
+}
+
+// roe_mhd.cpp:43-210 with RoeFlux :245-470 (adiabatic branch).  The LLF fallback of the reference
+// leaves the induction components at their Roe values (roe_mhd.cpp:193-205); so does this.
+ATHK_HD void roe_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                          Real f[7]) {
+  const Real gm1 = eos.gm1;
+  Real wroe[7], fl[7], fr[7], du[7], ev[7], el, er, pbl, pbr;
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl * sqrtdr;
+  wroe[IVX] = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  wroe[IVY] = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  wroe[IVZ] = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  wroe[IBY] = (sqrtdr * wl[IBY] + sqrtdl * wr[IBY]) * isdlpdr;
+  wroe[IBZ] = (sqrtdr * wl[IBZ] + sqrtdl * wr[IBZ]) * isdlpdr;
+  const Real x = 0.5 * (sqr(wl[IBY] - wr[IBY]) + sqr(wl[IBZ] - wr[IBZ])) / (sqr(sqrtdl + sqrtdr));
+  const Real y = 0.5 * (wl[IDN] + wr[IDN]) / wroe[IDN];
+  mhd_lr_fluxes(eos, wl, wr, bxi, fl, fr, du, &el, &er, &pbl, &pbr);
+  wroe[IPR] = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr;
+#pragma unroll
+  for (int n = 0; n < 7; ++n) f[n] = 0.5 * (fl[n] + fr[n]);
+  int llf_flag = 0;
+  {
+    const Real d = wroe[IDN], v1 = wroe[IVX], v2 = wroe[IVY], v3 = wroe[IVZ];
+    const Real b1 = bxi, b2 = wroe[IBY], b3 = wroe[IBZ];
+    Real di = 1.0 / d;
+    Real btsq = b2 * b2 + b3 * b3;
+    Real vaxsq = b1 * b1 * di;
+    Real vsq = v1 * v1 + v2 * v2 + v3 * v3;
+    Real hp = wroe[IPR] - (vaxsq + btsq * di);
+    Real bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+    Real twid_csq = max_std((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), ATHK_TINY_NUMBER);
+    Real ct2 = bt_starsq * di;
+    Real tsum = vaxsq + ct2 + twid_csq;
+    Real tdif = vaxsq + ct2 - twid_csq;
+    Real cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_csq * ct2);
+    Real cfsq = 0.5 * (tsum + cf2_cs2);
+    Real cf = sqrt(cfsq);
+    Real cssq = twid_csq * vaxsq / cfsq;
+    Real cs = sqrt(cssq);
+    Real bt = sqrt(btsq);
+    Real bt_star = sqrt(bt_starsq);
+    Real bet2 = 0.0;
+    Real bet3 = 0.0;
+    if (bt != 0.0) {
+      bet2 = b2 / bt;
+      bet3 = b3 / bt;
+    }
+    Real bet2_star = bet2 / sqrt(gm1 - (gm1 - 1.0) * y);
+    Real bet3_star = bet3 / sqrt(gm1 - (gm1 - 1.0) * y);
+    Real bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star;
+    Real vbet = v2 * bet2_star + v3 * bet3_star;
+    Real q2_star = 0.0;
+    Real q3_star = 0.0;
+    if (bet_starsq != 0.0) {
+      q2_star = bet2_star / bet_starsq;
+      q3_star = bet3_star / bet_starsq;
+    }
+    Real alpha_f, alpha_s;
+    if ((cfsq - cssq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else if ((twid_csq - cssq) <= 0.0) {
+      alpha_f = 0.0;
+      alpha_s = 1.0;
+    } else if ((cfsq - twid_csq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else {
+      alpha_f = sqrt((twid_csq - cssq) / (cfsq - cssq));
+      alpha_s = sqrt((cfsq - twid_csq) / (cfsq - cssq));
+    }
+    Real sqrtd = sqrt(d);
+    Real isqrtd = 1.0 / sqrtd;
+    Real s = sign_ath(b1);
+    Real twid_c = sqrt(twid_csq);
+    Real qf = cf * alpha_f * s;
+    Real qs = cs * alpha_s * s;
+    Real af_prime = twid_c * alpha_f * isqrtd;
+    Real as_prime = twid_c * alpha_s * isqrtd;
+    Real afpbb = af_prime * bt_star * bet_starsq;
+    Real aspbb = as_prime * bt_star * bet_starsq;
+    Real vqstr = (v2 * q2_star + v3 * q3_star);
+    Real vax = sqrt(vaxsq);
+    Real norm = 0.5 / twid_csq;
+    Real cff = norm * alpha_f * cf;
+    Real css = norm * alpha_s * cs;
+    Real qf_hat = qf * norm;
+    Real qs_hat = qs * norm;
+    Real af = norm * af_prime * d;
+    Real as = norm * as_prime * d;
+    Real afpb = norm * af_prime * bt_star;
+    Real aspb = norm * as_prime * bt_star;
+
+    ev[0] = v1 - cf;
+    ev[1] = v1 - vax;
+    ev[2] = v1 - cs;
+    ev[3] = v1;
+    ev[4] = v1 + cs;
+    ev[5] = v1 + vax;
+    ev[6] = v1 + cf;
+
+    Real a[7];
+    Real alpha_f_bar = alpha_f * gm1 * norm;
+    Real alpha_s_bar = alpha_s * gm1 * norm;
+    Real gm1a = gm1 / twid_csq;
+
+    a[0] = du[0] * (alpha_f_bar * (vsq - hp) + cff * (cf + v1) - qs_hat * vqstr - aspb);
+    a[0] -= du[1] * (alpha_f_bar * v1 + cff);
+    a[0] -= du[2] * (alpha_f_bar * v2 - qs_hat * q2_star);
+    a[0] -= du[3] * (alpha_f_bar * v3 - qs_hat * q3_star);
+    a[0] += du[4] * alpha_f_bar;
+    a[0] += du[5] * (as * q2_star - alpha_f_bar * b2);
+    a[0] += du[6] * (as * q3_star - alpha_f_bar * b3);
+
+    a[1] = du[0] * (v2 * bet3 - v3 * bet2);
+    a[1] -= du[2] * bet3;
+    a[1] += du[3] * bet2;
+    a[1] -= du[5] * sqrtd * bet3 * s;
+    a[1] += du[6] * sqrtd * bet2 * s;
+    a[1] *= 0.5;
+
+    a[2] = du[0] * (alpha_s_bar * (vsq - hp) + css * (cs + v1) + qf_hat * vqstr + afpb);
+    a[2] -= du[1] * (alpha_s_bar * v1 + css);
+    a[2] -= du[2] * (alpha_s_bar * v2 + qf_hat * q2_star);
+    a[2] -= du[3] * (alpha_s_bar * v3 + qf_hat * q3_star);
+    a[2] += du[4] * alpha_s_bar;
+    a[2] -= du[5] * (af * q2_star + alpha_s_bar * b2);
+    a[2] -= du[6] * (af * q3_star + alpha_s_bar * b3);
+
+    a[3] = du[0] * (1.0 - gm1a * (0.5 * vsq - (gm1 - 1.0) * x / gm1));
+    a[3] += du[1] * gm1a * v1;
+    a[3] += du[2] * gm1a * v2;
+    a[3] += du[3] * gm1a * v3;
+    a[3] -= du[4] * gm1a;
+    a[3] += du[5] * gm1a * b2;
+    a[3] += du[6] * gm1a * b3;
+
+    a[4] = du[0] * (alpha_s_bar * (vsq - hp) + css * (cs - v1) - qf_hat * vqstr + afpb);
+    a[4] -= du[1] * (alpha_s_bar * v1 - css);
+    a[4] -= du[2] * (alpha_s_bar * v2 - qf_hat * q2_star);
+    a[4] -= du[3] * (alpha_s_bar * v3 - qf_hat * q3_star);
+    a[4] += du[4] * alpha_s_bar;
+    a[4] -= du[5] * (af * q2_star + alpha_s_bar * b2);
+    a[4] -= du[6] * (af * q3_star + alpha_s_bar * b3);
+
+    a[5] = du[0] * (v3 * bet2 - v2 * bet3);
+    a[5] += du[2] * bet3;
+    a[5] -= du[3] * bet2;
+    a[5] -= du[5] * sqrtd * bet3 * s;
+    a[5] += du[6] * sqrtd * bet2 * s;
+    a[5] *= 0.5;
+
+    a[6] = du[0] * (alpha_f_bar * (vsq - hp) + cff * (cf - v1) + qs_hat * vqstr - aspb);
+    a[6] -= du[1] * (alpha_f_bar * v1 - cff);
+    a[6] -= du[2] * (alpha_f_bar * v2 + qs_hat * q2_star);
+    a[6] -= du[3] * (alpha_f_bar * v3 + qs_hat * q3_star);
+    a[6] += du[4] * alpha_f_bar;
+    a[6] += du[5] * (as * q2_star - alpha_f_bar * b2);
+    a[6] += du[6] * (as * q3_star - alpha_f_bar * b3);
+
+    Real coeff[7];
+#pragma unroll
+    for (int n = 0; n < 7; ++n) coeff[n] = -0.5 * fabs(ev[n]) * a[n];
+
+    Real dens = wl[IDN] + a[0] * alpha_f;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[2] * alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3];
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[4] * alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+
+    f[0] += coeff[0] * alpha_f;
+    f[0] += coeff[2] * alpha_s;
+    f[0] += coeff[3];
+    f[0] += coeff[4] * alpha_s;
+    f[0] += coeff[6] * alpha_f;
+
+    f[1] += coeff[0] * (alpha_f * (v1 - cf));
+    f[1] += coeff[2] * (alpha_s * (v1 - cs));
+    f[1] += coeff[3] * v1;
+    f[1] += coeff[4] * (alpha_s * (v1 + cs));
+    f[1] += coeff[6] * (alpha_f * (v1 + cf));
+
+    f[2] += coeff[0] * (alpha_f * v2 + qs * bet2_star);
+    f[2] -= coeff[1] * bet3;
+    f[2] += coeff[2] * (alpha_s * v2 - qf * bet2_star);
+    f[2] += coeff[3] * v2;
+    f[2] += coeff[4] * (alpha_s * v2 + qf * bet2_star);
+    f[2] += coeff[5] * bet3;
+    f[2] += coeff[6] * (alpha_f * v2 - qs * bet2_star);
+
+    f[3] += coeff[0] * (alpha_f * v3 + qs * bet3_star);
+    f[3] += coeff[1] * bet2;
+    f[3] += coeff[2] * (alpha_s * v3 - qf * bet3_star);
+    f[3] += coeff[3] * v3;
+    f[3] += coeff[4] * (alpha_s * v3 + qf * bet3_star);
+    f[3] -= coeff[5] * bet2;
+    f[3] += coeff[6] * (alpha_f * v3 - qs * bet3_star);
+
+    f[4] += coeff[0] * (alpha_f * (hp - v1 * cf) + qs * vbet + aspbb);
+    f[4] -= coeff[1] * (v2 * bet3 - v3 * bet2);
+    f[4] += coeff[2] * (alpha_s * (hp - v1 * cs) - qf * vbet - afpbb);
+    f[4] += coeff[3] * (0.5 * vsq + (gm1 - 1.0) * x / gm1);
+    f[4] += coeff[4] * (alpha_s * (hp + v1 * cs) + qf * vbet - afpbb);
+    f[4] += coeff[5] * (v1 * bet3 - v3 * bet2);
+    f[4] += coeff[6] * (alpha_f * (hp + v1 * cf) - qs * vbet + aspbb);
+
+    f[5] += coeff[0] * as_prime * bet2_star;
+    f[5] -= coeff[1] * bet3 * s * isqrtd;
+    f[5] -= coeff[2] * af_prime * bet2_star;
+    f[5] -= coeff[4] * af_prime * bet2_star;
+    f[5] -= coeff[5] * bet3 * s * isqrtd;
+    f[5] += coeff[6] * as_prime * bet2_star;
+
+    f[6] += coeff[0] * as_prime * bet3_star;
+    f[6] += coeff[1] * bet2 * s * isqrtd;
+    f[6] -= coeff[2] * af_prime * bet3_star;
+    f[6] -= coeff[4] * af_prime * bet3_star;
+    f[6] += coeff[5] * bet2 * s * isqrtd;
+    f[6] += coeff[6] * as_prime * bet3_star;
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) f[n] = fl[n];
+  }
+  if (ev[6] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) f[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    Real cfl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+    Real cfr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+    Real a = 0.5 * max_std((fabs(wl[IVX]) + cfl), (fabs(wr[IVX]) + cfr));
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
+  }
+}
+
+//----------------------------------------------------------------------------------------
+// compile-time selection: every solver is its own kernel instantiation, so the registers of the
+// default HLLC / HLLD kernels do not pay for the Roe eigen-decomposition.
+constexpr int default_rsolver(bool mhd) { return mhd ? RS_HLLD : RS_HLLC; }
+
+template <int RS>
+ATHK_HD void hydro_riemann(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  if (RS == RS_HLLE) hlle_hydro_flux(eos, wl, wr, f);
+  else if (RS == RS_ROE) roe_hydro_flux(eos, wl, wr, f);
+  else if (RS == RS_LLF) llf_hydro_flux(eos, wl, wr, f);
+  else hllc_flux(eos, wl, wr, f);
+}
+
+template <int RS>
+ATHK_HD void mhd_riemann(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                         Real f[7]) {
+  if (RS == RS_HLLE) hlle_mhd_flux(eos, wl, wr, bxi, f);
+  else if (RS == RS_ROE) roe_mhd_flux(eos, wl, wr, bxi, f);
+  else if (RS == RS_LLF) llf_mhd_flux(eos, wl, wr, bxi, f);
+  else hlld_flux(eos, wl, wr, bxi, f);
+}
+
+}  // namespace athk
+#endif  // ATHK_RSOLVERS_H_

@@ -64,13 +64,13 @@ ATHK_HD void load_q(const SweepArgs &a, int blk, idx_t c, Real q[7]) {
 }
 
 // Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
-template <int DIR, bool MHD>
+template <int DIR, bool MHD, int RS>
 ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
                         const Real wr[7], Real f[7], bool store) {
   const Grid &g = a.g;
   if (MHD) {
     const Real bxi = a.b[((idx_t)blk * 3 + DIR) * g.sn + c];
-    hlld_flux(a.eos, wl, wr, bxi, f);
+    mhd_riemann<RS>(a.eos, wl, wr, bxi, f);
     if (store) {
       Real *eb = a.ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
       eb[0] = -f[IBY];
@@ -79,7 +79,7 @@ ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const R
       a.wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, a.dt);
     }
   } else {
-    hllc_flux(a.eos, wl, wr, f);
+    hydro_riemann<RS>(a.eos, wl, wr, f);
   }
   if (store && a.flx[DIR]) {
     Real *fb = a.flx[DIR] + (idx_t)blk * 5 * g.sn + c;
@@ -144,7 +144,7 @@ ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsu
 // One face of a DIR-sweep, self-contained: reconstruct both adjacent cells (donor cell, PLM or
 // PPM), then Riemann solve.  c = index of the cell above the face, n_dir = its index along the
 // sweep.
-template <int DIR, int ORDER, bool MHD>
+template <int DIR, int ORDER, bool MHD, int RS>
 ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
   const Grid &g = a.g;
   const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
@@ -186,16 +186,16 @@ ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real 
     load_q<DIR, MHD>(a, blk, c - s, wl);
     load_q<DIR, MHD>(a, blk, c, wr);
   }
-  solve_face<DIR, MHD>(a, blk, c, n_dir, wl, wr, f, store);
+  solve_face<DIR, MHD, RS>(a, blk, c, n_dir, wl, wr, f, store);
 }
 
 // Hydro::CalculateFluxes as an operator: one thread per face, fluxes stored (a.flx[DIR] set)
-template <int DIR, int ORDER, bool MHD>
+template <int DIR, int ORDER, bool MHD, int RS = default_rsolver(MHD)>
 struct FacePoint {
   SweepArgs a;
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     Real f[7];
-    face_compute<DIR, ORDER, MHD>(a, blk, gidx(a.g, k, j, i), (DIR == 0) ? i : (DIR == 1 ? j : k), f, true);
+    face_compute<DIR, ORDER, MHD, RS>(a, blk, gidx(a.g, k, j, i), (DIR == 0) ? i : (DIR == 1 ? j : k), f, true);
   }
 };
 
@@ -204,7 +204,7 @@ struct FacePoint {
 // tile kernels in athk_sweep_kernels.cuh -- same faces, same stores.
 //   DIR=1: column (i,k), marches j ; DIR=2: column (i,j), marches k.
 // Column extents follow calculate_fluxes.cpp:176-182,299-302; faces s..e+1 along the sweep.
-template <int DIR, int ORDER, bool MHD>
+template <int DIR, int ORDER, bool MHD, int RS = default_rsolver(MHD)>
 struct SweepMarch {
   SweepArgs a;
   // (blk, k, j, i): for DIR=1 the j argument is ignored, for DIR=2 the k argument is ignored
@@ -225,7 +225,7 @@ struct SweepMarch {
     Real f[7], fprev[5];
     for (int n = n_s; n <= n_e + 1; ++n) {
       const idx_t c = (DIR == 1) ? gidx(g, k, n, i) : gidx(g, n, j, i);
-      face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
+      face_compute<DIR, ORDER, MHD, RS>(a, blk, c, n, f, true);
       if (interior && n > n_s) {
         // cell n-1: (A F)(n) - (A F)(n-1)
         const idx_t cc = c - s;
@@ -245,11 +245,11 @@ struct SweepMarch {
 // x1 sweep: one thread per face (coalesced along i).  compute() is the face solve; the GPU
 // kernel passes the flux of face i+1 to the owner of cell i with a warp shuffle, the host
 // harness (tests/emul) simply solves face i+1 again.
-template <int ORDER, bool MHD>
+template <int ORDER, bool MHD, int RS = default_rsolver(MHD)>
 struct SweepX1 {
   SweepArgs a;
   ATHK_HD void compute(int blk, int k, int j, int i, Real f[7], bool store) const {
-    face_compute<0, ORDER, MHD>(a, blk, gidx(a.g, k, j, i), i, f, store);
+    face_compute<0, ORDER, MHD, RS>(a, blk, gidx(a.g, k, j, i), i, f, store);
   }
   // cell (k,j,i) of the active zone.  The x1 sweep runs LAST: it forms
   //   dflx = (A1 F(i+1) - A1 F(i)); dflx += d2; dflx += d3     (add_flux_divergence.cpp:57-83)

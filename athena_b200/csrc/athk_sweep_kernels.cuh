@@ -28,7 +28,7 @@ namespace athk {
 #define ATHK_TILE_PREFETCH 1   // 1: prefetch.global.L2 of the next step's cell, 2: .L1, 0: off
 #endif
 
-template <int DIR, int ORDER, bool MHD>
+template <int DIR, int ORDER, bool MHD, int RS>
 __global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
 k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il,
              const int ni) {
@@ -88,7 +88,7 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
         }
       }
 #endif
-      face_compute<DIR, ORDER, MHD>(a, blk, c, n, f, true);
+      face_compute<DIR, ORDER, MHD, RS>(a, blk, c, n, f, true);
       sF[buf][r][0][lane] = f[IDN];
       sF[buf][r][1][lane] = f[IVX];
       sF[buf][r][2][lane] = f[IVY];
@@ -107,7 +107,7 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
   }
 }
 
-template <int DIR, int ORDER, bool MHD>
+template <int DIR, int ORDER, bool MHD, int RS>
 static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a, int nb, int o_lo,
                                             int o_hi, int il, int iu) {
   const int n_o = o_hi - o_lo + 1, ni = iu - il + 1;
@@ -115,7 +115,7 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   if (ncol <= 0) return cudaSuccess;
   dim3 block(32, ATHK_TILE_R);
   const unsigned grid = (unsigned)((ncol + 31) / 32);
-  k_sweep_tile<DIR, ORDER, MHD><<<grid, block, 0, st>>>(a, nb, o_lo, n_o, il, ni);
+  k_sweep_tile<DIR, ORDER, MHD, RS><<<grid, block, 0, st>>>(a, nb, o_lo, n_o, il, ni);
   return cudaGetLastError();
 }
 

@@ -29,7 +29,12 @@ CONFIGS = {
     "linwave_mhd_hlld": dict(PROB="linear_wave", MHD=1, FLUX="hlld"),
     "linwave_mhd_roe": dict(PROB="linear_wave", MHD=1, FLUX="roe"),
     "linwave_mhd_hlle": dict(PROB="linear_wave", MHD=1, FLUX="hlle"),
+    "linwave_hydro_llf": dict(PROB="linear_wave", MHD=0, FLUX="llf"),
+    "linwave_mhd_llf": dict(PROB="linear_wave", MHD=1, FLUX="llf"),
     "blast_mhd_hlld": dict(PROB="blast", MHD=1, FLUX="hlld"),
+    "blast_mhd_roe": dict(PROB="blast", MHD=1, FLUX="roe"),
+    "shocktube_hydro_roe": dict(PROB="shock_tube", MHD=0, FLUX="roe"),
+    "shocktube_mhd_roe": dict(PROB="shock_tube", MHD=1, FLUX="roe"),
     "blast_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc"),
     "ot_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld"),
     "kh_hydro_hllc_s1g3": dict(PROB="kh", MHD=0, FLUX="hllc", NGHOST=3, NSCALARS=1),
@@ -239,6 +244,23 @@ def read_hst(path):
             if line.strip():
                 rows.append([float(x) for x in line.split()])
     return names, np.array(rows)
+
+
+def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, **kw):
+    """athinput for pgen/shock_tube.cpp on the linear-wave test box (periodic, so the two
+    discontinuities interact across the seam).  left/right = (d, u, v, w, p[, by, bz]) in the
+    shock_dir frame (shock_tube.cpp:335-366)."""
+    b = linwave_blocks(mhd, problem_id="Sod", **kw)
+    ext = {1: 3.0, 2: 1.5, 3: 1.5}[shock_dir]
+    pr = {"shock_dir": shock_dir, "xshock": 0.5 * ext if xshock is None else xshock,
+          "compute_error": "false"}
+    for side, st in (("l", left), ("r", right)):
+        for key, val in zip(("d", "u", "v", "w", "p"), st[:5]):
+            pr[key + side] = float(val)
+        if mhd:
+            pr["bx" + side], pr["by" + side], pr["bz" + side] = float(bx), float(st[5]), float(st[6])
+    b["problem"] = pr
+    return b
 
 
 def linwave_blocks(mhd, mesh=(32, 16, 16), block=None, tlim=0.1, nlim=-1, wave_flag=0,

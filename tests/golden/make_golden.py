@@ -41,6 +41,45 @@ CASES = {
     "mhd_linwave_vl2_ppm_hlld": dict(cfg="linwave_mhd_hlld_g3", mhd=True, mesh=(32, 16, 16),
                                      block=(16, 8, 8), tlim=0.05, integrator="vl2", xorder=3,
                                      wave_flag=2, amp=1.0e-3),
+    # the alternative Riemann solvers (one reference build per --flux)
+    "hydro_linwave_vl2_plm_roe": dict(cfg="linwave_hydro_roe", mhd=False, mesh=(32, 16, 16),
+                                      block=(16, 8, 8), tlim=0.1, integrator="vl2", xorder=2,
+                                      amp=1.0e-3, flux="roe"),
+    # supersonic background flow: the upwind overrides of roe.cpp:133-146 / bm = 0 of hlle.cpp
+    "hydro_linwave_rk2_plm_roe_supersonic": dict(cfg="linwave_hydro_roe", mhd=False, mesh=(32, 16, 16),
+                                                 block=(16, 16, 16), tlim=0.05, integrator="rk2",
+                                                 xorder=2, amp=1.0e-2, vflow=2.0, flux="roe"),
+    "hydro_linwave_vl2_plm_hlle": dict(cfg="linwave_hydro_hlle", mhd=False, mesh=(32, 16, 16),
+                                       block=(16, 8, 8), tlim=0.1, integrator="vl2", xorder=2,
+                                       amp=1.0e-3, vflow=0.7, flux="hlle"),
+    "hydro_linwave_vl2_plm_llf": dict(cfg="linwave_hydro_llf", mhd=False, mesh=(32, 16, 16),
+                                      block=(32, 16, 16), tlim=0.05, integrator="vl2", xorder=2,
+                                      amp=1.0e-3, flux="llf"),
+    "mhd_linwave_vl2_plm_roe": dict(cfg="linwave_mhd_roe", mhd=True, mesh=(32, 16, 16),
+                                    block=(16, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
+                                    amp=1.0e-3, flux="roe"),
+    "mhd_linwave_rk3_plm_roe_slow": dict(cfg="linwave_mhd_roe", mhd=True, mesh=(32, 16, 16),
+                                         block=(16, 16, 16), tlim=0.03, integrator="rk3", xorder=2,
+                                         wave_flag=2, amp=1.0e-2, vflow=1.0, flux="roe"),
+    "mhd_linwave_vl2_plm_hlle": dict(cfg="linwave_mhd_hlle", mhd=True, mesh=(32, 16, 16),
+                                     block=(16, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
+                                     amp=1.0e-3, flux="hlle"),
+    "mhd_linwave_vl2_plm_llf": dict(cfg="linwave_mhd_llf", mhd=True, mesh=(32, 16, 16),
+                                    block=(32, 16, 16), tlim=0.03, integrator="vl2", xorder=2,
+                                    amp=1.0e-3, flux="llf"),
+    # strong double rarefaction (Einfeldt 1-2-3) + the collision across the periodic seam: Roe's
+    # intermediate densities go negative -> LLF fallback (roe.cpp:150-164, roe_mhd.cpp:189-205)
+    "hydro_shocktube_vl2_plm_roe_llf": dict(cfg="shocktube_hydro_roe", mhd=False, mesh=(32, 16, 16),
+                                            block=(16, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
+                                            flux="roe", shocktube=dict(
+                                                left=(1.0, -2.0, 0.0, 0.0, 0.4),
+                                                right=(1.0, 2.0, 0.0, 0.0, 0.4), shock_dir=1)),
+    "mhd_shocktube_vl2_plm_roe_llf": dict(cfg="shocktube_mhd_roe", mhd=True, mesh=(32, 16, 16),
+                                          block=(16, 8, 8), tlim=0.03, integrator="vl2", xorder=2,
+                                          flux="roe", shocktube=dict(
+                                              left=(1.0, -2.0, 0.3, 0.0, 0.4, 1.0, 0.2),
+                                              right=(0.5, 2.0, -0.3, 0.1, 0.3, -1.0, 0.0),
+                                              shock_dir=2, bx=0.75)),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),
@@ -51,10 +90,15 @@ def make(name):
     c = CASES[name]
     if not refrun.build_ref(c["cfg"]):
         raise SystemExit("reference binary for %s unavailable" % c["cfg"])
-    blocks = refrun.linwave_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
-                                   integrator=c["integrator"], xorder=c["xorder"],
-                                   wave_flag=c.get("wave_flag", 0), amp=c.get("amp", 1.0e-6),
-                                   vflow=c.get("vflow", 0.0))
+    if "shocktube" in c:
+        blocks = refrun.shocktube_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                         integrator=c["integrator"], xorder=c["xorder"],
+                                         **c["shocktube"])
+    else:
+        blocks = refrun.linwave_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                       integrator=c["integrator"], xorder=c["xorder"],
+                                       wave_flag=c.get("wave_flag", 0), amp=c.get("amp", 1.0e-6),
+                                       vflow=c.get("vflow", 0.0))
     wd, out = refrun.run_reference(c["cfg"], blocks)
     r0 = refrun.read_rst(glob.glob(wd + "/*.00000.rst")[0])
     rf = refrun.read_rst(glob.glob(wd + "/*.final.rst")[0])

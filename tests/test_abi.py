@@ -44,7 +44,8 @@ def test_no_device_is_an_error_not_a_fallback():
 def test_bad_arguments_are_rejected(emul_lib):
     lib = emul_lib
     h = ctypes.c_void_p()
-    for kw in (dict(nx1=2), dict(nghost=1), dict(nblocks=0), dict(gamma=0.9), dict(rsolver=capi.RS_ROE)):
+    for kw in (dict(nx1=2), dict(nghost=1), dict(nblocks=0), dict(gamma=0.9), dict(rsolver=capi.RS_HLLC),
+               dict(rsolver=7), dict(mhd=0)):   # hllc is hydro-only, hlld MHD-only (configure.py:376-389)
         base = dict(nx1=8, nx2=8, nx3=8, nghost=2, nblocks=1, mhd=1, nscalars=0,
                     rsolver=capi.RS_HLLD, device=0, gamma=1.4)
         base.update(kw)

@@ -7,7 +7,13 @@ import util
 
 CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_rk2_plm_hlld",
          "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2",
-         "hydro_linwave_rk3_ppm_hllc", "mhd_linwave_vl2_ppm_hlld"]
+         "hydro_linwave_rk3_ppm_hllc", "mhd_linwave_vl2_ppm_hlld",
+         # Roe / HLLE / LLF, hydro and MHD
+         "hydro_linwave_vl2_plm_roe", "hydro_linwave_rk2_plm_roe_supersonic",
+         "hydro_linwave_vl2_plm_hlle", "hydro_linwave_vl2_plm_llf", "mhd_linwave_vl2_plm_roe",
+         "mhd_linwave_rk3_plm_roe_slow", "mhd_linwave_vl2_plm_hlle", "mhd_linwave_vl2_plm_llf",
+         # Roe with negative intermediate densities -> LLF fallback, and supersonic upwinding
+         "hydro_shocktube_vl2_plm_roe_llf", "mhd_shocktube_vl2_plm_roe_llf"]
 
 
 @pytest.mark.parametrize("name", CASES)

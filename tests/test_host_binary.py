@@ -46,6 +46,8 @@ CASES = {
                           lambda: dict(refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(16, 8, 8),
                                                              tlim=0.1, rst_dt=0.05, integrator="rk3"))),
     "mhd_blast": ("blast_mhd_hlld", "blast", True, blast_blocks),
+    # --flux=roe through the host's configure switch
+    "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
 
 
@@ -60,12 +62,13 @@ def run_host(binary, blocks, prob, mhd, extra=()):
 
 
 def compare_with_reference(binary, case):
-    cfg, prob, mhd, mk = CASES[case]
+    cfg, prob, mhd, mk = CASES[case][:4]
+    extra = CASES[case][4] if len(CASES[case]) > 4 else []
     if not refrun.have_ref(cfg):
         pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
     blocks = mk()
     wd_ref, _ = refrun.run_reference(cfg, blocks)
-    wd, r = run_host(binary, blocks, prob, mhd)
+    wd, r = run_host(binary, blocks, prob, mhd, extra=extra)
     try:
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         ref_files = sorted(os.path.basename(f) for f in glob.glob(wd_ref + "/*.rst"))

@@ -63,9 +63,13 @@ def gather_from_ctx(ctx, reg="U"):
     return U, B
 
 
-def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, B=(None, None, None)):
+RSOLVERS = {"hllc": 0, "hlld": 1, "roe": 2, "hlle": 3, "llf": 4}   # enum athk_rsolver
+
+
+def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, B=(None, None, None),
+                         flux=None):
     mesh = pyhost.UniformMesh(mesh_nx, block_nx, xmin, xmax, ng=ng)
-    ctx = pyhost.Context(mesh, mhd, gamma, lib=lib)
+    ctx = pyhost.Context(mesh, mhd, gamma, rsolver=RSOLVERS[flux] if flux else None, lib=lib)
     blocks = split_to_blocks(mesh, U, *B)
     for lb, blk in enumerate(blocks):
         ctx.upload("U", lb, blk["u"])
@@ -83,7 +87,7 @@ def run_golden_case(lib, name, block=None, fused=False):
     mhd = meta["mhd"]
     B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
     ctx = make_ctx_from_global(lib, meta["mesh"], block or meta["block"], meta["xmin"], meta["xmax"],
-                               meta["ng"], mhd, meta["gamma"], z["u0"], B)
+                               meta["ng"], mhd, meta["gamma"], z["u0"], B, flux=meta.get("flux"))
     ti = pyhost.TimeIntegrator(ctx, meta["integrator"], meta["xorder"], meta["cfl"], fused=fused)
     ti.initialize(tlim=meta["tlim"])
     ti.run(meta["tlim"])
