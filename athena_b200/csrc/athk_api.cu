@@ -420,6 +420,8 @@ extern "C" int athk_request_block_dt(athk_ctx *c) {
 extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   NEED_READY(c);
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "cons2prim: register %d not allocated", reg);
+  const int ns = c->cfg.nscalars;
+  if (ns && !c->s[reg]) return fail(ATHK_ERR_ARG, "cons2prim: scalar register %d not allocated", reg);
   const Grid &g = c->g;
   Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
   Real *dt_out = nullptr;
@@ -430,10 +432,12 @@ extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
     dt_out = c->dt_blocks;
   }
   if (c->cfg.mhd) {
-    Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr, dt_out, c->geo};
+    Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr, dt_out, c->geo,
+                              ns ? c->s[reg] : nullptr, c->r, ns};
     LAUNCH(c, r, f);
   } else {
-    Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo};
+    Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo,
+                               ns ? c->s[reg] : nullptr, c->r, ns};
     LAUNCH(c, r, f);
   }
   if (c->dt_requested) { c->dt_valid = true; c->dt_requested = false; }
@@ -723,10 +727,157 @@ extern "C" int athk_new_block_dt(athk_ctx *c, double cfl_number, double *dt_bloc
 }
 
 //----------------------------------------------------------------------------------------
-// not yet implemented entry points (declared in athk.h; exported so the ABI is complete)
-extern "C" int athk_calculate_scalar_fluxes(athk_ctx *, int) { return fail(ATHK_ERR_ARG, "calculate_scalar_fluxes: not implemented yet"); }
-extern "C" int athk_add_scalar_flux_divergence(athk_ctx *, double, int) { return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: not implemented yet"); }
-extern "C" int athk_history(athk_ctx *, double *, int) { return fail(ATHK_ERR_ARG, "history: not implemented yet"); }
+// Passive scalars (athk_scalars.h)
+template <int ORDER>
+static int launch_scalar_fluxes(athk_ctx *c) {
+  const Grid &g = c->g;
+  const int ns = c->cfg.nscalars;
+  const MassFlux mf = {{c->flux[0], c->flux[1], c->flux[2]}, (idx_t)5 * g.sn};   // Hydro::flux[d](IDN)
+  {
+    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
+    ScalarFacePoint<0, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[0]};
+    LAUNCH_NAMED(c, "calculate_scalar_fluxes_x1", launch_points(c->stream, g.nb, r, f));
+  }
+  {
+    Range3 r = {g.ks, g.ke, g.js, g.je + 1, g.is, g.ie};
+    ScalarFacePoint<1, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[1]};
+    LAUNCH_NAMED(c, "calculate_scalar_fluxes_x2", launch_points(c->stream, g.nb, r, f));
+  }
+  {
+    Range3 r = {g.ks, g.ke + 1, g.js, g.je, g.is, g.ie};
+    ScalarFacePoint<2, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[2]};
+    LAUNCH_NAMED(c, "calculate_scalar_fluxes_x3", launch_points(c->stream, g.nb, r, f));
+  }
+  return ATHK_OK;
+}
+
+extern "C" int athk_calculate_scalar_fluxes(athk_ctx *c, int order) {
+  NEED_READY(c);
+  if (!c->cfg.nscalars) return fail(ATHK_ERR_ARG, "calculate_scalar_fluxes: context has no passive scalars");
+  int rc = check_order(c, order, "calculate_scalar_fluxes");
+  if (rc) return rc;
+  if (order == 1) return launch_scalar_fluxes<1>(c);
+  if (order == 2) return launch_scalar_fluxes<2>(c);
+  return launch_scalar_fluxes<3>(c);
+}
+
+extern "C" int athk_add_scalar_flux_divergence(athk_ctx *c, double wght, int reg) {
+  NEED_READY(c);
+  if (!c->cfg.nscalars) return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: context has no passive scalars");
+  if (bad_reg(reg) || !c->s[reg]) return fail(ATHK_ERR_ARG, "add_scalar_flux_divergence: register %d not allocated", reg);
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
+  FluxDivPoint f = {g, c->geo, c->cfg.nscalars, wght, c->sflux[0], c->sflux[1], c->sflux[2], c->s[reg]};
+  LAUNCH(c, r, f);
+  return ATHK_OK;
+}
+
+template <int ORDER>
+static int launch_scalar_integrate(athk_ctx *c, const HydroIntegrate &hi) {
+  const Grid &g = c->g;
+  const int ns = c->cfg.nscalars;
+  const MassFlux mf = {{c->sflux[0], c->sflux[1], c->sflux[2]}, (idx_t)ns * g.sn};   // left by the sweeps
+  Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
+  ScalarIntegratePoint<ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, hi};
+  LAUNCH_NAMED(c, "scalar_fluxes_integrate", launch_points(c->stream, g.nb, r, f));
+  return ATHK_OK;
+}
+// History sums (outputs/history.cpp:196-248).  The reference adds cells serially; here every
+// MeshBlock is reduced by one CTA in a fixed order (deterministic, not the serial order: the sums
+// agree with the reference to rounding, ~1e-15 relative; the north-star bar is 1e-10), and the
+// host adds the per-block partial sums block by block.
+struct HistoryCell {
+  Grid g;
+  Geom geo;
+  const Real *u, *bcc, *s;
+  int mhd, ns;
+  ATHK_HD int nvals() const { return 8 + (mhd ? 3 : 0) + ns; }
+  ATHK_HD void operator()(int blk, int k, int j, int i, Real *acc) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real vol = geo.dxf[0][blk * geo.PG + i] * geo.dxf[1][blk * geo.PG + j] * geo.dxf[2][blk * geo.PG + k];
+    const Real *ub = u + (idx_t)blk * 5 * g.sn + c;
+    const Real u_d = ub[0], u_mx = ub[g.sn], u_my = ub[2 * g.sn], u_mz = ub[3 * g.sn];
+    acc[0] += vol * u_d;
+    acc[1] += vol * u_mx;
+    acc[2] += vol * u_my;
+    acc[3] += vol * u_mz;
+    acc[4] += vol * 0.5 * sqr(u_mx) / u_d;
+    acc[5] += vol * 0.5 * sqr(u_my) / u_d;
+    acc[6] += vol * 0.5 * sqr(u_mz) / u_d;
+    acc[7] += vol * ub[4 * g.sn];
+    int n0 = 8;
+    if (mhd) {
+      const Real *bc = bcc + (idx_t)blk * 3 * g.sn + c;
+      acc[8] += vol * 0.5 * bc[0] * bc[0];
+      acc[9] += vol * 0.5 * bc[g.sn] * bc[g.sn];
+      acc[10] += vol * 0.5 * bc[2 * g.sn] * bc[2 * g.sn];
+      n0 = 11;
+    }
+    for (int n = 0; n < ns; ++n) acc[n0 + n] += vol * s[((idx_t)blk * ns + n) * g.sn + c];
+  }
+};
+#define ATHK_HIST_MAX 19   // 8 + 3 + nscalars(<=8)
+
+#ifndef ATHK_EMULATE
+__global__ void __launch_bounds__(256) k_history(const HistoryCell f, Real *out) {
+  const Grid &g = f.g;
+  const int blk = blockIdx.x;
+  const int nv = f.nvals();
+  const int ncell = g.nx1 * g.nx2 * g.nx3;
+  Real acc[ATHK_HIST_MAX];
+#pragma unroll
+  for (int v = 0; v < ATHK_HIST_MAX; ++v) acc[v] = 0.0;
+  for (int q = threadIdx.x; q < ncell; q += blockDim.x) {
+    const int i = q % g.nx1;
+    const int t = q / g.nx1;
+    f(blk, g.ks + t / g.nx2, g.js + t % g.nx2, g.is + i, acc);
+  }
+  __shared__ Real sm[8][ATHK_HIST_MAX];
+#pragma unroll
+  for (int v = 0; v < ATHK_HIST_MAX; ++v) {
+    Real m = acc[v];
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][v] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    Real m = 0.0;
+    for (int w = 0; w < 8; ++w) m += sm[w][threadIdx.x];
+    out[blk * ATHK_HIST_MAX + threadIdx.x] = m;
+  }
+}
+#endif
+
+extern "C" int athk_history(athk_ctx *c, double *sums, int nsums) {
+  NEED_READY(c);
+  const Grid &g = c->g;
+  HistoryCell f = {g, c->geo, c->u[0], c->bcc, c->s[0], c->cfg.mhd, c->cfg.nscalars};
+  const int nv = f.nvals();
+  if (!sums || nsums < nv) return fail(ATHK_ERR_ARG, "history: need room for %d sums (got %d)", nv, nsums);
+  std::vector<Real> h((size_t)g.nb * ATHK_HIST_MAX, 0.0);
+#ifndef ATHK_EMULATE
+  Real *d = nullptr;
+  CU(cudaMalloc((void **)&d, h.size() * sizeof(Real)));
+  prof_begin(c, "history");
+  k_history<<<g.nb, 256, 0, c->stream>>>(f, d);
+  prof_end(c);
+  c->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), d, h.size() * sizeof(Real), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ATHK_ERR_CUDA, "history: %s", cudaGetErrorString(e));
+#else
+  for (int b = 0; b < g.nb; ++b)
+    for (int k = g.ks; k <= g.ke; ++k)
+      for (int j = g.js; j <= g.je; ++j)
+        for (int i = g.is; i <= g.ie; ++i) f(b, k, j, i, &h[(size_t)b * ATHK_HIST_MAX]);
+#endif
+  for (int v = 0; v < nv; ++v) sums[v] = 0.0;
+  for (int b = 0; b < g.nb; ++b)
+    for (int v = 0; v < nv; ++v) sums[v] += h[(size_t)b * ATHK_HIST_MAX + v];
+  return ATHK_OK;
+}
 //----------------------------------------------------------------------------------------
 // Fused stage: same task sequence, fewer passes over HBM (see athk_sweep.h, athk_sweep_launch_impl.h).
 extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wghts *sw,
@@ -744,7 +895,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
   if (!sw) return fail(ATHK_ERR_ARG, "stage: null weights");
   if (sw->gamma_3 != 0.0) return fail(ATHK_ERR_ARG, "stage: gamma_3 != 0 (3-register integrators) not implemented");
   { int rco = check_order(c, order, "stage"); if (rco) return rco; }
-  if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "stage: passive scalars not implemented in the fused path");
+  const int ns = c->cfg.nscalars;
   const Grid &g = c->g;
   const bool mhd = c->cfg.mhd != 0;
   const int swap = (sw->gamma_1 == 0.0 && sw->gamma_2 == 1.0 && sw->gamma_3 == 0.0) ? 1 : 0;
@@ -763,6 +914,10 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     h.delta = sw->delta; h.g1 = sw->gamma_1; h.g2 = sw->gamma_2;
     h.wght = sw->beta * dt_mesh;
     h.swap = swap; h.u1_zero = (stage == 1) ? 1 : 0; h.wa_mode = wa;
+    if (ns) {   // the sweeps leave each face's mass flux in component 0 of s_flux[d]
+      for (int d = 0; d < 3; ++d) a.mf[d] = c->sflux[d];
+      a.mf_bstride = (idx_t)ns * g.sn;
+    }
     switch (c->cfg.rsolver) {
       case ATHK_RS_ROE: rc = mhd ? athk_sweeps_rs<RS_ROE, true>(c, order, a) : athk_sweeps_rs<RS_ROE, false>(c, order, a); break;
       case ATHK_RS_HLLE: rc = mhd ? athk_sweeps_rs<RS_HLLE, true>(c, order, a) : athk_sweeps_rs<RS_HLLE, false>(c, order, a); break;
@@ -771,6 +926,16 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     }
     if (rc) return rc;
     if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
+    if (ns) {   // IntegrateScalars with the same weights (time_integrator.cpp:2376-2403)
+      HydroIntegrate hs = h;
+      hs.u = c->s[0]; hs.u1 = c->s[1];
+      hs.u_out = swap ? c->s[1] : c->s[0];
+      hs.u1_out = c->s[1];
+      rc = (order == 1) ? launch_scalar_integrate<1>(c, hs)
+                        : (order == 2 ? launch_scalar_integrate<2>(c, hs) : launch_scalar_integrate<3>(c, hs));
+      if (rc) return rc;
+      if (swap) { Real *t = c->s[0]; c->s[0] = c->s[1]; c->s[1] = t; }
+    }
     if (mhd) {
       if ((rc = athk_compute_corner_e(c))) return rc;
       if ((rc = athk_send_flux_correction(c))) return rc;
@@ -795,7 +960,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     }
     return athk_remote_pack_ghosts(c, 0);
   }
-  if ((rc = athk_exchange_ghosts(c, mhd ? 3 : 1, 0))) return rc;
+  if ((rc = athk_exchange_ghosts(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0))) return rc;
   return athk_cons2prim(c, 0);
 }
 //----------------------------------------------------------------------------------------

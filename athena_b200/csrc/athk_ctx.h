@@ -16,6 +16,7 @@
 #include "athk_backend.h"
 #include "athk_ops.h"
 #include "athk_sweep.h"
+#include "athk_scalars.h"
 #ifndef ATHK_EMULATE
 #include "athk_sweep_kernels.cuh"
 #endif

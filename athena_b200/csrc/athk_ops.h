@@ -55,6 +55,11 @@ struct Cons2PrimPoint {
   // W(U): active cells also fold min(dx/(|v|+c)) into dt_out[blk] (null = off)
   Real *dt_out;
   Geom geo;
+  // passive scalars (ns > 0): EquationOfState::PassiveScalarConservedToPrimitive
+  // (eos/eos_scalars.cpp:31-60) over the same range, after the density floor
+  Real *s;          // [nb][ns][sn]  in/out (floored to sfloor*rho)
+  Real *r;          // [nb][ns][sn]
+  int ns;
   ATHK_HD void fold_dt(int blk, Real dtc) const {
 #if defined(__CUDA_ARCH__)
     // positive doubles order like their bit patterns; the racy pre-read only filters
@@ -98,6 +103,13 @@ struct Cons2PrimPoint {
     if (uc[IEN] != e0) ub[IEN * g.sn] = uc[IEN];
 #pragma unroll
     for (int n = 0; n < 5; ++n) wb[n * g.sn] = wc[n];
+    for (int n = 0; n < ns; ++n) {
+      const idx_t o = ((idx_t)blk * ns + n) * g.sn + c;
+      const Real s0 = s[o];
+      const Real sn = (s0 < eos.sfloor * uc[IDN]) ? eos.sfloor * uc[IDN] : s0;
+      if (sn != s0) s[o] = sn;
+      r[o] = sn / uc[IDN];
+    }
     if (dt_out != nullptr && i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks &&
         k <= g.ke) {
       Real dt1 = geo.dxf[0][blk * geo.PG + i], dt2 = geo.dxf[1][blk * geo.PG + j],

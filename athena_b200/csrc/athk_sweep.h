@@ -43,6 +43,8 @@ struct SweepArgs {
   Real *wct;                 // [nb][3][sn]
   Real *d2, *d3;             // [nb][5][sn] scratch: x2 / x3 terms of the flux divergence
   Real dt;                   // pmy_mesh->dt
+  Real *mf[3];               // passive scalars only: where to leave the mass flux of each face
+  idx_t mf_bstride;          //   (block stride; null = no scalars)  see athk_scalars.h
   HydroIntegrate hi;
 };
 
@@ -81,6 +83,7 @@ ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const R
   } else {
     hydro_riemann<RS>(a.eos, wl, wr, f);
   }
+  if (store && a.mf[DIR]) a.mf[DIR][(idx_t)blk * a.mf_bstride + c] = f[IDN];
   if (store && a.flx[DIR]) {
     Real *fb = a.flx[DIR] + (idx_t)blk * 5 * g.sn + c;
     fb[0] = f[IDN];
@@ -110,34 +113,36 @@ ATHK_HD void recon_cell(const Real qm[7], const Real q0[7], const Real qp[7], Re
   }
 }
 
-// finish the hydro update of one interior cell (all 5 variables): dflx already holds the
-// x1+x2 contributions, d3[] is this sweep's; then WeightedAve + flux divergence.
+// WeightedAve + AddFluxDivergence of ONE variable of one active cell (time_integrator.cpp:
+// 1806-1821 + add_flux_divergence.cpp:86-90; the scalar twin :2386-2403): o = its offset in the
+// registers, dsum = its summed flux divergence.
+ATHK_HD void integrate_var(const HydroIntegrate &h, idx_t o, Real dsum, Real vol) {
+  // load only what the stage's weights use (vl2 stage 2 never reads u, stage 1 never reads u1)
+  const Real un = (h.delta != 0.0 || !h.swap) ? h.u[o] : 0.0;
+  Real u1n = h.u1_zero ? 0.0 : h.u1[o];
+  if (h.delta != 0.0) u1n += h.delta * un;          // WeightedAve(u1,u,..,{1,delta,0,0,0})
+  Real r;
+  if (h.swap) {
+    r = u1n;                                        // u <-> u1
+  } else {
+    switch (h.wa_mode) {                            // WeightedAve(u,u1,..,{g1,g2,0,0,0})
+      case 1: r = un; r += h.g2 * u1n; break;
+      case 3: r = h.g2 * u1n; break;
+      case 5: r = h.g1 * un + h.g2 * u1n; break;
+      case 6: r = un; r *= h.g1; break;
+      default: r = un; break;
+    }
+    if (h.delta != 0.0) h.u1_out[o] = u1n;
+  }
+  r -= h.wght * dsum / vol;                         // AddFluxDivergence
+  h.u_out[o] = r;
+}
+
+// finish the hydro update of one interior cell (all 5 variables)
 ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsum[5], Real vol) {
   const Grid &g = a.g;
-  const HydroIntegrate &h = a.hi;
 #pragma unroll
-  for (int n = 0; n < 5; ++n) {
-    const idx_t o = ((idx_t)blk * 5 + n) * g.sn + c;
-    // load only what the stage's weights use (vl2 stage 2 never reads u, stage 1 never reads u1)
-    const Real un = (h.delta != 0.0 || !h.swap) ? h.u[o] : 0.0;
-    Real u1n = h.u1_zero ? 0.0 : h.u1[o];
-    if (h.delta != 0.0) u1n += h.delta * un;          // WeightedAve(u1,u,..,{1,delta,0,0,0})
-    Real r;
-    if (h.swap) {
-      r = u1n;                                        // u <-> u1
-    } else {
-      switch (h.wa_mode) {                            // WeightedAve(u,u1,..,{g1,g2,0,0,0})
-        case 1: r = un; r += h.g2 * u1n; break;
-        case 3: r = h.g2 * u1n; break;
-        case 5: r = h.g1 * un + h.g2 * u1n; break;
-        case 6: r = un; r *= h.g1; break;
-        default: r = un; break;
-      }
-      if (h.delta != 0.0) h.u1_out[o] = u1n;
-    }
-    r -= h.wght * dsum[n] / vol;                      // AddFluxDivergence
-    h.u_out[o] = r;
-  }
+  for (int n = 0; n < 5; ++n) integrate_var(a.hi, ((idx_t)blk * 5 + n) * g.sn + c, dsum[n], vol);
 }
 
 //========================================================================================

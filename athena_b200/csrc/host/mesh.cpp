@@ -285,9 +285,11 @@ void Mesh::Initialize(ParameterInput *pin) {
       AthkCheck(athk_upload(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::Initialize");
       AthkCheck(athk_upload(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::Initialize");
     }
+    if (NSCALARS > 0) AthkCheck(athk_upload(athk, ATHK_S, b, pmb->pscalars->s.data()), "Mesh::Initialize");
   }
   AthkCheck(athk_sync(athk), "Mesh::Initialize");
-  AthkCheck(athk_exchange_ghosts(athk, 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0), 0), "Mesh::Initialize");
+  AthkCheck(athk_exchange_ghosts(athk, 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0),
+            "Mesh::Initialize");
   AthkCheck(athk_cons2prim(athk, 0), "Mesh::Initialize");
   NewTimeStep();
 }
@@ -312,6 +314,10 @@ void Mesh::DownloadAll() {
       AthkCheck(athk_download(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::DownloadAll");
       AthkCheck(athk_download(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::DownloadAll");
       AthkCheck(athk_download(athk, ATHK_BCC, b, pmb->pfield->bcc.data()), "Mesh::DownloadAll");
+    }
+    if (NSCALARS > 0) {
+      AthkCheck(athk_download(athk, ATHK_S, b, pmb->pscalars->s.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_R, b, pmb->pscalars->r.data()), "Mesh::DownloadAll");
     }
   }
 }

@@ -119,21 +119,84 @@ static void OrszagTangGenerator(MeshBlock *pmb, ParameterInput *) {
 }
 
 //========================================================================================
-// kh, iprob = 2 (tanh shear layer, deterministic)
+// kh: iprob = 2 (tanh shear layer, single mode; kh.cpp:159-215) and iprob = 4 (the "Lecoanet"
+// test: two resolved shear layers, fully periodic, passive-scalar dye + its entropy as a user
+// history column; kh.cpp:285-422, PassiveDyeEntropy :516-536)
+static Real PassiveDyeEntropy(MeshBlock *pmb, int iout) {
+  Real total_entropy = 0;
+  AthenaArray<Real> &r = pmb->pscalars->r;
+  AthenaArray<Real> &w = pmb->phydro->w;
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) {
+        Real specific_entropy = -r(0, k, j, i) * std::log(r(0, k, j, i));
+        total_entropy += pmb->pcoord->GetCellVolume(k, j, i) * w(IDN, k, j, i) * specific_entropy;
+      }
+  return total_entropy;
+}
+
+static void KHInitUserMeshData(Mesh *pm, ParameterInput *pin) {
+  if (pin->GetInteger("problem", "iprob") == 4 && NSCALARS > 0)
+    pm->EnrollUserHistoryOutput(PassiveDyeEntropy, "tot-S", 0);   // kh.cpp:59-62
+}
+
 static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
   const int iprob = pin->GetInteger("problem", "iprob");
-  if (iprob != 2) {
+  if (iprob != 2 && iprob != 4) {
     std::stringstream msg;
     msg << "### FATAL ERROR in kh ProblemGenerator" << std::endl
-        << "iprob=" << iprob << " is not built into the B200 host (iprob=2 is)";
+        << "iprob=" << iprob << " is not built into the B200 host (iprob=2 and 4 are)";
     ATHENA_ERROR(msg);
   }
   const Real vflow = pin->GetReal("problem", "vflow");
   const Real amp = pin->GetReal("problem", "amp");
   const Real gm1 = pmb->peos->GetGamma() - 1.0;
-  const Real a = 0.02, sigma = 0.2;
   Coordinates *pc = pmb->pcoord;
   AthenaArray<Real> &u = pmb->phydro->u;
+  if (iprob == 4) {
+    const Real drho_rho0 = pin->GetOrAddReal("problem", "drho_rho0", 0.0);
+    const Real vboost = pin->GetOrAddReal("problem", "vboost", 0.0);
+    const Real P0 = 10.0, a = 0.05, sigma = 0.2, z1 = -0.5, z2 = 0.5;
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie; i++) {
+          Real dens = 1.0 + 0.5 * drho_rho0 * (std::tanh((pc->x2v(j) - z1) / a) - std::tanh((pc->x2v(j) - z2) / a));
+          u(IDN, k, j, i) = dens;
+          Real v1 = vflow * (std::tanh((pc->x2v(j) - z1) / a) - std::tanh((pc->x2v(j) - z2) / a) - 1.0) + vboost;
+          u(IM1, k, j, i) = v1 * dens;
+          // sine averaged with its half-period-shifted twin (shift symmetry in floating point)
+          Real ave_sine = std::sin(TWO_PI * pc->x1v(i));
+          if (pc->x1v(i) > 0.0) ave_sine -= std::sin(TWO_PI * (-0.5 + pc->x1v(i)));
+          else ave_sine -= std::sin(TWO_PI * (0.5 + pc->x1v(i)));
+          ave_sine /= 2.0;
+          Real v2 = -amp * ave_sine *
+                    (std::exp(-(SQR(pc->x2v(j) - z1)) / (sigma * sigma)) +
+                     std::exp(-(SQR(pc->x2v(j) - z2)) / (sigma * sigma)));
+          u(IM2, k, j, i) = v2 * dens;
+          u(IM3, k, j, i) = 0.0;
+          u(IEN, k, j, i) = P0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i))) /
+                                           u(IDN, k, j, i);
+          if (NSCALARS > 0) {
+            Real concentration = 0.5 * (std::tanh((pc->x2v(j) - z2) / a) - std::tanh((pc->x2v(j) - z1) / a) + 2.0);
+            const int scalar_norm = NSCALARS;
+            for (int n = 0; n < NSCALARS; ++n)
+              pmb->pscalars->s(n, k, j, i) = 1.0 / scalar_norm * concentration * u(IDN, k, j, i);
+          }
+        }
+    if (MAGNETIC_FIELDS_ENABLED) {
+      Real b0 = pin->GetReal("problem", "b0");
+      b0 = b0 / std::sqrt(4.0 * (PI));
+      FaceField &b = pmb->pfield->b;
+      for (int k = pmb->ks; k <= pmb->ke; k++)
+        for (int j = pmb->js; j <= pmb->je; j++)
+          for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0 * std::tanh((std::abs(pc->x2v(j)) - 0.5) / a);
+      for (int k = pmb->ks; k <= pmb->ke; k++)
+        for (int j = pmb->js; j <= pmb->je; j++)
+          for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * SQR(b.x1f(k, j, i));
+    }
+    return;
+  }
+  const Real a = 0.02, sigma = 0.2;
   for (int k = pmb->ks; k <= pmb->ke; k++)
     for (int j = pmb->js; j <= pmb->je; j++)
       for (int i = pmb->is; i <= pmb->ie; i++) {
@@ -429,7 +492,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
     {"blast", nullptr, BlastGenerator, nullptr},
     {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
-    {"kh", nullptr, KHGenerator, nullptr},
+    {"kh", KHInitUserMeshData, KHGenerator, nullptr},
 };
 
 const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {

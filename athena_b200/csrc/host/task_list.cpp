@@ -82,8 +82,10 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   if (stage == 1) {   // StartupTaskList (:1608-1619)
     AthkCheck(athk_zero_register(a, 0, 1), who);
     if (mhd) AthkCheck(athk_zero_register(a, 1, 1), who);
+    if (NSCALARS > 0) AthkCheck(athk_zero_register(a, 2, 1), who);   // ps->s1.ZeroClear() :1628-1630
   }
   AthkCheck(athk_calculate_fluxes(a, order, dt, 0), who);                 // CALC_HYDFLX
+  if (NSCALARS > 0) AthkCheck(athk_calculate_scalar_fluxes(a, order), who);   // CALC_SCLRFLX :2329-2340
   if (mhd) {
     AthkCheck(athk_compute_corner_e(a), who);                            // CALC_FLDFLX
     AthkCheck(athk_send_flux_correction(a), who);                        // SEND_FLDFLX
@@ -97,12 +99,18 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   if (swap) AthkCheck(athk_swap_registers(a, 0, 0, 1), who);
   else AthkCheck(athk_weighted_ave_cc(a, 0, 0, 1, 2, w2), who);
   AthkCheck(athk_add_flux_divergence(a, sw.beta * dt, 0), who);
+  if (NSCALARS > 0) {                                                   // INT_SCLR :2376-2403
+    AthkCheck(athk_weighted_ave_cc(a, 1, 1, 0, 2, w1), who);
+    if (swap) AthkCheck(athk_swap_registers(a, 2, 0, 1), who);
+    else AthkCheck(athk_weighted_ave_cc(a, 1, 0, 1, 2, w2), who);
+    AthkCheck(athk_add_scalar_flux_divergence(a, sw.beta * dt, 0), who);
+  }
   if (mhd) {   // IntegrateField (:1853-1885)
     AthkCheck(athk_weighted_ave_fc(a, 1, 0, 2, w1), who);
     if (swap) AthkCheck(athk_swap_registers(a, 1, 0, 1), who);
     else AthkCheck(athk_weighted_ave_fc(a, 0, 1, 2, w2), who);
     AthkCheck(athk_ct(a, sw.beta * dt, 0), who);
   }
-  AthkCheck(athk_exchange_ghosts(a, 1 | (mhd ? 2 : 0), 0), who);   // SEND/RECV/SETB_HYD,_FLD
+  AthkCheck(athk_exchange_ghosts(a, 1 | (mhd ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0), who);   // SEND/RECV/SETB_HYD,_FLD,_SCLR
   AthkCheck(athk_cons2prim(a, 0), who);                            // CONS2PRIM
 }

@@ -284,9 +284,13 @@ class TimeIntegrator:
             c.call("athk_zero_register", 0, 1)
             if mhd:
                 c.call("athk_zero_register", 1, 1)
+            if c.nscalars:
+                c.call("athk_zero_register", 2, 1)   # ps->s1.ZeroClear(), time_integrator.cpp:1628-1630
         # CALC_HYDFLX: donor cell on the VL2 predictor (time_integrator.cpp:1700-1701)
         order = 1 if (self.integrator == "vl2" and stage == 1) else self.xorder
         c.call("athk_calculate_fluxes", order, dt, 0)
+        if c.nscalars:
+            c.call("athk_calculate_scalar_fluxes", order)   # CALC_SCLRFLX (:2329-2340)
         if mhd:
             c.call("athk_compute_corner_e")          # CALC_FLDFLX
             c.call("athk_send_flux_correction")      # SEND_FLDFLX
@@ -304,6 +308,13 @@ class TimeIntegrator:
         else:
             c.call("athk_weighted_ave_cc", 0, 0, 1, 2, w2)
         c.call("athk_add_flux_divergence", beta * dt, 0)
+        if c.nscalars:   # INT_SCLR (time_integrator.cpp:2376-2403)
+            c.call("athk_weighted_ave_cc", 1, 1, 0, 2, w1)
+            if swap:
+                c.call("athk_swap_registers", 2, 0, 1)
+            else:
+                c.call("athk_weighted_ave_cc", 1, 0, 1, 2, w2)
+            c.call("athk_add_scalar_flux_divergence", beta * dt, 0)
         if mhd:   # INT_FLD (time_integrator.cpp:1853-1885)
             c.call("athk_weighted_ave_fc", 1, 0, 2, w1)
             if swap:
@@ -315,7 +326,7 @@ class TimeIntegrator:
         if xch is not None:
             c.call("athk_remote_pack_ghosts", 0)
             xch.exchange_ghosts()
-        c.call("athk_exchange_ghosts", 1 | (2 if mhd else 0), 0)
+        c.call("athk_exchange_ghosts", 1 | (2 if mhd else 0) | (4 if c.nscalars else 0), 0)
         c.call("athk_cons2prim", 0)
 
     def step(self, tlim=None, reduce_min=None):

@@ -38,6 +38,8 @@ CONFIGS = {
     "blast_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc"),
     "ot_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld"),
     "kh_hydro_hllc_s1g3": dict(PROB="kh", MHD=0, FLUX="hllc", NGHOST=3, NSCALARS=1),
+    "kh_hydro_hllc_s2": dict(PROB="kh", MHD=0, FLUX="hllc", NSCALARS=2),
+    "kh_mhd_hlld_s1": dict(PROB="kh", MHD=1, FLUX="hlld", NSCALARS=1),
     "linwave_hydro_hllc_g3": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=3),
     "linwave_mhd_hlld_g3": dict(PROB="linear_wave", MHD=1, FLUX="hlld", NGHOST=3),
 }
@@ -244,6 +246,33 @@ def read_hst(path):
             if line.strip():
                 rows.append([float(x) for x in line.split()])
     return names, np.array(rows)
+
+
+def kh_blocks(mesh=(32, 32, 8), block=None, tlim=0.05, integrator="rk3", xorder=3, cfl=0.3,
+              rst_dt=None, amp=0.01, vflow=1.0, drho_rho0=0.0, iprob=4, b0=None):
+    """athinput for pgen/kh.cpp iprob=4 (Lecoanet et al. 2016: periodic double shear layer with a
+    passive-scalar dye), extruded to 3-D; inputs/hydro/athinput.kh-shear-lecoanet without the
+    diffusion terms."""
+    block = block or mesh
+    extra = {} if b0 is None else {"b0": b0}
+    return {
+        "job": {"problem_id": "kh"},
+        "output1": {"file_type": "hst", "dt": 1.0e-9 if rst_dt is None else rst_dt,
+                    "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 1.0e30 if rst_dt is None else rst_dt},
+        "time": {"cfl_number": cfl, "nlim": -1, "tlim": tlim, "integrator": integrator,
+                 "xorder": xorder, "ncycle_out": 1},
+        "mesh": {"nx1": mesh[0], "x1min": -0.5, "x1max": 0.5, "ix1_bc": "periodic",
+                 "ox1_bc": "periodic",
+                 "nx2": mesh[1], "x2min": -1.0, "x2max": 1.0, "ix2_bc": "periodic",
+                 "ox2_bc": "periodic",
+                 "nx3": mesh[2], "x3min": -0.25, "x3max": 0.25, "ix3_bc": "periodic",
+                 "ox3_bc": "periodic", "num_threads": 1, "refinement": "none"},
+        "meshblock": {"nx1": block[0], "nx2": block[1], "nx3": block[2]},
+        "hydro": {"gamma": 1.6666667, "iso_sound_speed": 1.0},
+        "problem": dict({"iprob": iprob, "amp": amp, "vflow": vflow, "vboost": 0.0,
+                         "drho_rho0": drho_rho0}, **extra),
+    }
 
 
 def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, **kw):

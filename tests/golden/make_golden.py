@@ -80,6 +80,16 @@ CASES = {
                                               left=(1.0, -2.0, 0.3, 0.0, 0.4, 1.0, 0.2),
                                               right=(0.5, 2.0, -0.3, 0.1, 0.3, -1.0, 0.0),
                                               shock_dir=2, bx=0.75)),
+    # SURVEY 8 row a10 / BASELINE configs[3] at parity size: KH (Lecoanet) + passive-scalar dye
+    "hydro_kh_rk3_ppm_hllc_scalar": dict(cfg="kh_hydro_hllc_s1g3", mhd=False, mesh=(32, 32, 8),
+                                         block=(16, 16, 8), tlim=0.03, integrator="rk3", xorder=3,
+                                         nscalars=1, kh=dict(drho_rho0=0.5)),
+    "hydro_kh_vl2_plm_hllc_2scalars": dict(cfg="kh_hydro_hllc_s2", mhd=False, mesh=(32, 32, 8),
+                                           block=(16, 16, 8), tlim=0.03, integrator="vl2", xorder=2,
+                                           nscalars=2, kh=dict()),
+    "mhd_kh_rk2_plm_hlld_scalar": dict(cfg="kh_mhd_hlld_s1", mhd=True, mesh=(32, 32, 8),
+                                       block=(16, 16, 8), tlim=0.03, integrator="rk2", xorder=2,
+                                       nscalars=1, kh=dict(b0=0.5)),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),
@@ -90,7 +100,14 @@ def make(name):
     c = CASES[name]
     if not refrun.build_ref(c["cfg"]):
         raise SystemExit("reference binary for %s unavailable" % c["cfg"])
-    if "shocktube" in c:
+    xmin, xmax, gamma = [0.0, 0.0, 0.0], [3.0, 1.5, 1.5], 1.666666666666667
+    if "kh" in c:
+        blocks = refrun.kh_blocks(mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                  integrator=c["integrator"], xorder=c["xorder"], **c["kh"])
+        m = blocks["mesh"]
+        xmin, xmax = [m["x1min"], m["x2min"], m["x3min"]], [m["x1max"], m["x2max"], m["x3max"]]
+        gamma = blocks["hydro"]["gamma"]
+    elif "shocktube" in c:
         blocks = refrun.shocktube_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
                                          integrator=c["integrator"], xorder=c["xorder"],
                                          **c["shocktube"])
@@ -105,7 +122,7 @@ def make(name):
     a0, af = refrun.assemble(r0), refrun.assemble(rf)
     names, hst = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
     meta = dict(c, name=name, ng=r0["ng"], ncycle=rf["ncycle"], time=rf["time"], dt_final=rf["dt"],
-                dt0=r0["dt"], xmin=[0.0, 0.0, 0.0], xmax=[3.0, 1.5, 1.5], gamma=1.666666666666667,
+                dt0=r0["dt"], xmin=xmin, xmax=xmax, gamma=gamma,
                 cfl=0.3, loc=[list(l) for l in r0["loc"]], hst_names=names,
                 reference="Athena++ v24.0, g++ -O3 -std=c++11 -fopenmp, oracle/Makefile.ref")
     arrs = dict(meta=np.array(json.dumps(meta)), hst=hst, u0=a0["u"], uf=af["u"])
@@ -113,6 +130,8 @@ def make(name):
         for k in ("b1", "b2", "b3"):
             arrs[k + "_0"] = a0[k]
             arrs[k + "_f"] = af[k]
+    if c.get("nscalars"):
+        arrs["s0"], arrs["sf"] = a0["s"], af["s"]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
     shutil.rmtree(wd, ignore_errors=True)
     print("wrote", name, "cycles", rf["ncycle"], "size",

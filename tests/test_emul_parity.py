@@ -13,7 +13,9 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          "hydro_linwave_vl2_plm_hlle", "hydro_linwave_vl2_plm_llf", "mhd_linwave_vl2_plm_roe",
          "mhd_linwave_rk3_plm_roe_slow", "mhd_linwave_vl2_plm_hlle", "mhd_linwave_vl2_plm_llf",
          # Roe with negative intermediate densities -> LLF fallback, and supersonic upwinding
-         "hydro_shocktube_vl2_plm_roe_llf", "mhd_shocktube_vl2_plm_roe_llf"]
+         "hydro_shocktube_vl2_plm_roe_llf", "mhd_shocktube_vl2_plm_roe_llf",
+         # passive scalars (KH, Lecoanet dye), incl. BASELINE configs[3]'s RK3+PPM
+         "hydro_kh_rk3_ppm_hllc_scalar", "hydro_kh_vl2_plm_hllc_2scalars", "mhd_kh_rk2_plm_hlld_scalar"]
 
 
 @pytest.mark.parametrize("name", CASES)

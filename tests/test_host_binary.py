@@ -46,6 +46,19 @@ CASES = {
                           lambda: dict(refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(16, 8, 8),
                                                              tlim=0.1, rst_dt=0.05, integrator="rk3"))),
     "mhd_blast": ("blast_mhd_hlld", "blast", True, blast_blocks),
+    # BASELINE configs[3] at parity size: KH + RK3 + PPM + HLLC + one passive scalar (row a10)
+    "kh_rk3_ppm_scalar": ("kh_hydro_hllc_s1g3", "kh", False,
+                          lambda: refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03,
+                                                   rst_dt=0.015, drho_rho0=0.5),
+                          ["--nghost=3", "--nscalars=1"]),
+    "kh_vl2_plm_2scalars": ("kh_hydro_hllc_s2", "kh", False,
+                            lambda: refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03,
+                                                     rst_dt=0.015, integrator="vl2", xorder=2),
+                            ["--nscalars=2"]),
+    "kh_mhd_rk2_scalar": ("kh_mhd_hlld_s1", "kh", True,
+                          lambda: refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03,
+                                                   rst_dt=0.015, integrator="rk2", xorder=2, b0=0.5),
+                          ["--nscalars=1"]),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
@@ -61,14 +74,16 @@ def run_host(binary, blocks, prob, mhd, extra=()):
     return wd, r
 
 
-def compare_with_reference(binary, case):
+def compare_with_reference(binary, case, host_time_params=None):
     cfg, prob, mhd, mk = CASES[case][:4]
     extra = CASES[case][4] if len(CASES[case]) > 4 else []
     if not refrun.have_ref(cfg):
         pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
     blocks = mk()
     wd_ref, _ = refrun.run_reference(cfg, blocks)
-    wd, r = run_host(binary, blocks, prob, mhd, extra=extra)
+    host_blocks = {k: dict(v) for k, v in blocks.items()}
+    host_blocks["time"].update(host_time_params or {})
+    wd, r = run_host(binary, host_blocks, prob, mhd, extra=extra)
     try:
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         ref_files = sorted(os.path.basename(f) for f in glob.glob(wd_ref + "/*.rst"))
@@ -77,7 +92,7 @@ def compare_with_reference(binary, case):
         for name in ref_files:
             a, c = refrun.read_rst(os.path.join(wd_ref, name)), refrun.read_rst(os.path.join(wd, name))
             assert (a["ncycle"], a["time"], a["dt"], a["loc"]) == (c["ncycle"], c["time"], c["dt"], c["loc"]), name
-            for k in ("u", "b1", "b2", "b3"):
+            for k in ("u", "b1", "b2", "b3", "s"):
                 assert len(a[k]) == len(c[k])
                 for x, y in zip(a[k], c[k]):
                     np.testing.assert_array_equal(x, y, err_msg="%s %s" % (name, k))
@@ -104,6 +119,12 @@ def emul_binary(emul_lib):
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case):
     compare_with_reference(emul_binary, case)
+
+
+@pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe"])
+def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
+    # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
+    compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
 
 
 @pytest.mark.gpu

@@ -44,7 +44,7 @@ def gather_from_ctx(ctx, reg="U"):
     ng = mesh.ng
     nx1, nx2, nx3 = mesh.block_nx
     M1, M2, M3 = mesh.mesh_nx
-    U = np.empty((5, M3, M2, M1))
+    U = np.empty((ctx.nscalars if reg == "S" else 5, M3, M2, M1))
     B = [None, None, None]
     if ctx.mhd:
         B = [np.empty((M3, M2, M1 + 1)), np.empty((M3, M2 + 1, M1)), np.empty((M3 + 1, M2, M1))]
@@ -53,7 +53,7 @@ def gather_from_ctx(ctx, reg="U"):
         o1, o2, o3 = l1 * nx1, l2 * nx2, l3 * nx3
         u = ctx.download(reg, lb)
         U[:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1] = u[:, ng:ng + nx3, ng:ng + nx2, ng:ng + nx1]
-        if ctx.mhd:
+        if ctx.mhd and reg != "S":
             b1 = ctx.download("B_X1F", lb)
             b2 = ctx.download("B_X2F", lb)
             b3 = ctx.download("B_X3F", lb)
@@ -67,9 +67,13 @@ RSOLVERS = {"hllc": 0, "hlld": 1, "roe": 2, "hlle": 3, "llf": 4}   # enum athk_r
 
 
 def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, B=(None, None, None),
-                         flux=None):
+                         flux=None, S=None):
     mesh = pyhost.UniformMesh(mesh_nx, block_nx, xmin, xmax, ng=ng)
-    ctx = pyhost.Context(mesh, mhd, gamma, rsolver=RSOLVERS[flux] if flux else None, lib=lib)
+    ctx = pyhost.Context(mesh, mhd, gamma, rsolver=RSOLVERS[flux] if flux else None, lib=lib,
+                         nscalars=0 if S is None else S.shape[0])
+    if S is not None:
+        for lb, blk in enumerate(split_to_blocks(mesh, S)):
+            ctx.upload("S", lb, blk["u"])
     blocks = split_to_blocks(mesh, U, *B)
     for lb, blk in enumerate(blocks):
         ctx.upload("U", lb, blk["u"])
@@ -87,7 +91,8 @@ def run_golden_case(lib, name, block=None, fused=False):
     mhd = meta["mhd"]
     B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
     ctx = make_ctx_from_global(lib, meta["mesh"], block or meta["block"], meta["xmin"], meta["xmax"],
-                               meta["ng"], mhd, meta["gamma"], z["u0"], B, flux=meta.get("flux"))
+                               meta["ng"], mhd, meta["gamma"], z["u0"], B, flux=meta.get("flux"),
+                               S=z["s0"] if meta.get("nscalars") else None)
     ti = pyhost.TimeIntegrator(ctx, meta["integrator"], meta["xorder"], meta["cfl"], fused=fused)
     ti.initialize(tlim=meta["tlim"])
     ti.run(meta["tlim"])
@@ -107,3 +112,17 @@ def assert_matches_golden(meta, z, ctx, ti):
         np.testing.assert_array_equal(B[0], z["b1_f"])
         np.testing.assert_array_equal(B[1], z["b2_f"])
         np.testing.assert_array_equal(B[2], z["b3_f"])
+    if meta.get("nscalars"):
+        np.testing.assert_array_equal(gather_from_ctx(ctx, "S")[0], z["sf"])
+    # conserved-quantity history (north star: 1e-10 relative): athk_history against the last row
+    # of the reference's .hst (columns: time, dt, then the sums of outputs/history.cpp:196-248)
+    import ctypes
+    nv = 8 + (3 if meta["mhd"] else 0) + (meta.get("nscalars") or 0)
+    sums = (ctypes.c_double * nv)()
+    ctx.call("athk_history", sums, nv)
+    ref = hst[-1, 2:2 + nv]
+    scale = np.abs(hst[:, 2:2 + nv]).max(axis=0) + 1e-300
+    # momenta cancel to ~0 in these periodic problems: scale them by the sum of |terms| instead
+    vol = np.prod((np.array(meta["xmax"]) - np.array(meta["xmin"])) / np.array(meta["mesh"]))
+    scale[1:4] = vol * np.abs(z["uf"][1:4]).sum(axis=(1, 2, 3)) + 1e-300
+    assert np.all(np.abs(np.array(sums[:]) - ref) <= 1e-10 * scale), (np.array(sums[:]), ref)
