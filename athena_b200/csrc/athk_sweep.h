@@ -68,10 +68,9 @@ ATHK_HD void load_q(const SweepArgs &a, int blk, idx_t c, Real q[7]) {
 // Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
 template <int DIR, bool MHD, int RS>
 ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
-                        const Real wr[7], Real f[7], bool store) {
+                        const Real wr[7], const Real bxi, Real f[7], bool store) {
   const Grid &g = a.g;
   if (MHD) {
-    const Real bxi = a.b[((idx_t)blk * 3 + DIR) * g.sn + c];
     mhd_riemann<RS>(a.eos, wl, wr, bxi, f);
     if (store) {
       Real *eb = a.ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
@@ -149,21 +148,33 @@ ATHK_HD void integrate_cell(const SweepArgs &a, int blk, idx_t c, const Real dsu
 // One face of a DIR-sweep, self-contained: reconstruct both adjacent cells (donor cell, PLM or
 // PPM), then Riemann solve.  c = index of the cell above the face, n_dir = its index along the
 // sweep.
-template <int DIR, int ORDER, bool MHD, int RS>
-ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
-  const Grid &g = a.g;
-  const idx_t s = (DIR == 0) ? 1 : (DIR == 1 ? g.sj : g.sk);
+// Where a face's stencil comes from.  cell(off, q): rotated primitives of the cell `off` cells
+// above the face's upper cell (off = -ORDER .. ORDER-1); bx(): the face-normal field.
+// GlobalStencil reads the arrays in HBM/L2; the tile kernels (athk_sweep_kernels.cuh) read rows
+// they staged into shared memory.
+template <int DIR, bool MHD>
+struct GlobalStencil {
+  const SweepArgs &a;
+  int blk;
+  idx_t c, s;
+  ATHK_HD void cell(int off, Real q[7]) const { load_q<DIR, MHD>(a, blk, c + off * s, q); }
+  ATHK_HD Real bx() const { return MHD ? a.b[((idx_t)blk * 3 + DIR) * a.g.sn + c] : 0.0; }
+};
+
+template <int DIR, int ORDER, bool MHD, int RS, class ST>
+ATHK_HD void face_compute_from(const SweepArgs &a, int blk, idx_t c, int n_dir, const ST &st, Real f[7],
+                               bool store) {
   const int NW = MHD ? 7 : 5;
   Real wl[7], wr[7];
   if (ORDER == 3) {
     // PPM: L state from cell n-1 (stencil n-3..n+1), R state from cell n (stencil n-2..n+2)
     Real qm3[7], qm2[7], qm1[7], q0[7], qp1[7], qp2[7];
-    load_q<DIR, MHD>(a, blk, c - 3 * s, qm3);
-    load_q<DIR, MHD>(a, blk, c - 2 * s, qm2);
-    load_q<DIR, MHD>(a, blk, c - s, qm1);
-    load_q<DIR, MHD>(a, blk, c, q0);
-    load_q<DIR, MHD>(a, blk, c + s, qp1);
-    load_q<DIR, MHD>(a, blk, c + 2 * s, qp2);
+    st.cell(-3, qm3);
+    st.cell(-2, qm2);
+    st.cell(-1, qm1);
+    st.cell(0, q0);
+    st.cell(1, qp1);
+    st.cell(2, qp2);
 #pragma unroll
     for (int v = 0; v < NW; ++v) {
       Real up, lo;
@@ -178,20 +189,28 @@ ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real 
     wr[IDN] = (wr[IDN] > a.eos.dfloor) ? wr[IDN] : a.eos.dfloor;
     wr[IPR] = (wr[IPR] > a.eos.pfloor) ? wr[IPR] : a.eos.pfloor;
   } else if (ORDER == 2) {
-    Real q0[7], q1[7], q2[7], q3[7], t0[7], t1[7];
-    load_q<DIR, MHD>(a, blk, c - s, q1);
-    load_q<DIR, MHD>(a, blk, c, q2);
-    load_q<DIR, MHD>(a, blk, c - 2 * s, q0);
-    load_q<DIR, MHD>(a, blk, c + s, q3);
+    Real q0[7], q1[7], q2[7], q3[7];
+    st.cell(-1, q1);
+    st.cell(0, q2);
+    st.cell(-2, q0);
+    st.cell(1, q3);
     const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
     const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
+    Real t0[7], t1[7];
     recon_cell<ORDER, MHD>(q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
     recon_cell<ORDER, MHD>(q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
   } else {
-    load_q<DIR, MHD>(a, blk, c - s, wl);
-    load_q<DIR, MHD>(a, blk, c, wr);
+    st.cell(-1, wl);
+    st.cell(0, wr);
   }
-  solve_face<DIR, MHD, RS>(a, blk, c, n_dir, wl, wr, f, store);
+  solve_face<DIR, MHD, RS>(a, blk, c, n_dir, wl, wr, st.bx(), f, store);
+}
+
+template <int DIR, int ORDER, bool MHD, int RS>
+ATHK_HD void face_compute(const SweepArgs &a, int blk, idx_t c, int n_dir, Real f[7], bool store) {
+  const Grid &g = a.g;
+  const GlobalStencil<DIR, MHD> st = {a, blk, c, (DIR == 0) ? (idx_t)1 : (DIR == 1 ? g.sj : g.sk)};
+  face_compute_from<DIR, ORDER, MHD, RS>(a, blk, c, n_dir, st, f, store);
 }
 
 // Hydro::CalculateFluxes as an operator: one thread per face, fluxes stored (a.flx[DIR] set)

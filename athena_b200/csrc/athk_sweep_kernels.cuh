@@ -11,6 +11,14 @@
 //   r == 0: triple-buffered, so one barrier per step suffices and no face is solved twice)
 //   into the sweep's scratch term d2 / d3.  The x1 sweep (warp shuffles, no barrier) runs last,
 //   sums d1 + d2 + d3 in the reference's order and applies the integrator update.
+//
+// Stencil staging (ATHK_TILE_STAGE=1, default): with ~5 warps per scheduler a face solve that
+// starts with 28 dependent global loads spends 40 % of its cycles on the long scoreboard (ncu
+// source page, profiles/).  Instead the CTA keeps a ring of cell ROWS in shared memory -- the
+// pencil the sweep marches along, with its ghost halo: every step each thread cp.async's the one
+// cell it will first need at the NEXT step (8 doubles: w[5], the two transverse bcc, the face
+// field), the copies land during the Riemann solves, and stencils are read from shared memory.
+// Each cell is fetched from L2/HBM once per CTA instead of 2*ORDER times.
 #ifndef ATHK_SWEEP_KERNELS_CUH_
 #define ATHK_SWEEP_KERNELS_CUH_
 
@@ -19,14 +27,146 @@
 namespace athk {
 
 #ifndef ATHK_TILE_R
-#define ATHK_TILE_R 5
+#define ATHK_TILE_R 4     // 128 threads x 4 CTAs/SM = 128 registers: ~70 B of spills instead of ~370
 #endif
 #ifndef ATHK_TILE_MINB
 #define ATHK_TILE_MINB 4
 #endif
 #ifndef ATHK_TILE_PREFETCH
-#define ATHK_TILE_PREFETCH 1   // 1: prefetch.global.L2 of the next step's cell, 2: .L1, 0: off
+#define ATHK_TILE_PREFETCH 1   // (unstaged kernel) 1: prefetch.global.L2 of the next step's cell, 2: .L1, 0: off
 #endif
+#ifndef ATHK_TILE_STAGE
+#define ATHK_TILE_STAGE 1
+#endif
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows of the staged pencil: [slot][variable][lane]
+template <bool MHD>
+struct SmemStencil {
+  static constexpr int NQ = MHD ? 8 : 5;
+  const Real *ring;   // + lane
+  int slot0;          // ring slot of the face's upper cell
+  int nr;             // ring size
+  __device__ __forceinline__ const Real *row(int off) const {
+    int sl = slot0 + off;
+    sl = (sl < 0) ? sl + nr : (sl >= nr ? sl - nr : sl);
+    return ring + sl * (NQ * 32);
+  }
+  __device__ __forceinline__ void cell(int off, Real q[7]) const {
+    const Real *p = row(off);
+#pragma unroll
+    for (int v = 0; v < (MHD ? 7 : 5); ++v) q[v] = p[v * 32];
+  }
+  __device__ __forceinline__ Real bx() const { return MHD ? row(0)[7 * 32] : 0.0; }
+};
+
+template <int DIR, int ORDER, bool MHD, int RS>
+__global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
+k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il,
+                    const int ni) {
+  constexpr int R = ATHK_TILE_R;
+  constexpr int LO = ORDER, HI = ORDER - 1;   // cells n-LO .. n+HI around face n
+  constexpr int NR = 2 * R + LO + HI;         // rows in use by a step + rows in flight
+  constexpr int NQ = MHD ? 8 : 5;
+  // fluxes of the step: double-buffered (a fast warp writes step t+1 while a slow one still
+  // reads step t); the top row also feeds r == 0 of the NEXT step, hence its own 3-deep ring
+  extern __shared__ __align__(16) Real smem_tile[];
+  Real(*sF)[R][5][32] = reinterpret_cast<Real(*)[R][5][32]>(smem_tile);                 // [2]
+  Real(*sTop)[5][32] = reinterpret_cast<Real(*)[5][32]>(smem_tile + 2 * R * 5 * 32);     // [3]
+  Real(*sQ)[NQ][32] = reinterpret_cast<Real(*)[NQ][32]>(smem_tile + (2 * R + 3) * 5 * 32);   // [NR]
+  const Grid &g = a.g;
+  const int lane = threadIdx.x, r = threadIdx.y;
+  const long long col = (long long)blockIdx.x * 32 + lane;
+  const long long ncol = (long long)nb * n_o * ni;
+  const bool colvalid = col < ncol;
+  int blk = 0, o = o_lo, i = il;
+  if (colvalid) {
+    const int row = (int)(col / ni);
+    i = il + (int)(col - (long long)row * ni);
+    blk = row / n_o;
+    o = o_lo + (row - blk * n_o);
+  }
+  const idx_t s = (DIR == 1) ? g.sj : g.sk;
+  const int n_s = (DIR == 1) ? g.js : g.ks;
+  const int n_e = (DIR == 1) ? g.je : g.ke;
+  const int k0 = (DIR == 1) ? o : 0, j0 = (DIR == 1) ? 0 : o;
+  const bool interior = colvalid && (i >= g.is && i <= g.ie) &&
+                        ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
+  Real area = 0.0;
+  if (interior) {
+    const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
+    area = dx1 * a.geo.dxf[(DIR == 1) ? 2 : 1][blk * a.geo.PG + o];   // Face2Area / Face3Area
+  }
+  Real *dst = (DIR == 1) ? a.d2 : a.d3;
+  const int nf = n_e + 1 - n_s + 1;            // faces n_s .. n_e+1
+  const int nsteps = (nf + R - 1) / R;
+  const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
+  // this column's cell 0 along the sweep
+  const idx_t c0 = (DIR == 1) ? gidx(g, k0, 0, i) : gidx(g, 0, j0, i);
+  const int row_first = n_s - LO;            // ring slot 0
+  const int row_last = n_e + 1 + HI;         // last cell any face needs
+  // asynchronous copy of cell row m of this thread's column into its ring slot
+  auto stage_row = [&](int m) {
+    if (colvalid && m <= row_last) {
+      Real *d = &sQ[(m - row_first) % NR][0][lane];
+      const idx_t cm = c0 + (idx_t)m * s;
+      const Real *wsrc = a.w + (idx_t)blk * 5 * g.sn + cm;
+      cp_async8(d, wsrc);
+      cp_async8(d + 32, wsrc + (idx_t)(IVX + DIR) * g.sn);
+      cp_async8(d + 2 * 32, wsrc + (idx_t)(IVX + (DIR + 1) % 3) * g.sn);
+      cp_async8(d + 3 * 32, wsrc + (idx_t)(IVX + (DIR + 2) % 3) * g.sn);
+      cp_async8(d + 4 * 32, wsrc + (idx_t)IPR * g.sn);
+      if (MHD) {
+        const Real *bc = a.bcc + (idx_t)blk * 3 * g.sn + cm;
+        cp_async8(d + 5 * 32, bc + (idx_t)((DIR + 1) % 3) * g.sn);
+        cp_async8(d + 6 * 32, bc + (idx_t)((DIR + 2) % 3) * g.sn);
+        cp_async8(d + 7 * 32, a.b + ((idx_t)blk * 3 + DIR) * g.sn + cm);
+      }
+    }
+  };
+  // prologue: rows n_s-LO .. n_s+R-1+HI
+  for (int m = r; m < R + LO + HI; m += R) stage_row(row_first + m);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (int step = 0; step < nsteps; ++step) {
+    const int n = n_s + step * R + r;
+    const bool fvalid = colvalid && n <= n_e + 1;
+    const int buf = step & 1;
+    // rows first needed by the next step: n0+R+HI .. n0+2R-1+HI, one per thread row
+    stage_row(n + R + HI);
+    cp_async_commit();
+    Real f[7];
+    idx_t c = 0;
+    if (fvalid) {
+      c = c0 + (idx_t)n * s;
+      const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
+      face_compute_from<DIR, ORDER, MHD, RS>(a, blk, c, n, st, f, true);
+      Real(*mine)[32] = (r == R - 1) ? sTop[step % 3] : sF[buf][r];
+      mine[0][lane] = f[IDN];
+      mine[1][lane] = f[IVX];
+      mine[2][lane] = f[IVY];
+      mine[3][lane] = f[IVZ];
+      mine[4][lane] = f[IEN];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (fvalid && interior && n > n_s) {   // this thread owns cell n-1: pure store, no RMW
+      const Real(*below)[32] = (r > 0) ? sF[buf][r - 1] : sTop[(step + 2) % 3];
+      const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
+      const idx_t cc = c - s;
+#pragma unroll
+      for (int v = 0; v < 5; ++v)
+        dst[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = (area * fcur[v] - area * below[v][lane]);
+    }
+  }
+}
 
 template <int DIR, int ORDER, bool MHD, int RS>
 __global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
@@ -115,7 +255,20 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   if (ncol <= 0) return cudaSuccess;
   dim3 block(32, ATHK_TILE_R);
   const unsigned grid = (unsigned)((ncol + 31) / 32);
+#if ATHK_TILE_STAGE
+  constexpr int R = ATHK_TILE_R, NR = 2 * R + 2 * ORDER - 1, NQ = MHD ? 8 : 5;
+  constexpr size_t smem = sizeof(Real) * 32 * ((2 * R + 3) * 5 + NR * NQ);
+  static bool attr_set = false;   // > 48 KB of dynamic shared memory is opt-in, once per kernel
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_tile_staged<DIR, ORDER, MHD, RS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_sweep_tile_staged<DIR, ORDER, MHD, RS><<<grid, block, smem, st>>>(a, nb, o_lo, n_o, il, ni);
+#else
   k_sweep_tile<DIR, ORDER, MHD, RS><<<grid, block, 0, st>>>(a, nb, o_lo, n_o, il, ni);
+#endif
   return cudaGetLastError();
 }
 

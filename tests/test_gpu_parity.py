@@ -91,3 +91,4 @@ def test_cuda_fused_decomposition_invariance(cuda_lib, block):
                                             fused=True)
     util.assert_matches_golden(meta, z, ctx, ti)
     ctx.close()
+

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("libs", nargs="*")
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--block", type=int, default=64)
+    ap.add_argument("--sweeps", action="store_true", help="only the fused cycle + its per-kernel breakdown")
     args = ap.parse_args()
     libs = args.libs or [capi.LIB_PATH]
     torch.cuda.init()
@@ -56,6 +57,21 @@ def main():
         stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
         dt = ti.dt
         res = {}
+        if args.sweeps:
+            import json
+            res["cycle_fused"] = time_call(ctx, stream, lambda: ti.step(), reps=3)
+            ctx.call("athk_profile", 1, None, 0)
+            for _ in range(2):
+                ti.step()
+            buf = ctypes.create_string_buffer(16384)
+            ctx.call("athk_profile", 0, buf, len(buf))
+            rep = json.loads(buf.value.decode() or "{}")
+            for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+                if "sweep" in k:
+                    res[k] = v["ms"] / 2
+            print(os.path.basename(path), " ".join("%s=%.3f" % kv for kv in res.items()), flush=True)
+            ctx.close()
+            continue
         res["flux_o1"] = time_call(ctx, stream, lambda: ctx.call("athk_calculate_fluxes", 1, dt, 0))
         res["flux_o2"] = time_call(ctx, stream, lambda: ctx.call("athk_calculate_fluxes", 2, dt, 0))
         res["corner_e"] = time_call(ctx, stream, lambda: ctx.call("athk_compute_corner_e"))
