@@ -481,9 +481,10 @@ extern "C" int athk_send_flux_correction(athk_ctx *c) {
   NEED_READY(c);
   if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "send_flux_correction: context is not MHD");
   const Grid &g = c->g;
-  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  const Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};   // boundary surface only
+  const Range3 rin = {g.ks + 1, g.ke, g.js + 1, g.je, g.is + 1, g.ie};
   EmfPackPoint f = {g, c->sf, c->e, c->emfbuf};
-  LAUNCH(c, r, f);
+  LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
   return ATHK_OK;
 }
 
@@ -491,9 +492,10 @@ extern "C" int athk_recv_flux_correction(athk_ctx *c) {
   NEED_READY(c);
   if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "recv_flux_correction: context is not MHD");
   const Grid &g = c->g;
-  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  const Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  const Range3 rin = {g.ks + 1, g.ke, g.js + 1, g.je, g.is + 1, g.ie};
   EmfApplyPoint f = {g, c->sf, c->e, c->emfbuf, c->nbr, c->rl.erbuf, c->rl.ebase};
-  LAUNCH(c, r, f);
+  LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
   return ATHK_OK;
 }
 
@@ -605,15 +607,16 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
   NEED_READY(c);
   if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "exchange_ghosts: bad register");
   const Grid &g = c->g;
+  const Range3 rin = {g.ks, g.ke, g.js, g.je, g.is, g.ie};   // only the ghost shell is launched
   if (what_mask & 1) {
     if (!c->u[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: u register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
       GhostFillCC<true> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillCC<false> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   if (what_mask & 2) {
@@ -621,10 +624,10 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
     Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
     if (c->rl.n > 0) {
       GhostFillFC<true> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillFC<false> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   if (what_mask & 4) {
@@ -632,10 +635,10 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
       GhostFillCC<true> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillCC<false> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
-      LAUNCH(c, r, f);
+      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   return ATHK_OK;

@@ -78,6 +78,54 @@ static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r
   return cudaGetLastError();
 }
 
+// Points of an outer box that are NOT in an inner box (ghost zones around the active zone, the
+// boundary surface of the edge box): six disjoint slabs, flattened into one index so that only
+// the shell is launched -- a 64^3 block has 17 % of its cells in the ghost shell and 9 % of its
+// edges on the surface.
+struct Shell {
+  int k0[6], j0[6], i0[6], nj[6], ni[6];
+  unsigned end[6];   // cumulative point counts
+};
+static inline Shell make_shell(const Range3 &o, const Range3 &in) {
+  Shell s;
+  const Range3 b[6] = {{o.kl, in.kl - 1, o.jl, o.ju, o.il, o.iu},   {in.ku + 1, o.ku, o.jl, o.ju, o.il, o.iu},
+                       {in.kl, in.ku, o.jl, in.jl - 1, o.il, o.iu}, {in.kl, in.ku, in.ju + 1, o.ju, o.il, o.iu},
+                       {in.kl, in.ku, in.jl, in.ju, o.il, in.il - 1}, {in.kl, in.ku, in.jl, in.ju, in.iu + 1, o.iu}};
+  unsigned acc = 0;
+  for (int q = 0; q < 6; ++q) {
+    const int nk = b[q].ku - b[q].kl + 1, nj = b[q].ju - b[q].jl + 1, ni = b[q].iu - b[q].il + 1;
+    s.k0[q] = b[q].kl; s.j0[q] = b[q].jl; s.i0[q] = b[q].il;
+    s.nj[q] = nj > 0 ? nj : 1; s.ni[q] = ni > 0 ? ni : 1;
+    if (nk > 0 && nj > 0 && ni > 0) acc += (unsigned)nk * nj * ni;
+    s.end[q] = acc;
+  }
+  return s;
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_shell(const F f, const Shell s) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= s.end[5]) return;
+  int q = 0;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) q += (t >= s.end[m]) ? 1 : 0;
+  if (q > 0) t -= s.end[q - 1];
+  const unsigned ni = (unsigned)s.ni[q], nj = (unsigned)s.nj[q];
+  const unsigned row = t / ni, i = t - row * ni;
+  const unsigned k = row / nj, j = row - k * nj;
+  f((int)blockIdx.y, s.k0[q] + (int)k, s.j0[q] + (int)j, s.i0[q] + (int)i);
+}
+
+template <class F>
+static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &outer, const Range3 &inner,
+                                       const F &f) {
+  const Shell s = make_shell(outer, inner);
+  if (s.end[5] == 0 || nb <= 0) return cudaSuccess;
+  dim3 grid((s.end[5] + 255) / 256, (unsigned)nb);
+  k_shell<F><<<grid, 256, 0, st>>>(f, s);
+  return cudaGetLastError();
+}
+
 // x1 sweep: one lane per face; within a (k, MeshBlock) plane the faces form a stream and warps
 // advance by 31 so that lane L+1 always holds the flux of the upper face of lane L's cell (one
 // redundant face per warp, 3%).
@@ -154,6 +202,10 @@ static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, c
 template <class F>
 static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
   return launch_points(st, nb, r, f);
+}
+template <class F>
+static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &outer, const Range3 &, const F &f) {
+  return launch_points(st, nb, outer, f);   // the functors skip the points of the inner box themselves
 }
 #endif
 
