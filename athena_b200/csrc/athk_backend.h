@@ -160,16 +160,7 @@ k_sweep_x1(const F f, const int kl, const int jl, const int nj, const int il, co
     f.store_d1(blk, k, j, il + fi, fl, fn);
 }
 
-template <class F>
-static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
-  const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
-  if (nif <= 1 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
-  const int total = nj * nif;
-  const int nwarps = (total - 1 + 30) / 31;
-  dim3 grid((unsigned)((nwarps + 3) / 4), (unsigned)nk, (unsigned)nb);
-  k_sweep_x1<F><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il, nif, magic_u32(nif));
-  return cudaGetLastError();
-}
+// (launch_sweep_x1: athk_sweep_kernels.cuh)
 // (link, element) launcher for the variable-length remote messages
 template <class F>
 __global__ void __launch_bounds__(256) k_links(const F f, const long long maxcount) {

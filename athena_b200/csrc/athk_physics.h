@@ -302,7 +302,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   const Real SMALL_NUMBER = 1.0e-4;
   const Real igm1 = eos.igm1;
   Real spd[5];
-  Cons7 ul, ur, ulst, uldst, urdst, urst, fl, fr;
+  Cons7 ul, ur, ulst, uldst, urdst, urst;
 
   Real bxsq = bxi * bxi;
   Real pbl = 0.5 * (bxsq + (sqr(wl[IBY]) + sqr(wl[IBZ])));
@@ -334,22 +334,6 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
 
   Real ptl = wl[IPR] + pbl;
   Real ptr = wr[IPR] + pbr;
-
-  fl.d = ul.mx;
-  fl.mx = ul.mx * wl[IVX] + ptl - bxsq;
-  fl.my = ul.my * wl[IVX] - bxi * ul.by;
-  fl.mz = ul.mz * wl[IVX] - bxi * ul.bz;
-  fl.e = wl[IVX] * (ul.e + ptl - bxsq) - bxi * (wl[IVY] * ul.by + wl[IVZ] * ul.bz);
-  fl.by = ul.by * wl[IVX] - bxi * wl[IVY];
-  fl.bz = ul.bz * wl[IVX] - bxi * wl[IVZ];
-
-  fr.d = ur.mx;
-  fr.mx = ur.mx * wr[IVX] + ptr - bxsq;
-  fr.my = ur.my * wr[IVX] - bxi * ur.by;
-  fr.mz = ur.mz * wr[IVX] - bxi * ur.bz;
-  fr.e = wr[IVX] * (ur.e + ptr - bxsq) - bxi * (wr[IVY] * ur.by + wr[IVZ] * ur.bz);
-  fr.by = ur.by * wr[IVX] - bxi * wr[IVY];
-  fr.bz = ur.bz * wr[IVX] - bxi * wr[IVZ];
 
   Real sdl = spd[0] - wl[IVX];
   Real sdr = spd[4] - wr[IVX];
@@ -448,88 +432,53 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   uldst.e = ulst.e - sqrtdl * bxsig * (vbstl - tmp);
   urdst.e = urst.e + sqrtdr * bxsig * (vbstr - tmp);
 
-  // jump terms S*(U_a - U_b); the reference overwrites the state structs the same way
-  uldst.d = spd[1] * (uldst.d - ulst.d);
-  uldst.mx = spd[1] * (uldst.mx - ulst.mx);
-  uldst.my = spd[1] * (uldst.my - ulst.my);
-  uldst.mz = spd[1] * (uldst.mz - ulst.mz);
-  uldst.e = spd[1] * (uldst.e - ulst.e);
-  uldst.by = spd[1] * (uldst.by - ulst.by);
-  uldst.bz = spd[1] * (uldst.bz - ulst.bz);
-
-  ulst.d = spd[0] * (ulst.d - ul.d);
-  ulst.mx = spd[0] * (ulst.mx - ul.mx);
-  ulst.my = spd[0] * (ulst.my - ul.my);
-  ulst.mz = spd[0] * (ulst.mz - ul.mz);
-  ulst.e = spd[0] * (ulst.e - ul.e);
-  ulst.by = spd[0] * (ulst.by - ul.by);
-  ulst.bz = spd[0] * (ulst.bz - ul.bz);
-
-  urdst.d = spd[3] * (urdst.d - urst.d);
-  urdst.mx = spd[3] * (urdst.mx - urst.mx);
-  urdst.my = spd[3] * (urdst.my - urst.my);
-  urdst.mz = spd[3] * (urdst.mz - urst.mz);
-  urdst.e = spd[3] * (urdst.e - urst.e);
-  urdst.by = spd[3] * (urdst.by - urst.by);
-  urdst.bz = spd[3] * (urdst.bz - urst.bz);
-
-  urst.d = spd[4] * (urst.d - ur.d);
-  urst.mx = spd[4] * (urst.mx - ur.mx);
-  urst.my = spd[4] * (urst.my - ur.my);
-  urst.mz = spd[4] * (urst.mz - ur.mz);
-  urst.e = spd[4] * (urst.e - ur.e);
-  urst.by = spd[4] * (urst.by - ur.by);
-  urst.bz = spd[4] * (urst.bz - ur.bz);
-
-  if (spd[0] >= 0.0) {
-    f[IDN] = fl.d;
-    f[IVX] = fl.mx;
-    f[IVY] = fl.my;
-    f[IVZ] = fl.mz;
-    f[IEN] = fl.e;
-    f[IBY] = fl.by;
-    f[IBZ] = fl.bz;
-  } else if (spd[4] <= 0.0) {
-    f[IDN] = fr.d;
-    f[IVX] = fr.mx;
-    f[IVY] = fr.my;
-    f[IVZ] = fr.mz;
-    f[IEN] = fr.e;
-    f[IBY] = fr.by;
-    f[IBZ] = fr.bz;
-  } else if (spd[1] >= 0.0) {
-    f[IDN] = fl.d + ulst.d;
-    f[IVX] = fl.mx + ulst.mx;
-    f[IVY] = fl.my + ulst.my;
-    f[IVZ] = fl.mz + ulst.mz;
-    f[IEN] = fl.e + ulst.e;
-    f[IBY] = fl.by + ulst.by;
-    f[IBZ] = fl.bz + ulst.bz;
-  } else if (spd[3] <= 0.0) {
-    f[IDN] = fr.d + urst.d;
-    f[IVX] = fr.mx + urst.mx;
-    f[IVY] = fr.my + urst.my;
-    f[IVZ] = fr.mz + urst.mz;
-    f[IEN] = fr.e + urst.e;
-    f[IBY] = fr.by + urst.by;
-    f[IBZ] = fr.bz + urst.bz;
-  } else if (spd[2] >= 0.0) {
-    f[IDN] = fl.d + ulst.d + uldst.d;
-    f[IVX] = fl.mx + ulst.mx + uldst.mx;
-    f[IVY] = fl.my + ulst.my + uldst.my;
-    f[IVZ] = fl.mz + ulst.mz + uldst.mz;
-    f[IEN] = fl.e + ulst.e + uldst.e;
-    f[IBY] = fl.by + ulst.by + uldst.by;
-    f[IBZ] = fl.bz + ulst.bz + uldst.bz;
-  } else {
-    f[IDN] = fr.d + urst.d + urdst.d;
-    f[IVX] = fr.mx + urst.mx + urdst.mx;
-    f[IVY] = fr.my + urst.my + urdst.my;
-    f[IVZ] = fr.mz + urst.mz + urdst.mz;
-    f[IEN] = fr.e + urst.e + urdst.e;
-    f[IBY] = fr.by + urst.by + urdst.by;
-    f[IBZ] = fr.bz + urst.bz + urdst.bz;
+  // Flux of the region the face lies in (hlld.cpp:323-365): F_L or F_R plus the jump terms
+  // S*(U_a - U_b) across the waves between that side and the face.  The reference evaluates
+  // F_L, F_R and all four jumps and then picks; only the picked side is evaluated here (same
+  // expressions, same association, hence the same bits) -- 2 x 7 fewer values stay live across
+  // the star-state algebra, which is what the 96-128 register budget of the sweeps is short of.
+  bool left;
+  int depth;
+  if (spd[0] >= 0.0) { left = true; depth = 0; }
+  else if (spd[4] <= 0.0) { left = false; depth = 0; }
+  else if (spd[1] >= 0.0) { left = true; depth = 1; }
+  else if (spd[3] <= 0.0) { left = false; depth = 1; }
+  else if (spd[2] >= 0.0) { left = true; depth = 2; }
+  else { left = false; depth = 2; }
+  const Real vx = left ? wl[IVX] : wr[IVX], vy = left ? wl[IVY] : wr[IVY], vz = left ? wl[IVZ] : wr[IVZ];
+  const Real pt = left ? ptl : ptr;
+  const Real s_out = left ? spd[0] : spd[4], s_in = left ? spd[1] : spd[3];
+  Cons7 u0, u1, u2, fx;
+  u0.d = left ? ul.d : ur.d;         u1.d = left ? ulst.d : urst.d;         u2.d = left ? uldst.d : urdst.d;
+  u0.mx = left ? ul.mx : ur.mx;      u1.mx = left ? ulst.mx : urst.mx;      u2.mx = left ? uldst.mx : urdst.mx;
+  u0.my = left ? ul.my : ur.my;      u1.my = left ? ulst.my : urst.my;      u2.my = left ? uldst.my : urdst.my;
+  u0.mz = left ? ul.mz : ur.mz;      u1.mz = left ? ulst.mz : urst.mz;      u2.mz = left ? uldst.mz : urdst.mz;
+  u0.e = left ? ul.e : ur.e;         u1.e = left ? ulst.e : urst.e;         u2.e = left ? uldst.e : urdst.e;
+  u0.by = left ? ul.by : ur.by;      u1.by = left ? ulst.by : urst.by;      u2.by = left ? uldst.by : urdst.by;
+  u0.bz = left ? ul.bz : ur.bz;      u1.bz = left ? ulst.bz : urst.bz;      u2.bz = left ? uldst.bz : urdst.bz;
+  // physical flux of that side (hlld.cpp:123-139)
+  fx.d = u0.mx;
+  fx.mx = u0.mx * vx + pt - bxsq;
+  fx.my = u0.my * vx - bxi * u0.by;
+  fx.mz = u0.mz * vx - bxi * u0.bz;
+  fx.e = vx * (u0.e + pt - bxsq) - bxi * (vy * u0.by + vz * u0.bz);
+  fx.by = u0.by * vx - bxi * vy;
+  fx.bz = u0.bz * vx - bxi * vz;
+#define ATHK_HLLD_PICK(x, out)                                      \
+  {                                                                 \
+    Real r_ = fx.x;                                                 \
+    if (depth >= 1) r_ = fx.x + s_out * (u1.x - u0.x);              \
+    if (depth == 2) r_ = r_ + s_in * (u2.x - u1.x);                 \
+    out = r_;                                                       \
   }
+  ATHK_HLLD_PICK(d, f[IDN])
+  ATHK_HLLD_PICK(mx, f[IVX])
+  ATHK_HLLD_PICK(my, f[IVY])
+  ATHK_HLLD_PICK(mz, f[IVZ])
+  ATHK_HLLD_PICK(e, f[IEN])
+  ATHK_HLLD_PICK(by, f[IBY])
+  ATHK_HLLD_PICK(bz, f[IBZ])
+#undef ATHK_HLLD_PICK
 }
 
 }  // namespace athk

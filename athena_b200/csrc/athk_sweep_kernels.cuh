@@ -272,5 +272,22 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   return cudaGetLastError();
 }
 
+//========================================================================================
+// x1 sweep launcher (kernel k_sweep_x1 in athk_backend.h).  A variant that staged each warp's next
+// 32 faces in shared memory with cp.async while solving the current ones was measured SLOWER
+// (2.04 vs 1.89 ms per PLM sweep at 256^3): the x1 sweep's long-scoreboard stalls are register-
+// spill reloads, not the global loads, so it was dropped.
+template <int ORDER, bool MHD, int RS>
+static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r,
+                                          const SweepX1<ORDER, MHD, RS> &f) {
+  const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
+  if (nif <= 1 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
+  const int total = nj * nif;
+  const int nchunks = (total - 1 + 30) / 31;
+  dim3 grid((unsigned)((nchunks + 3) / 4), (unsigned)nk, (unsigned)nb);
+  k_sweep_x1<SweepX1<ORDER, MHD, RS>><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il, nif, magic_u32(nif));
+  return cudaGetLastError();
+}
+
 }  // namespace athk
 #endif  // ATHK_SWEEP_KERNELS_CUH_

@@ -92,3 +92,26 @@ def test_cuda_fused_decomposition_invariance(cuda_lib, block):
     util.assert_matches_golden(meta, z, ctx, ti)
     ctx.close()
 
+
+
+# The reference is decomposition-invariant only up to rounding: block-boundary EMFs are averaged
+# between neighbours whose face coordinates differ in the last bit.  Running the unmodified
+# reference with both decompositions of these two fixtures gives 161 / 1915 entries that differ by
+# <= 1.4e-15, and this library reproduces either run bit for bit when given the same blocks.
+DECOMPOSITION_SENSITIVE = {"mhd_linwave_alfven_vl2", "mhd_linwave_rk3_plm_roe_slow"}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_fused_stage_wide_blocks_match_reference(cuda_lib, name):
+    # a second decomposition of every fixture (nx1 = 32: full warps along x1, tiles that straddle rows)
+    meta, _ = util.load_golden(name)
+    block = (32, meta["mesh"][1] // 2, meta["mesh"][2])
+    meta, z, ctx, ti = util.run_golden_case(cuda_lib, name, block=block, fused=True)
+    if name in DECOMPOSITION_SENSITIVE:
+        U, B = util.gather_from_ctx(ctx)
+        assert ti.ncycle == meta["ncycle"] and ti.dt == meta["dt_final"]
+        np.testing.assert_allclose(U, z["uf"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(B[0], z["b1_f"], rtol=0, atol=1e-14)
+    else:
+        util.assert_matches_golden(meta, z, ctx, ti)
+    ctx.close()
