@@ -130,7 +130,7 @@ static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &ou
 // advance by 31 so that lane L+1 always holds the flux of the upper face of lane L's cell (one
 // redundant face per warp, 3%).
 #ifndef ATHK_X1_MINB
-#define ATHK_X1_MINB 5
+#define ATHK_X1_MINB 6   // 80 registers, 24 warps/SM (measured best after the HLLD register diet)
 #endif
 template <class F>
 __global__ void __launch_bounds__(128, ATHK_X1_MINB)

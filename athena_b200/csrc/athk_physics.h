@@ -307,14 +307,11 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   Real bxsq = bxi * bxi;
   Real pbl = 0.5 * (bxsq + (sqr(wl[IBY]) + sqr(wl[IBZ])));
   Real pbr = 0.5 * (bxsq + (sqr(wr[IBY]) + sqr(wr[IBZ])));
-  Real kel = 0.5 * wl[IDN] * (sqr(wl[IVX]) + (sqr(wl[IVY]) + sqr(wl[IVZ])));
-  Real ker = 0.5 * wr[IDN] * (sqr(wr[IVX]) + (sqr(wr[IVY]) + sqr(wr[IVZ])));
 
   ul.d = wl[IDN];
   ul.mx = wl[IVX] * ul.d;
   ul.my = wl[IVY] * ul.d;
   ul.mz = wl[IVZ] * ul.d;
-  ul.e = wl[IPR] * igm1 + kel + pbl;
   ul.by = wl[IBY];
   ul.bz = wl[IBZ];
 
@@ -322,7 +319,6 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   ur.mx = wr[IVX] * ur.d;
   ur.my = wr[IVY] * ur.d;
   ur.mz = wr[IVZ] * ur.d;
-  ur.e = wr[IPR] * igm1 + ker + pbr;
   ur.by = wr[IBY];
   ur.bz = wr[IBZ];
 
@@ -377,10 +373,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     ulst.by = ul.by * tmp;
     ulst.bz = ul.bz * tmp;
   }
-  Real vbstl = (ulst.mx * bxi + (ulst.my * ulst.by + ulst.mz * ulst.bz)) * ulst_d_inv;
-  // eq. 48
-  ulst.e = (sdl * ul.e - ptl * wl[IVX] + ptst * spd[2] +
-            bxi * (wl[IVX] * bxi + (wl[IVY] * ul.by + wl[IVZ] * ul.bz) - vbstl)) * sdml_inv;
+  // (v.B and the energy of the star states, eq. 48: formed below for the selected side only)
 
   // right star state
   urst.mx = urst.d * spd[2];
@@ -397,9 +390,6 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     urst.by = ur.by * tmp;
     urst.bz = ur.bz * tmp;
   }
-  Real vbstr = (urst.mx * bxi + (urst.my * urst.by + urst.mz * urst.bz)) * urst_d_inv;
-  urst.e = (sdr * ur.e - ptr * wr[IVX] + ptst * spd[2] +
-            bxi * (wr[IVX] * bxi + (wr[IVY] * ur.by + wr[IVZ] * ur.bz) - vbstr)) * sdmr_inv;
 
   // double-star states, eqs. 59-63
   Real invsumd = 1.0 / (sqrtdl + sqrtdr);
@@ -428,9 +418,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
                    bxsig * sqrtdl * sqrtdr * ((urst.mz * urst_d_inv) - (ulst.mz * ulst_d_inv)));
   uldst.bz = urdst.bz = tmp;
 
-  tmp = spd[2] * bxi + fdiv((uldst.my * uldst.by + uldst.mz * uldst.bz), uldst.d);
-  uldst.e = ulst.e - sqrtdl * bxsig * (vbstl - tmp);
-  urdst.e = urst.e + sqrtdr * bxsig * (vbstr - tmp);
+  const Real vbdst = spd[2] * bxi + fdiv((uldst.my * uldst.by + uldst.mz * uldst.bz), uldst.d);
 
   // Flux of the region the face lies in (hlld.cpp:323-365): F_L or F_R plus the jump terms
   // S*(U_a - U_b) across the waves between that side and the face.  The reference evaluates
@@ -453,9 +441,21 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   u0.mx = left ? ul.mx : ur.mx;      u1.mx = left ? ulst.mx : urst.mx;      u2.mx = left ? uldst.mx : urdst.mx;
   u0.my = left ? ul.my : ur.my;      u1.my = left ? ulst.my : urst.my;      u2.my = left ? uldst.my : urdst.my;
   u0.mz = left ? ul.mz : ur.mz;      u1.mz = left ? ulst.mz : urst.mz;      u2.mz = left ? uldst.mz : urdst.mz;
-  u0.e = left ? ul.e : ur.e;         u1.e = left ? ulst.e : urst.e;         u2.e = left ? uldst.e : urdst.e;
+  {   // total energy of that side (hlld.cpp:84-98); the other side's is never used
+    const Real dd = left ? wl[IDN] : wr[IDN], pp = left ? wl[IPR] : wr[IPR], pb = left ? pbl : pbr;
+    const Real ke = 0.5 * dd * (sqr(vx) + (sqr(vy) + sqr(vz)));
+    u0.e = pp * igm1 + ke + pb;
+  }
   u0.by = left ? ul.by : ur.by;      u1.by = left ? ulst.by : urst.by;      u2.by = left ? uldst.by : urdst.by;
   u0.bz = left ? ul.bz : ur.bz;      u1.bz = left ? ulst.bz : urst.bz;      u2.bz = left ? uldst.bz : urdst.bz;
+  {   // star / double-star energies of that side, eqs. 48 and 63 (hlld.cpp:226-230,262-266,301-303)
+    const Real sd = left ? sdl : sdr, sdm_inv = left ? sdml_inv : sdmr_inv;
+    const Real u1d_inv = left ? ulst_d_inv : urst_d_inv, sqrtd = left ? sqrtdl : sqrtdr;
+    const Real vbst = (u1.mx * bxi + (u1.my * u1.by + u1.mz * u1.bz)) * u1d_inv;
+    u1.e = (sd * u0.e - pt * vx + ptst * spd[2] + bxi * (vx * bxi + (vy * u0.by + vz * u0.bz) - vbst)) * sdm_inv;
+    const Real de = sqrtd * bxsig * (vbst - vbdst);
+    u2.e = left ? u1.e - de : u1.e + de;
+  }
   // physical flux of that side (hlld.cpp:123-139)
   fx.d = u0.mx;
   fx.mx = u0.mx * vx + pt - bxsq;

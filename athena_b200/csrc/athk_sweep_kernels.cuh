@@ -27,7 +27,7 @@
 namespace athk {
 
 #ifndef ATHK_TILE_R
-#define ATHK_TILE_R 4     // 128 threads x 4 CTAs/SM = 128 registers: ~70 B of spills instead of ~370
+#define ATHK_TILE_R 5
 #endif
 #ifndef ATHK_TILE_MINB
 #define ATHK_TILE_MINB 4
