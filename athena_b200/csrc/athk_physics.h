@@ -133,6 +133,8 @@ ATHK_HD Real vl_slope(Real dwl, Real dwr) {
 // Colella-Dawson interface limiter :139-193; Colella-Sekora / McCorquodale-Colella
 // extremum-preserving limiter :226-279, time/ext_preserving = true, C2 = 1.25).
 // Returns the left state of the upper face (ql_iph) and the right state of the lower face (qr_imh).
+// (qd/6 and qe/qd below go through fdiv: both numerators are exactly 0 wherever the profile is
+//  locally linear or uniform, which would otherwise take the FP64 division's slow path)
 ATHK_HD Real sign_ath(Real x) { return (x < 0.0) ? -1.0 : 1.0; }   // SIGN() of defs.hpp.in:150
 
 ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Real *ql_iph,
@@ -158,7 +160,7 @@ ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Re
     Real qd = 0.0;
     if (sign_ath(qa) == sign_ath(qb) && sign_ath(qa) == sign_ath(qc))
       qd = sign_ath(qa) * min_std(C2 * fabs(qb), min_std(C2 * fabs(qc), fabs(qa)));
-    const Real dph_tmp = 0.5 * (q_im1 + q) - qd / 6.0;
+    const Real dph_tmp = 0.5 * (q_im1 + q) - fdiv(qd, 6.0);
     if (qa_tmp * qb_tmp < 0.0) dph = dph_tmp;
   }
   {   // i+1/2 interface
@@ -170,7 +172,7 @@ ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Re
     Real qd = 0.0;
     if (sign_ath(qa) == sign_ath(qb) && sign_ath(qa) == sign_ath(qc))
       qd = sign_ath(qa) * min_std(C2 * fabs(qb), min_std(C2 * fabs(qc), fabs(qa)));
-    const Real dphip1_tmp = 0.5 * (q + q_ip1) - qd / 6.0;
+    const Real dphip1_tmp = 0.5 * (q + q_ip1) - fdiv(qd, 6.0);
     if (qa_tmp * qb_tmp < 0.0) dph_ip1 = dphip1_tmp;
   }
   const Real d2qf = 6.0 * (dph + dph_ip1 - 2.0 * q);
@@ -190,7 +192,7 @@ ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Re
     qa = max_std(fabs(q_im1), fabs(q_im2));
     qb = max_std(max_std(fabs(q), fabs(q_ip1)), fabs(q_ip2));
     Real rho = 0.0;
-    if (fabs(qd) > (1.0e-12) * max_std(qa, qb)) rho = qe / qd;
+    if (fabs(qd) > (1.0e-12) * max_std(qa, qb)) rho = fdiv(qe, qd);
     const Real tmp_m = q - rho * dqf_minus;
     const Real tmp_p = q + rho * dqf_plus;
     const Real tmp2_m = q - 2.0 * dqf_plus;

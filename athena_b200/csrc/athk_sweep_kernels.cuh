@@ -82,40 +82,55 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
   Real(*sQ)[NQ][32] = reinterpret_cast<Real(*)[NQ][32]>(smem_tile + (2 * R + 3) * 5 * 32);   // [NR]
   const Grid &g = a.g;
   const int lane = threadIdx.x, r = threadIdx.y;
-  const long long col = (long long)blockIdx.x * 32 + lane;
-  const long long ncol = (long long)nb * n_o * ni;
-  const bool colvalid = col < ncol;
-  int blk = 0, o = o_lo, i = il;
-  if (colvalid) {
-    const int row = (int)(col / ni);
-    i = il + (int)(col - (long long)row * ni);
-    blk = row / n_o;
-    o = o_lo + (row - blk * n_o);
-  }
+  // Per-column invariants (MeshBlock, first cell, face area, flags) live in shared memory and are
+  // re-read where needed: kept in registers they would be spilled around the Riemann solve, and
+  // local-memory reloads miss the 56 KB of L1 this kernel leaves (profiles/).
+  __shared__ idx_t sC0[32];
+  __shared__ Real sArea[32];
+  __shared__ int sBlk[32];   // blk | interior << 29 | colvalid << 30
   const idx_t s = (DIR == 1) ? g.sj : g.sk;
   const int n_s = (DIR == 1) ? g.js : g.ks;
   const int n_e = (DIR == 1) ? g.je : g.ke;
-  const int k0 = (DIR == 1) ? o : 0, j0 = (DIR == 1) ? 0 : o;
-  const bool interior = colvalid && (i >= g.is && i <= g.ie) &&
-                        ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
-  Real area = 0.0;
-  if (interior) {
-    const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
-    area = dx1 * a.geo.dxf[(DIR == 1) ? 2 : 1][blk * a.geo.PG + o];   // Face2Area / Face3Area
+  if (r == 0) {
+    const long long col = (long long)blockIdx.x * 32 + lane;
+    const long long ncol = (long long)nb * n_o * ni;
+    const bool colvalid = col < ncol;
+    int blk = 0, o = o_lo, i = il;
+    if (colvalid) {
+      const int row = (int)(col / ni);
+      i = il + (int)(col - (long long)row * ni);
+      blk = row / n_o;
+      o = o_lo + (row - blk * n_o);
+    }
+    const int k0 = (DIR == 1) ? o : 0, j0 = (DIR == 1) ? 0 : o;
+    const bool interior = colvalid && (i >= g.is && i <= g.ie) &&
+                          ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
+    Real area = 0.0;
+    if (interior) {
+      const Real dx1 = a.geo.dxf[0][blk * a.geo.PG + i];
+      area = dx1 * a.geo.dxf[(DIR == 1) ? 2 : 1][blk * a.geo.PG + o];   // Face2Area / Face3Area
+    }
+    sC0[lane] = (DIR == 1) ? gidx(g, k0, 0, i) : gidx(g, 0, j0, i);   // the column's cell 0 along the sweep
+    sArea[lane] = area;
+    sBlk[lane] = blk | (interior ? (1 << 29) : 0) | (colvalid ? (1 << 30) : 0);
   }
+  __syncthreads();
+  const volatile idx_t *vC0 = sC0;
+  const volatile Real *vArea = sArea;
+  const volatile int *vBlk = sBlk;
   Real *dst = (DIR == 1) ? a.d2 : a.d3;
   const int nf = n_e + 1 - n_s + 1;            // faces n_s .. n_e+1
   const int nsteps = (nf + R - 1) / R;
   const int vmap[5] = {IDN, IVX + DIR, IVX + (DIR + 1) % 3, IVX + (DIR + 2) % 3, IEN};
-  // this column's cell 0 along the sweep
-  const idx_t c0 = (DIR == 1) ? gidx(g, k0, 0, i) : gidx(g, 0, j0, i);
   const int row_first = n_s - LO;            // ring slot 0
   const int row_last = n_e + 1 + HI;         // last cell any face needs
   // asynchronous copy of cell row m of this thread's column into its ring slot
   auto stage_row = [&](int m) {
-    if (colvalid && m <= row_last) {
+    const int bf = vBlk[lane];
+    if ((bf >> 30) && m <= row_last) {
+      const int blk = bf & 0x1fffffff;
       Real *d = &sQ[(m - row_first) % NR][0][lane];
-      const idx_t cm = c0 + (idx_t)m * s;
+      const idx_t cm = vC0[lane] + (idx_t)m * s;
       const Real *wsrc = a.w + (idx_t)blk * 5 * g.sn + cm;
       cp_async8(d, wsrc);
       cp_async8(d + 32, wsrc + (idx_t)(IVX + DIR) * g.sn);
@@ -136,16 +151,21 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
   cp_async_wait_all();
   __syncthreads();
   for (int step = 0; step < nsteps; ++step) {
-    const int n = n_s + step * R + r;
-    const bool fvalid = colvalid && n <= n_e + 1;
+    // n is re-derived from the (warp-uniform) step counter every iteration: left to itself the
+    // compiler strength-reduces it into several per-thread induction variables, which it then has
+    // to spill around the Riemann solve and reload -- through a 56 KB L1 -- at the top of the loop
+    int sv = step;
+    asm volatile("" : "+r"(sv));
+    const int n = n_s + sv * R + r;
+    const bool fvalid = (vBlk[lane] >> 30) && n <= n_e + 1;
     const int buf = step & 1;
     // rows first needed by the next step: n0+R+HI .. n0+2R-1+HI, one per thread row
     stage_row(n + R + HI);
     cp_async_commit();
     Real f[7];
-    idx_t c = 0;
     if (fvalid) {
-      c = c0 + (idx_t)n * s;
+      const int blk = vBlk[lane] & 0x1fffffff;
+      const idx_t c = vC0[lane] + (idx_t)n * s;
       const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
       face_compute_from<DIR, ORDER, MHD, RS>(a, blk, c, n, st, f, true);
       Real(*mine)[32] = (r == R - 1) ? sTop[step % 3] : sF[buf][r];
@@ -157,10 +177,13 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
     }
     cp_async_wait_all();
     __syncthreads();
-    if (fvalid && interior && n > n_s) {   // this thread owns cell n-1: pure store, no RMW
+    const int bf = vBlk[lane];
+    if (fvalid && ((bf >> 29) & 1) && n > n_s) {   // this thread owns cell n-1: pure store, no RMW
       const Real(*below)[32] = (r > 0) ? sF[buf][r - 1] : sTop[(step + 2) % 3];
       const Real fcur[5] = {f[IDN], f[IVX], f[IVY], f[IVZ], f[IEN]};
-      const idx_t cc = c - s;
+      const idx_t cc = vC0[lane] + (idx_t)(n - 1) * s;
+      const Real area = vArea[lane];
+      const int blk = bf & 0x1fffffff;
 #pragma unroll
       for (int v = 0; v < 5; ++v)
         dst[((idx_t)blk * 5 + vmap[v]) * g.sn + cc] = (area * fcur[v] - area * below[v][lane]);

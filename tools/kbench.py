@@ -12,17 +12,22 @@ import torch  # noqa: E402
 from athena_b200 import capi, problems, pyhost  # noqa: E402
 
 
-def setup(lib, n, blk, mhd=True):
-    mesh = pyhost.UniformMesh((n,) * 3, (blk,) * 3, (-1.0,) * 3, (1.0,) * 3, ng=2)
-    ctx = pyhost.Context(mesh, mhd, 1.666666666667, lib=lib)
+def setup(lib, n, blk, mhd=True, config="blast"):
+    kh = config == "kh"   # BASELINE configs[3] shape: hydro, RK3 + PPM + HLLC + one passive scalar
+    if kh:
+        mhd = False
+    mesh = pyhost.UniformMesh((n,) * 3, (blk,) * 3, (-1.0,) * 3, (1.0,) * 3, ng=3 if kh else 2)
+    ctx = pyhost.Context(mesh, mhd, 1.666666666667, lib=lib, nscalars=1 if kh else 0)
     for lb, g in enumerate(ctx.gids):
         ic = problems.blast_block(mesh, mesh.loc[g], mhd, 1.666666666667)
         ctx.upload("U", lb, ic["u"])
+        if kh:
+            ctx.upload("S", lb, 0.5 * ic["u"][0:1])
         if mhd:
             ctx.upload("B_X1F", lb, ic["b1"])
             ctx.upload("B_X2F", lb, ic["b2"])
             ctx.upload("B_X3F", lb, ic["b3"])
-    ti = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=True)
+    ti = pyhost.TimeIntegrator(ctx, "rk3" if kh else "vl2", 3 if kh else 2, 0.3, fused=True)
     ti.initialize()
     for _ in range(3):
         ti.step()
@@ -48,12 +53,14 @@ def main():
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--block", type=int, default=64)
     ap.add_argument("--sweeps", action="store_true", help="only the fused cycle + its per-kernel breakdown")
+    ap.add_argument("--config", default="blast", choices=["blast", "kh"])
+    ap.add_argument("--all", action="store_true", help="with --sweeps: list every kernel, not only the sweeps")
     args = ap.parse_args()
     libs = args.libs or [capi.LIB_PATH]
     torch.cuda.init()
     for path in libs:
         lib = capi.bind(ctypes.CDLL(os.path.abspath(path)))
-        ctx, ti = setup(lib, args.n, args.block)
+        ctx, ti = setup(lib, args.n, args.block, config=args.config)
         stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
         dt = ti.dt
         res = {}
@@ -67,7 +74,7 @@ def main():
             ctx.call("athk_profile", 0, buf, len(buf))
             rep = json.loads(buf.value.decode() or "{}")
             for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
-                if "sweep" in k:
+                if "sweep" in k or args.all:
                     res[k] = v["ms"] / 2
             print(os.path.basename(path), " ".join("%s=%.3f" % kv for kv in res.items()), flush=True)
             ctx.close()

@@ -26,13 +26,18 @@ per = nb // world
 parts = [list(range(r * per, (r + 1) * per if r < world - 1 else nb)) for r in range(world)]
 rank_of = {g: r for r, gl in enumerate(parts) for g in gl}
 mhd = meta["mhd"]
-ctx = pyhost.Context(mesh, mhd, meta["gamma"], device=lr, gids=parts[rank], rank_of=rank_of, my_rank=rank, lib=lib)
+ns = meta.get("nscalars") or 0
+ctx = pyhost.Context(mesh, mhd, meta["gamma"], device=lr, gids=parts[rank], rank_of=rank_of, my_rank=rank, lib=lib,
+                     nscalars=ns, rsolver=util.RSOLVERS[meta["flux"]] if meta.get("flux") else None)
 stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
 multigpu.attach(ctx, rank, world, device="cuda", stream=stream)
 B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
 blocks = util.split_to_blocks(mesh, z["u0"], *B)
+sblocks = util.split_to_blocks(mesh, z["s0"]) if ns else None
 for lb, g in enumerate(ctx.gids):
     ctx.upload("U", lb, blocks[g]["u"])
+    if ns:
+        ctx.upload("S", lb, sblocks[g]["u"])
     if mhd:
         ctx.upload("B_X1F", lb, blocks[g]["b1"])
         ctx.upload("B_X2F", lb, blocks[g]["b2"])
@@ -50,6 +55,9 @@ for lb, g in enumerate(ctx.gids):
     o1, o2, o3 = l1 * nx1, l2 * nx2, l3 * nx3
     u = ctx.download("U", lb)[:, ng:ng + nx3, ng:ng + nx2, ng:ng + nx1]
     ok = ok and np.array_equal(u, z["uf"][:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1])
+    if ns:
+        sc = ctx.download("S", lb)[:, ng:ng + nx3, ng:ng + nx2, ng:ng + nx1]
+        ok = ok and np.array_equal(sc, z["sf"][:, o3:o3 + nx3, o2:o2 + nx2, o1:o1 + nx1])
     if mhd:
         b2 = ctx.download("B_X2F", lb)[ng:ng + nx3, ng:ng + nx2 + 1, ng:ng + nx1]
         ok = ok and np.array_equal(b2, z["b2_f"][o3:o3 + nx3, o2:o2 + nx2 + 1, o1:o1 + nx1])
