@@ -391,6 +391,11 @@ void athk_prof_end(athk_ctx *) {}
 #endif
 
 
+// streaming (HBM-bound) point kernels: compiled for 8 CTAs of 128 threads per SM (<= 64 registers)
+#ifndef ATHK_STREAM_MINB
+#define ATHK_STREAM_MINB 8
+#endif
+
 static bool bad_reg(int r) { return r < 0 || r > 2; }
 
 #ifndef ATHK_EMULATE
@@ -434,11 +439,11 @@ extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   if (c->cfg.mhd) {
     Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr, dt_out, c->geo,
                               ns ? c->s[reg] : nullptr, c->r, ns};
-    LAUNCH(c, r, f);
+    LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
   } else {
     Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo,
                                ns ? c->s[reg] : nullptr, c->r, ns};
-    LAUNCH(c, r, f);
+    LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
   }
   if (c->dt_requested) { c->dt_valid = true; c->dt_requested = false; }
   return ATHK_OK;
@@ -473,7 +478,7 @@ extern "C" int athk_compute_corner_e(athk_ctx *c) {
   const Grid &g = c->g;
   Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
   CornerEPoint f = {g, c->w, c->bcc, c->ef, c->wct, c->e};
-  LAUNCH(c, r, f);
+  LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
   return ATHK_OK;
 }
 
@@ -958,7 +963,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
       Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
       CTIntegratePoint f = {g, c->geo, c->e, fi};
-      LAUNCH_NAMED(c, "ct_integrate", launch_points(c->stream, g.nb, r, f));
+      LAUNCH_NAMED(c, "ct_integrate", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
       if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
     }
     return athk_remote_pack_ghosts(c, 0);

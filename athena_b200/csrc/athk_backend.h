@@ -56,8 +56,8 @@ struct Range3 {
 #endif
 static inline unsigned magic_u32(int d) { return (unsigned)((0x100000000ULL + (unsigned)d - 1) / (unsigned)d); }
 
-template <class F>
-__global__ void __launch_bounds__(ATHK_KP_THREADS, ATHK_KP_MINB)
+template <class F, int MINB>
+__global__ void __launch_bounds__(ATHK_KP_THREADS, MINB)
 k_points(const F f, const int kl, const int jl, const int nj, const int il, const int ni,
          const unsigned ni_magic) {
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,15 +67,22 @@ k_points(const F f, const int kl, const int jl, const int nj, const int il, cons
   f((int)blockIdx.z, kl + (int)blockIdx.y, jl + (int)j, il + (int)i);
 }
 
-template <class F>
-static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f,
-                                        int threads = ATHK_KP_THREADS) {
-  if (threads > ATHK_KP_THREADS) threads = ATHK_KP_THREADS;
+// MINB = resident CTAs per SM the kernel is compiled for (register budget 65536 / (128 * MINB)):
+// 5 for the FP64-heavy face kernels, more for streaming kernels that need loads in flight
+template <int MINB, class F>
+static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range3 &r, const F &f) {
+  const int threads = ATHK_KP_THREADS;
   const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
   dim3 grid((unsigned)((nj * ni + threads - 1) / threads), (unsigned)nk, (unsigned)nb);
-  k_points<F><<<grid, threads, 0, st>>>(f, r.kl, r.jl, nj, r.il, ni, magic_u32(ni));
+  k_points<F, MINB><<<grid, threads, 0, st>>>(f, r.kl, r.jl, nj, r.il, ni, magic_u32(ni));
   return cudaGetLastError();
+}
+
+template <class F>
+static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f,
+                                        int = ATHK_KP_THREADS) {
+  return launch_points_occ<ATHK_KP_MINB>(st, nb, r, f);
 }
 
 // Points of an outer box that are NOT in an inner box (ghost zones around the active zone, the
@@ -192,6 +199,10 @@ static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, c
 }
 template <class F>
 static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
+  return launch_points(st, nb, r, f);
+}
+template <int MINB, class F>
+static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range3 &r, const F &f) {
   return launch_points(st, nb, r, f);
 }
 template <class F>

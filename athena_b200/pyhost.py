@@ -11,6 +11,7 @@ Reference behaviour mirrored here (file:line under /root/reference/src):
   * global time step                       mesh/mesh.cpp:1236-1282, main.cpp:457-541
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -227,6 +228,7 @@ class TimeIntegrator:
         # cfl clamp, time_integrator.cpp:893-903
         self.cfl = min(cfl_number, cfl_limit)
         self.fused = fused
+        self.fold_dt = bool(int(os.environ.get("ATHK_FOLD_DT", "0")))
         self.time = 0.0
         self.dt = sys.float_info.max
         self.ncycle = 0
@@ -332,8 +334,9 @@ class TimeIntegrator:
     def step(self, tlim=None, reduce_min=None):
         nst = len(self.stages)
         for stage in range(1, nst + 1):
-            # (athk_request_block_dt could fold NEW_DT into this stage's W(U); measured slower
-            #  than the separate reduction kernel on B200, so it is not used here)
+            if stage == nst and self.fold_dt:
+                # NEW_DT folded into the last stage's W(U) (same per-cell values, exact min)
+                self.ctx.call("athk_request_block_dt")
             self.one_stage(stage)
         self.ncycle += 1
         self.time += self.dt
