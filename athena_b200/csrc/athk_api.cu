@@ -144,6 +144,10 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   }
   c->h_geo.assign((size_t)9 * g.nb * PG, 0.0);
   c->h_nbr.assign((size_t)g.nb * 27, -1);
+  c->h_bcflags.assign((size_t)g.nb * 6, 0);
+  c->bcflags = nullptr;
+  c->bc_dirty = false;
+  for (int f = 0; f < 6; ++f) c->bc_any[f] = 0;
   CU(cudaStreamSynchronize(st));
   *out = c;
   return ATHK_OK;
@@ -154,6 +158,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   for (int r = 0; r < 3; ++r) { cudaFree(c->u[r]); cudaFree(c->b[r]); cudaFree(c->s[r]); }
   for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
+  cudaFree(c->bcflags);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
@@ -790,6 +795,68 @@ static int launch_scalar_integrate(athk_ctx *c, const HydroIntegrate &hi) {
   LAUNCH_NAMED(c, "scalar_fluxes_integrate", launch_points(c->stream, g.nb, r, f));
   return ATHK_OK;
 }
+//----------------------------------------------------------------------------------------
+// Physical boundary conditions (athk_bcs.h)
+extern "C" int athk_set_boundary_flags(athk_ctx *c, int lb, const int flags[6]) {
+  if (!c || !flags) return fail(ATHK_ERR_ARG, "set_boundary_flags: null argument");
+  if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "set_boundary_flags: block %d out of range", lb);
+  for (int f = 0; f < 6; ++f) {
+    if (flags[f] < ATHK_BC_NONE || flags[f] > ATHK_BC_OUTFLOW)
+      return fail(ATHK_ERR_ARG, "set_boundary_flags: face %d has unknown flag %d (reflecting, outflow or none)",
+                  f, flags[f]);
+    c->h_bcflags[(size_t)lb * 6 + f] = flags[f];
+  }
+  c->bc_dirty = true;
+  return ATHK_OK;
+}
+
+template <int DIR>
+static int launch_bc_face(athk_ctx *c, int side) {
+  const Grid &g = c->g;
+  // the DIR coordinate runs over the ghost layer m = 1..ng, the others over the padded box
+  Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
+  if (DIR == 0) { r.il = 1; r.iu = g.ng; }
+  if (DIR == 1) { r.jl = 1; r.ju = g.ng; }
+  if (DIR == 2) { r.kl = 1; r.ku = g.ng; }
+  const int mhd = c->cfg.mhd, ns = c->cfg.nscalars;
+  PhysBCFillPoint<DIR> f1 = {g, side, c->bcflags, mhd, ns, c->w, mhd ? c->b[0] : nullptr, c->r};
+  LAUNCH_NAMED(c, "apply_physical_boundaries", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f1));
+  Range3 rc = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+  if (DIR == 0) { rc.il = 1; rc.iu = g.ng; }
+  if (DIR == 1) { rc.jl = 1; rc.ju = g.ng; }
+  if (DIR == 2) { rc.kl = 1; rc.ku = g.ng; }
+  PhysBCConsPoint<DIR> f2 = {g, side, c->bcflags, c->eos, mhd, ns, c->w, mhd ? c->b[0] : nullptr, c->r,
+                             c->bcc, c->u[0], ns ? c->s[0] : nullptr};
+  LAUNCH_NAMED(c, "apply_physical_boundaries", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, rc, f2));
+  return ATHK_OK;
+}
+
+extern "C" int athk_apply_physical_boundaries(athk_ctx *c) {
+  NEED_READY(c);
+  if (c->bc_dirty) {
+    for (int f = 0; f < 6; ++f) c->bc_any[f] = 0;
+    for (int b = 0; b < c->g.nb; ++b)
+      for (int f = 0; f < 6; ++f)
+        if (c->h_bcflags[(size_t)b * 6 + f] != ATHK_BC_NONE) {
+          if (c->h_nbr[(size_t)b * 27 + nbr_slot(f / 2 == 0 ? (f % 2 ? 1 : -1) : 0, f / 2 == 1 ? (f % 2 ? 1 : -1) : 0,
+                                                 f / 2 == 2 ? (f % 2 ? 1 : -1) : 0)] != -1)
+            return fail(ATHK_ERR_STATE, "apply_physical_boundaries: block %d face %d is flagged as a physical "
+                                        "boundary but has a neighbour in the table", b, f);
+          c->bc_any[f] = 1;
+        }
+    if (!c->bcflags) CU(cudaMalloc((void **)&c->bcflags, c->h_bcflags.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(c->bcflags, c->h_bcflags.data(), c->h_bcflags.size() * sizeof(int),
+                       cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->bc_dirty = false;
+  }
+  int rc = ATHK_OK;
+  for (int side = 0; side < 2 && !rc; ++side) if (c->bc_any[0 + side]) rc = launch_bc_face<0>(c, side);
+  for (int side = 0; side < 2 && !rc; ++side) if (c->bc_any[2 + side]) rc = launch_bc_face<1>(c, side);
+  for (int side = 0; side < 2 && !rc; ++side) if (c->bc_any[4 + side]) rc = launch_bc_face<2>(c, side);
+  return rc;
+}
+
 // History sums (outputs/history.cpp:196-248).  The reference adds cells serially; here every
 // MeshBlock is reduced by one CTA in a fixed order (deterministic, not the serial order: the sums
 // agree with the reference to rounding, ~1e-15 relative; the north-star bar is 1e-10), and the
@@ -969,7 +1036,8 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     return athk_remote_pack_ghosts(c, 0);
   }
   if ((rc = athk_exchange_ghosts(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0))) return rc;
-  return athk_cons2prim(c, 0);
+  if ((rc = athk_cons2prim(c, 0))) return rc;
+  return athk_apply_physical_boundaries(c);   // PHY_BVAL (no-op without physical boundaries)
 }
 //----------------------------------------------------------------------------------------
 // Remote links (neighbours that live on another GPU).  The transport itself (NCCL send/recv or

@@ -17,6 +17,7 @@
 #include "athk_ops.h"
 #include "athk_sweep.h"
 #include "athk_scalars.h"
+#include "athk_bcs.h"
 #ifndef ATHK_EMULATE
 #include "athk_sweep_kernels.cuh"
 #endif
@@ -74,6 +75,11 @@ struct athk_ctx {
   int *nbr;         // [nb][27]
   Real *dt_blocks;  // [nb]
   std::vector<int> h_nbr;
+  // physical boundaries: block_bcs per local block (enum athk_bc), device copy uploaded lazily
+  std::vector<int> h_bcflags;   // [nb][6]
+  int *bcflags;                 // device
+  bool bc_dirty;
+  int bc_any[6];                // does any local block have a physical boundary on face f
   std::vector<Real> h_geo;   // host mirror of geo_store
 };
 

@@ -165,9 +165,17 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     ATHENA_ERROR(msg);
   }
   for (int n = 0; n < 6; ++n) {
-    if (mesh_bcs[n] != BoundaryFlag::periodic) {
+    if (mesh_bcs[n] != BoundaryFlag::periodic && mesh_bcs[n] != BoundaryFlag::reflect &&
+        mesh_bcs[n] != BoundaryFlag::outflow) {
       msg << "### FATAL ERROR in Mesh constructor" << std::endl
-          << "The B200 path implements periodic mesh boundaries only (" << bn[n] << ")";
+          << "The B200 path implements periodic, reflecting and outflow mesh boundaries (" << bn[n] << ")";
+      ATHENA_ERROR(msg);
+    }
+  }
+  for (int d = 0; d < 3; ++d) {   // bvals_base.cpp: periodic boundaries come in pairs
+    if ((mesh_bcs[2 * d] == BoundaryFlag::periodic) != (mesh_bcs[2 * d + 1] == BoundaryFlag::periodic)) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "When periodic boundaries are in use, both sides must be periodic." << std::endl;
       ATHENA_ERROR(msg);
     }
   }
@@ -259,12 +267,32 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
       for (int o2 = -1; o2 <= 1; ++o2)
         for (int o1 = -1; o1 <= 1; ++o1) {
           if (o1 == 0 && o2 == 0 && o3 == 0) continue;
-          LogicalLocation q{(l.lx1 + o1 + nrbx1) % nrbx1, (l.lx2 + o2 + nrbx2) % nrbx2,
-                            (l.lx3 + o3 + nrbx3) % nrbx3, l.level};
+          // no neighbour across a non-periodic mesh boundary (entry stays -1)
+          const std::int64_t q1 = l.lx1 + o1, q2 = l.lx2 + o2, q3 = l.lx3 + o3;
+          if ((q1 < 0 || q1 >= nrbx1) && mesh_bcs[0] != BoundaryFlag::periodic) continue;
+          if ((q2 < 0 || q2 >= nrbx2) && mesh_bcs[2] != BoundaryFlag::periodic) continue;
+          if ((q3 < 0 || q3 >= nrbx3) && mesh_bcs[4] != BoundaryFlag::periodic) continue;
+          LogicalLocation q{(q1 + nrbx1) % nrbx1, (q2 + nrbx2) % nrbx2, (q3 + nrbx3) % nrbx3, l.level};
           nbr[(std::size_t)n * 27 + (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1)] = gid_of[MortonKey(q)];
         }
   }
   AthkCheck(athk_set_neighbors(athk, nbr.data()), "Mesh constructor (athk_set_neighbors)");
+  // BoundaryValues::block_bcs (bvals.cpp:60-120): mesh flag on the mesh edge, "block" elsewhere
+  for (int n = 0; n < nblocal; ++n) {
+    const LogicalLocation &l = loclist[n];
+    const std::int64_t lx[3] = {l.lx1, l.lx2, l.lx3}, nr[3] = {nrbx1, nrbx2, nrbx3};
+    int fl[6];
+    bool any = false;
+    for (int d = 0; d < 3; ++d)
+      for (int side = 0; side < 2; ++side) {
+        const BoundaryFlag bf = mesh_bcs[2 * d + side];
+        const bool edge = side ? (lx[d] == nr[d] - 1) : (lx[d] == 0);
+        fl[2 * d + side] = (!edge || bf == BoundaryFlag::periodic) ? ATHK_BC_NONE
+                           : (bf == BoundaryFlag::reflect ? ATHK_BC_REFLECT : ATHK_BC_OUTFLOW);
+        any = any || fl[2 * d + side] != ATHK_BC_NONE;
+      }
+    if (any) AthkCheck(athk_set_boundary_flags(athk, n, fl), "Mesh constructor (athk_set_boundary_flags)");
+  }
   if (pgen->init_user_mesh_data) pgen->init_user_mesh_data(this, pin);   // mesh.cpp:601
 }
 
@@ -291,6 +319,7 @@ void Mesh::Initialize(ParameterInput *pin) {
   AthkCheck(athk_exchange_ghosts(athk, 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0),
             "Mesh::Initialize");
   AthkCheck(athk_cons2prim(athk, 0), "Mesh::Initialize");
+  AthkCheck(athk_apply_physical_boundaries(athk), "Mesh::Initialize");   // mesh.cpp:1886-1891
   NewTimeStep();
 }
 

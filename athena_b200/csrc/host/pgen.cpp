@@ -219,6 +219,92 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
 }
 
 //========================================================================================
+// shock_tube (pgen/shock_tube.cpp:305-575, adiabatic branch): left/right states about xshock along
+// shock_dir, velocity and field components rotated with the direction
+static void ShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  std::stringstream msg;
+  const int shk_dir = pin->GetInteger("problem", "shock_dir");
+  const Real xshock = pin->GetReal("problem", "xshock");
+  const RegionSize &ms = pmb->pmy_mesh->mesh_size;
+  const Real lo[3] = {ms.x1min, ms.x2min, ms.x3min}, hi[3] = {ms.x1max, ms.x2max, ms.x3max};
+  if (shk_dir < 1 || shk_dir > 3) {
+    msg << "### FATAL ERROR in Problem Generator" << std::endl
+        << "shock_dir=" << shk_dir << " must be either 1,2, or 3" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  if (xshock < lo[shk_dir - 1] || xshock > hi[shk_dir - 1]) {
+    msg << "### FATAL ERROR in Problem Generator" << std::endl << "xshock="
+        << xshock << " lies outside x" << shk_dir << " domain for shkdir=" << shk_dir << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  Real wl[8], wr[8];
+  wl[IDN] = pin->GetReal("problem", "dl");
+  wl[IVX] = pin->GetReal("problem", "ul");
+  wl[IVY] = pin->GetReal("problem", "vl");
+  wl[IVZ] = pin->GetReal("problem", "wl");
+  wl[IPR] = pin->GetReal("problem", "pl");
+  wr[IDN] = pin->GetReal("problem", "dr");
+  wr[IVX] = pin->GetReal("problem", "ur");
+  wr[IVY] = pin->GetReal("problem", "vr");
+  wr[IVZ] = pin->GetReal("problem", "wr");
+  wr[IPR] = pin->GetReal("problem", "pr");
+  if (MAGNETIC_FIELDS_ENABLED) {
+    wl[5] = pin->GetReal("problem", "bxl");
+    wl[6] = pin->GetReal("problem", "byl");
+    wl[7] = pin->GetReal("problem", "bzl");
+    wr[5] = pin->GetReal("problem", "bxr");
+    wr[6] = pin->GetReal("problem", "byr");
+    wr[7] = pin->GetReal("problem", "bzr");
+  }
+  Coordinates *pc = pmb->pcoord;
+  AthenaArray<Real> &u = pmb->phydro->u;
+  // momentum component that receives (u, v, w) for each direction (shock_tube.cpp:372,418,452)
+  const int m1[3] = {IM1, IM2, IM3}, m2[3] = {IM2, IM3, IM1}, m3[3] = {IM3, IM1, IM2};
+  const int d = shk_dir - 1;
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  for (int k = pmb->ks; k <= pmb->ke; ++k)
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) {
+        const Real x = (d == 0) ? pc->x1v(i) : (d == 1 ? pc->x2v(j) : pc->x3v(k));
+        const Real *w = (x < xshock) ? wl : wr;
+        u(IDN, k, j, i) = w[IDN];
+        u(m1[d], k, j, i) = w[IVX] * w[IDN];
+        u(m2[d], k, j, i) = w[IVY] * w[IDN];
+        u(m3[d], k, j, i) = w[IVZ] * w[IDN];
+        u(IEN, k, j, i) = w[IPR] / gm1;
+        u(IEN, k, j, i) += 0.5 * w[IDN] * (w[IVX] * w[IVX] + w[IVY] * w[IVY] + w[IVZ] * w[IVZ]);
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    FaceField &b = pmb->pfield->b;
+    // (bx, by, bz) -> (x1f, x2f, x3f) per direction (shock_tube.cpp:503-531)
+    const int c1[3] = {5, 7, 6}, c2[3] = {6, 5, 7}, c3[3] = {7, 6, 5};
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) {
+          const Real x = (d == 0) ? pc->x1v(i) : (d == 1 ? pc->x2v(j) : pc->x3v(k));
+          const Real *w = (x < xshock) ? wl : wr;
+          b.x1f(k, j, i) = w[c1[d]];
+          b.x2f(k, j, i) = w[c2[d]];
+          b.x3f(k, j, i) = w[c3[d]];
+          u(IEN, k, j, i) += 0.5 * (SQR(b.x1f(k, j, i)) + SQR(b.x2f(k, j, i)) + SQR(b.x3f(k, j, i)));
+        }
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j) b.x1f(k, j, pmb->ie + 1) = b.x1f(k, j, pmb->ie);
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int i = pmb->is; i <= pmb->ie; ++i) b.x2f(k, pmb->je + 1, i) = b.x2f(k, pmb->je, i);
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) b.x3f(pmb->ke + 1, j, i) = b.x3f(pmb->ke, j, i);
+  }
+  if (NSCALARS > 0) {
+    const int scalar_norm = NSCALARS;
+    for (int n = 0; n < NSCALARS; ++n)
+      for (int k = pmb->ks; k <= pmb->ke; ++k)
+        for (int j = pmb->js; j <= pmb->je; ++j)
+          for (int i = pmb->is; i <= pmb->ie; ++i) pmb->pscalars->s(n, k, j, i) = 1.0 / scalar_norm * u(IDN, k, j, i);
+  }
+}
+
+//========================================================================================
 // linear_wave
 namespace {
 Real amp, vflow, ang_2, ang_3, sin_a2, cos_a2, sin_a3, cos_a3, lambda, k_par, gam, gm1;
@@ -493,6 +579,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"blast", nullptr, BlastGenerator, nullptr},
     {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
     {"kh", KHInitUserMeshData, KHGenerator, nullptr},
+    {"shock_tube", nullptr, ShockTubeGenerator, nullptr},
 };
 
 const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {

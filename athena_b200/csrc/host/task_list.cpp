@@ -113,4 +113,5 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   }
   AthkCheck(athk_exchange_ghosts(a, 1 | (mhd ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0), who);   // SEND/RECV/SETB_HYD,_FLD,_SCLR
   AthkCheck(athk_cons2prim(a, 0), who);                            // CONS2PRIM
+  AthkCheck(athk_apply_physical_boundaries(a), who);               // PHY_BVAL :2276-2311
 }

@@ -49,7 +49,20 @@ def morton_key(lx1, lx2, lx3):
 class UniformMesh:
     """Uniform Cartesian mesh cut into equal MeshBlocks, listed in the reference's Z-order."""
 
-    def __init__(self, mesh_nx, block_nx, xmin, xmax, ng=2, periodic=(True, True, True)):
+    def __init__(self, mesh_nx, block_nx, xmin, xmax, ng=2, periodic=(True, True, True), bcs=None):
+        """bcs: the six <mesh> flags (ix1_bc, ox1_bc, ix2_bc, ox2_bc, ix3_bc, ox3_bc) as
+        'periodic' | 'reflecting' | 'outflow'; overrides ``periodic``."""
+        if bcs is not None:
+            bcs = tuple(bcs)
+            for d in range(3):
+                if (bcs[2 * d] == "periodic") != (bcs[2 * d + 1] == "periodic"):
+                    raise ValueError("periodic boundaries must be paired (bvals_base.cpp)")
+            periodic = tuple(bcs[2 * d] == "periodic" for d in range(3))
+        else:
+            bcs = tuple("periodic" for _ in range(6))
+            if not all(periodic):
+                raise ValueError("non-periodic mesh: give the six boundary flags (bcs=...)")
+        self.bcs = bcs
         self.mesh_nx = tuple(mesh_nx)
         self.block_nx = tuple(block_nx)
         self.xmin = tuple(float(v) for v in xmin)
@@ -66,6 +79,16 @@ class UniformMesh:
         self.loc = locs
         self.nbtotal = len(locs)
         self.gid_of = {l: n for n, l in enumerate(locs)}
+
+    def block_bcs(self, loc):
+        """BoundaryValues::block_bcs as enum athk_bc: a face on the mesh edge takes the mesh flag
+        unless periodic; interior faces are 'block' (0)."""
+        code = {"periodic": 0, "reflecting": 1, "outflow": 2}
+        out = []
+        for d in range(3):
+            out.append(code[self.bcs[2 * d]] if loc[d] == 0 else 0)
+            out.append(code[self.bcs[2 * d + 1]] if loc[d] == self.nrbx[d] - 1 else 0)
+        return out
 
     def block_bounds(self, loc, d):
         lx = loc[d]
@@ -174,6 +197,12 @@ class Context:
         tab, self.remote = mesh.neighbor_table(self.gids, rank_of, my_rank)
         self.nbr = np.ascontiguousarray(tab, dtype=np.int32)
         capi.check(self.lib, self.lib.athk_set_neighbors(h, self.nbr.ctypes.data_as(C.POINTER(C.c_int))))
+        self.has_physical_bcs = False
+        for lb, g in enumerate(self.gids):
+            fl = mesh.block_bcs(mesh.loc[g])
+            if any(fl):
+                self.has_physical_bcs = True
+                capi.check(self.lib, self.lib.athk_set_boundary_flags(h, lb, (C.c_int * 6)(*fl)))
 
     def close(self):
         if self.h:
@@ -247,6 +276,7 @@ class TimeIntegrator:
             xch.exchange_ghosts()
         c.call("athk_exchange_ghosts", 1 | (2 if c.mhd else 0) | (4 if c.nscalars else 0), 0)
         c.call("athk_cons2prim", 0)
+        c.call("athk_apply_physical_boundaries")   # mesh.cpp:1886-1891 (no-op on a periodic mesh)
 
     def new_block_dt(self):
         m = C.c_double()
@@ -330,6 +360,7 @@ class TimeIntegrator:
             xch.exchange_ghosts()
         c.call("athk_exchange_ghosts", 1 | (2 if mhd else 0) | (4 if c.nscalars else 0), 0)
         c.call("athk_cons2prim", 0)
+        c.call("athk_apply_physical_boundaries")   # PHY_BVAL (time_integrator.cpp:2276-2311)
 
     def step(self, tlim=None, reduce_min=None):
         nst = len(self.stages)

@@ -74,6 +74,10 @@ enum athk_array {
 /* time-integrator registers (u,b,s move together only if the caller says so) */
 enum athk_reg { ATHK_REG0 = 0, ATHK_REG1 = 1, ATHK_REG2 = 2 };
 
+/* BoundaryFlag of a MeshBlock face that is a physical boundary (bvals/utils/boundary_flag.cpp);
+ * faces with a neighbour (block / periodic) are ATHK_BC_NONE */
+enum athk_bc { ATHK_BC_NONE = 0, ATHK_BC_REFLECT = 1, ATHK_BC_OUTFLOW = 2 };
+
 /* ---- lifecycle ------------------------------------------------------------------------ */
 int athk_create(const athk_config *cfg, athk_ctx **out);
 void athk_destroy(athk_ctx *ctx);
@@ -150,6 +154,16 @@ int athk_ct(athk_ctx *ctx, double wght, int reg);
  * neighbours (bvals/bvals_var.cpp:212-326, cc/bvals_cc.cpp:287-420, fc/bvals_fc.cpp:344-680);
  * what: bit0 hydro u, bit1 field b, bit2 scalars s; taken from register reg. */
 int athk_exchange_ghosts(athk_ctx *ctx, int what_mask, int reg);
+/* BoundaryValues::block_bcs of local block lb: flags[6] = {inner_x1, outer_x1, inner_x2, outer_x2,
+ * inner_x3, outer_x3} as enum athk_bc.  The neighbour table must hold -1 across those faces.
+ * Default: all ATHK_BC_NONE (fully periodic / interior). */
+int athk_set_boundary_flags(athk_ctx *ctx, int lb, const int flags[6]);
+/* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:453): reflecting / outflow functions on
+ * the primitives w (and r) and on b, face by face in the reference's order x1, x2, x3, each
+ * followed by bcc, PrimitiveToConserved and s = r*rho on that ghost slab.  Call after
+ * athk_cons2prim (task PHY_BVAL, time_integrator.cpp:2276); athk_stage does it itself.
+ * No-op when no local block has a physical boundary. */
+int athk_apply_physical_boundaries(athk_ctx *ctx);
 /* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:45): per-block min dt * cfl, blocks 0..nblocks-1
  * into dt_blocks (may be NULL), returns the min over local blocks in *dt_min. Synchronises. */
 int athk_new_block_dt(athk_ctx *ctx, double cfl_number, double *dt_blocks, double *dt_min);

@@ -34,6 +34,8 @@ CONFIGS = {
     "blast_mhd_hlld": dict(PROB="blast", MHD=1, FLUX="hlld"),
     "blast_mhd_roe": dict(PROB="blast", MHD=1, FLUX="roe"),
     "shocktube_hydro_roe": dict(PROB="shock_tube", MHD=0, FLUX="roe"),
+    "shocktube_hydro_hllc": dict(PROB="shock_tube", MHD=0, FLUX="hllc"),
+    "shocktube_mhd_hlld": dict(PROB="shock_tube", MHD=1, FLUX="hlld"),
     "shocktube_mhd_roe": dict(PROB="shock_tube", MHD=1, FLUX="roe"),
     "blast_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc"),
     "ot_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld"),
@@ -275,7 +277,41 @@ def kh_blocks(mesh=(32, 32, 8), block=None, tlim=0.05, integrator="rk3", xorder=
     }
 
 
-def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, **kw):
+BC_KEYS = ("ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc")
+
+
+def set_bcs(blocks, bcs):
+    """bcs: six <mesh> boundary flags ('periodic' | 'reflecting' | 'outflow') or None."""
+    if bcs is not None:
+        for key, val in zip(BC_KEYS, bcs):
+            blocks["mesh"][key] = val
+    return blocks
+
+
+def blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.02, integrator="vl2", xorder=2, cfl=0.3,
+                 rst_dt=None, bcs=None, center=(0.0, 0.0, 0.0), prat=100.0, b0=1.0, radius=0.1):
+    """athinput for pgen/blast.cpp in the box [-1,1]^3 (inputs/mhd/athinput.blast shape)."""
+    b = {
+        "job": {"problem_id": "Blast"},
+        "output1": {"file_type": "hst", "dt": 1.0e-9 if rst_dt is None else rst_dt,
+                    "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 1.0e30 if rst_dt is None else rst_dt},
+        "time": {"cfl_number": cfl, "nlim": -1, "tlim": tlim, "integrator": integrator, "xorder": xorder,
+                 "ncycle_out": 1},
+        "mesh": {"nx1": mesh[0], "x1min": -1.0, "x1max": 1.0, "ix1_bc": "periodic", "ox1_bc": "periodic",
+                 "nx2": mesh[1], "x2min": -1.0, "x2max": 1.0, "ix2_bc": "periodic", "ox2_bc": "periodic",
+                 "nx3": mesh[2], "x3min": -1.0, "x3max": 1.0, "ix3_bc": "periodic", "ox3_bc": "periodic",
+                 "num_threads": 1},
+        "meshblock": {"nx1": block[0], "nx2": block[1], "nx3": block[2]},
+        "hydro": {"gamma": 1.666666666667, "iso_sound_speed": 0.4082482905},
+        "problem": {"pamb": 0.1, "prat": prat, "radius": radius, "damb": 1.0, "drat": 1.0,
+                    "ramp": 0.0, "b0": b0, "angle": 30, "x1_0": center[0], "x2_0": center[1],
+                    "x3_0": center[2]},
+    }
+    return set_bcs(b, bcs)
+
+
+def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, bcs=None, **kw):
     """athinput for pgen/shock_tube.cpp on the linear-wave test box (periodic, so the two
     discontinuities interact across the seam).  left/right = (d, u, v, w, p[, by, bz]) in the
     shock_dir frame (shock_tube.cpp:335-366)."""
@@ -289,7 +325,7 @@ def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, **kw):
         if mhd:
             pr["bx" + side], pr["by" + side], pr["bz" + side] = float(bx), float(st[5]), float(st[6])
     b["problem"] = pr
-    return b
+    return set_bcs(b, bcs)
 
 
 def linwave_blocks(mhd, mesh=(32, 16, 16), block=None, tlim=0.1, nlim=-1, wave_flag=0,

@@ -90,6 +90,27 @@ CASES = {
     "mhd_kh_rk2_plm_hlld_scalar": dict(cfg="kh_mhd_hlld_s1", mhd=True, mesh=(32, 32, 8),
                                        block=(16, 16, 8), tlim=0.03, integrator="rk2", xorder=2,
                                        nscalars=1, kh=dict(b0=0.5)),
+    # physical boundary conditions (outflow / reflecting), incl. edges and corners
+    "hydro_sod_vl2_plm_hllc_outflow_x1": dict(cfg="shocktube_hydro_hllc", mhd=False, mesh=(32, 16, 16),
+                                              block=(16, 8, 8), tlim=0.25, integrator="vl2", xorder=2,
+                                              bcs=["outflow", "outflow"] + ["periodic"] * 4,
+                                              shocktube=dict(left=(1.0, 0.0, 0.0, 0.0, 1.0),
+                                                             right=(0.125, 0.0, 0.0, 0.0, 0.1), shock_dir=1)),
+    "mhd_briowu_rk2_plm_hlld_outflow_x2": dict(cfg="shocktube_mhd_hlld", mhd=True, mesh=(32, 16, 16),
+                                               block=(16, 8, 8), tlim=0.06, integrator="rk2", xorder=2,
+                                               bcs=["periodic"] * 2 + ["outflow"] * 2 + ["periodic"] * 2,
+                                               shocktube=dict(left=(1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0),
+                                                              right=(0.125, 0.0, 0.0, 0.0, 0.1, -1.0, 0.0),
+                                                              shock_dir=2, bx=0.75)),
+    "mhd_blast_vl2_plm_hlld_reflecting_box": dict(cfg="blast_mhd_hlld", mhd=True, mesh=(32, 32, 32),
+                                                  block=(16, 16, 16), tlim=0.1, integrator="vl2", xorder=2,
+                                                  bcs=["reflecting"] * 6,
+                                                  blast=dict(center=(0.6, 0.55, 0.5), radius=0.3)),
+    "hydro_blast_rk3_plm_hllc_mixed_bcs": dict(cfg="blast_hydro_hllc", mhd=False, mesh=(32, 32, 32),
+                                               block=(16, 16, 16), tlim=0.1, integrator="rk3", xorder=2,
+                                               bcs=["outflow", "reflecting", "reflecting", "outflow",
+                                                    "periodic", "periodic"],
+                                               blast=dict(center=(0.55, -0.6, 0.0), radius=0.3)),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),
@@ -107,9 +128,14 @@ def make(name):
         m = blocks["mesh"]
         xmin, xmax = [m["x1min"], m["x2min"], m["x3min"]], [m["x1max"], m["x2max"], m["x3max"]]
         gamma = blocks["hydro"]["gamma"]
+    elif "blast" in c:
+        blocks = refrun.blast_blocks(mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                     integrator=c["integrator"], xorder=c["xorder"], bcs=c.get("bcs"),
+                                     **c["blast"])
+        xmin, xmax, gamma = [-1.0] * 3, [1.0] * 3, blocks["hydro"]["gamma"]
     elif "shocktube" in c:
         blocks = refrun.shocktube_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
-                                         integrator=c["integrator"], xorder=c["xorder"],
+                                         integrator=c["integrator"], xorder=c["xorder"], bcs=c.get("bcs"),
                                          **c["shocktube"])
     else:
         blocks = refrun.linwave_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],

@@ -15,7 +15,10 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          # Roe with negative intermediate densities -> LLF fallback, and supersonic upwinding
          "hydro_shocktube_vl2_plm_roe_llf", "mhd_shocktube_vl2_plm_roe_llf",
          # passive scalars (KH, Lecoanet dye), incl. BASELINE configs[3]'s RK3+PPM
-         "hydro_kh_rk3_ppm_hllc_scalar", "hydro_kh_vl2_plm_hllc_2scalars", "mhd_kh_rk2_plm_hlld_scalar"]
+         "hydro_kh_rk3_ppm_hllc_scalar", "hydro_kh_vl2_plm_hllc_2scalars", "mhd_kh_rk2_plm_hlld_scalar",
+         # outflow / reflecting physical boundaries
+         "hydro_sod_vl2_plm_hllc_outflow_x1", "mhd_briowu_rk2_plm_hlld_outflow_x2",
+         "mhd_blast_vl2_plm_hlld_reflecting_box", "hydro_blast_rk3_plm_hllc_mixed_bcs"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -59,6 +59,19 @@ CASES = {
                           lambda: refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03,
                                                    rst_dt=0.015, integrator="rk2", xorder=2, b0=0.5),
                           ["--nscalars=1"]),
+    # physical boundaries through the host's <mesh> ix*_bc / ox*_bc flags
+    "sod_outflow_x1": ("shocktube_hydro_hllc", "shock_tube", False,
+                       lambda: refrun.shocktube_blocks(False, (1.0, 0.0, 0.0, 0.0, 1.0), (0.125, 0.0, 0.0, 0.0, 0.1),
+                                                       shock_dir=1, mesh=(32, 16, 16), block=(16, 8, 8), tlim=0.1,
+                                                       rst_dt=0.05, bcs=["outflow"] * 2 + ["periodic"] * 4)),
+    "briowu_x3_reflect_outflow": ("shocktube_mhd_hlld", "shock_tube", True,
+                                  lambda: refrun.shocktube_blocks(
+                                      True, (1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0), (0.125, 0.0, 0.0, 0.0, 0.1, -1.0, 0.0),
+                                      shock_dir=3, bx=0.75, mesh=(32, 16, 16), block=(16, 8, 8), tlim=0.05,
+                                      rst_dt=0.025, bcs=["periodic"] * 4 + ["reflecting", "outflow"])),
+    "mhd_blast_reflecting_box": ("blast_mhd_hlld", "blast", True,
+                                 lambda: refrun.blast_blocks(tlim=0.06, rst_dt=0.03, bcs=["reflecting"] * 6,
+                                                             center=(0.6, 0.55, 0.5), radius=0.3)),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
