@@ -148,7 +148,7 @@ def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
 
 
 def test_parameter_input_error_behaviour(emul_binary):
-    """Missing parameter / unknown cmdline override / non-periodic BC: message + exit status as
+    """Missing parameter / unknown cmdline override / unpaired periodic BC: message + exit status as
     ATHENA_ERROR does (src/defs.hpp.in:155-159, parameter_input.cpp:352-395)."""
     blocks = blast_blocks()
     bad = {k: dict(v) for k, v in blocks.items()}
@@ -162,7 +162,11 @@ def test_parameter_input_error_behaviour(emul_binary):
     bad = {k: dict(v) for k, v in blocks.items()}
     bad["mesh"]["ix1_bc"] = "outflow"
     wd, r = run_host(emul_binary, bad, "blast", True)
-    assert r.returncode != 0 and "periodic mesh boundaries only" in r.stdout
+    assert r.returncode != 0 and "both sides must be periodic" in r.stdout   # (ox1_bc is still periodic)
+    shutil.rmtree(wd, ignore_errors=True)
+    bad["mesh"]["ix1_bc"] = bad["mesh"]["ox1_bc"] = "user"
+    wd, r = run_host(emul_binary, bad, "blast", True)
+    assert r.returncode != 0 and "periodic, reflecting and outflow mesh boundaries" in r.stdout
     shutil.rmtree(wd, ignore_errors=True)
     wd, r = run_host(emul_binary, blocks, "blast", True, extra=["time/tlim=0.004"])
     assert r.returncode == 0 and "Terminating on time limit" in r.stdout
