@@ -75,7 +75,11 @@ int main(int argc, char *argv[]) {
     const auto t0 = std::chrono::steady_clock::now();
     while ((pmesh->time < pmesh->tlim) && (pmesh->nlim < 0 || pmesh->ncycle < pmesh->nlim)) {
       pmesh->OutputCycleDiagnostics();
-      for (int stage = 1; stage <= ptlist->nstages; ++stage) ptlist->DoTaskListOneStage(pmesh, stage);
+      for (int stage = 1; stage <= ptlist->nstages; ++stage) {
+        // NEW_DT rides on the last stage's W(U) pass (same per-cell values, exact min)
+        if (stage == ptlist->nstages) AthkCheck(athk_request_block_dt(pmesh->athk), "main");
+        ptlist->DoTaskListOneStage(pmesh, stage);
+      }
       pmesh->ncycle++;
       pmesh->time += pmesh->dt;
       mbcnt += pmesh->nbtotal;

@@ -257,7 +257,7 @@ class TimeIntegrator:
         # cfl clamp, time_integrator.cpp:893-903
         self.cfl = min(cfl_number, cfl_limit)
         self.fused = fused
-        self.fold_dt = bool(int(os.environ.get("ATHK_FOLD_DT", "0")))
+        self.fold_dt = bool(int(os.environ.get("ATHK_FOLD_DT", "1")))
         self.time = 0.0
         self.dt = sys.float_info.max
         self.ncycle = 0
