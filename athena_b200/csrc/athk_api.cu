@@ -427,16 +427,23 @@ extern "C" int athk_request_block_dt(athk_ctx *c) {
   return ATHK_OK;
 }
 
-extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
+// part 0: whole box; 1: active zone only (needs no ghost data: can run under the inter-GPU ghost
+// transfer); 2: ghost shell only.
+static int cons2prim_part(athk_ctx *c, int reg, int part);
+extern "C" int athk_cons2prim(athk_ctx *c, int reg) { return cons2prim_part(c, reg, 0); }
+
+static int cons2prim_part(athk_ctx *c, int reg, int part) {
   NEED_READY(c);
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "cons2prim: register %d not allocated", reg);
   const int ns = c->cfg.nscalars;
   if (ns && !c->s[reg]) return fail(ATHK_ERR_ARG, "cons2prim: scalar register %d not allocated", reg);
   const Grid &g = c->g;
-  Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+  const Range3 rall = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
+  const Range3 rin = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
   Real *dt_out = nullptr;
-  c->dt_valid = false;
-  if (c->dt_requested) {
+  const bool fold = c->dt_requested && part != 2;   // the block dt is a property of the active zone
+  if (part != 2) c->dt_valid = false;
+  if (fold) {
     int rc = fill_dt_blocks(c);
     if (rc) return rc;
     dt_out = c->dt_blocks;
@@ -444,13 +451,17 @@ extern "C" int athk_cons2prim(athk_ctx *c, int reg) {
   if (c->cfg.mhd) {
     Cons2PrimPoint<true> f = {g, c->eos, c->u[reg], c->b[reg], c->w, c->bcc, c->nbr, dt_out, c->geo,
                               ns ? c->s[reg] : nullptr, c->r, ns};
-    LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+    if (part == 2) LAUNCH_NAMED(c, "athk_cons2prim", launch_shell(c->stream, g.nb, rall, rin, f));
+    else LAUNCH_NAMED(c, "athk_cons2prim",
+                      launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f));
   } else {
     Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo,
                                ns ? c->s[reg] : nullptr, c->r, ns};
-    LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+    if (part == 2) LAUNCH_NAMED(c, "athk_cons2prim", launch_shell(c->stream, g.nb, rall, rin, f));
+    else LAUNCH_NAMED(c, "athk_cons2prim",
+                      launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f));
   }
-  if (c->dt_requested) { c->dt_valid = true; c->dt_requested = false; }
+  if (fold) { c->dt_valid = true; c->dt_requested = false; }
   return ATHK_OK;
 }
 
@@ -477,15 +488,22 @@ extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int
   }
 }
 
-extern "C" int athk_compute_corner_e(athk_ctx *c) {
+// part 0: every edge; 1: the block's boundary surface only (what the EMF exchange needs);
+// 2: the rest.  1 + 2 == 0; the split lets the inter-GPU EMF transfer run under part 2.
+static int corner_e_part(athk_ctx *c, int part) {
   NEED_READY(c);
   if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "compute_corner_e: context is not MHD");
   const Grid &g = c->g;
-  Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  const Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
+  const Range3 rin = {g.ks + 1, g.ke, g.js + 1, g.je, g.is + 1, g.ie};
   CornerEPoint f = {g, c->w, c->bcc, c->ef, c->wct, c->e};
-  LAUNCH_NAMED(c, __func__, launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+  if (part == 1) LAUNCH_NAMED(c, "athk_compute_corner_e", launch_shell(c->stream, g.nb, r, rin, f));
+  else LAUNCH_NAMED(c, "athk_compute_corner_e",
+                    launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 2 ? rin : r, f));
   return ATHK_OK;
 }
+
+extern "C" int athk_compute_corner_e(athk_ctx *c) { return corner_e_part(c, 0); }
 
 extern "C" int athk_send_flux_correction(athk_ctx *c) {
   NEED_READY(c);
@@ -613,8 +631,15 @@ extern "C" int athk_ct(athk_ctx *c, double wght, int reg) {
   return ATHK_OK;
 }
 
+// mode 0: all neighbours; 1: neighbours on this GPU only; 2: received remote messages only
+static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode);
 extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
+  return exchange_ghosts_mode(c, what_mask, reg, 0);
+}
+
+static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode) {
   NEED_READY(c);
+  if (mode == 2 && c->rl.n == 0) return ATHK_OK;
   if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "exchange_ghosts: bad register");
   const Grid &g = c->g;
   const Range3 rin = {g.ks, g.ke, g.js, g.je, g.is, g.ie};   // only the ghost shell is launched
@@ -622,10 +647,10 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
     if (!c->u[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: u register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
-      GhostFillCC<true> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
+      GhostFillCC<true> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
-      GhostFillCC<false> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl};
+      GhostFillCC<false> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
@@ -633,10 +658,10 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
     if (!c->cfg.mhd || !c->b[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: b register %d not allocated", reg);
     Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
     if (c->rl.n > 0) {
-      GhostFillFC<true> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
+      GhostFillFC<true> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
-      GhostFillFC<false> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl};
+      GhostFillFC<false> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
@@ -644,10 +669,10 @@ extern "C" int athk_exchange_ghosts(athk_ctx *c, int what_mask, int reg) {
     if (!c->s[reg]) return fail(ATHK_ERR_ARG, "exchange_ghosts: s register %d not allocated", reg);
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
-      GhostFillCC<true> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
+      GhostFillCC<true> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     } else {
-      GhostFillCC<false> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl};
+      GhostFillCC<false> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl, mode};
       LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
@@ -966,7 +991,10 @@ extern "C" int athk_stage(athk_ctx *c, int stage, int order, const athk_stage_wg
 extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
                                 const athk_stage_wghts *sw, double dt_mesh) {
   NEED_READY(c);
-  if (phase < 0 || phase > 2) return fail(ATHK_ERR_ARG, "stage_phase: phase must be 0, 1 or 2");
+  const bool split = phase >= 10;   // 10,13,11,14,12: the same stage with two extra overlap windows
+  if (split) phase -= 10;
+  if (phase < 0 || phase > (split ? 4 : 2))
+    return fail(ATHK_ERR_ARG, "stage_phase: phase must be 0, 1, 2 (or 10, 13, 11, 14, 12)");
   if (!sw) return fail(ATHK_ERR_ARG, "stage: null weights");
   if (sw->gamma_3 != 0.0) return fail(ATHK_ERR_ARG, "stage: gamma_3 != 0 (3-register integrators) not implemented");
   { int rco = check_order(c, order, "stage"); if (rco) return rco; }
@@ -1012,11 +1040,17 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       if (swap) { Real *t = c->s[0]; c->s[0] = c->s[1]; c->s[1] = t; }
     }
     if (mhd) {
-      if ((rc = athk_compute_corner_e(c))) return rc;
+      if ((rc = corner_e_part(c, split ? 1 : 0))) return rc;
       if ((rc = athk_send_flux_correction(c))) return rc;
       if ((rc = athk_remote_pack_emf(c))) return rc;
     }
     return ATHK_OK;
+  }
+  if (phase == 3) return mhd ? corner_e_part(c, 2) : ATHK_OK;   // interior edges, under the EMF transfer
+  if (phase == 4) {   // under the ghost transfer: ghosts from same-GPU neighbours (they must see the
+                      // neighbour's U before W(U) floors it, as in the reference), then the active zone
+    if ((rc = exchange_ghosts_mode(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0, 1))) return rc;
+    return cons2prim_part(c, 0, 1);
   }
   if (phase == 1) {
     if (mhd) {
@@ -1035,8 +1069,8 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     }
     return athk_remote_pack_ghosts(c, 0);
   }
-  if ((rc = athk_exchange_ghosts(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0))) return rc;
-  if ((rc = athk_cons2prim(c, 0))) return rc;
+  if ((rc = exchange_ghosts_mode(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0, split ? 2 : 0))) return rc;
+  if ((rc = cons2prim_part(c, 0, split ? 2 : 0))) return rc;
   return athk_apply_physical_boundaries(c);   // PHY_BVAL (no-op without physical boundaries)
 }
 //----------------------------------------------------------------------------------------

@@ -624,6 +624,7 @@ struct GhostFillCC {
   const int *nbr;
   int mhd, nscal, section;   // section 0 = hydro u, 4 = scalars (remote message layout)
   RemoteLinks rl;
+  int mode;                  // 0 all neighbours, 1 same-GPU neighbours only, 2 remote links only
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const int o1 = (i < g.is) ? -1 : (i > g.ie ? 1 : 0);
     const int o2 = (j < g.js) ? -1 : (j > g.je ? 1 : 0);
@@ -633,10 +634,11 @@ struct GhostFillCC {
     if (id == -1) return;   // physical boundary
     const idx_t dst = gidx(g, k, j, i);
     if (id >= 0) {
+      if (mode == 2) return;
       const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
       for (int n = 0; n < nvar; ++n)
         u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
-    } else if (REMOTE) {
+    } else if (REMOTE && mode != 1) {
       const int link = -id - 2;
       const int os = nbr_slot(o1, o2, o3);
       const Slab cc = rl.tab->slab[os][0];
@@ -657,6 +659,7 @@ struct GhostFillFC {
   const int *nbr;
   int nscal;
   RemoteLinks rl;
+  int mode;         // as GhostFillCC
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -672,9 +675,10 @@ struct GhostFillFC {
       if (id == -1) continue;
       const idx_t dst = gidx(g, k, j, i);
       if (id >= 0) {
+        if (mode == 2) continue;
         const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
         b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
-      } else if (REMOTE) {
+      } else if (REMOTE && mode != 1) {
         const int link = -id - 2;
         const int os = nbr_slot(o1, o2, o3);
         const Slab f = rl.tab->slab[os][1 + d];

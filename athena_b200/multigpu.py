@@ -27,6 +27,8 @@ class RemoteExchange:
         self.rank = rank
         self.world = world
         self.stream = stream
+        self.comm_stream = None
+        self._pending = []
         lib, h = ctx.lib, ctx.h
         links = ctx.remote          # [(lb, (o1,o2,o3), remote gid, remote rank)], index = link id
         n = len(links)
@@ -78,9 +80,7 @@ class RemoteExchange:
         ctx.call("athk_remote_set_buffers", self.gsbuf.data_ptr(), self.grbuf.data_ptr(),
                  self.esbuf.data_ptr(), self.erbuf.data_ptr())
 
-    def _exchange(self, sbuf, rbuf, seg):
-        if not self.peers:
-            return
+    def _ops(self, sbuf, rbuf, seg):
         ops = []
         for p in self.peers:
             s0, s1, r0, r1 = seg[p]
@@ -88,6 +88,49 @@ class RemoteExchange:
                 ops.append(dist.P2POp(dist.isend, sbuf[s0:s1], p))
             if r1 > r0:
                 ops.append(dist.P2POp(dist.irecv, rbuf[r0:r1], p))
+        return ops
+
+    # Overlapped form: start_*() orders the transfers after the pack kernels already queued on the
+    # context's stream but runs them on a separate communication stream, so kernels queued on the
+    # context's stream afterwards (interior corner-E, interior W(U)) execute while the messages
+    # cross NVLink; finish_*() makes the context's stream wait for them before the unpack kernels.
+    def _start(self, sbuf, rbuf, seg):
+        ops = self._ops(sbuf, rbuf, seg) if self.peers else []
+        if not ops:
+            return
+        if self.stream is None:          # CPU tensors (gloo tests): synchronous
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=sbuf.device)
+        packed = torch.cuda.Event()
+        packed.record(self.stream)
+        self.comm_stream.wait_event(packed)
+        with torch.cuda.stream(self.comm_stream):
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self._pending.append(done)
+
+    def _finish(self):
+        for ev in self._pending:
+            self.stream.wait_event(ev)
+        self._pending = []
+
+    def start_ghosts(self):
+        self._start(self.gsbuf, self.grbuf, self.gseg)
+
+    def start_emf(self):
+        if self.ctx.mhd:
+            self._start(self.esbuf, self.erbuf, self.eseg)
+
+    finish_ghosts = _finish
+    finish_emf = _finish
+
+    def _exchange(self, sbuf, rbuf, seg):
+        ops = self._ops(sbuf, rbuf, seg) if self.peers else []
         if not ops:
             return
         if self.stream is not None:

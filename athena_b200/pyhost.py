@@ -258,6 +258,7 @@ class TimeIntegrator:
         self.cfl = min(cfl_number, cfl_limit)
         self.fused = fused
         self.fold_dt = bool(int(os.environ.get("ATHK_FOLD_DT", "1")))
+        self.overlap = bool(int(os.environ.get("ATHK_OVERLAP", "0")))
         self.time = 0.0
         self.dt = sys.float_info.max
         self.ncycle = 0
@@ -305,12 +306,23 @@ class TimeIntegrator:
             sw = capi.StageWghts(delta, g1, g2, g3, beta)
             if xch is None:
                 c.call("athk_stage", stage, order, C.byref(sw), dt)
-            else:
+            elif not self.overlap:
                 c.call("athk_stage_phase", 0, stage, order, C.byref(sw), dt)
                 xch.exchange_emf()
                 c.call("athk_stage_phase", 1, stage, order, C.byref(sw), dt)
                 xch.exchange_ghosts()
                 c.call("athk_stage_phase", 2, stage, order, C.byref(sw), dt)
+            else:
+                # the inter-GPU transfers fly under the interior corner-E and the interior W(U)
+                c.call("athk_stage_phase", 10, stage, order, C.byref(sw), dt)
+                xch.start_emf()
+                c.call("athk_stage_phase", 13, stage, order, C.byref(sw), dt)
+                xch.finish_emf()
+                c.call("athk_stage_phase", 11, stage, order, C.byref(sw), dt)
+                xch.start_ghosts()
+                c.call("athk_stage_phase", 14, stage, order, C.byref(sw), dt)
+                xch.finish_ghosts()
+                c.call("athk_stage_phase", 12, stage, order, C.byref(sw), dt)
             return
         if stage == 1:   # StartupTaskList, time_integrator.cpp:1608-1619
             c.call("athk_zero_register", 0, 1)

@@ -189,7 +189,11 @@ int athk_stage(athk_ctx *ctx, int stage, int order, const athk_stage_wghts *sw, 
  *   phase 0: sweeps, corner E, pack EMF surfaces (local + remote links)      -> send/recv EMF
  *   phase 1: EMF correction, CT, pack ghost messages of remote links         -> send/recv ghosts
  *   phase 2: ghost fill (local neighbours + received messages), W(U)
- * athk_stage == phases 0,1,2 back to back (single GPU, or no remote links). */
+ * athk_stage == phases 0,1,2 back to back (single GPU, or no remote links).
+ * Overlap variant 10, 13, 11, 14, 12 (same results): 10 computes corner E on the block surface
+ * only before packing, 13 the interior edges (runs while the EMF messages fly), 11 == 1, 14 is
+ * the ghost fill from same-GPU neighbours + W(U) on the active zone (runs while the ghost messages
+ * fly), 12 the ghost fill from the received messages + W(U) on the ghost shell. */
 int athk_stage_phase(athk_ctx *ctx, int phase, int stage, int order, const athk_stage_wghts *sw,
                      double dt_mesh);
 

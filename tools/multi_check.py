@@ -20,7 +20,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 lib = capi.load()
 meta, z = util.load_golden(name)
-mesh = pyhost.UniformMesh(meta["mesh"], meta["block"], meta["xmin"], meta["xmax"], ng=meta["ng"])
+mesh = pyhost.UniformMesh(meta["mesh"], meta["block"], meta["xmin"], meta["xmax"], ng=meta["ng"], bcs=meta.get("bcs"))
 nb = mesh.nbtotal
 per = nb // world
 parts = [list(range(r * per, (r + 1) * per if r < world - 1 else nb)) for r in range(world)]
