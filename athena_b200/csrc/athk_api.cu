@@ -648,10 +648,10 @@ static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode) {
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
       GhostFillCC<true> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillCC<false> f = {g, 5, c->u[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 0, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   if (what_mask & 2) {
@@ -659,10 +659,10 @@ static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode) {
     Range3 r = {0, g.nc3, 0, g.nc2, 0, g.nc1};
     if (c->rl.n > 0) {
       GhostFillFC<true> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillFC<false> f = {g, c->b[reg], c->nbr, c->cfg.nscalars, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   if (what_mask & 4) {
@@ -670,10 +670,10 @@ static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode) {
     Range3 r = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
     if (c->rl.n > 0) {
       GhostFillCC<true> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     } else {
       GhostFillCC<false> f = {g, c->cfg.nscalars, c->s[reg], c->nbr, c->cfg.mhd, c->cfg.nscalars, 4, c->rl, mode};
-      LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
+      LAUNCH_NAMED(c, "athk_exchange_ghosts", launch_shell(c->stream, g.nb, r, rin, f));
     }
   }
   return ATHK_OK;

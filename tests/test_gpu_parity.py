@@ -115,3 +115,56 @@ def test_cuda_fused_stage_wide_blocks_match_reference(cuda_lib, name):
     else:
         util.assert_matches_golden(meta, z, ctx, ti)
     ctx.close()
+
+
+def test_full_bench_size_properties_256cubed(cuda_lib):
+    """BASELINE's full single-GPU size (MHD blast, 256^3 zones in 64^3 MeshBlocks -- the bench
+    workload), checked through size-independent properties: the fused stage and the
+    operator-per-task sequence give the same bits, div(B) stays at machine zero under CT, mass and
+    total energy are conserved on the periodic mesh."""
+    import ctypes
+    from athena_b200 import problems, pyhost
+    gamma = 1.666666666667
+
+    def make():
+        mesh = pyhost.UniformMesh((256,) * 3, (64,) * 3, (-1.0,) * 3, (1.0,) * 3, ng=2)
+        ctx = pyhost.Context(mesh, True, gamma, lib=cuda_lib)
+        for lb, g in enumerate(ctx.gids):
+            ic = problems.blast_block(mesh, mesh.loc[g], True, gamma)
+            ctx.upload("U", lb, ic["u"])
+            ctx.upload("B_X1F", lb, ic["b1"])
+            ctx.upload("B_X2F", lb, ic["b2"])
+            ctx.upload("B_X3F", lb, ic["b3"])
+        return mesh, ctx
+
+    def sums(ctx):
+        s = (ctypes.c_double * 11)()
+        ctx.call("athk_history", s, 11)
+        return np.array(s[:])
+
+    out = {}
+    for fused in (True, False):
+        mesh, ctx = make()
+        ti = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=fused)
+        ti.initialize()
+        h0 = sums(ctx)
+        for _ in range(3):
+            ti.step()
+        h1 = sums(ctx)
+        ng, dx = 2, 2.0 / 256
+        divmax = 0.0
+        for lb in (0, 21, 42, 63):   # a sample of MeshBlocks, the blast centre among them
+            b1, b2, b3 = (ctx.download(n, lb) for n in ("B_X1F", "B_X2F", "B_X3F"))
+            s = slice(ng, ng + 64)
+            div = ((b1[s, s, ng + 1:ng + 65] - b1[s, s, ng:ng + 64]) + (b2[s, ng + 1:ng + 65, s] - b2[s, ng:ng + 64, s])
+                   + (b3[ng + 1:ng + 65, s, s] - b3[ng:ng + 64, s, s]))
+            divmax = max(divmax, np.abs(div).max())
+        out[fused] = (h1, ti.dt, [ctx.download("U", lb) for lb in (0, 42)])
+        assert divmax < 1e-13, divmax                       # |B| = 1: a few ulp per CT update
+        assert abs(h1[0] - h0[0]) < 1e-13 * h0[0]           # mass
+        assert abs(h1[7] - h0[7]) < 1e-13 * h0[7]           # total energy
+        ctx.close()
+    assert out[True][1] == out[False][1]
+    np.testing.assert_array_equal(out[True][0], out[False][0])
+    for a, b in zip(out[True][2], out[False][2]):
+        np.testing.assert_array_equal(a, b)
