@@ -147,6 +147,8 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->h_bcflags.assign((size_t)g.nb * 6, 0);
   c->bcflags = nullptr;
   c->bc_dirty = false;
+  c->stage = nullptr;
+  c->stage_count = 0;
   for (int f = 0; f < 6; ++f) c->bc_any[f] = 0;
   CU(cudaStreamSynchronize(st));
   *out = c;
@@ -159,6 +161,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
   cudaFree(c->bcflags);
+  cudaFree(c->stage);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
@@ -308,6 +311,30 @@ static bool describe(athk_ctx *c, int array, ArrDesc *d) {
   return d->base != nullptr && d->nvar > 0;
 }
 
+// Host <-> device copies of one array of one MeshBlock.  The host side is AthenaArray's dense
+// layout, the device side the padded box: a strided cudaMemcpy3D moves 544-byte rows and reaches
+// only ~10 GB/s over PCIe, so the copy goes through a dense device staging buffer instead -- one
+// contiguous cudaMemcpyAsync at full PCIe rate plus a (microseconds) scatter / gather kernel.
+// Everything is ordered on the context's stream, which also serialises the reuse of the buffer.
+#ifndef ATHK_EMULATE
+__global__ void __launch_bounds__(256) k_stage_copy(Real *dev, Real *dense, int nvar, int n1, int n2, int n3,
+                                                    idx_t sn, idx_t sk, idx_t sj, int to_device) {
+  const long long total = (long long)nvar * n3 * n2 * n1;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(q % n1);
+    long long t = q / n1;
+    const int j = (int)(t % n2);
+    t /= n2;
+    const int k = (int)(t % n3);
+    const int n = (int)(t / n3);
+    Real *d = dev + (idx_t)n * sn + (idx_t)k * sk + (idx_t)j * sj + i;
+    if (to_device) *d = dense[q];
+    else dense[q] = *d;
+  }
+}
+#endif
+
 static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_device,
                       bool sync_after = true) {
   if (!c || !host) return fail(ATHK_ERR_ARG, "upload/download: null argument");
@@ -317,20 +344,31 @@ static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_devi
     return fail(ATHK_ERR_ARG, "upload/download: array %d not allocated in this configuration", array);
   const Grid &g = c->g;
   const int n1 = g.nc1 + d.a1, n2 = g.nc2 + d.a2, n3 = g.nc3 + d.a3;
-  for (int n = 0; n < d.nvar; ++n) {
-    Real *dev = d.base + ((idx_t)lb * d.ncomp_total + d.comp0 + n) * g.sn;
-    double *h = host + (size_t)n * n3 * n2 * n1;
+  Real *dev0 = d.base + ((idx_t)lb * d.ncomp_total + d.comp0) * g.sn;
 #ifndef ATHK_EMULATE
-    cudaMemcpy3DParms p;
-    memset(&p, 0, sizeof(p));
-    cudaPitchedPtr hp = make_cudaPitchedPtr((void *)h, (size_t)n1 * sizeof(Real), n1, n2);
-    cudaPitchedPtr dp = make_cudaPitchedPtr((void *)dev, (size_t)g.P1 * sizeof(Real), g.P1, g.P2);
-    p.srcPtr = to_device ? hp : dp;
-    p.dstPtr = to_device ? dp : hp;
-    p.extent = make_cudaExtent((size_t)n1 * sizeof(Real), n2, n3);
-    p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    CU(cudaMemcpy3DAsync(&p, c->stream));
+  const size_t count = (size_t)d.nvar * n3 * n2 * n1;
+  if (count > c->stage_count) {
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_count = 0;
+    CU(cudaMalloc((void **)&c->stage, count * sizeof(Real)));
+    c->stage_count = count;
+  }
+  const int blocks = (int)((count + 255) / 256 < 148 * 16 ? (count + 255) / 256 : 148 * 16);
+  if (to_device) {
+    CU(cudaMemcpyAsync(c->stage, host, count * sizeof(Real), cudaMemcpyHostToDevice, c->stream));
+    k_stage_copy<<<blocks, 256, 0, c->stream>>>(dev0, c->stage, d.nvar, n1, n2, n3, g.sn, g.sk, g.sj, 1);
+    CU(cudaGetLastError());
+  } else {
+    k_stage_copy<<<blocks, 256, 0, c->stream>>>(dev0, c->stage, d.nvar, n1, n2, n3, g.sn, g.sk, g.sj, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, c->stage, count * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+  }
 #else
+  for (int n = 0; n < d.nvar; ++n) {
+    Real *dev = dev0 + (idx_t)n * g.sn;
+    double *h = host + (size_t)n * n3 * n2 * n1;
     for (int k = 0; k < n3; ++k)
       for (int j = 0; j < n2; ++j) {
         Real *dr = dev + gidx(g, k, j, 0);
@@ -338,8 +376,8 @@ static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_devi
         if (to_device) memcpy(dr, hr, n1 * sizeof(Real));
         else memcpy(hr, dr, n1 * sizeof(Real));
       }
-#endif
   }
+#endif
   if (!to_device && sync_after) CU(cudaStreamSynchronize(c->stream));
   return ATHK_OK;
 }

@@ -75,6 +75,8 @@ struct athk_ctx {
   int *nbr;         // [nb][27]
   Real *dt_blocks;  // [nb]
   std::vector<int> h_nbr;
+  Real *stage;                  // dense device staging buffer of athk_upload / athk_download
+  size_t stage_count;
   // physical boundaries: block_bcs per local block (enum athk_bc), device copy uploaded lazily
   std::vector<int> h_bcflags;   // [nb][6]
   int *bcflags;                 // device
