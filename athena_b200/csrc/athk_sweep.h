@@ -307,9 +307,12 @@ struct SweepX1 {
 #pragma unroll
     for (int v = 0; v < 5; ++v) {
       const idx_t o = ((idx_t)blk * 5 + v) * g.sn + c;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d2 + o));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d3 + o));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(ureg + o));
+#ifndef ATHK_X1_PF
+#define ATHK_X1_PF "prefetch.global.L2 [%0];"
+#endif
+      asm volatile(ATHK_X1_PF ::"l"(a.d2 + o));
+      asm volatile(ATHK_X1_PF ::"l"(a.d3 + o));
+      asm volatile(ATHK_X1_PF ::"l"(ureg + o));
     }
 #endif
   }

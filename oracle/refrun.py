@@ -311,6 +311,16 @@ def blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.02, integrator="v
     return set_bcs(b, bcs)
 
 
+def ot_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.05, integrator="vl2", xorder=2, cfl=0.3, rst_dt=None):
+    """athinput for pgen/orszag_tang.cpp (inputs/mhd/athinput.orszag-tang), extruded along x3."""
+    b = kh_blocks(mesh=mesh, block=block, tlim=tlim, integrator=integrator, xorder=xorder, cfl=cfl, rst_dt=rst_dt)
+    b["job"]["problem_id"] = "OrszagTang"
+    b["mesh"].update(x1min=-0.5, x1max=0.5, x2min=-0.5, x2max=0.5)
+    b["hydro"] = {"gamma": 1.666666667, "iso_sound_speed": 1.0}
+    b["problem"] = {}
+    return b
+
+
 def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, bcs=None, **kw):
     """athinput for pgen/shock_tube.cpp on the linear-wave test box (periodic, so the two
     discontinuities interact across the seam).  left/right = (d, u, v, w, p[, by, bz]) in the

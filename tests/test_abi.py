@@ -52,3 +52,28 @@ def test_bad_arguments_are_rejected(emul_lib):
         cfg = capi.Config(**base)
         assert lib.athk_create(ctypes.byref(cfg), ctypes.byref(h)) == -1, kw
         assert lib.athk_last_error()
+
+
+def test_operator_argument_checks(emul_lib):
+    """Error behaviour of the operator entry points (host logic, exercised on the test-only host
+    build): wrong order / missing scalars / bad boundary flags return ATHK_ERR_* with a message,
+    the way the reference's constructors raise ATHENA_ERROR (reconstruction.cpp:117-127)."""
+    from athena_b200 import pyhost
+    lib = emul_lib
+    mesh = pyhost.UniformMesh((8, 8, 8), (8, 8, 8), (0.0,) * 3, (1.0,) * 3, ng=2)
+    ctx = pyhost.Context(mesh, False, 1.4, lib=lib)
+    h = ctx.h
+    assert lib.athk_calculate_fluxes(h, 3, 0.1, 0) == -1 and b"nghost >= 3" in lib.athk_last_error()   # PPM needs 3 ghosts
+    assert lib.athk_calculate_fluxes(h, 4, 0.1, 0) == -1
+    assert lib.athk_calculate_scalar_fluxes(h, 2) == -1 and b"no passive scalars" in lib.athk_last_error()
+    assert lib.athk_add_scalar_flux_divergence(h, 0.1, 0) == -1
+    assert lib.athk_compute_corner_e(h) == -1 and b"not MHD" in lib.athk_last_error()
+    bad = (ctypes.c_int * 6)(0, 0, 7, 0, 0, 0)
+    assert lib.athk_set_boundary_flags(h, 0, bad) == -1 and b"unknown flag" in lib.athk_last_error()
+    assert lib.athk_set_boundary_flags(h, 5, (ctypes.c_int * 6)()) == -1
+    # a face flagged as a physical boundary must not have a neighbour in the table
+    assert lib.athk_set_boundary_flags(h, 0, (ctypes.c_int * 6)(2, 0, 0, 0, 0, 0)) == 0
+    assert lib.athk_apply_physical_boundaries(h) == -4 and b"has a neighbour" in lib.athk_last_error()
+    sums = (ctypes.c_double * 4)()
+    assert lib.athk_history(h, sums, 4) == -1 and b"need room" in lib.athk_last_error()
+    ctx.close()

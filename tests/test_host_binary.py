@@ -72,6 +72,9 @@ CASES = {
     "mhd_blast_reflecting_box": ("blast_mhd_hlld", "blast", True,
                                  lambda: refrun.blast_blocks(tlim=0.06, rst_dt=0.03, bcs=["reflecting"] * 6,
                                                              center=(0.6, 0.55, 0.5), radius=0.3)),
+    # BASELINE configs[2] names Orszag-Tang next to the blast wave
+    "orszag_tang_rk2": ("ot_mhd_hlld", "orszag_tang", True,
+                        lambda: refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk2")),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
