@@ -14,7 +14,11 @@ Reference sources followed (file:line under /root/reference/src):
   eos/adiabatic_hydro.cpp:38-80, eos/adiabatic_mhd.cpp:41-90,149-156   cons2prim, sound/fast speed
   field/field.cpp:112-180                                              cell-centred field
   reconstruct/dc.cpp:24-110, reconstruct/plm.cpp:27-175                donor cell, PLM (van Leer)
+  reconstruct/ppm.cpp:44-342, reconstruct/reconstruction.cpp:486-505   PPM (uniform Cartesian, CS limiter)
+  scalars/calculate_scalar_fluxes.cpp:41-417, add_scalar_flux_divergence.cpp:42-96,
+  eos/eos_scalars.cpp:31-60,161-173                                    passive scalars
   hydro/rsolvers/hydro/hllc.cpp:32-179, hydro/rsolvers/mhd/hlld.cpp:36-376
+  hydro/rsolvers/hydro/{hlle,llf,roe}.cpp, hydro/rsolvers/mhd/{hlle_mhd,llf_mhd}.cpp   alternative solvers
   hydro/hydro.cpp:154-158                                              CT weight
   hydro/calculate_fluxes.cpp:38-415                                    sweeps, rotations
   field/calculate_corner_e.cpp:130-229, field/ct.cpp:31-116            corner EMF, CT
@@ -184,6 +188,66 @@ def fast_speed(gamma, d, p, by, bz, bx):   # adiabatic_mhd.cpp:149-156
     return np.sqrt(0.5 * (qsq + np.sqrt(tmp * tmp + 4.0 * asq * ct2)) / d)
 
 
+def sign(x):   # SIGN() of defs.hpp.in:150
+    return np.where(x < 0.0, -1.0, 1.0)
+
+
+def ppm_cell(q, d):
+    """PPM of one variable in every cell: (ql_iph, qr_imh) = left state of the cell's upper face,
+    right state of its lower face.  Uniform Cartesian branch of ppm.cpp:107-320 with the weights
+    of reconstruction.cpp:494-505 and the extremum-preserving CS limiter (C2 = 1.25)."""
+    C2 = 1.25
+    c1 = c2 = c3 = c4 = 0.5
+    c5, c6 = 1.0 / 6.0, -1.0 / 6.0
+    q_im2, q_im1, q_ip1, q_ip2 = sh(q, d, -2), sh(q, d, -1), sh(q, d, 1), sh(q, d, 2)
+    qa = (q - q_im1)
+    qb = (q_ip1 - q)
+    dd_im1 = c1 * qa + c2 * (q_im1 - q_im2)
+    dd = c1 * qb + c2 * qa
+    dd_ip1 = c1 * (q_ip2 - q_ip1) + c2 * qb
+    dph = (c3 * q_im1 + c4 * q) + (c5 * dd_im1 + c6 * dd)                       # ppm.cpp:124-127
+    dph_ip1 = (c3 * q + c4 * q_ip1) + (c5 * dd + c6 * dd_ip1)
+    d2qc_im1 = q_im2 + q - 2.0 * q_im1                                         # :142-146
+    d2qc = q_im1 + q_ip1 - 2.0 * q
+    d2qc_ip1 = q + q_ip2 - 2.0 * q_ip1
+
+    def face_limit(dph_x, q_lo, q_hi, qb_, qc_):                               # :149-189
+        qa_tmp = dph_x - q_lo
+        qb_tmp = q_hi - dph_x
+        qa_ = 3.0 * (q_lo + q_hi - 2.0 * dph_x)
+        same = (sign(qa_) == sign(qb_)) & (sign(qa_) == sign(qc_))
+        qd = np.where(same, sign(qa_) * np.minimum(C2 * np.abs(qb_), np.minimum(C2 * np.abs(qc_), np.abs(qa_))), 0.0)
+        tmp = 0.5 * (q_lo + q_hi) - qd / 6.0
+        return np.where(qa_tmp * qb_tmp < 0.0, tmp, dph_x)
+
+    dph = face_limit(dph, q_im1, q, d2qc_im1, d2qc)
+    dph_ip1 = face_limit(dph_ip1, q, q_ip1, d2qc, d2qc_ip1)
+    d2qf = 6.0 * (dph + dph_ip1 - 2.0 * q)                                     # :192-194
+    qminus, qplus = dph, dph_ip1
+    dqf_minus = q - qminus                                                      # :218-222
+    dqf_plus = qplus - q
+    qa_tmp = dqf_minus * dqf_plus                                               # :226-279
+    qb_tmp = (q_ip1 - q) * (q - q_im1)
+    qa, qb, qc, qd = d2qc_im1, d2qc, d2qc_ip1, d2qf
+    same = (sign(qa) == sign(qb)) & (sign(qa) == sign(qc)) & (sign(qa) == sign(qd))
+    qe = np.where(same, sign(qd) * np.minimum(np.minimum(C2 * np.abs(qa), C2 * np.abs(qb)),
+                                               np.minimum(C2 * np.abs(qc), np.abs(qd))), 0.0)
+    qa = np.maximum(np.abs(q_im1), np.abs(q_im2))
+    qb = np.maximum(np.maximum(np.abs(q), np.abs(q_ip1)), np.abs(q_ip2))
+    rho = np.where(np.abs(qd) > (1.0e-12) * np.maximum(qa, qb), qe / qd, 0.0)
+    tmp_m = q - rho * dqf_minus
+    tmp_p = q + rho * dqf_plus
+    tmp2_m = q - 2.0 * dqf_plus
+    tmp2_p = q + 2.0 * dqf_minus
+    extremum = (qa_tmp <= 0.0) | (qb_tmp <= 0.0)
+    smooth = rho <= (1.0 - (1.0e-12))
+    over_m = np.abs(dqf_minus) >= 2.0 * np.abs(dqf_plus)
+    over_p = np.abs(dqf_plus) >= 2.0 * np.abs(dqf_minus)
+    qminus_n = np.where(extremum, np.where(smooth, tmp_m, qminus), np.where(over_m, tmp2_m, qminus))
+    qplus_n = np.where(extremum, np.where(smooth, tmp_p, qplus), np.where(over_p, tmp2_p, qplus))
+    return qplus_n, qminus_n
+
+
 def reconstruct(q, d, order, mesh):
     """q: list of (k,j,i) arrays. Returns (wl, wr) at face n (between cells n-1 and n)."""
     wl, wr = [], []
@@ -193,6 +257,8 @@ def reconstruct(q, d, order, mesh):
         for a in q:
             if order == 1:
                 up, lo = a, a
+            elif order == 3:
+                up, lo = ppm_cell(a, d)
             else:
                 dwl = a - sh(a, d, -1)
                 dwr = sh(a, d, 1) - a
@@ -246,6 +312,196 @@ def hllc(wl, wr, gamma):   # hllc.cpp:53-175
         f[IVX] = sl * fl[IVX] + sr * fr[IVX] + sm * cp
         f[IEN] = sl * fl[IEN] + sr * fr[IEN] + sm * cp * am
     return f
+
+
+def _sq(x):
+    return x * x
+
+
+def hlle_hydro(wl, wr, gamma):   # hydro/rsolvers/hydro/hlle.cpp:53-160
+    gm1 = gamma - 1.0
+    igm1 = 1.0 / gm1
+    with np.errstate(all="ignore"):
+        sqrtdl, sqrtdr = np.sqrt(wl[IDN]), np.sqrt(wr[IDN])
+        isdlpdr = 1.0 / (sqrtdl + sqrtdr)
+        vroe = [(sqrtdl * wl[v] + sqrtdr * wr[v]) * isdlpdr for v in (IVX, IVY, IVZ)]
+        el = wl[IPR] * igm1 + 0.5 * wl[IDN] * (_sq(wl[IVX]) + _sq(wl[IVY]) + _sq(wl[IVZ]))
+        er = wr[IPR] * igm1 + 0.5 * wr[IDN] * (_sq(wr[IVX]) + _sq(wr[IVY]) + _sq(wr[IVZ]))
+        hroe = ((el + wl[IPR]) / sqrtdl + (er + wr[IPR]) / sqrtdr) * isdlpdr
+        cl = np.sqrt(gamma * wl[IPR] / wl[IDN])
+        cr = np.sqrt(gamma * wr[IPR] / wr[IDN])
+        q = hroe - 0.5 * (_sq(vroe[0]) + _sq(vroe[1]) + _sq(vroe[2]))
+        a = np.where(q < 0.0, 0.0, np.sqrt(gm1 * q))
+        al = np.minimum((vroe[0] - a), (wl[IVX] - cl))
+        ar = np.maximum((vroe[0] + a), (wr[IVX] + cr))
+        bp = np.where(ar > 0.0, ar, 0.0)
+        bm = np.where(al < 0.0, al, 0.0)
+        vxl = wl[IVX] - bm
+        vxr = wr[IVX] - bp
+        fl = [wl[IDN] * vxl, wl[IDN] * wl[IVX] * vxl + wl[IPR], wl[IDN] * wl[IVY] * vxl,
+              wl[IDN] * wl[IVZ] * vxl, el * vxl + wl[IPR] * wl[IVX]]
+        fr = [wr[IDN] * vxr, wr[IDN] * wr[IVX] * vxr + wr[IPR], wr[IDN] * wr[IVY] * vxr,
+              wr[IDN] * wr[IVZ] * vxr, er * vxr + wr[IPR] * wr[IVX]]
+        tmp = np.where(bp != bm, 0.5 * (bp + bm) / (bp - bm), 0.0)
+        return [0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp for n in range(5)]
+
+
+def _hydro_lr(wl, wr, gamma):
+    """physical fluxes and conserved jump shared by llf.cpp:72-112 and roe.cpp:86-121"""
+    gm1 = gamma - 1.0
+    mxl, mxr = wl[IDN] * wl[IVX], wr[IDN] * wr[IVX]
+    el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (_sq(wl[IVX]) + _sq(wl[IVY]) + _sq(wl[IVZ]))
+    er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (_sq(wr[IVX]) + _sq(wr[IVY]) + _sq(wr[IVZ]))
+    fl = [mxl, mxl * wl[IVX] + wl[IPR], mxl * wl[IVY], mxl * wl[IVZ], (el + wl[IPR]) * wl[IVX]]
+    fr = [mxr, mxr * wr[IVX] + wr[IPR], mxr * wr[IVY], mxr * wr[IVZ], (er + wr[IPR]) * wr[IVX]]
+    du = [wr[IDN] - wl[IDN], wr[IDN] * wr[IVX] - wl[IDN] * wl[IVX], wr[IDN] * wr[IVY] - wl[IDN] * wl[IVY],
+          wr[IDN] * wr[IVZ] - wl[IDN] * wl[IVZ], er - el]
+    return fl, fr, du, el, er
+
+
+def llf_hydro(wl, wr, gamma):   # hydro/rsolvers/hydro/llf.cpp:58-121
+    with np.errstate(all="ignore"):
+        cl = np.sqrt(gamma * wl[IPR] / wl[IDN])
+        cr = np.sqrt(gamma * wr[IPR] / wr[IDN])
+        a = 0.5 * np.maximum((np.abs(wl[IVX]) + cl), (np.abs(wr[IVX]) + cr))
+        fl, fr, du, _, _ = _hydro_lr(wl, wr, gamma)
+        return [0.5 * (fl[n] + fr[n]) - a * du[n] for n in range(5)]
+
+
+def roe_hydro(wl, wr, gamma):   # hydro/rsolvers/hydro/roe.cpp:72-175 + RoeFlux :213-300
+    gm1 = gamma - 1.0
+    with np.errstate(all="ignore"):
+        sqrtdl, sqrtdr = np.sqrt(wl[IDN]), np.sqrt(wr[IDN])
+        isdlpdr = 1.0 / (sqrtdl + sqrtdr)
+        v1, v2, v3 = [(sqrtdl * wl[v] + sqrtdr * wr[v]) * isdlpdr for v in (IVX, IVY, IVZ)]
+        fl, fr, du, el, er = _hydro_lr(wl, wr, gamma)
+        h = ((el + wl[IPR]) / sqrtdl + (er + wr[IPR]) / sqrtdr) * isdlpdr
+        flx = [0.5 * (fl[n] + fr[n]) for n in range(5)]
+        vsq = v1 * v1 + v2 * v2 + v3 * v3
+        q = h - 0.5 * vsq
+        cs_sq = np.where(q < 0.0, TINY_NUMBER, gm1 * q)
+        cs = np.sqrt(cs_sq)
+        ev = [v1 - cs, v1, v1, v1, v1 + cs]
+        na = 0.5 / cs_sq
+        a0 = du[0] * (0.5 * gm1 * vsq + v1 * cs)
+        a0 = a0 - du[1] * (gm1 * v1 + cs)
+        a0 = a0 - du[2] * gm1 * v2
+        a0 = a0 - du[3] * gm1 * v3
+        a0 = a0 + du[4] * gm1
+        a0 = a0 * na
+        a1 = du[0] * (-v2)
+        a1 = a1 + du[2]
+        a2 = du[0] * (-v3)
+        a2 = a2 + du[3]
+        qa = gm1 / cs_sq
+        a3 = du[0] * (1.0 - na * gm1 * vsq)
+        a3 = a3 + du[1] * qa * v1
+        a3 = a3 + du[2] * qa * v2
+        a3 = a3 + du[3] * qa * v3
+        a3 = a3 - du[4] * qa
+        a4 = du[0] * (0.5 * gm1 * vsq - v1 * cs)
+        a4 = a4 - du[1] * (gm1 * v1 - cs)
+        a4 = a4 - du[2] * gm1 * v2
+        a4 = a4 - du[3] * gm1 * v3
+        a4 = a4 + du[4] * gm1
+        a4 = a4 * na
+        a = [a0, a1, a2, a3, a4]
+        coeff = [-0.5 * np.abs(ev[n]) * a[n] for n in range(5)]
+        dens = wl[IDN] + a[0]
+        llf = dens < 0.0
+        dens = dens + a[3]
+        llf = llf | (dens < 0.0)
+        flx[0] = ((flx[0] + coeff[0]) + coeff[3]) + coeff[4]
+        flx[1] = ((flx[1] + coeff[0] * (v1 - cs)) + coeff[3] * v1) + coeff[4] * (v1 + cs)
+        flx[2] = (((flx[2] + coeff[0] * v2) + coeff[1]) + coeff[3] * v2) + coeff[4] * v2
+        flx[3] = (((flx[3] + coeff[0] * v3) + coeff[2]) + coeff[3] * v3) + coeff[4] * v3
+        flx[4] = ((((flx[4] + coeff[0] * (h - v1 * cs)) + coeff[1] * v2) + coeff[2] * v3)
+                  + coeff[3] * 0.5 * vsq) + coeff[4] * (h + v1 * cs)
+        flx = [np.where(ev[0] >= 0.0, fl[n], flx[n]) for n in range(5)]
+        flx = [np.where(ev[4] <= 0.0, fr[n], flx[n]) for n in range(5)]
+        cl = np.sqrt(gamma * wl[IPR] / wl[IDN])
+        cr = np.sqrt(gamma * wr[IPR] / wr[IDN])
+        al = 0.5 * np.maximum((np.abs(wl[IVX]) + cl), (np.abs(wr[IVX]) + cr))
+        return [np.where(llf, 0.5 * (fl[n] + fr[n]) - al * du[n], flx[n]) for n in range(5)]
+
+
+def _mhd_lr(wl, wr, bxi, gamma):
+    """llf_mhd.cpp:78-125 == roe_mhd.cpp:108-160: physical fluxes, conserved jump"""
+    gm1 = gamma - 1.0
+    mxl, mxr = wl[IDN] * wl[IVX], wr[IDN] * wr[IVX]
+    pbl = 0.5 * (bxi * bxi + _sq(wl[IBY]) + _sq(wl[IBZ]))
+    pbr = 0.5 * (bxi * bxi + _sq(wr[IBY]) + _sq(wr[IBZ]))
+    el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (_sq(wl[IVX]) + _sq(wl[IVY]) + _sq(wl[IVZ])) + pbl
+    er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (_sq(wr[IVX]) + _sq(wr[IVY]) + _sq(wr[IVZ])) + pbr
+    fl = [mxl, mxl * wl[IVX] + pbl - _sq(bxi) + wl[IPR], mxl * wl[IVY] - bxi * wl[IBY], mxl * wl[IVZ] - bxi * wl[IBZ],
+          (el + wl[IPR] + pbl - bxi * bxi) * wl[IVX] - bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]),
+          wl[IBY] * wl[IVX] - bxi * wl[IVY], wl[IBZ] * wl[IVX] - bxi * wl[IVZ]]
+    fr = [mxr, mxr * wr[IVX] + pbr - _sq(bxi) + wr[IPR], mxr * wr[IVY] - bxi * wr[IBY], mxr * wr[IVZ] - bxi * wr[IBZ],
+          (er + wr[IPR] + pbr - bxi * bxi) * wr[IVX] - bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]),
+          wr[IBY] * wr[IVX] - bxi * wr[IVY], wr[IBZ] * wr[IVX] - bxi * wr[IVZ]]
+    du = [wr[IDN] - wl[IDN], wr[IDN] * wr[IVX] - wl[IDN] * wl[IVX], wr[IDN] * wr[IVY] - wl[IDN] * wl[IVY],
+          wr[IDN] * wr[IVZ] - wl[IDN] * wl[IVZ], er - el, wr[IBY] - wl[IBY], wr[IBZ] - wl[IBZ]]
+    return fl, fr, du
+
+
+def llf_mhd(wl, wr, bxi, gamma):   # hydro/rsolvers/mhd/llf_mhd.cpp:72-148
+    with np.errstate(all="ignore"):
+        cfl = fast_speed(gamma, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi)
+        cfr = fast_speed(gamma, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi)
+        a = 0.5 * np.maximum((np.abs(wl[IVX]) + cfl), (np.abs(wr[IVX]) + cfr))
+        fl, fr, du = _mhd_lr(wl, wr, bxi, gamma)
+        return [0.5 * (fl[n] + fr[n]) - a * du[n] for n in range(7)]
+
+
+def hlle_mhd(wl, wr, bxi, gamma):   # hydro/rsolvers/mhd/hlle_mhd.cpp:63-170
+    gm1 = gamma - 1.0
+    with np.errstate(all="ignore"):
+        sqrtdl, sqrtdr = np.sqrt(wl[IDN]), np.sqrt(wr[IDN])
+        isdlpdr = 1.0 / (sqrtdl + sqrtdr)
+        d = sqrtdl * sqrtdr
+        v1, v2, v3 = [(sqrtdl * wl[v] + sqrtdr * wr[v]) * isdlpdr for v in (IVX, IVY, IVZ)]
+        b2 = (sqrtdr * wl[IBY] + sqrtdl * wr[IBY]) * isdlpdr
+        b3 = (sqrtdr * wl[IBZ] + sqrtdl * wr[IBZ]) * isdlpdr
+        x = 0.5 * (_sq(wl[IBY] - wr[IBY]) + _sq(wl[IBZ] - wr[IBZ])) / (_sq(sqrtdl + sqrtdr))
+        y = 0.5 * (wl[IDN] + wr[IDN]) / d
+        pbl = 0.5 * (bxi * bxi + _sq(wl[IBY]) + _sq(wl[IBZ]))
+        pbr = 0.5 * (bxi * bxi + _sq(wr[IBY]) + _sq(wr[IBZ]))
+        el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (_sq(wl[IVX]) + _sq(wl[IVY]) + _sq(wl[IVZ])) + pbl
+        er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (_sq(wr[IVX]) + _sq(wr[IVY]) + _sq(wr[IVZ])) + pbr
+        hroe = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr
+        cl = fast_speed(gamma, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi)
+        cr = fast_speed(gamma, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi)
+        btsq = _sq(b2) + _sq(b3)
+        vaxsq = bxi * bxi / d
+        bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq
+        hp = hroe - (vaxsq + btsq / d)
+        vsq = _sq(v1) + _sq(v2) + _sq(v3)
+        twid_asq = np.maximum((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 0.0)
+        ct2 = bt_starsq / d
+        tsum = vaxsq + ct2 + twid_asq
+        tdif = vaxsq + ct2 - twid_asq
+        cf2_cs2 = np.sqrt(tdif * tdif + 4.0 * twid_asq * ct2)
+        a = np.sqrt(0.5 * (tsum + cf2_cs2))
+        al = np.minimum((v1 - a), (wl[IVX] - cl))
+        ar = np.maximum((v1 + a), (wr[IVX] + cr))
+        bp = np.where(ar > 0.0, ar, 0.0)
+        bm = np.where(al < 0.0, al, 0.0)
+        vxl = wl[IVX] - bm
+        vxr = wr[IVX] - bp
+        fl = [wl[IDN] * vxl, wl[IDN] * wl[IVX] * vxl + pbl - _sq(bxi) + wl[IPR],
+              wl[IDN] * wl[IVY] * vxl - bxi * wl[IBY], wl[IDN] * wl[IVZ] * vxl - bxi * wl[IBZ],
+              el * vxl + wl[IVX] * (wl[IPR] + pbl - bxi * bxi) - bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]),
+              wl[IBY] * vxl - bxi * wl[IVY], wl[IBZ] * vxl - bxi * wl[IVZ]]
+        fr = [wr[IDN] * vxr, wr[IDN] * wr[IVX] * vxr + pbr - _sq(bxi) + wr[IPR],
+              wr[IDN] * wr[IVY] * vxr - bxi * wr[IBY], wr[IDN] * wr[IVZ] * vxr - bxi * wr[IBZ],
+              er * vxr + wr[IVX] * (wr[IPR] + pbr - bxi * bxi) - bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]),
+              wr[IBY] * vxr - bxi * wr[IVY], wr[IBZ] * vxr - bxi * wr[IVZ]]
+        tmp = np.where(bp != bm, 0.5 * (bp + bm) / (bp - bm), 0.0)
+        return [0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp for n in range(7)]
+
+
+HYDRO_SOLVERS = {"hllc": None, "hlle": hlle_hydro, "llf": llf_hydro, "roe": roe_hydro}
+MHD_SOLVERS = {"hlld": None, "hlle": hlle_mhd, "llf": llf_mhd}   # (Roe MHD is not restated here)
 
 
 def hlld(wl, wr, bxi, gamma):   # hlld.cpp:56-365 ; returns 7 flux components
@@ -358,17 +614,27 @@ class State:
     direction (the faces on the periodic seam are distinct arrays entries, as in the reference
     where each MeshBlock keeps its own copy of a shared face)."""
 
-    def __init__(self, mesh, gamma, u, b=None):
+    def __init__(self, mesh, gamma, u, b=None, s=None, flux=None):
         self.mesh, self.gamma = mesh, gamma
+        self.flux = flux   # None = hllc / hlld; "hlle", "llf", "roe" (hydro)
         self.mhd = b is not None
         self.u = mesh.fill_ghosts_cc(mesh.pad_cc(u))
         self.b = [mesh.fill_ghosts_fc(mesh.pad_fc(b[d], d), d) for d in range(3)] if self.mhd else None
+        # passive scalars: conserved s = r*rho (NSCALARS, ...), scalars.hpp
+        self.s = mesh.fill_ghosts_cc(mesh.pad_cc(s)) if s is not None else None
         self.prim()
 
     def prim(self):
         self.bcc = cell_centered_b(*self.b) if self.mhd else None
         with np.errstate(all="ignore"):
             self.w = cons2prim(self.u, self.gamma, self.bcc)
+            if self.s is not None:   # PassiveScalarConservedToPrimitive, eos_scalars.cpp:31-60
+                d = self.u[IDN]
+                self.s = np.where(self.s < FLOOR * d, FLOOR * d, self.s)
+                self.r = self.s / d
+
+    def interior_s(self):
+        return self.mesh.unpad(self.s)
 
     def interior_u(self):
         return self.mesh.unpad(self.u)
@@ -388,18 +654,37 @@ def fluxes(st, order, dt_mesh):
         if st.mhd:
             q += [st.bcc[(d + 1) % 3], st.bcc[(d + 2) % 3]]
         wl, wr = reconstruct(q, d, order, mesh)
+        if order == 3:   # ApplyPrimitiveFloors on both states, ppm.cpp:326-332
+            for ws in (wl, wr):
+                ws[0] = np.where(ws[0] > FLOOR, ws[0], FLOOR)
+                ws[4] = np.where(ws[4] > FLOOR, ws[4], FLOOR)
         if st.mhd:
-            f = hlld(wl, wr, st.b[d], g)
+            f = (MHD_SOLVERS.get(st.flux) or hlld)(wl, wr, st.b[d], g)
             flx = [None] * 5
             flx[IDN], flx[ivx], flx[ivy], flx[ivz], flx[IEN] = f[0], f[1], f[2], f[3], f[4]
             dxw = mesh.along(mesh.dxf[d], d)
             wct = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, dt_mesh)
             out.append((flx, -f[IBY], f[IBZ], wct))
         else:
-            f = hllc(wl, wr, g)
+            f = (HYDRO_SOLVERS.get(st.flux) or hllc)(wl, wr, g)
             flx = [None] * 5
             flx[IDN], flx[ivx], flx[ivy], flx[ivz], flx[IEN] = f[0], f[1], f[2], f[3], f[4]
             out.append((flx, None, None, None))
+    return out
+
+
+def scalar_fluxes(st, fx, order):
+    """PassiveScalars::CalculateFluxes + ComputeUpwindFlux (calculate_scalar_fluxes.cpp:41-417):
+    reconstruct r = s/rho like a hydro variable, concentration floor on both states for xorder=3,
+    flux = F(rho) * (F(rho) >= 0 ? r_L : r_R) with the hydro mass flux of the same face."""
+    out = []
+    for d in range(3):
+        rl, rr = reconstruct(list(st.r), d, order, st.mesh)
+        if order == 3:
+            rl = [np.where(x > FLOOR, x, FLOOR) for x in rl]
+            rr = [np.where(x > FLOOR, x, FLOOR) for x in rr]
+        mf = fx[d][0][IDN]
+        out.append([np.where(mf >= 0.0, mf * a, mf * b) for a, b in zip(rl, rr)])
     return out
 
 
@@ -537,6 +822,7 @@ class Integrator:
         faces = [actf[0] & act[1] & act[2], act[0] & actf[1] & act[2], act[0] & act[1] & actf[2]]
         u1 = np.zeros_like(st.u)
         b1 = [np.zeros_like(x) for x in st.b] if st.mhd else None
+        s1 = np.zeros_like(st.s) if st.s is not None else None
         for stage, (delta, g1, g2, g3, beta) in enumerate(self.stages, 1):
             order = 1 if (self.name == "vl2" and stage == 1) else self.xorder
             with np.errstate(all="ignore"):
@@ -559,6 +845,20 @@ class Integrator:
                     dflx = dflx + (a3 * sh(fx[2][0][n], 2, 1) - a3 * fx[2][0][n])
                     unew[n] = np.where(cells, st.u[n] - wght * dflx / vol, st.u[n])
                 st.u = unew
+                if st.s is not None:   # IntegrateScalars (time_integrator.cpp:2376-2403)
+                    sfx = scalar_fluxes(st, fx, order)
+                    s1 = np.where(cells, weighted_ave(s1, st.s, None, 1.0, delta, 0.0), s1)
+                    if g1 == 0.0 and g2 == 1.0 and g3 == 0.0:
+                        st.s, s1 = s1, st.s
+                    else:
+                        st.s = np.where(cells, weighted_ave(st.s, s1, None, g1, g2, g3), st.s)
+                    snew = st.s.copy()
+                    for n in range(st.s.shape[0]):
+                        dflx = (a1 * sh(sfx[0][n], 0, 1) - a1 * sfx[0][n])
+                        dflx = dflx + (a2 * sh(sfx[1][n], 1, 1) - a2 * sfx[1][n])
+                        dflx = dflx + (a3 * sh(sfx[2][n], 2, 1) - a3 * sfx[2][n])
+                        snew[n] = np.where(cells, st.s[n] - wght * dflx / vol, st.s[n])
+                    st.s = m.fill_ghosts_cc(snew)
                 if st.mhd:   # IntegrateField + CT (ct.cpp:31-116)
                     for c in range(3):
                         b1[c] = np.where(faces[c], weighted_ave(b1[c], st.b[c], None, 1.0, delta, 0.0), b1[c])

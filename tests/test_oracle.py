@@ -13,21 +13,31 @@ from oracle import athena_np as A
 from oracle import refrun
 
 CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_rk2_plm_hlld",
-         "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2"]
+         "mhd_linwave_rk3_plm_hlld", "hydro_linwave_rk3_plm_hllc", "mhd_linwave_alfven_vl2",
+         # PPM (nghost = 3) and passive scalars
+         "hydro_linwave_rk3_ppm_hllc", "mhd_linwave_vl2_ppm_hlld", "hydro_kh_rk3_ppm_hllc_scalar",
+         "hydro_kh_vl2_plm_hllc_2scalars", "mhd_kh_rk2_plm_hlld_scalar",
+         # alternative Riemann solvers (Roe incl. its supersonic overrides and LLF fallback)
+         "hydro_linwave_vl2_plm_roe", "hydro_linwave_rk2_plm_roe_supersonic", "hydro_linwave_vl2_plm_hlle",
+         "hydro_linwave_vl2_plm_llf", "mhd_linwave_vl2_plm_hlle", "mhd_linwave_vl2_plm_llf",
+         "hydro_shocktube_vl2_plm_roe_llf"]
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_numpy_oracle_matches_reference_bitwise(name):
     meta, z = util.load_golden(name)
-    mesh = A.Mesh(meta["mesh"], meta["xmin"], meta["xmax"])
+    mesh = A.Mesh(meta["mesh"], meta["xmin"], meta["xmax"], ng=meta["ng"])
     b = [z["b1_0"], z["b2_0"], z["b3_0"]] if meta["mhd"] else None
-    st = A.State(mesh, meta["gamma"], z["u0"], b)
+    st = A.State(mesh, meta["gamma"], z["u0"], b, s=z["s0"] if meta.get("nscalars") else None,
+                 flux=meta.get("flux"))
     it = A.Integrator(st, meta["integrator"], meta["xorder"], meta["cfl"], block_nx=meta["block"])
     it.run(meta["tlim"])
     assert it.ncycle == meta["ncycle"]
     np.testing.assert_array_equal(np.array(it.dt_history), z["hst"][:-1, 1])
     assert it.dt == meta["dt_final"]
     np.testing.assert_array_equal(st.interior_u(), z["uf"])
+    if meta.get("nscalars"):
+        np.testing.assert_array_equal(st.interior_s(), z["sf"])
     if meta["mhd"]:
         np.testing.assert_array_equal(st.interior_b(0), z["b1_f"])
         np.testing.assert_array_equal(st.interior_b(1), z["b2_f"])
