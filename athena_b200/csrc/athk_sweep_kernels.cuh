@@ -66,6 +66,26 @@ struct SmemStencil {
   __device__ __forceinline__ Real bx() const { return MHD ? row(0)[7 * 32] : 0.0; }
 };
 
+// PPM of every variable of the cell `off0` cells above the stencil's reference cell: left state of
+// its upper face (up) and right state of its lower face (lo), with the primitive floors the
+// reference applies to both face states (ppm.cpp:326-332)
+template <bool MHD, class ST>
+__device__ __forceinline__ void ppm_recon_cell(const EosParams &eos, const ST &st, int off0, Real up[7],
+                                               Real lo[7]) {
+  Real qm2[7], qm1[7], q0[7], qp1[7], qp2[7];
+  st.cell(off0 - 2, qm2);
+  st.cell(off0 - 1, qm1);
+  st.cell(off0, q0);
+  st.cell(off0 + 1, qp1);
+  st.cell(off0 + 2, qp2);
+#pragma unroll
+  for (int v = 0; v < (MHD ? 7 : 5); ++v) ppm_cell(qm2[v], qm1[v], q0[v], qp1[v], qp2[v], &up[v], &lo[v]);
+  up[IDN] = (up[IDN] > eos.dfloor) ? up[IDN] : eos.dfloor;
+  up[IPR] = (up[IPR] > eos.pfloor) ? up[IPR] : eos.pfloor;
+  lo[IDN] = (lo[IDN] > eos.dfloor) ? lo[IDN] : eos.dfloor;
+  lo[IPR] = (lo[IPR] > eos.pfloor) ? lo[IPR] : eos.pfloor;
+}
+
 template <int DIR, int ORDER, bool MHD, int RS>
 __global__ void __launch_bounds__(32 * ATHK_TILE_R, ATHK_TILE_MINB)
 k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il,
@@ -80,6 +100,10 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
   Real(*sF)[R][5][32] = reinterpret_cast<Real(*)[R][5][32]>(smem_tile);                 // [2]
   Real(*sTop)[5][32] = reinterpret_cast<Real(*)[5][32]>(smem_tile + 2 * R * 5 * 32);     // [3]
   Real(*sQ)[NQ][32] = reinterpret_cast<Real(*)[NQ][32]>(smem_tile + (2 * R + 3) * 5 * 32);   // [NR]
+  // PPM only: left states handed from cell n to face n+1 ([R] rows + the top row double-buffered)
+  constexpr int NWS = MHD ? 7 : 5;
+  Real(*sW)[NWS][32] = reinterpret_cast<Real(*)[NWS][32]>(smem_tile + ((2 * R + 3) * 5 + NR * NQ) * 32);   // [R]
+  Real(*sWtop)[NWS][32] = sW + R;                                                                            // [2]
   const Grid &g = a.g;
   const int lane = threadIdx.x, r = threadIdx.y;
   // Per-column invariants (MeshBlock, first cell, face area, flags) live in shared memory and are
@@ -163,7 +187,46 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
     stage_row(n + R + HI);
     cp_async_commit();
     Real f[7];
-    if (fvalid) {
+    if constexpr (ORDER == 3) {
+      // PPM: every thread reconstructs ITS cell n once (parabola -> left state of face n+1,
+      // right state of face n) and hands the left state to the thread above through shared
+      // memory, instead of every face rebuilding the parabolas of both adjacent cells.
+      constexpr int NW = MHD ? 7 : 5;
+      Real wr[7];
+      const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
+      if (fvalid) {
+        Real up[7];
+        ppm_recon_cell<MHD>(a.eos, st, 0, up, wr);
+#pragma unroll
+        for (int v = 0; v < NW; ++v) sW[r][v][lane] = up[v];
+        if (r == R - 1) {
+#pragma unroll
+          for (int v = 0; v < NW; ++v) sWtop[step & 1][v][lane] = up[v];
+        }
+        if (step == 0 && r == 0) {   // nobody owns cell n_s-1: the first face's left state
+          Real lo_unused[7];
+          ppm_recon_cell<MHD>(a.eos, st, -1, up, lo_unused);
+#pragma unroll
+          for (int v = 0; v < NW; ++v) sWtop[1][v][lane] = up[v];
+        }
+      }
+      __syncthreads();
+      if (fvalid) {
+        const int blk = vBlk[lane] & 0x1fffffff;
+        const idx_t c = vC0[lane] + (idx_t)n * s;
+        Real wl[7];
+        const Real(*src)[32] = (r > 0) ? sW[r - 1] : sWtop[(step + 1) & 1];
+#pragma unroll
+        for (int v = 0; v < NW; ++v) wl[v] = src[v][lane];
+        solve_face<DIR, MHD, RS>(a, blk, c, n, wl, wr, st.bx(), f, true);
+        Real(*mine)[32] = (r == R - 1) ? sTop[step % 3] : sF[buf][r];
+        mine[0][lane] = f[IDN];
+        mine[1][lane] = f[IVX];
+        mine[2][lane] = f[IVY];
+        mine[3][lane] = f[IVZ];
+        mine[4][lane] = f[IEN];
+      }
+    } else if (fvalid) {
       const int blk = vBlk[lane] & 0x1fffffff;
       const idx_t c = vC0[lane] + (idx_t)n * s;
       const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
@@ -280,7 +343,7 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   const unsigned grid = (unsigned)((ncol + 31) / 32);
 #if ATHK_TILE_STAGE
   constexpr int R = ATHK_TILE_R, NR = 2 * R + 2 * ORDER - 1, NQ = MHD ? 8 : 5;
-  constexpr size_t smem = sizeof(Real) * 32 * ((2 * R + 3) * 5 + NR * NQ);
+  constexpr size_t smem = sizeof(Real) * 32 * ((2 * R + 3) * 5 + NR * NQ + (ORDER == 3 ? (R + 2) * (MHD ? 7 : 5) : 0));
   static bool attr_set = false;   // > 48 KB of dynamic shared memory is opt-in, once per kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_sweep_tile_staged<DIR, ORDER, MHD, RS>,

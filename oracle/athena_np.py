@@ -500,8 +500,195 @@ def hlle_mhd(wl, wr, bxi, gamma):   # hydro/rsolvers/mhd/hlle_mhd.cpp:63-170
         return [0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp for n in range(7)]
 
 
+def roe_mhd(wl, wr, bxi, gamma):   # hydro/rsolvers/mhd/roe_mhd.cpp:60-215 + RoeFlux :245-470 (adiabatic)
+    gm1 = gamma - 1.0
+    with np.errstate(all="ignore"):
+        sqrtdl, sqrtdr = np.sqrt(wl[IDN]), np.sqrt(wr[IDN])
+        isdlpdr = 1.0 / (sqrtdl + sqrtdr)
+        d = sqrtdl * sqrtdr
+        v1, v2, v3 = [(sqrtdl * wl[v] + sqrtdr * wr[v]) * isdlpdr for v in (IVX, IVY, IVZ)]
+        b2 = (sqrtdr * wl[IBY] + sqrtdl * wr[IBY]) * isdlpdr
+        b3 = (sqrtdr * wl[IBZ] + sqrtdl * wr[IBZ]) * isdlpdr
+        x = 0.5 * (_sq(wl[IBY] - wr[IBY]) + _sq(wl[IBZ] - wr[IBZ])) / (_sq(sqrtdl + sqrtdr))
+        y = 0.5 * (wl[IDN] + wr[IDN]) / d
+        pbl = 0.5 * (bxi * bxi + _sq(wl[IBY]) + _sq(wl[IBZ]))
+        pbr = 0.5 * (bxi * bxi + _sq(wr[IBY]) + _sq(wr[IBZ]))
+        fl, fr, du = _mhd_lr(wl, wr, bxi, gamma)
+        el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (_sq(wl[IVX]) + _sq(wl[IVY]) + _sq(wl[IVZ])) + pbl
+        er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (_sq(wr[IVX]) + _sq(wr[IVY]) + _sq(wr[IVZ])) + pbr
+        h = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr
+        flx = [0.5 * (fl[n] + fr[n]) for n in range(7)]
+        # RoeFlux
+        b1 = bxi
+        di = 1.0 / d
+        btsq = b2 * b2 + b3 * b3
+        vaxsq = b1 * b1 * di
+        vsq = v1 * v1 + v2 * v2 + v3 * v3
+        hp = h - (vaxsq + btsq * di)
+        bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq
+        twid_csq = np.maximum((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), TINY_NUMBER)
+        ct2 = bt_starsq * di
+        tsum = vaxsq + ct2 + twid_csq
+        tdif = vaxsq + ct2 - twid_csq
+        cf2_cs2 = np.sqrt(tdif * tdif + 4.0 * twid_csq * ct2)
+        cfsq = 0.5 * (tsum + cf2_cs2)
+        cf = np.sqrt(cfsq)
+        cssq = twid_csq * vaxsq / cfsq
+        cs = np.sqrt(cssq)
+        bt = np.sqrt(btsq)
+        bt_star = np.sqrt(bt_starsq)
+        bet2 = np.where(bt != 0.0, b2 / bt, 0.0)
+        bet3 = np.where(bt != 0.0, b3 / bt, 0.0)
+        bet2_star = bet2 / np.sqrt(gm1 - (gm1 - 1.0) * y)
+        bet3_star = bet3 / np.sqrt(gm1 - (gm1 - 1.0) * y)
+        bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star
+        vbet = v2 * bet2_star + v3 * bet3_star
+        q2_star = np.where(bet_starsq != 0.0, bet2_star / bet_starsq, 0.0)
+        q3_star = np.where(bet_starsq != 0.0, bet3_star / bet_starsq, 0.0)
+        c1 = (cfsq - cssq) <= 0.0
+        c2 = (twid_csq - cssq) <= 0.0
+        c3 = (cfsq - twid_csq) <= 0.0
+        af_gen = np.sqrt((twid_csq - cssq) / (cfsq - cssq))
+        as_gen = np.sqrt((cfsq - twid_csq) / (cfsq - cssq))
+        alpha_f = np.where(c1, 1.0, np.where(c2, 0.0, np.where(c3, 1.0, af_gen)))
+        alpha_s = np.where(c1, 0.0, np.where(c2, 1.0, np.where(c3, 0.0, as_gen)))
+        sqrtd = np.sqrt(d)
+        isqrtd = 1.0 / sqrtd
+        sg = sign(b1)
+        twid_c = np.sqrt(twid_csq)
+        qf = cf * alpha_f * sg
+        qs = cs * alpha_s * sg
+        af_prime = twid_c * alpha_f * isqrtd
+        as_prime = twid_c * alpha_s * isqrtd
+        afpbb = af_prime * bt_star * bet_starsq
+        aspbb = as_prime * bt_star * bet_starsq
+        vqstr = (v2 * q2_star + v3 * q3_star)
+        vax = np.sqrt(vaxsq)
+        norm = 0.5 / twid_csq
+        cff = norm * alpha_f * cf
+        css = norm * alpha_s * cs
+        qf_hat = qf * norm
+        qs_hat = qs * norm
+        af = norm * af_prime * d
+        as_ = norm * as_prime * d
+        afpb = norm * af_prime * bt_star
+        aspb = norm * as_prime * bt_star
+        ev = [v1 - cf, v1 - vax, v1 - cs, v1, v1 + cs, v1 + vax, v1 + cf]
+        alpha_f_bar = alpha_f * gm1 * norm
+        alpha_s_bar = alpha_s * gm1 * norm
+        gm1a = gm1 / twid_csq
+        a = [None] * 7
+        t = du[0] * (alpha_f_bar * (vsq - hp) + cff * (cf + v1) - qs_hat * vqstr - aspb)
+        t = t - du[1] * (alpha_f_bar * v1 + cff)
+        t = t - du[2] * (alpha_f_bar * v2 - qs_hat * q2_star)
+        t = t - du[3] * (alpha_f_bar * v3 - qs_hat * q3_star)
+        t = t + du[4] * alpha_f_bar
+        t = t + du[5] * (as_ * q2_star - alpha_f_bar * b2)
+        a[0] = t + du[6] * (as_ * q3_star - alpha_f_bar * b3)
+        t = du[0] * (v2 * bet3 - v3 * bet2)
+        t = t - du[2] * bet3
+        t = t + du[3] * bet2
+        t = t - du[5] * sqrtd * bet3 * sg
+        t = t + du[6] * sqrtd * bet2 * sg
+        a[1] = t * 0.5
+        t = du[0] * (alpha_s_bar * (vsq - hp) + css * (cs + v1) + qf_hat * vqstr + afpb)
+        t = t - du[1] * (alpha_s_bar * v1 + css)
+        t = t - du[2] * (alpha_s_bar * v2 + qf_hat * q2_star)
+        t = t - du[3] * (alpha_s_bar * v3 + qf_hat * q3_star)
+        t = t + du[4] * alpha_s_bar
+        t = t - du[5] * (af * q2_star + alpha_s_bar * b2)
+        a[2] = t - du[6] * (af * q3_star + alpha_s_bar * b3)
+        t = du[0] * (1.0 - gm1a * (0.5 * vsq - (gm1 - 1.0) * x / gm1))
+        t = t + du[1] * gm1a * v1
+        t = t + du[2] * gm1a * v2
+        t = t + du[3] * gm1a * v3
+        t = t - du[4] * gm1a
+        t = t + du[5] * gm1a * b2
+        a[3] = t + du[6] * gm1a * b3
+        t = du[0] * (alpha_s_bar * (vsq - hp) + css * (cs - v1) - qf_hat * vqstr + afpb)
+        t = t - du[1] * (alpha_s_bar * v1 - css)
+        t = t - du[2] * (alpha_s_bar * v2 - qf_hat * q2_star)
+        t = t - du[3] * (alpha_s_bar * v3 - qf_hat * q3_star)
+        t = t + du[4] * alpha_s_bar
+        t = t - du[5] * (af * q2_star + alpha_s_bar * b2)
+        a[4] = t - du[6] * (af * q3_star + alpha_s_bar * b3)
+        t = du[0] * (v3 * bet2 - v2 * bet3)
+        t = t + du[2] * bet3
+        t = t - du[3] * bet2
+        t = t - du[5] * sqrtd * bet3 * sg
+        t = t + du[6] * sqrtd * bet2 * sg
+        a[5] = t * 0.5
+        t = du[0] * (alpha_f_bar * (vsq - hp) + cff * (cf - v1) + qs_hat * vqstr - aspb)
+        t = t - du[1] * (alpha_f_bar * v1 - cff)
+        t = t - du[2] * (alpha_f_bar * v2 + qs_hat * q2_star)
+        t = t - du[3] * (alpha_f_bar * v3 + qs_hat * q3_star)
+        t = t + du[4] * alpha_f_bar
+        t = t + du[5] * (as_ * q2_star - alpha_f_bar * b2)
+        a[6] = t + du[6] * (as_ * q3_star - alpha_f_bar * b3)
+        co = [-0.5 * np.abs(ev[n]) * a[n] for n in range(7)]
+        dens = wl[IDN] + a[0] * alpha_f
+        llf = dens < 0.0
+        dens = dens + a[2] * alpha_s
+        llf = llf | (dens < 0.0)
+        dens = dens + a[3]
+        llf = llf | (dens < 0.0)
+        dens = dens + a[4] * alpha_s
+        llf = llf | (dens < 0.0)
+        f0 = flx[0] + co[0] * alpha_f
+        f0 = f0 + co[2] * alpha_s
+        f0 = f0 + co[3]
+        f0 = f0 + co[4] * alpha_s
+        f0 = f0 + co[6] * alpha_f
+        f1 = flx[1] + co[0] * (alpha_f * (v1 - cf))
+        f1 = f1 + co[2] * (alpha_s * (v1 - cs))
+        f1 = f1 + co[3] * v1
+        f1 = f1 + co[4] * (alpha_s * (v1 + cs))
+        f1 = f1 + co[6] * (alpha_f * (v1 + cf))
+        f2 = flx[2] + co[0] * (alpha_f * v2 + qs * bet2_star)
+        f2 = f2 - co[1] * bet3
+        f2 = f2 + co[2] * (alpha_s * v2 - qf * bet2_star)
+        f2 = f2 + co[3] * v2
+        f2 = f2 + co[4] * (alpha_s * v2 + qf * bet2_star)
+        f2 = f2 + co[5] * bet3
+        f2 = f2 + co[6] * (alpha_f * v2 - qs * bet2_star)
+        f3 = flx[3] + co[0] * (alpha_f * v3 + qs * bet3_star)
+        f3 = f3 + co[1] * bet2
+        f3 = f3 + co[2] * (alpha_s * v3 - qf * bet3_star)
+        f3 = f3 + co[3] * v3
+        f3 = f3 + co[4] * (alpha_s * v3 + qf * bet3_star)
+        f3 = f3 - co[5] * bet2
+        f3 = f3 + co[6] * (alpha_f * v3 - qs * bet3_star)
+        f4 = flx[4] + co[0] * (alpha_f * (hp - v1 * cf) + qs * vbet + aspbb)
+        f4 = f4 - co[1] * (v2 * bet3 - v3 * bet2)
+        f4 = f4 + co[2] * (alpha_s * (hp - v1 * cs) - qf * vbet - afpbb)
+        f4 = f4 + co[3] * (0.5 * vsq + (gm1 - 1.0) * x / gm1)
+        f4 = f4 + co[4] * (alpha_s * (hp + v1 * cs) + qf * vbet - afpbb)
+        f4 = f4 + co[5] * (v1 * bet3 - v3 * bet2)
+        f4 = f4 + co[6] * (alpha_f * (hp + v1 * cf) - qs * vbet + aspbb)
+        f5 = flx[5] + co[0] * as_prime * bet2_star
+        f5 = f5 - co[1] * bet3 * sg * isqrtd
+        f5 = f5 - co[2] * af_prime * bet2_star
+        f5 = f5 - co[4] * af_prime * bet2_star
+        f5 = f5 - co[5] * bet3 * sg * isqrtd
+        f5 = f5 + co[6] * as_prime * bet2_star
+        f6 = flx[6] + co[0] * as_prime * bet3_star
+        f6 = f6 + co[1] * bet2 * sg * isqrtd
+        f6 = f6 - co[2] * af_prime * bet3_star
+        f6 = f6 - co[4] * af_prime * bet3_star
+        f6 = f6 + co[5] * bet2 * sg * isqrtd
+        f6 = f6 + co[6] * as_prime * bet3_star
+        out = [f0, f1, f2, f3, f4, f5, f6]
+        out = [np.where(ev[0] >= 0.0, fl[n], out[n]) for n in range(7)]
+        out = [np.where(ev[6] <= 0.0, fr[n], out[n]) for n in range(7)]
+        cfl_ = fast_speed(gamma, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi)
+        cfr_ = fast_speed(gamma, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi)
+        al = 0.5 * np.maximum((np.abs(wl[IVX]) + cfl_), (np.abs(wr[IVX]) + cfr_))
+        # the LLF fallback leaves the induction components at their Roe values (roe_mhd.cpp:193-205)
+        return [np.where(llf, 0.5 * (fl[n] + fr[n]) - al * du[n], out[n]) if n < 5 else out[n] for n in range(7)]
+
+
 HYDRO_SOLVERS = {"hllc": None, "hlle": hlle_hydro, "llf": llf_hydro, "roe": roe_hydro}
-MHD_SOLVERS = {"hlld": None, "hlle": hlle_mhd, "llf": llf_mhd}   # (Roe MHD is not restated here)
+MHD_SOLVERS = {"hlld": None, "hlle": hlle_mhd, "llf": llf_mhd, "roe": roe_mhd}
 
 
 def hlld(wl, wr, bxi, gamma):   # hlld.cpp:56-365 ; returns 7 flux components

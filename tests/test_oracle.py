@@ -20,7 +20,8 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          # alternative Riemann solvers (Roe incl. its supersonic overrides and LLF fallback)
          "hydro_linwave_vl2_plm_roe", "hydro_linwave_rk2_plm_roe_supersonic", "hydro_linwave_vl2_plm_hlle",
          "hydro_linwave_vl2_plm_llf", "mhd_linwave_vl2_plm_hlle", "mhd_linwave_vl2_plm_llf",
-         "hydro_shocktube_vl2_plm_roe_llf"]
+         "hydro_shocktube_vl2_plm_roe_llf", "mhd_linwave_vl2_plm_roe", "mhd_linwave_rk3_plm_roe_slow",
+         "mhd_shocktube_vl2_plm_roe_llf"]
 
 
 @pytest.mark.parametrize("name", CASES)
