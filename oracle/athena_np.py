@@ -25,6 +25,7 @@ Reference sources followed (file:line under /root/reference/src):
   bvals/fc/flux_correction_fc.cpp:689-760,1355-1541                    EMF correction (averaging)
   hydro/add_flux_divergence.cpp:39-96, mesh/weighted_ave.cpp:35-230    update
   hydro/new_blockdt.cpp:45-230, mesh/mesh.cpp:1236-1282                time step
+  bvals/bvals.cpp:453-660, bvals/cc/*reflect*/outflow*, bvals/fc/*     physical boundaries
   task_list/time_integrator.cpp:111-606,1694-1885                      stage weights / order
 """
 import sys
@@ -72,9 +73,12 @@ class Mesh:
     the oracle lives in the same padded box (nc3+1, nc2+1, nc1+1) so that cell, face and edge
     data share one index space (index ng = first active cell / face)."""
 
-    def __init__(self, nx, xmin, xmax, ng=NG):
+    def __init__(self, nx, xmin, xmax, ng=NG, bcs=None):
         self.nx = tuple(nx)
         self.ng = ng
+        # physical boundaries: per direction (inner, outer) in {None, "reflecting", "outflow"}
+        bcs = list(bcs) if bcs is not None else ["periodic"] * 6
+        self.bc = [tuple(None if f == "periodic" else f for f in bcs[2 * d:2 * d + 2]) for d in range(3)]
         self.nc = tuple(n + 2 * ng for n in nx)
         self.shape = tuple(n + 1 for n in self.nc[::-1])   # (k,j,i) padded box
         self.dxf, self.cp, self.cm = [], [], []
@@ -133,6 +137,8 @@ class Mesh:
     def fill_ghosts_cc(self, a):
         """periodic self-exchange of a cell-centred array (bvals_cc.cpp:287-302,386-420)"""
         for d in range(3):
+            if self.bc[d][0] is not None:   # physical boundary: ghosts are set by apply_physical_bcs
+                continue
             i = self.idx(d)
             n, ng = self.nx[d], self.ng
             lo = np.roll(a, n, axis=AX[d])    # value at index - n ... placed at index
@@ -144,6 +150,8 @@ class Mesh:
         """face field: along its own direction the shared faces ng and ng+n are kept
         (bvals_fc.cpp:591-593)"""
         for d in range(3):
+            if self.bc[d][0] is not None:
+                continue
             i = self.idx(d)
             n, ng = self.nx[d], self.ng
             top = ng + n - 1 + (1 if d == comp else 0)
@@ -819,6 +827,7 @@ class State:
                 d = self.u[IDN]
                 self.s = np.where(self.s < FLOOR * d, FLOOR * d, self.s)
                 self.r = self.s / d
+            apply_physical_bcs(self)
 
     def interior_s(self):
         return self.mesh.unpad(self.s)
@@ -930,7 +939,10 @@ def apply_emf_correction(e, mesh, block_nx):
     on = []
     for d in range(3):
         i = mesh.idx(d) - ng
-        on.append((i >= 0) & (i <= mesh.nx[d]) & (i % block_nx[d] == 0))
+        shared = (i >= 0) & (i <= mesh.nx[d]) & (i % block_nx[d] == 0)
+        if mesh.bc[d][0] is not None:   # the mesh edge has no neighbour: nothing to add or average
+            shared = shared & (i != 0) & (i != mesh.nx[d])
+        on.append(shared)
     out = []
     for comp, (da, db) in enumerate(((1, 2), (0, 2), (0, 1))):
         a = e[comp]
@@ -943,6 +955,84 @@ def apply_emf_correction(e, mesh, block_nx):
         v_edge = (((a + fa) + fb) + fe) * 0.25
         out.append(np.where(pa & pb, v_edge, np.where(pa, v_a, np.where(pb, v_b, a))))
     return out
+
+
+def apply_physical_bcs(st):
+    """BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:453-660) with the built-in
+    reflecting / outflow functions (bvals/cc/hydro/reflect_hydro.cpp, bvals/cc/outflow_cc.cpp,
+    bvals/cc/reflect_cc.cpp for r, bvals/fc/reflect_fc.cpp, outflow_fc.cpp) on w, r and b; then
+    bcc, PrimitiveToConserved (adiabatic_*.cpp) and s = r*rho on the same ghost slab.  Faces in
+    the order x1, x2, x3; a transverse direction includes its ghost zones once they are valid
+    (periodic from the exchange, or physical and already processed: bvals.cpp:457-470,560)."""
+    m = st.mesh
+    ng = m.ng
+    if all(m.bc[d][0] is None for d in range(3)):
+        return
+    igm1 = 1.0 / (st.gamma - 1.0)
+
+    def gather(a, d, src):   # a[..., index along d] <- a[..., src[index]]
+        return np.take(a, src, axis=AX[d])
+
+    for d in range(3):
+        n = m.nx[d]
+        idx1 = np.arange(m.nc[d] + 1)
+        for side in (0, 1):
+            flag = m.bc[d][side]
+            if flag is None:
+                continue
+            refl = flag == "reflecting"
+            i = m.idx(d)
+            ghost_c = (i < ng) if side == 0 else ((i > ng + n - 1) & (i <= ng + n - 1 + ng))
+            ghost_f = (i < ng) if side == 0 else ((i > ng + n) & (i <= ng + n + ng))
+            if side == 0:
+                src_c = np.where(idx1 < ng, (2 * ng - 1 - idx1) if refl else ng, idx1)
+                src_f = np.where(idx1 < ng, (2 * ng - idx1) if refl else ng, idx1)
+            else:
+                src_c = np.where(idx1 > ng + n - 1, (2 * (ng + n) - 1 - idx1) if refl else ng + n - 1, idx1)
+                src_f = np.where(idx1 > ng + n, (2 * (ng + n) - idx1) if refl else ng + n, idx1)
+            src_c = np.clip(src_c, 0, m.nc[d])
+            src_f = np.clip(src_f, 0, m.nc[d])
+            # transverse ranges of the cell-centred pass
+            tr = []
+            for t in range(3):
+                if t == d:
+                    continue
+                it = m.idx(t)
+                lo = ng - (ng if (t < d or m.bc[t][0] is None) else 0)
+                hi = ng + m.nx[t] - 1 + (ng if (t < d or m.bc[t][1] is None) else 0)
+                tr.append((t, it, lo, hi))
+            cmask = ghost_c
+            for t, it, lo, hi in tr:
+                cmask = cmask & (it >= lo) & (it <= hi)
+            for v in range(5):
+                val = gather(st.w[v], d, src_c)
+                if refl and v == IVX + d:
+                    val = -val
+                st.w[v] = np.where(cmask, val, st.w[v])
+            if st.s is not None:
+                for q in range(st.r.shape[0]):
+                    st.r[q] = np.where(cmask, gather(st.r[q], d, src_c), st.r[q])
+            if st.mhd:
+                for comp in range(3):
+                    fm = ghost_f if comp == d else ghost_c
+                    for t, it, lo, hi in tr:
+                        fm = fm & (it >= lo) & (it <= hi + (1 if t == comp else 0))
+                    val = gather(st.b[comp], d, src_f if comp == d else src_c)
+                    if refl and comp == d:
+                        val = -val
+                    st.b[comp] = np.where(fm, val, st.b[comp])
+                bcc = cell_centered_b(*st.b)
+                st.bcc = tuple(np.where(cmask, bcc[c], st.bcc[c]) for c in range(3))
+            w = st.w
+            e = w[IPR] * igm1 + 0.5 * w[IDN] * (w[IVX] * w[IVX] + w[IVY] * w[IVY] + w[IVZ] * w[IVZ])
+            if st.mhd:
+                e = w[IPR] * igm1 + 0.5 * (w[IDN] * (w[IVX] * w[IVX] + w[IVY] * w[IVY] + w[IVZ] * w[IVZ])
+                                           + (st.bcc[0] * st.bcc[0] + st.bcc[1] * st.bcc[1] + st.bcc[2] * st.bcc[2]))
+            unew = [w[IDN], w[IVX] * w[IDN], w[IVY] * w[IDN], w[IVZ] * w[IDN], e]
+            for v in range(5):
+                st.u[v] = np.where(cmask, unew[v], st.u[v])
+            if st.s is not None:
+                st.s = np.where(cmask, st.r * w[IDN], st.s)
 
 
 def weighted_ave(out, in1, in2, w0, w1, w2):   # weighted_ave.cpp:35-230 (wght[3]=wght[4]=0)

@@ -21,13 +21,16 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          "hydro_linwave_vl2_plm_roe", "hydro_linwave_rk2_plm_roe_supersonic", "hydro_linwave_vl2_plm_hlle",
          "hydro_linwave_vl2_plm_llf", "mhd_linwave_vl2_plm_hlle", "mhd_linwave_vl2_plm_llf",
          "hydro_shocktube_vl2_plm_roe_llf", "mhd_linwave_vl2_plm_roe", "mhd_linwave_rk3_plm_roe_slow",
-         "mhd_shocktube_vl2_plm_roe_llf"]
+         "mhd_shocktube_vl2_plm_roe_llf",
+         # reflecting / outflow physical boundaries
+         "hydro_sod_vl2_plm_hllc_outflow_x1", "mhd_briowu_rk2_plm_hlld_outflow_x2",
+         "hydro_blast_rk3_plm_hllc_mixed_bcs", "mhd_blast_vl2_plm_hlld_reflecting_box"]
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_numpy_oracle_matches_reference_bitwise(name):
     meta, z = util.load_golden(name)
-    mesh = A.Mesh(meta["mesh"], meta["xmin"], meta["xmax"], ng=meta["ng"])
+    mesh = A.Mesh(meta["mesh"], meta["xmin"], meta["xmax"], ng=meta["ng"], bcs=meta.get("bcs"))
     b = [z["b1_0"], z["b2_0"], z["b3_0"]] if meta["mhd"] else None
     st = A.State(mesh, meta["gamma"], z["u0"], b, s=z["s0"] if meta.get("nscalars") else None,
                  flux=meta.get("flux"))
