@@ -363,11 +363,89 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
 // 32 faces in shared memory with cp.async while solving the current ones was measured SLOWER
 // (2.04 vs 1.89 ms per PLM sweep at 256^3): the x1 sweep's long-scoreboard stalls are register-
 // spill reloads, not the global loads, so it was dropped.
+//========================================================================================
+// x1 sweep for PPM with one parabola per cell (ATHK_X1_PPM_SHARE): the cells i = is-1 .. ie+1 of
+// all rows of a (k, MeshBlock) plane form one stream, lane L of a warp owns cell t = 30*warp + L,
+// reconstructs it once (left state of face i+1, right state of face i) and passes the left state
+// to lane L+1 with a shuffle; lanes 1..31 solve the face below their cell, lanes 1..30 finish
+// their cell with the flux of lane L+1.  Consecutive warps overlap by two cells.  The plain
+// kernel rebuilds the parabolas of both cells at every face (10-14 ppm_cell per face instead of
+// 5-7).
+#ifndef ATHK_X1_PPM_SHARE
+#define ATHK_X1_PPM_SHARE 0
+#endif
+
+template <bool MHD>
+struct GlobalRowStencil {
+  const SweepArgs &a;
+  int blk;
+  idx_t c;
+  __device__ __forceinline__ void cell(int off, Real q[7]) const { load_q<0, MHD>(a, blk, c + off, q); }
+};
+
+template <bool MHD, int RS>
+__global__ void __launch_bounds__(128, ATHK_X1_MINB)
+k_sweep_x1_ppm(const SweepX1<3, MHD, RS> f, const int kl, const int jl, const int nj, const int icl,
+               const int ncr, const unsigned ncr_magic) {
+  constexpr int NW = MHD ? 7 : 5;
+  const SweepArgs &a = f.a;
+  const Grid &g = a.g;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned total = (unsigned)(nj * ncr);          // cells in the stream
+  const unsigned t = warp * 30 + lane;
+  const bool valid = t < total;
+  const int blk = (int)blockIdx.z, k = kl + (int)blockIdx.y;
+  int j = jl, ci = 0;
+  if (valid) {
+    const unsigned row = __umulhi(t, ncr_magic);
+    ci = (int)(t - row * (unsigned)ncr);
+    j = jl + (int)row;
+  }
+  const int i = icl + ci;                               // this lane's cell
+  const idx_t c = gidx(g, k, j, i);
+  Real up[7], lo[7];
+#pragma unroll
+  for (int v = 0; v < 7; ++v) up[v] = lo[v] = 0.0;
+  const bool cell_upd = valid && lane >= 1 && lane <= 30 && ci >= 1 && ci <= ncr - 2 && f.cell_active(k, j, i);
+  if (valid) {
+    if (cell_upd) f.prefetch_cell(blk, k, j, i);
+    const GlobalRowStencil<MHD> st = {a, blk, c};
+    ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
+  }
+  Real wl[7];
+#pragma unroll
+  for (int v = 0; v < NW; ++v) wl[v] = __shfl_up_sync(0xffffffffu, up[v], 1);
+  Real fl[7];
+#pragma unroll
+  for (int v = 0; v < 7; ++v) fl[v] = 0.0;
+  // face i (between cells i-1 and i): needs the lane below in the same row
+  if (valid && lane >= 1 && ci >= 1) {
+    const Real bx = MHD ? a.b[(idx_t)blk * 3 * g.sn + c] : 0.0;
+    // (the face of lane 31 is solved again by lane 1 of the next warp: same values, same stores)
+    solve_face<0, MHD, RS>(a, blk, c, i, wl, lo, bx, fl, true);
+  }
+  Real fn[7];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) fn[v] = __shfl_down_sync(0xffffffffu, fl[v], 1);
+  if (cell_upd) f.store_d1(blk, k, j, i, fl, fn);
+}
+
 template <int ORDER, bool MHD, int RS>
 static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r,
                                           const SweepX1<ORDER, MHD, RS> &f) {
   const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (nif <= 1 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
+#if ATHK_X1_PPM_SHARE
+  if constexpr (ORDER == 3) {
+    const int ncr = nif + 1;                       // cells il-1 .. iu of a row
+    const int total = nj * ncr;
+    const int nwarps = (total - 2 + 29) / 30;      // stride 30, two cells of overlap
+    dim3 grid((unsigned)((nwarps + 3) / 4), (unsigned)nk, (unsigned)nb);
+    k_sweep_x1_ppm<MHD, RS><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il - 1, ncr, magic_u32(ncr));
+    return cudaGetLastError();
+  }
+#endif
   const int total = nj * nif;
   const int nchunks = (total - 1 + 30) / 31;
   dim3 grid((unsigned)((nchunks + 3) / 4), (unsigned)nk, (unsigned)nb);
