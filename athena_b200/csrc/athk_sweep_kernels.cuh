@@ -372,7 +372,7 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
 // kernel rebuilds the parabolas of both cells at every face (10-14 ppm_cell per face instead of
 // 5-7).
 #ifndef ATHK_X1_PPM_SHARE
-#define ATHK_X1_PPM_SHARE 0
+#define ATHK_X1_PPM_SHARE 1
 #endif
 
 template <bool MHD>
