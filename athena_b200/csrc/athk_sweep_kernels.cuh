@@ -69,6 +69,32 @@ struct SmemStencil {
 // PPM of every variable of the cell `off0` cells above the stencil's reference cell: left state of
 // its upper face (up) and right state of its lower face (lo), with the primitive floors the
 // reference applies to both face states (ppm.cpp:326-332)
+// One reconstruction per cell (instead of two per face).  PPM: always.  PLM: measured on the MHD
+// blast at 256^3 -- the x1 sweep gains 3 % (shuffles are free), the x2/x3 tiles LOSE 9 % (the
+// hand-over costs a second barrier per step and the slopes of uniform regions are free anyway),
+// so the tiles keep the face-centric PLM.
+#ifndef ATHK_PLM_SHARE_TILES
+#define ATHK_PLM_SHARE_TILES 0
+#endif
+#ifndef ATHK_PLM_SHARE_X1
+#define ATHK_PLM_SHARE_X1 1
+#endif
+#define ATHK_SHARED_RECON(ORDER) ((ORDER) == 3 || ((ORDER) == 2 && ATHK_PLM_SHARE_TILES))
+#define ATHK_SHARED_RECON_X1(ORDER) ((ORDER) == 3 || ((ORDER) == 2 && ATHK_PLM_SHARE_X1))
+
+// PLM of every variable of the cell `off0` cells above the stencil's reference cell (index n_cell
+// along DIR): the two states recon_cell gives
+template <int DIR, bool MHD, class ST>
+__device__ __forceinline__ void plm_recon_cell(const SweepArgs &a, int blk, const ST &st, int off0, int n_cell,
+                                               Real up[7], Real lo[7]) {
+  Real qm[7], q0[7], qp[7];
+  st.cell(off0 - 1, qm);
+  st.cell(off0, q0);
+  st.cell(off0 + 1, qp);
+  const Real cp = a.geo.cp[DIR][blk * a.geo.PG + n_cell], cm = a.geo.cm[DIR][blk * a.geo.PG + n_cell];
+  recon_cell<2, MHD>(qm, q0, qp, cp, cm, up, lo);
+}
+
 template <bool MHD, class ST>
 __device__ __forceinline__ void ppm_recon_cell(const EosParams &eos, const ST &st, int off0, Real up[7],
                                                Real lo[7]) {
@@ -187,7 +213,7 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
     stage_row(n + R + HI);
     cp_async_commit();
     Real f[7];
-    if constexpr (ORDER == 3) {
+    if constexpr (ATHK_SHARED_RECON(ORDER)) {
       // PPM: every thread reconstructs ITS cell n once (parabola -> left state of face n+1,
       // right state of face n) and hands the left state to the thread above through shared
       // memory, instead of every face rebuilding the parabolas of both adjacent cells.
@@ -196,7 +222,8 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
       const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
       if (fvalid) {
         Real up[7];
-        ppm_recon_cell<MHD>(a.eos, st, 0, up, wr);
+        if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, 0, up, wr);
+        else plm_recon_cell<DIR, MHD>(a, vBlk[lane] & 0x1fffffff, st, 0, n, up, wr);
 #pragma unroll
         for (int v = 0; v < NW; ++v) sW[r][v][lane] = up[v];
         if (r == R - 1) {
@@ -205,7 +232,8 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
         }
         if (step == 0 && r == 0) {   // nobody owns cell n_s-1: the first face's left state
           Real lo_unused[7];
-          ppm_recon_cell<MHD>(a.eos, st, -1, up, lo_unused);
+          if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, -1, up, lo_unused);
+          else plm_recon_cell<DIR, MHD>(a, vBlk[lane] & 0x1fffffff, st, -1, n - 1, up, lo_unused);
 #pragma unroll
           for (int v = 0; v < NW; ++v) sWtop[1][v][lane] = up[v];
         }
@@ -343,7 +371,7 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   const unsigned grid = (unsigned)((ncol + 31) / 32);
 #if ATHK_TILE_STAGE
   constexpr int R = ATHK_TILE_R, NR = 2 * R + 2 * ORDER - 1, NQ = MHD ? 8 : 5;
-  constexpr size_t smem = sizeof(Real) * 32 * ((2 * R + 3) * 5 + NR * NQ + (ORDER == 3 ? (R + 2) * (MHD ? 7 : 5) : 0));
+  constexpr size_t smem = sizeof(Real) * 32 * ((2 * R + 3) * 5 + NR * NQ + (ATHK_SHARED_RECON(ORDER) ? (R + 2) * (MHD ? 7 : 5) : 0));
   static bool attr_set = false;   // > 48 KB of dynamic shared memory is opt-in, once per kernel
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_sweep_tile_staged<DIR, ORDER, MHD, RS>,
@@ -364,13 +392,13 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
 // (2.04 vs 1.89 ms per PLM sweep at 256^3): the x1 sweep's long-scoreboard stalls are register-
 // spill reloads, not the global loads, so it was dropped.
 //========================================================================================
-// x1 sweep for PPM with one parabola per cell (ATHK_X1_PPM_SHARE): the cells i = is-1 .. ie+1 of
-// all rows of a (k, MeshBlock) plane form one stream, lane L of a warp owns cell t = 30*warp + L,
+// x1 sweep with one reconstruction per cell (PPM, and PLM by ATHK_PLM_SHARE_X1): the cells
+// i = is-1 .. ie+1 of all rows of a (k, MeshBlock) plane form one stream, lane L of a warp owns cell t = 30*warp + L,
 // reconstructs it once (left state of face i+1, right state of face i) and passes the left state
 // to lane L+1 with a shuffle; lanes 1..31 solve the face below their cell, lanes 1..30 finish
-// their cell with the flux of lane L+1.  Consecutive warps overlap by two cells.  The plain
-// kernel rebuilds the parabolas of both cells at every face (10-14 ppm_cell per face instead of
-// 5-7).
+// their cell with the flux of lane L+1.  Consecutive warps overlap by two cells.  The face-centric
+// kernel (k_sweep_x1, athk_backend.h; still used for donor cell) rebuilds the slopes / parabolas
+// of both cells at every face (PPM: 10-14 ppm_cell per face instead of 5-7).
 #ifndef ATHK_X1_PPM_SHARE
 #define ATHK_X1_PPM_SHARE 1
 #endif
@@ -383,9 +411,9 @@ struct GlobalRowStencil {
   __device__ __forceinline__ void cell(int off, Real q[7]) const { load_q<0, MHD>(a, blk, c + off, q); }
 };
 
-template <bool MHD, int RS>
+template <int ORDER, bool MHD, int RS>
 __global__ void __launch_bounds__(128, ATHK_X1_MINB)
-k_sweep_x1_ppm(const SweepX1<3, MHD, RS> f, const int kl, const int jl, const int nj, const int icl,
+k_sweep_x1_cells(const SweepX1<ORDER, MHD, RS> f, const int kl, const int jl, const int nj, const int icl,
                const int ncr, const unsigned ncr_magic) {
   constexpr int NW = MHD ? 7 : 5;
   const SweepArgs &a = f.a;
@@ -411,7 +439,8 @@ k_sweep_x1_ppm(const SweepX1<3, MHD, RS> f, const int kl, const int jl, const in
   if (valid) {
     if (cell_upd) f.prefetch_cell(blk, k, j, i);
     const GlobalRowStencil<MHD> st = {a, blk, c};
-    ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
+    if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
+    else plm_recon_cell<0, MHD>(a, blk, st, 0, i, up, lo);
   }
   Real wl[7];
 #pragma unroll
@@ -437,12 +466,12 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
   const int nif = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
   if (nif <= 1 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
 #if ATHK_X1_PPM_SHARE
-  if constexpr (ORDER == 3) {
+  if constexpr (ATHK_SHARED_RECON_X1(ORDER)) {
     const int ncr = nif + 1;                       // cells il-1 .. iu of a row
     const int total = nj * ncr;
     const int nwarps = (total - 2 + 29) / 30;      // stride 30, two cells of overlap
     dim3 grid((unsigned)((nwarps + 3) / 4), (unsigned)nk, (unsigned)nb);
-    k_sweep_x1_ppm<MHD, RS><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il - 1, ncr, magic_u32(ncr));
+    k_sweep_x1_cells<ORDER, MHD, RS><<<grid, 128, 0, st>>>(f, r.kl, r.jl, nj, r.il - 1, ncr, magic_u32(ncr));
     return cudaGetLastError();
   }
 #endif
