@@ -15,7 +15,7 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__block
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct", "smsp__inst_executed.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
-NAMES = {"k_sweep_tile_staged<1,": "sweep_x2", "k_sweep_tile_staged<2,": "sweep_x3", "k_sweep_x1<": "sweep_x1",
+NAMES = {"k_sweep_tile_staged<1,": "sweep_x2", "k_sweep_tile_staged<2,": "sweep_x3", "k_sweep_x1<": "sweep_x1", "k_sweep_x1_cells<": "sweep_x1",
          "CornerEPoint": "corner_e", "Cons2PrimPoint": "cons2prim", "CTIntegratePoint": "ct_integrate"}
 
 
