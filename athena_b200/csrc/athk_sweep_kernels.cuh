@@ -80,7 +80,11 @@ struct SmemStencil {
 #define ATHK_PLM_SHARE_X1 1
 #endif
 #define ATHK_SHARED_RECON(ORDER) ((ORDER) == 3 || ((ORDER) == 2 && ATHK_PLM_SHARE_TILES))
-#define ATHK_SHARED_RECON_X1(ORDER) ((ORDER) == 3 || ((ORDER) == 2 && ATHK_PLM_SHARE_X1))
+#ifndef ATHK_DONOR_CELLS_X1
+#define ATHK_DONOR_CELLS_X1 0   // donor cell through the cell-owner x1 kernel: measured slower (1.56 vs 1.42 ms)
+#endif
+#define ATHK_SHARED_RECON_X1(ORDER) \
+  ((ORDER) == 3 || ((ORDER) == 2 && ATHK_PLM_SHARE_X1) || ((ORDER) == 1 && ATHK_DONOR_CELLS_X1))
 
 // PLM of every variable of the cell `off0` cells above the stencil's reference cell (index n_cell
 // along DIR): the two states recon_cell gives
@@ -439,8 +443,15 @@ k_sweep_x1_cells(const SweepX1<ORDER, MHD, RS> f, const int kl, const int jl, co
   if (valid) {
     if (cell_upd) f.prefetch_cell(blk, k, j, i);
     const GlobalRowStencil<MHD> st = {a, blk, c};
-    if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
-    else plm_recon_cell<0, MHD>(a, blk, st, 0, i, up, lo);
+    if constexpr (ORDER == 3) {
+      ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
+    } else if constexpr (ORDER == 2) {
+      plm_recon_cell<0, MHD>(a, blk, st, 0, i, up, lo);
+    } else {   // donor cell: both face states are the cell average (dc.cpp)
+      st.cell(0, up);
+#pragma unroll
+      for (int v = 0; v < NW; ++v) lo[v] = up[v];
+    }
   }
   Real wl[7];
 #pragma unroll
