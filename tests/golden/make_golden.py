@@ -111,6 +111,13 @@ CASES = {
                                                bcs=["outflow", "reflecting", "reflecting", "outflow",
                                                     "periodic", "periodic"],
                                                blast=dict(center=(0.55, -0.6, 0.0), radius=0.3)),
+    # extents that are neither powers of two nor multiples of 4 (row padding, tiles straddling rows)
+    "mhd_linwave_vl2_plm_hlld_oddmesh": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(24, 20, 28),
+                                             block=(12, 10, 14), tlim=0.05, integrator="vl2", xorder=2,
+                                             amp=1.0e-3),
+    "hydro_linwave_rk3_ppm_hllc_oddmesh": dict(cfg="linwave_hydro_hllc_g3", mhd=False, mesh=(22, 18, 26),
+                                               block=(11, 9, 13), tlim=0.05, integrator="rk3", xorder=3,
+                                               amp=1.0e-3, wave_flag=1, vflow=0.3),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),

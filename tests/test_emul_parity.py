@@ -18,7 +18,9 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          "hydro_kh_rk3_ppm_hllc_scalar", "hydro_kh_vl2_plm_hllc_2scalars", "mhd_kh_rk2_plm_hlld_scalar",
          # outflow / reflecting physical boundaries
          "hydro_sod_vl2_plm_hllc_outflow_x1", "mhd_briowu_rk2_plm_hlld_outflow_x2",
-         "mhd_blast_vl2_plm_hlld_reflecting_box", "hydro_blast_rk3_plm_hllc_mixed_bcs"]
+         "mhd_blast_vl2_plm_hlld_reflecting_box", "hydro_blast_rk3_plm_hllc_mixed_bcs",
+         # odd extents (11x9x13, 12x10x14 blocks): row padding, tiles / warps straddling rows
+         "mhd_linwave_vl2_plm_hlld_oddmesh", "hydro_linwave_rk3_ppm_hllc_oddmesh"]
 
 
 @pytest.mark.parametrize("name", CASES)

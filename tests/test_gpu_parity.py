@@ -12,7 +12,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(util.GOLDEN, "*.npz")))
-assert len(CASES) >= 16   # every committed reference fixture, all solvers / integrators / orders
+assert len(CASES) >= 27   # every committed reference fixture, all solvers / integrators / orders
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -105,7 +105,10 @@ DECOMPOSITION_SENSITIVE = {"mhd_linwave_alfven_vl2", "mhd_linwave_rk3_plm_roe_sl
 def test_cuda_fused_stage_wide_blocks_match_reference(cuda_lib, name):
     # a second decomposition of every fixture (nx1 = 32: full warps along x1, tiles that straddle rows)
     meta, _ = util.load_golden(name)
-    block = (32, meta["mesh"][1] // 2, meta["mesh"][2])
+    if meta["mesh"][0] != 32:   # the odd-extent fixtures: one block per mesh instead
+        block = tuple(meta["mesh"])
+    else:
+        block = (32, meta["mesh"][1] // 2, meta["mesh"][2])
     meta, z, ctx, ti = util.run_golden_case(cuda_lib, name, block=block, fused=True)
     if name in DECOMPOSITION_SENSITIVE:
         U, B = util.gather_from_ctx(ctx)
