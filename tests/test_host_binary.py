@@ -80,8 +80,8 @@ CASES = {
 }
 
 
-def run_host(binary, blocks, prob, mhd, extra=()):
-    wd = tempfile.mkdtemp(prefix="athhost_")
+def run_host(binary, blocks, prob, mhd, extra=(), wd=None):
+    wd = wd or tempfile.mkdtemp(prefix="athhost_")
     inp = os.path.join(wd, "athinput.host")
     with open(inp, "w") as f:
         f.write(refrun.format_athinput(blocks))
@@ -148,6 +148,56 @@ def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
 def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
     assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
     compare_with_reference(CUDA_BIN, case)
+
+
+# The reference's convergence regression (tst/regression/scripts/tests/{hydro,mhd}/*_linear_wave*):
+# run the wave for one period at two resolutions with problem/compute_error=true and read the rows
+# Mesh::UserWorkAfterLoop appends to linearwave-errors.dat (pgen/linear_wave.cpp:190-427).  North
+# star: the L1 error vectors agree to 1e-12 relative -- the printed rows are identical text.
+LINWAVE_ERR_CASES = {
+    "hydro_sound_plm": ("linwave_hydro_hllc", False, dict(wave_flag=0)),
+    "hydro_entropy_rk3": ("linwave_hydro_hllc", False, dict(wave_flag=3, vflow=1.0, integrator="rk3")),
+    "mhd_fast_plm": ("linwave_mhd_hlld", True, dict(wave_flag=0)),
+    "mhd_alfven_rk2": ("linwave_mhd_hlld", True, dict(wave_flag=1, integrator="rk2")),
+}
+
+
+def compare_linear_wave_errors(binary, case):
+    cfg, mhd, kw = LINWAVE_ERR_CASES[case]
+    if not refrun.have_ref(cfg):
+        pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
+    wd_ref, wd = tempfile.mkdtemp(prefix="athref_"), tempfile.mkdtemp(prefix="athhost_")
+    try:
+        for n in (16, 32):
+            blocks = refrun.linwave_blocks(mhd, mesh=(n, n // 2, n // 2), block=(n // 2, n // 4, n // 4),
+                                           tlim=1.0, **kw)
+            blocks["problem"]["compute_error"] = "true"
+            refrun.run_reference(cfg, blocks, workdir=wd_ref)
+            _, r = run_host(binary, blocks, "linear_wave", mhd, wd=wd)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        ref = open(os.path.join(wd_ref, "linearwave-errors.dat")).read()
+        ours = open(os.path.join(wd, "linearwave-errors.dat")).read()
+        assert ours == ref        # header once, one row per resolution, every printed digit
+        rows = np.array([[float(x) for x in l.split()] for l in ours.splitlines() if not l.startswith("#")])
+        assert rows.shape[0] == 2 and rows[0, 0] == 16 and rows[1, 0] == 32
+        nv = 8 if mhd else 5
+        np.testing.assert_allclose(rows[:, 4], np.sqrt((rows[:, 5:5 + nv] ** 2).sum(axis=1)), rtol=1e-5)
+        assert rows[1, 4] < rows[0, 4] / 3.0   # second-order scheme: RMS L1 error drops ~4x per doubling
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+        shutil.rmtree(wd_ref, ignore_errors=True)
+
+
+@pytest.mark.parametrize("case", sorted(LINWAVE_ERR_CASES))
+def test_linear_wave_error_vectors_match_reference(emul_binary, case):
+    compare_linear_wave_errors(emul_binary, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(LINWAVE_ERR_CASES))
+def test_linear_wave_error_vectors_on_gpu_match_reference(cuda_lib, case):
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    compare_linear_wave_errors(CUDA_BIN, case)
 
 
 def test_parameter_input_error_behaviour(emul_binary):
