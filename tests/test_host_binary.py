@@ -200,6 +200,61 @@ def test_linear_wave_error_vectors_on_gpu_match_reference(cuda_lib, case):
     compare_linear_wave_errors(CUDA_BIN, case)
 
 
+# Known answers the survey captured from the unmodified reference ("Oracle outputs
+# captured in this survey"; g++ -O3): BASELINE configs[0] at its full size and an 8-block MHD wave.
+# These do not need oracle/_ref at test time.
+KNOWN_ANSWERS = {
+    "hydro_64cubed_config0": dict(
+        mhd=False, mesh=(64, 64, 64), block=(64, 64, 64), tlim=1.0, ncycle=143,
+        errors={"RMS-L1-Error": "1.336316e-08", "d_L1": "6.501698e-09"},
+        last_dt=3.1269611416973042e-03, hst_row=-1,
+        hst={"mass": 6.7499999999971791e+00, "tot-E": 6.0749999999967788e+00}),
+    "mhd_64x32x32_8blocks": dict(
+        mhd=True, mesh=(64, 32, 32), block=(32, 16, 16), tlim=0.5, ncycle=72,
+        errors={"RMS-L1-Error": "5.973017e-08"},
+        first_dt=7.0317065028282708e-03, hst_row=0,
+        hst={"mass": 6.7500000000002407e+00, "tot-E": 1.7043749999996553e+01, "1-ME": 3.9413321153603178e+00,
+             "2-ME": 3.3816169015164186e+00, "3-ME": 3.6458009831252944e+00}),
+}
+
+
+def check_known_answer(binary, case):
+    ka = KNOWN_ANSWERS[case]
+    blocks = refrun.linwave_blocks(ka["mhd"], mesh=ka["mesh"], block=ka["block"], tlim=ka["tlim"])
+    blocks["problem"]["compute_error"] = "true"
+    wd, r = run_host(binary, blocks, "linear_wave", ka["mhd"])
+    try:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        head, row = open(os.path.join(wd, "linearwave-errors.dat")).read().splitlines()
+        cols = dict(zip(head.lstrip("#").split(), row.split()))
+        assert int(cols["Ncycle"]) == ka["ncycle"]
+        for k, v in ka["errors"].items():
+            assert cols[k] == v, (k, cols[k], v)
+        dts = [float(l.split("dt=")[1]) for l in r.stdout.splitlines() if l.startswith("cycle=")]
+        if "first_dt" in ka:
+            assert dts[0] == ka["first_dt"]
+        if "last_dt" in ka:
+            assert dts[-1] == ka["last_dt"]
+        names, h = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
+        for k, v in ka["hst"].items():
+            got = h[ka["hst_row"], names.index(k)]
+            assert abs(got - v) <= 1e-10 * abs(v), (k, got, v)   # north-star history tolerance
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+@pytest.mark.parametrize("case", sorted(KNOWN_ANSWERS))
+def test_survey_known_answers(emul_binary, case):
+    check_known_answer(emul_binary, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(KNOWN_ANSWERS))
+def test_survey_known_answers_on_gpu(cuda_lib, case):
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    check_known_answer(CUDA_BIN, case)
+
+
 def test_parameter_input_error_behaviour(emul_binary):
     """Missing parameter / unknown cmdline override / unpaired periodic BC: message + exit status as
     ATHENA_ERROR does (src/defs.hpp.in:155-159, parameter_input.cpp:352-395)."""
