@@ -200,6 +200,70 @@ def test_linear_wave_error_vectors_on_gpu_match_reference(cuda_lib, case):
     compare_linear_wave_errors(CUDA_BIN, case)
 
 
+# tst/regression/scripts/tests/symmetry/hydro_linwave_aligned.py, restricted to the 3-D update: a
+# sound wave along x1, x2 and x3 of a cube.  The x1 sweep is a different kernel from the x2/x3
+# sweeps (rows vs shared-memory tiles), so the three runs must agree the way the reference's do:
+# identical error rows under the momentum permutation, and (stronger than the reference's 5e-15)
+# the same density/energy/normal-momentum profile along the wave vector, digit for digit.
+def global_cons(rst):
+    nx1, nx2, nx3 = rst["nx"]
+    ng = rst["ng"]
+    m = rst["mesh_nx"]
+    g = np.zeros((5, m[2], m[1], m[0]))
+    for (l1, l2, l3, _), u in zip(rst["loc"], rst["u"]):
+        g[:, l3 * nx3:(l3 + 1) * nx3, l2 * nx2:(l2 + 1) * nx2, l1 * nx1:(l1 + 1) * nx1] = \
+            u[:, ng:ng + nx3, ng:ng + nx2, ng:ng + nx1]
+    return g
+
+
+def check_axis_symmetry(binary, integrator, xorder, extra):
+    wd = tempfile.mkdtemp(prefix="athhost_")
+    aligned = (dict(ang_2=0.0, ang_3=0.0), dict(ang_2=0.0, ang_3_vert="true"), dict(ang_2_vert="true"))
+    try:
+        fields = []
+        for kw in aligned:
+            blocks = refrun.linwave_blocks(False, mesh=(16, 16, 16), block=(8, 8, 8), tlim=1.0, rst_dt=1.0,
+                                           integrator=integrator, xorder=xorder)
+            for d in "123":
+                blocks["mesh"]["x%smax" % d] = 1.0
+            blocks["problem"].update(kw, compute_error="true")
+            for f in glob.glob(wd + "/*.rst"):
+                os.remove(f)
+            _, r = run_host(binary, blocks, "linear_wave", False, extra=extra, wd=wd)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            fields.append(global_cons(refrun.read_rst(sorted(glob.glob(wd + "/*.rst"))[-1])))
+        rows = [l.split() for l in open(os.path.join(wd, "linearwave-errors.dat")).read().splitlines()[1:]]
+        perm = ([6, 7, 8], [7, 8, 6], [8, 6, 7])     # (normal, transverse, transverse) momentum L1 columns
+        key = lambda row, p: row[3:6] + [row[c] for c in p] + row[9:12] + [row[c + 6] for c in p] + row[15:]   # noqa: E731
+        assert key(rows[0], perm[0]) == key(rows[1], perm[1]) == key(rows[2], perm[2])
+        u1, u2, u3 = fields
+        for a, b in ((IDN, IDN), (IEN, IEN)):
+            np.testing.assert_array_equal(u1[a, 0, 0, :], u2[b, 0, :, 0])
+            np.testing.assert_array_equal(u1[a, 0, 0, :], u3[b, :, 0, 0])
+        np.testing.assert_array_equal(u1[1, 0, 0, :], u2[2, 0, :, 0])
+        np.testing.assert_array_equal(u1[1, 0, 0, :], u3[3, :, 0, 0])
+        assert np.ptp(u1[IDN], axis=(0, 1)).max() == 0.0 and np.ptp(u2[IDN], axis=(0, 2)).max() == 0.0 \
+            and np.ptp(u3[IDN], axis=(1, 2)).max() == 0.0      # planar waves stay planar
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+IDN, IEN = 0, 4
+SYMMETRY_CASES = {"vl2_plm": ("vl2", 2, []), "rk3_ppm": ("rk3", 3, ["--nghost=3"])}
+
+
+@pytest.mark.parametrize("case", sorted(SYMMETRY_CASES))
+def test_axis_aligned_waves_are_symmetric(emul_binary, case):
+    check_axis_symmetry(emul_binary, *SYMMETRY_CASES[case])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(SYMMETRY_CASES))
+def test_axis_aligned_waves_are_symmetric_on_gpu(cuda_lib, case):
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    check_axis_symmetry(CUDA_BIN, *SYMMETRY_CASES[case])
+
+
 # Known answers the survey captured from the unmodified reference ("Oracle outputs
 # captured in this survey"; g++ -O3): BASELINE configs[0] at its full size and an 8-block MHD wave.
 # These do not need oracle/_ref at test time.
