@@ -305,6 +305,34 @@ static void ShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
 }
 
 //========================================================================================
+// B = curl A on the faces of the active zone from edge-centred potentials (the construction
+// linear_wave.cpp:503-528, cpaw.cpp:290-315 and field_loop.cpp:226-250 share): div B = 0 to rounding
+static void FaceFieldFromPotential(MeshBlock *pmb, const AthenaArray<Real> &a1, const AthenaArray<Real> &a2,
+                                   const AthenaArray<Real> &a3) {
+  Coordinates *pc = pmb->pcoord;
+  const int is = pmb->is, ie = pmb->ie, js = pmb->js, je = pmb->je, ks = pmb->ks, ke = pmb->ke;
+  FaceField &b = pmb->pfield->b;
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie + 1; i++)
+        b.x1f(k, j, i) = (a3(k, j + 1, i) - a3(k, j, i)) / pc->dx2f(j) - (a2(k + 1, j, i) - a2(k, j, i)) / pc->dx3f(k);
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie; i++)
+        b.x2f(k, j, i) = (a1(k + 1, j, i) - a1(k, j, i)) / pc->dx3f(k) - (a3(k, j, i + 1) - a3(k, j, i)) / pc->dx1f(i);
+  for (int k = ks; k <= ke + 1; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++)
+        b.x3f(k, j, i) = (a2(k, j, i + 1) - a2(k, j, i)) / pc->dx1f(i) - (a1(k, j + 1, i) - a1(k, j, i)) / pc->dx2f(j);
+}
+
+// magnetic energy of a cell from its face fields, 0.5*(<B1>^2 + <B2>^2 + <B3>^2)
+static Real CellMagneticEnergy(const FaceField &b, int k, int j, int i) {
+  return 0.5 * (SQR(0.5 * (b.x1f(k, j, i) + b.x1f(k, j, i + 1))) + SQR(0.5 * (b.x2f(k, j, i) + b.x2f(k, j + 1, i))) +
+                SQR(0.5 * (b.x3f(k, j, i) + b.x3f(k + 1, j, i))));
+}
+
+//========================================================================================
 // linear_wave
 namespace {
 Real amp, vflow, ang_2, ang_3, sin_a2, cos_a2, sin_a3, cos_a3, lambda, k_par, gam, gm1;
@@ -488,19 +516,7 @@ static void LinearWaveGenerator(MeshBlock *pmb, ParameterInput *) {
           a2(k, j, i) = A2(pc->x1f(i), pc->x2v(j), pc->x3f(k));
           a3(k, j, i) = A3(pc->x1f(i), pc->x2f(j), pc->x3v(k));
         }
-    FaceField &b = pmb->pfield->b;
-    for (int k = ks; k <= ke; k++)
-      for (int j = js; j <= je; j++)
-        for (int i = is; i <= ie + 1; i++)
-          b.x1f(k, j, i) = (a3(k, j + 1, i) - a3(k, j, i)) / pc->dx2f(j) - (a2(k + 1, j, i) - a2(k, j, i)) / pc->dx3f(k);
-    for (int k = ks; k <= ke; k++)
-      for (int j = js; j <= je + 1; j++)
-        for (int i = is; i <= ie; i++)
-          b.x2f(k, j, i) = (a1(k + 1, j, i) - a1(k, j, i)) / pc->dx3f(k) - (a3(k, j, i + 1) - a3(k, j, i)) / pc->dx1f(i);
-    for (int k = ks; k <= ke + 1; k++)
-      for (int j = js; j <= je; j++)
-        for (int i = is; i <= ie; i++)
-          b.x3f(k, j, i) = (a2(k, j, i + 1) - a2(k, j, i)) / pc->dx1f(i) - (a1(k, j + 1, i) - a1(k, j, i)) / pc->dx2f(j);
+    FaceFieldFromPotential(pmb, a1, a2, a3);
   }
   AthenaArray<Real> &u = pmb->phydro->u;
   for (int k = ks; k <= ke; k++)
@@ -614,6 +630,255 @@ static void LinearWaveErrors(Mesh *pm, ParameterInput *pin) {
   std::fclose(pfile);
 }
 
+// the reference refuses to compile these pgens without -b (#error); here the check is at run time
+static void RequireMagneticFields(const char *prob) {
+  if (MAGNETIC_FIELDS_ENABLED) return;
+  std::stringstream msg;
+  msg << "### FATAL ERROR in problem generator " << prob << std::endl
+      << "This problem generator requires magnetic fields (-b)" << std::endl;
+  ATHENA_ERROR(msg);
+}
+
+
+//========================================================================================
+// cpaw -- circularly polarised Alfven wave (src/pgen/cpaw.cpp: setup :55-105, ICs :212-355,
+// potentials :360-390, errors :108-205).  Exact nonlinear solution of ideal MHD: the regression
+// test mhd/cpaw.py measures convergence of the rows appended to cpaw-errors.dat.
+namespace cpaw {
+Real den, pres, gm1, b_par, b_perp, v_perp, v_par, fac, sin_a2, cos_a2, sin_a3, cos_a3, k_par;
+
+struct Rotated { Real x, y; };
+inline Rotated WaveFrame(Real x1, Real x2, Real x3) {
+  return {x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2, -x1 * sin_a3 + x2 * cos_a3};
+}
+inline Real PotY(Real x) { return fac * (b_perp / k_par) * std::sin(k_par * (x)); }
+inline Real PotZ(Real x, Real y) { return (b_perp / k_par) * std::cos(k_par * (x)) + b_par * y; }
+Real A1(Real x1, Real x2, Real x3) {
+  const Rotated r = WaveFrame(x1, x2, x3);
+  return -PotY(r.x) * sin_a3 - PotZ(r.x, r.y) * sin_a2 * cos_a3;
+}
+Real A2(Real x1, Real x2, Real x3) {
+  const Rotated r = WaveFrame(x1, x2, x3);
+  return PotY(r.x) * cos_a3 - PotZ(r.x, r.y) * sin_a2 * sin_a3;
+}
+Real A3(Real x1, Real x2, Real x3) {
+  const Rotated r = WaveFrame(x1, x2, x3);
+  return PotZ(r.x, r.y) * cos_a2;
+}
+
+// momentum and cell-centred field of the exact wave at phase k_par*x, rotated to the mesh axes
+struct WaveState { Real m1, m2, m3, b1, b2, b3; };
+inline WaveState Exact(Real x) {
+  const Real sn = std::sin(k_par * x);
+  const Real cs = fac * std::cos(k_par * x);
+  const Real mx = den * v_par, my = -fac * den * v_perp * sn, mz = -fac * den * v_perp * cs;
+  const Real bx = b_par, by = b_perp * sn, bz = b_perp * cs;
+  WaveState w;
+  w.m1 = mx * cos_a2 * cos_a3 - my * sin_a3 - mz * sin_a2 * cos_a3;
+  w.m2 = mx * cos_a2 * sin_a3 + my * cos_a3 - mz * sin_a2 * sin_a3;
+  w.m3 = mx * sin_a2 + mz * cos_a2;
+  w.b1 = bx * cos_a2 * cos_a3 - by * sin_a3 - bz * sin_a2 * cos_a3;
+  w.b2 = bx * cos_a2 * sin_a3 + by * cos_a3 - bz * sin_a2 * sin_a3;
+  w.b3 = bx * sin_a2 + bz * cos_a2;
+  return w;
+}
+
+static void CpawInit(Mesh *pm, ParameterInput *pin) {
+  RequireMagneticFields("cpaw");
+  b_par = pin->GetReal("problem", "b_par");
+  b_perp = pin->GetReal("problem", "b_perp");
+  v_par = pin->GetReal("problem", "v_par");
+  Real ang_2 = pin->GetOrAddReal("problem", "ang_2", -999.9);
+  Real ang_3 = pin->GetOrAddReal("problem", "ang_3", -999.9);
+  const Real dir = pin->GetOrAddReal("problem", "dir", 1);   // right (1) / left (2) polarisation
+  gm1 = pin->GetReal("hydro", "gamma") - 1.0;
+  pres = pin->GetReal("problem", "pres");
+  den = 1.0;
+  const Real x1size = pm->mesh_size.x1max - pm->mesh_size.x1min;
+  const Real x2size = pm->mesh_size.x2max - pm->mesh_size.x2min;
+  const Real x3size = pm->mesh_size.x3max - pm->mesh_size.x3min;
+  if (ang_3 == -999.9) ang_3 = std::atan(x1size / x2size);
+  sin_a3 = std::sin(ang_3);
+  cos_a3 = std::cos(ang_3);
+  if (ang_2 == -999.9) ang_2 = std::atan(0.5 * (x1size * cos_a3 + x2size * sin_a3) / x3size);
+  sin_a2 = std::sin(ang_2);
+  cos_a2 = std::cos(ang_2);
+  Real lambda = x1size * cos_a2 * cos_a3;
+  if (pm->f2 && ang_3 != 0.0) lambda = std::min(lambda, x2size * cos_a2 * sin_a3);
+  if (pm->f3 && ang_2 != 0.0) lambda = std::min(lambda, x3size * sin_a2);
+  k_par = 2.0 * (PI) / lambda;
+  v_perp = b_perp / std::sqrt(den);
+  fac = (dir == 1) ? 1.0 : -1.0;
+}
+
+static void CpawGenerator(MeshBlock *pmb, ParameterInput *) {
+  Coordinates *pc = pmb->pcoord;
+  const int is = pmb->is, ie = pmb->ie, js = pmb->js, je = pmb->je, ks = pmb->ks, ke = pmb->ke;
+  AthenaArray<Real> a1, a2, a3;
+  a1.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  a2.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  a3.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  // uniform level: the single-point branches of cpaw.cpp:225-285
+  for (int k = ks; k <= ke + 1; k++)
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie + 1; i++) {
+        a1(k, j, i) = A1(pc->x1v(i), pc->x2f(j), pc->x3f(k));
+        a2(k, j, i) = A2(pc->x1f(i), pc->x2v(j), pc->x3f(k));
+        a3(k, j, i) = A3(pc->x1f(i), pc->x2f(j), pc->x3v(k));
+      }
+  FaceFieldFromPotential(pmb, a1, a2, a3);
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        const Real x = cos_a2 * (pc->x1v(i) * cos_a3 + pc->x2v(j) * sin_a3) + pc->x3v(k) * sin_a2;
+        const WaveState w = Exact(x);
+        u(IDN, k, j, i) = den;
+        u(IM1, k, j, i) = w.m1;
+        u(IM2, k, j, i) = w.m2;
+        u(IM3, k, j, i) = w.m3;
+        u(IEN, k, j, i) = pres / gm1 + CellMagneticEnergy(pmb->pfield->b, k, j, i) +
+                          (0.5 / den) * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i)));
+      }
+}
+
+// mean absolute error per cell against the initial wave, appended to cpaw-errors.dat
+static void CpawErrors(Mesh *pm, ParameterInput *pin) {
+  if (!pin->GetOrAddBoolean("problem", "compute_error", false)) return;
+  pm->DownloadAll();
+  Real err[NHYDRO + 3] = {};
+  for (int b = 0; b < pm->nblocal; ++b) {
+    MeshBlock *pmb = pm->my_blocks(b);
+    Coordinates *pc = pmb->pcoord;
+    const AthenaArray<Real> &u = pmb->phydro->u, &bcc = pmb->pfield->bcc;
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie; i++) {
+          const Real x = cos_a2 * (pc->x1v(i) * cos_a3 + pc->x2v(j) * sin_a3) + pc->x3v(k) * sin_a2;
+          const WaveState w = Exact(x);
+          err[IDN] += std::abs(den - u(IDN, k, j, i));
+          err[IM1] += std::abs(w.m1 - u(IM1, k, j, i));
+          err[IM2] += std::abs(w.m2 - u(IM2, k, j, i));
+          err[IM3] += std::abs(w.m3 - u(IM3, k, j, i));
+          err[NHYDRO + IB1] += std::abs(w.b1 - bcc(IB1, k, j, i));
+          err[NHYDRO + IB2] += std::abs(w.b2 - bcc(IB2, k, j, i));
+          err[NHYDRO + IB3] += std::abs(w.b3 - bcc(IB3, k, j, i));
+          const Real e0 = pres / gm1 + 0.5 * (w.m1 * w.m1 + w.m2 * w.m2 + w.m3 * w.m3) / den +
+                          0.5 * (w.b1 * w.b1 + w.b2 * w.b2 + w.b3 * w.b3);
+          err[IEN] += std::abs(e0 - u(IEN, k, j, i));
+        }
+  }
+  const Real ncells = static_cast<Real>(static_cast<std::int64_t>(pm->mesh_size.nx1) * pm->mesh_size.nx2 *
+                                        pm->mesh_size.nx3);
+  Real rms_err = 0.0;
+  for (int n = 0; n < NHYDRO + 3; ++n) err[n] = err[n] / ncells;
+  for (int n = 0; n < NHYDRO + 3; ++n) rms_err += SQR(err[n]);
+  rms_err = std::sqrt(rms_err);
+  const char *fname = "cpaw-errors.dat";
+  FILE *pfile = std::fopen(fname, "r");
+  const bool fresh = (pfile == nullptr);
+  if (pfile != nullptr) std::fclose(pfile);
+  pfile = std::fopen(fname, fresh ? "w" : "a");
+  if (pfile == nullptr) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in function [Mesh::UserWorkAfterLoop]" << std::endl
+        << "Error output file could not be opened" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  if (fresh) std::fprintf(pfile, "# Nx1  Nx2  Nx3  Ncycle  RMS-Error  d  M1  M2  M3  E  B1c  B2c  B3c\n");
+  std::fprintf(pfile, "%d  %d  %d  %d  %e", pm->mesh_size.nx1, pm->mesh_size.nx2, pm->mesh_size.nx3, pm->ncycle,
+               rms_err);
+  for (int n = 0; n < NHYDRO + 3; ++n) std::fprintf(pfile, "  %e", err[n]);
+  std::fprintf(pfile, "\n");
+  std::fclose(pfile);
+}
+}  // namespace cpaw
+
+//========================================================================================
+// field_loop -- advection of a weak field loop (src/pgen/field_loop.cpp:52-262; Gardiner & Stone
+// 2005/2008): the classic test of the CT update.  iprob 1/2/3: cylindrical loop along x3/x1/x2,
+// 4: cylinder rotated about x2, 5: spherical loop.  Shearing-box terms are not part of this path.
+static void FieldLoopGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  RequireMagneticFields("field_loop");
+  Coordinates *pc = pmb->pcoord;
+  const int is = pmb->is, ie = pmb->ie, js = pmb->js, je = pmb->je, ks = pmb->ks, ke = pmb->ke;
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  AthenaArray<Real> ax, ay, az;
+  ax.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  ay.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  az.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  const Real rad = pin->GetReal("problem", "rad");
+  const Real amp = pin->GetReal("problem", "amp");
+  const Real vflow = pin->GetReal("problem", "vflow");
+  const Real drat = pin->GetOrAddReal("problem", "drat", 1.0);
+  const int iprob = pin->GetInteger("problem", "iprob");
+  const RegionSize &ms = pmb->pmy_mesh->mesh_size;
+  const Real x1size = ms.x1max - ms.x1min, x2size = ms.x2max - ms.x2min, x3size = ms.x3max - ms.x3min;
+  Real cos_a2 = 0.0, sin_a2 = 0.0, lambda = 0.0;
+  if (iprob == 4) {   // wavevector in the x1-x3 plane, one wavelength across the domain
+    if (x1size == x3size) {
+      cos_a2 = sin_a2 = std::sqrt(0.5);
+    } else {
+      const Real ang_2 = std::atan(x1size / x3size);
+      sin_a2 = std::sin(ang_2);
+      cos_a2 = std::cos(ang_2);
+    }
+    lambda = (cos_a2 >= sin_a2) ? x1size * cos_a2 : x3size * sin_a2;
+  }
+  const Real x0 = pin->GetOrAddReal("problem", "x0", 0.0);
+  const Real y0 = pin->GetOrAddReal("problem", "y0", 0.0);
+  // A = amp*(rad - r) inside the loop of radius rad, 0 outside
+  auto cone = [&](Real rsq) { return (rsq < rad * rad) ? amp * (rad - std::sqrt(rsq)) : 0.0; };
+  auto wrap = [&](Real x) {
+    while (x > 0.5 * lambda) x -= lambda;
+    while (x < -0.5 * lambda) x += lambda;
+    return x;
+  };
+  for (int k = ks; k <= ke + 1; k++)
+    for (int j = js; j <= je + 1; j++)
+      for (int i = is; i <= ie + 1; i++) {
+        Real vx = 0.0, vy = 0.0, vz = 0.0;
+        switch (iprob) {
+          case 1: vz = cone(SQR(pc->x1f(i) - x0) + SQR(pc->x2f(j) - y0)); break;
+          case 2: vx = cone(SQR(pc->x2f(j)) + SQR(pc->x3f(k))); break;
+          case 3: vy = cone(SQR(pc->x1f(i)) + SQR(pc->x3f(k))); break;
+          case 4: {
+            const Real y = pc->x2f(j);
+            Real x = wrap(pc->x1v(i) * cos_a2 + pc->x3f(k) * sin_a2);
+            vx = ((x * x + y * y) < rad * rad) ? amp * (rad - std::sqrt(x * x + y * y)) * (-sin_a2) : 0.0;
+            x = wrap(pc->x1f(i) * cos_a2 + pc->x3v(k) * sin_a2);
+            vz = ((x * x + y * y) < rad * rad) ? amp * (rad - std::sqrt(x * x + y * y)) * (cos_a2) : 0.0;
+            break;
+          }
+          case 5:
+            vy = cone(SQR(pc->x1f(i)) + SQR(pc->x2v(j)) + SQR(pc->x3f(k)));
+            vz = cone(SQR(pc->x1f(i)) + SQR(pc->x2f(j)) + SQR(pc->x3v(k)));
+            break;
+          default: break;
+        }
+        ax(k, j, i) = vx;
+        ay(k, j, i) = vy;
+        az(k, j, i) = vz;
+      }
+  const Real diag = std::sqrt(x1size * x1size + x2size * x2size + x3size * x3size);
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++) {
+        const bool inside = (SQR(pc->x1v(i)) + SQR(pc->x2v(j)) + SQR(pc->x3v(k))) < rad * rad;
+        u(IDN, k, j, i) = inside ? drat : 1.0;
+        u(IM1, k, j, i) = u(IDN, k, j, i) * vflow * x1size / diag;
+        u(IM2, k, j, i) = u(IDN, k, j, i) * vflow * x2size / diag;
+        u(IM3, k, j, i) = u(IDN, k, j, i) * vflow * x3size / diag;
+      }
+  FaceFieldFromPotential(pmb, ax, ay, az);
+  for (int k = ks; k <= ke; k++)
+    for (int j = js; j <= je; j++)
+      for (int i = is; i <= ie; i++)
+        u(IEN, k, j, i) = 1.0 / gm1 + CellMagneticEnergy(pmb->pfield->b, k, j, i) +
+                          (0.5) * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i))) / u(IDN, k, j, i);
+}
+
 //========================================================================================
 static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
@@ -621,6 +886,8 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
     {"kh", KHInitUserMeshData, KHGenerator, nullptr},
     {"shock_tube", nullptr, ShockTubeGenerator, nullptr},
+    {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
+    {"field_loop", nullptr, FieldLoopGenerator, nullptr},
 };
 
 const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {

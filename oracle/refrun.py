@@ -44,6 +44,8 @@ CONFIGS = {
     "kh_mhd_hlld_s1": dict(PROB="kh", MHD=1, FLUX="hlld", NSCALARS=1),
     "linwave_hydro_hllc_g3": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=3),
     "linwave_mhd_hlld_g3": dict(PROB="linear_wave", MHD=1, FLUX="hlld", NGHOST=3),
+    "cpaw_mhd_hlld": dict(PROB="cpaw", MHD=1, FLUX="hlld"),
+    "fieldloop_mhd_hlld": dict(PROB="field_loop", MHD=1, FLUX="hlld"),
 }
 
 
@@ -336,6 +338,50 @@ def shocktube_blocks(mhd, left, right, shock_dir=1, xshock=None, bx=0.0, bcs=Non
             pr["bx" + side], pr["by" + side], pr["bz" + side] = float(bx), float(st[5]), float(st[6])
     b["problem"] = pr
     return set_bcs(b, bcs)
+
+
+def periodic_mesh(mesh, block, lo, hi):
+    m = {}
+    for d in range(3):
+        m.update({"nx%d" % (d + 1): mesh[d], "x%dmin" % (d + 1): lo[d], "x%dmax" % (d + 1): hi[d],
+                  "ix%d_bc" % (d + 1): "periodic", "ox%d_bc" % (d + 1): "periodic"})
+    m.update(num_threads=1, refinement="none")
+    block = block or mesh
+    return m, {"nx1": block[0], "nx2": block[1], "nx3": block[2]}
+
+
+def cpaw_blocks(mesh=(32, 16, 16), block=(16, 8, 8), tlim=1.0, rst_dt=None, integrator="vl2", xorder=2,
+                cfl=0.3, v_par=0.0, direction=1, compute_error=True):
+    """Circularly polarised Alfven wave (inputs/mhd/athinput.cpaw2d parameters on the 3-D box of the
+    linear-wave inputs)."""
+    m, mb = periodic_mesh(mesh, block, (0.0, 0.0, 0.0), (3.0, 1.5, 1.5))
+    return {
+        "job": {"problem_id": "cpaw"},
+        "output1": {"file_type": "hst", "dt": 0.05, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 1.0e30 if rst_dt is None else rst_dt},
+        "time": {"cfl_number": cfl, "nlim": -1, "tlim": tlim, "integrator": integrator, "xorder": xorder,
+                 "ncycle_out": 1},
+        "mesh": m, "meshblock": mb,
+        "hydro": {"gamma": 1.666666666666667, "iso_sound_speed": 1.0},
+        "problem": {"compute_error": "true" if compute_error else "false", "b_par": 1.0, "b_perp": 0.1,
+                    "pres": 0.1, "v_par": v_par, "dir": direction},
+    }
+
+
+def fieldloop_blocks(iprob=1, mesh=(32, 16, 16), block=(16, 8, 8), tlim=0.3, rst_dt=None, integrator="vl2",
+                     xorder=2, cfl=0.3, drat=1.0):
+    """Field-loop advection (inputs/mhd/athinput.field_loop parameters, 3-D box)."""
+    m, mb = periodic_mesh(mesh, block, (-1.0, -0.5, -0.5), (1.0, 0.5, 0.5))
+    return {
+        "job": {"problem_id": "Loop"},
+        "output1": {"file_type": "hst", "dt": 0.05, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 1.0e30 if rst_dt is None else rst_dt},
+        "time": {"cfl_number": cfl, "nlim": -1, "tlim": tlim, "integrator": integrator, "xorder": xorder,
+                 "ncycle_out": 1},
+        "mesh": m, "meshblock": mb,
+        "hydro": {"iso_sound_speed": 1.732, "gamma": 1.66667},
+        "problem": {"rad": 0.3, "amp": 1.0e-3, "vflow": 3.0, "iprob": iprob, "drat": drat},
+    }
 
 
 def linwave_blocks(mhd, mesh=(32, 16, 16), block=None, tlim=0.1, nlim=-1, wave_flag=0,

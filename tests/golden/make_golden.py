@@ -118,6 +118,12 @@ CASES = {
     "hydro_linwave_rk3_ppm_hllc_oddmesh": dict(cfg="linwave_hydro_hllc_g3", mhd=False, mesh=(22, 18, 26),
                                                block=(11, 9, 13), tlim=0.05, integrator="rk3", xorder=3,
                                                amp=1.0e-3, wave_flag=1, vflow=0.3),
+    # vector-potential problems of the reference's MHD regression set: a nonlinear exact solution
+    # (cpaw) and a loop in an otherwise field-free box (HLLD / CT with B == 0 almost everywhere)
+    "mhd_cpaw_rk3_plm_hlld": dict(cfg="cpaw_mhd_hlld", mhd=True, mesh=(32, 16, 16), block=(16, 8, 8),
+                                  tlim=0.1, integrator="rk3", xorder=2, cpaw=dict(v_par=1.0, direction=2)),
+    "mhd_fieldloop_vl2_plm_hlld": dict(cfg="fieldloop_mhd_hlld", mhd=True, mesh=(32, 16, 16), block=(16, 8, 8),
+                                       tlim=0.1, integrator="vl2", xorder=2, fieldloop=dict(iprob=5, drat=2.0)),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),
@@ -140,6 +146,15 @@ def make(name):
                                      integrator=c["integrator"], xorder=c["xorder"], bcs=c.get("bcs"),
                                      **c["blast"])
         xmin, xmax, gamma = [-1.0] * 3, [1.0] * 3, blocks["hydro"]["gamma"]
+    elif "cpaw" in c:
+        blocks = refrun.cpaw_blocks(mesh=c["mesh"], block=c["block"], tlim=c["tlim"], integrator=c["integrator"],
+                                    xorder=c["xorder"], compute_error=False, **c["cpaw"])
+        blocks["output1"]["dt"] = 1.0e-9      # a history row every cycle (the dt sequence)
+    elif "fieldloop" in c:
+        blocks = refrun.fieldloop_blocks(mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
+                                         integrator=c["integrator"], xorder=c["xorder"], **c["fieldloop"])
+        blocks["output1"]["dt"] = 1.0e-9
+        xmin, xmax, gamma = [-1.0, -0.5, -0.5], [1.0, 0.5, 0.5], blocks["hydro"]["gamma"]
     elif "shocktube" in c:
         blocks = refrun.shocktube_blocks(c["mhd"], mesh=c["mesh"], block=c["block"], tlim=c["tlim"],
                                          integrator=c["integrator"], xorder=c["xorder"], bcs=c.get("bcs"),

@@ -12,7 +12,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(util.GOLDEN, "*.npz")))
-assert len(CASES) >= 27   # every committed reference fixture, all solvers / integrators / orders
+assert len(CASES) >= 29   # every committed reference fixture, all solvers / integrators / orders
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -75,6 +75,18 @@ CASES = {
     # BASELINE configs[2] names Orszag-Tang next to the blast wave
     "orszag_tang_rk2": ("ot_mhd_hlld", "orszag_tang", True,
                         lambda: refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk2")),
+    # the two classic CT problems of the reference's MHD regression set (mhd/cpaw.py; Gardiner & Stone
+    # field loop): vector-potential initial data, errors appended by UserWorkAfterLoop
+    "cpaw_standing_rk3": ("cpaw_mhd_hlld", "cpaw", True,
+                          lambda: refrun.cpaw_blocks(tlim=0.2, rst_dt=0.1, integrator="rk3", v_par=1.0)),
+    "cpaw_travelling_left": ("cpaw_mhd_hlld", "cpaw", True,
+                             lambda: refrun.cpaw_blocks(tlim=0.2, rst_dt=0.1, direction=2)),
+    "field_loop_x1x2": ("fieldloop_mhd_hlld", "field_loop", True,
+                        lambda: refrun.fieldloop_blocks(iprob=1, tlim=0.1, rst_dt=0.05)),
+    "field_loop_rotated": ("fieldloop_mhd_hlld", "field_loop", True,
+                           lambda: refrun.fieldloop_blocks(iprob=4, tlim=0.1, rst_dt=0.05, integrator="rk2")),
+    "field_loop_sphere_dense": ("fieldloop_mhd_hlld", "field_loop", True,
+                                lambda: refrun.fieldloop_blocks(iprob=5, tlim=0.1, rst_dt=0.05, drat=2.0)),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
@@ -120,6 +132,8 @@ def compare_with_reference(binary, case, host_time_params=None):
         scale = np.abs(h1).max(axis=0) + 1e-300
         assert np.all(np.abs(h1 - h2) <= 1e-10 * scale)
         np.testing.assert_array_equal(h1[:, :2], h2[:, :2])   # time and dt columns exactly
+        for f in glob.glob(wd_ref + "/*-errors.dat"):         # rows UserWorkAfterLoop appends
+            assert open(f).read() == open(os.path.join(wd, os.path.basename(f))).read()
     finally:
         shutil.rmtree(wd, ignore_errors=True)
         shutil.rmtree(wd_ref, ignore_errors=True)

@@ -25,7 +25,9 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          # reflecting / outflow physical boundaries
          "hydro_sod_vl2_plm_hllc_outflow_x1", "mhd_briowu_rk2_plm_hlld_outflow_x2",
          "hydro_blast_rk3_plm_hllc_mixed_bcs", "mhd_blast_vl2_plm_hlld_reflecting_box",
-         "mhd_linwave_vl2_plm_hlld_oddmesh", "hydro_linwave_rk3_ppm_hllc_oddmesh"]
+         "mhd_linwave_vl2_plm_hlld_oddmesh", "hydro_linwave_rk3_ppm_hllc_oddmesh",
+         # circularly polarised Alfven wave; field loop in a field-free box (HLLD / CT with B == 0)
+         "mhd_cpaw_rk3_plm_hlld", "mhd_fieldloop_vl2_plm_hlld"]
 
 
 @pytest.mark.parametrize("name", CASES)
