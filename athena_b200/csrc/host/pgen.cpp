@@ -304,6 +304,109 @@ static void ShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
   }
 }
 
+// Errors against the exact solutions the reference tabulates (shock_tube.cpp:46-270): Sod's tube
+// for hydro, the Ryu & Jones 2a tube for MHD, both at t = tlim with the discontinuity at 0.  As in
+// the reference only the first MeshBlock is summed and its extents are what the row reports.
+static void ShockTubeErrors(Mesh *pm, ParameterInput *pin) {
+  if (!pin->GetOrAddBoolean("problem", "compute_error", false)) return;
+  pm->DownloadAll();
+  MeshBlock *pmb = pm->my_blocks(0);
+  Coordinates *pc = pmb->pcoord;
+  const int shk_dir = pin->GetInteger("problem", "shock_dir");
+  // (normal, transverse, transverse) components for each tube direction
+  const int rot = (shk_dir == 1) ? 0 : (shk_dir == 2 ? 1 : 2);
+  const int im1 = IM1 + rot, im2 = IM1 + (rot + 1) % 3, im3 = IM1 + (rot + 2) % 3;
+  const int ib1 = IB1 + rot, ib2 = IB1 + (rot + 1) % 3, ib3 = IB1 + (rot + 2) % 3;
+  const Real tlim = pm->tlim;
+  const AthenaArray<Real> &u = pmb->phydro->u;
+  Real err[NHYDRO + 3] = {};
+  const int nvar = NHYDRO + (MAGNETIC_FIELDS_ENABLED ? 3 : 0);
+
+  // RJ2a: states between the seven waves, from the right; by, bz in units of 1/sqrt(4 pi)
+  struct RJState { Real xlo, d, vx, vy, vz, by, bz, p; };
+  const RJState rj2a[8] = {
+      {2.2638 * tlim, 1.0, 0.0, 0.0, 0.0, 4.0, 2.0, 1.0},
+      {(0.53432 + 1.0 / std::sqrt(PI * 1.309)) * tlim, 1.3090, 0.53432, -0.094572, -0.047286, 5.3452, 2.6726, 1.5844},
+      {(0.53432 + 0.48144 / 1.309) * tlim, 1.3090, 0.53432, -0.18411, 0.17554, 5.7083, 1.7689, 1.5844},
+      {0.57538 * tlim, 1.4735, 0.57538, 0.047601, 0.24734, 5.0074, 1.5517, 1.9317},
+      {(0.60588 - 0.51594 / 1.4903) * tlim, 1.6343, 0.57538, 0.047601, 0.24734, 5.0074, 1.5517, 1.9317},
+      {(0.60588 - 1.0 / std::sqrt(PI * 1.4903)) * tlim, 1.4903, 0.60588, 0.22157, 0.30125, 5.5713, 1.7264, 1.6558},
+      {(1.2 - 2.3305 / 1.08) * tlim, 1.4903, 0.60588, 0.11235, 0.55686, 5.0987, 2.8326, 1.6558},
+      {0.0 /* left state: everything else */, 1.08, 1.2, 0.01, 0.5, 3.6, 2.0, 0.95}};
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  // Sod: shock, contact, foot and head of the rarefaction
+  const Real xs = 1.7522 * tlim, xc = 0.92745 * tlim, xf = -0.07027 * tlim, xh = -1.1832 * tlim;
+
+  for (int k = pmb->ks; k <= pmb->ke; k++)
+    for (int j = pmb->js; j <= pmb->je; j++)
+      for (int i = pmb->is; i <= pmb->ie; i++) {
+        const Real r = (shk_dir == 1) ? pc->x1v(i) : (shk_dir == 2 ? pc->x2v(j) : pc->x3v(k));
+        Real d0, mx, my = 0.0, mz = 0.0, e0;
+        if (MAGNETIC_FIELDS_ENABLED) {
+          int n = 0;
+          while (n < 7 && !(r > rj2a[n].xlo)) ++n;
+          const RJState &q = rj2a[n];
+          const Real bx = 2.0 / std::sqrt(4.0 * PI);
+          const Real by = q.by / std::sqrt(4.0 * PI), bz = q.bz / std::sqrt(4.0 * PI);
+          d0 = q.d;
+          mx = q.vx * d0;
+          my = q.vy * d0;
+          mz = q.vz * d0;
+          e0 = q.p / gm1;
+          e0 += 0.5 * ((mx * mx + my * my + mz * mz) / d0 + (bx * bx + by * by + bz * bz));
+          const AthenaArray<Real> &bcc = pmb->pfield->bcc;
+          err[NHYDRO + ib1] += std::abs(bx - bcc(ib1, k, j, i));
+          err[NHYDRO + ib2] += std::abs(by - bcc(ib2, k, j, i));
+          err[NHYDRO + ib3] += std::abs(bz - bcc(ib3, k, j, i));
+        } else if (r > xs) {
+          d0 = 0.125, mx = 0.0, e0 = 0.25;
+        } else if (r > xc) {
+          d0 = 0.26557, mx = 0.92745 * d0, e0 = 0.87204;
+        } else if (r > xf) {
+          d0 = 0.42632, mx = 0.92745 * d0, e0 = 0.94118;
+        } else if (r > xh) {
+          const Real v0 = 0.92745 * (r - xh) / (xf - xh);
+          d0 = 0.42632 * std::pow((1.0 + 0.20046 * (0.92745 - v0)), 5);
+          mx = v0 * d0;
+          e0 = (0.30313 * std::pow((1.0 + 0.20046 * (0.92745 - v0)), 7)) / 0.4 + 0.5 * d0 * v0 * v0;
+        } else {
+          d0 = 1.0, mx = 0.0, e0 = 2.5;
+        }
+        err[IDN] += std::abs(d0 - u(IDN, k, j, i));
+        err[im1] += std::abs(mx - u(im1, k, j, i));
+        err[im2] += std::abs(my - u(im2, k, j, i));
+        err[im3] += std::abs(mz - u(im3, k, j, i));
+        err[IEN] += std::abs(e0 - u(IEN, k, j, i));
+      }
+  const Real ncells = static_cast<Real>(static_cast<std::int64_t>(pm->mesh_size.nx1) * pm->mesh_size.nx2 *
+                                        pm->mesh_size.nx3);
+  Real rms_err = 0.0;
+  for (int n = 0; n < nvar; ++n) err[n] = err[n] / ncells;
+  for (int n = 0; n < nvar; ++n) rms_err += SQR(err[n]);
+  rms_err = std::sqrt(rms_err);
+  const char *fname = "shock-errors.dat";
+  FILE *pfile = std::fopen(fname, "r");
+  const bool fresh = (pfile == nullptr);
+  if (pfile != nullptr) std::fclose(pfile);
+  pfile = std::fopen(fname, fresh ? "w" : "a");
+  if (pfile == nullptr) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in function [Mesh::UserWorkAfterLoop]" << std::endl
+        << "Error output file could not be opened" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  if (fresh) {
+    std::fprintf(pfile, "# Nx1  Nx2  Nx3  Ncycle  RMS-Error  d  M1  M2  M3  E");
+    if (MAGNETIC_FIELDS_ENABLED) std::fprintf(pfile, "  B1c  B2c  B3c");
+    std::fprintf(pfile, "\n");
+  }
+  std::fprintf(pfile, "%d  %d  %d  %d  %e", pmb->block_size.nx1, pmb->block_size.nx2, pmb->block_size.nx3,
+               pm->ncycle, rms_err);
+  for (int n = 0; n < nvar; ++n) std::fprintf(pfile, "  %e", err[n]);
+  std::fprintf(pfile, "\n");
+  std::fclose(pfile);
+}
+
 //========================================================================================
 // B = curl A on the faces of the active zone from edge-centred potentials (the construction
 // linear_wave.cpp:503-528, cpaw.cpp:290-315 and field_loop.cpp:226-250 share): div B = 0 to rounding
@@ -885,7 +988,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"blast", nullptr, BlastGenerator, nullptr},
     {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
     {"kh", KHInitUserMeshData, KHGenerator, nullptr},
-    {"shock_tube", nullptr, ShockTubeGenerator, nullptr},
+    {"shock_tube", nullptr, ShockTubeGenerator, ShockTubeErrors},
     {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
     {"field_loop", nullptr, FieldLoopGenerator, nullptr},
 };

@@ -38,6 +38,31 @@ def blast_blocks(n=32, blk=16, tlim=0.02):
     }
 
 
+def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
+    n = [8, 8, 8]
+    n[shock_dir - 1] = 64
+    blk = [8, 8, 8]
+    blk[shock_dir - 1] = 32
+    bcs = ["periodic"] * 6
+    bcs[2 * (shock_dir - 1)] = bcs[2 * (shock_dir - 1) + 1] = "outflow"
+    if mhd:    # Ryu & Jones 2a (inputs/mhd/athinput.rj2a)
+        left = (1.08, 1.2, 0.01, 0.5, 0.95, 1.0155412503859613, 0.5641895835477562)
+        right = (1.0, 0.0, 0.0, 0.0, 1.0, 1.1283791670955125, 0.5641895835477562)
+        b = refrun.shocktube_blocks(True, left, right, shock_dir=shock_dir, bx=0.5641895835477562, xshock=0.0,
+                                    mesh=tuple(n), block=tuple(blk), tlim=0.2, rst_dt=0.1, integrator=integrator,
+                                    bcs=bcs)
+        b["hydro"]["gamma"] = 1.666666666667
+    else:      # Sod (inputs/hydro/athinput.sod)
+        b = refrun.shocktube_blocks(False, (1.0, 0.0, 0.0, 0.0, 1.0), (0.125, 0.0, 0.0, 0.0, 0.1),
+                                    shock_dir=shock_dir, xshock=0.0, mesh=tuple(n), block=tuple(blk), tlim=0.25,
+                                    rst_dt=0.125, integrator=integrator, bcs=bcs)
+        b["hydro"]["gamma"] = 1.4
+    for d in "123":
+        b["mesh"]["x%smin" % d], b["mesh"]["x%smax" % d] = -0.5, 0.5
+    b["problem"]["compute_error"] = "true"
+    return b
+
+
 CASES = {
     "mhd_linwave": ("linwave_mhd_hlld", "linear_wave", True,
                     lambda: dict(refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(16, 8, 8),
@@ -87,6 +112,12 @@ CASES = {
                            lambda: refrun.fieldloop_blocks(iprob=4, tlim=0.1, rst_dt=0.05, integrator="rk2")),
     "field_loop_sphere_dense": ("fieldloop_mhd_hlld", "field_loop", True,
                                 lambda: refrun.fieldloop_blocks(iprob=5, tlim=0.1, rst_dt=0.05, drat=2.0)),
+    # hydro/sod_shock.py and mhd/rj2a_shock.py: tubes on [-0.5, 0.5] with outflow ends, errors against
+    # the tabulated exact solutions appended to shock-errors.dat (shock_tube.cpp:46-270)
+    "sod_errors_x2": ("shocktube_hydro_hllc", "shock_tube", False, lambda: tube_error_blocks(False, 2)),
+    "rj2a_errors_x1": ("shocktube_mhd_hlld", "shock_tube", True, lambda: tube_error_blocks(True, 1)),
+    "rj2a_errors_x3_rk3": ("shocktube_mhd_hlld", "shock_tube", True,
+                           lambda: tube_error_blocks(True, 3, integrator="rk3")),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
