@@ -273,13 +273,23 @@ class Outputs {
   void MakeOutputs(Mesh *pm, ParameterInput *pin, bool wtflag = false);   // outputs.cpp:1490
  private:
   struct OutputParameters {
-    std::string block_name, file_type, file_basename, data_format;
+    std::string block_name, file_type, file_basename, data_format, file_id, variable;
     Real dt, next_time;
     int dcycle, file_number;
+    bool include_ghost_zones = false;
+  };
+  // one column group of a .tab / .vtk file: nvar components of a MeshBlock array from n0 on
+  struct OutputField {
+    std::string type, name;   // "SCALARS" | "VECTORS", dataset name
+    const AthenaArray<Real> *src;
+    int n0, nvar;
   };
   std::vector<OutputParameters> types_;
   void WriteHistory(OutputParameters &op, Mesh *pm, ParameterInput *pin);
   void WriteRestart(OutputParameters &op, Mesh *pm, ParameterInput *pin, bool force);
+  void WriteTable(OutputParameters &op, Mesh *pm, ParameterInput *pin);
+  void WriteVTK(OutputParameters &op, Mesh *pm, ParameterInput *pin);
+  static std::vector<OutputField> SelectFields(MeshBlock *pmb, const std::string &variable);
 };
 
 #endif  // ATHENA_B200_HOST_ATHENA_HPP_

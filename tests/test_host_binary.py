@@ -63,6 +63,16 @@ def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     return b
 
 
+def with_data_dumps(blocks, tab_vars, vtk_vars, ghost_vars):
+    dt = blocks["output2"]["dt"]
+    blocks["output3"] = {"file_type": "tab", "variable": tab_vars, "dt": dt, "data_format": "%24.16e"}
+    blocks["output4"] = {"file_type": "vtk", "variable": vtk_vars, "dt": dt}
+    blocks["output5"] = {"file_type": "tab", "variable": ghost_vars, "dt": 2 * dt, "ghost_zones": "true",
+                         "id": "withghosts"}
+    blocks["output6"] = {"file_type": "vtk", "variable": ghost_vars, "dcycle": 3, "ghost_zones": "true"}
+    return blocks
+
+
 CASES = {
     "mhd_linwave": ("linwave_mhd_hlld", "linear_wave", True,
                     lambda: dict(refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(16, 8, 8),
@@ -118,6 +128,12 @@ CASES = {
     "rj2a_errors_x1": ("shocktube_mhd_hlld", "shock_tube", True, lambda: tube_error_blocks(True, 1)),
     "rj2a_errors_x3_rk3": ("shocktube_mhd_hlld", "shock_tube", True,
                            lambda: tube_error_blocks(True, 3, integrator="rk3")),
+    # formatted-table and VTK dumps (outputs/formatted_table.cpp, vtk.cpp): byte-identical files
+    "mhd_linwave_tab_vtk": ("linwave_mhd_hlld", "linear_wave", True, lambda: with_data_dumps(
+        refrun.linwave_blocks(True, mesh=(16, 8, 8), block=(8, 4, 4), tlim=0.06, rst_dt=0.03), "prim", "cons", "b,d")),
+    "kh_scalars_tab_vtk": ("kh_hydro_hllc_s2", "kh", False, lambda: with_data_dumps(
+        refrun.kh_blocks(mesh=(16, 16, 8), block=(8, 8, 8), tlim=0.02, rst_dt=0.01, integrator="vl2", xorder=2),
+        "cons", "prim", "r1,m2,vx,E"), ["--nscalars=2"]),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
@@ -165,6 +181,10 @@ def compare_with_reference(binary, case, host_time_params=None):
         np.testing.assert_array_equal(h1[:, :2], h2[:, :2])   # time and dt columns exactly
         for f in glob.glob(wd_ref + "/*-errors.dat"):         # rows UserWorkAfterLoop appends
             assert open(f).read() == open(os.path.join(wd, os.path.basename(f))).read()
+        for f in glob.glob(wd_ref + "/*.tab") + glob.glob(wd_ref + "/*.vtk"):   # per-MeshBlock data dumps
+            ours = os.path.join(wd, os.path.basename(f))
+            assert os.path.exists(ours), os.path.basename(f)
+            assert open(f, "rb").read() == open(ours, "rb").read(), os.path.basename(f)
     finally:
         shutil.rmtree(wd, ignore_errors=True)
         shutil.rmtree(wd_ref, ignore_errors=True)
