@@ -130,6 +130,8 @@ class ParameterInput {
   Real SetReal(const std::string &block, const std::string &name, Real v);
   std::string SetString(const std::string &block, const std::string &name, const std::string &v);
   const std::vector<Block> &blocks() const { return blocks_; }
+  void RollbackNextTime();               // restart: parameter_input.cpp:754
+  void ForwardNextTime(Real mesh_time);  // restart: parameter_input.cpp:790
 
  private:
   const Block *Find(const std::string &b) const;
@@ -224,6 +226,10 @@ class Mesh {   // mesh/mesh.hpp:206-447
   Mesh(ParameterInput *pin);
   ~Mesh();
   void Initialize(ParameterInput *pin);   // mesh.cpp:1622
+  // restart (mesh.cpp:621-960 + MeshBlock restart constructor, meshblock.cpp:263-420): raw = the
+  // whole .rst file, offset = first byte after <par_end>
+  void LoadRestart(const std::string &raw, std::size_t offset);
+  bool res_flag = false;
   void NewTimeStep();                     // mesh.cpp:1236
   void UserWorkAfterLoop(ParameterInput *pin);
   void OutputCycleDiagnostics();          // mesh.cpp:2304

@@ -6,6 +6,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <iterator>
 
 #include "athena.hpp"
 
@@ -23,18 +25,20 @@ static void ParseConfigure(const std::string &s) {
 }
 
 int main(int argc, char *argv[]) {
-  std::string input_filename, run_dir;
+  std::string input_filename, restart_filename, run_dir;
   bool narg_flag = false, have_cfg = false;
   std::string cfg_cmdline;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "-i" && i + 1 < argc) input_filename = argv[++i];
+    else if (a == "-r" && i + 1 < argc) restart_filename = argv[++i];
     else if (a == "-d" && i + 1 < argc) run_dir = argv[++i];
     else if (a == "-n") narg_flag = true;
     else if (a == "-h") {
       std::cout << "Athena++ (B200 path)" << std::endl
                 << "Usage: " << argv[0] << " [options] [block/par=value ...]" << std::endl
                 << "  -i <file>   specify input file [athinput]" << std::endl
+                << "  -r <file>   restart with this file" << std::endl
                 << "  -d <dir>    specify run dir [current dir]" << std::endl
                 << "  -n          parse input file and quit" << std::endl
                 << "  --prob=<pgen> [-b] [--flux=..] [--nghost=n] [--nscalars=n]  configure-time choices "
@@ -45,13 +49,36 @@ int main(int argc, char *argv[]) {
       have_cfg = true;
     }
   }
-  if (input_filename.empty()) {
+  if (input_filename.empty() && restart_filename.empty()) {
     std::cout << "### FATAL ERROR in main" << std::endl << "No input file or restart file is specified." << std::endl;
     return 1;
   }
   try {
     ParameterInput *pinput = new ParameterInput;
-    pinput->LoadFromFile(input_filename);
+    std::string restart_raw;
+    std::size_t restart_data = 0;
+    if (!restart_filename.empty()) {   // main.cpp:231-239: parameters first from the restart file ...
+      std::ifstream rf(restart_filename.c_str(), std::ios::binary);
+      if (!rf.good()) {
+        std::stringstream msg;
+        msg << "### FATAL ERROR in function [IOWrapper:Open]" << std::endl
+            << "Input file '" << restart_filename << "' could not be opened" << std::endl;
+        ATHENA_ERROR(msg);
+      }
+      restart_raw.assign(std::istreambuf_iterator<char>(rf), std::istreambuf_iterator<char>());
+      const std::size_t end = restart_raw.find("<par_end>\n");
+      if (end == std::string::npos) {
+        std::stringstream msg;
+        msg << "### FATAL ERROR in function [ParameterInput::LoadFromFile]" << std::endl
+            << "<par_end> not found in restart file '" << restart_filename << "'" << std::endl;
+        ATHENA_ERROR(msg);
+      }
+      restart_data = end + 10;
+      std::istringstream par(restart_raw.substr(0, restart_data));
+      pinput->LoadFromStream(par);
+      pinput->RollbackNextTime();
+    }
+    if (!input_filename.empty()) pinput->LoadFromFile(input_filename);   // ... then -i overrides them
     pinput->ModifyFromCmdline(argc, argv);
     if (have_cfg) ParseConfigure(cfg_cmdline);
     else if (pinput->DoesParameterExist("comment", "configure")) ParseConfigure(pinput->GetString("comment", "configure"));
@@ -61,6 +88,11 @@ int main(int argc, char *argv[]) {
       ATHENA_ERROR(msg);
     }
     Mesh *pmesh = new Mesh(pinput);
+    if (!restart_filename.empty()) {
+      pmesh->LoadRestart(restart_raw, restart_data);
+      std::string().swap(restart_raw);
+      pinput->ForwardNextTime(pmesh->time);   // main.cpp:304-308
+    }
     TimeIntegratorTaskList *ptlist = new TimeIntegratorTaskList(pinput, pmesh);
     if (narg_flag) {
       pinput->ParameterDump(std::cout);

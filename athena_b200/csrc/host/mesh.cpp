@@ -306,7 +306,7 @@ Mesh::~Mesh() {
 void Mesh::Initialize(ParameterInput *pin) {
   for (int b = 0; b < nblocal; ++b) {
     MeshBlock *pmb = blocks_[b];
-    pmb->ProblemGenerator(pin);
+    if (!res_flag) pmb->ProblemGenerator(pin);   // restart: the arrays were filled by LoadRestart
     AthkCheck(athk_upload(athk, ATHK_U, b, pmb->phydro->u.data()), "Mesh::Initialize");
     if (MAGNETIC_FIELDS_ENABLED) {
       AthkCheck(athk_upload(athk, ATHK_B_X1F, b, pmb->pfield->b.x1f.data()), "Mesh::Initialize");
@@ -321,6 +321,74 @@ void Mesh::Initialize(ParameterInput *pin) {
   AthkCheck(athk_cons2prim(athk, 0), "Mesh::Initialize");
   AthkCheck(athk_apply_physical_boundaries(athk), "Mesh::Initialize");   // mesh.cpp:1886-1891
   NewTimeStep();
+}
+
+// Restart: the header after <par_end> (restart.cpp:94-117), the per-block id list and the raw
+// register dumps.  The Mesh has already been built from the parameters the file carries; the
+// file must describe the same block list.
+void Mesh::LoadRestart(const std::string &raw, std::size_t off) {
+  std::stringstream msg;
+  auto take = [&](void *dst, std::size_t n) {
+    if (off + n > raw.size()) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl << "The restart file is broken." << std::endl;
+      ATHENA_ERROR(msg);
+    }
+    std::memcpy(dst, raw.data() + off, n);
+    off += n;
+  };
+  int nb_file, root_file;
+  RegionSize ms_file;
+  std::uint64_t datasize;
+  take(&nb_file, sizeof(int));
+  take(&root_file, sizeof(int));
+  take(&ms_file, sizeof(RegionSize));
+  take(&time, sizeof(Real));
+  take(&dt, sizeof(Real));
+  take(&ncycle, sizeof(int));
+  take(&datasize, sizeof(std::uint64_t));
+  if (nb_file != nbtotal || root_file != root_level || ms_file.nx1 != mesh_size.nx1 || ms_file.nx2 != mesh_size.nx2 ||
+      ms_file.nx3 != mesh_size.nx3) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "The restart file holds " << nb_file << " MeshBlocks of a " << ms_file.nx1 << "x" << ms_file.nx2 << "x"
+        << ms_file.nx3 << " mesh; the parameters describe " << nbtotal << " blocks of a " << mesh_size.nx1 << "x"
+        << mesh_size.nx2 << "x" << mesh_size.nx3 << " mesh" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  mesh_size = ms_file;
+  for (int n = 0; n < nbtotal; ++n) {
+    LogicalLocation l;
+    double cost;
+    take(&l, sizeof(LogicalLocation));
+    take(&cost, sizeof(double));
+    if (l.lx1 != loclist[n].lx1 || l.lx2 != loclist[n].lx2 || l.lx3 != loclist[n].lx3 || l.level != loclist[n].level) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "MeshBlock " << n << " of the restart file is not at the location the block list gives it" << std::endl;
+      ATHENA_ERROR(msg);
+    }
+  }
+  MeshBlock *p0 = blocks_[0];
+  std::uint64_t expect = p0->phydro->u.GetSizeInBytes();
+  if (MAGNETIC_FIELDS_ENABLED)
+    expect += p0->pfield->b.x1f.GetSizeInBytes() + p0->pfield->b.x2f.GetSizeInBytes() +
+              p0->pfield->b.x3f.GetSizeInBytes();
+  if (NSCALARS > 0) expect += p0->pscalars->s.GetSizeInBytes();
+  if (datasize != expect) {   // meshblock.cpp:411-417
+    msg << "### FATAL ERROR in MeshBlock constructor" << std::endl
+        << "The restart file is broken or input parameters are inconsistent (data size per MeshBlock "
+        << datasize << " != " << expect << ": check -b, --nghost, --nscalars)." << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  for (int n = 0; n < nbtotal; ++n) {
+    MeshBlock *pmb = blocks_[n];
+    take(pmb->phydro->u.data(), pmb->phydro->u.GetSizeInBytes());
+    if (MAGNETIC_FIELDS_ENABLED) {
+      take(pmb->pfield->b.x1f.data(), pmb->pfield->b.x1f.GetSizeInBytes());
+      take(pmb->pfield->b.x2f.data(), pmb->pfield->b.x2f.GetSizeInBytes());
+      take(pmb->pfield->b.x3f.data(), pmb->pfield->b.x3f.GetSizeInBytes());
+    }
+    if (NSCALARS > 0) take(pmb->pscalars->s.data(), pmb->pscalars->s.GetSizeInBytes());
+  }
+  res_flag = true;
 }
 
 void Mesh::NewTimeStep() {   // mesh.cpp:1236-1282

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <fstream>
 
+#include <cmath>
+
 #include "athena.hpp"
 
 static std::string trim(const std::string &s) {
@@ -208,4 +210,40 @@ void ParameterInput::ParameterDump(std::ostream &os) const {
   }
   os << "#------------------------- PAR_DUMP -------------------------" << std::endl;
   os << "<par_end>" << std::endl;
+}
+
+// Restart files carry every <outputN>'s next_time / file_number as of the dump.  The dump itself
+// had already advanced its own block, and an -i file or the command line may change dt: step back
+// by one dt here, then ForwardNextTime() moves each block to the first output time that is still
+// ahead of (mesh_time - dt) once the final parameters and the mesh time are known.
+void ParameterInput::RollbackNextTime() {
+  for (Block &b : blocks_) {
+    if (b.name.compare(0, 6, "output") != 0) continue;
+    Real next_time = static_cast<Real>(std::atof(FindLine(b.name, "next_time", "RollbackNextTime")->value.c_str()));
+    next_time -= static_cast<Real>(std::atof(FindLine(b.name, "dt", "RollbackNextTime")->value.c_str()));
+    SetReal(b.name, "next_time", next_time);
+  }
+}
+
+void ParameterInput::ForwardNextTime(Real mesh_time) {
+  bool fresh = false;   // (sticky once a block without next_time has been seen, as in the reference)
+  for (Block &b : blocks_) {
+    if (b.name.compare(0, 6, "output") != 0) continue;
+    Real next_time = mesh_time;
+    if (DoesParameterExist(b.name, "next_time")) {
+      next_time = static_cast<Real>(std::atof(FindLine(b.name, "next_time", "ForwardNextTime")->value.c_str()));
+    } else {
+      fresh = true;   // an output block added for the restarted run
+    }
+    const Real dt0 = static_cast<Real>(std::atof(FindLine(b.name, "dt", "ForwardNextTime")->value.c_str()));
+    if (!(dt0 > 0.0)) continue;   // dcycle-driven block: nothing to move
+    const Real dt = dt0 * static_cast<int>((mesh_time - next_time) / dt0) + dt0;
+    if (dt > 0) {
+      next_time += dt;
+      if (fresh) next_time -= std::fmod(next_time, dt0) + dt0;   // write it immediately
+    }
+    std::stringstream ss;
+    ss << next_time;
+    Add(&b, "next_time", ss.str(), "# Updated during run time");
+  }
 }

@@ -384,6 +384,78 @@ def test_survey_known_answers_on_gpu(cuda_lib, case):
     check_known_answer(CUDA_BIN, case)
 
 
+# Checkpoint / resume (main.cpp -r, Mesh restart constructor, tst/regression/scripts/tests/outputs/
+# restart tests): a run resumed from an intermediate .rst must end exactly where the uninterrupted
+# run ends, and the two codes must be able to resume from each other's files.
+def rst_equal(a, c):
+    assert (a["ncycle"], a["time"], a["dt"], a["loc"]) == (c["ncycle"], c["time"], c["dt"], c["loc"])
+    for k in ("u", "b1", "b2", "b3", "s"):
+        assert len(a[k]) == len(c[k])
+        for x, y in zip(a[k], c[k]):
+            np.testing.assert_array_equal(x, y, err_msg=k)
+
+
+def check_restart(binary, case):
+    cfg, prob, mhd, mk = CASES[case][:4]
+    extra = CASES[case][4] if len(CASES[case]) > 4 else []
+    if not refrun.have_ref(cfg):
+        pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
+    blocks = mk()
+    dirs = []
+    try:
+        wd_ref, _ = refrun.run_reference(cfg, blocks)
+        wd, r = run_host(binary, blocks, prob, mhd, extra=extra)
+        dirs += [wd_ref, wd]
+        assert r.returncode == 0, r.stdout[-2000:]
+        final_ref = refrun.read_rst(glob.glob(wd_ref + "/*.final.rst")[0])
+        rst_equal(final_ref, refrun.read_rst(glob.glob(wd + "/*.final.rst")[0]))
+        names, hst_full = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
+        flags = ["--prob=" + prob] + (["-b"] if mhd else []) + list(extra)
+        # host resumes from its own checkpoint, and from the reference's
+        for src in (wd, wd_ref):
+            mid = sorted(glob.glob(src + "/*.00001.rst"))[0]
+            wd2 = tempfile.mkdtemp(prefix="athhost_")
+            dirs.append(wd2)
+            r = subprocess.run([binary, "-r", mid, "-d", wd2] + flags, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            rst_equal(final_ref, refrun.read_rst(glob.glob(wd2 + "/*.final.rst")[0]))
+            assert not glob.glob(wd2 + "/*.00000.rst") and not glob.glob(wd2 + "/*.00001.rst")   # numbering goes on
+            _, hst_tail = refrun.read_hst(glob.glob(wd2 + "/*.hst")[0])
+            np.testing.assert_array_equal(hst_tail, hst_full[-hst_tail.shape[0]:])
+        # the reference resumes from the host's checkpoint
+        mid = sorted(glob.glob(wd + "/*.00001.rst"))[0]
+        wd3 = tempfile.mkdtemp(prefix="athref_")
+        dirs.append(wd3)
+        r = subprocess.run([refrun.ref_binary(cfg), "-r", mid, "-d", wd3], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rst_equal(final_ref, refrun.read_rst(glob.glob(wd3 + "/*.final.rst")[0]))
+        # -i next to -r overrides parameters of the checkpoint (main.cpp:240-245)
+        wd4 = tempfile.mkdtemp(prefix="athhost_")
+        dirs.append(wd4)
+        r = subprocess.run([binary, "-r", mid, "-d", wd4, "time/nlim=%d" % (final_ref["ncycle"] - 1)] + flags,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "Terminating on cycle limit" in r.stdout
+    finally:
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+
+
+RESTART_CASES = ["mhd_blast", "kh_rk3_ppm_scalar", "briowu_x3_reflect_outflow"]
+
+
+@pytest.mark.parametrize("case", RESTART_CASES)
+def test_restart_resumes_bitwise(emul_binary, case):
+    check_restart(emul_binary, case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", RESTART_CASES)
+def test_restart_resumes_bitwise_on_gpu(cuda_lib, case):
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    check_restart(CUDA_BIN, case)
+
+
 def test_parameter_input_error_behaviour(emul_binary):
     """Missing parameter / unknown cmdline override / unpaired periodic BC: message + exit status as
     ATHENA_ERROR does (src/defs.hpp.in:155-159, parameter_input.cpp:352-395)."""
