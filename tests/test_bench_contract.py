@@ -1,6 +1,6 @@
-"""bench.py contract checks that do not need a GPU: the reference arm (`--impl reference`) runs the
+"""bench.py contract checks.  Without a GPU: the reference arm (`--impl reference`) runs the
 unmodified reference binary on the host cores and prints ONE JSON line with the keys the driver
-reads; under torchrun only rank 0 works.  The GPU arm's line is checked in test_gpu_parity.py."""
+reads; under torchrun only rank 0 works.  With a GPU: the product arm's line at a reduced size."""
 import json
 import os
 import subprocess
@@ -43,3 +43,24 @@ def test_reference_arm_other_ranks_exit_quietly():
     lines = run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"] + TINY,
                       env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert lines == []
+
+
+@pytest.mark.gpu
+def test_product_arm_line_has_every_contract_key(cuda_lib):
+    lines = run_bench(["--gpus", "1", "--steps", "3", "--warmup", "3", "--per-gpu", "128", "--block", "64",
+                       "--no-cpu-baseline"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "zone-cycles/s" and d["dtype"] == "f64" and d["scaling"] == "weak" and d["steps"] == 3
+    assert d["value"] > 1e8 and d["gpu_launches"] > 0      # a CPU fallback could not reach this
+    assert abs(d["value"] - 128 ** 3 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert "workload" in d["config"] and "sm_mhz" in d["clocks"]
