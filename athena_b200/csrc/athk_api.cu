@@ -920,6 +920,22 @@ extern "C" int athk_apply_physical_boundaries(athk_ctx *c) {
   return rc;
 }
 
+extern "C" int athk_set_constant_acceleration(athk_ctx *c, double g1, double g2, double g3) {
+  if (!c) return fail(ATHK_ERR_ARG, "set_constant_acceleration: null context");
+  c->gacc[0] = g1; c->gacc[1] = g2; c->gacc[2] = g3;
+  return ATHK_OK;
+}
+
+extern "C" int athk_add_source_terms(athk_ctx *c, double beta_dt) {
+  NEED_READY(c);
+  if (c->gacc[0] == 0.0 && c->gacc[1] == 0.0 && c->gacc[2] == 0.0) return ATHK_OK;
+  const Grid &g = c->g;
+  Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
+  ConstAccPoint f = {g, c->w, c->u[0], beta_dt, c->gacc[0], c->gacc[1], c->gacc[2]};
+  LAUNCH_NAMED(c, "athk_add_source_terms", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+  return ATHK_OK;
+}
+
 // History sums (outputs/history.cpp:196-248).  The reference adds cells serially; here every
 // MeshBlock is reduced by one CTA in a fixed order (deterministic, not the serial order: the sums
 // agree with the reference to rounding, ~1e-15 relative; the north-star bar is 1e-10), and the
@@ -1067,6 +1083,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
     }
     if (rc) return rc;
     if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }
+    if ((rc = athk_add_source_terms(c, sw->beta * dt_mesh))) return rc;   // SRC_TERM follows INT_HYD
     if (ns) {   // IntegrateScalars with the same weights (time_integrator.cpp:2376-2403)
       HydroIntegrate hs = h;
       hs.u = c->s[0]; hs.u1 = c->s[1];

@@ -41,6 +41,41 @@ struct Geom {
 ATHK_HD int nbr_slot(int ox1, int ox2, int ox3) { return (ox3 + 1) * 9 + (ox2 + 1) * 3 + (ox1 + 1); }
 
 //========================================================================================
+// HydroSourceTerms::ConstantAcceleration (hydro/srcterms/constant_acc.cpp:25-76) for one cell:
+// momentum and energy sources from the stage-input primitives, direction after direction as the
+// reference's three loops add them
+struct ConstAccPoint {
+  Grid g;
+  const Real *w;   // [nb][5][sn] primitives at the beginning of the stage
+  Real *u;         // [nb][5][sn] conserved register the stage has just written
+  Real dt;         // beta * dt_mesh
+  Real g1, g2, g3;
+  ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const idx_t c = gidx(g, k, j, i);
+    const Real *wb = w + (idx_t)blk * 5 * g.sn + c;
+    Real *ub = u + (idx_t)blk * 5 * g.sn + c;
+    const Real rho = wb[0];
+    Real e = ub[(idx_t)IEN * g.sn];
+    if (g1 != 0.0) {
+      const Real src = dt * rho * g1;
+      ub[(idx_t)IM1 * g.sn] += src;
+      e += src * wb[(idx_t)IVX * g.sn];
+    }
+    if (g2 != 0.0) {
+      const Real src = dt * rho * g2;
+      ub[(idx_t)IM2 * g.sn] += src;
+      e += src * wb[(idx_t)IVY * g.sn];
+    }
+    if (g3 != 0.0) {
+      const Real src = dt * rho * g3;
+      ub[(idx_t)IM3 * g.sn] += src;
+      e += src * wb[(idx_t)IVZ * g.sn];
+    }
+    ub[(idx_t)IEN * g.sn] = e;
+  }
+};
+
+//========================================================================================
 // EquationOfState::ConservedToPrimitive for one cell (+ CalculateCellCenteredField for MHD)
 template <bool MHD>
 struct Cons2PrimPoint {

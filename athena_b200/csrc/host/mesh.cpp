@@ -249,6 +249,13 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   cfg.dfloor = blocks_[0]->peos->GetDensityFloor();
   cfg.pfloor = blocks_[0]->peos->GetPressureFloor();
   AthkCheck(athk_create(&cfg, &athk), "Mesh constructor (athk_create)");
+  {   // HydroSourceTerms constructor (hydro/srcterms/hydro_srcterms.cpp:42-46)
+    const Real g1 = pin->GetOrAddReal("hydro", "grav_acc1", 0.0);
+    const Real g2 = pin->GetOrAddReal("hydro", "grav_acc2", 0.0);
+    const Real g3 = pin->GetOrAddReal("hydro", "grav_acc3", 0.0);
+    if (g1 != 0.0 || g2 != 0.0 || g3 != 0.0)
+      AthkCheck(athk_set_constant_acceleration(athk, g1, g2, g3), "Mesh constructor (athk_set_constant_acceleration)");
+  }
   for (int n = 0; n < nblocal; ++n) {
     Coordinates *pc = blocks_[n]->pcoord;
     AthkCheck(athk_set_block_coords(athk, n, pc->x1f.data(), pc->x1v.data(), pc->dx1f.data(),

@@ -99,6 +99,7 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   if (swap) AthkCheck(athk_swap_registers(a, 0, 0, 1), who);
   else AthkCheck(athk_weighted_ave_cc(a, 0, 0, 1, 2, w2), who);
   AthkCheck(athk_add_flux_divergence(a, sw.beta * dt, 0), who);
+  AthkCheck(athk_add_source_terms(a, sw.beta * dt), who);               // SRC_TERM :1890-1913
   if (NSCALARS > 0) {                                                   // INT_SCLR :2376-2403
     AthkCheck(athk_weighted_ave_cc(a, 1, 1, 0, 2, w1), who);
     if (swap) AthkCheck(athk_swap_registers(a, 2, 0, 1), who);

@@ -168,7 +168,7 @@ class Context:
     """One GPU context = the MeshBlocks of one rank."""
 
     def __init__(self, mesh, mhd, gamma, rsolver=None, nscalars=0, device=0, gids=None,
-                 rank_of=None, my_rank=0, lib=None):
+                 rank_of=None, my_rank=0, lib=None, grav_acc=None):
         self.lib = lib if lib is not None else capi.load()
         self.mesh = mesh
         self.mhd = bool(mhd)
@@ -188,6 +188,8 @@ class Context:
         h = C.c_void_p()
         capi.check(self.lib, self.lib.athk_create(C.byref(cfg), C.byref(h)))
         self.h = h
+        if grav_acc is not None and any(float(x) != 0.0 for x in grav_acc):   # <hydro> grav_acc1/2/3
+            capi.check(self.lib, self.lib.athk_set_constant_acceleration(h, *[float(x) for x in grav_acc]))
         self.nc = tuple(n + 2 * mesh.ng for n in mesh.block_nx)
         for lb, g in enumerate(self.gids):
             cs = []
@@ -352,6 +354,7 @@ class TimeIntegrator:
         else:
             c.call("athk_weighted_ave_cc", 0, 0, 1, 2, w2)
         c.call("athk_add_flux_divergence", beta * dt, 0)
+        c.call("athk_add_source_terms", beta * dt)   # SRC_TERM (time_integrator.cpp:1890-1913)
         if c.nscalars:   # INT_SCLR (time_integrator.cpp:2376-2403)
             c.call("athk_weighted_ave_cc", 1, 1, 0, 2, w1)
             if swap:

@@ -164,6 +164,15 @@ int athk_set_boundary_flags(athk_ctx *ctx, int lb, const int flags[6]);
  * athk_cons2prim (task PHY_BVAL, time_integrator.cpp:2276); athk_stage does it itself.
  * No-op when no local block has a physical boundary. */
 int athk_apply_physical_boundaries(athk_ctx *ctx);
+/* HydroSourceTerms (hydro/srcterms/hydro_srcterms.cpp:42-46): the constant accelerations
+ * <hydro> grav_acc1 / grav_acc2 / grav_acc3.  All zero (the default) = no source terms. */
+int athk_set_constant_acceleration(athk_ctx *ctx, double g1, double g2, double g3);
+/* Task SRC_TERM, TimeIntegratorTaskList::AddSourceTerms (task_list/time_integrator.cpp:1890) ->
+ * HydroSourceTerms::ConstantAcceleration (hydro/srcterms/constant_acc.cpp:25): u(IM*) += dt*rho*g,
+ * u(IEN) += dt*rho*g*v on the active zone, rho and v from the stage-input primitives w; beta_dt =
+ * stage_wghts.beta * dt.  Call after athk_integrate_hydro; athk_stage does it itself.  No-op
+ * without accelerations. */
+int athk_add_source_terms(athk_ctx *ctx, double beta_dt);
 /* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:45): per-block min dt * cfl, blocks 0..nblocks-1
  * into dt_blocks (may be NULL), returns the min over local blocks in *dt_min. Synchronises. */
 int athk_new_block_dt(athk_ctx *ctx, double cfl_number, double *dt_blocks, double *dt_min);

@@ -1074,8 +1074,9 @@ def block_dt(st, cfl):   # new_blockdt.cpp:72-191
 
 
 class Integrator:
-    def __init__(self, st, integrator="vl2", xorder=2, cfl=0.3, block_nx=None):
+    def __init__(self, st, integrator="vl2", xorder=2, cfl=0.3, block_nx=None, grav_acc=None):
         self.st, self.name, self.xorder = st, integrator, xorder
+        self.grav_acc = tuple(float(x) for x in (grav_acc or (0.0, 0.0, 0.0)))   # <hydro> grav_acc1/2/3
         self.stages = INTEGRATORS[integrator]
         self.cfl = min(cfl, CFL_LIMIT[integrator])
         self.block_nx = block_nx or st.mesh.nx
@@ -1122,6 +1123,13 @@ class Integrator:
                     dflx = dflx + (a3 * sh(fx[2][0][n], 2, 1) - a3 * fx[2][0][n])
                     unew[n] = np.where(cells, st.u[n] - wght * dflx / vol, st.u[n])
                 st.u = unew
+                # AddSourceTerms -> ConstantAcceleration (hydro/srcterms/constant_acc.cpp:25-76): one
+                # direction after the other, rho and v from the stage-input primitives
+                for d, gd in enumerate(self.grav_acc):
+                    if gd != 0.0:
+                        src = wght * st.w[0] * gd
+                        st.u[1 + d] = np.where(cells, st.u[1 + d] + src, st.u[1 + d])
+                        st.u[4] = np.where(cells, st.u[4] + src * st.w[1 + d], st.u[4])
                 if st.s is not None:   # IntegrateScalars (time_integrator.cpp:2376-2403)
                     sfx = scalar_fluxes(st, fx, order)
                     s1 = np.where(cells, weighted_ave(s1, st.s, None, 1.0, delta, 0.0), s1)

@@ -124,6 +124,12 @@ CASES = {
                                   tlim=0.1, integrator="rk3", xorder=2, cpaw=dict(v_par=1.0, direction=2)),
     "mhd_fieldloop_vl2_plm_hlld": dict(cfg="fieldloop_mhd_hlld", mhd=True, mesh=(32, 16, 16), block=(16, 8, 8),
                                        tlim=0.1, integrator="vl2", xorder=2, fieldloop=dict(iprob=5, drat=2.0)),
+    # SRC_TERM: constant accelerations along all three axes (hydro/srcterms/constant_acc.cpp)
+    "mhd_blast_rk2_plm_hlld_gravity": dict(cfg="blast_mhd_hlld", mhd=True, mesh=(32, 32, 32), block=(16, 16, 16),
+                                           tlim=0.05, integrator="rk2", xorder=2,
+                                           bcs=["periodic"] * 4 + ["reflecting"] * 2,
+                                           blast=dict(center=(0.1, 0.0, -0.2), radius=0.3),
+                                           grav_acc=(0.3, -0.2, -0.7)),
     "mhd_linwave_alfven_vl2": dict(cfg="linwave_mhd_hlld", mhd=True, mesh=(32, 16, 16),
                                    block=(8, 8, 8), tlim=0.05, integrator="vl2", xorder=2,
                                    wave_flag=1, amp=1.0e-2),
@@ -164,6 +170,8 @@ def make(name):
                                        integrator=c["integrator"], xorder=c["xorder"],
                                        wave_flag=c.get("wave_flag", 0), amp=c.get("amp", 1.0e-6),
                                        vflow=c.get("vflow", 0.0))
+    for d, gd in enumerate(c.get("grav_acc", ())):
+        blocks["hydro"]["grav_acc%d" % (d + 1)] = gd
     wd, out = refrun.run_reference(c["cfg"], blocks)
     r0 = refrun.read_rst(glob.glob(wd + "/*.00000.rst")[0])
     rf = refrun.read_rst(glob.glob(wd + "/*.final.rst")[0])

@@ -22,7 +22,9 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          # odd extents (11x9x13, 12x10x14 blocks): row padding, tiles / warps straddling rows
          "mhd_linwave_vl2_plm_hlld_oddmesh", "hydro_linwave_rk3_ppm_hllc_oddmesh",
          # circularly polarised Alfven wave; field loop in a field-free box (HLLD / CT with B == 0)
-         "mhd_cpaw_rk3_plm_hlld", "mhd_fieldloop_vl2_plm_hlld"]
+         "mhd_cpaw_rk3_plm_hlld", "mhd_fieldloop_vl2_plm_hlld",
+         # task SRC_TERM: constant accelerations
+         "mhd_blast_rk2_plm_hlld_gravity"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -63,6 +63,11 @@ def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     return b
 
 
+def with_gravity(blocks, **acc):
+    blocks["hydro"].update(acc)
+    return blocks
+
+
 def with_data_dumps(blocks, tab_vars, vtk_vars, ghost_vars):
     dt = blocks["output2"]["dt"]
     blocks["output3"] = {"file_type": "tab", "variable": tab_vars, "dt": dt, "data_format": "%24.16e"}
@@ -134,6 +139,14 @@ CASES = {
     "kh_scalars_tab_vtk": ("kh_hydro_hllc_s2", "kh", False, lambda: with_data_dumps(
         refrun.kh_blocks(mesh=(16, 16, 8), block=(8, 8, 8), tlim=0.02, rst_dt=0.01, integrator="vl2", xorder=2),
         "cons", "prim", "r1,m2,vx,E"), ["--nscalars=2"]),
+    # constant accelerations <hydro> grav_acc1/2/3 (task SRC_TERM, hydro/srcterms/constant_acc.cpp)
+    "blast_hydro_gravity_x3_reflect": ("blast_hydro_hllc", "blast", False, lambda: with_gravity(
+        refrun.blast_blocks(tlim=0.06, rst_dt=0.03, integrator="rk3",
+                            bcs=["periodic"] * 4 + ["reflecting"] * 2, center=(0.1, 0.0, -0.2), radius=0.3),
+        grav_acc3=-0.7)),
+    "kh_mhd_gravity_all_axes": ("kh_mhd_hlld_s1", "kh", True, lambda: with_gravity(
+        refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03, rst_dt=0.015, integrator="vl2", xorder=2,
+                         b0=0.5), grav_acc1=0.3, grav_acc2=-0.5, grav_acc3=0.2), ["--nscalars=1"]),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
@@ -202,7 +215,8 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
     compare_with_reference(emul_binary, case)
 
 
-@pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe"])
+@pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe",
+                                  "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes"])
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})

@@ -44,7 +44,8 @@ def _worker(rank, world, port, name, fused, q, overlap=False):
         rank_of = {g: r for r, gl in enumerate(parts) for g in gl}
         mhd = meta["mhd"]
         ctx = pyhost.Context(mesh, mhd, meta["gamma"], gids=parts[rank], rank_of=rank_of, my_rank=rank, lib=lib,
-                             nscalars=ns, rsolver=util.RSOLVERS[meta["flux"]] if meta.get("flux") else None)
+                             nscalars=ns, rsolver=util.RSOLVERS[meta["flux"]] if meta.get("flux") else None,
+                     grav_acc=meta.get("grav_acc"))
         assert len(ctx.remote) > 0
         multigpu.attach(ctx, rank, world, device="cpu")
         B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
@@ -98,7 +99,8 @@ def _worker(rank, world, port, name, fused, q, overlap=False):
     ("mhd_kh_rk2_plm_hlld_scalar", True, True),              # passive scalars in the ghost messages
     ("mhd_shocktube_vl2_plm_roe_llf", True, False),          # solver choice
     ("mhd_blast_vl2_plm_hlld_reflecting_box", True, False),  # physical boundaries + remote links
-    ("hydro_blast_rk3_plm_hllc_mixed_bcs", False, False)])
+    ("hydro_blast_rk3_plm_hllc_mixed_bcs", False, False),
+    ("mhd_blast_rk2_plm_hlld_gravity", True, True)])         # source terms in the overlap-window phases
 def test_two_ranks_match_reference_bitwise(emul_lib, name, fused, overlap):
     world = 2
     port = _free_port()

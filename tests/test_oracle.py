@@ -27,7 +27,9 @@ CASES = ["mhd_linwave_vl2_plm_hlld", "hydro_linwave_vl2_plm_hllc", "mhd_linwave_
          "hydro_blast_rk3_plm_hllc_mixed_bcs", "mhd_blast_vl2_plm_hlld_reflecting_box",
          "mhd_linwave_vl2_plm_hlld_oddmesh", "hydro_linwave_rk3_ppm_hllc_oddmesh",
          # circularly polarised Alfven wave; field loop in a field-free box (HLLD / CT with B == 0)
-         "mhd_cpaw_rk3_plm_hlld", "mhd_fieldloop_vl2_plm_hlld"]
+         "mhd_cpaw_rk3_plm_hlld", "mhd_fieldloop_vl2_plm_hlld",
+         # task SRC_TERM: constant accelerations
+         "mhd_blast_rk2_plm_hlld_gravity"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -37,7 +39,8 @@ def test_numpy_oracle_matches_reference_bitwise(name):
     b = [z["b1_0"], z["b2_0"], z["b3_0"]] if meta["mhd"] else None
     st = A.State(mesh, meta["gamma"], z["u0"], b, s=z["s0"] if meta.get("nscalars") else None,
                  flux=meta.get("flux"))
-    it = A.Integrator(st, meta["integrator"], meta["xorder"], meta["cfl"], block_nx=meta["block"])
+    it = A.Integrator(st, meta["integrator"], meta["xorder"], meta["cfl"], block_nx=meta["block"],
+                      grav_acc=meta.get("grav_acc"))
     it.run(meta["tlim"])
     assert it.ncycle == meta["ncycle"]
     np.testing.assert_array_equal(np.array(it.dt_history), z["hst"][:-1, 1])

@@ -67,10 +67,10 @@ RSOLVERS = {"hllc": 0, "hlld": 1, "roe": 2, "hlle": 3, "llf": 4}   # enum athk_r
 
 
 def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, B=(None, None, None),
-                         flux=None, S=None, bcs=None):
+                         flux=None, S=None, bcs=None, grav_acc=None):
     mesh = pyhost.UniformMesh(mesh_nx, block_nx, xmin, xmax, ng=ng, bcs=bcs)
     ctx = pyhost.Context(mesh, mhd, gamma, rsolver=RSOLVERS[flux] if flux else None, lib=lib,
-                         nscalars=0 if S is None else S.shape[0])
+                         nscalars=0 if S is None else S.shape[0], grav_acc=grav_acc)
     if S is not None:
         for lb, blk in enumerate(split_to_blocks(mesh, S)):
             ctx.upload("S", lb, blk["u"])
@@ -92,7 +92,8 @@ def run_golden_case(lib, name, block=None, fused=False):
     B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
     ctx = make_ctx_from_global(lib, meta["mesh"], block or meta["block"], meta["xmin"], meta["xmax"],
                                meta["ng"], mhd, meta["gamma"], z["u0"], B, flux=meta.get("flux"),
-                               S=z["s0"] if meta.get("nscalars") else None, bcs=meta.get("bcs"))
+                               S=z["s0"] if meta.get("nscalars") else None, bcs=meta.get("bcs"),
+                               grav_acc=meta.get("grav_acc"))
     ti = pyhost.TimeIntegrator(ctx, meta["integrator"], meta["xorder"], meta["cfl"], fused=fused)
     ti.initialize(tlim=meta["tlim"])
     ti.run(meta["tlim"])

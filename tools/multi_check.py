@@ -28,7 +28,8 @@ rank_of = {g: r for r, gl in enumerate(parts) for g in gl}
 mhd = meta["mhd"]
 ns = meta.get("nscalars") or 0
 ctx = pyhost.Context(mesh, mhd, meta["gamma"], device=lr, gids=parts[rank], rank_of=rank_of, my_rank=rank, lib=lib,
-                     nscalars=ns, rsolver=util.RSOLVERS[meta["flux"]] if meta.get("flux") else None)
+                     nscalars=ns, rsolver=util.RSOLVERS[meta["flux"]] if meta.get("flux") else None,
+                     grav_acc=meta.get("grav_acc"))
 stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
 multigpu.attach(ctx, rank, world, device="cuda", stream=stream)
 B = (z["b1_0"], z["b2_0"], z["b3_0"]) if mhd else (None, None, None)
