@@ -493,4 +493,14 @@ def test_parameter_input_error_behaviour(emul_binary):
     shutil.rmtree(wd, ignore_errors=True)
     wd, r = run_host(emul_binary, blocks, "blast", True, extra=["time/tlim=0.004"])
     assert r.returncode == 0 and "Terminating on time limit" in r.stdout
+    # restart files that do not fit the configuration are refused with the reference's diagnosis
+    # (meshblock.cpp:411-417), never read into arrays of another shape
+    rst = glob.glob(wd + "/*.final.rst")[0]
+    for flags, text in ((["--prob=blast"], "input parameters are inconsistent"),
+                        (["--prob=blast", "-b", "--nghost=3"], "input parameters are inconsistent"),
+                        (["--prob=blast", "-b", "meshblock/nx1=8"], "The restart file holds 8 MeshBlocks")):
+        r = subprocess.run([emul_binary, "-r", rst, "-d", wd] + flags, capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and text in r.stdout, r.stdout[-500:]
+    r = subprocess.run([emul_binary, "-r", wd + "/missing.rst"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "could not be opened" in r.stdout
     shutil.rmtree(wd, ignore_errors=True)
