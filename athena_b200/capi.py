@@ -88,6 +88,7 @@ PROTOTYPES = {
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_set_boundary_flags": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "athk_apply_physical_boundaries": (C.c_int, [_P]),
+    "athk_set_block_floors": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),
     "athk_set_constant_acceleration": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "athk_add_source_terms": (C.c_int, [_P, C.c_double]),
     "athk_stage": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(StageWghts), C.c_double]),

@@ -161,6 +161,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
   cudaFree(c->bcflags);
+  cudaFree(c->d_floors);
   cudaFree(c->stage);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
@@ -811,17 +812,17 @@ static int launch_scalar_fluxes(athk_ctx *c) {
   const MassFlux mf = {{c->flux[0], c->flux[1], c->flux[2]}, (idx_t)5 * g.sn};   // Hydro::flux[d](IDN)
   {
     Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie + 1};
-    ScalarFacePoint<0, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[0]};
+    ScalarFacePoint<0, ORDER> f = {g, c->geo, c->eos, ns, c->r, mf, c->sflux[0]};
     LAUNCH_NAMED(c, "calculate_scalar_fluxes_x1", launch_points(c->stream, g.nb, r, f));
   }
   {
     Range3 r = {g.ks, g.ke, g.js, g.je + 1, g.is, g.ie};
-    ScalarFacePoint<1, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[1]};
+    ScalarFacePoint<1, ORDER> f = {g, c->geo, c->eos, ns, c->r, mf, c->sflux[1]};
     LAUNCH_NAMED(c, "calculate_scalar_fluxes_x2", launch_points(c->stream, g.nb, r, f));
   }
   {
     Range3 r = {g.ks, g.ke + 1, g.js, g.je, g.is, g.ie};
-    ScalarFacePoint<2, ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, c->sflux[2]};
+    ScalarFacePoint<2, ORDER> f = {g, c->geo, c->eos, ns, c->r, mf, c->sflux[2]};
     LAUNCH_NAMED(c, "calculate_scalar_fluxes_x3", launch_points(c->stream, g.nb, r, f));
   }
   return ATHK_OK;
@@ -854,7 +855,7 @@ static int launch_scalar_integrate(athk_ctx *c, const HydroIntegrate &hi) {
   const int ns = c->cfg.nscalars;
   const MassFlux mf = {{c->sflux[0], c->sflux[1], c->sflux[2]}, (idx_t)ns * g.sn};   // left by the sweeps
   Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
-  ScalarIntegratePoint<ORDER> f = {g, c->geo, c->eos.sfloor, ns, c->r, mf, hi};
+  ScalarIntegratePoint<ORDER> f = {g, c->geo, c->eos, ns, c->r, mf, hi};
   LAUNCH_NAMED(c, "scalar_fluxes_integrate", launch_points(c->stream, g.nb, r, f));
   return ATHK_OK;
 }
@@ -918,6 +919,32 @@ extern "C" int athk_apply_physical_boundaries(athk_ctx *c) {
   for (int side = 0; side < 2 && !rc; ++side) if (c->bc_any[2 + side]) rc = launch_bc_face<1>(c, side);
   for (int side = 0; side < 2 && !rc; ++side) if (c->bc_any[4 + side]) rc = launch_bc_face<2>(c, side);
   return rc;
+}
+
+extern "C" int athk_set_block_floors(athk_ctx *c, int lb, double dfloor, double pfloor, double sfloor) {
+  if (!c) return fail(ATHK_ERR_ARG, "set_block_floors: null context");
+  const int nb = c->g.nb;
+  if (lb < 0 || lb >= nb) return fail(ATHK_ERR_ARG, "set_block_floors: block %d out of range", lb);
+  if (!(dfloor > 0.0) || !(pfloor > 0.0) || !(sfloor >= 0.0))
+    return fail(ATHK_ERR_ARG, "set_block_floors: floors must be positive (got %g, %g, %g)", dfloor, pfloor, sfloor);
+  if (c->h_floors.empty()) {   // first call: every block starts from the context's floors
+    c->h_floors.resize((size_t)nb * 3);
+    for (int b = 0; b < nb; ++b) {
+      c->h_floors[3 * b] = c->eos.dfloor;
+      c->h_floors[3 * b + 1] = c->eos.pfloor;
+      c->h_floors[3 * b + 2] = c->eos.sfloor;
+    }
+    CU(cudaMalloc((void **)&c->d_floors, c->h_floors.size() * sizeof(Real)));
+  }
+  c->h_floors[3 * lb] = dfloor;
+  c->h_floors[3 * lb + 1] = pfloor;
+  c->h_floors[3 * lb + 2] = sfloor;
+  CU(cudaStreamSynchronize(c->stream));   // no kernel may be reading the table
+  CU(cudaMemcpyAsync(c->d_floors, c->h_floors.data(), c->h_floors.size() * sizeof(Real), cudaMemcpyHostToDevice,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->eos.blk_floors = c->d_floors;
+  return ATHK_OK;
 }
 
 extern "C" int athk_set_constant_acceleration(athk_ctx *c, double g1, double g2, double g3) {

@@ -83,6 +83,8 @@ struct athk_ctx {
   bool bc_dirty;
   int bc_any[6];                // does any local block have a physical boundary on face f
   double gacc[3] = {0.0, 0.0, 0.0};   // HydroSourceTerms: <hydro> grav_acc1/2/3 (0 = none)
+  std::vector<Real> h_floors;         // per-block (dfloor, pfloor, sfloor); empty = uniform
+  Real *d_floors = nullptr;
   std::vector<Real> h_geo;   // host mirror of geo_store
 };
 

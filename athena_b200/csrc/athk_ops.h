@@ -130,9 +130,9 @@ struct Cons2PrimPoint {
       bc[0] = bc1;
       bc[g.sn] = bc2;
       bc[2 * g.sn] = bc3;
-      cons2prim_mhd(eos, uc, bc1, bc2, bc3, wc);
+      cons2prim_mhd(eos_of_block(eos, blk), uc, bc1, bc2, bc3, wc);
     } else {
-      cons2prim_hydro(eos, uc, wc);
+      cons2prim_hydro(eos_of_block(eos, blk), uc, wc);
     }
     if (uc[IDN] != d0) ub[IDN * g.sn] = uc[IDN];
     if (uc[IEN] != e0) ub[IEN * g.sn] = uc[IEN];
@@ -141,7 +141,8 @@ struct Cons2PrimPoint {
     for (int n = 0; n < ns; ++n) {
       const idx_t o = ((idx_t)blk * ns + n) * g.sn + c;
       const Real s0 = s[o];
-      const Real sn = (s0 < eos.sfloor * uc[IDN]) ? eos.sfloor * uc[IDN] : s0;
+      const Real sfl = eos_sfloor(eos, blk);
+      const Real sn = (s0 < sfl * uc[IDN]) ? sfl * uc[IDN] : s0;
       if (sn != s0) s[o] = sn;
       r[o] = sn / uc[IDN];
     }

@@ -56,7 +56,25 @@ ATHK_HD Real fdiv(Real a, Real b) {
 struct EosParams {
   Real gamma, gm1, igm1;   // igm1 = 1.0/(gamma-1.0)
   Real dfloor, pfloor, sfloor;
+  // Every MeshBlock of the reference owns an EquationOfState with its own floors (eos/eos.hpp:
+  // 161-163), and they can differ: null = the three values above for every block, else
+  // [nb][3] = (dfloor, pfloor, sfloor) of each local block (athk_set_block_floors)
+  const Real *blk_floors;
 };
+
+// floors of block blk (uniform branch; a no-op unless per-block floors were set)
+ATHK_HD Real eos_dfloor(const EosParams &e, int blk) { return e.blk_floors ? e.blk_floors[3 * blk] : e.dfloor; }
+ATHK_HD Real eos_pfloor(const EosParams &e, int blk) { return e.blk_floors ? e.blk_floors[3 * blk + 1] : e.pfloor; }
+ATHK_HD Real eos_sfloor(const EosParams &e, int blk) { return e.blk_floors ? e.blk_floors[3 * blk + 2] : e.sfloor; }
+ATHK_HD EosParams eos_of_block(const EosParams &e, int blk) {
+  EosParams r = e;
+  if (e.blk_floors) {
+    r.dfloor = e.blk_floors[3 * blk];
+    r.pfloor = e.blk_floors[3 * blk + 1];
+    r.sfloor = e.blk_floors[3 * blk + 2];
+  }
+  return r;
+}
 
 ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
   EosParams e;
@@ -66,6 +84,7 @@ ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
   e.dfloor = dfloor;
   e.pfloor = pfloor;
   e.sfloor = sfloor;
+  e.blk_floors = nullptr;
   return e;
 }
 

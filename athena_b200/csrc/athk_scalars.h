@@ -98,12 +98,13 @@ template <int DIR, int ORDER>
 struct ScalarFacePoint {
   Grid g;
   Geom geo;
-  Real sfloor;
+  EosParams eos;    // for the concentration floor of block blk
   int ns;
   const Real *r;    // [nb][ns][sn]
   MassFlux mf;
   Real *sflux;      // s_flux[DIR]  [nb][ns][sn]
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const Real sfloor = eos_sfloor(eos, blk);
     const idx_t c = gidx(g, k, j, i);
     const Real m = mf.p[DIR][(idx_t)blk * mf.bstride + c];
     const int n_dir = (DIR == 0) ? i : (DIR == 1 ? j : k);
@@ -123,12 +124,13 @@ template <int ORDER>
 struct ScalarIntegratePoint {
   Grid g;
   Geom geo;
-  Real sfloor;
+  EosParams eos;       // for the concentration floor of block blk
   int ns;
   const Real *r;
   MassFlux mf;
   HydroIntegrate hi;   // registers s / s1 and the stage weights
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const Real sfloor = eos_sfloor(eos, blk);
     const idx_t c = gidx(g, k, j, i);
     const Real dx1 = geo.dxf[0][blk * geo.PG + i], dx2 = geo.dxf[1][blk * geo.PG + j],
                dx3 = geo.dxf[2][blk * geo.PG + k];

@@ -184,10 +184,11 @@ ATHK_HD void face_compute_from(const SweepArgs &a, int blk, idx_t c, int n_dir, 
       wr[v] = lo;
     }
     // ApplyPrimitiveFloors on both states (ppm.cpp:326-332)
-    wl[IDN] = (wl[IDN] > a.eos.dfloor) ? wl[IDN] : a.eos.dfloor;
-    wl[IPR] = (wl[IPR] > a.eos.pfloor) ? wl[IPR] : a.eos.pfloor;
-    wr[IDN] = (wr[IDN] > a.eos.dfloor) ? wr[IDN] : a.eos.dfloor;
-    wr[IPR] = (wr[IPR] > a.eos.pfloor) ? wr[IPR] : a.eos.pfloor;
+    const Real dfl = eos_dfloor(a.eos, blk), pfl = eos_pfloor(a.eos, blk);
+    wl[IDN] = (wl[IDN] > dfl) ? wl[IDN] : dfl;
+    wl[IPR] = (wl[IPR] > pfl) ? wl[IPR] : pfl;
+    wr[IDN] = (wr[IDN] > dfl) ? wr[IDN] : dfl;
+    wr[IPR] = (wr[IPR] > pfl) ? wr[IPR] : pfl;
   } else if (ORDER == 2) {
     Real q0[7], q1[7], q2[7], q3[7];
     st.cell(-1, q1);

@@ -100,8 +100,8 @@ __device__ __forceinline__ void plm_recon_cell(const SweepArgs &a, int blk, cons
 }
 
 template <bool MHD, class ST>
-__device__ __forceinline__ void ppm_recon_cell(const EosParams &eos, const ST &st, int off0, Real up[7],
-                                               Real lo[7]) {
+__device__ __forceinline__ void ppm_recon_cell(const EosParams &eos, int blk, const ST &st, int off0,
+                                               Real up[7], Real lo[7]) {
   Real qm2[7], qm1[7], q0[7], qp1[7], qp2[7];
   st.cell(off0 - 2, qm2);
   st.cell(off0 - 1, qm1);
@@ -110,10 +110,11 @@ __device__ __forceinline__ void ppm_recon_cell(const EosParams &eos, const ST &s
   st.cell(off0 + 2, qp2);
 #pragma unroll
   for (int v = 0; v < (MHD ? 7 : 5); ++v) ppm_cell(qm2[v], qm1[v], q0[v], qp1[v], qp2[v], &up[v], &lo[v]);
-  up[IDN] = (up[IDN] > eos.dfloor) ? up[IDN] : eos.dfloor;
-  up[IPR] = (up[IPR] > eos.pfloor) ? up[IPR] : eos.pfloor;
-  lo[IDN] = (lo[IDN] > eos.dfloor) ? lo[IDN] : eos.dfloor;
-  lo[IPR] = (lo[IPR] > eos.pfloor) ? lo[IPR] : eos.pfloor;
+  const Real dfl = eos_dfloor(eos, blk), pfl = eos_pfloor(eos, blk);
+  up[IDN] = (up[IDN] > dfl) ? up[IDN] : dfl;
+  up[IPR] = (up[IPR] > pfl) ? up[IPR] : pfl;
+  lo[IDN] = (lo[IDN] > dfl) ? lo[IDN] : dfl;
+  lo[IPR] = (lo[IPR] > pfl) ? lo[IPR] : pfl;
 }
 
 template <int DIR, int ORDER, bool MHD, int RS>
@@ -226,7 +227,7 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
       const SmemStencil<MHD> st = {&sQ[0][0][lane], (n - row_first) % NR, NR};
       if (fvalid) {
         Real up[7];
-        if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, 0, up, wr);
+        if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, vBlk[lane] & 0x1fffffff, st, 0, up, wr);
         else plm_recon_cell<DIR, MHD>(a, vBlk[lane] & 0x1fffffff, st, 0, n, up, wr);
 #pragma unroll
         for (int v = 0; v < NW; ++v) sW[r][v][lane] = up[v];
@@ -236,7 +237,7 @@ k_sweep_tile_staged(const SweepArgs a, const int nb, const int o_lo, const int n
         }
         if (step == 0 && r == 0) {   // nobody owns cell n_s-1: the first face's left state
           Real lo_unused[7];
-          if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, st, -1, up, lo_unused);
+          if constexpr (ORDER == 3) ppm_recon_cell<MHD>(a.eos, vBlk[lane] & 0x1fffffff, st, -1, up, lo_unused);
           else plm_recon_cell<DIR, MHD>(a, vBlk[lane] & 0x1fffffff, st, -1, n - 1, up, lo_unused);
 #pragma unroll
           for (int v = 0; v < NW; ++v) sWtop[1][v][lane] = up[v];
@@ -444,7 +445,7 @@ k_sweep_x1_cells(const SweepX1<ORDER, MHD, RS> f, const int kl, const int jl, co
     if (cell_upd) f.prefetch_cell(blk, k, j, i);
     const GlobalRowStencil<MHD> st = {a, blk, c};
     if constexpr (ORDER == 3) {
-      ppm_recon_cell<MHD>(a.eos, st, 0, up, lo);
+      ppm_recon_cell<MHD>(a.eos, blk, st, 0, up, lo);
     } else if constexpr (ORDER == 2) {
       plm_recon_cell<0, MHD>(a, blk, st, 0, i, up, lo);
     } else {   // donor cell: both face states are the cell average (dc.cpp)

@@ -188,8 +188,9 @@ class EquationOfState {   // eos/eos.hpp:32-181
   Real GetGamma() const { return gamma_; }
   Real GetDensityFloor() const { return dfloor_; }
   Real GetPressureFloor() const { return pfloor_; }
+  Real GetScalarFloor() const { return sfloor_; }
  private:
-  Real gamma_, dfloor_, pfloor_;
+  Real gamma_, dfloor_, pfloor_, sfloor_;
 };
 
 class MeshBlock {   // mesh/mesh.hpp:75-200

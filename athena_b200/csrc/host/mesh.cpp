@@ -106,6 +106,7 @@ EquationOfState::EquationOfState(ParameterInput *pin) {   // eos/adiabatic_*.cpp
   gamma_ = pin->GetReal("hydro", "gamma");
   dfloor_ = pin->GetOrAddReal("hydro", "dfloor", std::sqrt(1024 * float_min));
   pfloor_ = pin->GetOrAddReal("hydro", "pfloor", std::sqrt(1024 * float_min));
+  sfloor_ = pin->GetOrAddReal("hydro", "sfloor", std::sqrt(1024 * float_min));
 }
 
 MeshBlock::MeshBlock(int igid, int ilid, LogicalLocation iloc, RegionSize bs, Mesh *pm, ParameterInput *pin)
@@ -248,7 +249,17 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   cfg.gamma = blocks_[0]->peos->GetGamma();
   cfg.dfloor = blocks_[0]->peos->GetDensityFloor();
   cfg.pfloor = blocks_[0]->peos->GetPressureFloor();
+  cfg.sfloor = blocks_[0]->peos->GetScalarFloor();
   AthkCheck(athk_create(&cfg, &athk), "Mesh constructor (athk_create)");
+  // each MeshBlock's own EquationOfState: blocks built after the first read the floors back from
+  // the 6-digit strings the first one stored (see ParameterInput::GetOrAddReal)
+  for (int n = 1; n < nblocal; ++n) {
+    const EquationOfState *pe = blocks_[n]->peos;
+    if (pe->GetDensityFloor() != cfg.dfloor || pe->GetPressureFloor() != cfg.pfloor ||
+        pe->GetScalarFloor() != cfg.sfloor)
+      AthkCheck(athk_set_block_floors(athk, n, pe->GetDensityFloor(), pe->GetPressureFloor(), pe->GetScalarFloor()),
+                "Mesh constructor (athk_set_block_floors)");
+  }
   {   // HydroSourceTerms constructor (hydro/srcterms/hydro_srcterms.cpp:42-46)
     const Real g1 = pin->GetOrAddReal("hydro", "grav_acc1", 0.0);
     const Real g2 = pin->GetOrAddReal("hydro", "grav_acc2", 0.0);

@@ -163,8 +163,11 @@ int ParameterInput::GetOrAddInteger(const std::string &b, const std::string &n, 
 }
 Real ParameterInput::GetOrAddReal(const std::string &b, const std::string &n, Real def) {
   if (DoesParameterExist(b, n)) return GetReal(b, n);
+  // Stored as the reference stores it: default stream precision, 6 significant digits
+  // (parameter_input.cpp:603-623).  The caller that adds the parameter gets `def` itself, later
+  // callers read the string back -- which is why the MeshBlocks after the first see floors of
+  // 3.46945e-18 where the first sees sqrt(1024*FLT_MIN) (Mesh constructor, athk_set_block_floors).
   std::stringstream ss;
-  ss.precision(17);
   ss << def;
   Add(FindOrAdd(b), n, ss.str(), kDefaultComment);
   return def;
@@ -185,8 +188,7 @@ int ParameterInput::SetInteger(const std::string &b, const std::string &n, int v
 }
 Real ParameterInput::SetReal(const std::string &b, const std::string &n, Real v) {
   std::stringstream ss;
-  ss.precision(17);
-  ss << v;
+  ss << v;   // 6 significant digits, as parameter_input.cpp:706-716
   Add(FindOrAdd(b), n, ss.str(), "# Updated during run time");
   return v;
 }

@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstdio>
 
+#include <limits>
+
 #include "athena.hpp"
 
 //========================================================================================
@@ -119,6 +121,49 @@ static void OrszagTangGenerator(MeshBlock *pmb, ParameterInput *) {
 }
 
 //========================================================================================
+// noise for pgens with random perturbations
+namespace {
+// The reference draws its noise from utils/ran2.cpp: L'Ecuyer's combined multiplicative
+// congruential generator with a Bays-Durham shuffle table (Press et al., "ran2"), one stream per
+// MeshBlock, seeded with -1 - gid.  Same published algorithm, so the same numbers.
+class ShuffledLEcuyer {
+ public:
+  explicit ShuffledLEcuyer(std::int64_t seed) {
+    s1_ = (seed < 1) ? ((-seed < 1) ? 1 : -seed) : seed;
+    s2_ = s1_;
+    for (int j = kTab + 7; j >= 0; --j) {   // 8 warm-up draws, then fill the table from the top
+      AdvanceFirst();
+      if (j < kTab) tab_[j] = s1_;
+    }
+    last_ = tab_[0];
+  }
+  double Next() {
+    AdvanceFirst();
+    const std::int64_t q = s2_ / 52774;   // Schrage: 40692 * s2 mod 2147483399
+    s2_ = 40692 * (s2_ - q * 52774) - q * 3791;
+    if (s2_ < 0) s2_ += kM2;
+    const int j = static_cast<int>(last_ / (1 + (kM1 - 1) / kTab));
+    last_ = tab_[j] - s2_;
+    tab_[j] = s1_;
+    if (last_ < 1) last_ += kM1 - 1;
+    const double v = (1.0 / kM1) * last_;
+    const double vmax = 1.0 - std::numeric_limits<double>::epsilon();
+    return v > vmax ? vmax : v;
+  }
+
+ private:
+  static constexpr std::int64_t kM1 = 2147483563, kM2 = 2147483399;
+  static constexpr int kTab = 32;
+  void AdvanceFirst() {   // Schrage: 40014 * s1 mod 2147483563
+    const std::int64_t q = s1_ / 53668;
+    s1_ = 40014 * (s1_ - q * 53668) - q * 12211;
+    if (s1_ < 0) s1_ += kM1;
+  }
+  std::int64_t s1_, s2_, last_, tab_[kTab];
+};
+}  // namespace
+
+//========================================================================================
 // kh: iprob = 2 (tanh shear layer, single mode; kh.cpp:159-215) and iprob = 4 (the "Lecoanet"
 // test: two resolved shear layers, fully periodic, passive-scalar dye + its entropy as a user
 // history column; kh.cpp:285-422, PassiveDyeEntropy :516-536)
@@ -142,10 +187,10 @@ static void KHInitUserMeshData(Mesh *pm, ParameterInput *pin) {
 
 static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
   const int iprob = pin->GetInteger("problem", "iprob");
-  if (iprob != 2 && iprob != 4) {
+  if (iprob != 1 && iprob != 2 && iprob != 4) {
     std::stringstream msg;
     msg << "### FATAL ERROR in kh ProblemGenerator" << std::endl
-        << "iprob=" << iprob << " is not built into the B200 host (iprob=2 and 4 are)";
+        << "iprob=" << iprob << " is not built into the B200 host (iprob=1, 2 and 4 are)";
     ATHENA_ERROR(msg);
   }
   const Real vflow = pin->GetReal("problem", "vflow");
@@ -153,6 +198,39 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
   const Real gm1 = pmb->peos->GetGamma() - 1.0;
   Coordinates *pc = pmb->pcoord;
   AthenaArray<Real> &u = pmb->phydro->u;
+  if (iprob == 1) {   // kh.cpp:78-153: dense stream in |x2| < 1/4 between two slip surfaces, white noise
+    const Real drat = pin->GetReal("problem", "drat");
+    ShuffledLEcuyer noise(-1 - pmb->gid);
+    for (int k = pmb->ks; k <= pmb->ke; k++)
+      for (int j = pmb->js; j <= pmb->je; j++)
+        for (int i = pmb->is; i <= pmb->ie; i++) {
+          const bool stream = std::abs(pc->x2v(j)) < 0.25;
+          // every cell draws two numbers, cells of the stream two more that replace them
+          Real m1 = vflow + amp * (noise.Next() - 0.5);
+          Real m2 = amp * (noise.Next() - 0.5);
+          if (stream) {
+            m1 = -drat * (vflow + amp * (noise.Next() - 0.5));
+            m2 = drat * amp * (noise.Next() - 0.5);
+          }
+          u(IDN, k, j, i) = stream ? drat : 1.0;
+          u(IM1, k, j, i) = m1;
+          u(IM2, k, j, i) = m2;
+          u(IM3, k, j, i) = 0.0;
+          u(IEN, k, j, i) = 2.5 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
+          for (int n = 0; n < NSCALARS; ++n)   // odd scalars mark the ambient medium, even ones the stream
+            pmb->pscalars->s(n, k, j, i) = stream ? std::abs(n % 2 - 1) * drat : n % 2;
+        }
+    if (MAGNETIC_FIELDS_ENABLED) {
+      const Real b0 = pin->GetReal("problem", "b0");
+      FaceField &b = pmb->pfield->b;
+      for (int k = pmb->ks; k <= pmb->ke; k++)
+        for (int j = pmb->js; j <= pmb->je; j++) {
+          for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0;
+          for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * b0 * b0;
+        }
+    }
+    return;
+  }
   if (iprob == 4) {
     const Real drho_rho0 = pin->GetOrAddReal("problem", "drho_rho0", 0.0);
     const Real vboost = pin->GetOrAddReal("problem", "vboost", 0.0);

@@ -228,6 +228,10 @@ class Context:
         multi = capi.SHAPES[array][0] != 1
         return ((nvar,) + sh) if multi else sh
 
+    def set_block_floors(self, lb, dfloor, pfloor, sfloor):
+        """Floors of local block lb (each MeshBlock of the reference owns an EquationOfState)."""
+        self.call("athk_set_block_floors", lb, float(dfloor), float(pfloor), float(sfloor))
+
     def upload(self, array, lb, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         if a.shape != self.shape(array):

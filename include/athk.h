@@ -164,6 +164,13 @@ int athk_set_boundary_flags(athk_ctx *ctx, int lb, const int flags[6]);
  * athk_cons2prim (task PHY_BVAL, time_integrator.cpp:2276); athk_stage does it itself.
  * No-op when no local block has a physical boundary. */
 int athk_apply_physical_boundaries(athk_ctx *ctx);
+/* Floors of local block lb.  In the reference every MeshBlock owns an EquationOfState
+ * (mesh/meshblock.cpp:160-190) whose floors come from pin->GetOrAddReal("hydro","dfloor"|"pfloor"|
+ * "sfloor", sqrt(1024*FLT_MIN)) (eos/adiabatic_mhd.cpp:29-31): the first block gets the default in
+ * full precision, the blocks built after it read back the 6-digit string the first call stored
+ * (parameter_input.cpp:603-623), so floors may differ from block to block.  Default: athk_config's
+ * floors for every block. */
+int athk_set_block_floors(athk_ctx *ctx, int lb, double dfloor, double pfloor, double sfloor);
 /* HydroSourceTerms (hydro/srcterms/hydro_srcterms.cpp:42-46): the constant accelerations
  * <hydro> grav_acc1 / grav_acc2 / grav_acc3.  All zero (the default) = no source terms. */
 int athk_set_constant_acceleration(athk_ctx *ctx, double g1, double g2, double g3);

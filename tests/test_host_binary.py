@@ -63,6 +63,15 @@ def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     return b
 
 
+def kh_random_blocks(b0):
+    b = refrun.kh_blocks(mesh=(16, 32, 8), block=(8, 16, 8), tlim=0.05, rst_dt=0.025, integrator="vl2", xorder=2,
+                         iprob=1, vflow=0.5, b0=b0)
+    b["problem"]["drat"] = 2.0
+    b["mesh"]["x2min"], b["mesh"]["x2max"] = -0.5, 0.5
+    b["hydro"]["gamma"] = 1.4
+    return b
+
+
 def with_gravity(blocks, **acc):
     blocks["hydro"].update(acc)
     return blocks
@@ -147,6 +156,10 @@ CASES = {
     "kh_mhd_gravity_all_axes": ("kh_mhd_hlld_s1", "kh", True, lambda: with_gravity(
         refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03, rst_dt=0.015, integrator="vl2", xorder=2,
                          b0=0.5), grav_acc1=0.3, grav_acc2=-0.5, grav_acc3=0.2), ["--nscalars=1"]),
+    # kh iprob=1: slip surfaces with white noise from the reference's generator (utils/ran2.cpp), one
+    # stream per MeshBlock seeded by its gid; scalars mark stream / ambient medium
+    "kh_random_2scalars": ("kh_hydro_hllc_s2", "kh", False, lambda: kh_random_blocks(None), ["--nscalars=2"]),
+    "kh_random_mhd": ("kh_mhd_hlld_s1", "kh", True, lambda: kh_random_blocks(0.2), ["--nscalars=1"]),
     # --flux=roe through the host's configure switch
     "mhd_blast_roe": ("blast_mhd_roe", "blast", True, blast_blocks, ["--flux=roe"]),
 }
