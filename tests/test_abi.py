@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from athena_b200 import capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -77,3 +79,53 @@ def test_operator_argument_checks(emul_lib):
     sums = (ctypes.c_double * 4)()
     assert lib.athk_history(h, sums, 4) == -1 and b"need room" in lib.athk_last_error()
     ctx.close()
+
+
+def block_floor_check(lib):
+    """athk_set_block_floors / athk_add_source_terms through the C ABI: W(U) floors each block
+    with its own values; constant accelerations change momentum and energy as
+    hydro/srcterms/constant_acc.cpp does; bad arguments are refused."""
+    import numpy as np
+    from athena_b200 import pyhost
+    mesh = pyhost.UniformMesh((8, 4, 4), (4, 4, 4), (0.0,) * 3, (1.0,) * 3, ng=2)
+    ctx = pyhost.Context(mesh, False, 1.4, lib=lib, nscalars=1, grav_acc=(0.0, 0.5, 0.0))
+    h = ctx.h
+    assert lib.athk_set_block_floors(h, 2, 1e-3, 1e-3, 1e-3) == -1 and b"out of range" in lib.athk_last_error()
+    assert lib.athk_set_block_floors(h, 1, -1.0, 1e-3, 1e-3) == -1 and b"must be positive" in lib.athk_last_error()
+    ctx.set_block_floors(1, 1.0e-3, 2.0e-3, 4.0e-3)
+    u = np.zeros(ctx.shape("U"))
+    u[0] = 1.0e-30           # density far below any floor
+    u[4] = 1.0e-30
+    s = np.zeros(ctx.shape("S"))
+    for lb in range(2):
+        ctx.upload("U", lb, u)
+        ctx.upload("S", lb, s)
+    ctx.call("athk_cons2prim", 0)
+    fmin = np.sqrt(1024 * np.float64(np.finfo(np.float32).tiny))     # the default, block 0
+    for lb, (df, pf, sf) in enumerate(((fmin, fmin, fmin), (1.0e-3, 2.0e-3, 4.0e-3))):
+        w, r = ctx.download("W", lb), ctx.download("R", lb)
+        assert np.all(w[0] == df) and np.all(w[4] == pf)
+        assert np.all(r[0] == (sf * df) / df)
+    # SRC_TERM on block 1: u(IM2) += dt*rho*g2, u(IEN) += dt*rho*g2*v2 on the active zone only
+    before = ctx.download("U", 1)
+    w = ctx.download("W", 1)
+    ctx.call("athk_add_source_terms", 0.25)
+    after = ctx.download("U", 1)
+    act = (slice(2, 6),) * 3
+    src = 0.25 * w[0] * 0.5
+    np.testing.assert_array_equal(after[2][act], (before[2] + src)[act])
+    np.testing.assert_array_equal(after[4][act], (before[4] + src * w[2])[act])
+    ghost = np.ones(before[2].shape, dtype=bool)
+    ghost[act] = False
+    np.testing.assert_array_equal(after[2][ghost], before[2][ghost])
+    np.testing.assert_array_equal(after[1], before[1])
+    ctx.close()
+
+
+def test_block_floors_and_source_terms_host_logic(emul_lib):
+    block_floor_check(emul_lib)
+
+
+@pytest.mark.gpu
+def test_block_floors_and_source_terms_on_gpu(cuda_lib):
+    block_floor_check(cuda_lib)
