@@ -1,6 +1,7 @@
 // main.cpp -- driver of the B200 host: argv -> ParameterInput -> Mesh -> TimeIntegratorTaskList
 // -> main loop, following src/main.cpp:65-666 (flags :125-203, setup :230-424, loop :457-571,
 // wrap-up :584-652).  Prints the reference's own throughput lines (zone-cycles/...second).
+#include <signal.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -10,6 +11,34 @@
 #include <iterator>
 
 #include "athena.hpp"
+
+// Graceful termination (utils/signal_handler.cpp:34-141, main.cpp:216-218,568-575,613-618): SIGTERM,
+// SIGINT and the -t wall-time alarm only raise a flag; the main loop finishes its cycle, and the
+// final outputs -- including the restart dump to resume from -- are written as usual.
+namespace {
+volatile sig_atomic_t g_signal_term = 0, g_signal_int = 0, g_signal_alrm = 0;
+void RaiseSignalFlag(int s) {
+  if (s == SIGTERM) g_signal_term = 1;
+  if (s == SIGINT) g_signal_int = 1;
+  if (s == SIGALRM) g_signal_alrm = 1;
+  signal(s, RaiseSignalFlag);
+}
+bool SignalRaised() { return g_signal_term || g_signal_int || g_signal_alrm; }
+
+void ShowConfig() {   // -c: what configure.py fixes in the reference is chosen at run time here
+  std::cout << "This Athena++ executable (B200 path) is configured with:" << std::endl
+            << "  Problem generator:          " << g_config.problem << std::endl
+            << "  Coordinate system:          cartesian" << std::endl
+            << "  Equation of state:          adiabatic" << std::endl
+            << "  Riemann solver:             "
+            << (g_config.flux.empty() ? (g_config.mhd ? "hlld" : "hllc") : g_config.flux) << std::endl
+            << "  Magnetic fields:            " << (g_config.mhd ? "ON" : "OFF") << std::endl
+            << "  Number of ghost cells:      " << g_config.nghost << std::endl
+            << "  Number of scalars:          " << g_config.nscalars << std::endl
+            << "  Floating-point precision:   double" << std::endl
+            << "  Device:                     CUDA sm_100a through libathk (include/athk.h)" << std::endl;
+}
+}  // namespace
 
 static void ParseConfigure(const std::string &s) {
   // the tokens configure.py would take: --prob=<name> -b --flux=<name> --nghost=<n> --nscalars=<n>
@@ -26,7 +55,8 @@ static void ParseConfigure(const std::string &s) {
 
 int main(int argc, char *argv[]) {
   std::string input_filename, restart_filename, run_dir;
-  bool narg_flag = false, have_cfg = false;
+  bool narg_flag = false, have_cfg = false, carg_flag = false;
+  int wtlim = 0;
   std::string cfg_cmdline;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -34,6 +64,12 @@ int main(int argc, char *argv[]) {
     else if (a == "-r" && i + 1 < argc) restart_filename = argv[++i];
     else if (a == "-d" && i + 1 < argc) run_dir = argv[++i];
     else if (a == "-n") narg_flag = true;
+    else if (a == "-c") carg_flag = true;
+    else if (a == "-t" && i + 1 < argc) {   // -t <hh:mm:ss>
+      int wth = 0, wtm = 0, wts = 0;
+      std::sscanf(argv[++i], "%d:%d:%d", &wth, &wtm, &wts);
+      wtlim = wth * 3600 + wtm * 60 + wts;
+    }
     else if (a == "-h") {
       std::cout << "Athena++ (B200 path)" << std::endl
                 << "Usage: " << argv[0] << " [options] [block/par=value ...]" << std::endl
@@ -41,6 +77,8 @@ int main(int argc, char *argv[]) {
                 << "  -r <file>   restart with this file" << std::endl
                 << "  -d <dir>    specify run dir [current dir]" << std::endl
                 << "  -n          parse input file and quit" << std::endl
+                << "  -c          show configuration and quit" << std::endl
+                << "  -t hh:mm:ss wall time limit for final output" << std::endl
                 << "  --prob=<pgen> [-b] [--flux=..] [--nghost=n] [--nscalars=n]  configure-time choices "
                    "of the reference (default: the athinput's <comment> configure line)" << std::endl;
       return 0;
@@ -48,6 +86,11 @@ int main(int argc, char *argv[]) {
       cfg_cmdline += a + " ";
       have_cfg = true;
     }
+  }
+  if (carg_flag && input_filename.empty() && restart_filename.empty()) {
+    if (have_cfg) ParseConfigure(cfg_cmdline);
+    ShowConfig();
+    return 0;
   }
   if (input_filename.empty() && restart_filename.empty()) {
     std::cout << "### FATAL ERROR in main" << std::endl << "No input file or restart file is specified." << std::endl;
@@ -82,6 +125,14 @@ int main(int argc, char *argv[]) {
     pinput->ModifyFromCmdline(argc, argv);
     if (have_cfg) ParseConfigure(cfg_cmdline);
     else if (pinput->DoesParameterExist("comment", "configure")) ParseConfigure(pinput->GetString("comment", "configure"));
+    if (carg_flag) {
+      ShowConfig();
+      return 0;
+    }
+    signal(SIGTERM, RaiseSignalFlag);
+    signal(SIGINT, RaiseSignalFlag);
+    signal(SIGALRM, RaiseSignalFlag);
+    if (wtlim > 0) alarm(wtlim);
     if (!run_dir.empty() && chdir(run_dir.c_str()) != 0) {
       std::stringstream msg;
       msg << "### FATAL ERROR in function [ChangeRunDir]" << std::endl << "Cannot cd to directory '" << run_dir << "'";
@@ -117,14 +168,19 @@ int main(int argc, char *argv[]) {
       mbcnt += pmesh->nbtotal;
       pmesh->NewTimeStep();
       if (pmesh->time < pmesh->tlim) pouts->MakeOutputs(pmesh, pinput);   // final output happens later (main.cpp:546)
+      if (SignalRaised()) break;
     }
+    if (wtlim > 0) alarm(0);
     AthkCheck(athk_sync(pmesh->athk), "main");
     const double wsec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     pmesh->OutputCycleDiagnostics();
     pmesh->UserWorkAfterLoop(pinput);
     pouts->MakeOutputs(pmesh, pinput, true);   // final outputs (main.cpp:589)
 
-    if (pmesh->ncycle == pmesh->nlim) std::cout << std::endl << "Terminating on cycle limit" << std::endl;
+    if (g_signal_term) std::cout << std::endl << "Terminating on Terminate signal" << std::endl;
+    else if (g_signal_int) std::cout << std::endl << "Terminating on Interrupt signal" << std::endl;
+    else if (g_signal_alrm) std::cout << std::endl << "Terminating on wall-time limit" << std::endl;
+    else if (pmesh->ncycle == pmesh->nlim) std::cout << std::endl << "Terminating on cycle limit" << std::endl;
     else std::cout << std::endl << "Terminating on time limit" << std::endl;
     char buf[256];
     std::snprintf(buf, sizeof(buf), "time=%.16e cycle=%d\ntlim=%.16e nlim=%d\n", pmesh->time, pmesh->ncycle,

@@ -483,6 +483,52 @@ def test_restart_resumes_bitwise_on_gpu(cuda_lib, case):
     check_restart(CUDA_BIN, case)
 
 
+def test_wall_time_limit_and_signals_checkpoint_and_resume(emul_binary):
+    """-t hh:mm:ss and SIGTERM (utils/signal_handler.cpp, main.cpp:568-618): the run stops after
+    the current cycle, says why, and leaves a final restart dump; resuming from it ends on the
+    bits of the uninterrupted run."""
+    import signal
+    import time
+    blocks = blast_blocks(n=32, blk=16, tlim=0.12)
+    blocks["output2"]["dt"] = 1.0      # no intermediate dumps: only the final one
+    dirs = []
+    try:
+        wd_full, r = run_host(emul_binary, blocks, "blast", True)
+        dirs.append(wd_full)
+        assert r.returncode == 0 and "Terminating on time limit" in r.stdout
+        full = refrun.read_rst(glob.glob(wd_full + "/*.final.rst")[0])
+        for how in ("alarm", "sigterm"):
+            wd = tempfile.mkdtemp(prefix="athhost_")
+            dirs.append(wd)
+            inp = os.path.join(wd, "athinput.host")
+            with open(inp, "w") as f:
+                f.write(refrun.format_athinput(blocks))
+            args = [emul_binary, "-i", inp, "-d", wd, "--prob=blast", "-b"]
+            if how == "alarm":
+                r = subprocess.run(args + ["-t", "00:00:01"], capture_output=True, text=True, timeout=600)
+                out, msg = r.stdout, "Terminating on wall-time limit"
+            else:
+                p = subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                time.sleep(1.0)
+                p.send_signal(signal.SIGTERM)
+                out, _ = p.communicate(timeout=600)
+                msg = "Terminating on Terminate signal"
+            if "Terminating on time limit" in out:
+                pytest.skip("host finished the whole run within a second")
+            assert msg in out, out[-1500:]
+            part = refrun.read_rst(glob.glob(wd + "/*.final.rst")[0])
+            assert 0 < part["ncycle"] < full["ncycle"] and part["time"] < full["time"]
+            wd2 = tempfile.mkdtemp(prefix="athhost_")
+            dirs.append(wd2)
+            r = subprocess.run([emul_binary, "-r", glob.glob(wd + "/*.final.rst")[0], "-d", wd2, "--prob=blast", "-b"],
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0 and "Terminating on time limit" in r.stdout, r.stdout[-1500:]
+            rst_equal(full, refrun.read_rst(glob.glob(wd2 + "/*.final.rst")[0]))
+    finally:
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+
+
 def test_parameter_input_error_behaviour(emul_binary):
     """Missing parameter / unknown cmdline override / unpaired periodic BC: message + exit status as
     ATHENA_ERROR does (src/defs.hpp.in:155-159, parameter_input.cpp:352-395)."""
