@@ -8,11 +8,14 @@
 //                 :575-620 (vector potential), :640-760,1040-1075 (right eigenvectors)
 //   blast         src/pgen/blast.cpp:52-259
 //   orszag_tang   src/pgen/orszag_tang.cpp:40-110
-//   kh            src/pgen/kh.cpp:159-215 (iprob = 2)
+//   kh            src/pgen/kh.cpp:78-153 (iprob = 1, noise from utils/ran2.cpp), :159-215 (iprob = 2),
+//                 :290-420 (iprob = 4, Lecoanet et al. with the dye-entropy history output)
+//   shock_tube    src/pgen/shock_tube.cpp:305-575 (ICs), :46-270 (errors: Sod, Ryu-Jones 2a)
+//   cpaw          src/pgen/cpaw.cpp:55-390
+//   field_loop    src/pgen/field_loop.cpp:52-262 (iprob 1-5)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
-
 #include <limits>
 
 #include "athena.hpp"
