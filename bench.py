@@ -23,6 +23,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_ALG_MHD_VL2 = 320.0   # algorithmic bytes per zone-cycle, SURVEY.md section 8(d)
+F_ALG_MHD_VL2 = 3600.0  # algorithmic FP64 flops per zone-cycle (div/sqrt as 8-10), SURVEY.md section 8(d)
+FP64_PEAK_TFLOPS = 36.0  # 2 flops x 18.0 T FP64 FMA thread-instructions/s, measured on this pool's B200s
+#                          with tools/micro/fp64_peak.cu (profiles/README.md); not in MEASURED_PEAKS.json
 # algorithmic bytes per zone of ONE launch of the named kernel (kernel table)
 DOMINANT_ALG_BYTES = {"sweep_x1": 31 * 8, "sweep_x2": 16 * 8, "sweep_x3": 16 * 8}
 
@@ -399,6 +402,11 @@ def run_ours(args):
                 "peak_source": peak_src, "dominant": dominant,
                 "breakdown_ms_per_cycle": {k: round(v["ms_per_cycle"], 4) for k, v in sorted(
                     breakdown.items(), key=lambda kv: -kv[1]["ms_per_cycle"])}}
+        # the second ceiling SURVEY 8(d) asks for: the fused stage is FP64-pipe bound, not HBM bound
+        tflops = per_gpu_value * F_ALG_MHD_VL2 / 1e12
+        roof["fp64"] = {"alg_flops_per_zone_cycle": F_ALG_MHD_VL2, "achieved": tflops, "peak": FP64_PEAK_TFLOPS,
+                        "unit": "TFLOP/s", "frac": tflops / FP64_PEAK_TFLOPS,
+                        "peak_source": "tools/micro/fp64_peak.cu: 18.0 T DFMA thread-instr/s"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
