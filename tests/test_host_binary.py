@@ -463,6 +463,16 @@ def check_restart(binary, case):
         r = subprocess.run([binary, "-r", mid, "-d", wd4, "time/nlim=%d" % (final_ref["ncycle"] - 1)] + flags,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "Terminating on cycle limit" in r.stdout
+        # ... and so does an input file given with -i next to -r: only the blocks it names change
+        over = os.path.join(wd4, "athinput.override")
+        with open(over, "w") as f:
+            f.write("<time>\ntlim = %r\n" % (0.5 * (final_ref["time"] + refrun.read_rst(mid)["time"])))
+        r = subprocess.run([binary, "-r", mid, "-i", over, "-d", wd4] + flags, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0 and "Terminating on time limit" in r.stdout, r.stdout[-1500:]
+        short = refrun.read_rst(glob.glob(wd4 + "/*.final.rst")[0])
+        assert refrun.read_rst(mid)["time"] < short["time"] < final_ref["time"]
+        assert short["ncycle"] < final_ref["ncycle"]
     finally:
         for d in dirs:
             shutil.rmtree(d, ignore_errors=True)
