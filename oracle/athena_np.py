@@ -26,7 +26,12 @@ Reference sources followed (file:line under /root/reference/src):
   hydro/add_flux_divergence.cpp:39-96, mesh/weighted_ave.cpp:35-230    update
   hydro/new_blockdt.cpp:45-230, mesh/mesh.cpp:1236-1282                time step
   bvals/bvals.cpp:453-660, bvals/cc/*reflect*/outflow*, bvals/fc/*     physical boundaries
+  hydro/srcterms/constant_acc.cpp:25-76, task_list/time_integrator.cpp:1890-1913   constant accelerations
   task_list/time_integrator.cpp:111-606,1694-1885                      stage weights / order
+
+Floors: one value per run (eos.hpp:161).  The reference's MeshBlocks after the first actually read
+their floors back from a 6-digit string ("Bit-exactness rules"); no golden fixture
+lets a floor fire, that case is pinned through the host-binary tests instead.
 """
 import sys
 
