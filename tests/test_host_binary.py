@@ -463,6 +463,21 @@ def check_restart(binary, case):
         r = subprocess.run([binary, "-r", mid, "-d", wd4, "time/nlim=%d" % (final_ref["ncycle"] - 1)] + flags,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "Terminating on cycle limit" in r.stdout
+        # a changed output cadence after the restart: same dump schedule as the reference
+        # (ParameterInput::RollbackNextTime / ForwardNextTime, parameter_input.cpp:754-835)
+        new_dt = "output2/dt=%r" % (0.37 * blocks["output2"]["dt"])
+        wd5, wd6 = tempfile.mkdtemp(prefix="athref_"), tempfile.mkdtemp(prefix="athhost_")
+        dirs += [wd5, wd6]
+        r = subprocess.run([refrun.ref_binary(cfg), "-r", mid, "-d", wd5, new_dt], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert r.returncode == 0, r.stdout[-1500:]
+        r = subprocess.run([binary, "-r", mid, "-d", wd6, new_dt] + flags, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:]
+        names5 = sorted(os.path.basename(f) for f in glob.glob(wd5 + "/*.rst"))
+        names6 = sorted(os.path.basename(f) for f in glob.glob(wd6 + "/*.rst"))
+        assert names5 == names6 and len(names5) >= 2, (names5, names6)
+        for nm in names5:
+            rst_equal(refrun.read_rst(os.path.join(wd5, nm)), refrun.read_rst(os.path.join(wd6, nm)))
         # ... and so does an input file given with -i next to -r: only the blocks it names change
         over = os.path.join(wd4, "athinput.override")
         with open(over, "w") as f:
