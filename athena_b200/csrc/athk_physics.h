@@ -20,11 +20,7 @@
 
 #include <math.h>
 
-#if defined(__CUDACC__)
-#define ATHK_HD __host__ __device__ __forceinline__
-#else
-#define ATHK_HD inline
-#endif
+#include "athk_math.h"
 
 namespace athk {
 
@@ -46,12 +42,7 @@ ATHK_HD Real max_std(Real a, Real b) { return (a < b) ? b : a; }
 // same bits) for every finite non-zero b.  Static uniform regions (v = 0, equal pressures) make
 // several HLLD/HLLC numerators exactly 0, which sends the GPU's FP64 division into its
 // ~100-instruction slow path; the shortcut returns the identical result in 3 instructions.
-ATHK_HD Real fdiv(Real a, Real b) {
-#if defined(__CUDA_ARCH__)
-  if (a == 0.0 && b != 0.0 && fabs(b) <= 1.7976931348623157e308) return a * b;
-#endif
-  return a / b;
-}
+ATHK_HD Real fdiv(Real a, Real b) { return fdiv_ieee(a, b); }
 
 struct EosParams {
   Real gamma, gm1, igm1;   // igm1 = 1.0/(gamma-1.0)
@@ -124,13 +115,18 @@ ATHK_HD void cons2prim_mhd(const EosParams &eos, Real u[5], Real bc1, Real bc2, 
 // eos/adiabatic_hydro.cpp SoundSpeed ; eos/adiabatic_mhd.cpp:149-156 FastMagnetosonicSpeed
 ATHK_HD Real sound_speed(const EosParams &eos, Real d, Real p) { return sqrt(eos.gamma * p / d); }
 
-ATHK_HD Real fast_speed(const EosParams &eos, Real d, Real p, Real by, Real bz, Real bx) {
+template <class M>
+ATHK_HD Real fast_speed_m(M &m, const EosParams &eos, Real d, Real p, Real by, Real bz, Real bx) {
   Real asq = eos.gamma * p;
   Real vaxsq = bx * bx;
   Real ct2 = (by * by + bz * bz);
   Real qsq = vaxsq + ct2 + asq;
   Real tmp = vaxsq + ct2 - asq;
-  return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
+  return m.sqrt(m.div(0.5 * (qsq + m.sqrt(tmp * tmp + 4.0 * asq * ct2)), d));
+}
+ATHK_HD Real fast_speed(const EosParams &eos, Real d, Real p, Real by, Real bz, Real bx) {
+  MathIEEE m;
+  return fast_speed_m(m, eos, d, p, by, bz, bx);
 }
 
 //----------------------------------------------------------------------------------------
@@ -139,11 +135,11 @@ ATHK_HD Real fast_speed(const EosParams &eos, Real d, Real p, Real by, Real bz, 
 // The reference evaluates 2*dw2/(dwl+dwr) unconditionally and then overwrites it with 0 when
 // dw2 <= 0; skipping the division in that case gives the same bits and keeps 0/0 (uniform
 // regions) off the FP64 division slow path.  !(dw2 <= 0) keeps NaN inputs on the division.
+template <class M>
+ATHK_HD Real vl_slope_m(M &m, Real dwl, Real dwr) { return m.vl(dwl * dwr, dwl, dwr); }
 ATHK_HD Real vl_slope(Real dwl, Real dwr) {
-  Real dw2 = dwl * dwr;
-  Real dwm = 0.0;
-  if (!(dw2 <= 0.0)) dwm = 2.0 * dw2 / (dwl + dwr);
-  return dwm;
+  MathIEEE m;
+  return vl_slope_m(m, dwl, dwr);
 }
 
 //----------------------------------------------------------------------------------------
@@ -232,21 +228,27 @@ ATHK_HD void ppm_cell(Real q_im2, Real q_im1, Real q, Real q_ip1, Real q_ip2, Re
 
 //----------------------------------------------------------------------------------------
 // Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
-ATHK_HD Real ct_weight(Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
-  Real v_over_c = fdiv((1024.0) * dt * dflx, (dx * (rhol + rhor)));
+template <class M>
+ATHK_HD Real ct_weight_m(M &m, Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
+  Real v_over_c = m.fdiv((1024.0) * dt * dflx, (dx * (rhol + rhor)));
   Real tmp_min = min_std(0.5, v_over_c);
   return 0.5 + max_std(-0.5, tmp_min);
+}
+ATHK_HD Real ct_weight(Real dflx, Real rhol, Real rhor, Real dx, Real dt) {
+  MathIEEE m;
+  return ct_weight_m(m, dflx, rhol, rhor, dx, dt);
 }
 
 //----------------------------------------------------------------------------------------
 // HLLC (hydro/rsolvers/hydro/hllc.cpp:53-175).  wl/wr = (d, vx, vy, vz, p) with vx the
 // sweep-normal velocity; f = (mass, mom-x, mom-y, mom-z, energy) in the same rotated frame.
-ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+template <class M>
+ATHK_HD void hllc_flux_m(M &m, const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
   const Real gamma = eos.gamma;
   const Real igm1 = 1.0 / eos.gm1;
 
-  Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
-  Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+  Real cl = m.sqrt(m.div(eos.gamma * wl[IPR], wl[IDN]));
+  Real cr = m.sqrt(m.div(eos.gamma * wr[IPR], wr[IDN]));
   Real el = wl[IPR] * igm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
   Real er = wr[IPR] * igm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
   Real rhoa = .5 * (wl[IDN] + wr[IDN]);
@@ -254,10 +256,11 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
   Real pmid = .5 * (wl[IPR] + wr[IPR] + (wl[IVX] - wr[IVX]) * rhoa * ca);
   // umid, rhol, rhor are computed by the reference but never reach the flux (PVRS leftovers)
 
-  Real ql = (pmid <= wl[IPR]) ? 1.0
-            : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wl[IPR] - 1.0));
-  Real qr = (pmid <= wr[IPR]) ? 1.0
-            : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / wr[IPR] - 1.0));
+  // ((gamma + 1) / (2 * gamma) is evaluated at run time by the reference too; one division, hoisted)
+  const Real gfac = (gamma + 1) / (2 * gamma);
+  Real ql = 1.0, qr = 1.0;
+  if (!(pmid <= wl[IPR])) ql = m.sqrt(1.0 + gfac * (m.div(pmid, wl[IPR]) - 1.0));
+  if (!(pmid <= wr[IPR])) qr = m.sqrt(1.0 + gfac * (m.div(pmid, wr[IPR]) - 1.0));
 
   Real al = wl[IVX] - cl * ql;
   Real ar = wr[IVX] + cr * qr;
@@ -274,8 +277,8 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
   Real ml = wl[IDN] * vxl;
   Real mr = -(wr[IDN] * vxr);
 
-  Real am = fdiv((tl - tr), (ml + mr));
-  Real cp = (ml * tr + mr * tl) / (ml + mr);
+  Real am = m.fdiv((tl - tr), (ml + mr));
+  Real cp = m.div((ml * tr + mr * tl), (ml + mr));
   cp = cp > 0.0 ? cp : 0.0;
 
   vxl = wl[IVX] - bm;
@@ -295,13 +298,13 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
 
   Real sl, sr, sm;
   if (am >= 0.0) {
-    sl = fdiv(am, (am - bm));
+    sl = m.fdiv(am, (am - bm));
     sr = 0.0;
-    sm = -bm / (am - bm);
+    sm = m.div(-bm, (am - bm));
   } else {
     sl = 0.0;
-    sr = fdiv(-am, (bp - am));
-    sm = bp / (bp - am);
+    sr = m.fdiv(-am, (bp - am));
+    sm = m.div(bp, (bp - am));
   }
 
   f[IDN] = sl * fl[IDN] + sr * fr[IDN];
@@ -311,6 +314,11 @@ ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5],
   f[IEN] = sl * fl[IEN] + sr * fr[IEN] + sm * cp * am;
 }
 
+ATHK_HD void hllc_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  MathIEEE m;
+  hllc_flux_m(m, eos, wl, wr, f);
+}
+
 //----------------------------------------------------------------------------------------
 // HLLD (hydro/rsolvers/mhd/hlld.cpp:56-365).  wl/wr = (d, vx, vy, vz, p, by, bz) in the sweep
 // frame, bxi = normal face field.  f = (mass, mx, my, mz, E, by-flux, bz-flux).
@@ -318,8 +326,9 @@ struct Cons7 {
   Real d, mx, my, mz, e, by, bz;
 };
 
-ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
-                       Real f[7]) {
+template <class M>
+ATHK_HD void hlld_flux_m(M &m, const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                         Real f[7]) {
   const Real SMALL_NUMBER = 1.0e-4;
   const Real igm1 = eos.igm1;
   Real spd[5];
@@ -344,8 +353,8 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   ur.bz = wr[IBZ];
 
   // outer wave speeds, Miyoshi & Kusano eq. 67
-  Real cfl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
-  Real cfr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  Real cfl = fast_speed_m(m, eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cfr = fast_speed_m(m, eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
   spd[0] = min_std(wl[IVX] - cfl, wr[IVX] - cfr);
   spd[4] = max_std(wl[IVX] + cfl, wr[IVX] + cfr);
 
@@ -356,23 +365,23 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   Real sdr = spd[4] - wr[IVX];
 
   // S_M, eq. 38
-  spd[2] = fdiv((sdr * ur.mx - sdl * ul.mx + (ptl - ptr)), (sdr * ur.d - sdl * ul.d));
+  spd[2] = m.fdiv((sdr * ur.mx - sdl * ul.mx + (ptl - ptr)), (sdr * ur.d - sdl * ul.d));
 
   Real sdml = spd[0] - spd[2];
   Real sdmr = spd[4] - spd[2];
-  Real sdml_inv = 1.0 / sdml;
-  Real sdmr_inv = 1.0 / sdmr;
+  Real sdml_inv = m.rcp(sdml);
+  Real sdmr_inv = m.rcp(sdmr);
   // eq. 43
   ulst.d = ul.d * sdl * sdml_inv;
   urst.d = ur.d * sdr * sdmr_inv;
-  Real ulst_d_inv = 1.0 / ulst.d;
-  Real urst_d_inv = 1.0 / urst.d;
-  Real sqrtdl = sqrt(ulst.d);
-  Real sqrtdr = sqrt(urst.d);
+  Real ulst_d_inv = m.rcp(ulst.d);
+  Real urst_d_inv = m.rcp(urst.d);
+  Real sqrtdl = m.sqrt(ulst.d);
+  Real sqrtdr = m.sqrt(urst.d);
 
   // eq. 51
-  spd[1] = spd[2] - fabs(bxi) / sqrtdl;
-  spd[3] = spd[2] + fabs(bxi) / sqrtdr;
+  spd[1] = spd[2] - m.fdiv(fabs(bxi), sqrtdl);   // (a field-free normal direction is common: exact 0 numerator)
+  spd[3] = spd[2] + m.fdiv(fabs(bxi), sqrtdr);
 
   // eq. 41
   Real ptstl = ptl + ul.d * sdl * (spd[2] - wl[IVX]);
@@ -387,10 +396,10 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     ulst.by = ul.by;
     ulst.bz = ul.bz;
   } else {
-    Real tmp = fdiv(bxi * (sdl - sdml), (ul.d * sdl * sdml - bxsq));
+    Real tmp = m.fdiv(bxi * (sdl - sdml), (ul.d * sdl * sdml - bxsq));
     ulst.my = ulst.d * (wl[IVY] - ul.by * tmp);
     ulst.mz = ulst.d * (wl[IVZ] - ul.bz * tmp);
-    tmp = (ul.d * sqr(sdl) - bxsq) / (ul.d * sdl * sdml - bxsq);
+    tmp = m.div((ul.d * sqr(sdl) - bxsq), (ul.d * sdl * sdml - bxsq));
     ulst.by = ul.by * tmp;
     ulst.bz = ul.bz * tmp;
   }
@@ -404,16 +413,16 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
     urst.by = ur.by;
     urst.bz = ur.bz;
   } else {
-    Real tmp = fdiv(bxi * (sdr - sdmr), (ur.d * sdr * sdmr - bxsq));
+    Real tmp = m.fdiv(bxi * (sdr - sdmr), (ur.d * sdr * sdmr - bxsq));
     urst.my = urst.d * (wr[IVY] - ur.by * tmp);
     urst.mz = urst.d * (wr[IVZ] - ur.bz * tmp);
-    tmp = (ur.d * sqr(sdr) - bxsq) / (ur.d * sdr * sdmr - bxsq);
+    tmp = m.div((ur.d * sqr(sdr) - bxsq), (ur.d * sdr * sdmr - bxsq));
     urst.by = ur.by * tmp;
     urst.bz = ur.bz * tmp;
   }
 
   // double-star states, eqs. 59-63
-  Real invsumd = 1.0 / (sqrtdl + sqrtdr);
+  Real invsumd = m.rcp(sqrtdl + sqrtdr);
   Real bxsig = (bxi > 0.0 ? 1.0 : -1.0);
 
   uldst.d = ulst.d;
@@ -439,7 +448,7 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
                    bxsig * sqrtdl * sqrtdr * ((urst.mz * urst_d_inv) - (ulst.mz * ulst_d_inv)));
   uldst.bz = urdst.bz = tmp;
 
-  const Real vbdst = spd[2] * bxi + fdiv((uldst.my * uldst.by + uldst.mz * uldst.bz), uldst.d);
+  const Real vbdst = spd[2] * bxi + m.fdiv((uldst.my * uldst.by + uldst.mz * uldst.bz), uldst.d);
 
   // Flux of the region the face lies in (hlld.cpp:323-365): F_L or F_R plus the jump terms
   // S*(U_a - U_b) across the waves between that side and the face.  The reference evaluates
@@ -500,6 +509,12 @@ ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7],
   ATHK_HLLD_PICK(by, f[IBY])
   ATHK_HLLD_PICK(bz, f[IBZ])
 #undef ATHK_HLLD_PICK
+}
+
+ATHK_HD void hlld_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                       Real f[7]) {
+  MathIEEE m;
+  hlld_flux_m(m, eos, wl, wr, bxi, f);
 }
 
 }  // namespace athk

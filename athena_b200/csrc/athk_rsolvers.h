@@ -579,5 +579,20 @@ ATHK_HD void mhd_riemann(const EosParams &eos, const Real wl[7], const Real wr[7
   else hlld_flux(eos, wl, wr, bxi, f);
 }
 
+// Math-policy forms (athk_math.h): the default solvers HLLC / HLLD issue their divisions and square
+// roots through M; the alternative solvers keep the compiler's operations.
+template <int RS, class M>
+ATHK_HD void hydro_riemann_m(M &m, const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  if (RS == RS_HLLC) hllc_flux_m(m, eos, wl, wr, f);
+  else hydro_riemann<RS>(eos, wl, wr, f);
+}
+
+template <int RS, class M>
+ATHK_HD void mhd_riemann_m(M &m, const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                           Real f[7]) {
+  if (RS == RS_HLLD) hlld_flux_m(m, eos, wl, wr, bxi, f);
+  else mhd_riemann<RS>(eos, wl, wr, bxi, f);
+}
+
 }  // namespace athk
 #endif  // ATHK_RSOLVERS_H_

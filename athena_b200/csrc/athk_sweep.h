@@ -65,22 +65,46 @@ ATHK_HD void load_q(const SweepArgs &a, int blk, idx_t c, Real q[7]) {
   }
 }
 
+// Math policy of the fused sweeps (athk_math.h): HLLC / HLLD faces run the straight-line Newton
+// sequences (MathSL) and fall back to the compiler's operations for a face whose operands left
+// their domain; body(m) must be safe to run twice (it only computes and stores).
+#ifndef ATHK_SL_MATH
+#define ATHK_SL_MATH 1
+#endif
+template <int RS, class F>
+ATHK_HD void with_math(F &&body) {
+#if ATHK_SL_MATH && defined(__CUDA_ARCH__)
+  if (RS == RS_HLLC || RS == RS_HLLD) {
+    MathSL m;
+    body(m);
+    if (!m.ok()) {
+      MathIEEE mi;
+      body(mi);
+    }
+    return;
+  }
+#endif
+  MathIEEE mi;
+  body(mi);
+}
+
 // Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
-template <int DIR, bool MHD, int RS>
-ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
-                        const Real wr[7], const Real bxi, Real f[7], bool store) {
+// (dxw = dxf[DIR] of the face's upper cell, loaded by the caller: the marching kernels fetch it
+//  before they wait for their asynchronous copies)
+template <int DIR, bool MHD, int RS, class M>
+ATHK_HD void solve_face_dx(M &m, const SweepArgs &a, int blk, idx_t c, Real dxw, const Real wl[7],
+                           const Real wr[7], const Real bxi, Real f[7], bool store) {
   const Grid &g = a.g;
   if (MHD) {
-    mhd_riemann<RS>(a.eos, wl, wr, bxi, f);
+    mhd_riemann_m<RS>(m, a.eos, wl, wr, bxi, f);
     if (store) {
       Real *eb = a.ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
       eb[0] = -f[IBY];
       eb[g.sn] = f[IBZ];
-      const Real dxw = a.geo.dxf[DIR][blk * a.geo.PG + n_dir];
-      a.wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight(f[IDN], wl[IDN], wr[IDN], dxw, a.dt);
+      a.wct[((idx_t)blk * 3 + DIR) * g.sn + c] = ct_weight_m(m, f[IDN], wl[IDN], wr[IDN], dxw, a.dt);
     }
   } else {
-    hydro_riemann<RS>(a.eos, wl, wr, f);
+    hydro_riemann_m<RS>(m, a.eos, wl, wr, f);
   }
   if (store && a.mf[DIR]) a.mf[DIR][(idx_t)blk * a.mf_bstride + c] = f[IDN];
   if (store && a.flx[DIR]) {
@@ -92,12 +116,23 @@ ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const R
     fb[(idx_t)IEN * g.sn] = f[IEN];
   }
 }
+template <int DIR, bool MHD, int RS, class M>
+ATHK_HD void solve_face_m(M &m, const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
+                          const Real wr[7], const Real bxi, Real f[7], bool store) {
+  const Real dxw = (MHD && store) ? a.geo.dxf[DIR][blk * a.geo.PG + n_dir] : 0.0;
+  solve_face_dx<DIR, MHD, RS>(m, a, blk, c, dxw, wl, wr, bxi, f, store);
+}
+template <int DIR, bool MHD, int RS>
+ATHK_HD void solve_face(const SweepArgs &a, int blk, idx_t c, int n_dir, const Real wl[7],
+                        const Real wr[7], const Real bxi, Real f[7], bool store) {
+  with_math<RS>([&](auto &m) { solve_face_m<DIR, MHD, RS>(m, a, blk, c, n_dir, wl, wr, bxi, f, store); });
+}
 
 // PLM (or donor cell) of one cell from its two neighbours: left state of the upper face and
 // right state of the lower face (plm.cpp:104-112,149-154 / dc.cpp)
-template <int ORDER, bool MHD>
-ATHK_HD void recon_cell(const Real qm[7], const Real q0[7], const Real qp[7], Real cp, Real cm,
-                        Real wl_up[7], Real wr_lo[7]) {
+template <int ORDER, bool MHD, class M>
+ATHK_HD void recon_cell_m(M &m, const Real qm[7], const Real q0[7], const Real qp[7], Real cp, Real cm,
+                          Real wl_up[7], Real wr_lo[7]) {
   const int NW = MHD ? 7 : 5;
 #pragma unroll
   for (int n = 0; n < NW; ++n) {
@@ -105,11 +140,17 @@ ATHK_HD void recon_cell(const Real qm[7], const Real q0[7], const Real qp[7], Re
       wl_up[n] = q0[n];
       wr_lo[n] = q0[n];
     } else {
-      const Real dwm = vl_slope(q0[n] - qm[n], qp[n] - q0[n]);
+      const Real dwm = vl_slope_m(m, q0[n] - qm[n], qp[n] - q0[n]);
       wl_up[n] = q0[n] + cp * dwm;
       wr_lo[n] = q0[n] - cm * dwm;
     }
   }
+}
+template <int ORDER, bool MHD>
+ATHK_HD void recon_cell(const Real qm[7], const Real q0[7], const Real qp[7], Real cp, Real cm,
+                        Real wl_up[7], Real wr_lo[7]) {
+  MathIEEE m;
+  recon_cell_m<ORDER, MHD>(m, qm, q0, qp, cp, cm, wl_up, wr_lo);
 }
 
 // WeightedAve + AddFluxDivergence of ONE variable of one active cell (time_integrator.cpp:
@@ -133,7 +174,29 @@ ATHK_HD void integrate_var(const HydroIntegrate &h, idx_t o, Real dsum, Real vol
     }
     if (h.delta != 0.0) h.u1_out[o] = u1n;
   }
-  r -= h.wght * dsum / vol;                         // AddFluxDivergence
+  r -= fdiv(h.wght * dsum, vol);                    // AddFluxDivergence (0 / vol == 0 * vol)
+  h.u_out[o] = r;
+}
+
+// the same with the register values already loaded (un = h.u[o] where the stage reads it, u1n =
+// h.u1[o] likewise) and the division issued through a math policy
+template <class M>
+ATHK_HD void integrate_var_m(M &m, const HydroIntegrate &h, idx_t o, Real dsum, Real vol, Real un, Real u1n) {
+  if (h.delta != 0.0) u1n += h.delta * un;
+  Real r;
+  if (h.swap) {
+    r = u1n;
+  } else {
+    switch (h.wa_mode) {
+      case 1: r = un; r += h.g2 * u1n; break;
+      case 3: r = h.g2 * u1n; break;
+      case 5: r = h.g1 * un + h.g2 * u1n; break;
+      case 6: r = un; r *= h.g1; break;
+      default: r = un; break;
+    }
+    if (h.delta != 0.0) h.u1_out[o] = u1n;
+  }
+  r -= m.fdiv(h.wght * dsum, vol);   // (static regions: the divergence is exactly 0)
   h.u_out[o] = r;
 }
 
@@ -161,9 +224,9 @@ struct GlobalStencil {
   ATHK_HD Real bx() const { return MHD ? a.b[((idx_t)blk * 3 + DIR) * a.g.sn + c] : 0.0; }
 };
 
-template <int DIR, int ORDER, bool MHD, int RS, class ST>
-ATHK_HD void face_compute_from(const SweepArgs &a, int blk, idx_t c, int n_dir, const ST &st, Real f[7],
-                               bool store) {
+template <int DIR, int ORDER, bool MHD, int RS, class ST, class M>
+ATHK_HD void face_compute_from_m(M &m, const SweepArgs &a, int blk, idx_t c, int n_dir, const ST &st, Real f[7],
+                                 bool store) {
   const int NW = MHD ? 7 : 5;
   Real wl[7], wr[7];
   if (ORDER == 3) {
@@ -198,13 +261,18 @@ ATHK_HD void face_compute_from(const SweepArgs &a, int blk, idx_t c, int n_dir, 
     const Real *cpv = a.geo.cp[DIR] + blk * a.geo.PG;
     const Real *cmv = a.geo.cm[DIR] + blk * a.geo.PG;
     Real t0[7], t1[7];
-    recon_cell<ORDER, MHD>(q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
-    recon_cell<ORDER, MHD>(q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
+    recon_cell_m<ORDER, MHD>(m, q0, q1, q2, cpv[n_dir - 1], cmv[n_dir - 1], wl, t0);   // cell below
+    recon_cell_m<ORDER, MHD>(m, q1, q2, q3, cpv[n_dir], cmv[n_dir], t1, wr);           // cell above
   } else {
     st.cell(-1, wl);
     st.cell(0, wr);
   }
-  solve_face<DIR, MHD, RS>(a, blk, c, n_dir, wl, wr, st.bx(), f, store);
+  solve_face_m<DIR, MHD, RS>(m, a, blk, c, n_dir, wl, wr, st.bx(), f, store);
+}
+template <int DIR, int ORDER, bool MHD, int RS, class ST>
+ATHK_HD void face_compute_from(const SweepArgs &a, int blk, idx_t c, int n_dir, const ST &st, Real f[7],
+                               bool store) {
+  with_math<RS>([&](auto &m) { face_compute_from_m<DIR, ORDER, MHD, RS>(m, a, blk, c, n_dir, st, f, store); });
 }
 
 template <int DIR, int ORDER, bool MHD, int RS>
