@@ -85,6 +85,46 @@ static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r
   return launch_points_occ<ATHK_KP_MINB>(st, nb, r, f);
 }
 
+// The same launch shape for a functor whose run() returns a per-point value to be min-reduced per
+// MeshBlock (Hydro::NewBlockTimeStep folded into W(U)): warp shuffles + shared memory, then ONE
+// atomicMin per CTA on out[blk] (positive doubles order like their bit patterns; min is exact and
+// order independent).  No thread leaves before the reduction.
+template <class F, int MINB>
+__global__ void __launch_bounds__(ATHK_KP_THREADS, MINB)
+k_points_min(const F f, double *out, const int kl, const int jl, const int nj, const int il, const int ni,
+             const unsigned ni_magic) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 1.0e308;
+  if (t < (unsigned)(nj * ni)) {
+    const unsigned j = (ni == 1) ? t : __umulhi(t, ni_magic);
+    const unsigned i = t - j * (unsigned)ni;
+    m = f.run((int)blockIdx.z, kl + (int)blockIdx.y, jl + (int)j, il + (int)i);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (v < m) ? v : m;
+  }
+  __shared__ double sm[ATHK_KP_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < ATHK_KP_THREADS / 32; ++w) m = (sm[w] < m) ? sm[w] : m;
+    if (m < 1.0e300 && m < out[blockIdx.z])
+      atomicMin((unsigned long long *)&out[blockIdx.z], (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+template <int MINB, class F>
+static inline cudaError_t launch_points_min(cudaStream_t st, int nb, const Range3 &r, const F &f, double *out) {
+  const int threads = ATHK_KP_THREADS;
+  const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
+  if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((nj * ni + threads - 1) / threads), (unsigned)nk, (unsigned)nb);
+  k_points_min<F, MINB><<<grid, threads, 0, st>>>(f, out, r.kl, r.jl, nj, r.il, ni, magic_u32(ni));
+  return cudaGetLastError();
+}
+
 // Points of an outer box that are NOT in an inner box (ghost zones around the active zone, the
 // boundary surface of the edge box): six disjoint slabs, flattened into one index so that only
 // the shell is launched -- a 64^3 block has 17 % of its cells in the ghost shell and 9 % of its
@@ -204,6 +244,10 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
 template <int MINB, class F>
 static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range3 &r, const F &f) {
   return launch_points(st, nb, r, f);
+}
+template <int MINB, class F>
+static inline cudaError_t launch_points_min(cudaStream_t st, int nb, const Range3 &r, const F &f, double *) {
+  return launch_points(st, nb, r, f);   // operator() folds cell by cell
 }
 template <class F>
 static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &outer, const Range3 &, const F &f) {

@@ -105,14 +105,21 @@ struct Cons2PrimPoint {
 #endif
   }
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    const Real dtc = run(blk, k, j, i);
+    if (dt_out != nullptr && dtc < 1.0e300) fold_dt(blk, dtc);
+  }
+  // W(U) of one cell; returns the cell's time-step bound when the fold is on (else a huge number).
+  // The launcher reduces it per CTA (k_points_min) or operator() folds it cell by cell.
+  ATHK_HD Real run(int blk, int k, int j, int i) const {
+    const Real none = 1.0e308;
     // range: interior plus ghost sides with a neighbour (time_integrator.cpp:2206-2212)
     const int *nb = nbr + blk * 27;
-    if (i < g.is && nb[nbr_slot(-1, 0, 0)] == -1) return;
-    if (i > g.ie && nb[nbr_slot(1, 0, 0)] == -1) return;
-    if (j < g.js && nb[nbr_slot(0, -1, 0)] == -1) return;
-    if (j > g.je && nb[nbr_slot(0, 1, 0)] == -1) return;
-    if (k < g.ks && nb[nbr_slot(0, 0, -1)] == -1) return;
-    if (k > g.ke && nb[nbr_slot(0, 0, 1)] == -1) return;
+    if (i < g.is && nb[nbr_slot(-1, 0, 0)] == -1) return none;
+    if (i > g.ie && nb[nbr_slot(1, 0, 0)] == -1) return none;
+    if (j < g.js && nb[nbr_slot(0, -1, 0)] == -1) return none;
+    if (j > g.je && nb[nbr_slot(0, 1, 0)] == -1) return none;
+    if (k < g.ks && nb[nbr_slot(0, 0, -1)] == -1) return none;
+    if (k > g.ke && nb[nbr_slot(0, 0, 1)] == -1) return none;
     const idx_t c = gidx(g, k, j, i);
     Real *ub = u + (idx_t)blk * 5 * g.sn + c;
     Real *wb = w + (idx_t)blk * 5 * g.sn + c;
@@ -146,8 +153,12 @@ struct Cons2PrimPoint {
       if (sn != s0) s[o] = sn;
       r[o] = sn / uc[IDN];
     }
+    Real dtcell = none;
     if (dt_out != nullptr && i >= g.is && i <= g.ie && j >= g.js && j <= g.je && k >= g.ks &&
         k <= g.ke) {
+      // (three independent sqrt / sqrt / divide chains: issued straight-line they overlap, see
+      //  athk_math.h; min() folding is idempotent, so a flagged cell is simply redone)
+      with_math<RS_HLLD>([&](auto &m) {
       Real dt1 = geo.dxf[0][blk * geo.PG + i], dt2 = geo.dxf[1][blk * geo.PG + j],
            dt3 = geo.dxf[2][blk * geo.PG + k];
       if (MHD) {
@@ -155,19 +166,21 @@ struct Cons2PrimPoint {
         const Real b1 = 0.5 * bb[0] + 0.5 * bb[1], b2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj],
                    b3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
         Real bx = b1 + fabs(bb[0] - b1);
-        dt1 /= max_std(0.0, (fabs(wc[IVX]) + fast_speed(eos, wc[IDN], wc[IPR], b2, b3, bx)));
+        dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b2, b3, bx))));
         bx = b2 + fabs(bb[g.sn] - b2);
-        dt2 /= max_std(0.0, (fabs(wc[IVY]) + fast_speed(eos, wc[IDN], wc[IPR], b3, b1, bx)));
+        dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b3, b1, bx))));
         bx = b3 + fabs(bb[2 * g.sn] - b3);
-        dt3 /= max_std(0.0, (fabs(wc[IVZ]) + fast_speed(eos, wc[IDN], wc[IPR], b1, b2, bx)));
+        dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b1, b2, bx))));
       } else {
-        const Real cs = sound_speed(eos, wc[IDN], wc[IPR]);
-        dt1 /= max_std(0.0, (fabs(wc[IVX]) + cs));
-        dt2 /= max_std(0.0, (fabs(wc[IVY]) + cs));
-        dt3 /= max_std(0.0, (fabs(wc[IVZ]) + cs));
+        const Real cs = m.sqrt(m.div(eos.gamma * wc[IPR], wc[IDN]));
+        dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + cs)));
+        dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + cs)));
+        dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + cs)));
       }
-      fold_dt(blk, min_std(min_std(dt1, dt2), dt3));
+      dtcell = min_std(min_std(dt1, dt2), dt3);
+      });
     }
+    return dtcell;
   }
 };
 

@@ -594,5 +594,29 @@ ATHK_HD void mhd_riemann_m(M &m, const EosParams &eos, const Real wl[7], const R
   else mhd_riemann<RS>(eos, wl, wr, bxi, f);
 }
 
+// Math policy of the fused sweeps (athk_math.h): HLLC / HLLD faces run the straight-line Newton
+// sequences (MathSL) and fall back to the compiler's operations for a face whose operands left
+// their domain; body(m) must be safe to run twice (it only computes and stores).
+#ifndef ATHK_SL_MATH
+#define ATHK_SL_MATH 1
+#endif
+template <int RS, class F>
+ATHK_HD void with_math(F &&body) {
+#if ATHK_SL_MATH && defined(__CUDA_ARCH__)
+  if (RS == RS_HLLC || RS == RS_HLLD) {
+    MathSL m;
+    body(m);
+    if (!m.ok()) {
+      MathIEEE mi;
+      body(mi);
+    }
+    return;
+  }
+#endif
+  MathIEEE mi;
+  body(mi);
+}
+
+// Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
 }  // namespace athk
 #endif  // ATHK_RSOLVERS_H_

@@ -65,30 +65,6 @@ ATHK_HD void load_q(const SweepArgs &a, int blk, idx_t c, Real q[7]) {
   }
 }
 
-// Math policy of the fused sweeps (athk_math.h): HLLC / HLLD faces run the straight-line Newton
-// sequences (MathSL) and fall back to the compiler's operations for a face whose operands left
-// their domain; body(m) must be safe to run twice (it only computes and stores).
-#ifndef ATHK_SL_MATH
-#define ATHK_SL_MATH 1
-#endif
-template <int RS, class F>
-ATHK_HD void with_math(F &&body) {
-#if ATHK_SL_MATH && defined(__CUDA_ARCH__)
-  if (RS == RS_HLLC || RS == RS_HLLD) {
-    MathSL m;
-    body(m);
-    if (!m.ok()) {
-      MathIEEE mi;
-      body(mi);
-    }
-    return;
-  }
-#endif
-  MathIEEE mi;
-  body(mi);
-}
-
-// Riemann solve at one face + the per-face outputs (EMFs, CT weight, optional flux store)
 // (dxw = dxf[DIR] of the face's upper cell, loaded by the caller: the marching kernels fetch it
 //  before they wait for their asynchronous copies)
 template <int DIR, bool MHD, int RS, class M>

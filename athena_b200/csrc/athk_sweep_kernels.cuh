@@ -677,16 +677,21 @@ k_sweep_x1_cells(const SweepX1<ORDER, MHD, RS> f, const int kl, const int jl, co
 }
 
 //========================================================================================
-// x1 sweep, row-stream form (round 2; default).  Same lane-per-cell stream and warp shuffles as
+// x1 sweep, row-stream form (round 2; default).  Lane-per-cell stream and warp shuffles like
 // k_sweep_x1_cells, but built for 12 resident warps per SM (160 registers, no spills):
 //   * every WARP owns ATHK_X1R_NJW consecutive rows of one (k, MeshBlock) plane and walks its
-//     stream of cells in passes of 30; the rows it needs are copied into a warp-private ring in
-//     shared memory with 16-byte cp.async one pass ahead, so stencils are shared-memory reads and
-//     the kernel has no CTA-wide barrier (warps drift freely, as in k_sweep_march);
-//   * what the update of a cell reads at the END of its pass -- the x2/x3 flux-divergence terms
-//     and the register it averages -- is requested with cp.async at the START of the pass into the
-//     lane's own shared-memory slot: no registers held across the Riemann solve, no exposed
-//     latency;
+//     stream of cells in passes of 32.  The rows it needs are fetched into a warp-private ring in
+//     shared memory by TMA bulk copies (cp.async.bulk, one per variable and row, issued by lane 0
+//     one pass ahead; completion on one mbarrier per ring slot), so stencils are shared-memory
+//     reads, no lane spends issue slots on row loads, and the kernel has no CTA-wide barrier
+//     (warps drift freely, as in k_sweep_march);
+//   * lane L reconstructs cell t, solves the face below it with the left state of lane L-1 and
+//     finishes cell t-1 with that face's flux and the flux of lane L-1; lane 0 picks both up from
+//     where lane 31 of the previous pass left them -- 32 faces and 32 cells per pass, no face
+//     solved twice;
+//   * what the update reads at the END of the pass -- the x2/x3 flux-divergence terms and the
+//     register it averages -- is requested with cp.async at the START of the pass into the lane's
+//     own shared-memory slot: no registers held across the Riemann solve, no exposed latency;
 //   * divisions of reconstruction, Riemann solve and flux divergence go through the math policy.
 #ifndef ATHK_X1R_NJW
 #define ATHK_X1R_NJW 11
@@ -697,17 +702,41 @@ k_sweep_x1_cells(const SweepX1<ORDER, MHD, RS> f, const int kl, const int jl, co
 #ifndef ATHK_X1_ROWS
 #define ATHK_X1_ROWS 1
 #endif
+#ifndef ATHK_X1R_TMA
+#define ATHK_X1R_TMA 1
+#endif
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (bytes: multiple of 16)
+__device__ __forceinline__ void tma_bulk_g2s(void *smem, const void *gmem, unsigned bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+               "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
 struct X1RowsGeom {
   int kl, nk, jl, nj, icl, ncr;   // planes, rows, first stream cell (il - 1), cells per row
   unsigned ncr_magic;
   int njw, ngroups;               // rows per warp, warps per plane
-  int nrs_mask;                   // ring rows - 1 (ring size is a power of two)
+  int nrs_mask, nrs_shift;        // ring rows: a power of two
   int nwarps;                     // warps in the launch
   int wstride;                    // doubles of shared memory per warp
 };
@@ -715,7 +744,7 @@ struct X1RowsGeom {
 template <int ORDER, bool MHD, int RS>
 __global__ void __launch_bounds__(128, ATHK_X1R_MINB)
 k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
-  constexpr int NW = MHD ? 7 : 5, NQ = MHD ? 8 : 5, NI = 15;
+  constexpr int NW = MHD ? 7 : 5, NQ = MHD ? 8 : 5;
   const SweepArgs &a = f.a;
   const Grid &g = a.g;
   const HydroIntegrate &h = a.hi;
@@ -729,15 +758,40 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
   const int j0 = q.jl + grp * q.njw;
   const int nrows = min(q.njw, q.jl + q.nj - j0);
   const int P1 = g.P1;
+  const int nrs = q.nrs_mask + 1;
   extern __shared__ __align__(16) Real smem_x1r[];
-  Real *ring = smem_x1r + (size_t)(threadIdx.x >> 5) * q.wstride;   // [nrs][NQ][P1]
-  Real *geo1 = ring + (q.nrs_mask + 1) * NQ * P1;                    // [3][P1]: dx1f, cp, cm
-  Real *slot = geo1 + 3 * P1 + lane;                                 // [NI][32]
+  Real *wbase = smem_x1r + (size_t)(threadIdx.x >> 5) * q.wstride;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(wbase);   // [nrs] (nrs even)
+  Real *ring = wbase + nrs;                                          // [nrs][NQ][P1]
+  Real *geo1 = ring + nrs * NQ * P1;                                 // [3][P1]: dx1f, cp, cm
+  Real *carry = geo1 + 3 * P1;                                       // [12]: up[7], flux[5] of lane 31
+  Real *slot = carry + 12 + lane;                                    // [15][32]
   // source rows: w(0..4) (DIR = 0: no rotation), bcc(1,2), b.x1f
   const idx_t plane = (idx_t)k * g.sk;
   const Real *wsrc = a.w + (idx_t)blk * 5 * g.sn + plane;
   const Real *bcsrc = MHD ? a.bcc + ((idx_t)blk * 3 + 1) * g.sn + plane : nullptr;
   const Real *bsrc = MHD ? a.b + (idx_t)blk * 3 * g.sn + plane : nullptr;
+#if ATHK_X1R_TMA
+  if (lane == 0) {
+    for (int r = 0; r < nrs; ++r) mbar_init(&bars[r], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto load_row = [&](int r) {   // lane 0 only
+    Real *d = ring + (r & q.nrs_mask) * (NQ * P1);
+    void *bar = &bars[r & q.nrs_mask];
+    const idx_t off = (idx_t)(j0 + r) * g.sj;
+    const unsigned rb = (unsigned)P1 * 8u;
+    mbar_expect_tx(bar, rb * NQ);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) tma_bulk_g2s(d + v * P1, wsrc + (idx_t)v * g.sn + off, rb, bar);
+    if (MHD) {
+      tma_bulk_g2s(d + 5 * P1, bcsrc + off, rb, bar);
+      tma_bulk_g2s(d + 6 * P1, bcsrc + g.sn + off, rb, bar);
+      tma_bulk_g2s(d + 7 * P1, bsrc + off, rb, bar);
+    }
+  };
+#else
   const int nch = P1 >> 1;   // 16-byte chunks per row
   auto load_row = [&](int r) {
     Real *d = ring + (r & q.nrs_mask) * (NQ * P1);
@@ -753,6 +807,7 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
       }
     }
   };
+#endif
   for (int ii = lane; ii < P1; ii += 32) {
     const bool in = ii < g.nc1;
     geo1[ii] = in ? a.geo.dxf[0][blk * a.geo.PG + ii] : 1.0;
@@ -760,29 +815,39 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
     geo1[2 * P1 + ii] = in ? a.geo.cm[0][blk * a.geo.PG + ii] : 0.0;
   }
   const int L = nrows * q.ncr;              // cells in this warp's stream
-  const int npass = (L - 2 + 29) / 30;      // stride 30, two cells of overlap
+  const int npass = (L + 31) >> 5;
   auto row_hi = [&](int p) {                // last row pass p touches
-    int t = 30 * p + 31;
+    int t = 32 * p + 31;
     if (t > L - 1) t = L - 1;
     return (int)__umulhi((unsigned)t, q.ncr_magic);
   };
   int rows_issued = 0;
   {
     const int rh = row_hi(0);
+#if ATHK_X1R_TMA
+    if (lane == 0) for (int r = 0; r <= rh; ++r) load_row(r);
+    rows_issued = rh + 1;
+#else
     while (rows_issued <= rh) load_row(rows_issued++);
     cp_async_commit();
+#endif
   }
   const Real dx3 = a.geo.dxf[2][blk * a.geo.PG + k];
   const bool needs_u = (h.delta != 0.0 || !h.swap), needs_u1 = !h.u1_zero;
   const Real *ureg = needs_u ? h.u : h.u1;
   const idx_t blk5 = (idx_t)blk * 5 * g.sn;
   for (int p = 0; p < npass; ++p) {
-    __syncwarp();   // every lane is done with the rows of pass p-1 before their slots are refilled
+    __syncwarp();   // every lane is done with the rows (and the hand-over) of pass p-1
     if (p + 1 < npass) {
       const int rh = row_hi(p + 1);
+#if ATHK_X1R_TMA
+      if (lane == 0) for (int r = rows_issued; r <= rh; ++r) load_row(r);
+      if (rh >= rows_issued) rows_issued = rh + 1;
+#else
       while (rows_issued <= rh) load_row(rows_issued++);
+#endif
     }
-    const int t = 30 * p + lane;
+    const int t = 32 * p + lane;
     const bool valid = t < L;
     int row = 0, ci = 0;
     if (valid) {
@@ -791,9 +856,10 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
     }
     const int j = j0 + row, i = q.icl + ci;
     const idx_t c = plane + (idx_t)j * g.sj + i;
-    const bool cell_upd = valid && lane >= 1 && lane <= 30 && ci >= 1 && ci <= q.ncr - 2 && f.cell_active(k, j, i);
+    const bool face = valid && ci >= 1;                                     // face i: below this cell, same row
+    const bool cell_upd = face && ci >= 2 && f.cell_active(k, j, i - 1);    // this lane finishes cell i-1
     if (cell_upd) {   // what the end of the pass reads, requested now
-      const idx_t o = blk5 + c;
+      const idx_t o = blk5 + c - 1;
 #pragma unroll
       for (int v = 0; v < 5; ++v) {
         cp_async8(slot + v * 32, a.d2 + o + (idx_t)v * g.sn);
@@ -802,8 +868,12 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
       }
     }
     cp_async_commit();
+#if ATHK_X1R_TMA
+    if (valid) mbar_wait(&bars[row & q.nrs_mask], (unsigned)(row >> q.nrs_shift) & 1u);
+#else
     cp_async_wait_group<1>();
     __syncwarp();
+#endif
     const Real *rp = ring + (row & q.nrs_mask) * (NQ * P1) + i;
     Real up[7], lo[7];
 #pragma unroll
@@ -831,30 +901,44 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
         lo[IPR] = (lo[IPR] > pfl) ? lo[IPR] : pfl;
       }
     }
+    // left state of the face: the cell below, i.e. lane L-1 (lane 0: lane 31 of the previous pass)
     Real wl[7];
 #pragma unroll
-    for (int v = 0; v < NW; ++v) wl[v] = __shfl_up_sync(0xffffffffu, up[v], 1);
+    for (int v = 0; v < NW; ++v) {
+      wl[v] = __shfl_up_sync(0xffffffffu, up[v], 1);
+      if (lane == 0) wl[v] = carry[v];
+    }
     Real fl[7];
 #pragma unroll
     for (int v = 0; v < 7; ++v) fl[v] = 0.0;
-    if (valid && lane >= 1 && ci >= 1) {   // face i: between the lane below (same row) and this cell
+    if (face) {
       const Real bx = MHD ? rp[7 * P1] : 0.0;
       const Real dx1 = geo1[i];
-      // (the face of lane 31 is solved again by lane 1 of the next pass: same values, same stores)
       with_math<RS>([&](auto &m) { solve_face_dx<0, MHD, RS>(m, a, blk, c, dx1, wl, lo, bx, fl, true); });
     }
-    Real fn[5];
+    // flux of the face below cell i-1: lane L-1 (lane 0: lane 31 of the previous pass)
+    Real fb[5];
 #pragma unroll
-    for (int v = 0; v < 5; ++v) fn[v] = __shfl_down_sync(0xffffffffu, fl[v], 1);
+    for (int v = 0; v < 5; ++v) {
+      fb[v] = __shfl_up_sync(0xffffffffu, fl[v], 1);
+      if (lane == 0) fb[v] = carry[7 + v];
+    }
+    __syncwarp();   // lane 0 has read the hand-over of the previous pass
+    if (lane == 31) {
+#pragma unroll
+      for (int v = 0; v < NW; ++v) carry[v] = up[v];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) carry[7 + v] = fl[v];
+    }
     cp_async_wait_all();
     if (cell_upd) {
-      const Real dx1 = geo1[i], dx2 = a.geo.dxf[1][blk * a.geo.PG + j];
+      const Real dx1 = geo1[i - 1], dx2 = a.geo.dxf[1][blk * a.geo.PG + j];
       const Real area = dx2 * dx3, vol = dx1 * dx2 * dx3;   // Face1Area, cell volume
-      const idx_t o = blk5 + c;
+      const idx_t o = blk5 + c - 1;
       with_math<RS>([&](auto &m) {
 #pragma unroll
         for (int v = 0; v < 5; ++v) {   // DIR = 0: rotated index == variable index
-          Real d = (area * fn[v] - area * fl[v]);
+          Real d = (area * fl[v] - area * fb[v]);
           d += slot[v * 32];
           d += slot[(5 + v) * 32];
           const idx_t ov = o + (idx_t)v * g.sn;
@@ -882,11 +966,12 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
     q.ncr_magic = magic_u32(q.ncr);
     q.njw = ATHK_X1R_NJW < nj ? ATHK_X1R_NJW : nj;
     q.ngroups = (nj + q.njw - 1) / q.njw;
-    int nrs = 60 / q.ncr + 2, p2 = 2;   // rows two consecutive passes can span
-    while (p2 < nrs) p2 *= 2;
+    int nrs = 63 / q.ncr + 2, p2 = 2, sh = 1;   // rows two consecutive passes can span
+    while (p2 < nrs) { p2 *= 2; ++sh; }
     q.nrs_mask = p2 - 1;
+    q.nrs_shift = sh;
     q.nwarps = nb * nk * q.ngroups;
-    q.wstride = p2 * NQ * g.P1 + 3 * g.P1 + NI * 32;
+    q.wstride = p2 + p2 * NQ * g.P1 + 3 * g.P1 + 12 + NI * 32;   // mbarriers, ring, geometry, hand-over, lane slots
     q.wstride = (q.wstride + 1) & ~1;   // keep every warp's region 16-byte aligned
     const size_t smem = sizeof(Real) * 4 * (size_t)q.wstride;
     static size_t attr_smem = 0;   // > 48 KB of dynamic shared memory is opt-in
