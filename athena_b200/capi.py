@@ -99,6 +99,14 @@ PROTOTYPES = {
     "athk_remote_set_buffers": (C.c_int, [_P, _P, _P, _P, _P]),
     "athk_remote_pack_ghosts": (C.c_int, [_P, C.c_int]),
     "athk_remote_pack_emf": (C.c_int, [_P]),
+    "athk_p2p_alloc": (C.c_int, [_P, C.c_longlong, C.POINTER(_P), C.c_char_p]),
+    "athk_p2p_open": (C.c_int, [_P, C.c_char_p, C.POINTER(_P)]),
+    "athk_p2p_close": (C.c_int, [_P, _P]),
+    "athk_p2p_free": (C.c_int, [_P, _P]),
+    "athk_p2p_enable_peer": (C.c_int, [_P, C.c_int]),
+    "athk_remote_set_p2p": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, C.c_longlong, _P,
+                                      C.c_longlong, C.POINTER(_P), _P]),
+    "athk_p2p_timeouts": (C.c_longlong, [_P]),
 }
 
 

@@ -14,6 +14,11 @@ ATHK_EXTERN_RS(athk::RS_LLF, true)
 
 static thread_local std::string g_last_error;
 
+// peer-to-peer transport hooks (defined at the end of this file)
+int athk_p2p_before_ghost_fill(athk_ctx *c);
+int athk_p2p_before_emf_apply(athk_ctx *c);
+int athk_p2p_after_pack(athk_ctx *c, int which);
+
 #undef fail
 int athk_fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -166,6 +171,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
+  cudaFree(c->p2p.gdst); cudaFree(c->p2p.edst); cudaFree(c->p2p.peer_flags); cudaFree(c->p2p.timeouts);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -565,6 +571,7 @@ extern "C" int athk_recv_flux_correction(athk_ctx *c) {
   const Grid &g = c->g;
   const Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
   const Range3 rin = {g.ks + 1, g.ke, g.js + 1, g.je, g.is + 1, g.ie};
+  { int rcw = athk_p2p_before_emf_apply(c); if (rcw) return rcw; }
   EmfApplyPoint f = {g, c->sf, c->e, c->emfbuf, c->nbr, c->rl.erbuf, c->rl.ebase};
   LAUNCH_NAMED(c, __func__, launch_shell(c->stream, g.nb, r, rin, f));
   return ATHK_OK;
@@ -684,6 +691,7 @@ static int exchange_ghosts_mode(athk_ctx *c, int what_mask, int reg, int mode) {
   NEED_READY(c);
   if (mode == 2 && c->rl.n == 0) return ATHK_OK;
   if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "exchange_ghosts: bad register");
+  if (mode != 1) { int rcw = athk_p2p_before_ghost_fill(c); if (rcw) return rcw; }
   const Grid &g = c->g;
   const Range3 rin = {g.ks, g.ke, g.js, g.je, g.is, g.ie};   // only the ghost shell is launched
   if (what_mask & 1) {
@@ -1236,18 +1244,207 @@ extern "C" int athk_remote_pack_ghosts(athk_ctx *c, int reg) {
   NEED_READY(c);
   if (c->rl.n == 0) return ATHK_OK;
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "remote_pack_ghosts: register %d not allocated", reg);
-  if (!c->rl.gsbuf) return fail(ATHK_ERR_STATE, "remote_pack_ghosts: call athk_remote_set_buffers first");
-  RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, c->rl, c->u[reg],
+  if (!c->rl.gsbuf && !c->p2p.on) return fail(ATHK_ERR_STATE, "remote_pack_ghosts: call athk_remote_set_buffers first");
+  RemoteLinks rl = c->rl;
+  if (c->p2p.on) {   // message number gseq+1 goes straight into the receivers' buffer half (gseq+1)&1
+    c->p2p.gseq++;
+    rl.gdst = c->p2p.gdst + (c->p2p.gseq & 1) * (size_t)c->rl.n;
+  }
+  RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, rl, c->u[reg],
                        c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr};
   LAUNCH_NAMED(c, __func__, launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
+  if (c->p2p.on) return athk_p2p_after_pack(c, 0);
   return ATHK_OK;
 }
 
 extern "C" int athk_remote_pack_emf(athk_ctx *c) {
   NEED_READY(c);
   if (c->rl.n == 0 || !c->cfg.mhd) return ATHK_OK;
-  if (!c->rl.esbuf) return fail(ATHK_ERR_STATE, "remote_pack_emf: call athk_remote_set_buffers first");
-  RemoteEmfPack f = {c->sf, c->rl, c->emfbuf};
+  if (!c->rl.esbuf && !c->p2p.on) return fail(ATHK_ERR_STATE, "remote_pack_emf: call athk_remote_set_buffers first");
+  RemoteLinks rl = c->rl;
+  if (c->p2p.on) {
+    c->p2p.eseq++;
+    rl.edst = c->p2p.edst + (c->p2p.eseq & 1) * (size_t)c->rl.n;
+  }
+  RemoteEmfPack f = {c->sf, rl, c->emfbuf};
   LAUNCH_NAMED(c, __func__, launch_links(c->stream, c->rl.n, c->max_emf_count, f));
+  if (c->p2p.on) return athk_p2p_after_pack(c, 1);
   return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+// Peer-to-peer transport (include/athk.h): allocation / mapping helpers, flag kernels
+extern "C" int athk_p2p_alloc(athk_ctx *c, long long nbytes, void **dptr, unsigned char ipc_handle[64]) {
+  if (!c || !dptr || nbytes <= 0) return fail(ATHK_ERR_ARG, "p2p_alloc: bad argument");
+#ifndef ATHK_EMULATE
+  CU(cudaSetDevice(c->cfg.device));
+  CU(cudaMalloc(dptr, (size_t)nbytes));
+  CU(cudaMemset(*dptr, 0, (size_t)nbytes));
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, *dptr));
+    memcpy(ipc_handle, &h, 64);
+  }
+  return ATHK_OK;
+#else
+  *dptr = calloc(1, (size_t)nbytes);
+  if (ipc_handle) memset(ipc_handle, 0, 64);
+  return *dptr ? ATHK_OK : fail(ATHK_ERR_CUDA, "p2p_alloc: out of memory");
+#endif
+}
+
+extern "C" int athk_p2p_open(athk_ctx *c, const unsigned char ipc_handle[64], void **dptr) {
+  if (!c || !dptr || !ipc_handle) return fail(ATHK_ERR_ARG, "p2p_open: bad argument");
+#ifndef ATHK_EMULATE
+  CU(cudaSetDevice(c->cfg.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, 64);
+  CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return ATHK_OK;
+#else
+  return fail(ATHK_ERR_STATE, "p2p_open: no inter-process mapping in the host harness");
+#endif
+}
+
+extern "C" int athk_p2p_close(athk_ctx *c, void *dptr) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+#ifndef ATHK_EMULATE
+  if (dptr) CU(cudaIpcCloseMemHandle(dptr));
+#endif
+  return ATHK_OK;
+}
+
+extern "C" int athk_p2p_free(athk_ctx *c, void *dptr) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+#ifndef ATHK_EMULATE
+  CU(cudaStreamSynchronize(c->stream));
+  if (dptr) CU(cudaFree(dptr));
+#else
+  free(dptr);
+#endif
+  return ATHK_OK;
+}
+
+extern "C" int athk_p2p_enable_peer(athk_ctx *c, int peer_device) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+#ifndef ATHK_EMULATE
+  if (peer_device == c->cfg.device) return ATHK_OK;
+  CU(cudaSetDevice(c->cfg.device));
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, c->cfg.device, peer_device));
+  if (!can) return fail(ATHK_ERR_STATE, "p2p_enable_peer: device %d cannot access device %d", c->cfg.device, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  CU(e);
+#endif
+  return ATHK_OK;
+}
+
+extern "C" long long athk_p2p_timeouts(athk_ctx *c) {
+  if (!c || !c->p2p.timeouts) return 0;
+#ifndef ATHK_EMULATE
+  unsigned long long v = 0;
+  cudaStreamSynchronize(c->stream);
+  cudaMemcpy(&v, c->p2p.timeouts, sizeof(v), cudaMemcpyDeviceToHost);
+  return (long long)v;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int athk_remote_set_p2p(athk_ctx *c, int npeers, double *const *ghost_dst, double *const *emf_dst,
+                                   double *recv_ghost, long long ghost_half, double *recv_emf, long long emf_half,
+                                   unsigned long long *const *peer_flags, unsigned long long *my_flags) {
+  if (!c) return fail(ATHK_ERR_ARG, "null context");
+  const int n = c->rl.n;
+  if (n == 0 || npeers <= 0) { c->p2p.on = false; return ATHK_OK; }
+  if (!ghost_dst || !recv_ghost || !peer_flags || !my_flags)
+    return fail(ATHK_ERR_ARG, "remote_set_p2p: null argument");
+  if (c->cfg.mhd && (!emf_dst || !recv_emf)) return fail(ATHK_ERR_ARG, "remote_set_p2p: EMF buffers missing");
+  athk_ctx::P2P &p = c->p2p;
+#ifndef ATHK_EMULATE
+  cudaFree(p.gdst); cudaFree(p.edst); cudaFree(p.peer_flags); cudaFree(p.timeouts);
+  p.gdst = p.edst = nullptr; p.peer_flags = nullptr; p.timeouts = nullptr;
+  CU(cudaMalloc((void **)&p.gdst, 2 * (size_t)n * sizeof(Real *)));
+  CU(cudaMemcpy(p.gdst, ghost_dst, 2 * (size_t)n * sizeof(Real *), cudaMemcpyHostToDevice));
+  if (emf_dst) {
+    CU(cudaMalloc((void **)&p.edst, 2 * (size_t)n * sizeof(Real *)));
+    CU(cudaMemcpy(p.edst, emf_dst, 2 * (size_t)n * sizeof(Real *), cudaMemcpyHostToDevice));
+  }
+  CU(cudaMalloc((void **)&p.peer_flags, (size_t)npeers * sizeof(unsigned long long *)));
+  CU(cudaMemcpy(p.peer_flags, peer_flags, (size_t)npeers * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
+  CU(cudaMalloc((void **)&p.timeouts, sizeof(unsigned long long)));
+  CU(cudaMemset(p.timeouts, 0, sizeof(unsigned long long)));
+#else
+  (void)peer_flags;
+#endif
+  p.npeers = npeers;
+  p.grecv = recv_ghost; p.ghalf = ghost_half;
+  p.erecv = recv_emf; p.ehalf = emf_half;
+  p.my_flags = my_flags;
+  p.gseq = p.eseq = 0;
+  p.on = true;
+  return ATHK_OK;
+}
+
+#ifndef ATHK_EMULATE
+// raise this rank's word `which` (0 ghost, 1 emf) in every peer's flag array
+__global__ void k_p2p_signal(unsigned long long *const *peer_flags, int npeers, int which, unsigned long long seq) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npeers) return;
+  __threadfence_system();   // the pack kernel's peer stores are ordered before the flag
+  *(volatile unsigned long long *)(peer_flags[p] + which) = seq;
+}
+// wait until every peer's word `which` in this rank's flag array has reached seq
+__global__ void k_p2p_wait(unsigned long long *my_flags, int npeers, int which, unsigned long long seq,
+                           unsigned long long *timeouts) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npeers) return;
+  const volatile unsigned long long *f = my_flags + 2 * p + which;
+  const long long t0 = clock64();
+  while (*f < seq) {
+    if (clock64() - t0 > 20000000000LL) {   // ~10 s: the peer is gone; report instead of hanging
+      atomicAdd(timeouts, 1ULL);
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+#endif
+
+// after the pack kernel of message number seq: tell the peers
+static int p2p_signal(athk_ctx *c, int which, unsigned long long seq) {
+#ifndef ATHK_EMULATE
+  prof_begin(c, "p2p_signal");
+  k_p2p_signal<<<(c->p2p.npeers + 31) / 32, 32, 0, c->stream>>>(c->p2p.peer_flags, c->p2p.npeers, which, seq);
+  prof_end(c);
+  CU(cudaGetLastError());
+  c->launches++;
+#endif
+  return ATHK_OK;
+}
+static int p2p_wait(athk_ctx *c, int which, unsigned long long seq) {
+#ifndef ATHK_EMULATE
+  prof_begin(c, "p2p_wait");
+  k_p2p_wait<<<(c->p2p.npeers + 31) / 32, 32, 0, c->stream>>>(c->p2p.my_flags, c->p2p.npeers, which, seq, c->p2p.timeouts);
+  prof_end(c);
+  CU(cudaGetLastError());
+  c->launches++;
+#endif
+  return ATHK_OK;
+}
+int athk_p2p_before_ghost_fill(athk_ctx *c) {
+  if (!c->p2p.on || c->rl.n == 0) return ATHK_OK;
+  c->rl.grbuf = c->p2p.grecv + (c->p2p.gseq & 1) * c->p2p.ghalf;
+  return p2p_wait(c, 0, c->p2p.gseq);
+}
+int athk_p2p_before_emf_apply(athk_ctx *c) {
+  if (!c->p2p.on || c->rl.n == 0 || !c->cfg.mhd) return ATHK_OK;
+  c->rl.erbuf = c->p2p.erecv + (c->p2p.eseq & 1) * c->p2p.ehalf;
+  return p2p_wait(c, 1, c->p2p.eseq);
+}
+int athk_p2p_after_pack(athk_ctx *c, int which) {
+  return p2p_signal(c, which, which == 0 ? c->p2p.gseq : c->p2p.eseq);
 }

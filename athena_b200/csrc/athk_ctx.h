@@ -86,6 +86,18 @@ struct athk_ctx {
   std::vector<Real> h_floors;         // per-block (dfloor, pfloor, sfloor); empty = uniform
   Real *d_floors = nullptr;
   std::vector<Real> h_geo;   // host mirror of geo_store
+  // peer-to-peer transport of the remote messages (athk_remote_set_p2p)
+  struct P2P {
+    bool on = false;
+    int npeers = 0;
+    Real **gdst = nullptr, **edst = nullptr;          // device arrays [2][nlinks] of destination pointers
+    Real *grecv = nullptr, *erecv = nullptr;          // own receive buffers (two halves)
+    idx_t ghalf = 0, ehalf = 0;
+    unsigned long long **peer_flags = nullptr;        // device array [npeers]
+    unsigned long long *my_flags = nullptr;           // [npeers][2]
+    unsigned long long gseq = 0, eseq = 0;            // messages sent so far
+    unsigned long long *timeouts = nullptr;           // device counter
+  } p2p;
 };
 
 void athk_prof_begin(athk_ctx *c, const char *name);

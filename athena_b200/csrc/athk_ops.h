@@ -565,6 +565,10 @@ struct RemoteLinks {
   const Real *grbuf;                     // ghost receive buffer
   Real *esbuf;
   const Real *erbuf;
+  // peer-to-peer transport: where each link's message goes in the RECEIVER's memory (null = pack
+  // into gsbuf / esbuf for the host framework to move)
+  Real *const *gdst;                     // [n]
+  Real *const *edst;                     // [n]
 };
 
 ATHK_HD idx_t ghost_section_off(const Grid &g, bool mhd, int nscal, int o1, int o2, int o3,
@@ -590,7 +594,7 @@ struct RemoteGhostPack {
   // (link, e): e = element index inside the link's message
   ATHK_HD void operator()(int link, idx_t e) const {
     const int o1 = rl.o1[link], o2 = rl.o2[link], o3 = rl.o3[link], blk = rl.lb[link];
-    Real *dst = rl.gsbuf + rl.gsend[link] + e;
+    Real *dst = (rl.gdst ? rl.gdst[link] : rl.gsbuf + rl.gsend[link]) + e;
     const int os = nbr_slot(o1, o2, o3);
     if (e >= rl.tab->sec[os][5]) return;
     const Slab cc = rl.tab->slab[os][0];
@@ -654,8 +658,8 @@ struct RemoteEmfPack {
     const idx_t n = (dir == 0) ? sf.n_x1() : (dir == 1 ? sf.n_x2() : sf.n_x3());
     if (e >= n) return;
     // my boundary facing the neighbour: neighbour at +1 -> my outer side
-    rl.esbuf[rl.esend[link] + e] =
-        buf[(idx_t)rl.lb[link] * sf.per_block() + sf.face_off(dir, od > 0 ? 1 : 0) + e];
+    Real *dst = rl.edst ? rl.edst[link] : rl.esbuf + rl.esend[link];
+    dst[e] = buf[(idx_t)rl.lb[link] * sf.per_block() + sf.face_off(dir, od > 0 ? 1 : 0) + e];
   }
 };
 

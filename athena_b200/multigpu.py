@@ -6,10 +6,16 @@ Mirrors the rank-crossing half of the reference's BoundaryVariable machinery
 every (block, neighbour) pair whose neighbour lives on another rank is a "remote link".  Where
 the reference posts one MPI message per link, all links towards the same peer are coalesced here
 into ONE message per peer and quantity (ghost zones of u+b; EMF surfaces), packed by a single
-kernel launch and moved with NCCL send/recv over NVLink (torch.distributed is the plumbing; gloo
-on CPU tensors for the world_size-2 tests).  There is no collective on the data path: the only
-reduction is the global min of dt (Mesh::NewTimeStep, mesh.cpp:1263).
+kernel launch.  Transport, two forms:
+  * peer-to-peer (default on GPUs): every rank's receive buffers are CUDA-IPC mapped into its
+    peers, the pack kernels store the messages straight into the receiver's memory over NVLink and
+    raise a flag; no NCCL call, no host involvement on the data path (include/athk.h,
+    athk_remote_set_p2p).  torch.distributed only carries the 64-byte IPC handles at set-up;
+  * NCCL send/recv (ATHK_P2P=0) / gloo on CPU tensors for the world_size-2 tests.
+There is no collective on the data path: the only reduction is the global min of dt
+(Mesh::NewTimeStep, mesh.cpp:1263).
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -79,6 +85,55 @@ class RemoteExchange:
         ctx.call("athk_remote_configure", n, ia(lb), ia(o1), ia(o2), ia(o3), la(gs), la(gr), la(es), la(er))
         ctx.call("athk_remote_set_buffers", self.gsbuf.data_ptr(), self.grbuf.data_ptr(),
                  self.esbuf.data_ptr(), self.erbuf.data_ptr())
+        self.p2p = False
+        if stream is not None and os.environ.get("ATHK_P2P", "1") != "0":
+            self._setup_p2p(links, gs, es, g_r, e_r)
+
+    def _setup_p2p(self, links, gs, es, g_r, e_r):
+        """Map every peer's receive buffers and flag words into this process (CUDA IPC) and tell the
+        library where each link's message goes in the receiver's memory."""
+        ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.h
+        n, peers = len(links), self.peers
+        vp = C.c_void_p
+
+        def alloc(nbytes):
+            ptr, hd = vp(), C.create_string_buffer(64)
+            ctx.call("athk_p2p_alloc", C.c_longlong(max(int(nbytes), 64)), C.byref(ptr), hd)
+            return ptr.value, hd.raw
+
+        g_ptr, g_h = alloc(2 * 8 * g_r)
+        e_ptr, e_h = alloc(2 * 8 * e_r)
+        f_ptr, f_h = alloc(2 * 8 * max(len(peers), 1))
+        self._p2p_own = (g_ptr, e_ptr, f_ptr)
+        mine = {"g": g_h, "e": e_h, "f": f_h, "g_r": int(g_r), "e_r": int(e_r), "peers": list(peers),
+                "gr0": {p: int(self.gseg[p][2]) for p in peers}, "er0": {p: int(self.eseg[p][2]) for p in peers}}
+        allinfo = [None] * self.world
+        dist.all_gather_object(allinfo, mine)
+        self._p2p_maps = []
+        peer_g, peer_e, peer_f = {}, {}, {}
+        for p in peers:
+            for key, store in (("g", peer_g), ("e", peer_e), ("f", peer_f)):
+                ptr = vp()
+                ctx.call("athk_p2p_open", allinfo[p][key], C.byref(ptr))
+                store[p] = ptr.value
+                self._p2p_maps.append(ptr.value)
+        gdst = (vp * (2 * n))()
+        edst = (vp * (2 * n))()
+        for q in range(n):
+            p = links[q][3]
+            info = allinfo[p]
+            goff = info["gr0"][self.rank] + (int(gs[q]) - self.gseg[p][0])
+            eoff = info["er0"][self.rank] + (int(es[q]) - self.eseg[p][0])
+            for par in (0, 1):
+                gdst[par * n + q] = peer_g[p] + 8 * (par * info["g_r"] + goff)
+                edst[par * n + q] = peer_e[p] + 8 * (par * info["e_r"] + eoff)
+        pflags = (vp * len(peers))()
+        for k, p in enumerate(peers):
+            pflags[k] = peer_f[p] + 16 * allinfo[p]["peers"].index(self.rank)
+        ctx.call("athk_remote_set_p2p", len(peers), gdst, edst, vp(g_ptr), C.c_longlong(int(g_r)), vp(e_ptr),
+                 C.c_longlong(int(e_r)), pflags, vp(f_ptr))
+        dist.barrier()   # every rank has mapped its peers before the first message is written
+        self.p2p = True
 
     def _ops(self, sbuf, rbuf, seg):
         ops = []
@@ -120,10 +175,11 @@ class RemoteExchange:
         self._pending = []
 
     def start_ghosts(self):
-        self._start(self.gsbuf, self.grbuf, self.gseg)
+        if not self.p2p:
+            self._start(self.gsbuf, self.grbuf, self.gseg)
 
     def start_emf(self):
-        if self.ctx.mhd:
+        if self.ctx.mhd and not self.p2p:
             self._start(self.esbuf, self.erbuf, self.eseg)
 
     finish_ghosts = _finish
@@ -144,11 +200,25 @@ class RemoteExchange:
                 w.wait()
 
     def exchange_ghosts(self):
-        self._exchange(self.gsbuf, self.grbuf, self.gseg)
+        if not self.p2p:   # (peer-to-peer: the pack kernel already delivered the messages)
+            self._exchange(self.gsbuf, self.grbuf, self.gseg)
 
     def exchange_emf(self):
-        if self.ctx.mhd:
+        if self.ctx.mhd and not self.p2p:
             self._exchange(self.esbuf, self.erbuf, self.eseg)
+
+    def close(self):
+        """Unmap the peers' buffers and release this rank's (after a barrier: nobody writes any more)."""
+        if not self.p2p:
+            return
+        self.ctx.sync()
+        dist.barrier()
+        for ptr in self._p2p_maps:
+            self.ctx.call("athk_p2p_close", C.c_void_p(ptr))
+        dist.barrier()
+        for ptr in self._p2p_own:
+            self.ctx.call("athk_p2p_free", C.c_void_p(ptr))
+        self.p2p = False
 
 
 def attach(ctx, rank, world, device="cuda", stream=None):

@@ -237,6 +237,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     lib = capi.load()
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        # before anything is timed: a golden fixture (the reference's own output) split over the
+        # ranks -- the multi-GPU exchange must reproduce it bit for bit
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import multi_check
+        parity = multi_check.split_golden_case(lib, args.parity_case, rank, world, local_rank)
     mesh_nx, _ = weak_mesh(world, args.per_gpu)
     mesh = pyhost.UniformMesh(mesh_nx, (args.block,) * 3, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), ng=2)
     parts = zorder_partition(mesh.nbtotal, world)
@@ -425,7 +432,15 @@ def run_ours(args):
                                 "exchange + W(U), one VL2 cycle, (u,b) + block dt -> host"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "final_dt": ti.dt, "cycles_run": ti.ncycle}
+        if parity is not None:
+            line["parity_check"] = parity
+        if xch is not None:
+            line["exchange"] = {"transport": "p2p (peer stores over NVLink + flags)" if xch.p2p else "nccl send/recv",
+                                "ghost_bytes_per_stage": int(xch.ghost_bytes), "emf_bytes_per_stage": int(xch.emf_bytes),
+                                "p2p_timeouts": int(lib.athk_p2p_timeouts(ctx.h))}
         emit(line)
+    if xch is not None:
+        xch.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -461,6 +476,9 @@ def main():
     ap.add_argument("--block", type=int, default=64, help="MeshBlock size")
     ap.add_argument("--unfused", action="store_true", help="operator-per-kernel path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-case", default="mhd_linwave_vl2_plm_hlld",
+                    help="golden fixture run split over the ranks before the timed region (N > 1)")
     ap.add_argument("--ref-mesh", type=int, default=128)
     ap.add_argument("--ref-block", type=int, default=32)
     ap.add_argument("--ref-cycles", type=int, default=4)

@@ -234,6 +234,32 @@ int athk_remote_pack_ghosts(athk_ctx *ctx, int reg);
  * call after athk_send_flux_correction */
 int athk_remote_pack_emf(athk_ctx *ctx);
 
+/* ---- multi-GPU: peer-to-peer transport over NVLink -------------------------------------------
+ * CopyVariableBufferSameProcess (bvals_var.cpp:108-119) extended across GPUs: instead of handing
+ * the packed messages to NCCL/MPI, the pack kernels store every message straight into the
+ * RECEIVER's buffer through a peer-mapped pointer, a one-thread-per-peer kernel then raises the
+ * receiver's arrival flag (sequence number, after a system-scope fence), and the receiver's
+ * ghost-fill / EMF-correction is preceded by a kernel that waits for the flags of all its peers.
+ * Receive buffers are double-buffered by the parity of the sequence number, which together with
+ * the stream order of pack -> wait on every rank makes reuse safe without an acknowledgement.
+ * How the peer pointers are obtained is the host's business: CUDA IPC between processes
+ * (athk_p2p_alloc / athk_p2p_open), or plain pointers inside one process (athk_p2p_enable_peer). */
+int athk_p2p_alloc(athk_ctx *ctx, long long nbytes, void **dptr, unsigned char ipc_handle[64]);
+int athk_p2p_open(athk_ctx *ctx, const unsigned char ipc_handle[64], void **dptr);
+int athk_p2p_close(athk_ctx *ctx, void *dptr);    /* a pointer returned by athk_p2p_open */
+int athk_p2p_free(athk_ctx *ctx, void *dptr);     /* a pointer returned by athk_p2p_alloc */
+int athk_p2p_enable_peer(athk_ctx *ctx, int peer_device);
+/* ghost_dst / emf_dst: [2][nlinks] device pointers, where link q's message goes in the receiver's
+ * buffer half 0 / 1; recv_ghost / recv_emf: this context's own buffers, two halves of
+ * ghost_half / emf_half elements laid out as athk_remote_configure's *_recv_off describe;
+ * peer_flags[p]: the two 64-bit words (ghost, emf) in peer p's flag array that belong to this
+ * rank; my_flags: this rank's array [npeers][2] (zero-initialised). */
+int athk_remote_set_p2p(athk_ctx *ctx, int npeers, double *const *ghost_dst, double *const *emf_dst,
+                        double *recv_ghost, long long ghost_half, double *recv_emf, long long emf_half,
+                        unsigned long long *const *peer_flags, unsigned long long *my_flags);
+/* number of flag waits that ran into their time limit (0 in a healthy run) */
+long long athk_p2p_timeouts(athk_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -242,6 +242,64 @@ def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
     compare_with_reference(CUDA_BIN, case)
 
 
+# ---- parity AT SIZE (GPU only; the reference runs on all host cores) --------------------------
+def compare_final_state(binary, cfg, prob, mhd, blocks, threads, errors_file=None):
+    """Run reference and host on the same athinput; every .rst (ghost zones included), the dt /
+    time columns of the .hst and, where given, the appended error rows must be identical."""
+    if not refrun.have_ref(cfg):
+        pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
+    wd_ref, _ = refrun.run_reference(cfg, blocks, threads=threads)
+    wd, r = run_host(binary, blocks, prob, mhd)
+    try:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        ref_files = sorted(os.path.basename(f) for f in glob.glob(wd_ref + "/*.rst"))
+        our_files = sorted(os.path.basename(f) for f in glob.glob(wd + "/*.rst"))
+        assert ref_files == our_files and len(ref_files) >= 2
+        for name in ref_files:
+            a, c = refrun.read_rst(os.path.join(wd_ref, name)), refrun.read_rst(os.path.join(wd, name))
+            assert (a["ncycle"], a["time"], a["dt"], a["loc"]) == (c["ncycle"], c["time"], c["dt"], c["loc"]), name
+            for k in ("u", "b1", "b2", "b3"):
+                assert len(a[k]) == len(c[k])
+                for x, y in zip(a[k], c[k]):
+                    np.testing.assert_array_equal(x, y, err_msg="%s %s" % (name, k))
+            ncycle = a["ncycle"]
+        _, h1 = refrun.read_hst(glob.glob(wd_ref + "/*.hst")[0])
+        _, h2 = refrun.read_hst(glob.glob(wd + "/*.hst")[0])
+        np.testing.assert_array_equal(h1[:, :2], h2[:, :2])
+        scale = np.abs(h1).max(axis=0) + 1e-300
+        assert np.all(np.abs(h1 - h2) <= 1e-10 * scale)
+        if errors_file:
+            assert open(os.path.join(wd_ref, errors_file)).read() == open(os.path.join(wd, errors_file)).read()
+        return ncycle
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+        shutil.rmtree(wd_ref, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_baseline_config1_at_full_size_on_gpu(cuda_lib):
+    """BASELINE configs[1] as stated: MHD linear wave, 128^3 mesh in 32^3 MeshBlocks (64 blocks),
+    VL2 + PLM + HLLD + CT, to tlim = 0.5 -- final restart dump bit-equal, linearwave-errors.dat
+    text-equal (the L1 error vector, north star 1e-12)."""
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    blocks = refrun.linwave_blocks(True, mesh=(128, 128, 128), block=(32, 32, 32), tlim=0.5, rst_dt=0.5)
+    blocks["problem"]["compute_error"] = "true"
+    ncycle = compare_final_state(CUDA_BIN, "linwave_mhd_hlld", "linear_wave", True, blocks,
+                                 threads=min(os.cpu_count() or 1, 64), errors_file="linearwave-errors.dat")
+    assert ncycle > 100
+
+
+@pytest.mark.gpu
+def test_bench_workload_shape_matches_reference_on_gpu(cuda_lib):
+    """The shape bench.py times -- MHD blast, 64^3 MeshBlocks, several blocks per context -- against
+    the reference: 128^3 mesh (8 blocks of 64^3), 5 VL2 cycles, restart dumps bit-equal."""
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    blocks = refrun.blast_blocks(mesh=(128, 128, 128), block=(64, 64, 64), tlim=1.0, rst_dt=1.0)
+    blocks["time"]["nlim"] = 5
+    ncycle = compare_final_state(CUDA_BIN, "blast_mhd_hlld", "blast", True, blocks, threads=min(os.cpu_count() or 1, 8))
+    assert ncycle == 5
+
+
 # The reference's convergence regression (tst/regression/scripts/tests/{hydro,mhd}/*_linear_wave*):
 # run the wave for one period at two resolutions with problem/compute_error=true and read the rows
 # Mesh::UserWorkAfterLoop appends to linearwave-errors.dat (pgen/linear_wave.cpp:190-427).  North
