@@ -162,6 +162,7 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
 
 extern "C" void athk_destroy(athk_ctx *c) {
   if (!c) return;
+  cudaSetDevice(c->cfg.device);
   for (int r = 0; r < 3; ++r) { cudaFree(c->u[r]); cudaFree(c->b[r]); cudaFree(c->s[r]); }
   for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
   cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
@@ -178,6 +179,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
 
 extern "C" int athk_sync(athk_ctx *c) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
   CU(cudaStreamSynchronize(c->stream));
   return ATHK_OK;
 }
@@ -186,6 +188,7 @@ extern "C" long long athk_launch_count(const athk_ctx *c) { return c ? c->launch
 
 extern "C" int athk_profile(athk_ctx *c, int enable, char *report, int report_len) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
 #ifndef ATHK_EMULATE
   if (report && report_len > 0) {
     CU(cudaStreamSynchronize(c->stream));
@@ -228,6 +231,7 @@ extern "C" int athk_set_block_coords(athk_ctx *c, int lb, const double *x1f, con
                                      const double *dx2f, const double *x3f, const double *x3v,
                                      const double *dx3f) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
   if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "set_block_coords: block %d out of range", lb);
   const double *xf[3] = {x1f, x2f, x3f}, *xv[3] = {x1v, x2v, x3v}, *dxf[3] = {dx1f, dx2f, dx3f};
   const int nc[3] = {c->g.nc1, c->g.nc2, c->g.nc3};
@@ -255,6 +259,7 @@ extern "C" int athk_set_block_coords(athk_ctx *c, int lb, const double *x1f, con
 
 extern "C" int athk_set_neighbors(athk_ctx *c, const int *nbr) {
   if (!c || !nbr) return fail(ATHK_ERR_ARG, "set_neighbors: null argument");
+  cudaSetDevice(c->cfg.device);
   const int n = c->g.nb * 27;
   for (int q = 0; q < n; ++q) {
     if (nbr[q] >= c->g.nb) return fail(ATHK_ERR_ARG, "set_neighbors: entry %d = %d out of range", q, nbr[q]);
@@ -345,6 +350,7 @@ __global__ void __launch_bounds__(256) k_stage_copy(Real *dev, Real *dense, int 
 static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_device,
                       bool sync_after = true) {
   if (!c || !host) return fail(ATHK_ERR_ARG, "upload/download: null argument");
+  cudaSetDevice(c->cfg.device);
   if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "upload/download: block %d out of range", lb);
   ArrDesc d;
   if (!describe(c, array, &d))
@@ -414,9 +420,12 @@ extern "C" int athk_device_array(athk_ctx *c, int array, void **dptr, long long 
 }
 
 //----------------------------------------------------------------------------------------
+// (a process may hold one context per GPU -- the C++ host's <mesh> num_gpus -- so every entry
+//  point makes its context's device current first)
 #define NEED_READY(c)                                                                      \
   do {                                                                                     \
     if (!(c)) return fail(ATHK_ERR_ARG, "null context");                                   \
+    cudaSetDevice((c)->cfg.device);                                                        \
     if (!(c)->coords_set || !(c)->nbr_set)                                                 \
       return fail(ATHK_ERR_STATE, "%s: call athk_set_block_coords and athk_set_neighbors " \
                                   "first", __func__);                                      \
@@ -652,6 +661,7 @@ extern "C" int athk_swap_registers(athk_ctx *c, int what, int a, int b) {
 
 extern "C" int athk_zero_register(athk_ctx *c, int what, int reg) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
   if (bad_reg(reg)) return fail(ATHK_ERR_ARG, "zero_register: bad register");
   Real *p = (what == 0) ? c->u[reg] : (what == 1 ? c->b[reg] : (what == 2 ? c->s[reg] : nullptr));
   const int nvar = (what == 0) ? 5 : (what == 1 ? 3 : c->cfg.nscalars);
@@ -935,6 +945,7 @@ extern "C" int athk_apply_physical_boundaries(athk_ctx *c) {
 
 extern "C" int athk_set_block_floors(athk_ctx *c, int lb, double dfloor, double pfloor, double sfloor) {
   if (!c) return fail(ATHK_ERR_ARG, "set_block_floors: null context");
+  cudaSetDevice(c->cfg.device);
   const int nb = c->g.nb;
   if (lb < 0 || lb >= nb) return fail(ATHK_ERR_ARG, "set_block_floors: block %d out of range", lb);
   if (!(dfloor > 0.0) || !(pfloor > 0.0) || !(sfloor >= 0.0))
@@ -1189,6 +1200,7 @@ extern "C" int athk_remote_configure(athk_ctx *c, int nlinks, const int *lb, con
                                      const long long *ghost_recv_off,
                                      const long long *emf_send_off, const long long *emf_recv_off) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
   if (nlinks < 0) return fail(ATHK_ERR_ARG, "remote_configure: nlinks < 0");
   cudaFree(c->rl_int); cudaFree(c->rl_off);
   c->rl_int = nullptr; c->rl_off = nullptr;
@@ -1318,6 +1330,7 @@ extern "C" int athk_p2p_close(athk_ctx *c, void *dptr) {
 extern "C" int athk_p2p_free(athk_ctx *c, void *dptr) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
 #ifndef ATHK_EMULATE
+  cudaSetDevice(c->cfg.device);
   CU(cudaStreamSynchronize(c->stream));
   if (dptr) CU(cudaFree(dptr));
 #else
@@ -1344,6 +1357,7 @@ extern "C" int athk_p2p_enable_peer(athk_ctx *c, int peer_device) {
 extern "C" long long athk_p2p_timeouts(athk_ctx *c) {
   if (!c || !c->p2p.timeouts) return 0;
 #ifndef ATHK_EMULATE
+  cudaSetDevice(c->cfg.device);
   unsigned long long v = 0;
   cudaStreamSynchronize(c->stream);
   cudaMemcpy(&v, c->p2p.timeouts, sizeof(v), cudaMemcpyDeviceToHost);
@@ -1357,13 +1371,13 @@ extern "C" int athk_remote_set_p2p(athk_ctx *c, int npeers, double *const *ghost
                                    double *recv_ghost, long long ghost_half, double *recv_emf, long long emf_half,
                                    unsigned long long *const *peer_flags, unsigned long long *my_flags) {
   if (!c) return fail(ATHK_ERR_ARG, "null context");
+  cudaSetDevice(c->cfg.device);
   const int n = c->rl.n;
   if (n == 0 || npeers <= 0) { c->p2p.on = false; return ATHK_OK; }
   if (!ghost_dst || !recv_ghost || !peer_flags || !my_flags)
     return fail(ATHK_ERR_ARG, "remote_set_p2p: null argument");
   if (c->cfg.mhd && (!emf_dst || !recv_emf)) return fail(ATHK_ERR_ARG, "remote_set_p2p: EMF buffers missing");
   athk_ctx::P2P &p = c->p2p;
-#ifndef ATHK_EMULATE
   cudaFree(p.gdst); cudaFree(p.edst); cudaFree(p.peer_flags); cudaFree(p.timeouts);
   p.gdst = p.edst = nullptr; p.peer_flags = nullptr; p.timeouts = nullptr;
   CU(cudaMalloc((void **)&p.gdst, 2 * (size_t)n * sizeof(Real *)));
@@ -1375,10 +1389,10 @@ extern "C" int athk_remote_set_p2p(athk_ctx *c, int npeers, double *const *ghost
   CU(cudaMalloc((void **)&p.peer_flags, (size_t)npeers * sizeof(unsigned long long *)));
   CU(cudaMemcpy(p.peer_flags, peer_flags, (size_t)npeers * sizeof(unsigned long long *), cudaMemcpyHostToDevice));
   CU(cudaMalloc((void **)&p.timeouts, sizeof(unsigned long long)));
-  CU(cudaMemset(p.timeouts, 0, sizeof(unsigned long long)));
-#else
-  (void)peer_flags;
-#endif
+  {
+    const unsigned long long zero = 0;
+    CU(cudaMemcpy(p.timeouts, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  }
   p.npeers = npeers;
   p.grecv = recv_ghost; p.ghalf = ghost_half;
   p.erecv = recv_emf; p.ehalf = emf_half;

@@ -33,7 +33,7 @@ static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = 0; return 0; 
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return 0; }   // (every "device" is the host)
 #endif
 
 namespace athk {

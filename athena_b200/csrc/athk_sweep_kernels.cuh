@@ -381,6 +381,22 @@ k_sweep_tile(const SweepArgs a, const int nb, const int o_lo, const int n_o, con
 //     operations when the straight-line sequences flag it) until the next step picks it up, and so
 //     is the previous face's flux for the divergence term -- nothing is carried in registers
 //     across the Riemann solve.
+// > 48 KB of dynamic shared memory is opt-in per kernel AND per device (a process may drive
+// several GPUs): remember the largest size granted on each device
+template <class K>
+static inline cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t *granted /*[64], zero-initialised*/) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 63;
+  if (smem > granted[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    granted[dev] = smem;
+  }
+  return cudaSuccess;
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -565,13 +581,9 @@ static inline cudaError_t launch_sweep_tile(cudaStream_t st, const SweepArgs &a,
   {
     constexpr int NT = ATHK_MARCH_THREADS, NR = 2 * ORDER + ATHK_MARCH_PD, NQ = MHD ? 8 : 5, NW = MHD ? 7 : 5;
     constexpr size_t smem = sizeof(Real) * NT * (NR * NQ + 5 + 2 * NW);
-    static bool attr_set = false;   // > 48 KB of dynamic shared memory is opt-in, once per kernel
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_sweep_march<DIR, ORDER, MHD, RS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    static size_t granted[64];
+    cudaError_t e = ensure_dynamic_smem(k_sweep_march<DIR, ORDER, MHD, RS>, smem, granted);
+    if (e != cudaSuccess) return e;
     k_sweep_march<DIR, ORDER, MHD, RS><<<(unsigned)((ncol + NT - 1) / NT), NT, smem, st>>>(a, nb, o_lo, n_o, il, ni);
     return cudaGetLastError();
   }
@@ -974,13 +986,9 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
     q.wstride = p2 + p2 * NQ * g.P1 + 3 * g.P1 + 12 + NI * 32;   // mbarriers, ring, geometry, hand-over, lane slots
     q.wstride = (q.wstride + 1) & ~1;   // keep every warp's region 16-byte aligned
     const size_t smem = sizeof(Real) * 4 * (size_t)q.wstride;
-    static size_t attr_smem = 0;   // > 48 KB of dynamic shared memory is opt-in
-    if (smem > attr_smem) {
-      cudaError_t e = cudaFuncSetAttribute(k_sweep_x1_rows<ORDER, MHD, RS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_smem = smem;
-    }
+    static size_t granted[64];
+    cudaError_t e = ensure_dynamic_smem(k_sweep_x1_rows<ORDER, MHD, RS>, smem, granted);
+    if (e != cudaSuccess) return e;
     k_sweep_x1_rows<ORDER, MHD, RS><<<(unsigned)((q.nwarps + 3) / 4), 128, smem, st>>>(f, q);
     return cudaGetLastError();
   }

@@ -201,7 +201,8 @@ class MeshBlock {   // mesh/mesh.hpp:75-200
   Mesh *pmy_mesh;
   LogicalLocation loc;
   RegionSize block_size;
-  int gid, lid;
+  int gid, lid;                 // global id; local id on its GPU's context
+  int rank = 0;                 // which of the Mesh's GPUs owns the block (the reference's rank)
   int is, ie, js, je, ks, ke;
   int ncells1, ncells2, ncells3;
   Coordinates *pcoord;
@@ -235,6 +236,7 @@ class Mesh {   // mesh/mesh.hpp:206-447
   void UserWorkAfterLoop(ParameterInput *pin);
   void OutputCycleDiagnostics();          // mesh.cpp:2304
   void DownloadAll();                     // device -> host mirrors (outputs)
+  void ExchangeGhosts();                  // SEND/RECV/SETB of every variable, all GPUs
   MeshBlock *my_blocks(int b) { return blocks_[b]; }
   RegionSize mesh_size;
   BoundaryFlag mesh_bcs[6];
@@ -245,7 +247,15 @@ class Mesh {   // mesh/mesh.hpp:206-447
   int nbtotal, nblocal, root_level;
   int nrbx1, nrbx2, nrbx3;
   std::vector<LogicalLocation> loclist;
-  athk_ctx *athk;
+  // MeshBlocks are cut into contiguous Z-order ranges, one per GPU (amr_loadbalance.cpp:73-131:
+  // ranklist / nslist / nblist), one device context per GPU; neighbours on another GPU are remote
+  // links served by the peer-to-peer transport (include/athk.h).  <mesh> num_gpus, default 1.
+  int ngpu = 1;
+  std::vector<int> ranklist, nslist, nblist;
+  std::vector<athk_ctx *> ctx;            // [ngpu]
+  athk_ctx *ctx_of(const MeshBlock *pmb) { return ctx[pmb->rank]; }
+  athk_ctx *athk;                         // == ctx[0]
+  void SetupRemoteLinks();                // multigpu.cpp
   const ProblemGeneratorEntry *pgen;
   bool fused_stage;
   // user history output (mesh.hpp: EnrollUserHistoryOutput)
@@ -256,6 +266,8 @@ class Mesh {   // mesh/mesh.hpp:206-447
 
  private:
   std::vector<MeshBlock *> blocks_;
+  std::vector<void *> p2p_allocs_;        // per GPU: ghost, emf, flag buffers (athk_p2p_alloc)
+  int gpu_device0_ = 0;                   // <mesh> gpu_device: CUDA device of GPU 0 of this Mesh
 };
 
 void AthkCheck(int rc, const char *where);   // non-zero return -> ATHENA_ERROR(athk_last_error)

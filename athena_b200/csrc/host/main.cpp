@@ -160,7 +160,8 @@ int main(int argc, char *argv[]) {
       pmesh->OutputCycleDiagnostics();
       for (int stage = 1; stage <= ptlist->nstages; ++stage) {
         // NEW_DT rides on the last stage's W(U) pass (same per-cell values, exact min)
-        if (stage == ptlist->nstages) AthkCheck(athk_request_block_dt(pmesh->athk), "main");
+        if (stage == ptlist->nstages)
+          for (athk_ctx *a : pmesh->ctx) AthkCheck(athk_request_block_dt(a), "main");
         ptlist->DoTaskListOneStage(pmesh, stage);
       }
       pmesh->ncycle++;
@@ -171,7 +172,7 @@ int main(int argc, char *argv[]) {
       if (SignalRaised()) break;
     }
     if (wtlim > 0) alarm(0);
-    AthkCheck(athk_sync(pmesh->athk), "main");
+    for (athk_ctx *a : pmesh->ctx) AthkCheck(athk_sync(a), "main");
     const double wsec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     pmesh->OutputCycleDiagnostics();
     pmesh->UserWorkAfterLoop(pinput);
@@ -192,7 +193,11 @@ int main(int argc, char *argv[]) {
     std::snprintf(buf, sizeof(buf),
                   "zone-cycles = %llu\ngpu wtime used = %.16e\nzone-cycles/gpu_wsecond = %.16e\n"
                   "kernel launches = %lld\n",
-                  (unsigned long long)zonecycles, wsec, zonecycles / wsec, athk_launch_count(pmesh->athk));
+                  (unsigned long long)zonecycles, wsec, zonecycles / wsec, [&] {
+                    long long n = 0;
+                    for (athk_ctx *a : pmesh->ctx) n += athk_launch_count(a);
+                    return n;
+                  }());
     std::cout << buf << std::endl;
     delete pouts;
     delete ptlist;

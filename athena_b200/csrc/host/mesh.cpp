@@ -201,7 +201,28 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   std::sort(loclist.begin(), loclist.end(),
             [](const LogicalLocation &a, const LogicalLocation &b) { return MortonKey(a) < MortonKey(b); });
   nbtotal = static_cast<int>(loclist.size());
-  nblocal = nbtotal;   // one rank / one GPU in this binary
+  nblocal = nbtotal;   // one process drives every GPU: all MeshBlocks are "local" to the host
+  // Mesh::CalculateLoadBalance (amr_loadbalance.cpp:73-131) for equal costs: contiguous Z-order
+  // ranges, the remainder handed out from the last rank backwards
+  ngpu = pin->GetOrAddInteger("mesh", "num_gpus", 1);
+  if (ngpu < 1 || ngpu > nbtotal) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "<mesh> num_gpus = " << ngpu << " must be between 1 and the number of MeshBlocks (" << nbtotal << ")";
+    ATHENA_ERROR(msg);
+  }
+  ranklist.assign(nbtotal, 0);
+  nslist.assign(ngpu, 0);
+  nblist.assign(ngpu, 0);
+  {
+    const int base = nbtotal / ngpu, rem = nbtotal % ngpu;
+    int s = 0;
+    for (int r = 0; r < ngpu; ++r) {
+      nslist[r] = s;
+      nblist[r] = base + (r >= ngpu - rem ? 1 : 0);
+      for (int n = s; n < s + nblist[r]; ++n) ranklist[n] = r;
+      s += nblist[r];
+    }
+  }
 
   pgen = FindProblemGenerator(g_config.problem);
   if (pgen == nullptr) {
@@ -224,15 +245,15 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
       *q.bmax = (q.lx == q.nrb - 1) ? q.mmax
                                     : UniformMeshGenerator(ComputeMeshGeneratorX(q.lx + 1, q.nrb), q.mmin, q.mmax);
     }
-    blocks_.push_back(new MeshBlock(n, n, l, b, this, pin));
+    blocks_.push_back(new MeshBlock(n, n - nslist[ranklist[n]], l, b, this, pin));
+    blocks_.back()->rank = ranklist[n];
   }
 
-  // ---- device context: one for all MeshBlocks of this rank --------------------------------
+  // ---- device contexts: one per GPU, each for the MeshBlocks of its range ------------------
   athk_config cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.nx1 = bs.nx1; cfg.nx2 = bs.nx2; cfg.nx3 = bs.nx3;
   cfg.nghost = NGHOST;
-  cfg.nblocks = nblocal;
   cfg.mhd = MAGNETIC_FIELDS_ENABLED ? 1 : 0;
   cfg.nscalars = NSCALARS;
   const std::string flux = g_config.flux.empty() ? (MAGNETIC_FIELDS_ENABLED ? "hlld" : "hllc") : g_config.flux;
@@ -245,19 +266,27 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     msg << "### FATAL ERROR in Mesh constructor" << std::endl << "unknown Riemann solver '" << flux << "'";
     ATHENA_ERROR(msg);
   }
-  cfg.device = pin->GetOrAddInteger("mesh", "gpu_device", 0);
+  const int dev0 = pin->GetOrAddInteger("mesh", "gpu_device", 0);
+  gpu_device0_ = dev0;
   cfg.gamma = blocks_[0]->peos->GetGamma();
   cfg.dfloor = blocks_[0]->peos->GetDensityFloor();
   cfg.pfloor = blocks_[0]->peos->GetPressureFloor();
   cfg.sfloor = blocks_[0]->peos->GetScalarFloor();
-  AthkCheck(athk_create(&cfg, &athk), "Mesh constructor (athk_create)");
+  ctx.assign(ngpu, nullptr);
+  for (int r = 0; r < ngpu; ++r) {
+    cfg.device = dev0 + r;
+    cfg.nblocks = nblist[r];
+    AthkCheck(athk_create(&cfg, &ctx[r]), "Mesh constructor (athk_create)");
+  }
+  athk = ctx[0];
   // each MeshBlock's own EquationOfState: blocks built after the first read the floors back from
   // the 6-digit strings the first one stored (see ParameterInput::GetOrAddReal)
-  for (int n = 1; n < nblocal; ++n) {
+  for (int n = 0; n < nblocal; ++n) {
     const EquationOfState *pe = blocks_[n]->peos;
     if (pe->GetDensityFloor() != cfg.dfloor || pe->GetPressureFloor() != cfg.pfloor ||
         pe->GetScalarFloor() != cfg.sfloor)
-      AthkCheck(athk_set_block_floors(athk, n, pe->GetDensityFloor(), pe->GetPressureFloor(), pe->GetScalarFloor()),
+      AthkCheck(athk_set_block_floors(ctx_of(blocks_[n]), blocks_[n]->lid, pe->GetDensityFloor(),
+                                      pe->GetPressureFloor(), pe->GetScalarFloor()),
                 "Mesh constructor (athk_set_block_floors)");
   }
   {   // HydroSourceTerms constructor (hydro/srcterms/hydro_srcterms.cpp:42-46)
@@ -265,36 +294,18 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     const Real g2 = pin->GetOrAddReal("hydro", "grav_acc2", 0.0);
     const Real g3 = pin->GetOrAddReal("hydro", "grav_acc3", 0.0);
     if (g1 != 0.0 || g2 != 0.0 || g3 != 0.0)
-      AthkCheck(athk_set_constant_acceleration(athk, g1, g2, g3), "Mesh constructor (athk_set_constant_acceleration)");
+      for (athk_ctx *a : ctx)
+        AthkCheck(athk_set_constant_acceleration(a, g1, g2, g3), "Mesh constructor (athk_set_constant_acceleration)");
   }
   for (int n = 0; n < nblocal; ++n) {
     Coordinates *pc = blocks_[n]->pcoord;
-    AthkCheck(athk_set_block_coords(athk, n, pc->x1f.data(), pc->x1v.data(), pc->dx1f.data(),
-                                    pc->x2f.data(), pc->x2v.data(), pc->dx2f.data(),
+    AthkCheck(athk_set_block_coords(ctx_of(blocks_[n]), blocks_[n]->lid, pc->x1f.data(), pc->x1v.data(),
+                                    pc->dx1f.data(), pc->x2f.data(), pc->x2v.data(), pc->dx2f.data(),
                                     pc->x3f.data(), pc->x3v.data(), pc->dx3f.data()),
               "Mesh constructor (athk_set_block_coords)");
   }
-  // same-level neighbour table (BoundaryBase::SearchAndSetNeighbors, bvals_base.cpp:301):
-  // uniform periodic root grid => the neighbour is the block at the wrapped logical location
-  std::map<std::uint64_t, int> gid_of;
-  for (int n = 0; n < nbtotal; ++n) gid_of[MortonKey(loclist[n])] = n;
-  std::vector<int> nbr((std::size_t)nblocal * 27, -1);
-  for (int n = 0; n < nblocal; ++n) {
-    const LogicalLocation &l = loclist[n];
-    for (int o3 = -1; o3 <= 1; ++o3)
-      for (int o2 = -1; o2 <= 1; ++o2)
-        for (int o1 = -1; o1 <= 1; ++o1) {
-          if (o1 == 0 && o2 == 0 && o3 == 0) continue;
-          // no neighbour across a non-periodic mesh boundary (entry stays -1)
-          const std::int64_t q1 = l.lx1 + o1, q2 = l.lx2 + o2, q3 = l.lx3 + o3;
-          if ((q1 < 0 || q1 >= nrbx1) && mesh_bcs[0] != BoundaryFlag::periodic) continue;
-          if ((q2 < 0 || q2 >= nrbx2) && mesh_bcs[2] != BoundaryFlag::periodic) continue;
-          if ((q3 < 0 || q3 >= nrbx3) && mesh_bcs[4] != BoundaryFlag::periodic) continue;
-          LogicalLocation q{(q1 + nrbx1) % nrbx1, (q2 + nrbx2) % nrbx2, (q3 + nrbx3) % nrbx3, l.level};
-          nbr[(std::size_t)n * 27 + (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1)] = gid_of[MortonKey(q)];
-        }
-  }
-  AthkCheck(athk_set_neighbors(athk, nbr.data()), "Mesh constructor (athk_set_neighbors)");
+  // same-level neighbour tables, per-GPU remote links, peer-to-peer buffers (multigpu.cpp)
+  SetupRemoteLinks();
   // BoundaryValues::block_bcs (bvals.cpp:60-120): mesh flag on the mesh edge, "block" elsewhere
   for (int n = 0; n < nblocal; ++n) {
     const LogicalLocation &l = loclist[n];
@@ -309,14 +320,26 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
                            : (bf == BoundaryFlag::reflect ? ATHK_BC_REFLECT : ATHK_BC_OUTFLOW);
         any = any || fl[2 * d + side] != ATHK_BC_NONE;
       }
-    if (any) AthkCheck(athk_set_boundary_flags(athk, n, fl), "Mesh constructor (athk_set_boundary_flags)");
+    if (any) AthkCheck(athk_set_boundary_flags(ctx_of(blocks_[n]), blocks_[n]->lid, fl),
+                       "Mesh constructor (athk_set_boundary_flags)");
   }
   if (pgen->init_user_mesh_data) pgen->init_user_mesh_data(this, pin);   // mesh.cpp:601
 }
 
 Mesh::~Mesh() {
   for (MeshBlock *p : blocks_) delete p;
-  if (athk) athk_destroy(athk);
+  for (athk_ctx *a : ctx) if (a) athk_sync(a);
+  for (std::size_t q = 0; q < p2p_allocs_.size(); ++q)
+    if (p2p_allocs_[q]) athk_p2p_free(ctx[q / 3], p2p_allocs_[q]);
+  for (athk_ctx *a : ctx) if (a) athk_destroy(a);
+}
+
+// SEND_HYD/_FLD/_SCLR, RECV, SETB for every GPU: pack the messages for neighbours on other GPUs
+// (peer stores), then fill the ghost zones
+void Mesh::ExchangeGhosts() {
+  const int what = 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0) | (NSCALARS > 0 ? 4 : 0);
+  if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), "Mesh::ExchangeGhosts");
+  for (athk_ctx *a : ctx) AthkCheck(athk_exchange_ghosts(a, what, 0), "Mesh::ExchangeGhosts");
 }
 
 // Mesh::Initialize for a fresh run (mesh.cpp:1622-1967): pgen on the host, upload, first
@@ -325,19 +348,20 @@ void Mesh::Initialize(ParameterInput *pin) {
   for (int b = 0; b < nblocal; ++b) {
     MeshBlock *pmb = blocks_[b];
     if (!res_flag) pmb->ProblemGenerator(pin);   // restart: the arrays were filled by LoadRestart
-    AthkCheck(athk_upload(athk, ATHK_U, b, pmb->phydro->u.data()), "Mesh::Initialize");
+    athk_ctx *a = ctx_of(pmb);
+    const int l = pmb->lid;
+    AthkCheck(athk_upload(a, ATHK_U, l, pmb->phydro->u.data()), "Mesh::Initialize");
     if (MAGNETIC_FIELDS_ENABLED) {
-      AthkCheck(athk_upload(athk, ATHK_B_X1F, b, pmb->pfield->b.x1f.data()), "Mesh::Initialize");
-      AthkCheck(athk_upload(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::Initialize");
-      AthkCheck(athk_upload(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(a, ATHK_B_X1F, l, pmb->pfield->b.x1f.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(a, ATHK_B_X2F, l, pmb->pfield->b.x2f.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(a, ATHK_B_X3F, l, pmb->pfield->b.x3f.data()), "Mesh::Initialize");
     }
-    if (NSCALARS > 0) AthkCheck(athk_upload(athk, ATHK_S, b, pmb->pscalars->s.data()), "Mesh::Initialize");
+    if (NSCALARS > 0) AthkCheck(athk_upload(a, ATHK_S, l, pmb->pscalars->s.data()), "Mesh::Initialize");
   }
-  AthkCheck(athk_sync(athk), "Mesh::Initialize");
-  AthkCheck(athk_exchange_ghosts(athk, 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0),
-            "Mesh::Initialize");
-  AthkCheck(athk_cons2prim(athk, 0), "Mesh::Initialize");
-  AthkCheck(athk_apply_physical_boundaries(athk), "Mesh::Initialize");   // mesh.cpp:1886-1891
+  for (athk_ctx *a : ctx) AthkCheck(athk_sync(a), "Mesh::Initialize");
+  ExchangeGhosts();
+  for (athk_ctx *a : ctx) AthkCheck(athk_cons2prim(a, 0), "Mesh::Initialize");
+  for (athk_ctx *a : ctx) AthkCheck(athk_apply_physical_boundaries(a), "Mesh::Initialize");   // mesh.cpp:1886-1891
   NewTimeStep();
 }
 
@@ -412,7 +436,8 @@ void Mesh::LoadRestart(const std::string &raw, std::size_t off) {
 void Mesh::NewTimeStep() {   // mesh.cpp:1236-1282
   std::vector<Real> bdt(nblocal);
   Real dtmin;
-  AthkCheck(athk_new_block_dt(athk, cfl_number, bdt.data(), &dtmin), "Mesh::NewTimeStep");
+  for (int r = 0; r < ngpu; ++r)
+    AthkCheck(athk_new_block_dt(ctx[r], cfl_number, bdt.data() + nslist[r], &dtmin), "Mesh::NewTimeStep");
   for (int b = 0; b < nblocal; ++b) blocks_[b]->new_block_dt_ = bdt[b];
   dt = static_cast<Real>(2.0) * dt;
   for (int b = 0; b < nblocal; ++b) dt = std::min(dt, blocks_[b]->new_block_dt_);
@@ -422,17 +447,19 @@ void Mesh::NewTimeStep() {   // mesh.cpp:1236-1282
 void Mesh::DownloadAll() {
   for (int b = 0; b < nblocal; ++b) {
     MeshBlock *pmb = blocks_[b];
-    AthkCheck(athk_download(athk, ATHK_U, b, pmb->phydro->u.data()), "Mesh::DownloadAll");
-    AthkCheck(athk_download(athk, ATHK_W, b, pmb->phydro->w.data()), "Mesh::DownloadAll");
+    athk_ctx *athk = ctx_of(pmb);   // (shadows the member: this block's GPU)
+    const int l = pmb->lid;
+    AthkCheck(athk_download(athk, ATHK_U, l, pmb->phydro->u.data()), "Mesh::DownloadAll");
+    AthkCheck(athk_download(athk, ATHK_W, l, pmb->phydro->w.data()), "Mesh::DownloadAll");
     if (MAGNETIC_FIELDS_ENABLED) {
-      AthkCheck(athk_download(athk, ATHK_B_X1F, b, pmb->pfield->b.x1f.data()), "Mesh::DownloadAll");
-      AthkCheck(athk_download(athk, ATHK_B_X2F, b, pmb->pfield->b.x2f.data()), "Mesh::DownloadAll");
-      AthkCheck(athk_download(athk, ATHK_B_X3F, b, pmb->pfield->b.x3f.data()), "Mesh::DownloadAll");
-      AthkCheck(athk_download(athk, ATHK_BCC, b, pmb->pfield->bcc.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_B_X1F, l, pmb->pfield->b.x1f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_B_X2F, l, pmb->pfield->b.x2f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_B_X3F, l, pmb->pfield->b.x3f.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_BCC, l, pmb->pfield->bcc.data()), "Mesh::DownloadAll");
     }
     if (NSCALARS > 0) {
-      AthkCheck(athk_download(athk, ATHK_S, b, pmb->pscalars->s.data()), "Mesh::DownloadAll");
-      AthkCheck(athk_download(athk, ATHK_R, b, pmb->pscalars->r.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_S, l, pmb->pscalars->s.data()), "Mesh::DownloadAll");
+      AthkCheck(athk_download(athk, ATHK_R, l, pmb->pscalars->r.data()), "Mesh::DownloadAll");
     }
   }
 }

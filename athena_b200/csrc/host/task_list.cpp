@@ -67,52 +67,61 @@ TimeIntegratorTaskList::TimeIntegratorTaskList(ParameterInput *pin, Mesh *pm) {
 }
 
 void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
-  athk_ctx *a = pm->athk;
   const IntegratorWeight &sw = stage_wghts[stage - 1];
   const bool mhd = MAGNETIC_FIELDS_ENABLED;
   // CalculateHydroFlux: donor cell on the VL2 predictor (time_integrator.cpp:1700-1701)
   const int order = (integrator == "vl2" && stage == 1) ? 1 : xorder;
   const Real dt = pm->dt;
+  const char *who = "TimeIntegratorTaskList::DoTaskListOneStage";
+  // Every call acts on all MeshBlocks of one GPU and only enqueues work, so a task is issued to
+  // every GPU before the next one (the reference's per-MeshBlock task loop, task_list.cpp:66-117,
+  // with the GPUs running concurrently); messages between GPUs travel inside the pack calls.
+  auto all = [&](auto &&fn) { for (athk_ctx *a : pm->ctx) AthkCheck(fn(a), who); };
   if (pm->fused_stage) {
     athk_stage_wghts w = {sw.delta, sw.gamma_1, sw.gamma_2, sw.gamma_3, sw.beta};
-    AthkCheck(athk_stage(a, stage, order, &w, dt), "TimeIntegratorTaskList (athk_stage)");
+    if (pm->ngpu == 1) {
+      AthkCheck(athk_stage(pm->athk, stage, order, &w, dt), "TimeIntegratorTaskList (athk_stage)");
+    } else {   // the same stage cut at its two exchange points
+      for (int phase = 0; phase < 3; ++phase)
+        all([&](athk_ctx *a) { return athk_stage_phase(a, phase, stage, order, &w, dt); });
+    }
     return;
   }
-  const char *who = "TimeIntegratorTaskList::DoTaskListOneStage";
   if (stage == 1) {   // StartupTaskList (:1608-1619)
-    AthkCheck(athk_zero_register(a, 0, 1), who);
-    if (mhd) AthkCheck(athk_zero_register(a, 1, 1), who);
-    if (NSCALARS > 0) AthkCheck(athk_zero_register(a, 2, 1), who);   // ps->s1.ZeroClear() :1628-1630
+    all([&](athk_ctx *a) { return athk_zero_register(a, 0, 1); });
+    if (mhd) all([&](athk_ctx *a) { return athk_zero_register(a, 1, 1); });
+    if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_zero_register(a, 2, 1); });   // ps->s1.ZeroClear() :1628-1630
   }
-  AthkCheck(athk_calculate_fluxes(a, order, dt, 0), who);                 // CALC_HYDFLX
-  if (NSCALARS > 0) AthkCheck(athk_calculate_scalar_fluxes(a, order), who);   // CALC_SCLRFLX :2329-2340
+  all([&](athk_ctx *a) { return athk_calculate_fluxes(a, order, dt, 0); });                    // CALC_HYDFLX
+  if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_calculate_scalar_fluxes(a, order); });  // CALC_SCLRFLX :2329-2340
   if (mhd) {
-    AthkCheck(athk_compute_corner_e(a), who);                            // CALC_FLDFLX
-    AthkCheck(athk_send_flux_correction(a), who);                        // SEND_FLDFLX
-    AthkCheck(athk_recv_flux_correction(a), who);                        // RECV_FLDFLX
+    all([&](athk_ctx *a) { return athk_compute_corner_e(a); });                                // CALC_FLDFLX
+    all([&](athk_ctx *a) { return athk_send_flux_correction(a); });                            // SEND_FLDFLX
+    if (pm->ngpu > 1) all([&](athk_ctx *a) { return athk_remote_pack_emf(a); });
+    all([&](athk_ctx *a) { return athk_recv_flux_correction(a); });                            // RECV_FLDFLX
   }
   // IntegrateHydro (:1797-1847)
   const Real w1[5] = {1.0, sw.delta, 0.0, 0.0, 0.0};
   const Real w2[5] = {sw.gamma_1, sw.gamma_2, sw.gamma_3, 0.0, 0.0};
   const bool swap = (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0);
-  AthkCheck(athk_weighted_ave_cc(a, 0, 1, 0, 2, w1), who);
-  if (swap) AthkCheck(athk_swap_registers(a, 0, 0, 1), who);
-  else AthkCheck(athk_weighted_ave_cc(a, 0, 0, 1, 2, w2), who);
-  AthkCheck(athk_add_flux_divergence(a, sw.beta * dt, 0), who);
-  AthkCheck(athk_add_source_terms(a, sw.beta * dt), who);               // SRC_TERM :1890-1913
-  if (NSCALARS > 0) {                                                   // INT_SCLR :2376-2403
-    AthkCheck(athk_weighted_ave_cc(a, 1, 1, 0, 2, w1), who);
-    if (swap) AthkCheck(athk_swap_registers(a, 2, 0, 1), who);
-    else AthkCheck(athk_weighted_ave_cc(a, 1, 0, 1, 2, w2), who);
-    AthkCheck(athk_add_scalar_flux_divergence(a, sw.beta * dt, 0), who);
+  all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 0, 1, 0, 2, w1); });
+  if (swap) all([&](athk_ctx *a) { return athk_swap_registers(a, 0, 0, 1); });
+  else all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 0, 0, 1, 2, w2); });
+  all([&](athk_ctx *a) { return athk_add_flux_divergence(a, sw.beta * dt, 0); });
+  all([&](athk_ctx *a) { return athk_add_source_terms(a, sw.beta * dt); });                    // SRC_TERM :1890-1913
+  if (NSCALARS > 0) {                                                                          // INT_SCLR :2376-2403
+    all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 1, 0, 2, w1); });
+    if (swap) all([&](athk_ctx *a) { return athk_swap_registers(a, 2, 0, 1); });
+    else all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 0, 1, 2, w2); });
+    all([&](athk_ctx *a) { return athk_add_scalar_flux_divergence(a, sw.beta * dt, 0); });
   }
   if (mhd) {   // IntegrateField (:1853-1885)
-    AthkCheck(athk_weighted_ave_fc(a, 1, 0, 2, w1), who);
-    if (swap) AthkCheck(athk_swap_registers(a, 1, 0, 1), who);
-    else AthkCheck(athk_weighted_ave_fc(a, 0, 1, 2, w2), who);
-    AthkCheck(athk_ct(a, sw.beta * dt, 0), who);
+    all([&](athk_ctx *a) { return athk_weighted_ave_fc(a, 1, 0, 2, w1); });
+    if (swap) all([&](athk_ctx *a) { return athk_swap_registers(a, 1, 0, 1); });
+    else all([&](athk_ctx *a) { return athk_weighted_ave_fc(a, 0, 1, 2, w2); });
+    all([&](athk_ctx *a) { return athk_ct(a, sw.beta * dt, 0); });
   }
-  AthkCheck(athk_exchange_ghosts(a, 1 | (mhd ? 2 : 0) | (NSCALARS > 0 ? 4 : 0), 0), who);   // SEND/RECV/SETB_HYD,_FLD,_SCLR
-  AthkCheck(athk_cons2prim(a, 0), who);                            // CONS2PRIM
-  AthkCheck(athk_apply_physical_boundaries(a), who);               // PHY_BVAL :2276-2311
+  pm->ExchangeGhosts();                                                // SEND/RECV/SETB_HYD,_FLD,_SCLR
+  all([&](athk_ctx *a) { return athk_cons2prim(a, 0); });              // CONS2PRIM
+  all([&](athk_ctx *a) { return athk_apply_physical_boundaries(a); }); // PHY_BVAL :2276-2311
 }

@@ -175,7 +175,7 @@ def run_host(binary, blocks, prob, mhd, extra=(), wd=None):
     return wd, r
 
 
-def compare_with_reference(binary, case, host_time_params=None):
+def compare_with_reference(binary, case, host_time_params=None, host_mesh_params=None):
     cfg, prob, mhd, mk = CASES[case][:4]
     extra = CASES[case][4] if len(CASES[case]) > 4 else []
     if not refrun.have_ref(cfg):
@@ -184,6 +184,7 @@ def compare_with_reference(binary, case, host_time_params=None):
     wd_ref, _ = refrun.run_reference(cfg, blocks)
     host_blocks = {k: dict(v) for k, v in blocks.items()}
     host_blocks["time"].update(host_time_params or {})
+    host_blocks["mesh"].update(host_mesh_params or {})
     wd, r = run_host(binary, host_blocks, prob, mhd, extra=extra)
     try:
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -240,6 +241,40 @@ def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
 def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
     assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
     compare_with_reference(CUDA_BIN, case)
+
+
+# ---- MeshBlocks partitioned over several GPUs by the C++ host (<mesh> num_gpus) ----------------
+# Mesh::CalculateLoadBalance ranges + remote links + peer-to-peer transport (host/multigpu.cpp).
+# CPU: the harness library treats every "device" as host memory, which exercises the block ranges,
+# neighbour tables, message layouts and stage phases; GPU: needs a box with that many devices.
+@pytest.mark.parametrize("ngpu,fused", [(2, "true"), (3, "true"), (4, "false")])
+def test_host_partitions_blocks_over_gpus_emulated(emul_binary, ngpu, fused):
+    def mk():
+        b = refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.05, rst_dt=0.02)
+        return b
+    CASES["_mg"] = ("linwave_mhd_hlld", "linear_wave", True, mk)
+    try:
+        compare_with_reference(emul_binary, "_mg", host_time_params={"fused_stage": fused},
+                               host_mesh_params={"num_gpus": ngpu})
+    finally:
+        del CASES["_mg"]
+
+
+def _visible_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,ngpu", [("mhd_blast", 2), ("kh_mhd_rk2_scalar", 2), ("mhd_blast", 8)])
+def test_host_binary_on_several_gpus_reproduces_reference_files(cuda_lib, case, ngpu):
+    if _visible_gpus() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    assert os.access(CUDA_BIN, os.X_OK), "athena_b200/bin/athena_b200 not built"
+    compare_with_reference(CUDA_BIN, case, host_mesh_params={"num_gpus": ngpu})
 
 
 # ---- parity AT SIZE (GPU only; the reference runs on all host cores) --------------------------
