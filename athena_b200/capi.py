@@ -17,6 +17,7 @@ ARRAYS = dict(
     E_X3E=19, E3_X1F=20, E2_X1F=21, E1_X2F=22, E3_X2F=23, E2_X3F=24, E1_X3F=25, WGHT_X1F=26,
     WGHT_X2F=27, WGHT_X3F=28, S=29, S1=30, S2=31, R=32, SFLUX_X1=33, SFLUX_X2=34, SFLUX_X3=35)
 RS_HLLC, RS_HLLD, RS_ROE, RS_HLLE, RS_LLF = range(5)
+ARITH_STRICT, ARITH_FAST = 0, 1
 
 # (nvar, a1, a2, a3): host shape = (nvar, nc3+a3, nc2+a2, nc1+a1); nvar None = nscalars
 SHAPES = {}
@@ -39,7 +40,7 @@ SHAPES.update(FLUX_X1=(5, 1, 0, 0), FLUX_X2=(5, 0, 1, 0), FLUX_X3=(5, 0, 0, 1),
 class Config(C.Structure):
     _fields_ = [("nx1", C.c_int), ("nx2", C.c_int), ("nx3", C.c_int), ("nghost", C.c_int),
                 ("nblocks", C.c_int), ("mhd", C.c_int), ("nscalars", C.c_int),
-                ("rsolver", C.c_int), ("device", C.c_int), ("reserved", C.c_int),
+                ("rsolver", C.c_int), ("device", C.c_int), ("arith", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("sfloor", C.c_double)]
 

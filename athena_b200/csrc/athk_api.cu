@@ -11,6 +11,10 @@ ATHK_EXTERN_RS(athk::RS_HLLE, false)
 ATHK_EXTERN_RS(athk::RS_HLLE, true)
 ATHK_EXTERN_RS(athk::RS_LLF, false)
 ATHK_EXTERN_RS(athk::RS_LLF, true)
+#ifndef ATHK_EMULATE
+ATHK_EXTERN_RS_FAST(athk::RS_HLLC, false)   // athk_fast.cu (--fmad=true)
+ATHK_EXTERN_RS_FAST(athk::RS_HLLD, true)
+#endif
 
 static thread_local std::string g_last_error;
 
@@ -64,6 +68,10 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   if (!cfg->mhd && cfg->rsolver == ATHK_RS_HLLD)
     return fail(ATHK_ERR_ARG, "athk_create: rsolver HLLD needs mhd=1 (use HLLC, Roe, HLLE or LLF)");
   if (!(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
+  if (cfg->arith != ATHK_ARITH_STRICT && cfg->arith != ATHK_ARITH_FAST)
+    return fail(ATHK_ERR_ARG, "athk_create: arith must be ATHK_ARITH_STRICT (0) or ATHK_ARITH_FAST (1)");
+  if (cfg->arith == ATHK_ARITH_FAST && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_HLLD)
+    return fail(ATHK_ERR_ARG, "athk_create: the fast-arithmetic kernel set exists for HLLC / HLLD only");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(ATHK_ERR_NODEVICE, "athk_create: no CUDA device visible; libathk has no CPU path");
@@ -1126,10 +1134,18 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       a.mf_bstride = (idx_t)ns * g.sn;
     }
     switch (c->cfg.rsolver) {
-      case ATHK_RS_ROE: rc = mhd ? athk_sweeps_rs<RS_ROE, true>(c, order, a) : athk_sweeps_rs<RS_ROE, false>(c, order, a); break;
-      case ATHK_RS_HLLE: rc = mhd ? athk_sweeps_rs<RS_HLLE, true>(c, order, a) : athk_sweeps_rs<RS_HLLE, false>(c, order, a); break;
-      case ATHK_RS_LLF: rc = mhd ? athk_sweeps_rs<RS_LLF, true>(c, order, a) : athk_sweeps_rs<RS_LLF, false>(c, order, a); break;
-      default: rc = mhd ? athk_sweeps_rs<RS_HLLD, true>(c, order, a) : athk_sweeps_rs<RS_HLLC, false>(c, order, a); break;
+      case ATHK_RS_ROE: rc = mhd ? athk_sweeps_rs<RS_ROE, true, 0>(c, order, a) : athk_sweeps_rs<RS_ROE, false, 0>(c, order, a); break;
+      case ATHK_RS_HLLE: rc = mhd ? athk_sweeps_rs<RS_HLLE, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLE, false, 0>(c, order, a); break;
+      case ATHK_RS_LLF: rc = mhd ? athk_sweeps_rs<RS_LLF, true, 0>(c, order, a) : athk_sweeps_rs<RS_LLF, false, 0>(c, order, a); break;
+      default:
+#ifndef ATHK_EMULATE
+        if (c->cfg.arith == ATHK_ARITH_FAST) {   // contracted, approximately rounded kernel set (athk_fast.cu)
+          rc = mhd ? athk_sweeps_rs<RS_HLLD, true, 1>(c, order, a) : athk_sweeps_rs<RS_HLLC, false, 1>(c, order, a);
+          break;
+        }
+#endif
+        rc = mhd ? athk_sweeps_rs<RS_HLLD, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLC, false, 0>(c, order, a);
+        break;
     }
     if (rc) return rc;
     if (swap) { Real *t = c->u[0]; c->u[0] = c->u[1]; c->u[1] = t; }

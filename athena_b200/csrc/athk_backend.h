@@ -1,11 +1,8 @@
-// athk_backend.h -- thin device-runtime layer used by athk_api.cu.
-//
-// Product build (nvcc, sm_100a): CUDA runtime + one-thread-per-point kernels.
-// Test-harness build (g++ -DATHK_EMULATE, tests/emul/ only): the same operator bodies are run by
-// plain host loops so that index logic can be debugged in a container without a GPU.  The
-// harness library has a different soname (libathk_emul.so), is never built by
-// __graft_entry__.build() into the package and is never loaded by athena_b200; it is not a
-// fallback.
+// athk_backend.h -- thin device-runtime layer used by athk_api.cu: CUDA runtime + the generic
+// one-thread-per-point launchers (nvcc, sm_100a).
+// (The test harness under tests/emul/ compiles the operator bodies for the host with
+//  -DATHK_EMULATE and substitutes its own two headers for the CUDA parts of this file; that
+//  library is never built into the package nor loaded by it.)
 #ifndef ATHK_BACKEND_H_
 #define ATHK_BACKEND_H_
 
@@ -16,24 +13,9 @@
 #ifndef ATHK_EMULATE
 #include <cuda_runtime.h>
 #else
-// ---- minimal stand-ins for the CUDA runtime calls the API layer uses ----------------------
-typedef int cudaError_t;
-typedef void *cudaStream_t;
-typedef void *cudaEvent_t;
-#define cudaSuccess 0
-static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
-static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
-static inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
-enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
-static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int) { memcpy(d, s, n); return 0; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
-static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = 0; return 0; }
-static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
-static inline cudaError_t cudaGetLastError() { return 0; }
-static inline cudaError_t cudaSetDevice(int) { return 0; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 8; return 0; }   // (every "device" is the host)
+// test-harness build only: stand-ins for the CUDA runtime calls and plain-loop launchers live under
+// tests/emul/ (on the include path of that build alone)
+#include "athk_emul_runtime.h"
 #endif
 
 namespace athk {
@@ -173,40 +155,6 @@ static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &ou
   return cudaGetLastError();
 }
 
-// x1 sweep: one lane per face; within a (k, MeshBlock) plane the faces form a stream and warps
-// advance by 31 so that lane L+1 always holds the flux of the upper face of lane L's cell (one
-// redundant face per warp, 3%).
-#ifndef ATHK_X1_MINB
-#define ATHK_X1_MINB 6   // 80 registers, 24 warps/SM (measured best after the HLLD register diet)
-#endif
-template <class F>
-__global__ void __launch_bounds__(128, ATHK_X1_MINB)
-k_sweep_x1(const F f, const int kl, const int jl, const int nj, const int il, const int nif,
-           const unsigned nif_magic) {
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned total = (unsigned)(nj * nif);
-  const unsigned s = warp * 31 + lane;
-  const bool valid = s < total;
-  const int blk = (int)blockIdx.z, k = kl + (int)blockIdx.y;
-  int j = 0, fi = 0;
-  double fl[7];
-#pragma unroll
-  for (int v = 0; v < 7; ++v) fl[v] = 0.0;
-  if (valid) {
-    const unsigned row = __umulhi(s, nif_magic);
-    fi = (int)(s - row * (unsigned)nif);
-    j = jl + (int)row;
-    if (lane < 31 && fi + 1 < nif && f.cell_active(k, j, il + fi)) f.prefetch_cell(blk, k, j, il + fi);
-    f.compute(blk, k, j, il + fi, fl, lane < 31 || s == total - 1);
-  }
-  double fn[7];
-#pragma unroll
-  for (int v = 0; v < 5; ++v) fn[v] = __shfl_down_sync(0xffffffffu, fl[v], 1);
-  if (valid && lane < 31 && fi + 1 < nif && f.cell_active(k, j, il + fi))
-    f.store_d1(blk, k, j, il + fi, fl, fn);
-}
-
 // (launch_sweep_x1: athk_sweep_kernels.cuh)
 // (link, element) launcher for the variable-length remote messages
 template <class F>
@@ -222,37 +170,7 @@ static inline cudaError_t launch_links(cudaStream_t st, int nlinks, long long ma
   return cudaGetLastError();
 }
 #else
-template <class F>
-static inline cudaError_t launch_links(cudaStream_t, int nlinks, long long maxcount, const F &f) {
-  for (int l = 0; l < nlinks; ++l)
-    for (long long e = 0; e < maxcount; ++e) f(l, e);
-  return 0;
-}
-template <class F>
-static inline cudaError_t launch_points(cudaStream_t, int nb, const Range3 &r, const F &f,
-                                        int = 256) {
-  for (int b = 0; b < nb; ++b)
-    for (int k = r.kl; k <= r.ku; ++k)
-      for (int j = r.jl; j <= r.ju; ++j)
-        for (int i = r.il; i <= r.iu; ++i) f(b, k, j, i);
-  return 0;
-}
-template <class F>
-static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 &r, const F &f) {
-  return launch_points(st, nb, r, f);
-}
-template <int MINB, class F>
-static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range3 &r, const F &f) {
-  return launch_points(st, nb, r, f);
-}
-template <int MINB, class F>
-static inline cudaError_t launch_points_min(cudaStream_t st, int nb, const Range3 &r, const F &f, double *) {
-  return launch_points(st, nb, r, f);   // operator() folds cell by cell
-}
-template <class F>
-static inline cudaError_t launch_shell(cudaStream_t st, int nb, const Range3 &outer, const Range3 &, const F &f) {
-  return launch_points(st, nb, outer, f);   // the functors skip the points of the inner box themselves
-}
+#include "athk_emul_launch.h"
 #endif
 
 }  // namespace athk

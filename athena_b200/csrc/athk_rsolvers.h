@@ -600,8 +600,16 @@ ATHK_HD void mhd_riemann_m(M &m, const EosParams &eos, const Real wl[7], const R
 #ifndef ATHK_SL_MATH
 #define ATHK_SL_MATH 1
 #endif
-template <int RS, class F>
+// AR = 1: the fast-arithmetic kernel set (MathFast, no fallback); only instantiated by athk_fast.cu
+template <int RS, int AR = 0, class F>
 ATHK_HD void with_math(F &&body) {
+#if defined(__CUDA_ARCH__)
+  if (AR == 1) {
+    MathFast m;
+    body(m);
+    return;
+  }
+#endif
 #if ATHK_SL_MATH && defined(__CUDA_ARCH__)
   if (RS == RS_HLLC || RS == RS_HLLD) {
     MathSL m;

@@ -22,7 +22,7 @@ static inline SweepArgs make_sweep_args(athk_ctx *c, double dt, int breg, bool s
 template <int RS, bool MHD>
 int athk_flux3_rs(athk_ctx *c, int order, double dt, int breg);
 // fused path: x2 / x3 tile sweeps then the x1 sweep that integrates
-template <int RS, bool MHD>
+template <int RS, bool MHD, int AR>
 int athk_sweeps_rs(athk_ctx *c, int order, const SweepArgs &a);
 
 #endif  // ATHK_SWEEP_LAUNCH_H_

@@ -266,6 +266,14 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     msg << "### FATAL ERROR in Mesh constructor" << std::endl << "unknown Riemann solver '" << flux << "'";
     ATHENA_ERROR(msg);
   }
+  {   // <hydro> gpu_arithmetic = strict (default: the reference's arithmetic, bit for bit) | fast
+    const std::string ar = pin->GetOrAddString("hydro", "gpu_arithmetic", "strict");
+    if (ar != "strict" && ar != "fast") {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl << "<hydro> gpu_arithmetic must be strict or fast";
+      ATHENA_ERROR(msg);
+    }
+    cfg.arith = (ar == "fast") ? ATHK_ARITH_FAST : ATHK_ARITH_STRICT;
+  }
   const int dev0 = pin->GetOrAddInteger("mesh", "gpu_device", 0);
   gpu_device0_ = dev0;
   cfg.gamma = blocks_[0]->peos->GetGamma();

@@ -168,7 +168,7 @@ class Context:
     """One GPU context = the MeshBlocks of one rank."""
 
     def __init__(self, mesh, mhd, gamma, rsolver=None, nscalars=0, device=0, gids=None,
-                 rank_of=None, my_rank=0, lib=None, grav_acc=None):
+                 rank_of=None, my_rank=0, lib=None, grav_acc=None, arith=0):
         self.lib = lib if lib is not None else capi.load()
         self.mesh = mesh
         self.mhd = bool(mhd)
@@ -183,6 +183,7 @@ class Context:
         cfg.nscalars = nscalars
         cfg.rsolver = rsolver if rsolver is not None else (capi.RS_HLLD if mhd else capi.RS_HLLC)
         cfg.device = device
+        cfg.arith = arith      # capi.ARITH_STRICT (bit-exact, default) / capi.ARITH_FAST
         cfg.gamma = gamma
         cfg.dfloor = cfg.pfloor = cfg.sfloor = 0.0
         h = C.c_void_p()

@@ -39,6 +39,12 @@ enum athk_status {
 /* Riemann solvers: one is linked per build in the reference (Makefile.in:73) */
 enum athk_rsolver { ATHK_RS_HLLC = 0, ATHK_RS_HLLD = 1, ATHK_RS_ROE = 2, ATHK_RS_HLLE = 3, ATHK_RS_LLF = 4 };
 
+/* ATHK_ARITH_STRICT: the reference's double-precision arithmetic operation by operation (no FMA
+ * contraction, correctly rounded divisions and square roots): results identical to the CPU build.
+ * ATHK_ARITH_FAST (HLLC / HLLD): contraction on, divisions and square roots refined to ~1 ulp;
+ * agrees with the strict set to rounding (tests/test_fast_arith.py), not bit for bit. */
+enum athk_arith { ATHK_ARITH_STRICT = 0, ATHK_ARITH_FAST = 1 };
+
 /* what the reference fixes at configure time (configure.py) plus <hydro> runtime parameters */
 typedef struct athk_config {
   int nx1, nx2, nx3;   /* active zones per MeshBlock (<meshblock> nx1..3)          */
@@ -48,7 +54,7 @@ typedef struct athk_config {
   int nscalars;        /* NSCALARS                                                */
   int rsolver;         /* enum athk_rsolver                                       */
   int device;          /* CUDA device ordinal                                     */
-  int reserved;
+  int arith;           /* enum athk_arith: which kernel set the fused sweeps run             */
   double gamma;        /* <hydro> gamma                                           */
   double dfloor, pfloor, sfloor; /* floors; <=0 selects sqrt(1024*FLT_MIN) (eos.hpp:161) */
 } athk_config;

@@ -67,10 +67,10 @@ RSOLVERS = {"hllc": 0, "hlld": 1, "roe": 2, "hlle": 3, "llf": 4}   # enum athk_r
 
 
 def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, B=(None, None, None),
-                         flux=None, S=None, bcs=None, grav_acc=None):
+                         flux=None, S=None, bcs=None, grav_acc=None, arith=0):
     mesh = pyhost.UniformMesh(mesh_nx, block_nx, xmin, xmax, ng=ng, bcs=bcs)
     ctx = pyhost.Context(mesh, mhd, gamma, rsolver=RSOLVERS[flux] if flux else None, lib=lib,
-                         nscalars=0 if S is None else S.shape[0], grav_acc=grav_acc)
+                         nscalars=0 if S is None else S.shape[0], grav_acc=grav_acc, arith=arith)
     if S is not None:
         for lb, blk in enumerate(split_to_blocks(mesh, S)):
             ctx.upload("S", lb, blk["u"])
@@ -84,7 +84,7 @@ def make_ctx_from_global(lib, mesh_nx, block_nx, xmin, xmax, ng, mhd, gamma, U, 
     return ctx
 
 
-def run_golden_case(lib, name, block=None, fused=False):
+def run_golden_case(lib, name, block=None, fused=False, arith=0):
     """Run the driver from a golden fixture's initial state to its tlim. Returns
     (meta, z, ctx, integrator)."""
     meta, z = load_golden(name)
@@ -93,7 +93,7 @@ def run_golden_case(lib, name, block=None, fused=False):
     ctx = make_ctx_from_global(lib, meta["mesh"], block or meta["block"], meta["xmin"], meta["xmax"],
                                meta["ng"], mhd, meta["gamma"], z["u0"], B, flux=meta.get("flux"),
                                S=z["s0"] if meta.get("nscalars") else None, bcs=meta.get("bcs"),
-                               grav_acc=meta.get("grav_acc"))
+                               grav_acc=meta.get("grav_acc"), arith=arith)
     ti = pyhost.TimeIntegrator(ctx, meta["integrator"], meta["xorder"], meta["cfl"], fused=fused)
     ti.initialize(tlim=meta["tlim"])
     ti.run(meta["tlim"])
