@@ -69,6 +69,8 @@ PROTOTYPES = {
     "athk_upload": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "athk_download": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "athk_download_async": (C.c_int, [_P, C.c_int, C.c_int, _D]),
+    "athk_upload_all": (C.c_int, [_P, C.c_int, _D, C.c_int]),
+    "athk_download_all_async": (C.c_int, [_P, C.c_int, _D, C.c_int]),
     "athk_device_array": (C.c_int, [_P, C.c_int, C.POINTER(_P), _LL, _LL, _LL, _LL]),
     "athk_cons2prim": (C.c_int, [_P, C.c_int]),
     "athk_calculate_fluxes": (C.c_int, [_P, C.c_int, C.c_double, C.c_int]),

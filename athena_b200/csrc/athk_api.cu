@@ -403,6 +403,85 @@ static int copy_array(athk_ctx *c, int array, int lb, double *host, bool to_devi
   return ATHK_OK;
 }
 
+// all MeshBlocks of an array through ONE contiguous PCIe copy and one scatter / gather kernel
+#ifndef ATHK_EMULATE
+__global__ void __launch_bounds__(256) k_stage_copy_all(Real *dev, Real *dense, int nb, int nvar, int n1, int n2, int n3,
+                                                        int o1, int o2, int o3, idx_t sblk, idx_t sn, idx_t sk, idx_t sj,
+                                                        int to_device) {
+  const long long per = (long long)nvar * n3 * n2 * n1;
+  const long long total = per * nb;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(q % n1);
+    long long t = q / n1;
+    const int j = (int)(t % n2);
+    t /= n2;
+    const int k = (int)(t % n3);
+    t /= n3;
+    const int n = (int)(t % nvar);
+    const int b = (int)(t / nvar);
+    Real *d = dev + (idx_t)b * sblk + (idx_t)n * sn + (idx_t)(k + o3) * sk + (idx_t)(j + o2) * sj + (i + o1);
+    if (to_device) *d = dense[q];
+    else dense[q] = *d;
+  }
+}
+#endif
+
+static int copy_all(athk_ctx *c, int array, double *host, int active_only, bool to_device) {
+  if (!c || !host) return fail(ATHK_ERR_ARG, "upload_all/download_all: null argument");
+  cudaSetDevice(c->cfg.device);
+  ArrDesc d;
+  if (!describe(c, array, &d))
+    return fail(ATHK_ERR_ARG, "upload_all/download_all: array %d not allocated in this configuration", array);
+  const Grid &g = c->g;
+  const int n1 = (active_only ? g.nx1 : g.nc1) + d.a1, n2 = (active_only ? g.nx2 : g.nc2) + d.a2,
+            n3 = (active_only ? g.nx3 : g.nc3) + d.a3;
+  const int o = active_only ? g.ng : 0;
+  Real *dev0 = d.base + (idx_t)d.comp0 * g.sn;
+  const idx_t sblk = (idx_t)d.ncomp_total * g.sn;
+#ifndef ATHK_EMULATE
+  const size_t count = (size_t)g.nb * d.nvar * n3 * n2 * n1;
+  if (count > c->stage_count) {
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_count = 0;
+    CU(cudaMalloc((void **)&c->stage, count * sizeof(Real)));
+    c->stage_count = count;
+  }
+  const int blocks = 148 * 16;
+  if (to_device) {
+    CU(cudaMemcpyAsync(c->stage, host, count * sizeof(Real), cudaMemcpyHostToDevice, c->stream));
+    k_stage_copy_all<<<blocks, 256, 0, c->stream>>>(dev0, c->stage, g.nb, d.nvar, n1, n2, n3, o, o, o, sblk, g.sn, g.sk, g.sj, 1);
+    CU(cudaGetLastError());
+  } else {
+    k_stage_copy_all<<<blocks, 256, 0, c->stream>>>(dev0, c->stage, g.nb, d.nvar, n1, n2, n3, o, o, o, sblk, g.sn, g.sk, g.sj, 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, c->stage, count * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->launches++;
+#else
+  double *h = host;
+  for (int b = 0; b < g.nb; ++b)
+    for (int n = 0; n < d.nvar; ++n)
+      for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n2; ++j) {
+          Real *dr = dev0 + (idx_t)b * sblk + (idx_t)n * g.sn + gidx(g, k + o, j + o, o);
+          if (to_device) memcpy(dr, h, n1 * sizeof(Real));
+          else memcpy(h, dr, n1 * sizeof(Real));
+          h += n1;
+        }
+#endif
+  return ATHK_OK;
+}
+
+extern "C" int athk_upload_all(athk_ctx *c, int array, const double *host, int active_only) {
+  return copy_all(c, array, const_cast<double *>(host), active_only, true);
+}
+extern "C" int athk_download_all_async(athk_ctx *c, int array, double *host, int active_only) {
+  return copy_all(c, array, host, active_only, false);
+}
+
 extern "C" int athk_download_async(athk_ctx *c, int array, int lb, double *host) {
   return copy_array(c, array, lb, host, false, false);
 }

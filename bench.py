@@ -24,22 +24,26 @@ sys.path.insert(0, ROOT)
 
 B_ALG_MHD_VL2 = 320.0   # algorithmic bytes per zone-cycle, SURVEY.md section 8(d)
 F_ALG_MHD_VL2 = 3600.0  # algorithmic FP64 flops per zone-cycle (div/sqrt as 8-10), SURVEY.md section 8(d)
-FP64_PEAK_TFLOPS = 36.0  # 2 flops x 18.0 T FP64 FMA thread-instructions/s, measured on this pool's B200s
-#                          with tools/micro/fp64_peak.cu (profiles/README.md); not in MEASURED_PEAKS.json
+FP64_PEAK_TFLOPS = 36.0  # fallback: 2 flops x 18.0 T FP64 FMA thread-instructions/s (round-1 measurement)
+
+
+def fp64_peak():
+    """FP64 FMA peak of this pool's B200s from the committed raw output of tools/micro/fp64_peak.cu
+    (profiles/r2_fp64_peak.json: best rate over resident warps x ILP, with the clock record)."""
+    p = os.path.join(ROOT, "profiles", "r2_fp64_peak.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return 2.0 * float(d["best_t_thread_inst_per_s"]), "profiles/r2_fp64_peak.json (tools/micro/fp64_peak.cu)"
+    return FP64_PEAK_TFLOPS, "fallback: 18.0 T DFMA thread-instr/s (round 1)"
+
+
+def committed_traffic():
+    """Whole-cycle and per-kernel DRAM bytes from the committed ncu launch list of this bench
+    (profiles/r2_cycle_traffic.json, made by tools/ncu_launch_list.py --json)."""
+    p = os.path.join(ROOT, "profiles", "r2_cycle_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
 # algorithmic bytes per zone of ONE launch of the named kernel (DESIGN.md, kernel table)
 DOMINANT_ALG_BYTES = {"sweep_x1": 31 * 8, "sweep_x2": 16 * 8, "sweep_x3": 16 * 8}
-
-
-def ncu_traffic(kernel):
-    """dram bytes of the kernel from the committed ncu capture (profiles/ncu_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    for k, v in d.items():
-        if kernel.startswith(k):
-            return v
-    return None
 
 
 def measured_peaks():
@@ -159,7 +163,10 @@ def run_reference(args):
             "unit": "zone-cycles/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
             "ms_per_step": 1e3 * (n ** 3) * args.ref_cycles / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
+            "config": dict(workload_config(args), ref_mesh=n, ref_block=blk, ref_cycles_per_step=args.ref_cycles,
+                           note="same problem, physics and algorithm as the product arm; the CPU arm times a "
+                                "bounded sample on a %d^3 mesh in %d^3 MeshBlocks (zone-cycles/s is size-"
+                                "independent to first order, SURVEY 8d)" % (n, blk)),
             "cpu_baseline": {"value": v, "unit": "zone-cycles/s", "cores": threads,
                              "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
@@ -271,22 +278,27 @@ def run_ours(args):
         hnp["B_X1F"][lb] = ic["b1"]
         hnp["B_X2F"][lb] = ic["b2"]
         hnp["B_X3F"][lb] = ic["b3"]
-    state_bytes = sum(v.numel() * 8 for v in host.values())
-
     dp = C.POINTER(C.c_double)
+    for k in hnp:   # initial state: AthenaArray extents (ghost zones zero), one transfer per array
+        ctx.call("athk_upload_all", capi.ARRAYS[k], hnp[k].ctypes.data_as(dp), 0)
+    ctx.sync()
+    # e2e buffers: the ACTIVE zone of every MeshBlock (ghost zones are refreshed on the device),
+    # pinned; one PCIe transfer per array and direction
+    nx = args.block
+    ashp = {"U": (5, nx, nx, nx), "B_X1F": (nx, nx, nx + 1), "B_X2F": (nx, nx + 1, nx), "B_X3F": (nx + 1, nx, nx)}
+    ahost = {k: torch.empty((nb,) + ashp[k], dtype=torch.float64, pin_memory=True) for k in ashp}
+    anp = {k: v.numpy() for k, v in ahost.items()}
+    state_bytes = sum(v.numel() * 8 for v in ahost.values())
 
     def h2d():
-        for k in hnp:
-            for lb in range(nb):
-                ctx.call("athk_upload", capi.ARRAYS[k], lb, hnp[k][lb].ctypes.data_as(dp))
+        for k in anp:
+            ctx.call("athk_upload_all", capi.ARRAYS[k], anp[k].ctypes.data_as(dp), 1)
 
     def d2h():
-        for k in hnp:
-            for lb in range(nb):
-                ctx.call("athk_download_async", capi.ARRAYS[k], lb, hnp[k][lb].ctypes.data_as(dp))
+        for k in anp:
+            ctx.call("athk_download_all_async", capi.ARRAYS[k], anp[k].ctypes.data_as(dp), 1)
         ctx.sync()
 
-    h2d()
     reduce_min = multigpu.reduce_min_fn("cuda") if world > 1 else None
     ti = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=not args.unfused)
     ti.initialize(reduce_min=reduce_min)
@@ -379,6 +391,27 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, e2e_n)
     e2e_value = zones * e2e_n / (ms_e2e * 1e-3)
 
+    # ---- the fast-arithmetic kernel set on the same workload (reported next to `value`, which is
+    # the strict, bit-exact set): same state, a few cycles, device-timed -------------------------
+    fast = None
+    if world == 1 and not args.no_fast_arith:
+        ctx.close()
+        ctx = pyhost.Context(mesh, True, gamma, device=local_rank, gids=gids, rank_of=rank_of,
+                             my_rank=rank, lib=lib, arith=capi.ARITH_FAST)
+        stream = torch.cuda.ExternalStream(lib.athk_stream(ctx.h))
+        for k in hnp:
+            ctx.call("athk_upload_all", capi.ARRAYS[k], hnp[k].ctypes.data_as(dp), 0)
+        tif = pyhost.TimeIntegrator(ctx, "vl2", 2, 0.3, fused=True)
+        tif.initialize()
+        for _ in range(args.warmup):
+            tif.step()
+        nfast = max(3, min(args.steps, 10))
+        msf = timed(lambda: tif.step(), nfast)
+        fast = {"value": zones * nfast / (msf * 1e-3), "unit": "zone-cycles/s", "ms_per_step": msf / nfast,
+                "what": "athk_config.arith = ATHK_ARITH_FAST (FMA contraction, ~1 ulp divisions): agrees with "
+                        "the reference to rounding (tests/test_fast_arith.py), not bit for bit; `value` is the "
+                        "strict set"}
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         per_gpu_value = value / world
@@ -398,11 +431,18 @@ def run_ours(args):
             if alg:
                 gbs = alg * args.per_gpu ** 3 / (ms_launch * 1e-3) / 1e9
                 dominant.update({"achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak})
-            tr = ncu_traffic(top)
-            if tr:
-                dominant.update(tr)
+            ct = committed_traffic()
+            if ct:
+                for kname, kv in ct.get("kernels", {}).items():
+                    if top.startswith(kname):
+                        dominant.update(kv)
+        ct = committed_traffic()
+        fpeak, fpeak_src = fp64_peak()
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (dominant or {}).get("traffic"),
+                "frac": achieved / peak,
+                # DRAM bytes of ONE whole VL2 cycle (sum over every launch of the committed ncu list)
+                "traffic": ct["cycle_dram_bytes"] if ct else None,
+                "traffic_source": ct.get("source") if ct else None,
                 "kernel": "whole VL2 cycle = every kernel of the step; %g algorithmic B/zone-cycle "
                           "(SURVEY 8d). The sweeps are FP64-issue bound, not HBM bound: see "
                           "fp64_pipe_pct in profiles/ and DESIGN.md" % B_ALG_MHD_VL2,
@@ -411,9 +451,10 @@ def run_ours(args):
                     breakdown.items(), key=lambda kv: -kv[1]["ms_per_cycle"])}}
         # the second ceiling SURVEY 8(d) asks for: the fused stage is FP64-pipe bound, not HBM bound
         tflops = per_gpu_value * F_ALG_MHD_VL2 / 1e12
-        roof["fp64"] = {"alg_flops_per_zone_cycle": F_ALG_MHD_VL2, "achieved": tflops, "peak": FP64_PEAK_TFLOPS,
-                        "unit": "TFLOP/s", "frac": tflops / FP64_PEAK_TFLOPS,
-                        "peak_source": "tools/micro/fp64_peak.cu: 18.0 T DFMA thread-instr/s"}
+        roof["fp64"] = {"alg_flops_per_zone_cycle": F_ALG_MHD_VL2, "achieved": tflops, "peak": fpeak,
+                        "unit": "TFLOP/s", "frac": tflops / fpeak, "peak_source": fpeak_src}
+        if fast is not None:
+            roof["fast_arith"] = fast
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -428,8 +469,9 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "zone-cycles/s",
                         "h2d_bytes_per_step": state_bytes * world,
                         "d2h_bytes_per_step": state_bytes * world + 8 * mesh.nbtotal,
-                        "what": "per step: pinned-host (u,b) of every MeshBlock -> device, ghost "
-                                "exchange + W(U), one VL2 cycle, (u,b) + block dt -> host"},
+                        "what": "per step: pinned-host active zones of (u,b) of every MeshBlock -> device "
+                                "(one transfer per array), ghost exchange + W(U), one VL2 cycle, "
+                                "(u,b) + block dt -> host"},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "final_dt": ti.dt, "cycles_run": ti.ncycle}
         if parity is not None:
@@ -477,6 +519,7 @@ def main():
     ap.add_argument("--unfused", action="store_true", help="operator-per-kernel path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-fast-arith", action="store_true", help="skip the extra fast-arithmetic measurement (N=1)")
     ap.add_argument("--parity-case", default="mhd_linwave_vl2_plm_hlld",
                     help="golden fixture run split over the ranks before the timed region (N > 1)")
     ap.add_argument("--ref-mesh", type=int, default=128)

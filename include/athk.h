@@ -119,6 +119,14 @@ int athk_upload(athk_ctx *ctx, int array, int lb, const double *host);
 int athk_download(athk_ctx *ctx, int array, int lb, double *host);
 /* as athk_download but stream-ordered: host (pinned) is valid only after athk_sync */
 int athk_download_async(athk_ctx *ctx, int array, int lb, double *host);
+/* The same for ALL local MeshBlocks in one call and one PCIe transfer per array: host is
+ * [nblocks][nvar][n3][n2][n1] dense.  active_only = 0: AthenaArray extents including ghost zones
+ * (n = nc + a, as athk_upload); active_only = 1: the active zone only (n = nx + a; for a face
+ * field the nx+1 faces of its own direction) -- what a caller that refreshes the ghost zones
+ * afterwards (Mesh::Initialize) needs, 17 % fewer bytes for 64^3 blocks.  Stream-ordered; a
+ * download's host buffer is valid after athk_sync. */
+int athk_upload_all(athk_ctx *ctx, int array, const double *host, int active_only);
+int athk_download_all_async(athk_ctx *ctx, int array, double *host, int active_only);
 /* raw device pointer + padded strides of an array (for zero-copy consumers; elements) */
 int athk_device_array(athk_ctx *ctx, int array, void **dptr, long long *stride_block,
                       long long *stride_var, long long *stride_k, long long *stride_j);

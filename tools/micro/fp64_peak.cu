@@ -19,6 +19,9 @@ __global__ void k(double *out, double a, double b, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+static double g_best = 0.0;
+static int g_best_ilp = 0, g_best_warps = 0;
+
 template <int ILP>
 void run(int warps_per_sm) {
   const int iters = 8192 / ILP * 4;
@@ -37,7 +40,9 @@ void run(int warps_per_sm) {
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   double inst = (double)blocks * threads * iters * ILP;
-  printf("ILP=%d warps/SM=%2d  %6.2f T thread-inst/s\n", ILP, warps_per_sm, inst / ms * 1e-9);
+  const double rate = inst / ms * 1e-9;
+  printf("ILP=%d warps/SM=%2d  %6.2f T thread-inst/s\n", ILP, warps_per_sm, rate);
+  if (rate > g_best) { g_best = rate; g_best_ilp = ILP; g_best_warps = warps_per_sm; }
   cudaFree(out);
 }
 
@@ -48,5 +53,11 @@ int main() {
     run<4>(w);
     run<8>(w);
   }
+  // one JSON line for profiles/r2_fp64_peak.json (bench.py reads best_t_thread_inst_per_s)
+  cudaDeviceProp pr;
+  cudaGetDeviceProperties(&pr, 0);
+  printf("JSON {\"best_t_thread_inst_per_s\": %.3f, \"ilp\": %d, \"warps_per_sm\": %d, \"device\": \"%s\", "
+         "\"sms\": %d, \"what\": \"DFMA thread-instructions per second, independent chains (tools/micro/fp64_peak.cu)\"}\n",
+         g_best, g_best_ilp, g_best_warps, pr.name, pr.multiProcessorCount);
   return 0;
 }
