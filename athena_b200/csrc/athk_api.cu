@@ -101,6 +101,11 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
   c->dt_requested = c->dt_valid = false;
+  {   // planes per thread of the k-marching stencil kernels (development knobs: ATHK_KT_CORNER, ATHK_KT_CT)
+    const char *e1 = getenv("ATHK_KT_CORNER"), *e2 = getenv("ATHK_KT_CT");
+    c->kt_corner = e1 ? atoi(e1) : 13;
+    c->kt_ct = e2 ? atoi(e2) : 13;
+  }
   c->prof_on = false;
   c->coords_set = c->nbr_set = false;
   c->nremote = 0;
@@ -541,6 +546,13 @@ void athk_prof_end(athk_ctx *) {}
 #ifndef ATHK_STREAM_MINB
 #define ATHK_STREAM_MINB 8
 #endif
+// the k-marching stencil kernels hold a whole plane's operands in registers (corner E: ~45 doubles)
+#ifndef ATHK_CORNER_MINB
+#define ATHK_CORNER_MINB 4
+#endif
+#ifndef ATHK_CT_MINB
+#define ATHK_CT_MINB 6
+#endif
 
 static bool bad_reg(int r) { return r < 0 || r > 2; }
 
@@ -644,7 +656,7 @@ static int corner_e_part(athk_ctx *c, int part) {
   CornerEPoint f = {g, c->w, c->bcc, c->ef, c->wct, c->e};
   if (part == 1) LAUNCH_NAMED(c, "athk_compute_corner_e", launch_shell(c->stream, g.nb, r, rin, f));
   else LAUNCH_NAMED(c, "athk_compute_corner_e",
-                    launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 2 ? rin : r, f));
+                    launch_points_kcol<ATHK_CORNER_MINB>(c->stream, g.nb, part == 2 ? rin : r, c->kt_corner, f));
   return ATHK_OK;
 }
 
@@ -1264,7 +1276,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       fi.swap = swap; fi.b1_zero = (stage == 1) ? 1 : 0; fi.wa_mode = wa;
       Range3 r = {g.ks, g.ke + 1, g.js, g.je + 1, g.is, g.ie + 1};
       CTIntegratePoint f = {g, c->geo, c->e, fi};
-      LAUNCH_NAMED(c, "ct_integrate", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+      LAUNCH_NAMED(c, "ct_integrate", launch_points_kcol<ATHK_CT_MINB>(c->stream, g.nb, r, c->kt_ct, f));
       if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
     }
     return athk_remote_pack_ghosts(c, 0);

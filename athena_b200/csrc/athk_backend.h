@@ -61,6 +61,33 @@ static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range
   return cudaGetLastError();
 }
 
+// The same (j,i) plane decode, but every thread walks KT consecutive k planes (f.col): stencil
+// kernels whose points share operands with the plane below (corner E, CT) carry those in registers
+// instead of loading them again, and issue all loads of a plane before its first store.
+template <class F, int MINB>
+__global__ void __launch_bounds__(ATHK_KP_THREADS, MINB)
+k_points_kcol(const F f, const int kl, const int ku, const int kt, const int jl, const int nj, const int il,
+              const int ni, const unsigned ni_magic) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(nj * ni)) return;
+  const unsigned j = (ni == 1) ? t : __umulhi(t, ni_magic);
+  const unsigned i = t - j * (unsigned)ni;
+  const int k0 = kl + (int)blockIdx.y * kt;
+  const int k1 = (k0 + kt - 1 < ku) ? k0 + kt - 1 : ku;
+  f.col((int)blockIdx.z, k0, k1, jl + (int)j, il + (int)i);
+}
+
+template <int MINB, class F>
+static inline cudaError_t launch_points_kcol(cudaStream_t st, int nb, const Range3 &r, int kt, const F &f) {
+  const int threads = ATHK_KP_THREADS;
+  const int ni = r.iu - r.il + 1, nj = r.ju - r.jl + 1, nk = r.ku - r.kl + 1;
+  if (ni <= 0 || nj <= 0 || nk <= 0 || nb <= 0) return cudaSuccess;
+  if (kt < 1) kt = 1;
+  dim3 grid((unsigned)((nj * ni + threads - 1) / threads), (unsigned)((nk + kt - 1) / kt), (unsigned)nb);
+  k_points_kcol<F, MINB><<<grid, threads, 0, st>>>(f, r.kl, r.ku, kt, r.jl, nj, r.il, ni, magic_u32(ni));
+  return cudaGetLastError();
+}
+
 template <class F>
 static inline cudaError_t launch_points(cudaStream_t st, int nb, const Range3 &r, const F &f,
                                         int = ATHK_KP_THREADS) {

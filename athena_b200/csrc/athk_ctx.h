@@ -67,6 +67,7 @@ struct athk_ctx {
   idx_t max_ghost_count, max_emf_count;
   SlabTable *slab_tab;   // device
   bool dt_requested, dt_valid;   // NewBlockTimeStep fused into the next / last W(U)
+  int kt_corner, kt_ct;          // planes per thread of the k-marching corner-E / CT kernels
   // optional per-kernel timing with CUDA events on the launching stream (athk_profile)
   bool prof_on;
   struct ProfRec { const char *name; cudaEvent_t a, b; };

@@ -201,6 +201,79 @@ struct CornerEPoint {
     if (comp == 1) return v1 * b3 - v3 * b1;
     return v2 * b1 - v1 * b2;
   }
+  // k-marching form (launch_points_kcol): the edges (k0..k1, j, i).  Same expressions as
+  // operator() below; what plane k shares with plane k-1 (four cell-centred EMFs, two CT weights, two
+  // face EMFs) is carried in registers, and every load of a plane is issued before its three
+  // stores (the arrays are not declared restrict, so a store fences the loads behind it).
+  struct CellVB { Real v1, v2, v3, b1, b2, b3; };
+  ATHK_HD CellVB ldcell(const Real *wb, const Real *bc, idx_t c) const {
+    CellVB q;
+    q.v1 = wb[IVX * g.sn + c]; q.v2 = wb[IVY * g.sn + c]; q.v3 = wb[IVZ * g.sn + c];
+    q.b1 = bc[c]; q.b2 = bc[g.sn + c]; q.b3 = bc[2 * g.sn + c];
+    return q;
+  }
+  ATHK_HD static Real cc0(const CellVB &q) { return q.v3 * q.b2 - q.v2 * q.b3; }
+  ATHK_HD static Real cc1(const CellVB &q) { return q.v1 * q.b3 - q.v3 * q.b1; }
+  ATHK_HD static Real cc2(const CellVB &q) { return q.v2 * q.b1 - q.v1 * q.b2; }
+  ATHK_HD void col(int blk, int k0, int k1, int j, int i) const {
+    const idx_t si = 1, sj = g.sj, sk = g.sk;
+    const Real *wb = w + (idx_t)blk * 5 * g.sn;
+    const Real *bc = bcc + (idx_t)blk * 3 * g.sn;
+    const Real *efb = ef + (idx_t)blk * 6 * g.sn;
+    const Real *e3_x1f = efb, *e2_x1f = efb + g.sn, *e1_x2f = efb + 2 * g.sn,
+               *e3_x2f = efb + 3 * g.sn, *e2_x3f = efb + 4 * g.sn, *e1_x3f = efb + 5 * g.sn;
+    const Real *w_x1f = wct + (idx_t)blk * 3 * g.sn, *w_x2f = w_x1f + g.sn,
+               *w_x3f = w_x1f + 2 * g.sn;
+    Real *eb = e + (idx_t)blk * 3 * g.sn;
+    idx_t c = gidx(g, k0, j, i);
+    Real p_cc0, p_cc0j, p_cc1, p_cc1i, p_wx2, p_wx1, p_e1x2, p_e2x1;   // plane k-1
+    {
+      const CellVB a = ldcell(wb, bc, c - sk), aj = ldcell(wb, bc, c - sk - sj), ai = ldcell(wb, bc, c - sk - si);
+      p_cc0 = cc0(a); p_cc0j = cc0(aj); p_cc1 = cc1(a); p_cc1i = cc1(ai);
+      p_wx2 = w_x2f[c - sk]; p_wx1 = w_x1f[c - sk]; p_e1x2 = e1_x2f[c - sk]; p_e2x1 = e2_x1f[c - sk];
+    }
+    for (int k = k0; k <= k1; ++k, c += sk) {
+      const CellVB q = ldcell(wb, bc, c), qj = ldcell(wb, bc, c - sj), qi = ldcell(wb, bc, c - si);
+      const Real v1ji = wb[IVX * g.sn + c - sj - si], v2ji = wb[IVY * g.sn + c - sj - si];
+      const Real b1ji = bc[c - sj - si], b2ji = bc[g.sn + c - sj - si];
+      const Real wx1 = w_x1f[c], wx1j = w_x1f[c - sj], wx2 = w_x2f[c], wx2i = w_x2f[c - si];
+      const Real wx3 = w_x3f[c], wx3j = w_x3f[c - sj], wx3i = w_x3f[c - si];
+      const Real e1x2 = e1_x2f[c], e1x3 = e1_x3f[c], e1x3j = e1_x3f[c - sj];
+      const Real e2x1 = e2_x1f[c], e2x3 = e2_x3f[c], e2x3i = e2_x3f[c - si];
+      const Real e3x1 = e3_x1f[c], e3x1j = e3_x1f[c - sj], e3x2 = e3_x2f[c], e3x2i = e3_x2f[c - si];
+      const Real c0 = cc0(q), c0j = cc0(qj), c1 = cc1(q), c1i = cc1(qi);
+      Real r1, r2, r3;
+      {
+        const Real cc00 = c0, cc0m = c0j, ccm0 = p_cc0, ccmm = p_cc0j;
+        Real de1_l3 = (1.0 - p_wx2) * (e1x3 - ccm0) + (p_wx2) * (e1x3j - ccmm);
+        Real de1_r3 = (1.0 - wx2) * (e1x3 - cc00) + (wx2) * (e1x3j - cc0m);
+        Real de1_l2 = (1.0 - wx3j) * (e1x2 - cc0m) + (wx3j) * (p_e1x2 - ccmm);
+        Real de1_r2 = (1.0 - wx3) * (e1x2 - cc00) + (wx3) * (p_e1x2 - ccm0);
+        r1 = 0.25 * (de1_l3 + de1_r3 + de1_l2 + de1_r2 + p_e1x2 + e1x2 + e1x3j + e1x3);
+      }
+      {
+        const Real cc00 = c1, cc0m = c1i, ccm0 = p_cc1, ccmm = p_cc1i;
+        Real de2_l3 = (1.0 - p_wx1) * (e2x3 - ccm0) + (p_wx1) * (e2x3i - ccmm);
+        Real de2_r3 = (1.0 - wx1) * (e2x3 - cc00) + (wx1) * (e2x3i - cc0m);
+        Real de2_l1 = (1.0 - wx3i) * (e2x1 - cc0m) + (wx3i) * (p_e2x1 - ccmm);
+        Real de2_r1 = (1.0 - wx3) * (e2x1 - cc00) + (wx3) * (p_e2x1 - ccm0);
+        r2 = 0.25 * (de2_l3 + de2_r3 + de2_l1 + de2_r1 + e2x3i + e2x3 + p_e2x1 + e2x1);
+      }
+      {
+        const Real cc00 = cc2(q), cc0m = cc2(qi), ccm0 = cc2(qj), ccmm = v2ji * b1ji - v1ji * b2ji;
+        Real de3_l2 = (1.0 - wx1j) * (e3x2 - ccm0) + (wx1j) * (e3x2i - ccmm);
+        Real de3_r2 = (1.0 - wx1) * (e3x2 - cc00) + (wx1) * (e3x2i - cc0m);
+        Real de3_l1 = (1.0 - wx2i) * (e3x1 - cc0m) + (wx2i) * (e3x1j - ccmm);
+        Real de3_r1 = (1.0 - wx2) * (e3x1 - cc00) + (wx2) * (e3x1j - ccm0);
+        r3 = 0.25 * (de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3x2i + e3x2 + e3x1j + e3x1);
+      }
+      eb[c] = r1;
+      eb[g.sn + c] = r2;
+      eb[2 * g.sn + c] = r3;
+      p_cc0 = c0; p_cc0j = c0j; p_cc1 = c1; p_cc1i = c1i;
+      p_wx2 = wx2; p_wx1 = wx1; p_e1x2 = e1x2; p_e2x1 = e2x1;
+    }
+  }
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const idx_t c = gidx(g, k, j, i);
     const idx_t si = 1, sj = g.sj, sk = g.sk;
@@ -686,19 +759,33 @@ struct GhostFillCC {
     const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
     if (id == -1) return;   // physical boundary
     const idx_t dst = gidx(g, k, j, i);
+    // (source and destination are the same array: a store would fence the loads behind it, so the
+    //  components are loaded five at a time before any is stored)
+    const Real *src;
+    idx_t sstride;
     if (id >= 0) {
       if (mode == 2) return;
-      const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
-      for (int n = 0; n < nvar; ++n)
-        u[((idx_t)blk * nvar + n) * g.sn + dst] = u[((idx_t)id * nvar + n) * g.sn + src];
+      src = u + (idx_t)id * nvar * g.sn + gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
+      sstride = g.sn;
     } else if (REMOTE && mode != 1) {
       const int link = -id - 2;
       const int os = nbr_slot(o1, o2, o3);
       const Slab cc = rl.tab->slab[os][0];
       const idx_t e = ((idx_t)(k - cc.r3) * cc.d2 + (j - cc.r2)) * cc.d1 + (i - cc.r1);
-      const Real *src = rl.grbuf + rl.grecv[link] + rl.tab->sec[os][section] + e;
-      const idx_t ncc = cc.count();
-      for (int n = 0; n < nvar; ++n) u[((idx_t)blk * nvar + n) * g.sn + dst] = src[n * ncc];
+      src = rl.grbuf + rl.grecv[link] + rl.tab->sec[os][section] + e;
+      sstride = cc.count();
+    } else {
+      return;
+    }
+    Real *d = u + (idx_t)blk * nvar * g.sn + dst;
+    for (int n0 = 0; n0 < nvar; n0 += 5) {
+      Real v[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (n0 + q < nvar) v[q] = src[(idx_t)(n0 + q) * sstride];
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (n0 + q < nvar) d[(idx_t)(n0 + q) * g.sn] = v[q];
     }
   }
 };
@@ -714,6 +801,9 @@ struct GhostFillFC {
   RemoteLinks rl;
   int mode;         // as GhostFillCC
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
+    // (the three components are loaded before any is stored: same array on both sides)
+    const Real *src[3] = {nullptr, nullptr, nullptr};
+    const idx_t dst = gidx(g, k, j, i);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       // validity of (k,j,i) for component d
@@ -726,19 +816,24 @@ struct GhostFillFC {
       if (o1 == 0 && o2 == 0 && o3 == 0) continue;
       const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
       if (id == -1) continue;
-      const idx_t dst = gidx(g, k, j, i);
       if (id >= 0) {
         if (mode == 2) continue;
-        const idx_t src = gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
-        b[((idx_t)blk * 3 + d) * g.sn + dst] = b[((idx_t)id * 3 + d) * g.sn + src];
+        src[d] = b + ((idx_t)id * 3 + d) * g.sn + gidx(g, k - o3 * g.nx3, j - o2 * g.nx2, i - o1 * g.nx1);
       } else if (REMOTE && mode != 1) {
         const int link = -id - 2;
         const int os = nbr_slot(o1, o2, o3);
         const Slab f = rl.tab->slab[os][1 + d];
         const idx_t e = ((idx_t)(k - f.r3) * f.d2 + (j - f.r2)) * f.d1 + (i - f.r1);
-        b[((idx_t)blk * 3 + d) * g.sn + dst] = rl.grbuf[rl.grecv[link] + rl.tab->sec[os][1 + d] + e];
+        src[d] = rl.grbuf + rl.grecv[link] + rl.tab->sec[os][1 + d] + e;
       }
     }
+    Real v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (src[d]) v[d] = *src[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (src[d]) b[((idx_t)blk * 3 + d) * g.sn + dst] = v[d];
   }
 };
 

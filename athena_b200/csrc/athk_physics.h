@@ -396,10 +396,11 @@ ATHK_HD void hlld_flux_m(M &m, const EosParams &eos, const Real wl[7], const Rea
     ulst.by = ul.by;
     ulst.bz = ul.bz;
   } else {
-    Real tmp = m.fdiv(bxi * (sdl - sdml), (ul.d * sdl * sdml - bxsq));
+    const Real den = (ul.d * sdl * sdml - bxsq), rden = m.div_rcp(den);   // one divisor, two quotients
+    Real tmp = m.fdiv_by(bxi * (sdl - sdml), den, rden);
     ulst.my = ulst.d * (wl[IVY] - ul.by * tmp);
     ulst.mz = ulst.d * (wl[IVZ] - ul.bz * tmp);
-    tmp = m.div((ul.d * sqr(sdl) - bxsq), (ul.d * sdl * sdml - bxsq));
+    tmp = m.div_by((ul.d * sqr(sdl) - bxsq), den, rden);
     ulst.by = ul.by * tmp;
     ulst.bz = ul.bz * tmp;
   }
@@ -413,10 +414,11 @@ ATHK_HD void hlld_flux_m(M &m, const EosParams &eos, const Real wl[7], const Rea
     urst.by = ur.by;
     urst.bz = ur.bz;
   } else {
-    Real tmp = m.fdiv(bxi * (sdr - sdmr), (ur.d * sdr * sdmr - bxsq));
+    const Real den = (ur.d * sdr * sdmr - bxsq), rden = m.div_rcp(den);
+    Real tmp = m.fdiv_by(bxi * (sdr - sdmr), den, rden);
     urst.my = urst.d * (wr[IVY] - ur.by * tmp);
     urst.mz = urst.d * (wr[IVZ] - ur.bz * tmp);
-    tmp = m.div((ur.d * sqr(sdr) - bxsq), (ur.d * sdr * sdmr - bxsq));
+    tmp = m.div_by((ur.d * sqr(sdr) - bxsq), den, rden);
     urst.by = ur.by * tmp;
     urst.bz = ur.bz * tmp;
   }

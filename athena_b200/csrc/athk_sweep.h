@@ -156,8 +156,9 @@ ATHK_HD void integrate_var(const HydroIntegrate &h, idx_t o, Real dsum, Real vol
 
 // the same with the register values already loaded (un = h.u[o] where the stage reads it, u1n =
 // h.u1[o] likewise) and the division issued through a math policy
+// (rvol = m.div_rcp(vol): the five variables of a cell divide by the same volume)
 template <class M>
-ATHK_HD void integrate_var_m(M &m, const HydroIntegrate &h, idx_t o, Real dsum, Real vol, Real un, Real u1n) {
+ATHK_HD void integrate_var_m(M &m, const HydroIntegrate &h, idx_t o, Real dsum, Real vol, Real rvol, Real un, Real u1n) {
   if (h.delta != 0.0) u1n += h.delta * un;
   Real r;
   if (h.swap) {
@@ -172,7 +173,7 @@ ATHK_HD void integrate_var_m(M &m, const HydroIntegrate &h, idx_t o, Real dsum, 
     }
     if (h.delta != 0.0) h.u1_out[o] = u1n;
   }
-  r -= m.fdiv(h.wght * dsum, vol);   // (static regions: the divergence is exactly 0)
+  r -= m.fdiv_by(h.wght * dsum, vol, rvol);   // (static regions: the divergence is exactly 0)
   h.u_out[o] = r;
 }
 
@@ -409,6 +410,74 @@ struct CTIntegratePoint {
       if (fi.delta != 0.0) fi.b1_out[o] = b1n;
     }
     return r;
+  }
+  // the two register values averaged() reads, and the average from them (same expressions)
+  ATHK_HD void ld_regs(idx_t o, Real *bn, Real *b1n) const {
+    *bn = (fi.delta != 0.0 || !fi.swap) ? fi.b[o] : 0.0;
+    *b1n = fi.b1_zero ? 0.0 : fi.b1[o];
+  }
+  ATHK_HD Real averaged_from(idx_t o, Real bn, Real b1n) const {
+    if (fi.delta != 0.0) b1n += fi.delta * bn;
+    Real r;
+    if (fi.swap) {
+      r = b1n;
+    } else {
+      switch (fi.wa_mode) {
+        case 1: r = bn; r += fi.g2 * b1n; break;
+        case 3: r = fi.g2 * b1n; break;
+        case 5: r = fi.g1 * bn + fi.g2 * b1n; break;
+        case 6: r = bn; r *= fi.g1; break;
+        default: r = bn; break;
+      }
+      if (fi.delta != 0.0) fi.b1_out[o] = b1n;
+    }
+    return r;
+  }
+  // k-marching form (launch_points_kcol): faces (k0..k1, j, i); e1, e2 of plane k+1 become those of
+  // plane k at the next step, and every load of a plane is issued before its stores
+  ATHK_HD void col(int blk, int k0, int k1, int j, int i) const {
+    idx_t c = gidx(g, k0, j, i);
+    const Real *e1 = e + (idx_t)blk * 3 * g.sn, *e2 = e1 + g.sn, *e3 = e1 + 2 * g.sn;
+    const Real dx1 = geo.dxf[0][blk * geo.PG + i], dx2 = geo.dxf[1][blk * geo.PG + j];
+    const Real wght = fi.wght;
+    const bool jok = j <= g.je, iok = i <= g.ie;
+    Real e1c = e1[c], e2c = e2[c];
+    for (int k = k0; k <= k1; ++k, c += g.sk) {
+      const idx_t o = (idx_t)blk * 3 * g.sn + c;
+      const bool kok = k <= g.ke;
+      const bool f1 = kok && jok, f2 = kok && iok, f3 = jok && iok;
+      const Real dx3 = geo.dxf[2][blk * geo.PG + k];
+      // (all inside the padded box: k+1 <= nc3, j+1 <= nc2, i+1 <= nc1 for every launched point)
+      const Real e3c = e3[c], e3j = e3[c + g.sj], e3i = e3[c + 1];
+      const Real e1k = e1[c + g.sk], e1j = e1[c + g.sj], e2k = e2[c + g.sk], e2i = e2[c + 1];
+      Real bn1 = 0.0, b1n1 = 0.0, bn2 = 0.0, b1n2 = 0.0, bn3 = 0.0, b1n3 = 0.0;
+      if (f1) ld_regs(o, &bn1, &b1n1);
+      if (f2) ld_regs(o + g.sn, &bn2, &b1n2);
+      if (f3) ld_regs(o + 2 * g.sn, &bn3, &b1n3);
+      if (f1) {
+        const Real area = dx2 * dx3;
+        Real v = averaged_from(o, bn1, b1n1);
+        v -= (wght / area) * (dx3 * e3j - dx3 * e3c);
+        v += (wght / area) * (dx2 * e2k - dx2 * e2c);
+        fi.b_out[o] = v;
+      }
+      if (f2) {
+        const Real area = dx1 * dx3;
+        Real v = averaged_from(o + g.sn, bn2, b1n2);
+        v += (wght / area) * (dx3 * e3i - dx3 * e3c);
+        v -= (wght / area) * (dx1 * e1k - dx1 * e1c);
+        fi.b_out[o + g.sn] = v;
+      }
+      if (f3) {
+        const Real area = dx1 * dx2;
+        Real v = averaged_from(o + 2 * g.sn, bn3, b1n3);
+        v -= (wght / area) * (dx2 * e2i - dx2 * e2c);
+        v += (wght / area) * (dx1 * e1j - dx1 * e1c);
+        fi.b_out[o + 2 * g.sn] = v;
+      }
+      e1c = e1k;
+      e2c = e2k;
+    }
   }
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const idx_t c = gidx(g, k, j, i);

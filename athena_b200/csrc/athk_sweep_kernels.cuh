@@ -499,6 +499,7 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
       const Real area = dx2 * dx3, vol = dx1 * dx2 * dx3;   // Face1Area, cell volume
       const idx_t o = blk5 + c - 1;
       with_math<RS, AR>([&](auto &m) {
+        const Real rvol = m.div_rcp(vol);
 #pragma unroll
         for (int v = 0; v < 5; ++v) {   // DIR = 0: rotated index == variable index
           Real d = (area * fl[v] - area * fb[v]);
@@ -508,7 +509,7 @@ k_sweep_x1_rows(const SweepX1<ORDER, MHD, RS> f, const X1RowsGeom q) {
           const Real ur = slot[(10 + v) * 32];
           const Real un = needs_u ? ur : 0.0;
           const Real u1n = needs_u1 ? (needs_u ? h.u1[ov] : ur) : 0.0;
-          integrate_var_m(m, h, ov, d, vol, un, u1n);
+          integrate_var_m(m, h, ov, d, vol, rvol, un, u1n);
         }
       });
     }

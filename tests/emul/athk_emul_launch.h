@@ -24,6 +24,15 @@ static inline cudaError_t launch_points_occ(cudaStream_t st, int nb, const Range
   return launch_points(st, nb, r, f);
 }
 template <int MINB, class F>
+static inline cudaError_t launch_points_kcol(cudaStream_t, int nb, const Range3 &r, int kt, const F &f) {
+  if (kt < 1) kt = 1;
+  for (int b = 0; b < nb; ++b)
+    for (int k0 = r.kl; k0 <= r.ku; k0 += kt)
+      for (int j = r.jl; j <= r.ju; ++j)
+        for (int i = r.il; i <= r.iu; ++i) f.col(b, k0, (k0 + kt - 1 < r.ku) ? k0 + kt - 1 : r.ku, j, i);
+  return 0;
+}
+template <int MINB, class F>
 static inline cudaError_t launch_points_min(cudaStream_t st, int nb, const Range3 &r, const F &f, double *) {
   return launch_points(st, nb, r, f);   // operator() folds cell by cell
 }
