@@ -551,7 +551,7 @@ void athk_prof_end(athk_ctx *) {}
 #define ATHK_CORNER_MINB 4
 #endif
 #ifndef ATHK_CT_MINB
-#define ATHK_CT_MINB 6
+#define ATHK_CT_MINB 8
 #endif
 
 static bool bad_reg(int r) { return r < 0 || r > 2; }
@@ -714,10 +714,10 @@ static int weighted_ave(athk_ctx *c, Real *out, const Real *in1, const Real *in2
   if ((mode == 0 || mode == 2 || mode == 4) && !in2) return fail(ATHK_ERR_ARG, "weighted_ave: in2 register not allocated");
   if (mode != 6 && mode != 7 && !in1) return fail(ATHK_ERR_ARG, "weighted_ave: in1 register not allocated");
   Range3 r = {g.ks, g.ke + fc, g.js, g.je + fc, g.is, g.ie + fc};
-  if (mode == 7) {   // out = 0*out + 0: the reference zeroes through the (w0==0,w1==0) branch
-    WeightedAvePoint f = {g, nvar, fc, 6, 0.0, 0.0, 0.0, out, out, out};
-    // weighted_ave.cpp: with w0==0 and all other weights 0 nothing is executed in the reference
-    (void)f;
+  if (mode == 7) {   // all weights zero: the reference takes its `u_out = wght[1]*u_in1` branch
+                     // (weighted_ave.cpp:135-158), i.e. the register is zeroed
+    WeightedAvePoint f = {g, nvar, fc, 3, 0.0, 0.0, 0.0, out, in1 ? in1 : out, out};
+    LAUNCH(c, r, f);
     return ATHK_OK;
   }
   WeightedAvePoint f = {g, nvar, fc, mode, w[0], w[1], w[2], out, in1 ? in1 : out, in2 ? in2 : out};

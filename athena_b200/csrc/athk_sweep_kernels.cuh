@@ -89,8 +89,11 @@ struct RingStencil {
   __device__ __forceinline__ Real bx() const { return MHD ? row(0)[7 * NT] : 0.0; }
 };
 
+#ifndef ATHK_MARCH_MINB_DONOR
+#define ATHK_MARCH_MINB_DONOR ATHK_MARCH_MINB
+#endif
 template <int DIR, int ORDER, bool MHD, int RS, int AR>
-__global__ void __launch_bounds__(ATHK_MARCH_THREADS, ATHK_MARCH_MINB)
+__global__ void __launch_bounds__(ATHK_MARCH_THREADS, (ORDER == 1) ? ATHK_MARCH_MINB_DONOR : ATHK_MARCH_MINB)
 k_sweep_march(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il, const int ni) {
   constexpr int NT = ATHK_MARCH_THREADS, PD = ATHK_MARCH_PD;
   constexpr int LO = ORDER, HI = ORDER - 1;   // cells n-LO .. n+HI around face n

@@ -404,6 +404,17 @@ void Mesh::LoadRestart(const std::string &raw, std::size_t off) {
         << mesh_size.nx2 << "x" << mesh_size.nx3 << " mesh" << std::endl;
     ATHENA_ERROR(msg);
   }
+  // the MeshBlocks, their coordinates and the device geometry were built from the parsed <mesh>
+  // block: a restart whose -i / command line moved the domain would run on other coordinates than
+  // the file's (the reference builds its blocks from the file's RegionSize)
+  if (ms_file.x1min != mesh_size.x1min || ms_file.x1max != mesh_size.x1max || ms_file.x2min != mesh_size.x2min ||
+      ms_file.x2max != mesh_size.x2max || ms_file.x3min != mesh_size.x3min || ms_file.x3max != mesh_size.x3max ||
+      ms_file.x1rat != mesh_size.x1rat || ms_file.x2rat != mesh_size.x2rat || ms_file.x3rat != mesh_size.x3rat) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in Mesh::LoadRestart" << std::endl
+        << "the <mesh> limits / ratios in the parameters differ from the restart file's RegionSize" << std::endl;
+    ATHENA_ERROR(msg);
+  }
   mesh_size = ms_file;
   for (int n = 0; n < nbtotal; ++n) {
     LogicalLocation l;

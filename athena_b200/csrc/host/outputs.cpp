@@ -25,41 +25,56 @@ Outputs::Outputs(Mesh *pm, ParameterInput *pin) {
   for (const std::string &bn : names) {
     OutputParameters op;
     op.block_name = bn;
+    // the reference's order (outputs.cpp:206-223): next_time first, so that a disabled block carries
+    // it into every restart file too; then the two consistency checks
+    op.next_time = pin->GetOrAddReal(bn, "next_time", pm->time);
     op.dt = pin->GetOrAddReal(bn, "dt", 0.0);
     op.dcycle = pin->GetOrAddInteger(bn, "dcycle", 0);
-    if (op.dt <= 0.0 && op.dcycle <= 0) continue;   // outputs.cpp:209-223: disabled block
-    op.file_type = pin->GetString(bn, "file_type");
-    op.file_basename = basename;
-    op.next_time = pin->GetOrAddReal(bn, "next_time", pm->time);
+    if (op.dt == 0.0 && op.dcycle == 0) {
+      std::stringstream msg;
+      msg << "### FATAL ERROR in Outputs constructor" << std::endl
+          << "Either dt or dcycle must be specified in " << bn << std::endl;
+      ATHENA_ERROR(msg);
+    }
+    if (op.dt > 0.0 && op.dcycle > 0) {
+      std::stringstream msg;
+      msg << "### FATAL ERROR in Outputs constructor" << std::endl
+          << "dt and dcycle cannot be specified simultaneously in " << bn << std::endl;
+      ATHENA_ERROR(msg);
+    }
+    if (!(op.dt > 0.0 || op.dcycle > 0)) continue;   // disabled block (e.g. dt = -1)
     op.file_number = pin->GetOrAddInteger(bn, "file_number", 0);
-    op.data_format = pin->GetOrAddString(bn, "data_format", "%12.5e");
-    op.data_format.insert(0, " ");
+    op.file_basename = basename;
+    op.file_id = pin->GetOrAddString(bn, "id", "out" + bn.substr(6));   // default id = "outN"
+    op.file_type = pin->GetString(bn, "file_type");
     if (op.file_type != "hst" && op.file_type != "rst" && op.file_type != "tab" && op.file_type != "vtk") {
       std::cout << "### Warning in Outputs constructor" << std::endl
                 << "output type '" << op.file_type << "' of block <" << bn
                 << "> is not implemented by the B200 host (hst, rst, tab and vtk are); skipped" << std::endl;
       continue;
     }
-    if (op.file_type == "tab" || op.file_type == "vtk") {
-      op.file_id = pin->GetOrAddString(bn, "id", "out" + bn.substr(6));   // default id = "outN"
-      for (const char *key : {"x1_slice", "x2_slice", "x3_slice"})
-        if (pin->DoesParameterExist(bn, key)) {
-          std::stringstream msg;
-          msg << "### FATAL ERROR in Outputs constructor" << std::endl
-              << "'" << key << "' in block <" << bn << ">: sliced outputs are not implemented by the B200 host"
-              << std::endl;
-          ATHENA_ERROR(msg);
-        }
-      for (const char *key : {"x1_sum", "x2_sum", "x3_sum"})
-        if (pin->GetOrAddBoolean(bn, key, false)) {
-          std::stringstream msg;
-          msg << "### FATAL ERROR in Outputs constructor" << std::endl
-              << "'" << key << "' in block <" << bn << ">: summed outputs are not implemented by the B200 host"
-              << std::endl;
-          ATHENA_ERROR(msg);
-        }
-      op.include_ghost_zones = pin->GetOrAddBoolean(bn, "ghost_zones", false);
-      op.variable = pin->GetString(bn, "variable");
+    for (const char *key : {"x1_slice", "x2_slice", "x3_slice"})
+      if (pin->DoesParameterExist(bn, key)) {
+        std::stringstream msg;
+        msg << "### FATAL ERROR in Outputs constructor" << std::endl
+            << "'" << key << "' in block <" << bn << ">: sliced outputs are not implemented by the B200 host"
+            << std::endl;
+        ATHENA_ERROR(msg);
+      }
+    for (const char *key : {"x1_sum", "x2_sum", "x3_sum"})
+      if (pin->GetOrAddBoolean(bn, key, false)) {
+        std::stringstream msg;
+        msg << "### FATAL ERROR in Outputs constructor" << std::endl
+            << "'" << key << "' in block <" << bn << ">: summed outputs are not implemented by the B200 host"
+            << std::endl;
+        ATHENA_ERROR(msg);
+      }
+    op.include_ghost_zones = pin->GetOrAddBoolean(bn, "ghost_zones", false);
+    pin->GetOrAddBoolean(bn, "orbital_system", false);
+    if (op.file_type == "tab" || op.file_type == "vtk") op.variable = pin->GetString(bn, "variable");
+    if (op.file_type == "hst" || op.file_type == "tab") {
+      op.data_format = pin->GetOrAddString(bn, "data_format", "%12.5e");
+      op.data_format.insert(0, " ");
     }
     types_.push_back(op);
   }
@@ -130,7 +145,7 @@ void Outputs::WriteHistory(OutputParameters &op, Mesh *pm, ParameterInput *pin) 
     }
   }
   const std::string fname = op.file_basename + ".hst";
-  FILE *pfile = std::fopen(fname.c_str(), op.file_number == 0 ? "w" : "a");
+  FILE *pfile = std::fopen(fname.c_str(), "a");   // always appended to, as history.cpp:367
   if (pfile == nullptr) {
     std::stringstream msg;
     msg << "### FATAL ERROR in function [OutputType::HistoryFile]" << std::endl

@@ -601,6 +601,38 @@ def test_restart_resumes_bitwise_on_gpu(cuda_lib, case):
     check_restart(CUDA_BIN, case)
 
 
+def test_restart_with_a_disabled_output_block_and_output_block_checks(emul_binary):
+    """outputs.cpp:206-223: `next_time` is added to every <outputN> block before the enable check, so
+    a checkpoint written next to a disabled block (the common `dt = -1`) can be resumed; a block
+    with neither dt nor dcycle, or with both, is a fatal error."""
+    blocks = blast_blocks(n=32, blk=16, tlim=0.04)
+    blocks["output3"] = {"file_type": "vtk", "variable": "prim", "dt": -1}
+    dirs = []
+    try:
+        wd, r = run_host(emul_binary, blocks, "blast", True)
+        dirs.append(wd)
+        assert r.returncode == 0, r.stdout[-1500:]
+        assert not glob.glob(wd + "/*.vtk")
+        full = refrun.read_rst(glob.glob(wd + "/*.final.rst")[0])
+        mid = sorted(glob.glob(wd + "/*.00001.rst"))[0]
+        wd2 = tempfile.mkdtemp(prefix="athhost_")
+        dirs.append(wd2)
+        r = subprocess.run([emul_binary, "-r", mid, "-d", wd2, "--prob=blast", "-b"], capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        rst_equal(full, refrun.read_rst(glob.glob(wd2 + "/*.final.rst")[0]))
+        for bad, msg in (({"file_type": "vtk", "variable": "prim"}, "Either dt or dcycle must be specified"),
+                         ({"file_type": "vtk", "variable": "prim", "dt": 0.01, "dcycle": 3},
+                          "dt and dcycle cannot be specified simultaneously")):
+            blocks["output3"] = bad
+            wd3, r = run_host(emul_binary, blocks, "blast", True)
+            dirs.append(wd3)
+            assert r.returncode != 0 and msg in (r.stdout + r.stderr), (r.stdout + r.stderr)[-800:]
+    finally:
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+
+
 def test_wall_time_limit_and_signals_checkpoint_and_resume(emul_binary):
     """-t hh:mm:ss and SIGTERM (utils/signal_handler.cpp, main.cpp:568-618): the run stops after
     the current cycle, says why, and leaves a final restart dump; resuming from it ends on the
