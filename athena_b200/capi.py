@@ -91,6 +91,8 @@ PROTOTYPES = {
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_set_boundary_flags": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "athk_apply_physical_boundaries": (C.c_int, [_P]),
+    "athk_enroll_user_boundary": (C.c_int, [_P, C.c_int, _P, _P]),
+    "athk_set_boundary_time": (C.c_int, [_P, C.c_double, C.c_double]),
     "athk_set_block_floors": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),
     "athk_set_constant_acceleration": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
     "athk_add_source_terms": (C.c_int, [_P, C.c_double]),
@@ -111,6 +113,19 @@ PROTOTYPES = {
                                       C.c_longlong, C.POINTER(_P), _P]),
     "athk_p2p_timeouts": (C.c_longlong, [_P]),
 }
+
+
+class BvalArgs(C.Structure):
+    """struct athk_bval_args (include/athk.h)"""
+    _fields_ = [("lb", C.c_int), ("face", C.c_int), ("time", C.c_double), ("dt", C.c_double),
+                ("il", C.c_int), ("iu", C.c_int), ("jl", C.c_int), ("ju", C.c_int), ("kl", C.c_int), ("ku", C.c_int),
+                ("ngh", C.c_int),
+                ("w", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p), ("r", C.c_void_p),
+                ("stride_j", C.c_longlong), ("stride_k", C.c_longlong), ("stride_n", C.c_longlong),
+                ("nscalars", C.c_int), ("stream", C.c_void_p)]
+
+
+BVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(BvalArgs))   # athk_bval_fn
 
 
 def bind(cdll):

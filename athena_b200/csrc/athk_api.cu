@@ -986,8 +986,8 @@ extern "C" int athk_set_boundary_flags(athk_ctx *c, int lb, const int flags[6]) 
   if (!c || !flags) return fail(ATHK_ERR_ARG, "set_boundary_flags: null argument");
   if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "set_boundary_flags: block %d out of range", lb);
   for (int f = 0; f < 6; ++f) {
-    if (flags[f] < ATHK_BC_NONE || flags[f] > ATHK_BC_OUTFLOW)
-      return fail(ATHK_ERR_ARG, "set_boundary_flags: face %d has unknown flag %d (reflecting, outflow or none)",
+    if (flags[f] < ATHK_BC_NONE || flags[f] > ATHK_BC_USER)
+      return fail(ATHK_ERR_ARG, "set_boundary_flags: face %d has unknown flag %d (reflecting, outflow, user or none)",
                   f, flags[f]);
     c->h_bcflags[(size_t)lb * 6 + f] = flags[f];
   }
@@ -1006,6 +1006,41 @@ static int launch_bc_face(athk_ctx *c, int side) {
   const int mhd = c->cfg.mhd, ns = c->cfg.nscalars;
   PhysBCFillPoint<DIR> f1 = {g, side, c->bcflags, mhd, ns, c->w, mhd ? c->b[0] : nullptr, c->r};
   LAUNCH_NAMED(c, "apply_physical_boundaries", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f1));
+  // user-enrolled functions of this face (bvals.cpp:673-676), block after block
+  const int face = 2 * DIR + side;
+  for (int lb = 0; lb < g.nb; ++lb) {
+    const int *fl = &c->h_bcflags[(size_t)lb * 6];
+    if (fl[face] != ATHK_BC_USER) continue;
+    if (!c->user_bc[face])   // bvals.cpp:349-356
+      return fail(ATHK_ERR_STATE, "A user-defined boundary is specified but the actual boundary function "
+                                  "is not enrolled in direction %d (athk_enroll_user_boundary)", face);
+    athk_bval_args a;
+    a.lb = lb; a.face = face; a.time = c->bc_time; a.dt = c->bc_dt; a.ngh = g.ng;
+    a.il = g.is; a.iu = g.ie; a.jl = g.js; a.ju = g.je; a.kl = g.ks; a.ku = g.ke;
+    // transverse limits of bvals.cpp:457-470 and of the x2 / x3 passes
+    if (DIR == 0) {
+      if (fl[2] == ATHK_BC_NONE) a.jl -= g.ng;
+      if (fl[3] == ATHK_BC_NONE) a.ju += g.ng;
+    } else {
+      a.il -= g.ng; a.iu += g.ng;
+    }
+    if (DIR != 2) {
+      if (fl[4] == ATHK_BC_NONE) a.kl -= g.ng;
+      if (fl[5] == ATHK_BC_NONE) a.ku += g.ng;
+    } else {
+      a.jl = g.js - g.ng; a.ju = g.je + g.ng;
+    }
+    a.w = c->w + (idx_t)lb * 5 * g.sn;
+    a.b1 = mhd ? c->b[0] + (idx_t)lb * 3 * g.sn : nullptr;
+    a.b2 = mhd ? a.b1 + g.sn : nullptr;
+    a.b3 = mhd ? a.b1 + 2 * g.sn : nullptr;
+    a.r = ns ? c->r + (idx_t)lb * ns * g.sn : nullptr;
+    a.stride_j = g.sj; a.stride_k = g.sk; a.stride_n = g.sn;
+    a.nscalars = ns;
+    a.stream = (void *)c->stream;
+    if (c->user_bc[face](c->user_bc_data[face], &a) != 0)
+      return fail(ATHK_ERR_STATE, "user boundary function of face %d failed on block %d", face, lb);
+  }
   Range3 rc = {0, g.nc3 - 1, 0, g.nc2 - 1, 0, g.nc1 - 1};
   if (DIR == 0) { rc.il = 1; rc.iu = g.ng; }
   if (DIR == 1) { rc.jl = 1; rc.ju = g.ng; }
@@ -1013,6 +1048,21 @@ static int launch_bc_face(athk_ctx *c, int side) {
   PhysBCConsPoint<DIR> f2 = {g, side, c->bcflags, c->eos, mhd, ns, c->w, mhd ? c->b[0] : nullptr, c->r,
                              c->bcc, c->u[0], ns ? c->s[0] : nullptr};
   LAUNCH_NAMED(c, "apply_physical_boundaries", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, rc, f2));
+  return ATHK_OK;
+}
+
+extern "C" int athk_enroll_user_boundary(athk_ctx *c, int face, athk_bval_fn fn, void *user) {
+  if (!c) return fail(ATHK_ERR_ARG, "enroll_user_boundary: null context");
+  if (face < 0 || face > 5) return fail(ATHK_ERR_ARG, "enroll_user_boundary: face %d (0..5)", face);
+  c->user_bc[face] = fn;
+  c->user_bc_data[face] = user;
+  return ATHK_OK;
+}
+
+extern "C" int athk_set_boundary_time(athk_ctx *c, double time, double dt) {
+  if (!c) return fail(ATHK_ERR_ARG, "set_boundary_time: null context");
+  c->bc_time = time;
+  c->bc_dt = dt;
   return ATHK_OK;
 }
 

@@ -17,7 +17,7 @@
 
 namespace athk {
 
-enum { BC_NONE = 0, BC_REFLECT = 1, BC_OUTFLOW = 2 };   // == enum athk_bc
+enum { BC_NONE = 0, BC_REFLECT = 1, BC_OUTFLOW = 2, BC_USER = 3 };   // == enum athk_bc
 
 // transverse limits of the pass over faces of direction DIR for one block (bvals.cpp:457-470,560)
 template <int DIR>
@@ -53,7 +53,7 @@ struct PhysBCFillPoint {
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const int *fl = flags + blk * 6;
     const int bc = fl[2 * DIR + side];
-    if (bc == BC_NONE) return;
+    if (bc == BC_NONE || bc == BC_USER) return;   // (user faces are filled by the enrolled function)
     const int m = (DIR == 0) ? i : (DIR == 1 ? j : k);
     const int ta = (DIR == 0) ? j : i;                  // first transverse coordinate
     const int tb = (DIR == 2) ? j : k;                  // second

@@ -83,6 +83,9 @@ struct athk_ctx {
   int *bcflags;                 // device
   bool bc_dirty;
   int bc_any[6];                // does any local block have a physical boundary on face f
+  athk_bval_fn user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // enrolled BValFuncs
+  void *user_bc_data[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double bc_time = 0.0, bc_dt = 0.0;
   double gacc[3] = {0.0, 0.0, 0.0};   // HydroSourceTerms: <hydro> grav_acc1/2/3 (0 = none)
   std::vector<Real> h_floors;         // per-block (dfloor, pfloor, sfloor); empty = uniform
   Real *d_floors = nullptr;

@@ -213,6 +213,12 @@ class MeshBlock {   // mesh/mesh.hpp:75-200
   Real new_block_dt_;
 };
 
+// athena.hpp:98-100, 214-217: user-enrolled boundary functions act on the HOST mirrors of the
+// primitives and of the face field (see Mesh::EnrollUserBoundaryFunction)
+enum BoundaryFace { undef = -1, inner_x1 = 0, outer_x1 = 1, inner_x2 = 2, outer_x2 = 3, inner_x3 = 4, outer_x3 = 5 };
+using BValFunc = void (*)(MeshBlock *pmb, Coordinates *pco, AthenaArray<Real> &prim, FaceField &b, Real time, Real dt,
+                          int is, int ie, int js, int je, int ks, int ke, int ngh);
+
 typedef void (*PgenFn)(MeshBlock *pmb, ParameterInput *pin);
 typedef void (*MeshHookFn)(Mesh *pm, ParameterInput *pin);
 struct ProblemGeneratorEntry {
@@ -263,6 +269,13 @@ class Mesh {   // mesh/mesh.hpp:206-447
   struct UserHistory { HistoryFn fn; std::string name; int op; /*0 sum,1 max,2 min*/ };
   std::vector<UserHistory> user_history;
   void EnrollUserHistoryOutput(HistoryFn fn, const char *name, int op) { user_history.push_back({fn, name, op}); }
+  // Mesh::EnrollUserBoundaryFunction (mesh.cpp:1288-1309).  The function runs on the host, like the
+  // reference's: at PHY_BVAL the block's primitives (and face field) are brought to the host
+  // mirrors, handed to it, and its ghost zones sent back (a CUDA boundary function can instead be
+  // enrolled with athk_enroll_user_boundary and stays on the device).
+  void EnrollUserBoundaryFunction(BoundaryFace face, BValFunc my_func);
+  BValFunc BoundaryFunction_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  MeshBlock *FindLocalBlock(int rank, int lid);
 
  private:
   std::vector<MeshBlock *> blocks_;
@@ -280,7 +293,7 @@ class TimeIntegratorTaskList {
   std::string integrator;
   int nstages;
   Real cfl_limit;
-  struct IntegratorWeight { Real delta, gamma_1, gamma_2, gamma_3, beta; };
+  struct IntegratorWeight { Real delta, gamma_1, gamma_2, gamma_3, beta, ebeta; };
   IntegratorWeight stage_wghts[6];
   int xorder;
 };

@@ -167,9 +167,9 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   }
   for (int n = 0; n < 6; ++n) {
     if (mesh_bcs[n] != BoundaryFlag::periodic && mesh_bcs[n] != BoundaryFlag::reflect &&
-        mesh_bcs[n] != BoundaryFlag::outflow) {
+        mesh_bcs[n] != BoundaryFlag::outflow && mesh_bcs[n] != BoundaryFlag::user) {
       msg << "### FATAL ERROR in Mesh constructor" << std::endl
-          << "The B200 path implements periodic, reflecting and outflow mesh boundaries (" << bn[n] << ")";
+          << "The B200 path implements periodic, reflecting, outflow and user mesh boundaries (" << bn[n] << ")";
       ATHENA_ERROR(msg);
     }
   }
@@ -325,13 +325,79 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
         const BoundaryFlag bf = mesh_bcs[2 * d + side];
         const bool edge = side ? (lx[d] == nr[d] - 1) : (lx[d] == 0);
         fl[2 * d + side] = (!edge || bf == BoundaryFlag::periodic) ? ATHK_BC_NONE
-                           : (bf == BoundaryFlag::reflect ? ATHK_BC_REFLECT : ATHK_BC_OUTFLOW);
+                           : (bf == BoundaryFlag::reflect ? ATHK_BC_REFLECT
+                                                          : (bf == BoundaryFlag::user ? ATHK_BC_USER : ATHK_BC_OUTFLOW));
         any = any || fl[2 * d + side] != ATHK_BC_NONE;
       }
     if (any) AthkCheck(athk_set_boundary_flags(ctx_of(blocks_[n]), blocks_[n]->lid, fl),
                        "Mesh constructor (athk_set_boundary_flags)");
   }
   if (pgen->init_user_mesh_data) pgen->init_user_mesh_data(this, pin);   // mesh.cpp:601
+  for (int n = 0; n < 6; ++n)   // bvals.cpp:349-356
+    if (mesh_bcs[n] == BoundaryFlag::user && BoundaryFunction_[n] == nullptr) {
+      msg << "### FATAL ERROR in BoundaryValues constructor" << std::endl
+          << "A user-defined boundary is specified but the actual boundary function "
+          << "is not enrolled in direction " << n << " (in [0,6])." << std::endl;
+      ATHENA_ERROR(msg);
+    }
+}
+
+MeshBlock *Mesh::FindLocalBlock(int rank, int lid) {
+  for (MeshBlock *p : blocks_)
+    if (p->rank == rank && p->lid == lid) return p;
+  return nullptr;
+}
+
+// The library's side of a user boundary function is a host callback that enqueues device work
+// (athk_enroll_user_boundary); a BValFunc written for the reference works on host arrays, so this
+// adapter brings the block's primitives / face field to the host mirrors, runs it, and sends them
+// back.  Synchronous and per block: the cost of keeping the reference's host-side function as is.
+namespace {
+struct UserBCSlot { Mesh *pm; int rank; };
+int HostBValAdapter(void *user, const athk_bval_args *a) {
+  UserBCSlot *slot = static_cast<UserBCSlot *>(user);
+  Mesh *pm = slot->pm;
+  MeshBlock *pmb = pm->FindLocalBlock(slot->rank, a->lb);
+  if (pmb == nullptr || pm->BoundaryFunction_[a->face] == nullptr) return 1;
+  athk_ctx *c = pm->ctx[slot->rank];
+  if (athk_download(c, ATHK_W, a->lb, pmb->phydro->w.data())) return 1;
+  if (MAGNETIC_FIELDS_ENABLED) {
+    if (athk_download(c, ATHK_B_X1F, a->lb, pmb->pfield->b.x1f.data())) return 1;
+    if (athk_download(c, ATHK_B_X2F, a->lb, pmb->pfield->b.x2f.data())) return 1;
+    if (athk_download(c, ATHK_B_X3F, a->lb, pmb->pfield->b.x3f.data())) return 1;
+  }
+  pm->BoundaryFunction_[a->face](pmb, pmb->pcoord, pmb->phydro->w, pmb->pfield->b, a->time, a->dt, a->il, a->iu,
+                                 a->jl, a->ju, a->kl, a->ku, a->ngh);
+  if (athk_upload(c, ATHK_W, a->lb, pmb->phydro->w.data())) return 1;
+  if (MAGNETIC_FIELDS_ENABLED) {
+    if (athk_upload(c, ATHK_B_X1F, a->lb, pmb->pfield->b.x1f.data())) return 1;
+    if (athk_upload(c, ATHK_B_X2F, a->lb, pmb->pfield->b.x2f.data())) return 1;
+    if (athk_upload(c, ATHK_B_X3F, a->lb, pmb->pfield->b.x3f.data())) return 1;
+  }
+  return 0;
+}
+}  // namespace
+
+void Mesh::EnrollUserBoundaryFunction(BoundaryFace dir, BValFunc my_bc) {
+  std::stringstream msg;
+  if (dir < 0 || dir > 5) {
+    msg << "### FATAL ERROR in EnrollUserBoundaryFunction" << std::endl
+        << "dirName = " << dir << " not valid" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  if (mesh_bcs[dir] != BoundaryFlag::user) {
+    msg << "### FATAL ERROR in EnrollUserBoundaryFunction" << std::endl
+        << "The boundary condition flag must be set to the string 'user' in the "
+        << " <mesh> block in the input file to use user-enrolled BCs" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  BoundaryFunction_[dir] = my_bc;
+  static std::vector<UserBCSlot *> slots;   // live as long as the process (one Mesh per run)
+  for (int r = 0; r < ngpu; ++r) {
+    UserBCSlot *sl = new UserBCSlot{this, r};
+    slots.push_back(sl);
+    AthkCheck(athk_enroll_user_boundary(ctx[r], dir, HostBValAdapter, sl), "Mesh::EnrollUserBoundaryFunction");
+  }
 }
 
 Mesh::~Mesh() {
@@ -369,6 +435,7 @@ void Mesh::Initialize(ParameterInput *pin) {
   for (athk_ctx *a : ctx) AthkCheck(athk_sync(a), "Mesh::Initialize");
   ExchangeGhosts();
   for (athk_ctx *a : ctx) AthkCheck(athk_cons2prim(a, 0), "Mesh::Initialize");
+  for (athk_ctx *a : ctx) AthkCheck(athk_set_boundary_time(a, time, 0.0), "Mesh::Initialize");
   for (athk_ctx *a : ctx) AthkCheck(athk_apply_physical_boundaries(a), "Mesh::Initialize");   // mesh.cpp:1886-1891
   NewTimeStep();
 }

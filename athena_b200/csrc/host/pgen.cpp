@@ -13,6 +13,7 @@
 //   shock_tube    src/pgen/shock_tube.cpp:305-575 (ICs), :46-270 (errors: Sod, Ryu-Jones 2a)
 //   cpaw          src/pgen/cpaw.cpp:55-390
 //   field_loop    src/pgen/field_loop.cpp:52-262 (iprob 1-5)
+//   jet           src/pgen/jet.cpp:46-235 (user-enrolled inner-x1 boundary function)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -1064,6 +1065,103 @@ static void FieldLoopGenerator(MeshBlock *pmb, ParameterInput *pin) {
 }
 
 //========================================================================================
+// jet (src/pgen/jet.cpp:46-235): uniform ambient medium, jet injected through a user-enrolled
+// inner-x1 boundary function
+namespace jet {
+Real d_amb, p_amb, vx_amb, vy_amb, vz_amb, bx_amb, by_amb, bz_amb;
+Real r_jet, d_jet, p_jet, vx_jet, vy_jet, vz_jet, bx_jet, by_jet, bz_jet;
+Real x2_0, x3_0;
+
+void JetInnerX1(MeshBlock *pmb, Coordinates *pco, AthenaArray<Real> &prim, FaceField &b, Real time, Real dt, int il,
+                int iu, int jl, int ju, int kl, int ku, int ngh) {
+  auto inside = [&](int k, int j) {
+    const Real rad = std::sqrt(SQR(pco->x2v(j) - x2_0) + SQR(pco->x3v(k) - x3_0));
+    return rad <= r_jet;
+  };
+  for (int k = kl; k <= ku; ++k)
+    for (int j = jl; j <= ju; ++j)
+      for (int i = 1; i <= ngh; ++i) {
+        if (inside(k, j)) {
+          prim(IDN, k, j, il - i) = d_jet;
+          prim(IVX, k, j, il - i) = vx_jet;
+          prim(IVY, k, j, il - i) = vy_jet;
+          prim(IVZ, k, j, il - i) = vz_jet;
+          prim(IPR, k, j, il - i) = p_jet;
+        } else {
+          for (int n = 0; n < NHYDRO; ++n) prim(n, k, j, il - i) = prim(n, k, j, il);
+        }
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    for (int k = kl; k <= ku; ++k)
+      for (int j = jl; j <= ju; ++j)
+        for (int i = 1; i <= ngh; ++i) b.x1f(k, j, il - i) = inside(k, j) ? bx_jet : b.x1f(k, j, il);
+    for (int k = kl; k <= ku; ++k)
+      for (int j = jl; j <= ju + 1; ++j)
+        for (int i = 1; i <= ngh; ++i) b.x2f(k, j, il - i) = inside(k, j) ? by_jet : b.x2f(k, j, il);
+    for (int k = kl; k <= ku + 1; ++k)
+      for (int j = jl; j <= ju; ++j)
+        for (int i = 1; i <= ngh; ++i) b.x3f(k, j, il - i) = inside(k, j) ? bz_jet : b.x3f(k, j, il);
+  }
+}
+
+void JetInit(Mesh *pm, ParameterInput *pin) {
+  d_amb = pin->GetReal("problem", "d");
+  p_amb = pin->GetReal("problem", "p");
+  vx_amb = pin->GetReal("problem", "vx");
+  vy_amb = pin->GetReal("problem", "vy");
+  vz_amb = pin->GetReal("problem", "vz");
+  if (MAGNETIC_FIELDS_ENABLED) {
+    bx_amb = pin->GetReal("problem", "bx");
+    by_amb = pin->GetReal("problem", "by");
+    bz_amb = pin->GetReal("problem", "bz");
+  }
+  d_jet = pin->GetReal("problem", "djet");
+  p_jet = pin->GetReal("problem", "pjet");
+  vx_jet = pin->GetReal("problem", "vxjet");
+  vy_jet = pin->GetReal("problem", "vyjet");
+  vz_jet = pin->GetReal("problem", "vzjet");
+  if (MAGNETIC_FIELDS_ENABLED) {
+    bx_jet = pin->GetReal("problem", "bxjet");
+    by_jet = pin->GetReal("problem", "byjet");
+    bz_jet = pin->GetReal("problem", "bzjet");
+  }
+  r_jet = pin->GetReal("problem", "rjet");
+  x2_0 = 0.5 * (pm->mesh_size.x2max + pm->mesh_size.x2min);
+  x3_0 = 0.5 * (pm->mesh_size.x3max + pm->mesh_size.x3min);
+  pm->EnrollUserBoundaryFunction(BoundaryFace::inner_x1, JetInnerX1);
+}
+
+void JetGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = pmb->ks; k <= pmb->ke; ++k)
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) {
+        u(IDN, k, j, i) = d_amb;
+        u(IM1, k, j, i) = d_amb * vx_amb;
+        u(IM2, k, j, i) = d_amb * vy_amb;
+        u(IM3, k, j, i) = d_amb * vz_amb;
+        u(IEN, k, j, i) = p_amb / gm1 + 0.5 * d_amb * (SQR(vx_amb) + SQR(vy_amb) + SQR(vz_amb));
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    FaceField &b = pmb->pfield->b;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie + 1; ++i) b.x1f(k, j, i) = bx_amb;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je + 1; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x2f(k, j, i) = by_amb;
+    for (int k = pmb->ks; k <= pmb->ke + 1; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x3f(k, j, i) = bz_amb;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) u(IEN, k, j, i) += 0.5 * (SQR(bx_amb) + SQR(by_amb) + SQR(bz_amb));
+  }
+}
+}  // namespace jet
+
+//========================================================================================
 static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
     {"blast", nullptr, BlastGenerator, nullptr},
@@ -1072,6 +1170,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"shock_tube", nullptr, ShockTubeGenerator, ShockTubeErrors},
     {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
     {"field_loop", nullptr, FieldLoopGenerator, nullptr},
+    {"jet", jet::JetInit, jet::JetGenerator, nullptr},
 };
 
 const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {

@@ -83,7 +83,7 @@ class UniformMesh:
     def block_bcs(self, loc):
         """BoundaryValues::block_bcs as enum athk_bc: a face on the mesh edge takes the mesh flag
         unless periodic; interior faces are 'block' (0)."""
-        code = {"periodic": 0, "reflecting": 1, "outflow": 2}
+        code = {"periodic": 0, "reflecting": 1, "outflow": 2, "user": 3}
         out = []
         for d in range(3):
             out.append(code[self.bcs[2 * d]] if loc[d] == 0 else 0)
@@ -206,6 +206,14 @@ class Context:
             if any(fl):
                 self.has_physical_bcs = True
                 capi.check(self.lib, self.lib.athk_set_boundary_flags(h, lb, (C.c_int * 6)(*fl)))
+
+    def enroll_user_boundary(self, face, fn):
+        """Mesh::EnrollUserBoundaryFunction for the device path: fn(args: capi.BvalArgs) -> int is
+        called once per flagged local block at the face's place in the x1, x2, x3 order and must
+        enqueue its work on args.stream (athk_enroll_user_boundary)."""
+        cb = capi.BVAL_FN(lambda user, a: int(fn(a.contents) or 0))
+        self._user_bcs = getattr(self, "_user_bcs", []) + [cb]   # keep the thunk alive
+        capi.check(self.lib, self.lib.athk_enroll_user_boundary(self.h, face, C.cast(cb, C.c_void_p), None))
 
     def close(self):
         if self.h:

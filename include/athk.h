@@ -82,7 +82,7 @@ enum athk_reg { ATHK_REG0 = 0, ATHK_REG1 = 1, ATHK_REG2 = 2 };
 
 /* BoundaryFlag of a MeshBlock face that is a physical boundary (bvals/utils/boundary_flag.cpp);
  * faces with a neighbour (block / periodic) are ATHK_BC_NONE */
-enum athk_bc { ATHK_BC_NONE = 0, ATHK_BC_REFLECT = 1, ATHK_BC_OUTFLOW = 2 };
+enum athk_bc { ATHK_BC_NONE = 0, ATHK_BC_REFLECT = 1, ATHK_BC_OUTFLOW = 2, ATHK_BC_USER = 3 };
 
 /* ---- lifecycle ------------------------------------------------------------------------ */
 int athk_create(const athk_config *cfg, athk_ctx **out);
@@ -178,6 +178,31 @@ int athk_set_boundary_flags(athk_ctx *ctx, int lb, const int flags[6]);
  * athk_cons2prim (task PHY_BVAL, time_integrator.cpp:2276); athk_stage does it itself.
  * No-op when no local block has a physical boundary. */
 int athk_apply_physical_boundaries(athk_ctx *ctx);
+/* User-enrolled boundary functions: BValFunc (athena.hpp:214-217), Mesh::EnrollUserBoundaryFunction
+ * (mesh/mesh.cpp:1288), dispatched by BoundaryValues::DispatchBoundaryFunctions (bvals/bvals.cpp:673)
+ * for faces flagged ATHK_BC_USER.  The function is a HOST callback invoked once per flagged local
+ * MeshBlock at the face's place in the reference's x1, x2, x3 order; it fills the ghost zones of the
+ * PRIMITIVES w (and of b, r) of that face by enqueueing its own device work on args->stream
+ * (asynchronous, stream-ordered after the library's kernels), exactly what a BValFunc does to
+ * `prim` and `b`; the library then forms bcc, U(W) and s on the slab as for the built-in functions.
+ * Transverse limits (il..ku) are the ones the reference passes (extended into ghost zones that the
+ * neighbour exchange filled).  Arrays use the padded-box layout: element (n,k,j,i) of w at
+ * w[n*stride_n + k*stride_k + j*stride_j + i]; b1/b2/b3 likewise without n.  Return non-zero to
+ * abort (reported as ATHK_ERR_STATE). */
+typedef struct athk_bval_args {
+  int lb, face;                  /* local block; 0..5 = inner_x1, outer_x1, inner_x2, ... */
+  double time, dt;               /* as passed to BValFunc (athk_set_boundary_time) */
+  int il, iu, jl, ju, kl, ku, ngh;
+  double *w, *b1, *b2, *b3, *r;  /* DEVICE pointers of this block (b*, r null without MHD / scalars) */
+  long long stride_j, stride_k, stride_n;
+  int nscalars;
+  void *stream;                  /* cudaStream_t the work must be enqueued on */
+} athk_bval_args;
+typedef int (*athk_bval_fn)(void *user, const athk_bval_args *args);
+int athk_enroll_user_boundary(athk_ctx *ctx, int face, athk_bval_fn fn, void *user);
+/* time and dt handed to the user functions by the next athk_apply_physical_boundaries / athk_stage
+ * (time_integrator.cpp:2276-2290: end-of-stage time and the stage's dt) */
+int athk_set_boundary_time(athk_ctx *ctx, double time, double dt);
 /* Floors of local block lb.  In the reference every MeshBlock owns an EquationOfState
  * (mesh/meshblock.cpp:160-190) whose floors come from pin->GetOrAddReal("hydro","dfloor"|"pfloor"|
  * "sfloor", sqrt(1024*FLT_MIN)) (eos/adiabatic_mhd.cpp:29-31): the first block gets the default in

@@ -87,7 +87,34 @@ def with_data_dumps(blocks, tab_vars, vtk_vars, ghost_vars):
     return blocks
 
 
+def jet_blocks(mhd, integrator="vl2"):
+    """inputs/hydro/athinput.jet in 3-D at test size: user-enrolled inner-x1 boundary (the inlet),
+    outflow elsewhere; 2x2x2 MeshBlocks, so the inlet crosses block edges and the boundary function
+    sees ghost zones the neighbour exchange filled."""
+    b = {
+        "job": {"problem_id": "jet"},
+        "output1": {"file_type": "hst", "dt": 0.25, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 0.5},
+        "time": {"cfl_number": 0.3, "nlim": -1, "tlim": 1.0, "integrator": integrator, "xorder": 2,
+                 "ncycle_out": 1},
+        "mesh": {"nx1": 24, "x1min": 0.0, "x1max": 6.0, "ix1_bc": "user", "ox1_bc": "outflow",
+                 "nx2": 16, "x2min": -2.0, "x2max": 2.0, "ix2_bc": "outflow", "ox2_bc": "outflow",
+                 "nx3": 16, "x3min": -2.0, "x3max": 2.0, "ix3_bc": "outflow", "ox3_bc": "outflow",
+                 "num_threads": 1},
+        "meshblock": {"nx1": 12, "nx2": 8, "nx3": 8},
+        "hydro": {"gamma": 1.666666666667},
+        "problem": {"d": 1.0, "p": 6.0e-3, "vx": 0.0, "vy": 0.0, "vz": 0.0, "djet": 0.1, "pjet": 6.0e-3,
+                    "vxjet": 1.0, "vyjet": 0.0, "vzjet": 0.0, "rjet": 1.0},
+    }
+    if mhd:
+        b["problem"].update({"bx": 0.1, "by": 0.0, "bz": 0.0, "bxjet": 0.1, "byjet": 0.02, "bzjet": 0.0})
+    return b
+
+
 CASES = {
+    # SURVEY 8(f).1: user-enrolled boundary functions (Mesh::EnrollUserBoundaryFunction, BValFunc)
+    "jet_user_bc_hydro": ("jet_hydro_hllc", "jet", False, lambda: jet_blocks(False)),
+    "jet_user_bc_mhd_rk3": ("jet_mhd_hlld", "jet", True, lambda: jet_blocks(True, "rk3")),
     "mhd_linwave": ("linwave_mhd_hlld", "linear_wave", True,
                     lambda: dict(refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(16, 8, 8),
                                                        tlim=0.05, rst_dt=0.02))),
@@ -230,7 +257,7 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
 
 
 @pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe",
-                                  "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes"])
+                                  "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes", "jet_user_bc_mhd_rk3"])
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
