@@ -91,6 +91,10 @@ PROTOTYPES = {
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_set_boundary_flags": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "athk_apply_physical_boundaries": (C.c_int, [_P]),
+    "athk_refine_enable": (C.c_int, [_P]),
+    "athk_refine_set_block_coords": (C.c_int, [_P, C.c_int] + [_D] * 6),
+    "athk_refine_set_ops": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "athk_refine_run": (C.c_int, [_P, C.c_int, C.c_int]),
     "athk_enroll_user_boundary": (C.c_int, [_P, C.c_int, _P, _P]),
     "athk_set_boundary_time": (C.c_int, [_P, C.c_double, C.c_double]),
     "athk_set_block_floors": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),

@@ -183,6 +183,8 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->d_floors);
   cudaFree(c->stage);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
+  cudaFree(c->rf.cu); cudaFree(c->rf.cw); cudaFree(c->rf.xv); cudaFree(c->rf.cxv);
+  for (int p = 0; p < 8; ++p) cudaFree(c->rf.ops[p]);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
   cudaFree(c->p2p.gdst); cudaFree(c->p2p.edst); cudaFree(c->p2p.peer_flags); cudaFree(c->p2p.timeouts);
@@ -1048,6 +1050,104 @@ static int launch_bc_face(athk_ctx *c, int side) {
   PhysBCConsPoint<DIR> f2 = {g, side, c->bcflags, c->eos, mhd, ns, c->w, mhd ? c->b[0] : nullptr, c->r,
                              c->bcc, c->u[0], ns ? c->s[0] : nullptr};
   LAUNCH_NAMED(c, "apply_physical_boundaries", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, rc, f2));
+  return ATHK_OK;
+}
+
+//----------------------------------------------------------------------------------------
+// Static mesh refinement, cell-centred variables (athk_refine.h)
+extern "C" int athk_refine_enable(athk_ctx *c) {
+  if (!c) return fail(ATHK_ERR_ARG, "refine_enable: null context");
+  cudaSetDevice(c->cfg.device);
+  if (c->rf.on) return ATHK_OK;
+  if (c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for hydro (face-centred "
+                                            "restriction / prolongation and the EMF correction are not)");
+  if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "refine_enable: passive scalars are not refined");
+  const Grid &g = c->g;
+  if (g.nx1 % 2 || g.nx2 % 2 || g.nx3 % 2)   // mesh.cpp:340-346
+    return fail(ATHK_ERR_ARG, "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR.");
+  CoarseGrid &cg = c->rf.cg;
+  cg.cng = (g.ng + 1) / 2 + 1;
+  cg.cn1 = g.nx1 / 2 + 2 * g.ng; cg.cn2 = g.nx2 / 2 + 2 * g.ng; cg.cn3 = g.nx3 / 2 + 2 * g.ng;
+  cg.cis = cg.cjs = cg.cks = g.ng;
+  cg.csj = cg.cn1; cg.csk = (idx_t)cg.cn1 * cg.cn2; cg.csn = cg.csk * cg.cn3;
+  cg.CPG = std::max(cg.cn1, std::max(cg.cn2, cg.cn3));
+  const size_t nc = (size_t)g.nb * 5 * cg.csn;
+  int rc = dev_alloc(&c->rf.cu, nc, c->stream);
+  if (!rc) rc = dev_alloc(&c->rf.cw, nc, c->stream);
+  if (!rc) rc = dev_alloc(&c->rf.xv, (size_t)g.nb * 3 * c->geo.PG, c->stream);
+  if (!rc) rc = dev_alloc(&c->rf.cxv, (size_t)g.nb * 3 * cg.CPG, c->stream);
+  if (rc) return rc;
+  c->rf.on = true;
+  return ATHK_OK;
+}
+
+extern "C" int athk_refine_set_block_coords(athk_ctx *c, int lb, const double *x1v, const double *x2v,
+                                            const double *x3v, const double *cx1v, const double *cx2v,
+                                            const double *cx3v) {
+  if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_set_block_coords: call athk_refine_enable first");
+  cudaSetDevice(c->cfg.device);
+  if (lb < 0 || lb >= c->g.nb) return fail(ATHK_ERR_ARG, "refine_set_block_coords: block %d out of range", lb);
+  const double *xv[3] = {x1v, x2v, x3v}, *cxv[3] = {cx1v, cx2v, cx3v};
+  const int nc[3] = {c->g.nc1, c->g.nc2, c->g.nc3}, cn[3] = {c->rf.cg.cn1, c->rf.cg.cn2, c->rf.cg.cn3};
+  for (int d = 0; d < 3; ++d) {
+    if (!xv[d] || !cxv[d]) return fail(ATHK_ERR_ARG, "refine_set_block_coords: null array");
+    CU(cudaMemcpyAsync(c->rf.xv + ((size_t)lb * 3 + d) * c->geo.PG, xv[d], nc[d] * sizeof(Real),
+                       cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->rf.cxv + ((size_t)lb * 3 + d) * c->rf.cg.CPG, cxv[d], cn[d] * sizeof(Real),
+                       cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return ATHK_OK;
+}
+
+extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *ops, int nops) {
+  if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_set_ops: call athk_refine_enable first");
+  cudaSetDevice(c->cfg.device);
+  if (phase < 0 || phase >= ATHK_REFINE_NPHASES) return fail(ATHK_ERR_ARG, "refine_set_ops: phase %d", phase);
+  if (nops < 0 || (nops > 0 && !ops)) return fail(ATHK_ERR_ARG, "refine_set_ops: bad list");
+  static_assert(sizeof(athk_box_op) == sizeof(BoxOp), "athk_box_op layout");
+  const Grid &g = c->g;
+  const CoarseGrid &cg = c->rf.cg;
+  long long maxvol = 0;
+  for (int n = 0; n < nops; ++n) {   // every box must lie inside the array it addresses
+    const athk_box_op &o = ops[n];
+    if (o.kind < BOX_RESTRICT || o.kind > BOX_FLUX_FROM_FINER || o.dst < 0 || o.dst >= g.nb || o.src < 0 || o.src >= g.nb)
+      return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
+    const bool coarse_dst = (o.kind == BOX_RESTRICT || o.kind == BOX_FROM_COARSER || o.kind == BOX_C2P_COARSE ||
+                             o.kind == BOX_PROLONG);
+    const int lim[3] = {coarse_dst ? cg.cn1 : g.nc1 + 1, coarse_dst ? cg.cn2 : g.nc2 + 1, coarse_dst ? cg.cn3 : g.nc3 + 1};
+    long long vol = 1;
+    for (int d = 0; d < 3; ++d) {
+      const int inset = (o.kind == BOX_PROLONG) ? 1 : 0;   // the gradients read one coarse cell around
+      if (o.lo[d] < inset || o.hi[d] >= lim[d] - inset || o.hi[d] < o.lo[d])
+        return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d) leaves its array in direction %d: %d..%d", n,
+                    o.kind, d, o.lo[d], o.hi[d]);
+      vol *= o.hi[d] - o.lo[d] + 1;
+    }
+    if (o.kind == BOX_FLUX_FROM_FINER && (o.dir < 0 || o.dir > 2 || o.lo[o.dir] != o.hi[o.dir]))
+      return fail(ATHK_ERR_ARG, "refine_set_ops: box %d is not a face box of direction %d", n, o.dir);
+    maxvol = std::max(maxvol, vol);
+  }
+  if (c->rf.ops[phase]) { cudaFree(c->rf.ops[phase]); c->rf.ops[phase] = nullptr; }
+  c->rf.nops[phase] = nops;
+  c->rf.maxvol[phase] = maxvol;
+  if (nops > 0) {
+    CU(cudaMalloc((void **)&c->rf.ops[phase], (size_t)nops * sizeof(BoxOp)));
+    CU(cudaMemcpyAsync(c->rf.ops[phase], ops, (size_t)nops * sizeof(BoxOp), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return ATHK_OK;
+}
+
+extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
+  NEED_READY(c);
+  if (!c->rf.on) return fail(ATHK_ERR_STATE, "refine_run: call athk_refine_enable first");
+  if (phase < 0 || phase >= ATHK_REFINE_NPHASES) return fail(ATHK_ERR_ARG, "refine_run: phase %d", phase);
+  if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "refine_run: register %d not allocated", reg);
+  if (c->rf.nops[phase] == 0) return ATHK_OK;
+  BoxOpPoint f = {c->g, c->rf.cg, c->geo, c->eos, c->rf.ops[phase], c->u[reg], c->w, c->rf.cu, c->rf.cw,
+                  {c->flux[0], c->flux[1], c->flux[2]}, c->rf.xv, c->rf.cxv};
+  LAUNCH_NAMED(c, "athk_refine_run", launch_links(c->stream, c->rf.nops[phase], c->rf.maxvol[phase], f));
   return ATHK_OK;
 }
 

@@ -18,6 +18,7 @@
 #include "athk_sweep.h"
 #include "athk_scalars.h"
 #include "athk_bcs.h"
+#include "athk_refine.h"
 #ifndef ATHK_EMULATE
 #include "athk_sweep_kernels.cuh"
 #endif
@@ -83,6 +84,15 @@ struct athk_ctx {
   int *bcflags;                 // device
   bool bc_dirty;
   int bc_any[6];                // does any local block have a physical boundary on face f
+  // static mesh refinement (athk_refine_*): coarse buffers, coordinates, per-phase box lists
+  struct Refine {
+    bool on = false;
+    CoarseGrid cg;
+    Real *cu = nullptr, *cw = nullptr, *xv = nullptr, *cxv = nullptr;
+    BoxOp *ops[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int nops[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long maxvol[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  } rf;
   athk_bval_fn user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // enrolled BValFuncs
   void *user_bc_data[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double bc_time = 0.0, bc_dt = 0.0;

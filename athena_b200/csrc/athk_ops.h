@@ -37,6 +37,8 @@ struct Geom {
   const Real *cm[3];    // (xv(n) - xf(n)) / dxf(n)     plm.cpp:153
 };
 
+// table entry towards a coarser or finer neighbour (== ATHK_NBR_REFINED, include/athk.h)
+enum { NBR_REFINED = -1000000 };
 // neighbour table entry for offsets (ox1,ox2,ox3) in {-1,0,1}
 ATHK_HD int nbr_slot(int ox1, int ox2, int ox3) { return (ox3 + 1) * 9 + (ox2 + 1) * 3 + (ox1 + 1); }
 
@@ -757,7 +759,7 @@ struct GhostFillCC {
     const int o3 = (k < g.ks) ? -1 : (k > g.ke ? 1 : 0);
     if (o1 == 0 && o2 == 0 && o3 == 0) return;
     const int id = nbr[blk * 27 + nbr_slot(o1, o2, o3)];
-    if (id == -1) return;   // physical boundary
+    if (id == -1 || id == NBR_REFINED) return;   // physical boundary; coarser / finer neighbour (athk_refine.h)
     const idx_t dst = gidx(g, k, j, i);
     // (source and destination are the same array: a store would fence the loads behind it, so the
     //  components are loaded five at a time before any is stored)

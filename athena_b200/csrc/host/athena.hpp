@@ -193,6 +193,35 @@ class EquationOfState {   // eos/eos.hpp:32-181
   Real gamma_, dfloor_, pfloor_, sfloor_;
 };
 
+// bvals/bvals_interfaces.hpp:120-190 (NeighborBlock) -- what the refinement code needs of it
+struct NeighborBlock {
+  int gid, lid, level;
+  int ox1, ox2, ox3, fi1, fi2;
+  int type;   // 0 face, 1 edge, 2 corner
+  int fid;    // BoundaryFace of a face neighbour
+};
+
+// mesh/meshblock_tree.hpp: octree of LogicalLocations (3-D), leaves = MeshBlocks
+class MeshBlockTree {
+ public:
+  explicit MeshBlockTree(Mesh *pmesh);
+  MeshBlockTree(MeshBlockTree *parent, int ox1, int ox2, int ox3);
+  ~MeshBlockTree();
+  void CreateRootGrid();
+  void AddMeshBlock(LogicalLocation rloc);
+  void Refine();
+  void GetMeshBlockList(std::vector<LogicalLocation> *list);
+  MeshBlockTree *FindNeighbor(LogicalLocation myloc, int ox1, int ox2, int ox3);
+  MeshBlockTree *GetLeaf(int ox1, int ox2, int ox3) { return pleaf_[ox1 + (ox2 << 1) + (ox3 << 2)]; }
+  LogicalLocation loc_;
+  bool has_leaves_ = false;
+  int gid_ = -1;
+ private:
+  Mesh *pmesh_;
+  MeshBlockTree *proot_;
+  MeshBlockTree *pleaf_[8];
+};
+
 class MeshBlock {   // mesh/mesh.hpp:75-200
  public:
   MeshBlock(int gid, int lid, LogicalLocation loc, RegionSize bs, Mesh *pm, ParameterInput *pin);
@@ -211,6 +240,9 @@ class MeshBlock {   // mesh/mesh.hpp:75-200
   PassiveScalars *pscalars;
   EquationOfState *peos;
   Real new_block_dt_;
+  // static mesh refinement (bvals_base.hpp): neighbours in SearchAndSetNeighbors' order, their levels
+  std::vector<NeighborBlock> neighbor;
+  int nblevel[3][3][3];
 };
 
 // athena.hpp:98-100, 214-217: user-enrolled boundary functions act on the HOST mirrors of the
@@ -262,6 +294,13 @@ class Mesh {   // mesh/mesh.hpp:206-447
   athk_ctx *ctx_of(const MeshBlock *pmb) { return ctx[pmb->rank]; }
   athk_ctx *athk;                         // == ctx[0]
   void SetupRemoteLinks();                // multigpu.cpp
+  // static mesh refinement (<mesh> refinement = static, <refinementN> blocks): refinement.cpp
+  bool multilevel = false;
+  int current_level = 0;
+  MeshBlockTree *tree = nullptr;
+  void BuildRefinedTree(ParameterInput *pin);
+  void SearchAndSetNeighbors(MeshBlock *pmb);
+  void SetupRefinement();
   const ProblemGeneratorEntry *pgen;
   bool fused_stage;
   // user history output (mesh.hpp: EnrollUserHistoryOutput)

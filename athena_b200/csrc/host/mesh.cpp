@@ -68,7 +68,7 @@ Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm) {
     d.dxf->NewAthenaArray(d.nc);
     d.dxv->NewAthenaArray(d.nc);
     const int il = ng, iu = ng + d.nx - 1;
-    const std::int64_t nrootmesh = d.mnx;   // uniform level
+    const std::int64_t nrootmesh = (std::int64_t)d.mnx * (1LL << (pmb->loc.level - pm->root_level));   // coordinates.cpp:95
     // coordinates.cpp:143-152 (uniform mesh generator branch)
     const Real dx = (d.bmax - d.bmin) / (iu - il + 1);
     for (int i = il - ng; i <= iu + ng + 1; ++i) {
@@ -159,11 +159,40 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
         << "The B200 path implements 3-D MeshBlocks only (nx1,nx2,nx3 > 1)";
     ATHENA_ERROR(msg);
   }
-  if (mesh_size.x1rat != 1.0 || mesh_size.x2rat != 1.0 || mesh_size.x3rat != 1.0 ||
-      pin->GetOrAddString("mesh", "refinement", "none") != "none") {
+  if (mesh_size.x1rat != 1.0 || mesh_size.x2rat != 1.0 || mesh_size.x3rat != 1.0) {
     msg << "### FATAL ERROR in Mesh constructor" << std::endl
-        << "The B200 path implements uniform Cartesian meshes without refinement";
+        << "The B200 path implements uniform Cartesian meshes (x?rat = 1)";
     ATHENA_ERROR(msg);
+  }
+  {   // mesh.cpp:226-233
+    const std::string ref = pin->GetOrAddString("mesh", "refinement", "none");
+    if (ref == "static") {
+      multilevel = true;
+    } else if (ref != "none") {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "The B200 path implements static mesh refinement (refinement = static); '" << ref << "' is not";
+      ATHENA_ERROR(msg);
+    }
+  }
+  if (multilevel) {
+    if (MAGNETIC_FIELDS_ENABLED || NSCALARS > 0) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "Static mesh refinement on the B200 path covers hydrodynamics (cell-centred variables); the "
+          << "face-centred field and passive scalars are not refined";
+      ATHENA_ERROR(msg);
+    }
+    if (NGHOST % 2 == 1) {   // prolongation fills 2*(cnghost-1) ghost cells: more than an odd NGHOST holds
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "Mesh refinement needs an even number of ghost zones (nghost=" << NGHOST << ")";
+      ATHENA_ERROR(msg);
+    }
+    for (int n = 0; n < 6; ++n)
+      if (mesh_bcs[n] != BoundaryFlag::periodic) {
+        msg << "### FATAL ERROR in Mesh constructor" << std::endl
+            << "Static mesh refinement on the B200 path needs periodic mesh boundaries (physical boundaries "
+            << "on the coarse buffer are not implemented)";
+        ATHENA_ERROR(msg);
+      }
   }
   for (int n = 0; n < 6; ++n) {
     if (mesh_bcs[n] != BoundaryFlag::periodic && mesh_bcs[n] != BoundaryFlag::reflect &&
@@ -200,11 +229,24 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
       for (std::int64_t i = 0; i < nrbx1; ++i) loclist.push_back(LogicalLocation{i, j, k, root_level});
   std::sort(loclist.begin(), loclist.end(),
             [](const LogicalLocation &a, const LogicalLocation &b) { return MortonKey(a) < MortonKey(b); });
+  if (multilevel) {   // mesh.cpp:340-492: the block tree with its <refinementN> regions, leaves in Z-order
+    if (bs.nx1 % 2 == 1 || bs.nx2 % 2 == 1 || bs.nx3 % 2 == 1) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl
+          << "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR." << std::endl;
+      ATHENA_ERROR(msg);
+    }
+    BuildRefinedTree(pin);
+  }
   nbtotal = static_cast<int>(loclist.size());
   nblocal = nbtotal;   // one process drives every GPU: all MeshBlocks are "local" to the host
   // Mesh::CalculateLoadBalance (amr_loadbalance.cpp:73-131) for equal costs: contiguous Z-order
   // ranges, the remainder handed out from the last rank backwards
   ngpu = pin->GetOrAddInteger("mesh", "num_gpus", 1);
+  if (multilevel && ngpu != 1) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "Static mesh refinement runs on one GPU (<mesh> num_gpus = 1)";
+    ATHENA_ERROR(msg);
+  }
   if (ngpu < 1 || ngpu > nbtotal) {
     msg << "### FATAL ERROR in Mesh constructor" << std::endl
         << "<mesh> num_gpus = " << ngpu << " must be between 1 and the number of MeshBlocks (" << nbtotal << ")";
@@ -231,15 +273,19 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     ATHENA_ERROR(msg);
   }
   fused_stage = pin->GetOrAddBoolean("time", "fused_stage", true);
+  // the flux correction between levels replaces stored face fluxes before they are differenced:
+  // refined meshes run the operator sequence (the fused stage never stores fluxes)
+  if (multilevel) fused_stage = false;
 
   for (int n = 0; n < nbtotal; ++n) {
     const LogicalLocation &l = loclist[n];
     RegionSize b = bs;
     // SetBlockSizeAndBoundaries, mesh.cpp:1984-2060
-    struct { std::int64_t lx; int nrb; Real mmin, mmax; Real *bmin, *bmax; } d[3] = {
-        {l.lx1, nrbx1, mesh_size.x1min, mesh_size.x1max, &b.x1min, &b.x1max},
-        {l.lx2, nrbx2, mesh_size.x2min, mesh_size.x2max, &b.x2min, &b.x2max},
-        {l.lx3, nrbx3, mesh_size.x3min, mesh_size.x3max, &b.x3min, &b.x3max}};
+    const int lsh = l.level - root_level;   // nrbx_ll = nrbx << (ll - root_level)
+    struct { std::int64_t lx; std::int64_t nrb; Real mmin, mmax; Real *bmin, *bmax; } d[3] = {
+        {l.lx1, (std::int64_t)nrbx1 << lsh, mesh_size.x1min, mesh_size.x1max, &b.x1min, &b.x1max},
+        {l.lx2, (std::int64_t)nrbx2 << lsh, mesh_size.x2min, mesh_size.x2max, &b.x2min, &b.x2max},
+        {l.lx3, (std::int64_t)nrbx3 << lsh, mesh_size.x3min, mesh_size.x3max, &b.x3min, &b.x3max}};
     for (auto &q : d) {
       *q.bmin = (q.lx == 0) ? q.mmin : UniformMeshGenerator(ComputeMeshGeneratorX(q.lx, q.nrb), q.mmin, q.mmax);
       *q.bmax = (q.lx == q.nrb - 1) ? q.mmax
@@ -313,11 +359,14 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
               "Mesh constructor (athk_set_block_coords)");
   }
   // same-level neighbour tables, per-GPU remote links, peer-to-peer buffers (multigpu.cpp)
-  SetupRemoteLinks();
+  if (multilevel) SetupRefinement();   // neighbours across levels, coarse buffers, exchange boxes
+  else SetupRemoteLinks();
   // BoundaryValues::block_bcs (bvals.cpp:60-120): mesh flag on the mesh edge, "block" elsewhere
   for (int n = 0; n < nblocal; ++n) {
     const LogicalLocation &l = loclist[n];
-    const std::int64_t lx[3] = {l.lx1, l.lx2, l.lx3}, nr[3] = {nrbx1, nrbx2, nrbx3};
+    const int lsh = l.level - root_level;
+    const std::int64_t lx[3] = {l.lx1, l.lx2, l.lx3},
+                       nr[3] = {(std::int64_t)nrbx1 << lsh, (std::int64_t)nrbx2 << lsh, (std::int64_t)nrbx3 << lsh};
     int fl[6];
     bool any = false;
     for (int d = 0; d < 3; ++d)
@@ -402,6 +451,7 @@ void Mesh::EnrollUserBoundaryFunction(BoundaryFace dir, BValFunc my_bc) {
 
 Mesh::~Mesh() {
   for (MeshBlock *p : blocks_) delete p;
+  delete tree;
   for (athk_ctx *a : ctx) if (a) athk_sync(a);
   for (std::size_t q = 0; q < p2p_allocs_.size(); ++q)
     if (p2p_allocs_[q]) athk_p2p_free(ctx[q / 3], p2p_allocs_[q]);
@@ -412,6 +462,17 @@ Mesh::~Mesh() {
 // (peer stores), then fill the ghost zones
 void Mesh::ExchangeGhosts() {
   const int what = 1 | (MAGNETIC_FIELDS_ENABLED ? 2 : 0) | (NSCALARS > 0 ? 4 : 0);
+  if (multilevel) {
+    // SEND_HYD: blocks next to a coarser one restrict their boundary cells (phase 1); SETB_HYD: same
+    // level (neighbour table), from finer / from coarser (phase 2); PROLONG (time_integrator.cpp:
+    // 2133-2160, bvals_refine.cpp:95): restrict the ghost-ghost zones, W(U) on the coarse buffer,
+    // prolongate the primitives, U(W) on the new ghost zones (phases 3-6)
+    const char *who = "Mesh::ExchangeGhosts";
+    AthkCheck(athk_refine_run(athk, 1, 0), who);
+    AthkCheck(athk_exchange_ghosts(athk, what, 0), who);
+    for (int phase = 2; phase <= 6; ++phase) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    return;
+  }
   if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), "Mesh::ExchangeGhosts");
   for (athk_ctx *a : ctx) AthkCheck(athk_exchange_ghosts(a, what, 0), "Mesh::ExchangeGhosts");
 }

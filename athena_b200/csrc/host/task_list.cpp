@@ -96,6 +96,8 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
     if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_zero_register(a, 2, 1); });   // ps->s1.ZeroClear() :1628-1630
   }
   all([&](athk_ctx *a) { return athk_calculate_fluxes(a, order, dt, 0); });                    // CALC_HYDFLX
+  if (pm->multilevel)   // SEND/RECV_HYDFLX: fluxes on faces shared with finer blocks (:1757-1795)
+    all([&](athk_ctx *a) { return athk_refine_run(a, 0, 0); });
   if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_calculate_scalar_fluxes(a, order); });  // CALC_SCLRFLX :2329-2340
   if (mhd) {
     all([&](athk_ctx *a) { return athk_compute_corner_e(a); });                                // CALC_FLDFLX

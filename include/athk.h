@@ -200,6 +200,41 @@ typedef struct athk_bval_args {
 } athk_bval_args;
 typedef int (*athk_bval_fn)(void *user, const athk_bval_args *args);
 int athk_enroll_user_boundary(athk_ctx *ctx, int face, athk_bval_fn fn, void *user);
+/* ---- static mesh refinement, cell-centred variables (hydro) ---------------------------------
+ * The host owns the block tree and the neighbour levels (MeshBlockTree, BoundaryBase::
+ * SearchAndSetNeighbors) and hands the library, per phase of the boundary exchange, the list of
+ * index boxes the reference's Load/Set/Restrict/Prolongate functions loop over; the library holds
+ * the coarse buffers and does the arithmetic on the device (athena_b200/csrc/athk_refine.h).
+ * Neighbour-table entries towards a coarser or finer neighbour are ATHK_NBR_REFINED: such ghost
+ * zones are filled by the box operations, and count as "has a neighbour" for W(U).
+ *   kind  1 RestrictCellCenteredValues own u -> own coarse buffer   (mesh_refinement.cpp:116;
+ *           LoadBoundaryBufferToCoarser bvals_cc.cpp:309, RestrictGhostCellsOnSameLevel bvals_refine.cpp:263)
+ *         2 SetBoundaryFromFiner: u[dst] box <- coarse buffer of src          (bvals_cc.cpp:485)
+ *         3 LoadBoundaryBufferToFiner + SetBoundaryFromCoarser: coarse buffer of dst <- u[src]  (:335,:424)
+ *         4 ConservedToPrimitive on the coarse buffer                      (bvals_refine.cpp:437)
+ *         5 ProlongateCellCenteredValues coarse primitives -> w            (mesh_refinement.cpp:464)
+ *         6 PrimitiveToConserved on the prolongated ghost zones            (bvals_refine.cpp:655)
+ *         7 flux correction: flux[dir] of dst on a face box <- area-weighted flux of the finer src
+ *           (flux_correction_cc.cpp:77-160, 222-275)
+ * Boxes are inclusive (i, j, k) ranges of the destination; so = source origin matching lo. */
+#define ATHK_NBR_REFINED (-1000000)
+typedef struct athk_box_op {
+  int kind, dst, src, dir;
+  int lo[3], hi[3];
+  int so[3];
+  int pad;
+} athk_box_op;
+enum { ATHK_REFINE_NPHASES = 8 };
+/* allocates coarse_cons_ / coarse_prim_ (hydro/hydro.cpp:60-75): 2 x 5 x (nx/2 + 2 nghost)^3 per block */
+int athk_refine_enable(athk_ctx *ctx);
+/* Coordinates::x?v of the block and of its coarse twin pcoarsec (mesh_refinement.cpp:60-75), lengths
+ * nc? and nx?/2 + 2 nghost */
+int athk_refine_set_block_coords(athk_ctx *ctx, int lb, const double *x1v, const double *x2v, const double *x3v,
+                                 const double *cx1v, const double *cx2v, const double *cx3v);
+/* the boxes of one phase (0 .. ATHK_REFINE_NPHASES-1; their meaning is the host's), copied to the device */
+int athk_refine_set_ops(athk_ctx *ctx, int phase, const athk_box_op *ops, int nops);
+/* one launch over all boxes of the phase; reg = the conserved register kinds 1-3 and 6 act on */
+int athk_refine_run(athk_ctx *ctx, int phase, int reg);
 /* time and dt handed to the user functions by the next athk_apply_physical_boundaries / athk_stage
  * (time_integrator.cpp:2276-2290: end-of-stage time and the stage's dt) */
 int athk_set_boundary_time(athk_ctx *ctx, double time, double dt);

@@ -46,6 +46,7 @@ CONFIGS = {
     "linwave_mhd_hlld_g3": dict(PROB="linear_wave", MHD=1, FLUX="hlld", NGHOST=3),
     "cpaw_mhd_hlld": dict(PROB="cpaw", MHD=1, FLUX="hlld"),
     "fieldloop_mhd_hlld": dict(PROB="field_loop", MHD=1, FLUX="hlld"),
+    "linwave_hydro_hllc_g4": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=4),   # PPM on a refined mesh
     "jet_hydro_hllc": dict(PROB="jet", MHD=0, FLUX="hllc"),       # user-enrolled inner-x1 boundary
     "jet_mhd_hlld": dict(PROB="jet", MHD=1, FLUX="hlld"),
 }

@@ -111,7 +111,30 @@ def jet_blocks(mhd, integrator="vl2"):
     return b
 
 
+def refined(blocks, *regions):
+    """<mesh> refinement = static with <refinementN> blocks (x1min, x1max, x2min, x2max, x3min, x3max, level)"""
+    blocks["mesh"]["refinement"] = "static"
+    for n, r in enumerate(regions):
+        blocks["refinement%d" % (n + 1)] = dict(zip(("x1min", "x1max", "x2min", "x2max", "x3min", "x3max", "level"), r))
+    return blocks
+
+
 CASES = {
+    # SURVEY 8(f).2: static mesh refinement, hydro (restriction / prolongation of the cell-centred
+    # variables, flux correction).  The reference's own linear-wave regression runs refined.
+    "smr_linwave_hydro_centre": ("linwave_hydro_hllc", "linear_wave", False, lambda: refined(
+        refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.05, rst_dt=0.025),
+        (0.75, 2.25, 0.375, 1.125, 0.375, 1.125, 1))),
+    "smr_linwave_hydro_two_levels_rk3": ("linwave_hydro_hllc", "linear_wave", False, lambda: refined(
+        refrun.linwave_blocks(False, mesh=(24, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3"),
+        (0.0, 0.6, 0.0, 0.5, 0.9, 1.5, 2))),   # region in a corner of the periodic box, 2:1 balance cascades
+    "smr_blast_hydro": ("blast_hydro_hllc", "blast", False, lambda: refined(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.06, rst_dt=0.03, b0=None, radius=0.25),
+        (-0.3, 0.3, -0.3, 0.3, -0.3, 0.3, 1))),
+    "smr_linwave_hydro_ppm_two_regions": ("linwave_hydro_hllc_g4", "linear_wave", False, lambda: refined(
+        refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3",
+                              xorder=3),
+        (1.0, 1.6, 0.2, 0.5, 0.9, 1.2, 1), (2.4, 2.9, 1.0, 1.4, 0.1, 0.3, 1)), ["--nghost=4"]),
     # SURVEY 8(f).1: user-enrolled boundary functions (Mesh::EnrollUserBoundaryFunction, BValFunc)
     "jet_user_bc_hydro": ("jet_hydro_hllc", "jet", False, lambda: jet_blocks(False)),
     "jet_user_bc_mhd_rk3": ("jet_mhd_hlld", "jet", True, lambda: jet_blocks(True, "rk3")),
@@ -613,7 +636,7 @@ def check_restart(binary, case):
             shutil.rmtree(d, ignore_errors=True)
 
 
-RESTART_CASES = ["mhd_blast", "kh_rk3_ppm_scalar", "briowu_x3_reflect_outflow"]
+RESTART_CASES = ["mhd_blast", "kh_rk3_ppm_scalar", "briowu_x3_reflect_outflow", "smr_linwave_hydro_two_levels_rk3"]
 
 
 @pytest.mark.parametrize("case", RESTART_CASES)
