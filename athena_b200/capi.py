@@ -91,6 +91,8 @@ PROTOTYPES = {
     "athk_history": (C.c_int, [_P, _D, C.c_int]),
     "athk_set_boundary_flags": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "athk_apply_physical_boundaries": (C.c_int, [_P]),
+    "athk_enroll_user_source": (C.c_int, [_P, _P, _P]),
+    "athk_set_source_time": (C.c_int, [_P, C.c_double]),
     "athk_refine_enable": (C.c_int, [_P]),
     "athk_refine_set_block_coords": (C.c_int, [_P, C.c_int] + [_D] * 6),
     "athk_refine_set_ops": (C.c_int, [_P, C.c_int, _P, C.c_int]),

@@ -1225,13 +1225,45 @@ extern "C" int athk_set_constant_acceleration(athk_ctx *c, double g1, double g2,
   return ATHK_OK;
 }
 
+extern "C" int athk_enroll_user_source(athk_ctx *c, athk_src_fn fn, void *user) {
+  if (!c) return fail(ATHK_ERR_ARG, "enroll_user_source: null context");
+  c->user_src = fn;
+  c->user_src_data = user;
+  return ATHK_OK;
+}
+
+extern "C" int athk_set_source_time(athk_ctx *c, double time) {
+  if (!c) return fail(ATHK_ERR_ARG, "set_source_time: null context");
+  c->src_time = time;
+  return ATHK_OK;
+}
+
 extern "C" int athk_add_source_terms(athk_ctx *c, double beta_dt) {
   NEED_READY(c);
-  if (c->gacc[0] == 0.0 && c->gacc[1] == 0.0 && c->gacc[2] == 0.0) return ATHK_OK;
   const Grid &g = c->g;
-  Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
-  ConstAccPoint f = {g, c->w, c->u[0], beta_dt, c->gacc[0], c->gacc[1], c->gacc[2]};
-  LAUNCH_NAMED(c, "athk_add_source_terms", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+  if (!(c->gacc[0] == 0.0 && c->gacc[1] == 0.0 && c->gacc[2] == 0.0)) {
+    Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
+    ConstAccPoint f = {g, c->w, c->u[0], beta_dt, c->gacc[0], c->gacc[1], c->gacc[2]};
+    LAUNCH_NAMED(c, "athk_add_source_terms", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
+  }
+  if (c->user_src) {   // user-defined source terms come last (hydro_srcterms.cpp:151-154)
+    const int ns = c->cfg.nscalars;
+    for (int lb = 0; lb < g.nb; ++lb) {
+      athk_src_args a;
+      a.lb = lb; a.time = c->src_time; a.dt = beta_dt;
+      a.is = g.is; a.ie = g.ie; a.js = g.js; a.je = g.je; a.ks = g.ks; a.ke = g.ke;
+      a.w = c->w + (idx_t)lb * 5 * g.sn;
+      a.bcc = c->cfg.mhd ? c->bcc + (idx_t)lb * 3 * g.sn : nullptr;
+      a.r = ns ? c->r + (idx_t)lb * ns * g.sn : nullptr;
+      a.u = c->u[0] + (idx_t)lb * 5 * g.sn;
+      a.s = ns ? c->s[0] + (idx_t)lb * ns * g.sn : nullptr;
+      a.stride_j = g.sj; a.stride_k = g.sk; a.stride_n = g.sn;
+      a.nscalars = ns;
+      a.stream = (void *)c->stream;
+      if (c->user_src(c->user_src_data, &a) != 0)
+        return fail(ATHK_ERR_STATE, "user source function failed on block %d", lb);
+    }
+  }
   return ATHK_OK;
 }
 

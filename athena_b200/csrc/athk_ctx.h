@@ -96,6 +96,9 @@ struct athk_ctx {
   athk_bval_fn user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // enrolled BValFuncs
   void *user_bc_data[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double bc_time = 0.0, bc_dt = 0.0;
+  athk_src_fn user_src = nullptr;   // enrolled SrcTermFunc
+  void *user_src_data = nullptr;
+  double src_time = 0.0;
   double gacc[3] = {0.0, 0.0, 0.0};   // HydroSourceTerms: <hydro> grav_acc1/2/3 (0 = none)
   std::vector<Real> h_floors;         // per-block (dfloor, pfloor, sfloor); empty = uniform
   Real *d_floors = nullptr;

@@ -251,6 +251,10 @@ enum BoundaryFace { undef = -1, inner_x1 = 0, outer_x1 = 1, inner_x2 = 2, outer_
 using BValFunc = void (*)(MeshBlock *pmb, Coordinates *pco, AthenaArray<Real> &prim, FaceField &b, Real time, Real dt,
                           int is, int ie, int js, int je, int ks, int ke, int ngh);
 
+using SrcTermFunc = void (*)(MeshBlock *pmb, const Real time, const Real dt, const AthenaArray<Real> &prim,
+                             const AthenaArray<Real> &prim_scalar, const AthenaArray<Real> &bcc,
+                             AthenaArray<Real> &cons, AthenaArray<Real> &cons_scalar);   // athena.hpp:218-222
+
 typedef void (*PgenFn)(MeshBlock *pmb, ParameterInput *pin);
 typedef void (*MeshHookFn)(Mesh *pm, ParameterInput *pin);
 struct ProblemGeneratorEntry {
@@ -314,6 +318,9 @@ class Mesh {   // mesh/mesh.hpp:206-447
   // enrolled with athk_enroll_user_boundary and stays on the device).
   void EnrollUserBoundaryFunction(BoundaryFace face, BValFunc my_func);
   BValFunc BoundaryFunction_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Mesh::EnrollUserExplicitSourceFunction (mesh.cpp:1345): host function on the host mirrors, as above
+  void EnrollUserExplicitSourceFunction(SrcTermFunc my_func);
+  SrcTermFunc UserSourceTerm_ = nullptr;
   MeshBlock *FindLocalBlock(int rank, int lid);
 
  private:
@@ -332,7 +339,7 @@ class TimeIntegratorTaskList {
   std::string integrator;
   int nstages;
   Real cfl_limit;
-  struct IntegratorWeight { Real delta, gamma_1, gamma_2, gamma_3, beta, ebeta; };
+  struct IntegratorWeight { Real delta, gamma_1, gamma_2, gamma_3, beta, ebeta, sbeta; };
   IntegratorWeight stage_wghts[6];
   int xorder;
 };

@@ -427,6 +427,38 @@ int HostBValAdapter(void *user, const athk_bval_args *a) {
 }
 }  // namespace
 
+namespace {
+int HostSrcAdapter(void *user, const athk_src_args *a) {
+  UserBCSlot *slot = static_cast<UserBCSlot *>(user);
+  Mesh *pm = slot->pm;
+  MeshBlock *pmb = pm->FindLocalBlock(slot->rank, a->lb);
+  if (pmb == nullptr || pm->UserSourceTerm_ == nullptr) return 1;
+  athk_ctx *c = pm->ctx[slot->rank];
+  if (athk_download(c, ATHK_W, a->lb, pmb->phydro->w.data())) return 1;
+  if (athk_download(c, ATHK_U, a->lb, pmb->phydro->u.data())) return 1;
+  if (MAGNETIC_FIELDS_ENABLED && athk_download(c, ATHK_BCC, a->lb, pmb->pfield->bcc.data())) return 1;
+  if (NSCALARS > 0) {
+    if (athk_download(c, ATHK_R, a->lb, pmb->pscalars->r.data())) return 1;
+    if (athk_download(c, ATHK_S, a->lb, pmb->pscalars->s.data())) return 1;
+  }
+  pm->UserSourceTerm_(pmb, a->time, a->dt, pmb->phydro->w, pmb->pscalars->r, pmb->pfield->bcc, pmb->phydro->u,
+                      pmb->pscalars->s);
+  if (athk_upload(c, ATHK_U, a->lb, pmb->phydro->u.data())) return 1;
+  if (NSCALARS > 0 && athk_upload(c, ATHK_S, a->lb, pmb->pscalars->s.data())) return 1;
+  return 0;
+}
+}  // namespace
+
+void Mesh::EnrollUserExplicitSourceFunction(SrcTermFunc my_func) {
+  UserSourceTerm_ = my_func;
+  static std::vector<UserBCSlot *> slots;
+  for (int r = 0; r < ngpu; ++r) {
+    UserBCSlot *sl = new UserBCSlot{this, r};
+    slots.push_back(sl);
+    AthkCheck(athk_enroll_user_source(ctx[r], HostSrcAdapter, sl), "Mesh::EnrollUserExplicitSourceFunction");
+  }
+}
+
 void Mesh::EnrollUserBoundaryFunction(BoundaryFace dir, BValFunc my_bc) {
   std::stringstream msg;
   if (dir < 0 || dir > 5) {

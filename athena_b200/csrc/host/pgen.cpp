@@ -1162,6 +1162,75 @@ void JetGenerator(MeshBlock *pmb, ParameterInput *pin) {
 }  // namespace jet
 
 //========================================================================================
+// usrsrc: the user problem of oracle/pgen/usrsrc.cpp (a smooth bump in a periodic box driven by a
+// time-dependent body force along x3 and a cooling term through EnrollUserExplicitSourceFunction);
+// the reference ships no Cartesian problem whose user source term runs without a shearing box
+namespace usrsrc {
+Real g0, tcool, lz, zmin;
+
+void DrivenCooling(MeshBlock *pmb, const Real time, const Real dt, const AthenaArray<Real> &prim,
+                   const AthenaArray<Real> &prim_scalar, const AthenaArray<Real> &bcc, AthenaArray<Real> &cons,
+                   AthenaArray<Real> &cons_scalar) {
+  for (int k = pmb->ks; k <= pmb->ke; ++k)
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) {
+        const Real den = prim(IDN, k, j, i);
+        const Real x3 = pmb->pcoord->x3v(k);
+        const Real acc = g0 * (1.0 + time) * std::sin(TWO_PI * (x3 - zmin) / lz);
+        cons(IM3, k, j, i) -= dt * den * acc;
+        cons(IEN, k, j, i) -= dt * den * acc * prim(IVZ, k, j, i);
+        cons(IEN, k, j, i) -= dt * prim(IPR, k, j, i) / tcool;
+      }
+}
+
+void Init(Mesh *pm, ParameterInput *pin) {
+  g0 = pin->GetReal("problem", "g0");
+  tcool = pin->GetReal("problem", "tcool");
+  lz = pm->mesh_size.x3max - pm->mesh_size.x3min;
+  zmin = pm->mesh_size.x3min;
+  pm->EnrollUserExplicitSourceFunction(DrivenCooling);
+}
+
+void Generator(MeshBlock *pmb, ParameterInput *pin) {
+  const Real gm1 = pmb->peos->GetGamma() - 1.0;
+  const Real amp = pin->GetReal("problem", "amp");
+  const Real b0 = MAGNETIC_FIELDS_ENABLED ? pin->GetReal("problem", "b0") : 0.0;
+  const RegionSize &ms = pmb->pmy_mesh->mesh_size;
+  Coordinates *pc = pmb->pcoord;
+  AthenaArray<Real> &u = pmb->phydro->u;
+  for (int k = pmb->ks; k <= pmb->ke; ++k)
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) {
+        const Real s1 = std::sin(TWO_PI * (pc->x1v(i) - ms.x1min) / (ms.x1max - ms.x1min));
+        const Real s2 = std::cos(TWO_PI * (pc->x2v(j) - ms.x2min) / (ms.x2max - ms.x2min));
+        const Real s3 = std::sin(TWO_PI * (pc->x3v(k) - ms.x3min) / (ms.x3max - ms.x3min));
+        const Real d = 1.0 + amp * s1 * s2;
+        const Real p = 1.0 + amp * s2 * s3;
+        u(IDN, k, j, i) = d;
+        u(IM1, k, j, i) = 0.1 * d * s3;
+        u(IM2, k, j, i) = 0.0;
+        u(IM3, k, j, i) = -0.05 * d * s1;
+        u(IEN, k, j, i) = p / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM3, k, j, i))) / d;
+      }
+  if (MAGNETIC_FIELDS_ENABLED) {
+    FaceField &b = pmb->pfield->b;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie + 1; ++i) b.x1f(k, j, i) = b0;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je + 1; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x2f(k, j, i) = 0.5 * b0;
+    for (int k = pmb->ks; k <= pmb->ke + 1; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) b.x3f(k, j, i) = 0.0;
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) u(IEN, k, j, i) += 0.5 * (SQR(b0) + SQR(0.5 * b0));
+  }
+}
+}  // namespace usrsrc
+
+//========================================================================================
 static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
     {"blast", nullptr, BlastGenerator, nullptr},
@@ -1171,6 +1240,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
     {"field_loop", nullptr, FieldLoopGenerator, nullptr},
     {"jet", jet::JetInit, jet::JetGenerator, nullptr},
+    {"usrsrc", usrsrc::Init, usrsrc::Generator, nullptr},
 };
 
 const ProblemGeneratorEntry *FindProblemGenerator(const std::string &name) {

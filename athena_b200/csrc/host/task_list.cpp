@@ -9,32 +9,32 @@
 TimeIntegratorTaskList::TimeIntegratorTaskList(ParameterInput *pin, Mesh *pm) {
   integrator = pin->GetOrAddString("time", "integrator", "vl2");
   std::stringstream msg;
-  // (ebeta: fraction of dt reached at the end of the stage, handed to boundary functions)
-  auto set = [&](int n, Real delta, Real g1, Real g2, Real g3, Real beta, Real ebeta) {
-    stage_wghts[n] = IntegratorWeight{delta, g1, g2, g3, beta, ebeta};
+  // (ebeta / sbeta: fraction of dt at the end / beginning of the stage, handed to boundary / source functions)
+  auto set = [&](int n, Real delta, Real g1, Real g2, Real g3, Real beta, Real ebeta, Real sbeta) {
+    stage_wghts[n] = IntegratorWeight{delta, g1, g2, g3, beta, ebeta, sbeta};
   };
   if (integrator == "vl2") {
     nstages = 2;
     cfl_limit = 1.0;
     if (pm->ndim == 2) cfl_limit = 0.5;
     if (pm->ndim == 3) cfl_limit = 0.5;
-    set(0, 1.0, 0.0, 1.0, 0.0, 0.5, 0.5);
-    set(1, 0.0, 0.0, 1.0, 0.0, 1.0, 1.0);
+    set(0, 1.0, 0.0, 1.0, 0.0, 0.5, 0.5, 0.0);
+    set(1, 0.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.5);
   } else if (integrator == "rk1") {
     nstages = 1;
     cfl_limit = 1.0;
-    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0);
+    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0);
   } else if (integrator == "rk2") {
     nstages = 2;
     cfl_limit = 1.0;
-    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0);
-    set(1, 0.0, 0.5, 0.5, 0.0, 0.5, 1.0);
+    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0);
+    set(1, 0.0, 0.5, 0.5, 0.0, 0.5, 1.0, 1.0);
   } else if (integrator == "rk3") {
     nstages = 3;
     cfl_limit = 1.0;
-    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0);
-    set(1, 0.0, 0.25, 0.75, 0.0, 0.25, 0.5);
-    set(2, 0.0, TWO_3RD, ONE_3RD, 0.0, TWO_3RD, 1.0);
+    set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0);
+    set(1, 0.0, 0.25, 0.75, 0.0, 0.25, 0.5, 1.0);
+    set(2, 0.0, TWO_3RD, ONE_3RD, 0.0, TWO_3RD, 1.0, 0.5);
   } else {
     msg << "### FATAL ERROR in TimeIntegratorTaskList constructor" << std::endl
         << "integrator=" << integrator << " not valid time integrator" << std::endl;
@@ -80,6 +80,8 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   auto all = [&](auto &&fn) { for (athk_ctx *a : pm->ctx) AthkCheck(fn(a), who); };
   // what PhysicalBoundary hands to user-enrolled boundary functions (:2284-2287)
   all([&](athk_ctx *a) { return athk_set_boundary_time(a, pm->time + sw.ebeta * dt, sw.beta * dt); });
+  // ... and AddSourceTerms to user source functions: the time at the beginning of the stage (:1901-1903)
+  all([&](athk_ctx *a) { return athk_set_source_time(a, pm->time + sw.sbeta * dt); });
   if (pm->fused_stage) {
     athk_stage_wghts w = {sw.delta, sw.gamma_1, sw.gamma_2, sw.gamma_3, sw.beta};
     if (pm->ngpu == 1) {

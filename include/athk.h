@@ -200,6 +200,26 @@ typedef struct athk_bval_args {
 } athk_bval_args;
 typedef int (*athk_bval_fn)(void *user, const athk_bval_args *args);
 int athk_enroll_user_boundary(athk_ctx *ctx, int face, athk_bval_fn fn, void *user);
+/* User-enrolled explicit source terms: SrcTermFunc (athena.hpp:218-222), Mesh::EnrollUserExplicit
+ * SourceFunction (mesh.cpp:1345), called last by HydroSourceTerms::AddSourceTerms (hydro/srcterms/
+ * hydro_srcterms.cpp:151-154).  Like the boundary hook, the function is a HOST callback invoked once per
+ * local MeshBlock by athk_add_source_terms (and by athk_stage, after INT_HYD); it adds its terms to
+ * the conserved register u (and s) of the active zone from the stage-input primitives w (bcc, r) by
+ * enqueueing device work on args->stream.  time = beginning of the stage (athk_set_source_time,
+ * time_integrator.cpp:1901-1903), dt = beta*dt_mesh.  Same array layout as athk_bval_args. */
+typedef struct athk_src_args {
+  int lb;
+  double time, dt;
+  int is, ie, js, je, ks, ke;
+  const double *w, *bcc, *r;     /* DEVICE pointers of this block (bcc, r null without MHD / scalars) */
+  double *u, *s;
+  long long stride_j, stride_k, stride_n;
+  int nscalars;
+  void *stream;
+} athk_src_args;
+typedef int (*athk_src_fn)(void *user, const athk_src_args *args);
+int athk_enroll_user_source(athk_ctx *ctx, athk_src_fn fn, void *user);
+int athk_set_source_time(athk_ctx *ctx, double time);
 /* ---- static mesh refinement, cell-centred variables (hydro) ---------------------------------
  * The host owns the block tree and the neighbour levels (MeshBlockTree, BoundaryBase::
  * SearchAndSetNeighbors) and hands the library, per phase of the boundary exchange, the list of

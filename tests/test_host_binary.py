@@ -119,7 +119,30 @@ def refined(blocks, *regions):
     return blocks
 
 
+def usrsrc_blocks(mhd, integrator):
+    b = {
+        "job": {"problem_id": "usrsrc"},
+        "output1": {"file_type": "hst", "dt": 0.05, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 0.1},
+        "time": {"cfl_number": 0.3, "nlim": -1, "tlim": 0.2, "integrator": integrator, "xorder": 2, "ncycle_out": 1},
+        "mesh": {"nx1": 16, "x1min": -0.5, "x1max": 0.5, "ix1_bc": "periodic", "ox1_bc": "periodic",
+                 "nx2": 16, "x2min": -0.5, "x2max": 0.5, "ix2_bc": "periodic", "ox2_bc": "periodic",
+                 "nx3": 24, "x3min": -0.75, "x3max": 0.75, "ix3_bc": "periodic", "ox3_bc": "periodic",
+                 "num_threads": 1},
+        "meshblock": {"nx1": 8, "nx2": 8, "nx3": 12},
+        "hydro": {"gamma": 1.4},
+        "problem": {"amp": 0.2, "g0": 0.8, "tcool": 0.5},
+    }
+    if mhd:
+        b["problem"]["b0"] = 0.3
+    return b
+
+
 CASES = {
+    # user-enrolled explicit source terms (SrcTermFunc, time-dependent) -- the reference
+    # side is the unmodified reference linked with the user problem file oracle/pgen/usrsrc.cpp
+    "user_source_hydro_rk3": ("usrsrc_hydro_hllc", "usrsrc", False, lambda: usrsrc_blocks(False, "rk3")),
+    "user_source_mhd_vl2": ("usrsrc_mhd_hlld", "usrsrc", True, lambda: usrsrc_blocks(True, "vl2")),
     # static mesh refinement, hydro (restriction / prolongation of the cell-centred
     # variables, flux correction).  The reference's own linear-wave regression runs refined.
     "smr_linwave_hydro_centre": ("linwave_hydro_hllc", "linear_wave", False, lambda: refined(
@@ -280,7 +303,8 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
 
 
 @pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe",
-                                  "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes", "jet_user_bc_mhd_rk3"])
+                                  "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes", "jet_user_bc_mhd_rk3",
+                                  "user_source_mhd_vl2"])
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
