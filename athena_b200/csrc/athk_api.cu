@@ -11,6 +11,8 @@ ATHK_EXTERN_RS(athk::RS_HLLE, false)
 ATHK_EXTERN_RS(athk::RS_HLLE, true)
 ATHK_EXTERN_RS(athk::RS_LLF, false)
 ATHK_EXTERN_RS(athk::RS_LLF, true)
+ATHK_EXTERN_RS(athk::RS_HLLE_ISO, false)   // athk_rs_iso.cu
+ATHK_EXTERN_RS(athk::RS_HLLD_ISO, true)
 #ifndef ATHK_EMULATE
 ATHK_EXTERN_RS_FAST(athk::RS_HLLC, false)   // athk_fast.cu (--fmad=true)
 ATHK_EXTERN_RS_FAST(athk::RS_HLLD, true)
@@ -22,6 +24,8 @@ static thread_local std::string g_last_error;
 int athk_p2p_before_ghost_fill(athk_ctx *c);
 int athk_p2p_before_emf_apply(athk_ctx *c);
 int athk_p2p_after_pack(athk_ctx *c, int which);
+static int ghost_pack_early(athk_ctx *c, int reg);
+static int ghost_pack_finish(athk_ctx *c, int reg);
 
 #undef fail
 int athk_fail(int code, const char *fmt, ...) {
@@ -67,9 +71,17 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     return fail(ATHK_ERR_ARG, "athk_create: rsolver HLLC is hydro-only (use HLLD, Roe, HLLE or LLF with mhd=1)");
   if (!cfg->mhd && cfg->rsolver == ATHK_RS_HLLD)
     return fail(ATHK_ERR_ARG, "athk_create: rsolver HLLD needs mhd=1 (use HLLC, Roe, HLLE or LLF)");
-  if (!(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
+  if (cfg->eos != ATHK_EOS_ISOTHERMAL && !(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
   if (cfg->arith != ATHK_ARITH_STRICT && cfg->arith != ATHK_ARITH_FAST)
     return fail(ATHK_ERR_ARG, "athk_create: arith must be ATHK_ARITH_STRICT (0) or ATHK_ARITH_FAST (1)");
+  if (cfg->eos != ATHK_EOS_ADIABATIC && cfg->eos != ATHK_EOS_ISOTHERMAL)
+    return fail(ATHK_ERR_ARG, "athk_create: unknown eos %d", cfg->eos);
+  if (cfg->eos == ATHK_EOS_ISOTHERMAL) {
+    if (!(cfg->iso_sound_speed > 0.0)) return fail(ATHK_ERR_ARG, "athk_create: isothermal EOS needs iso_sound_speed > 0");
+    if (cfg->rsolver != (cfg->mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE))
+      return fail(ATHK_ERR_ARG, "athk_create: the isothermal EOS is implemented with rsolver HLLE (hydro) and HLLD (mhd)");
+    if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for the isothermal EOS");
+  }
   if (cfg->arith == ATHK_ARITH_FAST && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_HLLD)
     return fail(ATHK_ERR_ARG, "athk_create: the fast-arithmetic kernel set exists for HLLC / HLLD only");
   int ndev = 0;
@@ -98,6 +110,8 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->eos = make_eos(cfg->gamma, cfg->dfloor > 0 ? cfg->dfloor : fmin_default,
                     cfg->pfloor > 0 ? cfg->pfloor : fmin_default,
                     cfg->sfloor > 0 ? cfg->sfloor : fmin_default);
+  c->eos.iso = (cfg->eos == ATHK_EOS_ISOTHERMAL) ? 1 : 0;
+  c->eos.iso_cs = cfg->iso_sound_speed;
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
   c->dt_requested = c->dt_valid = false;
@@ -188,6 +202,9 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
   cudaFree(c->p2p.gdst); cudaFree(c->p2p.edst); cudaFree(c->p2p.peer_flags); cudaFree(c->p2p.timeouts);
+#ifndef ATHK_EMULATE
+  if (c->p2p.side) { cudaStreamDestroy(c->p2p.side); cudaEventDestroy(c->p2p.ev_ready); cudaEventDestroy(c->p2p.ev_packed); }
+#endif
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -299,9 +316,10 @@ struct ArrDesc {
 static bool describe(athk_ctx *c, int array, ArrDesc *d) {
   const int ns = c->cfg.nscalars;
   switch (array) {
+    // (isothermal EOS: the host's arrays have NHYDRO = 4 components; the device's fifth stays zero)
     case ATHK_U: case ATHK_U1: case ATHK_U2:
-      *d = {c->u[array - ATHK_U], 5, 0, 5, 0, 0, 0}; break;
-    case ATHK_W: *d = {c->w, 5, 0, 5, 0, 0, 0}; break;
+      *d = {c->u[array - ATHK_U], 5, 0, c->eos.iso ? 4 : 5, 0, 0, 0}; break;
+    case ATHK_W: *d = {c->w, 5, 0, c->eos.iso ? 4 : 5, 0, 0, 0}; break;
     case ATHK_BCC: *d = {c->bcc, 3, 0, 3, 0, 0, 0}; break;
     case ATHK_B_X1F: case ATHK_B_X2F: case ATHK_B_X3F: {
       const int q = array - ATHK_B_X1F;
@@ -639,6 +657,8 @@ extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int
   int rc = check_order(c, order, "calculate_fluxes");
   if (rc) return rc;
   const bool mhd = c->cfg.mhd != 0;
+  if (c->eos.iso)
+    return mhd ? athk_flux3_rs<RS_HLLD_ISO, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLE_ISO, false>(c, order, dt_mesh, breg);
   switch (c->cfg.rsolver) {
     case ATHK_RS_ROE: return mhd ? athk_flux3_rs<RS_ROE, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_ROE, false>(c, order, dt_mesh, breg);
     case ATHK_RS_HLLE: return mhd ? athk_flux3_rs<RS_HLLE, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLE, false>(c, order, dt_mesh, breg);
@@ -1062,6 +1082,7 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   if (c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for hydro (face-centred "
                                             "restriction / prolongation and the EMF correction are not)");
   if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "refine_enable: passive scalars are not refined");
+  if (c->eos.iso) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for the adiabatic EOS");
   const Grid &g = c->g;
   if (g.nx1 % 2 || g.nx2 % 2 || g.nx3 % 2)   // mesh.cpp:340-346
     return fail(ATHK_ERR_ARG, "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR.");
@@ -1243,7 +1264,7 @@ extern "C" int athk_add_source_terms(athk_ctx *c, double beta_dt) {
   const Grid &g = c->g;
   if (!(c->gacc[0] == 0.0 && c->gacc[1] == 0.0 && c->gacc[2] == 0.0)) {
     Range3 r = {g.ks, g.ke, g.js, g.je, g.is, g.ie};
-    ConstAccPoint f = {g, c->w, c->u[0], beta_dt, c->gacc[0], c->gacc[1], c->gacc[2]};
+    ConstAccPoint f = {g, c->w, c->u[0], beta_dt, c->gacc[0], c->gacc[1], c->gacc[2], c->eos.iso};
     LAUNCH_NAMED(c, "athk_add_source_terms", launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, r, f));
   }
   if (c->user_src) {   // user-defined source terms come last (hydro_srcterms.cpp:151-154)
@@ -1406,6 +1427,9 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       for (int d = 0; d < 3; ++d) a.mf[d] = c->sflux[d];
       a.mf_bstride = (idx_t)ns * g.sn;
     }
+    if (c->eos.iso) {
+      rc = mhd ? athk_sweeps_rs<RS_HLLD_ISO, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLE_ISO, false, 0>(c, order, a);
+    } else
     switch (c->cfg.rsolver) {
       case ATHK_RS_ROE: rc = mhd ? athk_sweeps_rs<RS_ROE, true, 0>(c, order, a) : athk_sweeps_rs<RS_ROE, false, 0>(c, order, a); break;
       case ATHK_RS_HLLE: rc = mhd ? athk_sweeps_rs<RS_HLLE, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLE, false, 0>(c, order, a); break;
@@ -1433,6 +1457,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       if (rc) return rc;
       if (swap) { Real *t = c->s[0]; c->s[0] = c->s[1]; c->s[1] = t; }
     }
+    if (!split && (rc = ghost_pack_early(c, 0))) return rc;   // u (and s) are final: send them now
     if (mhd) {
       if ((rc = corner_e_part(c, split ? 1 : 0))) return rc;
       if ((rc = athk_send_flux_correction(c))) return rc;
@@ -1461,7 +1486,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       LAUNCH_NAMED(c, "ct_integrate", launch_points_kcol<ATHK_CT_MINB>(c->stream, g.nb, r, c->kt_ct, f));
       if (swap) { Real *t = c->b[0]; c->b[0] = c->b[1]; c->b[1] = t; }
     }
-    return athk_remote_pack_ghosts(c, 0);
+    return ghost_pack_finish(c, 0);
   }
   if ((rc = exchange_ghosts_mode(c, (mhd ? 3 : 1) | (ns ? 4 : 0), 0, split ? 2 : 0))) return rc;
   if ((rc = cons2prim_part(c, 0, split ? 2 : 0))) return rc;
@@ -1552,10 +1577,52 @@ extern "C" int athk_remote_pack_ghosts(athk_ctx *c, int reg) {
     rl.gdst = c->p2p.gdst + (c->p2p.gseq & 1) * (size_t)c->rl.n;
   }
   RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, rl, c->u[reg],
-                       c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr};
+                       c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr, 0};
   LAUNCH_NAMED(c, __func__, launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
   if (c->p2p.on) return athk_p2p_after_pack(c, 0);
   return ATHK_OK;
+}
+
+// Peer-to-peer transport only: the cell-centred sections of the next ghost message, packed on the
+// side stream as soon as the registers are final (after the sweeps), while the main stream goes on
+// with corner E / EMF correction / CT.  ghost_pack_finish adds the face-field sections and raises
+// the flags.  (Message n+1 lands in the buffer half the receiver read message n-1 from; it has
+// finished with it: it sent message n after that read, and this GPU waited for message n before
+// the sweeps that precede this pack.)
+static int ghost_pack_early(athk_ctx *c, int reg) {
+#ifndef ATHK_EMULATE
+  if (!c->p2p.on || c->rl.n == 0 || !c->p2p.side) return ATHK_OK;
+  c->p2p.gseq++;
+  RemoteLinks rl = c->rl;
+  rl.gdst = c->p2p.gdst + (c->p2p.gseq & 1) * (size_t)c->rl.n;
+  RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, rl, c->u[reg],
+                       c->cfg.mhd ? c->b[reg] : nullptr, c->cfg.nscalars ? c->s[reg] : nullptr, 1};
+  CU(cudaEventRecord(c->p2p.ev_ready, c->stream));
+  CU(cudaStreamWaitEvent(c->p2p.side, c->p2p.ev_ready, 0));
+  CU(launch_links(c->p2p.side, c->rl.n, c->max_ghost_count, f));
+  c->launches++;
+  CU(cudaEventRecord(c->p2p.ev_packed, c->p2p.side));
+  c->p2p.early_pending = true;
+#endif
+  return ATHK_OK;
+}
+
+static int ghost_pack_finish(athk_ctx *c, int reg) {
+#ifndef ATHK_EMULATE
+  if (c->p2p.on && c->p2p.early_pending) {
+    c->p2p.early_pending = false;
+    if (c->cfg.mhd) {
+      RemoteLinks rl = c->rl;
+      rl.gdst = c->p2p.gdst + (c->p2p.gseq & 1) * (size_t)c->rl.n;
+      RemoteGhostPack f = {c->g, c->cfg.mhd, c->cfg.nscalars, rl, c->u[reg], c->b[reg],
+                           c->cfg.nscalars ? c->s[reg] : nullptr, 2};
+      LAUNCH_NAMED(c, "athk_remote_pack_ghosts", launch_links(c->stream, c->rl.n, c->max_ghost_count, f));
+    }
+    CU(cudaStreamWaitEvent(c->stream, c->p2p.ev_packed, 0));
+    return athk_p2p_after_pack(c, 0);
+  }
+#endif
+  return athk_remote_pack_ghosts(c, reg);
 }
 
 extern "C" int athk_remote_pack_emf(athk_ctx *c) {
@@ -1688,6 +1755,13 @@ extern "C" int athk_remote_set_p2p(athk_ctx *c, int npeers, double *const *ghost
   p.my_flags = my_flags;
   p.gseq = p.eseq = 0;
   p.on = true;
+#ifndef ATHK_EMULATE
+  if (!p.side && !getenv("ATHK_NO_EARLY_PACK")) {   // side stream of the early ghost pack (ghost_pack_early)
+    CU(cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&p.ev_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p.ev_packed, cudaEventDisableTiming));
+  }
+#endif
   return ATHK_OK;
 }
 

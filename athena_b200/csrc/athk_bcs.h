@@ -142,10 +142,11 @@ struct PhysBCConsPoint {
       bc[0] = bcc1;
       bc[g.sn] = bcc2;
       bc[2 * g.sn] = bcc3;
-      ub[4 * g.sn] = w_p * igm1 + 0.5 * (w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz)) +
-                                         (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
+      if (!eos.iso)   // (isothermal EOS: no energy, eos/isothermal_mhd.cpp:88-112)
+        ub[4 * g.sn] = w_p * igm1 + 0.5 * (w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz)) +
+                                           (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
     } else {
-      ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
+      if (!eos.iso) ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
     }
     for (int n = 0; n < ns; ++n) {
       const idx_t o = ((idx_t)blk * ns + n) * g.sn + c;

@@ -114,6 +114,11 @@ struct athk_ctx {
     unsigned long long *my_flags = nullptr;           // [npeers][2]
     unsigned long long gseq = 0, eseq = 0;            // messages sent so far
     unsigned long long *timeouts = nullptr;           // device counter
+    // the hydro (and scalar) part of a ghost message is final once the sweeps are done: it is packed
+    // -- i.e. sent over NVLink -- on a side stream under corner E / EMF correction / CT
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_packed = nullptr;
+    bool early_pending = false;
   } p2p;
 };
 

@@ -52,6 +52,7 @@ struct ConstAccPoint {
   Real *u;         // [nb][5][sn] conserved register the stage has just written
   Real dt;         // beta * dt_mesh
   Real g1, g2, g3;
+  int iso;         // isothermal EOS: no energy source (constant_acc.cpp:38: if (NON_BAROTROPIC_EOS))
   ATHK_HD void operator()(int blk, int k, int j, int i) const {
     const idx_t c = gidx(g, k, j, i);
     const Real *wb = w + (idx_t)blk * 5 * g.sn + c;
@@ -73,7 +74,7 @@ struct ConstAccPoint {
       ub[(idx_t)IM3 * g.sn] += src;
       e += src * wb[(idx_t)IVZ * g.sn];
     }
-    ub[(idx_t)IEN * g.sn] = e;
+    if (!iso) ub[(idx_t)IEN * g.sn] = e;
   }
 };
 
@@ -139,9 +140,11 @@ struct Cons2PrimPoint {
       bc[0] = bc1;
       bc[g.sn] = bc2;
       bc[2 * g.sn] = bc3;
-      cons2prim_mhd(eos_of_block(eos, blk), uc, bc1, bc2, bc3, wc);
+      if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
+      else cons2prim_mhd(eos_of_block(eos, blk), uc, bc1, bc2, bc3, wc);
     } else {
-      cons2prim_hydro(eos_of_block(eos, blk), uc, wc);
+      if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
+      else cons2prim_hydro(eos_of_block(eos, blk), uc, wc);
     }
     if (uc[IDN] != d0) ub[IDN * g.sn] = uc[IDN];
     if (uc[IEN] != e0) ub[IEN * g.sn] = uc[IEN];
@@ -168,13 +171,21 @@ struct Cons2PrimPoint {
         const Real b1 = 0.5 * bb[0] + 0.5 * bb[1], b2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj],
                    b3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
         Real bx = b1 + fabs(bb[0] - b1);
+        if (eos.iso) {   // (isothermal EOS: compiler operations, eos/isothermal_mhd.cpp:121)
+          dt1 = dt1 / max_std(0.0, (fabs(wc[IVX]) + fast_speed_iso(eos, wc[IDN], b2, b3, bx)));
+          bx = b2 + fabs(bb[g.sn] - b2);
+          dt2 = dt2 / max_std(0.0, (fabs(wc[IVY]) + fast_speed_iso(eos, wc[IDN], b3, b1, bx)));
+          bx = b3 + fabs(bb[2 * g.sn] - b3);
+          dt3 = dt3 / max_std(0.0, (fabs(wc[IVZ]) + fast_speed_iso(eos, wc[IDN], b1, b2, bx)));
+        } else {
         dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b2, b3, bx))));
         bx = b2 + fabs(bb[g.sn] - b2);
         dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b3, b1, bx))));
         bx = b3 + fabs(bb[2 * g.sn] - b3);
         dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b1, b2, bx))));
+        }
       } else {
-        const Real cs = m.sqrt(m.div(eos.gamma * wc[IPR], wc[IDN]));
+        const Real cs = eos.iso ? eos.iso_cs : m.sqrt(m.div(eos.gamma * wc[IPR], wc[IDN]));
         dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + cs)));
         dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + cs)));
         dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + cs)));
@@ -666,6 +677,7 @@ struct RemoteGhostPack {
   int mhd, nscal;
   RemoteLinks rl;
   const Real *u, *b, *s;
+  int part;   // 0 the whole message; 1 its cell-centred sections (u, s); 2 its face-field sections
   // (link, e): e = element index inside the link's message
   ATHK_HD void operator()(int link, idx_t e) const {
     const int o1 = rl.o1[link], o2 = rl.o2[link], o3 = rl.o3[link], blk = rl.lb[link];
@@ -675,6 +687,10 @@ struct RemoteGhostPack {
     const Slab cc = rl.tab->slab[os][0];
     idx_t base = 0;
     const idx_t ncc = cc.count();
+    if (part != 0) {   // is e in a section this launch packs?
+      const bool in_fc = (e >= rl.tab->sec[os][1] && e < rl.tab->sec[os][4]);
+      if ((part == 2) != in_fc) return;
+    }
     if (e < 5 * ncc) {
       const int n = (int)(e / ncc);
       idx_t q = e - n * ncc;
@@ -859,16 +875,16 @@ struct CellDt {
       const Real *bf = b + (idx_t)blk * 3 * g.sn + c;
       const Real b1 = bc[0], b2 = bc[g.sn], b3 = bc[2 * g.sn];
       Real bx = b1 + fabs(bf[0] - b1);
-      Real cf = fast_speed(eos, d, p, b2, b3, bx);
+      Real cf = eos.iso ? fast_speed_iso(eos, d, b2, b3, bx) : fast_speed(eos, d, p, b2, b3, bx);
       dt1 /= max_std(0.0, (fabs(vx) + cf));
       bx = b2 + fabs(bf[g.sn] - b2);
-      cf = fast_speed(eos, d, p, b3, b1, bx);
+      cf = eos.iso ? fast_speed_iso(eos, d, b3, b1, bx) : fast_speed(eos, d, p, b3, b1, bx);
       dt2 /= max_std(0.0, (fabs(vy) + cf));
       bx = b3 + fabs(bf[2 * g.sn] - b3);
-      cf = fast_speed(eos, d, p, b1, b2, bx);
+      cf = eos.iso ? fast_speed_iso(eos, d, b1, b2, bx) : fast_speed(eos, d, p, b1, b2, bx);
       dt3 /= max_std(0.0, (fabs(vz) + cf));
     } else {
-      const Real cs = sound_speed(eos, d, p);
+      const Real cs = eos.iso ? eos.iso_cs : sound_speed(eos, d, p);
       dt1 /= max_std(0.0, (fabs(vx) + cs));
       dt2 /= max_std(0.0, (fabs(vy) + cs));
       dt3 /= max_std(0.0, (fabs(vz) + cs));

@@ -51,6 +51,11 @@ struct EosParams {
   // 161-163), and they can differ: null = the three values above for every block, else
   // [nb][3] = (dfloor, pfloor, sfloor) of each local block (athk_set_block_floors)
   const Real *blk_floors;
+  // isothermal EOS (eos/isothermal_hydro.cpp, isothermal_mhd.cpp): p = iso_cs^2 * rho, no energy
+  // equation.  The registers keep their five components; the fifth stays zero (zero flux, zero
+  // source) and the pressure slot of w is a dummy.
+  int iso;
+  Real iso_cs;
 };
 
 // floors of block blk (uniform branch; a no-op unless per-block floors were set)
@@ -76,6 +81,8 @@ ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
   e.pfloor = pfloor;
   e.sfloor = sfloor;
   e.blk_floors = nullptr;
+  e.iso = 0;
+  e.iso_cs = 0.0;
   return e;
 }
 
@@ -110,6 +117,26 @@ ATHK_HD void cons2prim_mhd(const EosParams &eos, Real u[5], Real bc1, Real bc2, 
   Real p = eos.gm1 * (u[IEN] - e_k - pb);
   u[IEN] = (p > eos.pfloor) ? u[IEN] : ((eos.pfloor / eos.gm1) + e_k + pb);
   w[IPR] = (p > eos.pfloor) ? p : eos.pfloor;
+}
+
+// eos/isothermal_hydro.cpp:50-72, isothermal_mhd.cpp:60-78: density floor, velocities; nothing else
+ATHK_HD void cons2prim_iso(const EosParams &eos, Real u[5], Real w[5]) {
+  u[IDN] = (u[IDN] > eos.dfloor) ? u[IDN] : eos.dfloor;
+  w[IDN] = u[IDN];
+  Real di = 1.0 / u[IDN];
+  w[IVX] = u[IM1] * di;
+  w[IVY] = u[IM2] * di;
+  w[IVZ] = u[IM3] * di;
+  w[IPR] = 0.0;
+}
+// eos/isothermal_mhd.cpp:121-129
+ATHK_HD Real fast_speed_iso(const EosParams &eos, Real d, Real by, Real bz, Real bx) {
+  Real asq = (eos.iso_cs * eos.iso_cs) * d;
+  Real vaxsq = bx * bx;
+  Real ct2 = by * by + bz * bz;
+  Real qsq = vaxsq + ct2 + asq;
+  Real tmp = vaxsq + ct2 - asq;
+  return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
 }
 
 // eos/adiabatic_hydro.cpp SoundSpeed ; eos/adiabatic_mhd.cpp:149-156 FastMagnetosonicSpeed

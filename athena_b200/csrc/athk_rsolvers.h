@@ -15,7 +15,8 @@
 
 namespace athk {
 
-enum { RS_HLLC = 0, RS_HLLD = 1, RS_ROE = 2, RS_HLLE = 3, RS_LLF = 4 };   // == enum athk_rsolver
+enum { RS_HLLC = 0, RS_HLLD = 1, RS_ROE = 2, RS_HLLE = 3, RS_LLF = 4,   // == enum athk_rsolver
+       RS_HLLE_ISO = 5, RS_HLLD_ISO = 6 };   // isothermal EOS: hlle.cpp's barotropic branch, hlld_iso.cpp
 
 //----------------------------------------------------------------------------------------
 ATHK_HD void hlle_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
@@ -558,6 +559,141 @@ ATHK_HD void roe_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[
 }
 
 //----------------------------------------------------------------------------------------
+// Isothermal EOS.  HLLE for hydro: hydro/rsolvers/hydro/hlle.cpp:56-150 with NON_BAROTROPIC_EOS == 0
+// (Roe-averaged velocity, a = iso_cs); the energy flux is zero.
+ATHK_HD void hlle_iso_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real iso_cs = eos.iso_cs;
+  Real fl[4], fr[4];
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  Real wroe_vx = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  Real cl = iso_cs, cr = iso_cs;   // EquationOfState::SoundSpeed (isothermal_hydro.cpp)
+  Real a = iso_cs;
+  Real al = min_std((wroe_vx - a), (wl[IVX] - cl));
+  Real ar = max_std((wroe_vx + a), (wr[IVX] + cr));
+  Real bp = ar > 0.0 ? ar : 0.0;
+  Real bm = al < 0.0 ? al : 0.0;
+  Real vxl = wl[IVX] - bm;
+  Real vxr = wr[IVX] - bp;
+  fl[IDN] = wl[IDN] * vxl;
+  fr[IDN] = wr[IDN] * vxr;
+  fl[IVX] = wl[IDN] * wl[IVX] * vxl;
+  fr[IVX] = wr[IDN] * wr[IVX] * vxr;
+  fl[IVY] = wl[IDN] * wl[IVY] * vxl;
+  fr[IVY] = wr[IDN] * wr[IVY] * vxr;
+  fl[IVZ] = wl[IDN] * wl[IVZ] * vxl;
+  fr[IVZ] = wr[IDN] * wr[IVZ] * vxr;
+  fl[IVX] += (iso_cs * iso_cs) * wl[IDN];
+  fr[IVX] += (iso_cs * iso_cs) * wr[IDN];
+  Real tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+#pragma unroll
+  for (int n = 0; n < 4; ++n) f[n] = 0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp;
+  f[IEN] = 0.0;
+}
+
+// HLLD for isothermal MHD (Mignone 2007): hydro/rsolvers/mhd/hlld_iso.cpp:52-245.
+// wl/wr = (d, vx, vy, vz, -, by, bz); f = (mass, mx, my, mz, 0, by-flux, bz-flux)
+ATHK_HD void hlld_iso_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi, Real f[7]) {
+  const Real SMALL_NUMBER = 1.0e-4;
+  const Real dfloor = eos.dfloor, cs = eos.iso_cs;
+  Real spd[5];
+  struct C6 { Real d, mx, my, mz, by, bz; } ul, ur, ulst, urst, ucst, fl, fr;
+  ul.d = wl[IDN]; ul.mx = wl[IVX] * ul.d; ul.my = wl[IVY] * ul.d; ul.mz = wl[IVZ] * ul.d; ul.by = wl[IBY]; ul.bz = wl[IBZ];
+  ur.d = wr[IDN]; ur.mx = wr[IVX] * ur.d; ur.my = wr[IVY] * ur.d; ur.mz = wr[IVZ] * ur.d; ur.by = wr[IBY]; ur.bz = wr[IBZ];
+  Real cfl = fast_speed_iso(eos, wl[IDN], wl[IBY], wl[IBZ], bxi);
+  Real cfr = fast_speed_iso(eos, wr[IDN], wr[IBY], wr[IBZ], bxi);
+  spd[0] = min_std(wl[IVX] - cfl, wr[IVX] - cfr);
+  spd[4] = max_std(wl[IVX] + cfl, wr[IVX] + cfr);
+  Real bxsq = bxi * bxi;
+  Real ptl = sqr(cs) * wl[IDN] + 0.5 * (bxsq + sqr(wl[IBY]) + sqr(wl[IBZ]));
+  Real ptr = sqr(cs) * wr[IDN] + 0.5 * (bxsq + sqr(wr[IBY]) + sqr(wr[IBZ]));
+  fl.d = ul.mx;
+  fl.mx = ul.mx * wl[IVX] + ptl - bxsq;
+  fl.my = ul.my * wl[IVX] - bxi * ul.by;
+  fl.mz = ul.mz * wl[IVX] - bxi * ul.bz;
+  fl.by = ul.by * wl[IVX] - bxi * wl[IVY];
+  fl.bz = ul.bz * wl[IVX] - bxi * wl[IVZ];
+  fr.d = ur.mx;
+  fr.mx = ur.mx * wr[IVX] + ptr - bxsq;
+  fr.my = ur.my * wr[IVX] - bxi * ur.by;
+  fr.mz = ur.mz * wr[IVX] - bxi * ur.bz;
+  fr.by = ur.by * wr[IVX] - bxi * wr[IVY];
+  fr.bz = ur.bz * wr[IVX] - bxi * wr[IVZ];
+  Real idspd = 1.0 / (spd[4] - spd[0]);
+  Real dhll = (spd[4] * ur.d - spd[0] * ul.d - fr.d + fl.d) * idspd;
+  dhll = max_std(dhll, dfloor);
+  Real sqrtdhll = sqrt(dhll);
+  Real fdhll = (spd[4] * fl.d - spd[0] * fr.d + spd[4] * spd[0] * (ur.d - ul.d)) * idspd;
+  Real fmxhll = (spd[4] * fl.mx - spd[0] * fr.mx + spd[4] * spd[0] * (ur.mx - ul.mx)) * idspd;
+  Real ustar = fdhll / dhll;
+  Real mxhll = (spd[4] * ur.mx - spd[0] * ul.mx - fr.mx + fl.mx) * idspd;
+  spd[1] = ustar - fabs(bxi) / sqrtdhll;
+  spd[3] = ustar + fabs(bxi) / sqrtdhll;
+  ulst.d = dhll;
+  ulst.mx = mxhll;
+  Real tmp = (spd[0] - spd[1]) * (spd[0] - spd[3]);
+  if (fabs(spd[0] - spd[1]) < (SMALL_NUMBER)*cs) {
+    ulst.my = ul.my; ulst.mz = ul.mz; ulst.by = ul.by; ulst.bz = ul.bz;
+  } else {
+    Real mfact = bxi * (ustar - wl[IVX]) / tmp;
+    Real bfact = (ul.d * sqr(spd[0] - wl[IVX]) - bxsq) / (dhll * tmp);
+    ulst.my = dhll * wl[IVY] - ul.by * mfact;
+    ulst.mz = dhll * wl[IVZ] - ul.bz * mfact;
+    ulst.by = ul.by * bfact;
+    ulst.bz = ul.bz * bfact;
+  }
+  urst.d = dhll;
+  urst.mx = mxhll;
+  tmp = (spd[4] - spd[1]) * (spd[4] - spd[3]);
+  if (fabs(spd[4] - spd[3]) < (SMALL_NUMBER)*cs) {
+    urst.my = ur.my; urst.mz = ur.mz; urst.by = ur.by; urst.bz = ur.bz;
+  } else {
+    Real mfact = bxi * (ustar - wr[IVX]) / tmp;
+    Real bfact = (ur.d * sqr(spd[4] - wr[IVX]) - bxsq) / (dhll * tmp);
+    urst.my = dhll * wr[IVY] - ur.by * mfact;
+    urst.mz = dhll * wr[IVZ] - ur.bz * mfact;
+    urst.by = ur.by * bfact;
+    urst.bz = ur.bz * bfact;
+  }
+  Real x = sqrtdhll * (bxi > 0.0 ? 1.0 : -1.0);
+  ucst.d = dhll;
+  ucst.mx = mxhll;
+  ucst.my = 0.5 * (ulst.my + urst.my + (urst.by - ulst.by) * x);
+  ucst.mz = 0.5 * (ulst.mz + urst.mz + (urst.bz - ulst.bz) * x);
+  ucst.by = 0.5 * (ulst.by + urst.by + (urst.my - ulst.my) / x);
+  ucst.bz = 0.5 * (ulst.bz + urst.bz + (urst.mz - ulst.mz) / x);
+  if (spd[0] >= 0.0) {
+    f[IDN] = fl.d; f[IVX] = fl.mx; f[IVY] = fl.my; f[IVZ] = fl.mz; f[IBY] = fl.by; f[IBZ] = fl.bz;
+  } else if (spd[4] <= 0.0) {
+    f[IDN] = fr.d; f[IVX] = fr.mx; f[IVY] = fr.my; f[IVZ] = fr.mz; f[IBY] = fr.by; f[IBZ] = fr.bz;
+  } else if (spd[1] >= 0.0) {
+    f[IDN] = fl.d + spd[0] * (ulst.d - ul.d);
+    f[IVX] = fl.mx + spd[0] * (ulst.mx - ul.mx);
+    f[IVY] = fl.my + spd[0] * (ulst.my - ul.my);
+    f[IVZ] = fl.mz + spd[0] * (ulst.mz - ul.mz);
+    f[IBY] = fl.by + spd[0] * (ulst.by - ul.by);
+    f[IBZ] = fl.bz + spd[0] * (ulst.bz - ul.bz);
+  } else if (spd[3] <= 0.0) {
+    f[IDN] = fr.d + spd[4] * (urst.d - ur.d);
+    f[IVX] = fr.mx + spd[4] * (urst.mx - ur.mx);
+    f[IVY] = fr.my + spd[4] * (urst.my - ur.my);
+    f[IVZ] = fr.mz + spd[4] * (urst.mz - ur.mz);
+    f[IBY] = fr.by + spd[4] * (urst.by - ur.by);
+    f[IBZ] = fr.bz + spd[4] * (urst.bz - ur.bz);
+  } else {
+    f[IDN] = dhll * ustar;
+    f[IVX] = fmxhll;
+    f[IVY] = ucst.my * ustar - bxi * ucst.by;
+    f[IVZ] = ucst.mz * ustar - bxi * ucst.bz;
+    f[IBY] = ucst.by * ustar - bxi * ucst.my / ucst.d;
+    f[IBZ] = ucst.bz * ustar - bxi * ucst.mz / ucst.d;
+  }
+  f[IEN] = 0.0;
+}
+
+//----------------------------------------------------------------------------------------
 // compile-time selection: every solver is its own kernel instantiation, so the registers of the
 // default HLLC / HLLD kernels do not pay for the Roe eigen-decomposition.
 constexpr int default_rsolver(bool mhd) { return mhd ? RS_HLLD : RS_HLLC; }
@@ -565,6 +701,7 @@ constexpr int default_rsolver(bool mhd) { return mhd ? RS_HLLD : RS_HLLC; }
 template <int RS>
 ATHK_HD void hydro_riemann(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
   if (RS == RS_HLLE) hlle_hydro_flux(eos, wl, wr, f);
+  else if (RS == RS_HLLE_ISO) hlle_iso_hydro_flux(eos, wl, wr, f);
   else if (RS == RS_ROE) roe_hydro_flux(eos, wl, wr, f);
   else if (RS == RS_LLF) llf_hydro_flux(eos, wl, wr, f);
   else hllc_flux(eos, wl, wr, f);
@@ -574,6 +711,7 @@ template <int RS>
 ATHK_HD void mhd_riemann(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
                          Real f[7]) {
   if (RS == RS_HLLE) hlle_mhd_flux(eos, wl, wr, bxi, f);
+  else if (RS == RS_HLLD_ISO) hlld_iso_flux(eos, wl, wr, bxi, f);
   else if (RS == RS_ROE) roe_mhd_flux(eos, wl, wr, bxi, f);
   else if (RS == RS_LLF) llf_mhd_flux(eos, wl, wr, bxi, f);
   else hlld_flux(eos, wl, wr, bxi, f);

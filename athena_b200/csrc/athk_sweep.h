@@ -72,7 +72,8 @@ ATHK_HD void solve_face_dx(M &m, const SweepArgs &a, int blk, idx_t c, Real dxw,
                            const Real wr[7], const Real bxi, Real f[7], bool store) {
   const Grid &g = a.g;
   if (MHD) {
-    mhd_riemann_m<RS>(m, a.eos, wl, wr, bxi, f);
+    if (RS == RS_HLLD_ISO) mhd_riemann_m<RS>(m, eos_of_block(a.eos, blk), wl, wr, bxi, f);   // (uses the block's density floor)
+    else mhd_riemann_m<RS>(m, a.eos, wl, wr, bxi, f);
     if (store) {
       Real *eb = a.ef + ((idx_t)blk * 6 + 2 * DIR) * g.sn + c;
       eb[0] = -f[IBY];

@@ -92,9 +92,16 @@ struct RingStencil {
 #ifndef ATHK_MARCH_MINB_DONOR
 #define ATHK_MARCH_MINB_DONOR ATHK_MARCH_MINB
 #endif
-template <int DIR, int ORDER, bool MHD, int RS, int AR>
+// (nseg, seglen: on small meshes a column is cut into nseg segments of seglen cells, each marched by
+//  its own thread, so that one 64^3 block still fills the machine; a segment solves seglen + 1
+//  faces -- the face it shares with the next segment is solved by both, same bits -- and finishes
+//  its own seglen cells)
+// (SEG = false is the whole-column kernel of the large meshes, compiled without the segment's limits:
+//  they cost the x3 PLM instantiation 24 bytes of spills and 13 % of its time)
+template <int DIR, int ORDER, bool MHD, int RS, int AR, bool SEG>
 __global__ void __launch_bounds__(ATHK_MARCH_THREADS, (ORDER == 1) ? ATHK_MARCH_MINB_DONOR : ATHK_MARCH_MINB)
-k_sweep_march(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il, const int ni) {
+k_sweep_march(const SweepArgs a, const int nb, const int o_lo, const int n_o, const int il, const int ni,
+              const int nseg, const int seglen) {
   constexpr int NT = ATHK_MARCH_THREADS, PD = ATHK_MARCH_PD;
   constexpr int LO = ORDER, HI = ORDER - 1;   // cells n-LO .. n+HI around face n
   constexpr int NR = LO + HI + 1 + PD;        // rows in use by a step + rows in flight
@@ -106,13 +113,18 @@ k_sweep_march(const SweepArgs a, const int nb, const int o_lo, const int n_o, co
   const Grid &g = a.g;
   const long long col = (long long)blockIdx.x * NT + threadIdx.x;
   if (col >= (long long)nb * n_o * ni) return;
+  const int seg = SEG ? blockIdx.y : 0;
   const int rowid = (int)(col / ni);
   const int i = il + (int)(col - (long long)rowid * ni);
   const int blk = rowid / n_o;
   const int o = o_lo + (rowid - blk * n_o);
   const idx_t s = (DIR == 1) ? g.sj : g.sk;
-  const int n_s = (DIR == 1) ? g.js : g.ks;
-  const int n_e = (DIR == 1) ? g.je : g.ke;
+  const int n_s0 = (DIR == 1) ? g.js : g.ks;
+  const int n_e0 = (DIR == 1) ? g.je : g.ke;
+  // this thread's cells n_s .. n_e (faces n_s .. n_e + 1)
+  const int n_s = SEG ? n_s0 + seg * seglen : n_s0;
+  const int n_e = SEG ? ((n_s + seglen - 1 < n_e0) ? n_s + seglen - 1 : n_e0) : n_e0;
+  if (SEG && n_s > n_e0) return;
   const bool interior = (i >= g.is && i <= g.ie) && ((DIR == 1) ? (o >= g.ks && o <= g.ke) : (o >= g.js && o <= g.je));
   Real area = 0.0;
   if (interior) area = a.geo.dxf[0][blk * a.geo.PG + i] * a.geo.dxf[(DIR == 1) ? 2 : 1][blk * a.geo.PG + o];   // Face2Area / Face3Area
@@ -236,12 +248,30 @@ static inline cudaError_t launch_sweep_march(cudaStream_t st, const SweepArgs &a
   const int n_o = o_hi - o_lo + 1, ni = iu - il + 1;
   const long long ncol = (long long)nb * n_o * ni;
   if (ncol <= 0) return cudaSuccess;
+  // segments per column: enough threads for ~2 waves of a B200 (148 SMs x 3 CTAs x 128 threads),
+  // segments no shorter than 8 cells
+  const int nx = (DIR == 1) ? a.g.nx2 : a.g.nx3;
+  int nseg = 1;
+  {
+    const long long want = 2LL * 148 * 3 * ATHK_MARCH_THREADS;
+    static const int forced = getenv("ATHK_MARCH_NSEG") ? atoi(getenv("ATHK_MARCH_NSEG")) : 0;
+    if (forced > 0) nseg = forced;
+    else while (ncol * nseg < want && nx / (2 * nseg) >= 8) nseg *= 2;
+    if (nseg > nx) nseg = nx;
+  }
+  const int seglen = (nx + nseg - 1) / nseg;
   constexpr int NT = ATHK_MARCH_THREADS, NR = 2 * ORDER + ATHK_MARCH_PD, NQ = MHD ? 8 : 5, NW = MHD ? 7 : 5;
   constexpr size_t smem = sizeof(Real) * NT * (NR * NQ + 5 + 2 * NW);
-  static size_t granted[64];
-  cudaError_t e = ensure_dynamic_smem(k_sweep_march<DIR, ORDER, MHD, RS, AR>, smem, granted);
-  if (e != cudaSuccess) return e;
-  k_sweep_march<DIR, ORDER, MHD, RS, AR><<<(unsigned)((ncol + NT - 1) / NT), NT, smem, st>>>(a, nb, o_lo, n_o, il, ni);
+  static size_t granted[2][64];
+  if (nseg == 1) {
+    cudaError_t e = ensure_dynamic_smem(k_sweep_march<DIR, ORDER, MHD, RS, AR, false>, smem, granted[0]);
+    if (e != cudaSuccess) return e;
+    k_sweep_march<DIR, ORDER, MHD, RS, AR, false><<<(unsigned)((ncol + NT - 1) / NT), NT, smem, st>>>(a, nb, o_lo, n_o, il, ni, 1, nx);
+  } else {
+    cudaError_t e = ensure_dynamic_smem(k_sweep_march<DIR, ORDER, MHD, RS, AR, true>, smem, granted[1]);
+    if (e != cudaSuccess) return e;
+    k_sweep_march<DIR, ORDER, MHD, RS, AR, true><<<dim3((unsigned)((ncol + NT - 1) / NT), (unsigned)nseg), NT, smem, st>>>(a, nb, o_lo, n_o, il, ni, nseg, seglen);
+  }
   return cudaGetLastError();
 }
 
@@ -530,6 +560,8 @@ static inline cudaError_t launch_sweep_x1(cudaStream_t st, int nb, const Range3 
   q.kl = r.kl; q.nk = nk; q.jl = r.jl; q.nj = nj; q.icl = r.il - 1; q.ncr = nif + 1;
   q.ncr_magic = magic_u32(q.ncr);
   q.njw = ATHK_X1R_NJW < nj ? ATHK_X1R_NJW : nj;
+  // small meshes: fewer rows per warp, so that there are ~2 waves of warps (148 SMs x 12)
+  while (q.njw > 1 && (long long)nb * nk * ((nj + q.njw - 1) / q.njw) < 2LL * 148 * 12) q.njw = (q.njw + 1) / 2;
   q.ngroups = (nj + q.njw - 1) / q.njw;
   int nrs = 63 / q.ncr + 2, p2 = 2, sh = 1;   // rows two consecutive passes can span
   while (p2 < nrs) { p2 *= 2; ++sh; }

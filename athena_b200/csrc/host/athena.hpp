@@ -33,7 +33,7 @@ enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4 };
 enum { IVX = 1, IVY = 2, IVZ = 3, IPR = 4, IBY = 5, IBZ = 6 };
 enum { IB1 = 0, IB2 = 1, IB3 = 2 };
 enum { X1DIR = 0, X2DIR = 1, X3DIR = 2 };
-constexpr int NHYDRO = 5;
+// NHYDRO: 5, or 4 with the isothermal equation of state (run-time here, see Config)
 
 // defs.hpp.in:137-159
 #define PI 3.1415926535897932
@@ -52,14 +52,17 @@ struct Config {
   std::string flux = "";      // RIEMANN_SOLVER (default hllc / hlld)
   int nghost = 2;             // NGHOST
   int nscalars = 0;           // NSCALARS
-  int nwave() const { return mhd ? 7 : 5; }
+  bool isothermal = false;    // --eos=isothermal: NON_BAROTROPIC_EOS == 0, NHYDRO == 4
+  int nhydro() const { return isothermal ? 4 : 5; }
+  int nwave() const { return nhydro() + (mhd ? 2 : 0); }
 };
 extern Config g_config;
 #define MAGNETIC_FIELDS_ENABLED (g_config.mhd)
 #define NGHOST (g_config.nghost)
 #define NSCALARS (g_config.nscalars)
 #define NWAVE (g_config.nwave())
-#define NON_BAROTROPIC_EOS 1
+#define NON_BAROTROPIC_EOS (!g_config.isothermal)
+#define NHYDRO (g_config.nhydro())
 
 //----------------------------------------------------------------------------------------
 // AthenaArray (athena_arrays.hpp:25-171): dense, last index fastest
@@ -186,11 +189,12 @@ class EquationOfState {   // eos/eos.hpp:32-181
  public:
   explicit EquationOfState(ParameterInput *pin);
   Real GetGamma() const { return gamma_; }
+  Real GetIsoSoundSpeed() const { return iso_sound_speed_; }
   Real GetDensityFloor() const { return dfloor_; }
   Real GetPressureFloor() const { return pfloor_; }
   Real GetScalarFloor() const { return sfloor_; }
  private:
-  Real gamma_, dfloor_, pfloor_, sfloor_;
+  Real gamma_, dfloor_, pfloor_, sfloor_, iso_sound_speed_ = 0.0;
 };
 
 // bvals/bvals_interfaces.hpp:120-190 (NeighborBlock) -- what the refinement code needs of it

@@ -103,6 +103,14 @@ PassiveScalars::PassiveScalars(MeshBlock *pmb) {
 }
 EquationOfState::EquationOfState(ParameterInput *pin) {   // eos/adiabatic_*.cpp:26-31
   const Real float_min = std::numeric_limits<float>::min();
+  if (g_config.isothermal) {   // eos/isothermal_hydro.cpp:25-30, isothermal_mhd.cpp:26-31
+    iso_sound_speed_ = pin->GetReal("hydro", "iso_sound_speed");   // error if missing!
+    gamma_ = 1.0;   // (never used)
+    dfloor_ = pin->GetOrAddReal("hydro", "dfloor", std::sqrt(1024 * float_min));
+    pfloor_ = std::sqrt(1024 * float_min);
+    sfloor_ = pin->GetOrAddReal("hydro", "sfloor", std::sqrt(1024 * float_min));
+    return;
+  }
   gamma_ = pin->GetReal("hydro", "gamma");
   dfloor_ = pin->GetOrAddReal("hydro", "dfloor", std::sqrt(1024 * float_min));
   pfloor_ = pin->GetOrAddReal("hydro", "pfloor", std::sqrt(1024 * float_min));
@@ -302,7 +310,17 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   cfg.nghost = NGHOST;
   cfg.mhd = MAGNETIC_FIELDS_ENABLED ? 1 : 0;
   cfg.nscalars = NSCALARS;
-  const std::string flux = g_config.flux.empty() ? (MAGNETIC_FIELDS_ENABLED ? "hlld" : "hllc") : g_config.flux;
+  // configure.py's defaults: hlld with -b, else hllc, or hlle for the isothermal EOS
+  const std::string flux = g_config.flux.empty()
+                               ? (MAGNETIC_FIELDS_ENABLED ? "hlld" : (g_config.isothermal ? "hlle" : "hllc"))
+                               : g_config.flux;
+  cfg.eos = g_config.isothermal ? ATHK_EOS_ISOTHERMAL : ATHK_EOS_ADIABATIC;
+  cfg.iso_sound_speed = g_config.isothermal ? blocks_[0]->peos->GetIsoSoundSpeed() : 0.0;
+  if (g_config.isothermal && multilevel) {
+    msg << "### FATAL ERROR in Mesh constructor" << std::endl
+        << "Static mesh refinement on the B200 path is implemented for the adiabatic EOS";
+    ATHENA_ERROR(msg);
+  }
   if (flux == "hllc") cfg.rsolver = ATHK_RS_HLLC;
   else if (flux == "hlld") cfg.rsolver = ATHK_RS_HLLD;
   else if (flux == "roe") cfg.rsolver = ATHK_RS_ROE;

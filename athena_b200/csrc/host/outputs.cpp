@@ -125,7 +125,7 @@ void Outputs::WriteHistory(OutputParameters &op, Mesh *pm, ParameterInput *pin) 
           h[4] += vol * 0.5 * SQR(u_mx) / u_d;
           h[5] += vol * 0.5 * SQR(u_my) / u_d;
           h[6] += vol * 0.5 * SQR(u_mz) / u_d;
-          h[7] += vol * u(IEN, k, j, i);
+          if (NON_BAROTROPIC_EOS) h[7] += vol * u(IEN, k, j, i);
           if (mhd) {
             const AthenaArray<Real> &bcc = pmb->pfield->bcc;
             const Real &b1 = bcc(IB1, k, j, i), &b2 = bcc(IB2, k, j, i), &b3 = bcc(IB3, k, j, i);
@@ -164,7 +164,7 @@ void Outputs::WriteHistory(OutputParameters &op, Mesh *pm, ParameterInput *pin) 
     std::fprintf(pfile, "[%d]=1-KE     ", iout++);
     std::fprintf(pfile, "[%d]=2-KE     ", iout++);
     std::fprintf(pfile, "[%d]=3-KE     ", iout++);
-    std::fprintf(pfile, "[%d]=tot-E   ", iout++);
+    if (NON_BAROTROPIC_EOS) std::fprintf(pfile, "[%d]=tot-E   ", iout++);
     if (mhd) {
       std::fprintf(pfile, "[%d]=1-ME    ", iout++);
       std::fprintf(pfile, "[%d]=2-ME    ", iout++);
@@ -266,8 +266,10 @@ std::vector<Outputs::OutputField> Outputs::SelectFields(MeshBlock *pmb, const st
   // the order below is the order of the columns / datasets in the reference's files
   scalar(ListHas(var, "D") || cons, "dens", u, IDN);
   scalar(ListHas(var, "d") || prim, "rho", w, IDN);
-  scalar(ListHas(var, "E") || cons, "Etot", u, IEN);
-  scalar(ListHas(var, "p") || prim, "press", w, IPR);
+  if (NON_BAROTROPIC_EOS) {   // outputs.cpp:521-548
+    scalar(ListHas(var, "E") || cons, "Etot", u, IEN);
+    scalar(ListHas(var, "p") || prim, "press", w, IPR);
+  }
   vector(ListHas(var, "m") || cons, "mom", u, IM1);
   scalar(ListHas(var, "m1"), "mom1", u, IM1);
   scalar(ListHas(var, "m2"), "mom2", u, IM2);

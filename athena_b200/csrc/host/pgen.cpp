@@ -61,7 +61,7 @@ static void BlastGenerator(MeshBlock *pmb, ParameterInput *pin) {
         u(IM1, k, j, i) = 0.0;
         u(IM2, k, j, i) = 0.0;
         u(IM3, k, j, i) = 0.0;
-        u(IEN, k, j, i) = pres / gm1;
+        if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) = pres / gm1;
       }
   if (MAGNETIC_FIELDS_ENABLED) {
     FaceField &b = pmb->pfield->b;
@@ -76,7 +76,7 @@ static void BlastGenerator(MeshBlock *pmb, ParameterInput *pin) {
         for (int i = pmb->is; i <= pmb->ie; ++i) b.x3f(k, j, i) = 0.0;
     for (int k = pmb->ks; k <= pmb->ke; ++k)
       for (int j = pmb->js; j <= pmb->je; ++j)
-        for (int i = pmb->is; i <= pmb->ie; ++i) u(IEN, k, j, i) += 0.5 * b0 * b0;
+        for (int i = pmb->is; i <= pmb->ie; ++i) if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) += 0.5 * b0 * b0;
   }
 }
 
@@ -116,6 +116,7 @@ static void OrszagTangGenerator(MeshBlock *pmb, ParameterInput *) {
   for (int k = pmb->ks; k <= pmb->ke; k++)
     for (int j = pmb->js; j <= pmb->je; j++)
       for (int i = pmb->is; i <= pmb->ie; i++)
+        if (NON_BAROTROPIC_EOS)
         u(IEN, k, j, i) = p0 / gm1 +
                           0.5 * (SQR(0.5 * (b.x1f(k, j, i) + b.x1f(k, j, i + 1))) +
                                  SQR(0.5 * (b.x2f(k, j, i) + b.x2f(k, j + 1, i))) +
@@ -220,7 +221,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
           u(IM1, k, j, i) = m1;
           u(IM2, k, j, i) = m2;
           u(IM3, k, j, i) = 0.0;
-          u(IEN, k, j, i) = 2.5 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
+          if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) = 2.5 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
           for (int n = 0; n < NSCALARS; ++n)   // odd scalars mark the ambient medium, even ones the stream
             pmb->pscalars->s(n, k, j, i) = stream ? std::abs(n % 2 - 1) * drat : n % 2;
         }
@@ -230,7 +231,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
       for (int k = pmb->ks; k <= pmb->ke; k++)
         for (int j = pmb->js; j <= pmb->je; j++) {
           for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0;
-          for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * b0 * b0;
+          for (int i = pmb->is; i <= pmb->ie; i++) if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) += 0.5 * b0 * b0;
         }
     }
     return;
@@ -256,7 +257,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
                      std::exp(-(SQR(pc->x2v(j) - z2)) / (sigma * sigma)));
           u(IM2, k, j, i) = v2 * dens;
           u(IM3, k, j, i) = 0.0;
-          u(IEN, k, j, i) = P0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i))) /
+          if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) = P0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i)) + SQR(u(IM3, k, j, i))) /
                                            u(IDN, k, j, i);
           if (NSCALARS > 0) {
             Real concentration = 0.5 * (std::tanh((pc->x2v(j) - z2) / a) - std::tanh((pc->x2v(j) - z1) / a) + 2.0);
@@ -274,7 +275,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
           for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0 * std::tanh((std::abs(pc->x2v(j)) - 0.5) / a);
       for (int k = pmb->ks; k <= pmb->ke; k++)
         for (int j = pmb->js; j <= pmb->je; j++)
-          for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * SQR(b.x1f(k, j, i));
+          for (int i = pmb->is; i <= pmb->ie; i++) if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) += 0.5 * SQR(b.x1f(k, j, i));
     }
     return;
   }
@@ -286,7 +287,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
         u(IM1, k, j, i) = vflow * std::tanh((pc->x2v(j)) / a);
         u(IM2, k, j, i) = amp * std::cos(TWO_PI * pc->x1v(i)) * std::exp(-(SQR(pc->x2v(j))) / SQR(sigma));
         u(IM3, k, j, i) = 0.0;
-        u(IEN, k, j, i) = 1.0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
+        if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) = 1.0 / gm1 + 0.5 * (SQR(u(IM1, k, j, i)) + SQR(u(IM2, k, j, i))) / u(IDN, k, j, i);
       }
   if (MAGNETIC_FIELDS_ENABLED) {
     const Real b0 = pin->GetReal("problem", "b0");
@@ -296,7 +297,7 @@ static void KHGenerator(MeshBlock *pmb, ParameterInput *pin) {
         for (int i = pmb->is; i <= pmb->ie + 1; i++) b.x1f(k, j, i) = b0;
     for (int k = pmb->ks; k <= pmb->ke; k++)
       for (int j = pmb->js; j <= pmb->je; j++)
-        for (int i = pmb->is; i <= pmb->ie; i++) u(IEN, k, j, i) += 0.5 * b0 * b0;
+        for (int i = pmb->is; i <= pmb->ie; i++) if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) += 0.5 * b0 * b0;
   }
 }
 

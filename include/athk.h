@@ -39,6 +39,12 @@ enum athk_status {
 /* Riemann solvers: one is linked per build in the reference (Makefile.in:73) */
 enum athk_rsolver { ATHK_RS_HLLC = 0, ATHK_RS_HLLD = 1, ATHK_RS_ROE = 2, ATHK_RS_HLLE = 3, ATHK_RS_LLF = 4 };
 
+/* Equation of state.  ATHK_EOS_ISOTHERMAL (eos/isothermal_hydro.cpp, isothermal_mhd.cpp): p = cs^2 rho,
+ * no energy equation; Riemann solvers HLLE for hydro (hlle.cpp, the reference's default) and HLLD
+ * for MHD (hlld_iso.cpp).  Registers keep the adiabatic layout; the energy component stays zero and
+ * upload / download of U, U1, U2, W move the NHYDRO = 4 components the reference has. */
+enum athk_eos { ATHK_EOS_ADIABATIC = 0, ATHK_EOS_ISOTHERMAL = 1 };
+
 /* ATHK_ARITH_STRICT: the reference's double-precision arithmetic operation by operation (no FMA
  * contraction, correctly rounded divisions and square roots): results identical to the CPU build.
  * ATHK_ARITH_FAST (HLLC / HLLD): contraction on, divisions and square roots refined to ~1 ulp;
@@ -57,6 +63,8 @@ typedef struct athk_config {
   int arith;           /* enum athk_arith: which kernel set the fused sweeps run             */
   double gamma;        /* <hydro> gamma                                           */
   double dfloor, pfloor, sfloor; /* floors; <=0 selects sqrt(1024*FLT_MIN) (eos.hpp:161) */
+  int eos;             /* enum athk_eos: configure.py --eos                        */
+  double iso_sound_speed; /* <hydro> iso_sound_speed (isothermal EOS)              */
 } athk_config;
 
 /* device-resident arrays addressable through upload/download */

@@ -49,6 +49,10 @@ CONFIGS = {
     "linwave_hydro_hllc_g4": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=4),   # PPM on a refined mesh
     "usrsrc_hydro_hllc": dict(PROB="usrsrc", MHD=0, FLUX="hllc", PGEN="oracle"),   # oracle/pgen/usrsrc.cpp
     "usrsrc_mhd_hlld": dict(PROB="usrsrc", MHD=1, FLUX="hlld", PGEN="oracle"),
+    "blast_iso_hydro_hlle": dict(PROB="blast", MHD=0, FLUX="hlle", EOS="isothermal"),
+    "ot_iso_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld", EOS="isothermal"),   # (blast.cpp:208 writes
+    # u(IEN) unguarded with -b: the reference's own blast problem cannot run isothermal MHD)
+    "kh_iso_mhd_hlld_s1": dict(PROB="kh", MHD=1, FLUX="hlld", EOS="isothermal", NSCALARS=1),
     "jet_hydro_hllc": dict(PROB="jet", MHD=0, FLUX="hllc"),       # user-enrolled inner-x1 boundary
     "jet_mhd_hlld": dict(PROB="jet", MHD=1, FLUX="hlld"),
 }
@@ -165,21 +169,26 @@ def read_rst(path):
     # infer NGHOST, MHD and NSCALARS from datasize
     nd = datasize // 8
     found = None
-    for ng in (2, 3, 4):
-        nc = [n + 2 * ng if n > 1 else 1 for n in bnx]
-        cells = nc[0] * nc[1] * nc[2]
-        faces = ((nc[0] + 1) * nc[1] * nc[2] + nc[0] * (nc[1] + (1 if bnx[1] > 1 else 0)) * nc[2]
-                 + nc[0] * nc[1] * (nc[2] + (1 if bnx[2] > 1 else 0)))
-        for mhd in (0, 1):
-            rest = nd - 5 * cells - mhd * faces
-            if rest >= 0 and rest % cells == 0 and rest // cells <= 8:
-                found = (ng, mhd, rest // cells, nc)
+    # (NHYDRO = 5, or 4 for the isothermal EOS: tried second, so an isothermal file with scalars reads
+    #  as 5 + (nscalars - 1) components -- the same bytes in the same order)
+    for nh in (5, 4):
+        for ng in (2, 3, 4):
+            nc = [n + 2 * ng if n > 1 else 1 for n in bnx]
+            cells = nc[0] * nc[1] * nc[2]
+            faces = ((nc[0] + 1) * nc[1] * nc[2] + nc[0] * (nc[1] + (1 if bnx[1] > 1 else 0)) * nc[2]
+                     + nc[0] * nc[1] * (nc[2] + (1 if bnx[2] > 1 else 0)))
+            for mhd in (0, 1):
+                rest = nd - nh * cells - mhd * faces
+                if rest >= 0 and rest % cells == 0 and rest // cells <= 8:
+                    found = (ng, mhd, rest // cells, nc, nh)
+                    break
+            if found:
                 break
         if found:
             break
     if not found:
         raise ValueError("cannot infer restart layout (datasize=%d)" % datasize)
-    ng, mhd, nscal, nc = found
+    ng, mhd, nscal, nc, nh = found
     out = dict(params=params, nb=nbtotal, root_level=root_level, mesh_size=rs, time=time, dt=dt,
                ncycle=ncycle, nx=tuple(bnx), mesh_nx=tuple(mnx), ng=ng, mhd=bool(mhd),
                nscalars=nscal, loc=locs, u=[], b1=[], b2=[], b3=[], s=[])
@@ -189,8 +198,8 @@ def read_rst(path):
         a = np.frombuffer(raw, dtype=np.float64, count=nd, offset=off)
         off += datasize
         p = 0
-        n = 5 * nc[2] * nc[1] * nc[0]
-        out["u"].append(a[p:p + n].reshape(5, nc[2], nc[1], nc[0]).copy())
+        n = nh * nc[2] * nc[1] * nc[0]
+        out["u"].append(a[p:p + n].reshape(nh, nc[2], nc[1], nc[0]).copy())
         p += n
         if mhd:
             n = nc[2] * nc[1] * (nc[0] + 1)

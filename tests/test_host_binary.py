@@ -138,7 +138,26 @@ def usrsrc_blocks(mhd, integrator):
     return b
 
 
+def iso(blocks, cs, **problem):
+    blocks["hydro"]["iso_sound_speed"] = cs
+    blocks["problem"].update(problem)
+    return blocks
+
+
 CASES = {
+    # isothermal equation of state (--eos=isothermal: NHYDRO = 4; HLLE for hydro, hlld_iso for MHD)
+    "iso_blast_hydro_hlle": ("blast_iso_hydro_hlle", "blast", False, lambda: iso(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.1, rst_dt=0.05, b0=None, radius=0.3),
+        0.7, drat=8.0), ["--eos=isothermal"]),
+    "iso_blast_hydro_reflecting_rk3": ("blast_iso_hydro_hlle", "blast", False, lambda: iso(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.1, rst_dt=0.05, b0=None, radius=0.3,
+                            integrator="rk3", bcs=["reflecting"] * 4 + ["outflow"] * 2, center=(0.5, 0.4, 0.3)),
+        0.7, drat=8.0), ["--eos=isothermal"]),
+    "iso_kh_mhd_hlld_scalar": ("kh_iso_mhd_hlld_s1", "kh", True, lambda: iso(
+        refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.1, rst_dt=0.05, integrator="vl2", xorder=2,
+                         b0=0.5), 1.1), ["--eos=isothermal", "--nscalars=1"]),
+    "iso_orszag_tang_rk3": ("ot_iso_mhd_hlld", "orszag_tang", True, lambda: iso(
+        refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk3"), 0.9), ["--eos=isothermal"]),
     # user-enrolled explicit source terms (SrcTermFunc, time-dependent) -- the reference
     # side is the unmodified reference linked with the user problem file oracle/pgen/usrsrc.cpp
     "user_source_hydro_rk3": ("usrsrc_hydro_hllc", "usrsrc", False, lambda: usrsrc_blocks(False, "rk3")),
@@ -304,7 +323,7 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
 
 @pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe",
                                   "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes", "jet_user_bc_mhd_rk3",
-                                  "user_source_mhd_vl2"])
+                                  "user_source_mhd_vl2", "iso_kh_mhd_hlld_scalar", "iso_blast_hydro_reflecting_rk3"])
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
@@ -770,9 +789,13 @@ def test_parameter_input_error_behaviour(emul_binary):
     wd, r = run_host(emul_binary, bad, "blast", True)
     assert r.returncode != 0 and "both sides must be periodic" in r.stdout   # (ox1_bc is still periodic)
     shutil.rmtree(wd, ignore_errors=True)
-    bad["mesh"]["ix1_bc"] = bad["mesh"]["ox1_bc"] = "user"
+    bad["mesh"]["ix1_bc"] = bad["mesh"]["ox1_bc"] = "user"   # ... and the blast problem enrolls no function
     wd, r = run_host(emul_binary, bad, "blast", True)
-    assert r.returncode != 0 and "periodic, reflecting and outflow mesh boundaries" in r.stdout
+    assert r.returncode != 0 and "A user-defined boundary is specified but the actual boundary function" in r.stdout
+    shutil.rmtree(wd, ignore_errors=True)
+    bad["mesh"]["ix1_bc"] = bad["mesh"]["ox1_bc"] = "polar"
+    wd, r = run_host(emul_binary, bad, "blast", True)
+    assert r.returncode != 0 and "GetBoundaryFlag" in r.stdout
     shutil.rmtree(wd, ignore_errors=True)
     wd, r = run_host(emul_binary, blocks, "blast", True, extra=["time/tlim=0.004"])
     assert r.returncode == 0 and "Terminating on time limit" in r.stdout
