@@ -1756,7 +1756,11 @@ extern "C" int athk_remote_set_p2p(athk_ctx *c, int npeers, double *const *ghost
   p.gseq = p.eseq = 0;
   p.on = true;
 #ifndef ATHK_EMULATE
-  if (!p.side && !getenv("ATHK_NO_EARLY_PACK")) {   // side stream of the early ghost pack (ghost_pack_early)
+  // side stream of the early ghost pack (ghost_pack_early).  Opt-in (ATHK_EARLY_PACK=1): measured at 8
+  // GPUs it LOSES 0.2 ms per cycle (9.97 vs 9.76 ms) -- the NVLink-bound pack kernel holds SM slots
+  // while corner E / the EMF kernels run, and they slow down by more than the pack hides
+  // (profiles/r2_bench_n8_early_pack_variant.json)
+  if (!p.side && getenv("ATHK_EARLY_PACK")) {
     CU(cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&p.ev_ready, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&p.ev_packed, cudaEventDisableTiming));

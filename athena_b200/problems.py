@@ -49,3 +49,35 @@ def blast_block(mesh, loc, mhd, gamma, pamb=0.1, prat=100.0, radius=0.1, damb=1.
         u[4][sl] += 0.5 * b0 * b0
         out.update(b1=b1, b2=b2, b3=b3)
     return out
+
+
+def sound_wave_block(mesh, loc, mhd, gamma, amp=1.0e-6, b=(1.0, 1.4142135623730951, 0.5)):
+    """A small-amplitude plane wave along x1 on a uniform background (the shape of pgen/linear_wave.cpp's
+    wave_flag=0 set-up: rho0 = 1, p0 = 1/gamma, |delta| ~ amp; with MHD a uniform field b): throughput
+    workload for the BASELINE configs[0] / configs[1] shapes, not the eigenvector of the parity tests
+    (those run through the C++ host's linear_wave problem generator)."""
+    ng = mesh.ng
+    nx1, nx2, nx3 = mesh.block_nx
+    x1v = mesh.coords(loc, 0)[1]
+    nc1, nc2, nc3 = nx1 + 2 * ng, nx2 + 2 * ng, nx3 + 2 * ng
+    lx = mesh.xmax[0] - mesh.xmin[0]
+    sn = np.sin(2.0 * PI * (x1v - mesh.xmin[0]) / lx)[None, None, :] * np.ones((nc3, nc2, 1))
+    d = 1.0 + amp * sn
+    p = 1.0 / gamma + amp * sn
+    vx = amp * sn
+    u = np.zeros((5, nc3, nc2, nc1))
+    sl = (slice(ng, ng + nx3), slice(ng, ng + nx2), slice(ng, ng + nx1))
+    u[0][sl] = d[sl]
+    u[1][sl] = (d * vx)[sl]
+    u[4][sl] = (p / (gamma - 1.0) + 0.5 * d * vx * vx)[sl]
+    out = dict(u=u)
+    if mhd:
+        b1 = np.zeros((nc3, nc2, nc1 + 1))
+        b2 = np.zeros((nc3, nc2 + 1, nc1))
+        b3 = np.zeros((nc3 + 1, nc2, nc1))
+        b1[ng:ng + nx3, ng:ng + nx2, ng:ng + nx1 + 1] = b[0]
+        b2[ng:ng + nx3, ng:ng + nx2 + 1, ng:ng + nx1] = b[1]
+        b3[ng:ng + nx3 + 1, ng:ng + nx2, ng:ng + nx1] = b[2]
+        u[4][sl] += 0.5 * (b[0] ** 2 + b[1] ** 2 + b[2] ** 2)
+        out.update(b1=b1, b2=b2, b3=b3)
+    return out

@@ -412,6 +412,36 @@ def run_ours(args):
                         "the reference to rounding (tests/test_fast_arith.py), not bit for bit; `value` is the "
                         "strict set"}
 
+    # ---- the other single-GPU BASELINE shapes through the same code path (device-timed, a few
+    # cycles each): configs[0] hydro 64^3 in ONE MeshBlock (VL2+PLM+HLLC), configs[1] MHD 128^3 in 32^3
+    # MeshBlocks (VL2+PLM+HLLD+CT).  Parity of both at full size is in tests/ (C++ host vs reference).
+    other = None
+    if world == 1 and not args.no_other_workloads:
+        other = {}
+        ctx.close()
+        for key, n, blk, mhd_o in (("configs[0]: hydro wave 64^3, one 64^3 MeshBlock, VL2+PLM+HLLC", 64, 64, False),
+                                   ("configs[1]: MHD wave 128^3, 32^3 MeshBlocks, VL2+PLM+HLLD+CT", 128, 32, True)):
+            m_o = pyhost.UniformMesh((n,) * 3, (blk,) * 3, (0.0, 0.0, 0.0), (3.0, 1.5, 1.5), ng=2)
+            c_o = pyhost.Context(m_o, mhd_o, gamma, device=local_rank, lib=lib)
+            for lb, g_ in enumerate(c_o.gids):
+                ic = problems.sound_wave_block(m_o, m_o.loc[g_], mhd_o, gamma)
+                c_o.upload("U", lb, ic["u"])
+                if mhd_o:
+                    c_o.upload("B_X1F", lb, ic["b1"])
+                    c_o.upload("B_X2F", lb, ic["b2"])
+                    c_o.upload("B_X3F", lb, ic["b3"])
+            stream = torch.cuda.ExternalStream(lib.athk_stream(c_o.h))
+            t_o = pyhost.TimeIntegrator(c_o, "vl2", 2, 0.3, fused=True)
+            t_o.initialize()
+            for _ in range(5):
+                t_o.step()
+            n_o = 40
+            ctx = c_o   # (timed() synchronises through ctx)
+            ms_o = timed(lambda: t_o.step(), n_o)
+            other[key] = {"value": n ** 3 * n_o / (ms_o * 1e-3), "unit": "zone-cycles/s", "ms_per_cycle": ms_o / n_o,
+                          "cycles": n_o, "data": "synthetic plane wave (athena_b200/problems.py)"}
+            c_o.close()
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         per_gpu_value = value / world
@@ -455,6 +485,8 @@ def run_ours(args):
                         "unit": "TFLOP/s", "frac": tflops / fpeak, "peak_source": fpeak_src}
         if fast is not None:
             roof["fast_arith"] = fast
+        if other is not None:
+            roof["other_workloads"] = other
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -520,6 +552,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-fast-arith", action="store_true", help="skip the extra fast-arithmetic measurement (N=1)")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the BASELINE configs[0] / configs[1] shape measurements (N=1)")
     ap.add_argument("--parity-case", default="mhd_linwave_vl2_plm_hlld",
                     help="golden fixture run split over the ranks before the timed region (N > 1)")
     ap.add_argument("--ref-mesh", type=int, default=128)
