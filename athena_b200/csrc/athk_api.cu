@@ -1132,10 +1132,14 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
   long long maxvol = 0;
   for (int n = 0; n < nops; ++n) {   // every box must lie inside the array it addresses
     const athk_box_op &o = ops[n];
-    if (o.kind < BOX_RESTRICT || o.kind > BOX_FLUX_FROM_FINER || o.dst < 0 || o.dst >= g.nb || o.src < 0 || o.src >= g.nb)
+    if (o.kind < BOX_RESTRICT || o.kind > BOX_COARSE_BC || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
+        (o.kind != BOX_COARSE_BC && o.src >= g.nb))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
     const bool coarse_dst = (o.kind == BOX_RESTRICT || o.kind == BOX_FROM_COARSER || o.kind == BOX_C2P_COARSE ||
-                             o.kind == BOX_PROLONG);
+                             o.kind == BOX_PROLONG || o.kind == BOX_COARSE_BC);
+    if (o.kind == BOX_COARSE_BC && (o.dir < 0 || o.dir > 2 || o.lo[o.dir] != o.hi[o.dir] || (o.src != 1 && o.src != 2) ||
+                                    o.so[o.dir] < 0 || o.so[o.dir] >= (o.dir == 0 ? cg.cn1 : (o.dir == 1 ? cg.cn2 : cg.cn3))))
+      return fail(ATHK_ERR_ARG, "refine_set_ops: box %d is not a one-layer boundary box", n);
     const int lim[3] = {coarse_dst ? cg.cn1 : g.nc1 + 1, coarse_dst ? cg.cn2 : g.nc2 + 1, coarse_dst ? cg.cn3 : g.nc3 + 1};
     long long vol = 1;
     for (int d = 0; d < 3; ++d) {

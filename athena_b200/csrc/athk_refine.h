@@ -28,7 +28,10 @@ enum {
   BOX_C2P_COARSE = 4,     // coarse_cons -> coarse_prim over the coarse box (floors written back)
   BOX_PROLONG = 5,        // coarse_prim box [lo,hi] -> w, eight fine cells per coarse cell
   BOX_P2C_FINE = 6,       // w -> u over the fine box [lo,hi]
-  BOX_FLUX_FROM_FINER = 7 // flux[dir][dst] face box [lo,hi] <- area-weighted flux[dir][src], fine origin so
+  BOX_FLUX_FROM_FINER = 7, // flux[dir][dst] face box [lo,hi] <- area-weighted flux[dir][src], fine origin so
+  BOX_COARSE_BC = 8       // reflecting / outflow function on coarse_prim, one ghost layer (bvals_refine.cpp:445-530):
+                          // box [lo,hi] = the ghost layer, dir = its direction, src = 1 reflect / 2 outflow,
+                          // so[dir] = the active coarse cell it is copied from
 };
 
 struct BoxOp {   // == athk_box_op (include/athk.h)
@@ -117,6 +120,18 @@ struct BoxOpPoint {
         break;
       }
       case BOX_FLUX_FROM_FINER: flux_cell(op, k, j, i, dk, dj, di); break;
+      case BOX_COARSE_BC: {   // bvals/cc/outflow_cc.cpp, bvals/cc/hydro/reflect_hydro.cpp with ngh = 1
+        const int si = (op.dir == 0) ? op.so[0] : i, sj = (op.dir == 1) ? op.so[1] : j, sk = (op.dir == 2) ? op.so[2] : k;
+        const idx_t s = cidx(cg, sk, sj, si), d = cidx(cg, k, j, i);
+        Real *wb = cw + (idx_t)op.dst * 5 * cg.csn;
+        Real v[5];
+#pragma unroll
+        for (int n = 0; n < 5; ++n) v[n] = wb[n * cg.csn + s];
+        if (op.src == 1) v[IVX + op.dir] = -v[IVX + op.dir];   // reflect the normal velocity
+#pragma unroll
+        for (int n = 0; n < 5; ++n) wb[n * cg.csn + d] = v[n];
+        break;
+      }
       default: break;
     }
   }

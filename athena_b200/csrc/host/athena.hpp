@@ -247,6 +247,8 @@ class MeshBlock {   // mesh/mesh.hpp:75-200
   // static mesh refinement (bvals_base.hpp): neighbours in SearchAndSetNeighbors' order, their levels
   std::vector<NeighborBlock> neighbor;
   int nblevel[3][3][3];
+  BoundaryFlag block_bcs[6] = {BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block,
+                               BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block};
 };
 
 // athena.hpp:98-100, 214-217: user-enrolled boundary functions act on the HOST mirrors of the

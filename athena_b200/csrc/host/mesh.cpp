@@ -195,10 +195,10 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
       ATHENA_ERROR(msg);
     }
     for (int n = 0; n < 6; ++n)
-      if (mesh_bcs[n] != BoundaryFlag::periodic) {
+      if (mesh_bcs[n] == BoundaryFlag::user) {
         msg << "### FATAL ERROR in Mesh constructor" << std::endl
-            << "Static mesh refinement on the B200 path needs periodic mesh boundaries (physical boundaries "
-            << "on the coarse buffer are not implemented)";
+            << "Static mesh refinement on the B200 path takes periodic, reflecting and outflow mesh boundaries "
+            << "(user-enrolled functions are not applied to the coarse buffer)";
         ATHENA_ERROR(msg);
       }
   }
@@ -301,6 +301,10 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     }
     blocks_.push_back(new MeshBlock(n, n - nslist[ranklist[n]], l, b, this, pin));
     blocks_.back()->rank = ranklist[n];
+    for (int q = 0; q < 3; ++q) {   // SetBlockSizeAndBoundaries: the mesh's flag on the mesh edge, else "block"
+      blocks_.back()->block_bcs[2 * q] = (d[q].lx == 0) ? mesh_bcs[2 * q] : BoundaryFlag::block;
+      blocks_.back()->block_bcs[2 * q + 1] = (d[q].lx == d[q].nrb - 1) ? mesh_bcs[2 * q + 1] : BoundaryFlag::block;
+    }
   }
 
   // ---- device contexts: one per GPU, each for the MeshBlocks of its range ------------------
@@ -520,7 +524,8 @@ void Mesh::ExchangeGhosts() {
     const char *who = "Mesh::ExchangeGhosts";
     AthkCheck(athk_refine_run(athk, 1, 0), who);
     AthkCheck(athk_exchange_ghosts(athk, what, 0), who);
-    for (int phase = 2; phase <= 6; ++phase) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    // (phase 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation)
+    for (int phase : {2, 3, 4, 7, 5, 6}) AthkCheck(athk_refine_run(athk, phase, 0), who);
     return;
   }
   if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), "Mesh::ExchangeGhosts");

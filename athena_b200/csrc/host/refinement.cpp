@@ -448,6 +448,28 @@ void Mesh::SetupRefinement() {
         if (o3 == 0) { f3m = pmb->nblevel[0][1][1] != -1; f3p = pmb->nblevel[2][1][1] != -1; }
         Box c2p = {p.si - f1m, p.ei + f1p, p.sj - f2m, p.ej + f2p, p.sk - f3m, p.ek + f3p};
         ph[4].push_back(MakeOp(4, t, t, 0, c2p, 0, 0, 0));
+        // ... then the physical boundary functions on the coarse primitives, one ghost layer, on the
+        // faces this neighbour's box touches (:445-530); reflecting / outflow here (phase 7, run
+        // between phases 4 and 5)
+        {
+          const int off[3] = {o1, o2, o3};
+          const int clo[3] = {cis, cjs, cks}, chi[3] = {cie, cje, cke};
+          for (int d = 0; d < 3; ++d) {
+            if (off[d] != 0) continue;
+            for (int side = 0; side < 2; ++side) {
+              const BoundaryFlag bf = pmb->block_bcs[2 * d + side];
+              if (bf != BoundaryFlag::reflect && bf != BoundaryFlag::outflow) continue;
+              Box bb = p;
+              int so[3] = {0, 0, 0};
+              const int ghost = side ? chi[d] + 1 : clo[d] - 1;
+              so[d] = side ? chi[d] : clo[d];   // (ngh = 1: mirror image and outflow source coincide)
+              if (d == 0) bb.si = bb.ei = ghost;
+              if (d == 1) bb.sj = bb.ej = ghost;
+              if (d == 2) bb.sk = bb.ek = ghost;
+              ph[7].push_back(MakeOp(8, t, bf == BoundaryFlag::reflect ? 1 : 2, d, bb, so[0], so[1], so[2]));
+            }
+          }
+        }
         ph[5].push_back(MakeOp(5, t, t, 0, p, 0, 0, 0));
         Box f = {(p.si - cis) * 2 + is, (p.ei - cis) * 2 + is + 1, (p.sj - cjs) * 2 + js, (p.ej - cjs) * 2 + js + 1,
                  (p.sk - cks) * 2 + ks, (p.ek - cks) * 2 + ks + 1};

@@ -244,6 +244,9 @@ int athk_set_source_time(athk_ctx *ctx, double time);
  *         6 PrimitiveToConserved on the prolongated ghost zones            (bvals_refine.cpp:655)
  *         7 flux correction: flux[dir] of dst on a face box <- area-weighted flux of the finer src
  *           (flux_correction_cc.cpp:77-160, 222-275)
+ *         8 ApplyPhysicalBoundariesOnCoarseLevel (bvals_refine.cpp:445-530): the reflecting (src = 1) or
+ *           outflow (src = 2) function on the coarse primitives, one ghost layer of direction dir copied
+ *           from the active coarse cell so[dir]
  * Boxes are inclusive (i, j, k) ranges of the destination; so = source origin matching lo. */
 #define ATHK_NBR_REFINED (-1000000)
 typedef struct athk_box_op {

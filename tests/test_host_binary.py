@@ -173,6 +173,13 @@ CASES = {
     "smr_blast_hydro": ("blast_hydro_hllc", "blast", False, lambda: refined(
         refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.06, rst_dt=0.03, b0=None, radius=0.25),
         (-0.3, 0.3, -0.3, 0.3, -0.3, 0.3, 1))),
+    # ... with walls: the boundary functions also act on the coarse buffer (bvals_refine.cpp:445-530);
+    # one region in a reflecting corner, a two-level one in an outflow corner
+    "smr_blast_hydro_walls": ("blast_hydro_hllc", "blast", False, lambda: refined(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.08, rst_dt=0.04, b0=None, radius=0.25,
+                            bcs=["reflecting", "outflow", "outflow", "reflecting", "reflecting", "outflow"],
+                            center=(-0.6, 0.5, -0.55)),
+        (-1.0, -0.4, 0.3, 1.0, -1.0, -0.3, 1), (0.5, 1.0, -1.0, -0.6, 0.4, 1.0, 2))),
     "smr_linwave_hydro_ppm_two_regions": ("linwave_hydro_hllc_g4", "linear_wave", False, lambda: refined(
         refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3",
                               xorder=3),
