@@ -198,7 +198,8 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->stage);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->rf.cu); cudaFree(c->rf.cw); cudaFree(c->rf.xv); cudaFree(c->rf.cxv);
-  for (int p = 0; p < 8; ++p) cudaFree(c->rf.ops[p]);
+  cudaFree(c->rf.cb); cudaFree(c->rf.cbcc);
+  for (int p = 0; p < ATHK_REFINE_NPHASES; ++p) cudaFree(c->rf.ops[p]);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
   cudaFree(c->p2p.gdst); cudaFree(c->p2p.edst); cudaFree(c->p2p.peer_flags); cudaFree(c->p2p.timeouts);
@@ -1079,8 +1080,6 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   if (!c) return fail(ATHK_ERR_ARG, "refine_enable: null context");
   cudaSetDevice(c->cfg.device);
   if (c->rf.on) return ATHK_OK;
-  if (c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for hydro (face-centred "
-                                            "restriction / prolongation and the EMF correction are not)");
   if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "refine_enable: passive scalars are not refined");
   if (c->eos.iso) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for the adiabatic EOS");
   const Grid &g = c->g;
@@ -1092,11 +1091,14 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   cg.cis = cg.cjs = cg.cks = g.ng;
   cg.csj = cg.cn1; cg.csk = (idx_t)cg.cn1 * cg.cn2; cg.csn = cg.csk * cg.cn3;
   cg.CPG = std::max(cg.cn1, std::max(cg.cn2, cg.cn3));
+  cg.cfj = cg.cn1 + 1; cg.cfk = (idx_t)(cg.cn1 + 1) * (cg.cn2 + 1); cg.cfn = cg.cfk * (cg.cn3 + 1);
   const size_t nc = (size_t)g.nb * 5 * cg.csn;
   int rc = dev_alloc(&c->rf.cu, nc, c->stream);
   if (!rc) rc = dev_alloc(&c->rf.cw, nc, c->stream);
   if (!rc) rc = dev_alloc(&c->rf.xv, (size_t)g.nb * 3 * c->geo.PG, c->stream);
   if (!rc) rc = dev_alloc(&c->rf.cxv, (size_t)g.nb * 3 * cg.CPG, c->stream);
+  if (!rc && c->cfg.mhd) rc = dev_alloc(&c->rf.cb, (size_t)g.nb * 3 * cg.cfn, c->stream);     // coarse_b_ (field/field.cpp:60-70)
+  if (!rc && c->cfg.mhd) rc = dev_alloc(&c->rf.cbcc, (size_t)g.nb * 3 * cg.csn, c->stream);   // coarse_bcc_
   if (rc) return rc;
   c->rf.on = true;
   return ATHK_OK;
@@ -1132,18 +1134,30 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
   long long maxvol = 0;
   for (int n = 0; n < nops; ++n) {   // every box must lie inside the array it addresses
     const athk_box_op &o = ops[n];
-    if (o.kind < BOX_RESTRICT || o.kind > BOX_COARSE_BC || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
-        (o.kind != BOX_COARSE_BC && o.src >= g.nb))
+    if (o.kind < BOX_RESTRICT || o.kind > BOX_EMF_SCALE || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
+        (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.src >= g.nb))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
+    if (o.kind >= BOX_FC_COPY) {
+      if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d) needs an MHD context", n, o.kind);
+      if (o.kind != BOX_FC_PROLONG_INTERNAL && (o.dir < 0 || o.dir > 2))
+        return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d): component %d", n, o.kind, o.dir);
+      if (o.kind == BOX_EMF_SCALE && o.src < 1) return fail(ATHK_ERR_ARG, "refine_set_ops: box %d: divisor %d", n, o.src);
+    }
     const bool coarse_dst = (o.kind == BOX_RESTRICT || o.kind == BOX_FROM_COARSER || o.kind == BOX_C2P_COARSE ||
-                             o.kind == BOX_PROLONG || o.kind == BOX_COARSE_BC);
+                             o.kind == BOX_PROLONG || o.kind == BOX_COARSE_BC || o.kind == BOX_FC_RESTRICT ||
+                             o.kind == BOX_FC_FROM_COARSER || o.kind == BOX_FC_PROLONG_SHARED ||
+                             o.kind == BOX_FC_PROLONG_INTERNAL);
+    const bool coarse_face = (o.kind == BOX_FC_RESTRICT || o.kind == BOX_FC_FROM_COARSER || o.kind == BOX_FC_PROLONG_SHARED);
     if (o.kind == BOX_COARSE_BC && (o.dir < 0 || o.dir > 2 || o.lo[o.dir] != o.hi[o.dir] || (o.src != 1 && o.src != 2) ||
                                     o.so[o.dir] < 0 || o.so[o.dir] >= (o.dir == 0 ? cg.cn1 : (o.dir == 1 ? cg.cn2 : cg.cn3))))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d is not a one-layer boundary box", n);
-    const int lim[3] = {coarse_dst ? cg.cn1 : g.nc1 + 1, coarse_dst ? cg.cn2 : g.nc2 + 1, coarse_dst ? cg.cn3 : g.nc3 + 1};
+    const int lim[3] = {coarse_dst ? cg.cn1 + (coarse_face && o.dir == 0) : g.nc1 + 1,
+                        coarse_dst ? cg.cn2 + (coarse_face && o.dir == 1) : g.nc2 + 1,
+                        coarse_dst ? cg.cn3 + (coarse_face && o.dir == 2) : g.nc3 + 1};
     long long vol = 1;
     for (int d = 0; d < 3; ++d) {
-      const int inset = (o.kind == BOX_PROLONG) ? 1 : 0;   // the gradients read one coarse cell around
+      // the gradients read one coarse cell around (shared faces: in the two transverse directions)
+      const int inset = (o.kind == BOX_PROLONG || (o.kind == BOX_FC_PROLONG_SHARED && d != o.dir)) ? 1 : 0;
       if (o.lo[d] < inset || o.hi[d] >= lim[d] - inset || o.hi[d] < o.lo[d])
         return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d) leaves its array in direction %d: %d..%d", n,
                     o.kind, d, o.lo[d], o.hi[d]);
@@ -1170,9 +1184,16 @@ extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
   if (phase < 0 || phase >= ATHK_REFINE_NPHASES) return fail(ATHK_ERR_ARG, "refine_run: phase %d", phase);
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "refine_run: register %d not allocated", reg);
   if (c->rf.nops[phase] == 0) return ATHK_OK;
+  const bool mhd = c->cfg.mhd != 0;
   BoxOpPoint f = {c->g, c->rf.cg, c->geo, c->eos, c->rf.ops[phase], c->u[reg], c->w, c->rf.cu, c->rf.cw,
-                  {c->flux[0], c->flux[1], c->flux[2]}, c->rf.xv, c->rf.cxv};
-  LAUNCH_NAMED(c, "athk_refine_run", launch_links(c->stream, c->rf.nops[phase], c->rf.maxvol[phase], f));
+                  {c->flux[0], c->flux[1], c->flux[2]}, c->rf.xv, c->rf.cxv,
+                  mhd ? 1 : 0, mhd ? c->b[reg] : nullptr, c->bcc, c->rf.cb, c->rf.cbcc, c->e, c->emfbuf, c->sf};
+  if (mhd && !c->b[reg]) return fail(ATHK_ERR_ARG, "refine_run: field register %d not allocated", reg);
+  for (int first = 0; first < c->rf.nops[phase]; first += 32768) {   // (grid.y limit)
+    f.ops = c->rf.ops[phase] + first;
+    const int n = std::min(32768, c->rf.nops[phase] - first);
+    LAUNCH_NAMED(c, "athk_refine_run", launch_links(c->stream, n, c->rf.maxvol[phase], f));
+  }
   return ATHK_OK;
 }
 

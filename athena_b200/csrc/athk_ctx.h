@@ -89,9 +89,10 @@ struct athk_ctx {
     bool on = false;
     CoarseGrid cg;
     Real *cu = nullptr, *cw = nullptr, *xv = nullptr, *cxv = nullptr;
-    BoxOp *ops[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int nops[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long maxvol[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    Real *cb = nullptr, *cbcc = nullptr;   // MHD: coarse_b_, coarse_bcc_
+    BoxOp *ops[ATHK_REFINE_NPHASES] = {};
+    int nops[ATHK_REFINE_NPHASES] = {};
+    long long maxvol[ATHK_REFINE_NPHASES] = {};
   } rf;
   athk_bval_fn user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // enrolled BValFuncs
   void *user_bc_data[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -431,15 +431,15 @@ struct EmfApplyPoint {
       int cnt = 1;
       if (bq != 0) {
         const int id = nb[nbr_slot(0, bq, 0)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e1(kk, ii)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e1(kk, ii)]; ++cnt; }
       }
       if (cq != 0) {
         const int id = nb[nbr_slot(0, 0, cq)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e1(jj, ii)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e1(jj, ii)]; ++cnt; }
       }
       if (bq != 0 && cq != 0) {
         const int id = nb[nbr_slot(0, bq, cq)];
-        if (id != -1) {
+        if (id != -1 && id != NBR_REFINED) {
           v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e1(kk - cq * g.nx3, ii)];
           ++cnt;
         }
@@ -455,15 +455,15 @@ struct EmfApplyPoint {
       int cnt = 1;
       if (a != 0) {
         const int id = nb[nbr_slot(a, 0, 0)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e2(kk, jj)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e2(kk, jj)]; ++cnt; }
       }
       if (cq != 0) {
         const int id = nb[nbr_slot(0, 0, cq)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e2(jj, ii)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(2, cq < 0 ? 1 : 0) + sf.x3_e2(jj, ii)]; ++cnt; }
       }
       if (a != 0 && cq != 0) {
         const int id = nb[nbr_slot(a, 0, cq)];
-        if (id != -1) {
+        if (id != -1 && id != NBR_REFINED) {
           v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e2(kk - cq * g.nx3, jj)];
           ++cnt;
         }
@@ -479,15 +479,15 @@ struct EmfApplyPoint {
       int cnt = 1;
       if (a != 0) {
         const int id = nb[nbr_slot(a, 0, 0)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e3(kk, jj)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e3(kk, jj)]; ++cnt; }
       }
       if (bq != 0) {
         const int id = nb[nbr_slot(0, bq, 0)];
-        if (id != -1) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e3(kk, ii)]; ++cnt; }
+        if (id != -1 && id != NBR_REFINED) { v += surf_of(id)[sf.face_off(1, bq < 0 ? 1 : 0) + sf.x2_e3(kk, ii)]; ++cnt; }
       }
       if (a != 0 && bq != 0) {
         const int id = nb[nbr_slot(a, bq, 0)];
-        if (id != -1) {
+        if (id != -1 && id != NBR_REFINED) {
           v += surf_of(id)[sf.face_off(0, a < 0 ? 1 : 0) + sf.x1_e3(kk, jj - bq * g.nx2)];
           ++cnt;
         }

@@ -1,6 +1,11 @@
-// athk_refine.h -- static mesh refinement, cell-centred (hydro) variables: the arithmetic of
+// athk_refine.h -- static mesh refinement: the arithmetic of
 //   MeshRefinement::RestrictCellCenteredValues      mesh/mesh_refinement.cpp:116-186
 //   MeshRefinement::ProlongateCellCenteredValues    mesh/mesh_refinement.cpp:464-545
+//   MeshRefinement::RestrictFieldX1/X2/X3           mesh/mesh_refinement.cpp:272-460
+//   MeshRefinement::ProlongateSharedFieldX1/X2/X3   mesh/mesh_refinement.cpp:776-1220 (Cartesian branch)
+//   MeshRefinement::ProlongateInternalField         mesh/mesh_refinement.cpp:1223-1340 (Toth & Roe)
+//   FaceCenteredBoundaryVariable::LoadFluxBoundaryBufferToCoarser / SetFluxBoundaryFromFiner /
+//   ClearCoarseFluxBoundary / AverageFluxBoundary   bvals/fc/flux_correction_fc.cpp:315-570,944-1190,1214-1541
 //   CellCenteredBoundaryVariable::LoadFluxBoundaryBufferToCoarser / SetFluxBoundaryFromFiner
 //                                                   bvals/cc/flux_correction_cc.cpp:77-160,222-275
 //   ConservedToPrimitive / PrimitiveToConserved on the coarse buffer and on the prolongated ghost
@@ -29,9 +34,21 @@ enum {
   BOX_PROLONG = 5,        // coarse_prim box [lo,hi] -> w, eight fine cells per coarse cell
   BOX_P2C_FINE = 6,       // w -> u over the fine box [lo,hi]
   BOX_FLUX_FROM_FINER = 7, // flux[dir][dst] face box [lo,hi] <- area-weighted flux[dir][src], fine origin so
-  BOX_COARSE_BC = 8       // reflecting / outflow function on coarse_prim, one ghost layer (bvals_refine.cpp:445-530):
+  BOX_COARSE_BC = 8,      // reflecting / outflow function on coarse_prim, one ghost layer (bvals_refine.cpp:445-530):
                           // box [lo,hi] = the ghost layer, dir = its direction, src = 1 reflect / 2 outflow,
                           // so[dir] = the active coarse cell it is copied from
+  // ---- face-centred field (dir = component: 0 x1f, 1 x2f, 2 x3f)
+  BOX_FC_COPY = 9,          // b[dst].dir box [lo,hi] <- b[src].dir from origin so (SetBoundarySameLevel on a refined mesh)
+  BOX_FC_RESTRICT = 10,     // own b.dir -> own coarse_b.dir over the coarse face box [lo,hi]
+  BOX_FC_FROM_FINER = 11,   // b[dst].dir box <- coarse_b[src].dir from coarse origin so
+  BOX_FC_FROM_COARSER = 12, // coarse_b[dst].dir box <- b[src].dir from fine origin so
+  BOX_FC_PROLONG_SHARED = 13,   // coarse_b.dir coarse face box -> the four fine faces on each coarse face
+  BOX_FC_PROLONG_INTERNAL = 14, // coarse cell box: the twelve internal fine faces of each coarse cell
+  // ---- EMF correction across levels (dir = component: 0 e1, 1 e2, 2 e3)
+  BOX_EMF_CLEAR = 15,       // e[dst].dir box = 0
+  BOX_EMF_FROM_FINER = 16,  // e[dst].dir box += length-weighted pair of the finer src's packed surface EMFs,
+                            // fine origin so (in the pair's direction and in the others: stride 2)
+  BOX_EMF_SCALE = 17        // e[dst].dir box *= 1/src
 };
 
 struct BoxOp {   // == athk_box_op (include/athk.h)
@@ -47,9 +64,11 @@ struct CoarseGrid {
   int cis, cjs, cks;             // first active coarse index (= NGHOST)
   idx_t csj, csk, csn;
   int CPG;                       // stride of the per-block coarse coordinate arrays
+  idx_t cfj, cfk, cfn;           // coarse face arrays (coarse_b_): one box of (cn1+1, cn2+1, cn3+1) per component
 };
 
 ATHK_HD idx_t cidx(const CoarseGrid &cg, int k, int j, int i) { return (idx_t)k * cg.csk + (idx_t)j * cg.csj + i; }
+ATHK_HD idx_t cfidx(const CoarseGrid &cg, int k, int j, int i) { return (idx_t)k * cg.cfk + (idx_t)j * cg.cfj + i; }
 
 struct BoxOpPoint {
   Grid g;
@@ -63,6 +82,15 @@ struct BoxOpPoint {
   Real *flx[3];            // [nb][5][sn]
   const Real *xv;          // [nb][3][PG]   fine x1v, x2v, x3v
   const Real *cxv;         // [nb][3][CPG]  coarse (pcoarsec) x1v, x2v, x3v
+  // MHD (null / 0 for hydro)
+  int mhd;
+  Real *b;                 // [nb][3][sn]   the field register the exchange acts on
+  Real *bcc;               // [nb][3][sn]
+  Real *cb;                // [nb][3][cfn]  coarse_b_
+  Real *cbcc;              // [nb][3][csn]  coarse_bcc_
+  Real *emf;               // [nb][3][sn]   edge EMFs
+  const Real *emfbuf;      // [nb][per_block] packed raw surface EMFs (EmfPackPoint)
+  EmfSurf sf;
   ATHK_HD void operator()(int opi, idx_t e) const {
     const BoxOp op = ops[opi];
     const int n1 = op.hi[0] - op.lo[0] + 1, n2 = op.hi[1] - op.lo[1] + 1, n3 = op.hi[2] - op.lo[2] + 1;
@@ -98,7 +126,18 @@ struct BoxOpPoint {
 #pragma unroll
         for (int n = 0; n < 5; ++n) uc[n] = ub[n * cg.csn];
         const Real d0 = uc[IDN], e0 = uc[IEN];
-        cons2prim_hydro(eos_of_block(eos, op.dst), uc, wc);
+        if (mhd) {   // CalculateCellCenteredField on coarse_b_ (field.cpp:139-142, uniform average), then W(U)
+          const idx_t fc = cfidx(cg, k, j, i);
+          const Real *bb = cb + (idx_t)op.dst * 3 * cg.cfn + fc;
+          const Real bc1 = 0.5 * bb[0] + 0.5 * bb[1];
+          const Real bc2 = 0.5 * bb[cg.cfn] + 0.5 * bb[cg.cfn + cg.cfj];
+          const Real bc3 = 0.5 * bb[2 * cg.cfn] + 0.5 * bb[2 * cg.cfn + cg.cfk];
+          Real *bc = cbcc + (idx_t)op.dst * 3 * cg.csn + c;
+          bc[0] = bc1; bc[cg.csn] = bc2; bc[2 * cg.csn] = bc3;
+          cons2prim_mhd(eos_of_block(eos, op.dst), uc, bc1, bc2, bc3, wc);
+        } else {
+          cons2prim_hydro(eos_of_block(eos, op.dst), uc, wc);
+        }
         if (uc[IDN] != d0) ub[IDN * cg.csn] = uc[IDN];
         if (uc[IEN] != e0) ub[IEN * cg.csn] = uc[IEN];
 #pragma unroll
@@ -116,7 +155,18 @@ struct BoxOpPoint {
         ub[g.sn] = w_vx * w_d;
         ub[2 * g.sn] = w_vy * w_d;
         ub[3 * g.sn] = w_vz * w_d;
-        ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
+        if (mhd) {   // bvals_refine.cpp:640-657: bcc of the prolongated field, then U(W, bcc) (adiabatic_mhd.cpp:99-135)
+          const Real *bb = b + (idx_t)op.dst * 3 * g.sn + c;
+          Real *bc = bcc + (idx_t)op.dst * 3 * g.sn + c;
+          const Real bcc1 = 0.5 * bb[0] + 0.5 * bb[1];
+          const Real bcc2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj];
+          const Real bcc3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
+          bc[0] = bcc1; bc[g.sn] = bcc2; bc[2 * g.sn] = bcc3;
+          ub[4 * g.sn] = w_p * igm1 + 0.5 * (w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz)) +
+                                             (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
+        } else {
+          ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
+        }
         break;
       }
       case BOX_FLUX_FROM_FINER: flux_cell(op, k, j, i, dk, dj, di); break;
@@ -132,8 +182,192 @@ struct BoxOpPoint {
         for (int n = 0; n < 5; ++n) wb[n * cg.csn + d] = v[n];
         break;
       }
+      case BOX_FC_COPY: {
+        Real *bd = b + ((idx_t)op.dst * 3 + op.dir) * g.sn;
+        const Real *bs = b + ((idx_t)op.src * 3 + op.dir) * g.sn;
+        bd[gidx(g, k, j, i)] = bs[gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
+        break;
+      }
+      case BOX_FC_RESTRICT: restrict_face(op.dst, op.dir, k, j, i); break;
+      case BOX_FC_FROM_FINER:
+        b[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] =
+            cb[((idx_t)op.src * 3 + op.dir) * cg.cfn + cfidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
+        break;
+      case BOX_FC_FROM_COARSER:
+        cb[((idx_t)op.dst * 3 + op.dir) * cg.cfn + cfidx(cg, k, j, i)] =
+            b[((idx_t)op.src * 3 + op.dir) * g.sn + gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
+        break;
+      case BOX_FC_PROLONG_SHARED: prolong_shared_face(op.dst, op.dir, k, j, i); break;
+      case BOX_FC_PROLONG_INTERNAL: prolong_internal(op.dst, k, j, i); break;
+      case BOX_EMF_CLEAR: emf[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] = 0.0; break;
+      case BOX_EMF_FROM_FINER: emf_from_finer(op, k, j, i, dk, dj, di); break;
+      case BOX_EMF_SCALE: emf[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] *= (1.0 / (Real)op.src); break;
       default: break;
     }
+  }
+  // MeshRefinement::RestrictFieldX1/X2/X3, 3-D Cartesian (mesh_refinement.cpp:280-299, 338-362, 411-426):
+  // area-weighted average of the four fine faces on a coarse face, summed in the reference's order
+  ATHK_HD void restrict_face(int blk, int dir, int ck, int cj, int ci) const {
+    const int k = (ck - cg.cks) * 2 + g.ks, j = (cj - cg.cjs) * 2 + g.js, i = (ci - cg.cis) * 2 + g.is;
+    const Real *dx1 = geo.dxf[0] + blk * geo.PG, *dx2 = geo.dxf[1] + blk * geo.PG, *dx3 = geo.dxf[2] + blk * geo.PG;
+    const Real *f = b + ((idx_t)blk * 3 + dir) * g.sn + gidx(g, k, j, i);
+    Real a0, a1, a2, a3;
+    idx_t o1, o2, o3;
+    if (dir == 0) {          // (k,j), (k,j+1), (k+1,j), (k+1,j+1): Face1Area = dx2f(j)*dx3f(k)
+      a0 = dx2[j] * dx3[k]; a1 = dx2[j + 1] * dx3[k]; a2 = dx2[j] * dx3[k + 1]; a3 = dx2[j + 1] * dx3[k + 1];
+      o1 = g.sj; o2 = g.sk; o3 = g.sk + g.sj;
+    } else if (dir == 1) {   // (k,i), (k,i+1), (k+1,i), (k+1,i+1): Face2Area = dx1f(i)*dx3f(k)
+      a0 = dx1[i] * dx3[k]; a1 = dx1[i + 1] * dx3[k]; a2 = dx1[i] * dx3[k + 1]; a3 = dx1[i + 1] * dx3[k + 1];
+      o1 = 1; o2 = g.sk; o3 = g.sk + 1;
+    } else {                 // (j,i), (j,i+1), (j+1,i), (j+1,i+1): Face3Area = dx1f(i)*dx2f(j)
+      a0 = dx1[i] * dx2[j]; a1 = dx1[i + 1] * dx2[j]; a2 = dx1[i] * dx2[j + 1]; a3 = dx1[i + 1] * dx2[j + 1];
+      o1 = 1; o2 = g.sj; o3 = g.sj + 1;
+    }
+    const Real tarea = a0 + a1 + a2 + a3;
+    cb[((idx_t)blk * 3 + dir) * cg.cfn + cfidx(cg, ck, cj, ci)] = (f[0] * a0 + f[o1] * a1 + f[o2] * a2 + f[o3] * a3) / tarea;
+  }
+  ATHK_HD static Real lim_grad(Real gm, Real gp) {   // 0.5*(SIGN(gm)+SIGN(gp))*min(|gm|,|gp|)
+    return 0.5 * (sign_of(gm) + sign_of(gp)) * min_std(fabs(gm), fabs(gp));
+  }
+  // MeshRefinement::ProlongateSharedFieldX1/X2/X3, 3-D Cartesian (fluxinterp_ = false;
+  // mesh_refinement.cpp:838-875, 968-1008, 1112-1153): x?s? = x?v (coordinates/cartesian.cpp)
+  ATHK_HD void prolong_shared_face(int blk, int dir, int k, int j, int i) const {
+    const int fk = (k - cg.cks) * 2 + g.ks, fj = (j - cg.cjs) * 2 + g.js, fi = (i - cg.cis) * 2 + g.is;
+    const Real *cx1 = cxv + ((idx_t)blk * 3 + 0) * cg.CPG, *cx2 = cxv + ((idx_t)blk * 3 + 1) * cg.CPG,
+               *cx3 = cxv + ((idx_t)blk * 3 + 2) * cg.CPG;
+    const Real *fx1 = xv + ((idx_t)blk * 3 + 0) * geo.PG, *fx2 = xv + ((idx_t)blk * 3 + 1) * geo.PG,
+               *fx3 = xv + ((idx_t)blk * 3 + 2) * geo.PG;
+    const Real *c = cb + ((idx_t)blk * 3 + dir) * cg.cfn + cfidx(cg, k, j, i);
+    Real *f = b + ((idx_t)blk * 3 + dir) * g.sn + gidx(g, fk, fj, fi);
+    const Real ccval = c[0];
+    if (dir == 0) {
+      const Real x3c = cx3[k], dx3m = x3c - cx3[k - 1], dx3p = cx3[k + 1] - x3c;
+      const Real fx3m = fx3[fk], fx3p = fx3[fk + 1];
+      const Real x2c = cx2[j], dx2m = x2c - cx2[j - 1], dx2p = cx2[j + 1] - x2c;
+      const Real fx2m = fx2[fj], fx2p = fx2[fj + 1];
+      const Real gx2c = lim_grad((ccval - c[-cg.cfj]) / dx2m, (c[cg.cfj] - ccval) / dx2p);
+      const Real gx3c = lim_grad((ccval - c[-cg.cfk]) / dx3m, (c[cg.cfk] - ccval) / dx3p);
+      f[0] = ccval - gx2c * (x2c - fx2m) - gx3c * (x3c - fx3m);
+      f[g.sj] = ccval + gx2c * (fx2p - x2c) - gx3c * (x3c - fx3m);
+      f[g.sk] = ccval - gx2c * (x2c - fx2m) + gx3c * (fx3p - x3c);
+      f[g.sk + g.sj] = ccval + gx2c * (fx2p - x2c) + gx3c * (fx3p - x3c);
+    } else if (dir == 1) {
+      const Real x3c = cx3[k], dx3m = x3c - cx3[k - 1], dx3p = cx3[k + 1] - x3c;
+      const Real fx3m = fx3[fk], fx3p = fx3[fk + 1];
+      const Real x1c = cx1[i], dx1m = x1c - cx1[i - 1], dx1p = cx1[i + 1] - x1c;
+      const Real fx1m = fx1[fi], fx1p = fx1[fi + 1];
+      const Real gx1c = lim_grad((ccval - c[-1]) / dx1m, (c[1] - ccval) / dx1p);
+      const Real gx3c = lim_grad((ccval - c[-cg.cfk]) / dx3m, (c[cg.cfk] - ccval) / dx3p);
+      f[0] = ccval - gx1c * (x1c - fx1m) - gx3c * (x3c - fx3m);
+      f[1] = ccval + gx1c * (fx1p - x1c) - gx3c * (x3c - fx3m);
+      f[g.sk] = ccval - gx1c * (x1c - fx1m) + gx3c * (fx3p - x3c);
+      f[g.sk + 1] = ccval + gx1c * (fx1p - x1c) + gx3c * (fx3p - x3c);
+    } else {
+      const Real x2c = cx2[j], dx2m = x2c - cx2[j - 1], dx2p = cx2[j + 1] - x2c;
+      const Real fx2m = fx2[fj], fx2p = fx2[fj + 1];
+      const Real x1c = cx1[i], dx1m = x1c - cx1[i - 1], dx1p = cx1[i + 1] - x1c;
+      const Real fx1m = fx1[fi], fx1p = fx1[fi + 1];
+      const Real gx1c = lim_grad((ccval - c[-1]) / dx1m, (c[1] - ccval) / dx1p);
+      const Real gx2c = lim_grad((ccval - c[-cg.cfj]) / dx2m, (c[cg.cfj] - ccval) / dx2p);
+      f[0] = ccval - gx1c * (x1c - fx1m) - gx2c * (x2c - fx2m);
+      f[1] = ccval + gx1c * (fx1p - x1c) - gx2c * (x2c - fx2m);
+      f[g.sj] = ccval - gx1c * (x1c - fx1m) + gx2c * (fx2p - x2c);
+      f[g.sj + 1] = ccval + gx1c * (fx1p - x1c) + gx2c * (fx2p - x2c);
+    }
+  }
+  // MeshRefinement::ProlongateInternalField, 3-D (mesh_refinement.cpp:1228-1338): the divergence-
+  // preserving interpolation of Toth & Roe for the twelve fine faces inside one coarse cell; reads
+  // only the fine faces ON the coarse cell's surface.  Accumulation order as the reference's jj, ii loops.
+  ATHK_HD void prolong_internal(int blk, int k, int j, int i) const {
+    const int fk = (k - cg.cks) * 2 + g.ks, fj = (j - cg.cjs) * 2 + g.js, fi = (i - cg.cis) * 2 + g.is;
+    const Real *dx1 = geo.dxf[0] + blk * geo.PG, *dx2 = geo.dxf[1] + blk * geo.PG, *dx3 = geo.dxf[2] + blk * geo.PG;
+    Real *b1 = b + ((idx_t)blk * 3 + 0) * g.sn, *b2 = b + ((idx_t)blk * 3 + 1) * g.sn, *b3 = b + ((idx_t)blk * 3 + 2) * g.sn;
+    auto X1 = [&](int kk, int jj, int ii) -> Real & { return b1[gidx(g, kk, jj, ii)]; };
+    auto X2 = [&](int kk, int jj, int ii) -> Real & { return b2[gidx(g, kk, jj, ii)]; };
+    auto X3 = [&](int kk, int jj, int ii) -> Real & { return b3[gidx(g, kk, jj, ii)]; };
+    auto A1 = [&](int kk, int jj) { return dx2[jj] * dx3[kk]; };   // Face1Area(k,j,.)
+    auto A2 = [&](int kk, int ii) { return dx1[ii] * dx3[kk]; };   // Face2Area(k,.,i)
+    auto A3 = [&](int jj, int ii) { return dx1[ii] * dx2[jj]; };   // Face3Area(.,j,i)
+    Real Uxx = 0.0, Vyy = 0.0, Wzz = 0.0, Uxyz = 0.0, Vxyz = 0.0, Wxyz = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++) {
+      const int js = 2 * jj - 1, fjj = fj + jj, fjp = fj + 2 * jj;
+#pragma unroll
+      for (int ii = 0; ii < 2; ii++) {
+        const int is = 2 * ii - 1, fii = fi + ii, fip = fi + 2 * ii;
+        const Real sis = (Real)is, sjs = (Real)js, sij = (Real)(is * js);
+        const Real x2lo = X2(fk, fjp, fii) * A2(fk, fii), x2hi = X2(fk + 1, fjp, fii) * A2(fk + 1, fii);
+        const Real x3hi = X3(fk + 2, fjj, fii) * A3(fjj, fii), x3lo = X3(fk, fjj, fii) * A3(fjj, fii);
+        const Real x1lo = X1(fk, fjj, fip) * A1(fk, fjj), x1hi = X1(fk + 1, fjj, fip) * A1(fk + 1, fjj);
+        Uxx += sis * (sjs * (x2lo + x2hi) + (x3hi - x3lo));
+        Vyy += sjs * ((x3hi - x3lo) + sis * (x1lo + x1hi));
+        Wzz += sis * (x1hi - x1lo) + sjs * (x2hi - x2lo);
+        Uxyz += sij * (x1hi - x1lo);
+        Vxyz += sij * (x2hi - x2lo);
+        Wxyz += sij * (x3hi - x3lo);
+      }
+    }
+    const Real Sdx1 = sqr(dx1[fi] + dx1[fi + 1]);
+    const Real Sdx2 = sqr(dx2[fj] + dx2[fj + 1]);     // GetEdge2Length = dx2f(j)
+    const Real Sdx3 = sqr(dx3[fk] + dx3[fk + 1]);     // GetEdge3Length = dx3f(k)
+    Uxx *= 0.125; Vyy *= 0.125; Wzz *= 0.125;
+    Uxyz *= 0.125 / (Sdx2 + Sdx3);
+    Vxyz *= 0.125 / (Sdx1 + Sdx3);
+    Wxyz *= 0.125 / (Sdx1 + Sdx2);
+    // x1 faces at fi+1
+    {
+      const Real a00 = A1(fk, fj), a01 = A1(fk, fj + 1), a10 = A1(fk + 1, fj), a11 = A1(fk + 1, fj + 1);
+      const Real v00 = (0.5 * (X1(fk, fj, fi) * a00 + X1(fk, fj, fi + 2) * a00) + Uxx - Sdx3 * Vxyz - Sdx2 * Wxyz) / a00;
+      const Real v01 = (0.5 * (X1(fk, fj + 1, fi) * a01 + X1(fk, fj + 1, fi + 2) * a01) + Uxx - Sdx3 * Vxyz + Sdx2 * Wxyz) / a01;
+      const Real v10 = (0.5 * (X1(fk + 1, fj, fi) * a10 + X1(fk + 1, fj, fi + 2) * a10) + Uxx + Sdx3 * Vxyz - Sdx2 * Wxyz) / a10;
+      const Real v11 = (0.5 * (X1(fk + 1, fj + 1, fi) * a11 + X1(fk + 1, fj + 1, fi + 2) * a11) + Uxx + Sdx3 * Vxyz + Sdx2 * Wxyz) / a11;
+      X1(fk, fj, fi + 1) = v00; X1(fk, fj + 1, fi + 1) = v01; X1(fk + 1, fj, fi + 1) = v10; X1(fk + 1, fj + 1, fi + 1) = v11;
+    }
+    // x2 faces at fj+1 (sarea_x2_[.][0], [.][2], [.][1] = Face2Area at fj, fj+2, fj+1: dx1f(i)*dx3f(k), no j)
+    {
+      const Real a0i = A2(fk, fi), a0p = A2(fk, fi + 1), a1i = A2(fk + 1, fi), a1p = A2(fk + 1, fi + 1);
+      const Real v00 = (0.5 * (X2(fk, fj, fi) * a0i + X2(fk, fj + 2, fi) * a0i) + Vyy - Sdx3 * Uxyz - Sdx1 * Wxyz) / a0i;
+      const Real v01 = (0.5 * (X2(fk, fj, fi + 1) * a0p + X2(fk, fj + 2, fi + 1) * a0p) + Vyy - Sdx3 * Uxyz + Sdx1 * Wxyz) / a0p;
+      const Real v10 = (0.5 * (X2(fk + 1, fj, fi) * a1i + X2(fk + 1, fj + 2, fi) * a1i) + Vyy + Sdx3 * Uxyz - Sdx1 * Wxyz) / a1i;
+      const Real v11 = (0.5 * (X2(fk + 1, fj, fi + 1) * a1p + X2(fk + 1, fj + 2, fi + 1) * a1p) + Vyy + Sdx3 * Uxyz + Sdx1 * Wxyz) / a1p;
+      X2(fk, fj + 1, fi) = v00; X2(fk, fj + 1, fi + 1) = v01; X2(fk + 1, fj + 1, fi) = v10; X2(fk + 1, fj + 1, fi + 1) = v11;
+    }
+    // x3 faces at fk+1 (note the reference's operand order: fk+2 first)
+    {
+      const Real a0i = A3(fj, fi), a0p = A3(fj, fi + 1), a1i = A3(fj + 1, fi), a1p = A3(fj + 1, fi + 1);
+      const Real v00 = (0.5 * (X3(fk + 2, fj, fi) * a0i + X3(fk, fj, fi) * a0i) + Wzz - Sdx2 * Uxyz - Sdx1 * Vxyz) / a0i;
+      const Real v01 = (0.5 * (X3(fk + 2, fj, fi + 1) * a0p + X3(fk, fj, fi + 1) * a0p) + Wzz - Sdx2 * Uxyz + Sdx1 * Vxyz) / a0p;
+      const Real v10 = (0.5 * (X3(fk + 2, fj + 1, fi) * a1i + X3(fk, fj + 1, fi) * a1i) + Wzz + Sdx2 * Uxyz - Sdx1 * Vxyz) / a1i;
+      const Real v11 = (0.5 * (X3(fk + 2, fj + 1, fi + 1) * a1p + X3(fk, fj + 1, fi + 1) * a1p) + Wzz + Sdx2 * Uxyz + Sdx1 * Vxyz) / a1p;
+      X3(fk + 1, fj, fi) = v00; X3(fk + 1, fj, fi + 1) = v01; X3(fk + 1, fj + 1, fi) = v10; X3(fk + 1, fj + 1, fi + 1) = v11;
+    }
+  }
+  // raw (as computed by ComputeCornerE) surface EMF of a block from its packed surface buffer
+  ATHK_HD Real raw_emf(int blk, int comp, int k, int j, int i) const {
+    const Real *s = emfbuf + (idx_t)blk * sf.per_block();
+    const int kk = k - g.ks, jj = j - g.js, ii = i - g.is;
+    const bool ib = (i == g.is || i == g.ie + 1), jb = (j == g.js || j == g.je + 1);
+    if (comp == 0) {
+      if (jb) return s[sf.face_off(1, j == g.js ? 0 : 1) + sf.x2_e1(kk, ii)];
+      return s[sf.face_off(2, k == g.ks ? 0 : 1) + sf.x3_e1(jj, ii)];
+    } else if (comp == 1) {
+      if (ib) return s[sf.face_off(0, i == g.is ? 0 : 1) + sf.x1_e2(kk, jj)];
+      return s[sf.face_off(2, k == g.ks ? 0 : 1) + sf.x3_e2(jj, ii)];
+    }
+    if (ib) return s[sf.face_off(0, i == g.is ? 0 : 1) + sf.x1_e3(kk, jj)];
+    return s[sf.face_off(1, j == g.js ? 0 : 1) + sf.x2_e3(kk, ii)];
+  }
+  // LoadFluxBoundaryBufferToCoarser (flux_correction_fc.cpp:333-570) + SetFluxBoundaryFromFiner (:944-1165):
+  // the two fine edges under a coarse edge, weighted by their lengths (Cartesian: dx?f of the fine block)
+  ATHK_HD void emf_from_finer(const BoxOp &op, int k, int j, int i, int dk, int dj, int di) const {
+    const int sblk = op.src, c = op.dir;
+    const int fi = op.so[0] + 2 * di, fj = op.so[1] + 2 * dj, fk = op.so[2] + 2 * dk;
+    const Real *dx = geo.dxf[c] + sblk * geo.PG;
+    const int n = (c == 0) ? fi : (c == 1 ? fj : fk);
+    const Real el1 = dx[n], el2 = dx[n + 1];
+    const Real v1 = raw_emf(sblk, c, fk, fj, fi);
+    const Real v2 = raw_emf(sblk, c, fk + (c == 2), fj + (c == 1), fi + (c == 0));
+    emf[((idx_t)op.dst * 3 + c) * g.sn + gidx(g, k, j, i)] += (v1 * el1 + v2 * el2) / (el1 + el2);
   }
   // mesh_refinement.cpp:123-151 (3-D, Cartesian volumes dx1f*dx2f*dx3f, coordinates/cartesian.cpp)
   ATHK_HD void restrict_cell(int blk, int ck, int cj, int ci) const {

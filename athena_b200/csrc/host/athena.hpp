@@ -311,6 +311,7 @@ class Mesh {   // mesh/mesh.hpp:206-447
   void BuildRefinedTree(ParameterInput *pin);
   void SearchAndSetNeighbors(MeshBlock *pmb);
   void SetupRefinement();
+  void SetupFieldRefinement(std::vector<athk_box_op> *lists);   // face-centred field + EMF correction boxes
   const ProblemGeneratorEntry *pgen;
   bool fused_stage;
   // user history output (mesh.hpp: EnrollUserHistoryOutput)

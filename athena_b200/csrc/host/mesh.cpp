@@ -125,6 +125,7 @@ MeshBlock::MeshBlock(int igid, int ilid, LogicalLocation iloc, RegionSize bs, Me
   ncells1 = bs.nx1 + 2 * NGHOST;
   ncells2 = bs.nx2 + 2 * NGHOST;
   ncells3 = bs.nx3 + 2 * NGHOST;
+  for (auto &a : nblevel) for (auto &b : a) for (int &v : b) v = -1;   // (set by SearchAndSetNeighbors on refined meshes)
   pcoord = new Coordinates(this, pm);
   phydro = new Hydro(this);
   pfield = new Field(this);
@@ -183,12 +184,19 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     }
   }
   if (multilevel) {
-    if (MAGNETIC_FIELDS_ENABLED || NSCALARS > 0) {
+    if (NSCALARS > 0) {
       msg << "### FATAL ERROR in Mesh constructor" << std::endl
-          << "Static mesh refinement on the B200 path covers hydrodynamics (cell-centred variables); the "
-          << "face-centred field and passive scalars are not refined";
+          << "Static mesh refinement on the B200 path covers hydrodynamics and MHD; passive scalars are not refined";
       ATHENA_ERROR(msg);
     }
+    if (MAGNETIC_FIELDS_ENABLED)
+      for (int n = 0; n < 6; ++n)
+        if (mesh_bcs[n] != BoundaryFlag::periodic) {
+          msg << "### FATAL ERROR in Mesh constructor" << std::endl
+              << "Static mesh refinement with magnetic fields on the B200 path takes periodic mesh boundaries (the "
+              << "face-centred boundary functions are not applied to the coarse buffer)";
+          ATHENA_ERROR(msg);
+        }
     if (NGHOST % 2 == 1) {   // prolongation fills 2*(cnghost-1) ghost cells: more than an odd NGHOST holds
       msg << "### FATAL ERROR in Mesh constructor" << std::endl
           << "Mesh refinement needs an even number of ghost zones (nghost=" << NGHOST << ")";
@@ -523,9 +531,17 @@ void Mesh::ExchangeGhosts() {
     // prolongate the primitives, U(W) on the new ghost zones (phases 3-6)
     const char *who = "Mesh::ExchangeGhosts";
     AthkCheck(athk_refine_run(athk, 1, 0), who);
-    AthkCheck(athk_exchange_ghosts(athk, what, 0), who);
-    // (phase 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation)
-    for (int phase : {2, 3, 4, 7, 5, 6}) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    AthkCheck(athk_exchange_ghosts(athk, what & ~2, 0), who);
+    // SETB_FLD on a refined mesh (refinement.cpp, SetupFieldRefinement): face, edge, corner neighbours in
+    // turn (same level and from finer), then from coarser into the coarse buffer
+    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {8, 9, 10}) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    AthkCheck(athk_refine_run(athk, 2, 0), who);
+    if (MAGNETIC_FIELDS_ENABLED) AthkCheck(athk_refine_run(athk, 11, 0), who);
+    // (phase 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation;
+    //  12, 13 = shared and internal faces of the prolongated field, before U(W, bcc) of phase 6)
+    for (int phase : {3, 4, 7, 5}) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {12, 13}) AthkCheck(athk_refine_run(athk, phase, 0), who);
+    AthkCheck(athk_refine_run(athk, 6, 0), who);
     return;
   }
   if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), "Mesh::ExchangeGhosts");

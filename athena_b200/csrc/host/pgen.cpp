@@ -694,13 +694,40 @@ static void LinearWaveGenerator(MeshBlock *pmb, ParameterInput *) {
     a3.NewAthenaArray(pmb->ncells3, pmb->ncells2, pmb->ncells1);
     dby = amp * rem[NWAVE - 2][wave_flag];
     dbz = amp * rem[NWAVE - 1][wave_flag];
-    // uniform level: no finer neighbours, the single-point branches of linear_wave.cpp:449-500
+    // linear_wave.cpp:455-505: an edge shared with a finer block takes the mean of the potential at
+    // the centres of the two fine edges, so that both levels start from the same face fluxes
+    const int level = pmb->loc.level;
+    auto &nl = pmb->nblevel;   // (-1 everywhere off a refined mesh: single-point branches)
     for (int k = ks; k <= ke + 1; k++)
       for (int j = js; j <= je + 1; j++)
         for (int i = is; i <= ie + 1; i++) {
-          a1(k, j, i) = A1(pc->x1v(i), pc->x2f(j), pc->x3f(k));
-          a2(k, j, i) = A2(pc->x1f(i), pc->x2v(j), pc->x3f(k));
-          a3(k, j, i) = A3(pc->x1f(i), pc->x2f(j), pc->x3v(k));
+          if ((nl[1][0][1] > level && j == js) || (nl[1][2][1] > level && j == je + 1) ||
+              (nl[0][1][1] > level && k == ks) || (nl[2][1][1] > level && k == ke + 1) ||
+              (nl[0][0][1] > level && j == js && k == ks) || (nl[0][2][1] > level && j == je + 1 && k == ks) ||
+              (nl[2][0][1] > level && j == js && k == ke + 1) || (nl[2][2][1] > level && j == je + 1 && k == ke + 1)) {
+            const Real x1l = pc->x1f(i) + 0.25 * pc->dx1f(i), x1r = pc->x1f(i) + 0.75 * pc->dx1f(i);
+            a1(k, j, i) = 0.5 * (A1(x1l, pc->x2f(j), pc->x3f(k)) + A1(x1r, pc->x2f(j), pc->x3f(k)));
+          } else {
+            a1(k, j, i) = A1(pc->x1v(i), pc->x2f(j), pc->x3f(k));
+          }
+          if ((nl[1][1][0] > level && i == is) || (nl[1][1][2] > level && i == ie + 1) ||
+              (nl[0][1][1] > level && k == ks) || (nl[2][1][1] > level && k == ke + 1) ||
+              (nl[0][1][0] > level && i == is && k == ks) || (nl[0][1][2] > level && i == ie + 1 && k == ks) ||
+              (nl[2][1][0] > level && i == is && k == ke + 1) || (nl[2][1][2] > level && i == ie + 1 && k == ke + 1)) {
+            const Real x2l = pc->x2f(j) + 0.25 * pc->dx2f(j), x2r = pc->x2f(j) + 0.75 * pc->dx2f(j);
+            a2(k, j, i) = 0.5 * (A2(pc->x1f(i), x2l, pc->x3f(k)) + A2(pc->x1f(i), x2r, pc->x3f(k)));
+          } else {
+            a2(k, j, i) = A2(pc->x1f(i), pc->x2v(j), pc->x3f(k));
+          }
+          if ((nl[1][1][0] > level && i == is) || (nl[1][1][2] > level && i == ie + 1) ||
+              (nl[1][0][1] > level && j == js) || (nl[1][2][1] > level && j == je + 1) ||
+              (nl[1][0][0] > level && i == is && j == js) || (nl[1][0][2] > level && i == ie + 1 && j == js) ||
+              (nl[1][2][0] > level && i == is && j == je + 1) || (nl[1][2][2] > level && i == ie + 1 && j == je + 1)) {
+            const Real x3l = pc->x3f(k) + 0.25 * pc->dx3f(k), x3r = pc->x3f(k) + 0.75 * pc->dx3f(k);
+            a3(k, j, i) = 0.5 * (A3(pc->x1f(i), pc->x2f(j), x3l) + A3(pc->x1f(i), pc->x2f(j), x3r));
+          } else {
+            a3(k, j, i) = A3(pc->x1f(i), pc->x2f(j), pc->x3v(k));
+          }
         }
     FaceFieldFromPotential(pmb, a1, a2, a3);
   }

@@ -10,6 +10,11 @@
 //   Load / Set boundary buffers         bvals/cc/bvals_cc.cpp:309-560
 //   ProlongateBoundaries                bvals/bvals_refine.cpp:95-330, 553-660
 //   flux correction                     bvals/cc/flux_correction_cc.cpp:77-275
+//   face-centred field: Load / Set      bvals/fc/bvals_fc.cpp:344-976 (same level on a refined mesh, to / from
+//                                       coarser and finer), RestrictGhostCellsOnSameLevel / ProlongateGhostCells
+//                                       bvals/bvals_refine.cpp:318-356, 588-637
+//   EMF correction across levels        bvals/fc/flux_correction_fc.cpp:315-570, 944-1190, 1214-1541;
+//                                       CountFineEdges bvals/fc/bvals_fc.cpp:1129-1197
 #include <algorithm>
 #include <cmath>
 
@@ -526,6 +531,323 @@ void Mesh::SetupRefinement() {
       }
     }
   }
+  if (MAGNETIC_FIELDS_ENABLED) SetupFieldRefinement(ph);
   for (int p = 0; p < ATHK_REFINE_NPHASES; ++p)
     AthkCheck(athk_refine_set_ops(athk, p, ph[p].data(), (int)ph[p].size()), who);
+}
+
+//----------------------------------------------------------------------------------------
+// Face-centred field and EMF correction on a refined mesh.  Lists (see Mesh::ExchangeGhosts and
+// TimeIntegratorTaskList::DoTaskListOneStage for the order they run in):
+//   1  (shared with the cell-centred boxes) RestrictField for coarser neighbours
+//   8, 9, 10  SetBoundarySameLevel / SetBoundaryFromFiner of face, edge, corner neighbours: the reference
+//      sets neighbour after neighbour in that order and edge / corner neighbours overwrite shared faces
+//   11 SetBoundaryFromCoarser (after 8-10: it overwrites boundary faces of the coarse buffer that the
+//      restriction for OTHER neighbours produced and list 8-10 still read)
+//   3  (shared) RestrictGhostCellsOnSameLevel, 12 ProlongateSharedField, 13 ProlongateInternalField
+//   14 ClearCoarseFluxBoundary, 16 + slot SetFluxBoundaryFromFiner of the slot-th face / edge neighbour
+//      (accumulation order = neighbour order), 15 AverageFluxBoundary where finer EMFs were summed
+void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
+  const char *who = "Mesh::SetupFieldRefinement";
+  const int ng = NGHOST, cng = (NGHOST + 1) / 2 + 1;
+  for (int n = 0; n < nbtotal; ++n) {
+    MeshBlock *pmb = blocks_[n];
+    const int t = pmb->lid, L = pmb->loc.level;
+    const int s_[3] = {pmb->is, pmb->js, pmb->ks}, e_[3] = {pmb->ie, pmb->je, pmb->ke};
+    const int nx[3] = {pmb->block_size.nx1, pmb->block_size.nx2, pmb->block_size.nx3};
+    const int cs[3] = {ng, ng, ng}, ce[3] = {ng + nx[0] / 2 - 1, ng + nx[1] / 2 - 1, ng + nx[2] / 2 - 1};
+    const std::int64_t lx[3] = {pmb->loc.lx1, pmb->loc.lx2, pmb->loc.lx3};
+    auto mk = [](const int lo[3], const int hi[3]) { return Box{lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]}; };
+    // which of (fi1, fi2) halves direction d of a neighbour at offset o (bvals_fc.cpp:820-860)
+    auto fi_of = [](const int o[3], int d, int fi1, int fi2) {
+      if (d == 0) return fi1;
+      if (d == 1) return (o[0] != 0) ? fi1 : fi2;
+      return (o[0] != 0 && o[1] != 0) ? fi1 : fi2;
+    };
+    // LoadBoundaryBufferToCoarser (bvals_fc.cpp:403-470): coarse-index box of component c the block restricts
+    // for a coarser neighbour at offset p
+    auto to_coarser_fc = [&](int c, const int p[3], bool face) {
+      int lo[3], hi[3];
+      for (int d = 0; d < 3; ++d) {
+        if (d == c) {
+          if (p[d] == 0) { lo[d] = cs[d]; hi[d] = ce[d] + 1; }
+          else if (p[d] > 0) { lo[d] = ce[d] - ng + 1; hi[d] = ce[d]; }
+          else { lo[d] = cs[d] + 1; hi[d] = cs[d] + ng; }
+          if (!face) { if (p[d] > 0) hi[d]++; else if (p[d] < 0) lo[d]--; }
+        } else {
+          if (p[d] == 0) { lo[d] = cs[d]; hi[d] = ce[d]; }
+          else if (p[d] > 0) { lo[d] = ce[d] - ng + 1; hi[d] = ce[d]; }
+          else { lo[d] = cs[d]; hi[d] = cs[d] + ng - 1; }
+        }
+      }
+      return mk(lo, hi);
+    };
+    for (const NeighborBlock &nb : pmb->neighbor) {
+      const int o[3] = {nb.ox1, nb.ox2, nb.ox3};
+      const int po[3] = {-nb.ox1, -nb.ox2, -nb.ox3};
+      const bool face = (nb.type == 0);
+      const int list_set = 8 + nb.type;
+      if (nb.level == L) {
+        // ---- SetBoundarySameLevel, multilevel form (bvals_fc.cpp:583-680)
+        for (int c = 0; c < 3; ++c) {
+          int lo[3], hi[3];
+          for (int d = 0; d < 3; ++d) {
+            if (d == c) {
+              if (o[d] == 0) { lo[d] = s_[d]; hi[d] = e_[d] + 1; }
+              else if (o[d] > 0) { lo[d] = e_[d] + 2; hi[d] = e_[d] + ng + 1; }
+              else { lo[d] = s_[d] - ng; hi[d] = s_[d] - 1; }
+              if (!face) { if (o[d] > 0) lo[d]--; else if (o[d] < 0) hi[d]++; }
+            } else {
+              if (o[d] == 0) { lo[d] = s_[d]; hi[d] = e_[d]; }
+              else if (o[d] > 0) { lo[d] = e_[d] + 1; hi[d] = e_[d] + ng; }
+              else { lo[d] = s_[d] - ng; hi[d] = s_[d] - 1; }
+            }
+          }
+          ph[list_set].push_back(MakeOp(9, t, nb.lid, c, mk(lo, hi), lo[0] - o[0] * nx[0], lo[1] - o[1] * nx[1],
+                                        lo[2] - o[2] * nx[2]));
+        }
+      } else if (nb.level > L) {
+        // ---- SetBoundaryFromFiner (bvals_fc.cpp:813-976) <- the finer block's restricted box
+        for (int c = 0; c < 3; ++c) {
+          int lo[3], hi[3];
+          for (int d = 0; d < 3; ++d) {
+            const int fi = fi_of(o, d, nb.fi1, nb.fi2);
+            if (d == c) {
+              if (o[d] == 0) { lo[d] = s_[d]; hi[d] = e_[d] + 1; if (fi == 1) lo[d] += nx[d] / 2; else hi[d] -= nx[d] / 2; }
+              else if (o[d] > 0) { lo[d] = e_[d] + 2; hi[d] = e_[d] + ng + 1; }
+              else { lo[d] = s_[d] - ng; hi[d] = s_[d] - 1; }
+              if (!face) { if (o[d] > 0) lo[d]--; else if (o[d] < 0) hi[d]++; }
+            } else {
+              if (o[d] == 0) { lo[d] = s_[d]; hi[d] = e_[d]; if (fi == 1) lo[d] += nx[d] / 2; else hi[d] -= nx[d] / 2; }
+              else if (o[d] > 0) { lo[d] = e_[d] + 1; hi[d] = e_[d] + ng; }
+              else { lo[d] = s_[d] - ng; hi[d] = s_[d] - 1; }
+            }
+          }
+          const Box d = mk(lo, hi), sb = to_coarser_fc(c, po, face);   // (block sizes are equal on every level)
+          if (sb.count() != d.count() || (sb.ei - sb.si) != (d.ei - d.si) || (sb.ej - sb.sj) != (d.ej - d.sj)) {
+            std::stringstream msg;
+            msg << "### FATAL ERROR in " << who << std::endl << "to-coarser field boxes of blocks " << nb.gid << " -> " << n
+                << " disagree" << std::endl;
+            ATHENA_ERROR(msg);
+          }
+          ph[list_set].push_back(MakeOp(11, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
+        }
+      } else {
+        // ---- list 1: RestrictField for this coarser neighbour (LoadBoundaryBufferToCoarser)
+        for (int c = 0; c < 3; ++c) ph[1].push_back(MakeOp(10, t, t, c, to_coarser_fc(c, o, face), 0, 0, 0));
+        // ---- list 11: SetBoundaryFromCoarser (bvals_fc.cpp:690-806) <- LoadBoundaryBufferToFiner of the
+        // coarser block (:476-576), which sees this block at -o with fi = this block's parities
+        int fi1 = 0, fi2 = 0;
+        {
+          const int par[3] = {(int)(lx[0] & 1LL), (int)(lx[1] & 1LL), (int)(lx[2] & 1LL)};
+          const int nz = (po[0] != 0) + (po[1] != 0) + (po[2] != 0);
+          if (nz == 1) {
+            if (po[0] != 0) { fi1 = par[1]; fi2 = par[2]; }
+            else if (po[1] != 0) { fi1 = par[0]; fi2 = par[2]; }
+            else { fi1 = par[0]; fi2 = par[1]; }
+          } else if (nz == 2) {
+            if (po[2] == 0) fi1 = par[2];
+            else if (po[1] == 0) fi1 = par[1];
+            else fi1 = par[0];
+          }
+        }
+        const int cn = cng - 1;
+        for (int c = 0; c < 3; ++c) {
+          int lo[3], hi[3], slo[3], shi[3];
+          for (int d = 0; d < 3; ++d) {
+            const bool even = (lx[d] & 1LL) == 0LL;
+            const int fi = fi_of(po, d, fi1, fi2);
+            if (d == c) {
+              if (o[d] == 0) { lo[d] = cs[d]; hi[d] = ce[d] + 1; if (even) hi[d] += cng; else lo[d] -= cng; }
+              else if (o[d] > 0) { lo[d] = ce[d] + 1; hi[d] = ce[d] + 1 + cng; }
+              else { lo[d] = cs[d] - cng; hi[d] = cs[d]; }
+              if (po[d] == 0) {
+                if (fi == 1) { slo[d] = s_[d] + nx[d] / 2 - cng; shi[d] = e_[d] + 1; }
+                else { slo[d] = s_[d]; shi[d] = e_[d] + 1 - nx[d] / 2 + cng; }
+              } else if (po[d] > 0) { slo[d] = e_[d] + 1 - cng; shi[d] = e_[d] + 1; }
+              else { slo[d] = s_[d]; shi[d] = s_[d] + cng; }
+            } else {
+              if (o[d] == 0) { lo[d] = cs[d]; hi[d] = ce[d]; if (even) hi[d] += cng; else lo[d] -= cng; }
+              else if (o[d] > 0) { lo[d] = ce[d] + 1; hi[d] = ce[d] + cng; }
+              else { lo[d] = cs[d] - cng; hi[d] = cs[d] - 1; }
+              if (po[d] == 0) {
+                slo[d] = s_[d]; shi[d] = e_[d];
+                if (fi == 1) slo[d] += nx[d] / 2 - cng; else shi[d] -= nx[d] / 2 - cng;
+              } else if (po[d] > 0) { slo[d] = e_[d] - cn; shi[d] = e_[d]; }
+              else { slo[d] = s_[d]; shi[d] = s_[d] + cn; }
+            }
+          }
+          const Box d = mk(lo, hi), sb = mk(slo, shi);
+          if (sb.count() != d.count() || (sb.ei - sb.si) != (d.ei - d.si) || (sb.ej - sb.sj) != (d.ej - d.sj)) {
+            std::stringstream msg;
+            msg << "### FATAL ERROR in " << who << std::endl << "to-finer field boxes of blocks " << nb.gid << " -> " << n
+                << " disagree (component " << c << ")" << std::endl;
+            ATHENA_ERROR(msg);
+          }
+          ph[11].push_back(MakeOp(12, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
+        }
+        // ---- list 3: RestrictGhostCellsOnSameLevel, field part (bvals_refine.cpp:318-356)
+        const int nlo[3] = {std::max(o[0] - 1, -1), std::max(o[1] - 1, -1), std::max(o[2] - 1, -1)};
+        const int nhi[3] = {std::min(o[0] + 1, 1), std::min(o[1] + 1, 1), std::min(o[2] + 1, 1)};
+        for (int nk = nlo[2]; nk <= nhi[2]; ++nk)
+          for (int nj = nlo[1]; nj <= nhi[1]; ++nj)
+            for (int ni = nlo[0]; ni <= nhi[0]; ++ni) {
+              const int nn[3] = {ni, nj, nk};
+              if (std::abs(ni) + std::abs(nj) + std::abs(nk) == 0 || pmb->nblevel[nk + 1][nj + 1][ni + 1] != L) continue;
+              int rlo[3], rhi[3];
+              for (int d = 0; d < 3; ++d) {
+                if (nn[d] == 0) { rlo[d] = cs[d]; rhi[d] = ce[d]; if (o[d] == 1) rlo[d] = ce[d]; else if (o[d] == -1) rhi[d] = cs[d]; }
+                else if (nn[d] == 1) { rlo[d] = rhi[d] = ce[d] + 1; }
+                else { rlo[d] = rhi[d] = cs[d] - 1; }
+              }
+              for (int c = 0; c < 3; ++c) {
+                int lo[3] = {rlo[0], rlo[1], rlo[2]}, hi[3] = {rhi[0], rhi[1], rhi[2]};
+                hi[c] = rhi[c] + 1;
+                // the face on the block's boundary is not restricted when the block beyond it is coarser
+                int m[3] = {ni + 1, nj + 1, nk + 1};
+                if (lo[c] == cs[c]) { m[c] = nn[c]; if (pmb->nblevel[m[2]][m[1]][m[0]] < L) lo[c]++; }
+                m[c] = nn[c] + 1;
+                if (hi[c] == ce[c] + 1) { m[c] = nn[c] + 2; if (pmb->nblevel[m[2]][m[1]][m[0]] < L) hi[c]--; }
+                if (lo[c] > hi[c]) continue;
+                ph[3].push_back(MakeOp(10, t, t, c, mk(lo, hi), 0, 0, 0));
+              }
+            }
+        // ---- lists 12, 13: ProlongateGhostCells, field part (bvals_refine.cpp:588-637)
+        int plo[3], phi[3];
+        for (int d = 0; d < 3; ++d) {
+          if (o[d] == 0) { plo[d] = cs[d]; phi[d] = ce[d]; if ((lx[d] & 1LL) == 0LL) phi[d] += cn; else plo[d] -= cn; }
+          else if (o[d] > 0) { plo[d] = ce[d] + 1; phi[d] = ce[d] + cn; }
+          else { plo[d] = cs[d] - cn; phi[d] = cs[d] - 1; }
+        }
+        for (int c = 0; c < 3; ++c) {
+          int lo[3] = {plo[0], plo[1], plo[2]}, hi[3] = {phi[0], phi[1], phi[2]};
+          hi[c] = phi[c] + 1;
+          int m[3] = {o[0] + 1, o[1] + 1, o[2] + 1};
+          m[c] = o[c];       // the block below this neighbour in direction c
+          if (o[c] >= 0 && pmb->nblevel[m[2]][m[1]][m[0]] >= L) lo[c]++;
+          m[c] = o[c] + 2;   // ... and above it
+          if (o[c] <= 0 && pmb->nblevel[m[2]][m[1]][m[0]] >= L) hi[c]--;
+          if (lo[c] > hi[c]) continue;
+          ph[12].push_back(MakeOp(13, t, t, c, mk(lo, hi), 0, 0, 0));
+        }
+        ph[13].push_back(MakeOp(14, t, t, 0, mk(plo, phi), 0, 0, 0));
+      }
+    }
+    // ---- EMF correction: CountFineEdges (bvals_fc.cpp:1129-1197)
+    bool edge_flag[12];
+    int nedge_fine[12];
+    {
+      int eid = 0;
+      for (int pl = 0; pl < 3; ++pl)   // x1x2 (ox2 outer, ox1 inner), x1x3 (ox3, ox1), x2x3 (ox3, ox2)
+        for (int oa = -1; oa <= 1; oa += 2)
+          for (int ob = -1; ob <= 1; ob += 2) {
+            const int as = std::max(oa - 1, -1), ae = std::min(oa + 1, 1), bs = std::max(ob - 1, -1), be = std::min(ob + 1, 1);
+            int nf = 0, fl = L;
+            for (int na = as; na <= ae; ++na)
+              for (int nbb = bs; nbb <= be; ++nbb) {
+                const int lev = (pl == 0) ? pmb->nblevel[1][na + 1][nbb + 1]
+                                          : (pl == 1 ? pmb->nblevel[na + 1][1][nbb + 1] : pmb->nblevel[na + 1][nbb + 1][1]);
+                if (lev > fl) { fl++; nf = 0; }
+                if (lev == fl) nf++;
+              }
+            edge_flag[eid] = (fl == L);
+            nedge_fine[eid++] = nf;
+          }
+    }
+    const int is = s_[0], ie = e_[0], js = s_[1], je = e_[1], ks = s_[2], ke = e_[2];
+    // ---- list 14 ClearCoarseFluxBoundary (:1214-1350) and list 15 AverageFluxBoundary (:1355-1541), the
+    // parts that concern EMFs summed from finer blocks (the same-level average is athk_recv_flux_correction's)
+    for (int f = 0; f < 6; ++f) {
+      const int dir = f / 2, side = f & 1;
+      const int lev = (dir == 0) ? pmb->nblevel[1][1][2 * side] : (dir == 1 ? pmb->nblevel[1][2 * side][1] : pmb->nblevel[2 * side][1][1]);
+      if (lev <= L) continue;
+      if (dir == 0) {
+        const int i = side ? ie + 1 : is;
+        ph[14].push_back(MakeOp(15, t, t, 1, Box{i, i, js, je, ks + 1, ke}, 0, 0, 0));
+        ph[14].push_back(MakeOp(15, t, t, 2, Box{i, i, js + 1, je, ks, ke}, 0, 0, 0));
+        const int km = ks + nx[2] / 2, jm = js + nx[1] / 2;
+        ph[15].push_back(MakeOp(17, t, 2, 1, Box{i, i, js, je, km, km}, 0, 0, 0));
+        ph[15].push_back(MakeOp(17, t, 2, 2, Box{i, i, jm, jm, ks, ke}, 0, 0, 0));
+      } else if (dir == 1) {
+        const int j = side ? je + 1 : js;
+        ph[14].push_back(MakeOp(15, t, t, 0, Box{is, ie, j, j, ks + 1, ke}, 0, 0, 0));
+        ph[14].push_back(MakeOp(15, t, t, 2, Box{is + 1, ie, j, j, ks, ke}, 0, 0, 0));
+        const int km = ks + nx[2] / 2, im = is + nx[0] / 2;
+        ph[15].push_back(MakeOp(17, t, 2, 0, Box{is, ie, j, j, km, km}, 0, 0, 0));
+        ph[15].push_back(MakeOp(17, t, 2, 2, Box{im, im, j, j, ks, ke}, 0, 0, 0));
+      } else {
+        const int k = side ? ke + 1 : ks;
+        ph[14].push_back(MakeOp(15, t, t, 0, Box{is, ie, js + 1, je, k, k}, 0, 0, 0));
+        ph[14].push_back(MakeOp(15, t, t, 1, Box{is + 1, ie, js, je, k, k}, 0, 0, 0));
+        const int jm = js + nx[1] / 2, im = is + nx[0] / 2;
+        ph[15].push_back(MakeOp(17, t, 2, 0, Box{is, ie, jm, jm, k, k}, 0, 0, 0));
+        ph[15].push_back(MakeOp(17, t, 2, 1, Box{im, im, js, je, k, k}, 0, 0, 0));
+      }
+    }
+    for (int eid = 0; eid < 12; ++eid) {
+      if (edge_flag[eid]) continue;
+      Box b;
+      int comp;
+      if (eid < 4) { const int i = (eid & 1) ? ie + 1 : is, j = (eid & 2) ? je + 1 : js; b = Box{i, i, j, j, ks, ke}; comp = 2; }
+      else if (eid < 8) { const int i = (eid & 1) ? ie + 1 : is, k = (eid & 2) ? ke + 1 : ks; b = Box{i, i, js, je, k, k}; comp = 1; }
+      else { const int j = (eid & 1) ? je + 1 : js, k = (eid & 2) ? ke + 1 : ks; b = Box{is, ie, j, j, k, k}; comp = 0; }
+      ph[14].push_back(MakeOp(15, t, t, comp, b, 0, 0, 0));
+      if (nedge_fine[eid] != 1) ph[15].push_back(MakeOp(17, t, nedge_fine[eid], comp, b, 0, 0, 0));
+    }
+    // ---- lists 16 + slot: SetFluxBoundaryFromFiner (:944-1165) of the restricted surface EMFs the finer
+    // neighbour loads (LoadFluxBoundaryBufferToCoarser :315-570)
+    for (const NeighborBlock &nb : pmb->neighbor) {
+      if (nb.level != L + 1 || nb.type > 1) continue;
+      const int h1 = nx[0] / 2, h2 = nx[1] / 2, h3 = nx[2] / 2;
+      if (nb.type == 0) {
+        const int dir = nb.fid / 2, outer = nb.fid & 1;
+        const int list = 16 + nb.fid * 4 + nb.fi2 * 2 + nb.fi1;
+        int il = is, iu = ie, jl = js, ju = je, kl = ks, ku = ke;
+        if (dir == 0) {
+          const int i = outer ? ie + 1 : is, fi = outer ? is : ie + 1;
+          if (nb.fi1 == 0) ju = js + h2 - 1; else jl = js + h2;
+          if (nb.fi2 == 0) ku = ks + h3 - 1; else kl = ks + h3;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, kl, ku + 1}, fi, js, ks));
+          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{i, i, jl, ju + 1, kl, ku}, fi, js, ks));
+        } else if (dir == 1) {
+          const int j = outer ? je + 1 : js, fj = outer ? js : je + 1;
+          if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
+          if (nb.fi2 == 0) ku = ks + h3 - 1; else kl = ks + h3;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, kl, ku + 1}, is, fj, ks));
+          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{il, iu + 1, j, j, kl, ku}, is, fj, ks));
+        } else {
+          const int k = outer ? ke + 1 : ks, fk = outer ? ks : ke + 1;
+          if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
+          if (nb.fi2 == 0) ju = js + h2 - 1; else jl = js + h2;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, jl, ju + 1, k, k}, is, js, fk));
+          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{il, iu + 1, jl, ju, k, k}, is, js, fk));
+        }
+      } else {
+        int eid;
+        if (nb.ox3 == 0) eid = ((nb.ox1 + 1) >> 1) | ((nb.ox2 + 1) & 2);
+        else if (nb.ox2 == 0) eid = 4 + (((nb.ox1 + 1) >> 1) | ((nb.ox3 + 1) & 2));
+        else eid = 8 + (((nb.ox2 + 1) >> 1) | ((nb.ox3 + 1) & 2));
+        const int list = 16 + 24 + eid * 2 + nb.fi1;
+        if (eid < 4) {
+          const int i = (eid & 1) ? ie + 1 : is, j = (eid & 2) ? je + 1 : js;
+          const int fi = (eid & 1) ? is : ie + 1, fj = (eid & 2) ? js : je + 1;
+          int kl = ks, ku = ke;
+          if (nb.fi1 == 0) ku = ks + h3 - 1; else kl = ks + h3;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{i, i, j, j, kl, ku}, fi, fj, ks));
+        } else if (eid < 8) {
+          const int i = (eid & 1) ? ie + 1 : is, k = (eid & 2) ? ke + 1 : ks;
+          const int fi = (eid & 1) ? is : ie + 1, fk = (eid & 2) ? ks : ke + 1;
+          int jl = js, ju = je;
+          if (nb.fi1 == 0) ju = js + h2 - 1; else jl = js + h2;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, k, k}, fi, js, fk));
+        } else {
+          const int j = (eid & 1) ? je + 1 : js, k = (eid & 2) ? ke + 1 : ks;
+          const int fj = (eid & 1) ? js : je + 1, fk = (eid & 2) ? ks : ke + 1;
+          int il = is, iu = ie;
+          if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
+          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, k, k}, is, fj, fk));
+        }
+      }
+    }
+  }
 }

@@ -106,6 +106,12 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
     all([&](athk_ctx *a) { return athk_send_flux_correction(a); });                            // SEND_FLDFLX
     if (pm->ngpu > 1) all([&](athk_ctx *a) { return athk_remote_pack_emf(a); });
     all([&](athk_ctx *a) { return athk_recv_flux_correction(a); });                            // RECV_FLDFLX
+    if (pm->multilevel) {   // ... from finer blocks (flux_correction_fc.cpp:1648-1680): clear, add neighbour by
+                            // neighbour (lists 16..63, most of them empty), average
+      all([&](athk_ctx *a) { return athk_refine_run(a, 14, 0); });
+      for (int list = 16; list < 16 + 48; ++list) all([&](athk_ctx *a) { return athk_refine_run(a, list, 0); });
+      all([&](athk_ctx *a) { return athk_refine_run(a, 15, 0); });
+    }
   }
   // IntegrateHydro (:1797-1847)
   const Real w1[5] = {1.0, sw.delta, 0.0, 0.0, 0.0};

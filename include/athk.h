@@ -228,7 +228,7 @@ typedef struct athk_src_args {
 typedef int (*athk_src_fn)(void *user, const athk_src_args *args);
 int athk_enroll_user_source(athk_ctx *ctx, athk_src_fn fn, void *user);
 int athk_set_source_time(athk_ctx *ctx, double time);
-/* ---- static mesh refinement, cell-centred variables (hydro) ---------------------------------
+/* ---- static mesh refinement (hydro and MHD) -------------------------------------------------
  * The host owns the block tree and the neighbour levels (MeshBlockTree, BoundaryBase::
  * SearchAndSetNeighbors) and hands the library, per phase of the boundary exchange, the list of
  * index boxes the reference's Load/Set/Restrict/Prolongate functions loop over; the library holds
@@ -247,7 +247,25 @@ int athk_set_source_time(athk_ctx *ctx, double time);
  *         8 ApplyPhysicalBoundariesOnCoarseLevel (bvals_refine.cpp:445-530): the reflecting (src = 1) or
  *           outflow (src = 2) function on the coarse primitives, one ghost layer of direction dir copied
  *           from the active coarse cell so[dir]
- * Boxes are inclusive (i, j, k) ranges of the destination; so = source origin matching lo. */
+ * MHD (dir = component of the face field / of the edge EMF):
+ *         9 SetBoundarySameLevel on a refined mesh (edge and corner neighbours also set the faces
+ *           they share: bvals_fc.cpp:583-680): b[dst].dir box <- b[src].dir
+ *        10 RestrictFieldX1/X2/X3 own b -> own coarse_b        (mesh_refinement.cpp:272-460;
+ *           LoadBoundaryBufferToCoarser bvals_fc.cpp:403, RestrictGhostCellsOnSameLevel bvals_refine.cpp:318)
+ *        11 SetBoundaryFromFiner: b[dst].dir box <- coarse_b of src          (bvals_fc.cpp:813)
+ *        12 LoadBoundaryBufferToFiner + SetBoundaryFromCoarser: coarse_b of dst <- b[src] (:476,:690)
+ *        13 ProlongateSharedFieldX1/X2/X3 over a coarse face box   (mesh_refinement.cpp:776-1220)
+ *        14 ProlongateInternalField over a coarse cell box         (mesh_refinement.cpp:1223)
+ *        15 ClearCoarseFluxBoundary: e[dst].dir box = 0            (flux_correction_fc.cpp:1214)
+ *        16 LoadFluxBoundaryBufferToCoarser + SetFluxBoundaryFromFiner: e[dst].dir box += the
+ *           length-weighted pairs of the finer src's surface EMFs as athk_send_flux_correction packed
+ *           them (flux_correction_fc.cpp:315, 944)
+ *        17 AverageFluxBoundary: e[dst].dir box *= 1/src            (flux_correction_fc.cpp:1355)
+ *   kinds 4 and 6 on an MHD context also form the cell-centred field of the coarse buffer / of the
+ *   prolongated ghost zones (bvals_refine.cpp:437, 640-657).
+ * Boxes are inclusive (i, j, k) ranges of the destination; so = source origin matching lo.  Boxes of
+ * one list run concurrently: lists whose boxes overwrite each other with different values (face,
+ * edge, corner neighbours of the field; successive EMF contributions) are the host's to keep apart. */
 #define ATHK_NBR_REFINED (-1000000)
 typedef struct athk_box_op {
   int kind, dst, src, dir;
@@ -255,8 +273,9 @@ typedef struct athk_box_op {
   int so[3];
   int pad;
 } athk_box_op;
-enum { ATHK_REFINE_NPHASES = 8 };
-/* allocates coarse_cons_ / coarse_prim_ (hydro/hydro.cpp:60-75): 2 x 5 x (nx/2 + 2 nghost)^3 per block */
+enum { ATHK_REFINE_NPHASES = 96 };
+/* allocates coarse_cons_ / coarse_prim_ (hydro/hydro.cpp:60-75): 2 x 5 x (nx/2 + 2 nghost)^3 per block;
+ * MHD: also coarse_b_ / coarse_bcc_ (field/field.cpp:60-75) */
 int athk_refine_enable(athk_ctx *ctx);
 /* Coordinates::x?v of the block and of its coarse twin pcoarsec (mesh_refinement.cpp:60-75), lengths
  * nc? and nx?/2 + 2 nghost */
@@ -264,7 +283,7 @@ int athk_refine_set_block_coords(athk_ctx *ctx, int lb, const double *x1v, const
                                  const double *cx1v, const double *cx2v, const double *cx3v);
 /* the boxes of one phase (0 .. ATHK_REFINE_NPHASES-1; their meaning is the host's), copied to the device */
 int athk_refine_set_ops(athk_ctx *ctx, int phase, const athk_box_op *ops, int nops);
-/* one launch over all boxes of the phase; reg = the conserved register kinds 1-3 and 6 act on */
+/* one launch over all boxes of the phase; reg = the conserved (and field) register the boxes act on */
 int athk_refine_run(athk_ctx *ctx, int phase, int reg);
 /* time and dt handed to the user functions by the next athk_apply_physical_boundaries / athk_stage
  * (time_integrator.cpp:2276-2290: end-of-stage time and the stage's dt) */

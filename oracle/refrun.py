@@ -47,6 +47,7 @@ CONFIGS = {
     "cpaw_mhd_hlld": dict(PROB="cpaw", MHD=1, FLUX="hlld"),
     "fieldloop_mhd_hlld": dict(PROB="field_loop", MHD=1, FLUX="hlld"),
     "linwave_hydro_hllc_g4": dict(PROB="linear_wave", MHD=0, FLUX="hllc", NGHOST=4),   # PPM on a refined mesh
+    "linwave_mhd_hlld_g4": dict(PROB="linear_wave", MHD=1, FLUX="hlld", NGHOST=4),     # ... with magnetic fields
     "usrsrc_hydro_hllc": dict(PROB="usrsrc", MHD=0, FLUX="hllc", PGEN="oracle"),   # oracle/pgen/usrsrc.cpp
     "usrsrc_mhd_hlld": dict(PROB="usrsrc", MHD=1, FLUX="hlld", PGEN="oracle"),
     "blast_iso_hydro_hlle": dict(PROB="blast", MHD=0, FLUX="hlle", EOS="isothermal"),

@@ -184,6 +184,24 @@ CASES = {
         refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3",
                               xorder=3),
         (1.0, 1.6, 0.2, 0.5, 0.9, 1.2, 1), (2.4, 2.9, 1.0, 1.4, 0.1, 0.3, 1)), ["--nghost=4"]),
+    # ... and MHD: restriction / prolongation of the face-centred field (shared faces, then the
+    # divergence-preserving internal faces), same-level / to-coarser / to-finer field buffers with the
+    # faces edge and corner neighbours share, EMF correction from finer blocks.  One level in the
+    # middle of the box; two levels in a corner of the periodic box with RK3; a blast crossing the
+    # level boundary; PPM with nghost=4 (cnghost=3) and two separate regions
+    "smr_linwave_mhd_centre": ("linwave_mhd_hlld", "linear_wave", True, lambda: refined(
+        refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.05, rst_dt=0.025),
+        (0.75, 2.25, 0.375, 1.125, 0.375, 1.125, 1))),
+    "smr_linwave_mhd_two_levels_rk3": ("linwave_mhd_hlld", "linear_wave", True, lambda: refined(
+        refrun.linwave_blocks(True, mesh=(24, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3"),
+        (0.0, 0.6, 0.0, 0.5, 0.9, 1.5, 2))),
+    "smr_blast_mhd": ("blast_mhd_hlld", "blast", True, lambda: refined(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.06, rst_dt=0.03, radius=0.25),
+        (-0.3, 0.3, -0.3, 0.3, -0.3, 0.3, 1))),
+    "smr_linwave_mhd_ppm_two_regions": ("linwave_mhd_hlld_g4", "linear_wave", True, lambda: refined(
+        refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3",
+                              xorder=3),
+        (1.0, 1.6, 0.2, 0.5, 0.9, 1.2, 1), (2.4, 2.9, 1.0, 1.4, 0.1, 0.3, 1)), ["--nghost=4"]),
     # user-enrolled boundary functions (Mesh::EnrollUserBoundaryFunction, BValFunc)
     "jet_user_bc_hydro": ("jet_hydro_hllc", "jet", False, lambda: jet_blocks(False)),
     "jet_user_bc_mhd_rk3": ("jet_mhd_hlld", "jet", True, lambda: jet_blocks(True, "rk3")),
@@ -686,7 +704,8 @@ def check_restart(binary, case):
             shutil.rmtree(d, ignore_errors=True)
 
 
-RESTART_CASES = ["mhd_blast", "kh_rk3_ppm_scalar", "briowu_x3_reflect_outflow", "smr_linwave_hydro_two_levels_rk3"]
+RESTART_CASES = ["mhd_blast", "kh_rk3_ppm_scalar", "briowu_x3_reflect_outflow", "smr_linwave_hydro_two_levels_rk3",
+                 "smr_linwave_mhd_centre"]
 
 
 @pytest.mark.parametrize("case", RESTART_CASES)
