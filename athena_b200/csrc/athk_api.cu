@@ -1178,6 +1178,9 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
   return ATHK_OK;
 }
 
+#ifdef ATHK_EMULATE
+#include "athk_emul_refine_check.h"
+#endif
 extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
   NEED_READY(c);
   if (!c->rf.on) return fail(ATHK_ERR_STATE, "refine_run: call athk_refine_enable first");
@@ -1189,6 +1192,27 @@ extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
                   {c->flux[0], c->flux[1], c->flux[2]}, c->rf.xv, c->rf.cxv,
                   mhd ? 1 : 0, mhd ? c->b[reg] : nullptr, c->bcc, c->rf.cb, c->rf.cbcc, c->e, c->emfbuf, c->sf};
   if (mhd && !c->b[reg]) return fail(ATHK_ERR_ARG, "refine_run: field register %d not allocated", reg);
+#ifdef ATHK_EMULATE
+  // test harness only (tests/emul/athk_emul_refine_check.h): with ATHK_REFINE_ORDER_CHECK set, the list is also
+  // run box by box in reverse order from the same state; any difference means two boxes of one list
+  // disagree about an element, which the concurrent launch on the device would turn into a race
+  if (int rcq = athk_emul_refine_order_check(c, phase, reg, f)) return rcq;
+#endif
+  static const char *serial_env = getenv("ATHK_REFINE_SERIAL");   // debugging: one launch per box of the listed phases ("all" or e.g. "12,13")
+  bool serial = false;
+  if (serial_env) {
+    char key[16];
+    snprintf(key, sizeof key, ",%d,", phase);
+    std::string sl = std::string(",") + serial_env + ",";
+    serial = (sl == ",all,") || sl.find(key) != std::string::npos;
+  }
+  if (serial) {
+    for (int n = 0; n < c->rf.nops[phase]; ++n) {
+      f.ops = c->rf.ops[phase] + n;
+      LAUNCH_NAMED(c, "athk_refine_run", launch_links(c->stream, 1, c->rf.maxvol[phase], f));
+    }
+    return ATHK_OK;
+  }
   for (int first = 0; first < c->rf.nops[phase]; first += 32768) {   // (grid.y limit)
     f.ops = c->rf.ops[phase] + first;
     const int n = std::min(32768, c->rf.nops[phase] - first);

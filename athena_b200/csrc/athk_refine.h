@@ -193,10 +193,11 @@ struct BoxOpPoint {
         b[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] =
             cb[((idx_t)op.src * 3 + op.dir) * cg.cfn + cfidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
         break;
-      case BOX_FC_FROM_COARSER:
+      case BOX_FC_FROM_COARSER: {
         cb[((idx_t)op.dst * 3 + op.dir) * cg.cfn + cfidx(cg, k, j, i)] =
             b[((idx_t)op.src * 3 + op.dir) * g.sn + gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
         break;
+      }
       case BOX_FC_PROLONG_SHARED: prolong_shared_face(op.dst, op.dir, k, j, i); break;
       case BOX_FC_PROLONG_INTERNAL: prolong_internal(op.dst, k, j, i); break;
       case BOX_EMF_CLEAR: emf[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] = 0.0; break;

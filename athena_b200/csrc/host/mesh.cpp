@@ -536,7 +536,7 @@ void Mesh::ExchangeGhosts() {
     // turn (same level and from finer), then from coarser into the coarse buffer
     if (MAGNETIC_FIELDS_ENABLED) for (int phase : {8, 9, 10}) AthkCheck(athk_refine_run(athk, phase, 0), who);
     AthkCheck(athk_refine_run(athk, 2, 0), who);
-    if (MAGNETIC_FIELDS_ENABLED) AthkCheck(athk_refine_run(athk, 11, 0), who);
+    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {11, 64, 65}) AthkCheck(athk_refine_run(athk, phase, 0), who);
     // (phase 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation;
     //  12, 13 = shared and internal faces of the prolongated field, before U(W, bcc) of phase 6)
     for (int phase : {3, 4, 7, 5}) AthkCheck(athk_refine_run(athk, phase, 0), who);

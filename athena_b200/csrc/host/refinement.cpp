@@ -542,8 +542,10 @@ void Mesh::SetupRefinement() {
 //   1  (shared with the cell-centred boxes) RestrictField for coarser neighbours
 //   8, 9, 10  SetBoundarySameLevel / SetBoundaryFromFiner of face, edge, corner neighbours: the reference
 //      sets neighbour after neighbour in that order and edge / corner neighbours overwrite shared faces
-//   11 SetBoundaryFromCoarser (after 8-10: it overwrites boundary faces of the coarse buffer that the
-//      restriction for OTHER neighbours produced and list 8-10 still read)
+//   11, 64, 65 SetBoundaryFromCoarser of face, edge, corner neighbours (in that order: two coarser blocks
+//      both hand over the face they share, and their copies of it may differ in the last bits; after 8-10:
+//      it overwrites boundary faces of the coarse buffer that the restriction for OTHER neighbours
+//      produced and lists 8-10 still read)
 //   3  (shared) RestrictGhostCellsOnSameLevel, 12 ProlongateSharedField, 13 ProlongateInternalField
 //   14 ClearCoarseFluxBoundary, 16 + slot SetFluxBoundaryFromFiner of the slot-th face / edge neighbour
 //      (accumulation order = neighbour order), 15 AverageFluxBoundary where finer EMFs were summed
@@ -635,7 +637,7 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
       } else {
         // ---- list 1: RestrictField for this coarser neighbour (LoadBoundaryBufferToCoarser)
         for (int c = 0; c < 3; ++c) ph[1].push_back(MakeOp(10, t, t, c, to_coarser_fc(c, o, face), 0, 0, 0));
-        // ---- list 11: SetBoundaryFromCoarser (bvals_fc.cpp:690-806) <- LoadBoundaryBufferToFiner of the
+        // ---- lists 11 / 64 / 65: SetBoundaryFromCoarser (bvals_fc.cpp:690-806) <- LoadBoundaryBufferToFiner of the
         // coarser block (:476-576), which sees this block at -o with fi = this block's parities
         int fi1 = 0, fi2 = 0;
         {
@@ -684,7 +686,7 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
                 << " disagree (component " << c << ")" << std::endl;
             ATHENA_ERROR(msg);
           }
-          ph[11].push_back(MakeOp(12, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
+          ph[nb.type == 0 ? 11 : 63 + nb.type].push_back(MakeOp(12, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
         }
         // ---- list 3: RestrictGhostCellsOnSameLevel, field part (bvals_refine.cpp:318-356)
         const int nlo[3] = {std::max(o[0] - 1, -1), std::max(o[1] - 1, -1), std::max(o[2] - 1, -1)};

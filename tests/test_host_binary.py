@@ -354,6 +354,28 @@ def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
 
 
+@pytest.mark.parametrize("case,ncycle", [("smr_linwave_mhd_centre", 1), ("smr_linwave_mhd_two_levels_rk3", 0),
+                                         ("smr_blast_hydro_walls", 1), ("smr_linwave_mhd_ppm_two_regions", 1)])
+def test_refinement_lists_do_not_depend_on_box_order(emul_binary, case, ncycle):
+    """The boxes of one refinement list run concurrently on the device.  The harness library runs every
+    list forwards and backwards from the same state (ATHK_REFINE_ORDER_CHECK, tests/emul/
+    athk_emul_refine_check.h) and fails if two boxes of a list disagree about an element -- e.g. two
+    coarser neighbours handing over their copies of the face they share, which is why the host keeps
+    face, edge and corner neighbours in separate lists (refinement.cpp)."""
+    cfg, prob, mhd, mk = CASES[case][:4]
+    extra = CASES[case][4] if len(CASES[case]) > 4 else []
+    blocks = mk()
+    blocks["time"]["nlim"] = ncycle   # (0: the exchange of Mesh::Initialize only)
+    os.environ["ATHK_REFINE_ORDER_CHECK"] = "1"
+    try:
+        wd, r = run_host(emul_binary, blocks, prob, mhd, extra=extra)
+    finally:
+        del os.environ["ATHK_REFINE_ORDER_CHECK"]
+    shutil.rmtree(wd, ignore_errors=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "cycle=%d" % ncycle in r.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_host_binary_on_gpu_reproduces_reference_files(cuda_lib, case):
