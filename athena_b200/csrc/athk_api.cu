@@ -1081,7 +1081,6 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->rf.on) return ATHK_OK;
   if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "refine_enable: passive scalars are not refined");
-  if (c->eos.iso) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is implemented for the adiabatic EOS");
   const Grid &g = c->g;
   if (g.nx1 % 2 || g.nx2 % 2 || g.nx3 % 2)   // mesh.cpp:340-346
     return fail(ATHK_ERR_ARG, "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR.");
@@ -1134,20 +1133,27 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
   long long maxvol = 0;
   for (int n = 0; n < nops; ++n) {   // every box must lie inside the array it addresses
     const athk_box_op &o = ops[n];
-    if (o.kind < BOX_RESTRICT || o.kind > BOX_EMF_SCALE || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
-        (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.src >= g.nb))
+    if (o.kind < BOX_RESTRICT || o.kind > BOX_COARSE_BC_FC || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
+        (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.kind != BOX_COARSE_BC_FC && o.src >= g.nb))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
     if (o.kind >= BOX_FC_COPY) {
       if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d) needs an MHD context", n, o.kind);
       if (o.kind != BOX_FC_PROLONG_INTERNAL && (o.dir < 0 || o.dir > 2))
         return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d): component %d", n, o.kind, o.dir);
       if (o.kind == BOX_EMF_SCALE && o.src < 1) return fail(ATHK_ERR_ARG, "refine_set_ops: box %d: divisor %d", n, o.src);
+      if (o.kind == BOX_COARSE_BC_FC) {
+        const int d = o.pad;
+        if (d < 0 || d > 2 || o.lo[d] != o.hi[d] || (o.src != 1 && o.src != 2) || o.so[d] < 0 ||
+            o.so[d] >= (d == 0 ? cg.cn1 : (d == 1 ? cg.cn2 : cg.cn3)) + (o.dir == d))
+          return fail(ATHK_ERR_ARG, "refine_set_ops: box %d is not a one-layer boundary box of the field", n);
+      }
     }
     const bool coarse_dst = (o.kind == BOX_RESTRICT || o.kind == BOX_FROM_COARSER || o.kind == BOX_C2P_COARSE ||
                              o.kind == BOX_PROLONG || o.kind == BOX_COARSE_BC || o.kind == BOX_FC_RESTRICT ||
                              o.kind == BOX_FC_FROM_COARSER || o.kind == BOX_FC_PROLONG_SHARED ||
-                             o.kind == BOX_FC_PROLONG_INTERNAL);
-    const bool coarse_face = (o.kind == BOX_FC_RESTRICT || o.kind == BOX_FC_FROM_COARSER || o.kind == BOX_FC_PROLONG_SHARED);
+                             o.kind == BOX_FC_PROLONG_INTERNAL || o.kind == BOX_COARSE_BC_FC);
+    const bool coarse_face = (o.kind == BOX_FC_RESTRICT || o.kind == BOX_FC_FROM_COARSER || o.kind == BOX_FC_PROLONG_SHARED ||
+                              o.kind == BOX_COARSE_BC_FC);
     if (o.kind == BOX_COARSE_BC && (o.dir < 0 || o.dir > 2 || o.lo[o.dir] != o.hi[o.dir] || (o.src != 1 && o.src != 2) ||
                                     o.so[o.dir] < 0 || o.so[o.dir] >= (o.dir == 0 ? cg.cn1 : (o.dir == 1 ? cg.cn2 : cg.cn3))))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d is not a one-layer boundary box", n);

@@ -48,7 +48,10 @@ enum {
   BOX_EMF_CLEAR = 15,       // e[dst].dir box = 0
   BOX_EMF_FROM_FINER = 16,  // e[dst].dir box += length-weighted pair of the finer src's packed surface EMFs,
                             // fine origin so (in the pair's direction and in the others: stride 2)
-  BOX_EMF_SCALE = 17        // e[dst].dir box *= 1/src
+  BOX_EMF_SCALE = 17,       // e[dst].dir box *= 1/src
+  BOX_COARSE_BC_FC = 18     // reflecting / outflow function on coarse_b_.dir, one ghost layer of boundary direction
+                            // pad (bvals/fc/reflect_fc.cpp, outflow_fc.cpp with ngh = 1): box [lo,hi] = the ghost
+                            // layer, copied from index so[pad]; src = 1 negates (the reflected normal component)
 };
 
 struct BoxOp {   // == athk_box_op (include/athk.h)
@@ -134,9 +137,11 @@ struct BoxOpPoint {
           const Real bc3 = 0.5 * bb[2 * cg.cfn] + 0.5 * bb[2 * cg.cfn + cg.cfk];
           Real *bc = cbcc + (idx_t)op.dst * 3 * cg.csn + c;
           bc[0] = bc1; bc[cg.csn] = bc2; bc[2 * cg.csn] = bc3;
-          cons2prim_mhd(eos_of_block(eos, op.dst), uc, bc1, bc2, bc3, wc);
+          if (eos.iso) cons2prim_iso(eos_of_block(eos, op.dst), uc, wc);
+          else cons2prim_mhd(eos_of_block(eos, op.dst), uc, bc1, bc2, bc3, wc);
         } else {
-          cons2prim_hydro(eos_of_block(eos, op.dst), uc, wc);
+          if (eos.iso) cons2prim_iso(eos_of_block(eos, op.dst), uc, wc);
+          else cons2prim_hydro(eos_of_block(eos, op.dst), uc, wc);
         }
         if (uc[IDN] != d0) ub[IDN * cg.csn] = uc[IDN];
         if (uc[IEN] != e0) ub[IEN * cg.csn] = uc[IEN];
@@ -162,9 +167,10 @@ struct BoxOpPoint {
           const Real bcc2 = 0.5 * bb[g.sn] + 0.5 * bb[g.sn + g.sj];
           const Real bcc3 = 0.5 * bb[2 * g.sn] + 0.5 * bb[2 * g.sn + g.sk];
           bc[0] = bcc1; bc[g.sn] = bcc2; bc[2 * g.sn] = bcc3;
-          ub[4 * g.sn] = w_p * igm1 + 0.5 * (w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz)) +
-                                             (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
-        } else {
+          if (!eos.iso)   // (isothermal: no energy, eos/isothermal_mhd.cpp:88-112)
+            ub[4 * g.sn] = w_p * igm1 + 0.5 * (w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz)) +
+                                               (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
+        } else if (!eos.iso) {
           ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
         }
         break;
@@ -200,6 +206,14 @@ struct BoxOpPoint {
       }
       case BOX_FC_PROLONG_SHARED: prolong_shared_face(op.dst, op.dir, k, j, i); break;
       case BOX_FC_PROLONG_INTERNAL: prolong_internal(op.dst, k, j, i); break;
+      case BOX_COARSE_BC_FC: {
+        const int d = op.pad;
+        const int si = (d == 0) ? op.so[0] : i, sj = (d == 1) ? op.so[1] : j, sk = (d == 2) ? op.so[2] : k;
+        Real *cbd = cb + ((idx_t)op.dst * 3 + op.dir) * cg.cfn;
+        const Real v = cbd[cfidx(cg, sk, sj, si)];
+        cbd[cfidx(cg, k, j, i)] = (op.src == 1) ? -v : v;
+        break;
+      }
       case BOX_EMF_CLEAR: emf[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] = 0.0; break;
       case BOX_EMF_FROM_FINER: emf_from_finer(op, k, j, i, dk, dj, di); break;
       case BOX_EMF_SCALE: emf[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] *= (1.0 / (Real)op.src); break;

@@ -189,14 +189,7 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
           << "Static mesh refinement on the B200 path covers hydrodynamics and MHD; passive scalars are not refined";
       ATHENA_ERROR(msg);
     }
-    if (MAGNETIC_FIELDS_ENABLED)
-      for (int n = 0; n < 6; ++n)
-        if (mesh_bcs[n] != BoundaryFlag::periodic) {
-          msg << "### FATAL ERROR in Mesh constructor" << std::endl
-              << "Static mesh refinement with magnetic fields on the B200 path takes periodic mesh boundaries (the "
-              << "face-centred boundary functions are not applied to the coarse buffer)";
-          ATHENA_ERROR(msg);
-        }
+
     if (NGHOST % 2 == 1) {   // prolongation fills 2*(cnghost-1) ghost cells: more than an odd NGHOST holds
       msg << "### FATAL ERROR in Mesh constructor" << std::endl
           << "Mesh refinement needs an even number of ghost zones (nghost=" << NGHOST << ")";
@@ -328,11 +321,6 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
                                : g_config.flux;
   cfg.eos = g_config.isothermal ? ATHK_EOS_ISOTHERMAL : ATHK_EOS_ADIABATIC;
   cfg.iso_sound_speed = g_config.isothermal ? blocks_[0]->peos->GetIsoSoundSpeed() : 0.0;
-  if (g_config.isothermal && multilevel) {
-    msg << "### FATAL ERROR in Mesh constructor" << std::endl
-        << "Static mesh refinement on the B200 path is implemented for the adiabatic EOS";
-    ATHENA_ERROR(msg);
-  }
   if (flux == "hllc") cfg.rsolver = ATHK_RS_HLLC;
   else if (flux == "hlld") cfg.rsolver = ATHK_RS_HLLD;
   else if (flux == "roe") cfg.rsolver = ATHK_RS_ROE;

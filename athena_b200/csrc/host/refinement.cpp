@@ -472,6 +472,25 @@ void Mesh::SetupRefinement() {
               if (d == 1) bb.sj = bb.ej = ghost;
               if (d == 2) bb.sk = bb.ek = ghost;
               ph[7].push_back(MakeOp(8, t, bf == BoundaryFlag::reflect ? 1 : 2, d, bb, so[0], so[1], so[2]));
+              if (MAGNETIC_FIELDS_ENABLED) {   // ... and on coarse_b_ (bvals/fc/reflect_fc.cpp, outflow_fc.cpp, ngh = 1)
+                const bool refl = (bf == BoundaryFlag::reflect);
+                for (int c = 0; c < 3; ++c) {
+                  int lo[3] = {p.si, p.sj, p.sk}, hi[3] = {p.ei, p.ej, p.ek}, fso[3] = {0, 0, 0};
+                  bool negate = false;
+                  if (c == d) {   // the normal component: faces clo-1 / chi+2 from clo+1 / chi (reflected) or clo / chi+1
+                    lo[d] = hi[d] = side ? chi[d] + 2 : clo[d] - 1;
+                    fso[d] = refl ? (side ? chi[d] : clo[d] + 1) : (side ? chi[d] + 1 : clo[d]);
+                    negate = refl;
+                  } else {        // transverse components: the ghost cell layer from the first active one
+                    lo[d] = hi[d] = side ? chi[d] + 1 : clo[d] - 1;
+                    fso[d] = side ? chi[d] : clo[d];
+                    hi[c] += 1;
+                  }
+                  athk_box_op o = MakeOp(18, t, negate ? 1 : 2, c, Box{lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]}, fso[0], fso[1], fso[2]);
+                  o.pad = d;
+                  ph[7].push_back(o);
+                }
+              }
             }
           }
         }

@@ -261,6 +261,8 @@ int athk_set_source_time(athk_ctx *ctx, double time);
  *           length-weighted pairs of the finer src's surface EMFs as athk_send_flux_correction packed
  *           them (flux_correction_fc.cpp:315, 944)
  *        17 AverageFluxBoundary: e[dst].dir box *= 1/src            (flux_correction_fc.cpp:1355)
+ *        18 as 8 for coarse_b (reflect_fc.cpp, outflow_fc.cpp with ngh = 1): the ghost layer of boundary
+ *           direction pad copied from index so[pad] of component dir, negated when src = 1
  *   kinds 4 and 6 on an MHD context also form the cell-centred field of the coarse buffer / of the
  *   prolongated ghost zones (bvals_refine.cpp:437, 640-657).
  * Boxes are inclusive (i, j, k) ranges of the destination; so = source origin matching lo.  Boxes of
