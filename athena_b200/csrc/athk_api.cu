@@ -198,7 +198,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaFree(c->stage);
   cudaFree(c->r); cudaFree(c->emfbuf); cudaFree(c->geo_store); cudaFree(c->nbr);
   cudaFree(c->rf.cu); cudaFree(c->rf.cw); cudaFree(c->rf.xv); cudaFree(c->rf.cxv);
-  cudaFree(c->rf.cb); cudaFree(c->rf.cbcc);
+  cudaFree(c->rf.cb); cudaFree(c->rf.cbcc); cudaFree(c->rf.cs); cudaFree(c->rf.cr);
   for (int p = 0; p < ATHK_REFINE_NPHASES; ++p) cudaFree(c->rf.ops[p]);
   cudaFree(c->dt_blocks);
   cudaFree(c->rl_int); cudaFree(c->rl_off); cudaFree(c->slab_tab);
@@ -1080,7 +1080,6 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   if (!c) return fail(ATHK_ERR_ARG, "refine_enable: null context");
   cudaSetDevice(c->cfg.device);
   if (c->rf.on) return ATHK_OK;
-  if (c->cfg.nscalars) return fail(ATHK_ERR_ARG, "refine_enable: passive scalars are not refined");
   const Grid &g = c->g;
   if (g.nx1 % 2 || g.nx2 % 2 || g.nx3 % 2)   // mesh.cpp:340-346
     return fail(ATHK_ERR_ARG, "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR.");
@@ -1096,6 +1095,8 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   if (!rc) rc = dev_alloc(&c->rf.cw, nc, c->stream);
   if (!rc) rc = dev_alloc(&c->rf.xv, (size_t)g.nb * 3 * c->geo.PG, c->stream);
   if (!rc) rc = dev_alloc(&c->rf.cxv, (size_t)g.nb * 3 * cg.CPG, c->stream);
+  if (!rc && c->cfg.nscalars) rc = dev_alloc(&c->rf.cs, (size_t)g.nb * c->cfg.nscalars * cg.csn, c->stream);   // coarse_s_
+  if (!rc && c->cfg.nscalars) rc = dev_alloc(&c->rf.cr, (size_t)g.nb * c->cfg.nscalars * cg.csn, c->stream);   // coarse_r_
   if (!rc && c->cfg.mhd) rc = dev_alloc(&c->rf.cb, (size_t)g.nb * 3 * cg.cfn, c->stream);     // coarse_b_ (field/field.cpp:60-70)
   if (!rc && c->cfg.mhd) rc = dev_alloc(&c->rf.cbcc, (size_t)g.nb * 3 * cg.csn, c->stream);   // coarse_bcc_
   if (rc) return rc;
@@ -1136,6 +1137,8 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
     if (o.kind < BOX_RESTRICT || o.kind > BOX_COARSE_BC_FC || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
         (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.kind != BOX_COARSE_BC_FC && o.src >= g.nb))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
+    if (o.kind < BOX_FC_COPY && o.pad != 0 && (o.pad != 1 || !c->cfg.nscalars))
+      return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d): variable set %d", n, o.kind, o.pad);
     if (o.kind >= BOX_FC_COPY) {
       if (!c->cfg.mhd) return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d) needs an MHD context", n, o.kind);
       if (o.kind != BOX_FC_PROLONG_INTERNAL && (o.dir < 0 || o.dir > 2))
@@ -1194,8 +1197,11 @@ extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
   if (bad_reg(reg) || !c->u[reg]) return fail(ATHK_ERR_ARG, "refine_run: register %d not allocated", reg);
   if (c->rf.nops[phase] == 0) return ATHK_OK;
   const bool mhd = c->cfg.mhd != 0;
+  const int ns = c->cfg.nscalars;
+  if (ns && !c->s[reg]) return fail(ATHK_ERR_ARG, "refine_run: scalar register %d not allocated", reg);
   BoxOpPoint f = {c->g, c->rf.cg, c->geo, c->eos, c->rf.ops[phase], c->u[reg], c->w, c->rf.cu, c->rf.cw,
                   {c->flux[0], c->flux[1], c->flux[2]}, c->rf.xv, c->rf.cxv,
+                  ns, ns ? c->s[reg] : nullptr, c->r, c->rf.cs, c->rf.cr, {c->sflux[0], c->sflux[1], c->sflux[2]},
                   mhd ? 1 : 0, mhd ? c->b[reg] : nullptr, c->bcc, c->rf.cb, c->rf.cbcc, c->e, c->emfbuf, c->sf};
   if (mhd && !c->b[reg]) return fail(ATHK_ERR_ARG, "refine_run: field register %d not allocated", reg);
 #ifdef ATHK_EMULATE

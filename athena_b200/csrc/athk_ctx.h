@@ -90,6 +90,7 @@ struct athk_ctx {
     CoarseGrid cg;
     Real *cu = nullptr, *cw = nullptr, *xv = nullptr, *cxv = nullptr;
     Real *cb = nullptr, *cbcc = nullptr;   // MHD: coarse_b_, coarse_bcc_
+    Real *cs = nullptr, *cr = nullptr;     // passive scalars: coarse_s_, coarse_r_
     BoxOp *ops[ATHK_REFINE_NPHASES] = {};
     int nops[ATHK_REFINE_NPHASES] = {};
     long long maxvol[ATHK_REFINE_NPHASES] = {};

@@ -85,6 +85,12 @@ struct BoxOpPoint {
   Real *flx[3];            // [nb][5][sn]
   const Real *xv;          // [nb][3][PG]   fine x1v, x2v, x3v
   const Real *cxv;         // [nb][3][CPG]  coarse (pcoarsec) x1v, x2v, x3v
+  // passive scalars (ns = 0: none): boxes with pad = 1 act on them instead of the hydro variables
+  int ns;
+  Real *s;                 // [nb][ns][sn]  the scalar register the exchange acts on
+  Real *r;                 // [nb][ns][sn]
+  Real *cs, *cr;           // [nb][ns][csn] coarse_s_, coarse_r_
+  Real *sflx[3];           // [nb][ns][sn]
   // MHD (null / 0 for hydro)
   int mhd;
   Real *b;                 // [nb][3][sn]   the field register the exchange acts on
@@ -103,23 +109,24 @@ struct BoxOpPoint {
     const int dk = (int)(e / ((idx_t)n1 * n2));
     const int i = op.lo[0] + di, j = op.lo[1] + dj, k = op.lo[2] + dk;
     switch (op.kind) {
-      case BOX_RESTRICT: restrict_cell(op.dst, k, j, i); break;
+      case BOX_RESTRICT:
+        if (op.pad == 1) restrict_cell(s, cs, ns, op.dst, k, j, i);
+        else restrict_cell(u, cu, 5, op.dst, k, j, i);
+        break;
       case BOX_FROM_FINER: {
-        const idx_t s = cidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = gidx(g, k, j, i);
-        Real v[5];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) v[n] = cu[((idx_t)op.src * 5 + n) * cg.csn + s];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) u[((idx_t)op.dst * 5 + n) * g.sn + d] = v[n];
+        const idx_t so = cidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = gidx(g, k, j, i);
+        const int nv = (op.pad == 1) ? ns : 5;
+        const Real *src = (op.pad == 1) ? cs : cu;
+        Real *dst = (op.pad == 1) ? s : u;
+        for (int n = 0; n < nv; ++n) dst[((idx_t)op.dst * nv + n) * g.sn + d] = src[((idx_t)op.src * nv + n) * cg.csn + so];
         break;
       }
       case BOX_FROM_COARSER: {
-        const idx_t s = gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = cidx(cg, k, j, i);
-        Real v[5];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) v[n] = u[((idx_t)op.src * 5 + n) * g.sn + s];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) cu[((idx_t)op.dst * 5 + n) * cg.csn + d] = v[n];
+        const idx_t so = gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = cidx(cg, k, j, i);
+        const int nv = (op.pad == 1) ? ns : 5;
+        const Real *src = (op.pad == 1) ? s : u;
+        Real *dst = (op.pad == 1) ? cs : cu;
+        for (int n = 0; n < nv; ++n) dst[((idx_t)op.dst * nv + n) * cg.csn + d] = src[((idx_t)op.src * nv + n) * g.sn + so];
         break;
       }
       case BOX_C2P_COARSE: {
@@ -147,9 +154,21 @@ struct BoxOpPoint {
         if (uc[IEN] != e0) ub[IEN * cg.csn] = uc[IEN];
 #pragma unroll
         for (int n = 0; n < 5; ++n) wb[n * cg.csn] = wc[n];
+        // PassiveScalarConservedToPrimitive on the coarse buffer (bvals_refine.cpp:443-449, eos_scalars.cpp:31-60)
+        for (int n = 0; n < ns; ++n) {
+          const idx_t o = ((idx_t)op.dst * ns + n) * cg.csn + c;
+          const Real s0 = cs[o];
+          const Real sfl = eos_sfloor(eos, op.dst);
+          const Real sn = (s0 < sfl * uc[IDN]) ? sfl * uc[IDN] : s0;
+          if (sn != s0) cs[o] = sn;
+          cr[o] = sn / uc[IDN];
+        }
         break;
       }
-      case BOX_PROLONG: prolong_cell(op.dst, k, j, i); break;
+      case BOX_PROLONG:
+        if (op.pad == 1) prolong_cell(cr, r, ns, op.dst, k, j, i);
+        else prolong_cell(cw, w, 5, op.dst, k, j, i);
+        break;
       case BOX_P2C_FINE: {
         const idx_t c = gidx(g, k, j, i);
         const Real *wb = w + (idx_t)op.dst * 5 * g.sn + c;
@@ -173,16 +192,25 @@ struct BoxOpPoint {
         } else if (!eos.iso) {
           ub[4 * g.sn] = w_p * igm1 + 0.5 * w_d * (sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
         }
+        // PassiveScalarPrimitiveToConserved (bvals_refine.cpp:658-662, eos_scalars.cpp:133-152)
+        for (int n = 0; n < ns; ++n) {
+          const idx_t o = ((idx_t)op.dst * ns + n) * g.sn + c;
+          s[o] = r[o] * w_d;
+        }
         break;
       }
       case BOX_FLUX_FROM_FINER: flux_cell(op, k, j, i, dk, dj, di); break;
       case BOX_COARSE_BC: {   // bvals/cc/outflow_cc.cpp, bvals/cc/hydro/reflect_hydro.cpp with ngh = 1
         const int si = (op.dir == 0) ? op.so[0] : i, sj = (op.dir == 1) ? op.so[1] : j, sk = (op.dir == 2) ? op.so[2] : k;
-        const idx_t s = cidx(cg, sk, sj, si), d = cidx(cg, k, j, i);
+        const idx_t so = cidx(cg, sk, sj, si), d = cidx(cg, k, j, i);
+        if (op.pad == 1) {   // coarse_r_: bvals/cc/reflect_cc.cpp, outflow_cc.cpp (plain copies)
+          for (int n = 0; n < ns; ++n) cr[((idx_t)op.dst * ns + n) * cg.csn + d] = cr[((idx_t)op.dst * ns + n) * cg.csn + so];
+          break;
+        }
         Real *wb = cw + (idx_t)op.dst * 5 * cg.csn;
         Real v[5];
 #pragma unroll
-        for (int n = 0; n < 5; ++n) v[n] = wb[n * cg.csn + s];
+        for (int n = 0; n < 5; ++n) v[n] = wb[n * cg.csn + so];
         if (op.src == 1) v[IVX + op.dir] = -v[IVX + op.dir];   // reflect the normal velocity
 #pragma unroll
         for (int n = 0; n < 5; ++n) wb[n * cg.csn + d] = v[n];
@@ -385,7 +413,7 @@ struct BoxOpPoint {
     emf[((idx_t)op.dst * 3 + c) * g.sn + gidx(g, k, j, i)] += (v1 * el1 + v2 * el2) / (el1 + el2);
   }
   // mesh_refinement.cpp:123-151 (3-D, Cartesian volumes dx1f*dx2f*dx3f, coordinates/cartesian.cpp)
-  ATHK_HD void restrict_cell(int blk, int ck, int cj, int ci) const {
+  ATHK_HD void restrict_cell(const Real *fine, Real *coarse, int nv, int blk, int ck, int cj, int ci) const {
     const int k = (ck - cg.cks) * 2 + g.ks, j = (cj - cg.cjs) * 2 + g.js, i = (ci - cg.cis) * 2 + g.is;
     const Real *dx1 = geo.dxf[0] + blk * geo.PG, *dx2 = geo.dxf[1] + blk * geo.PG, *dx3 = geo.dxf[2] + blk * geo.PG;
     // fvol_[a][b](i) = CellVolume(k+a, j+b, i) = dx1f(i)*dx2f(j+b)*dx3f(k+a)
@@ -395,19 +423,16 @@ struct BoxOpPoint {
     const Real v11i = dx1[i] * dx2[j + 1] * dx3[k + 1], v11p = dx1[i + 1] * dx2[j + 1] * dx3[k + 1];
     const Real tvol = ((v00i + v01i) + (v00p + v01p)) + ((v10i + v11i) + (v10p + v11p));
     const idx_t c = gidx(g, k, j, i), cc = cidx(cg, ck, cj, ci);
-    Real r[5];
-#pragma unroll
-    for (int n = 0; n < 5; ++n) {
-      const Real *f = u + ((idx_t)blk * 5 + n) * g.sn + c;
-      r[n] = (((f[0] * v00i + f[g.sj] * v01i) + (f[1] * v00p + f[g.sj + 1] * v01p)) +
-              ((f[g.sk] * v10i + f[g.sk + g.sj] * v11i) + (f[g.sk + 1] * v10p + f[g.sk + g.sj + 1] * v11p))) / tvol;
+    for (int n = 0; n < nv; ++n) {
+      const Real *f = fine + ((idx_t)blk * nv + n) * g.sn + c;
+      coarse[((idx_t)blk * nv + n) * cg.csn + cc] =
+          (((f[0] * v00i + f[g.sj] * v01i) + (f[1] * v00p + f[g.sj + 1] * v01p)) +
+           ((f[g.sk] * v10i + f[g.sk + g.sj] * v11i) + (f[g.sk + 1] * v10p + f[g.sk + g.sj + 1] * v11p))) / tvol;
     }
-#pragma unroll
-    for (int n = 0; n < 5; ++n) cu[((idx_t)blk * 5 + n) * cg.csn + cc] = r[n];
   }
   ATHK_HD static Real sign_of(Real x) { return (x < 0.0) ? -1.0 : 1.0; }   // SIGN(), defs.hpp.in:150
   // mesh_refinement.cpp:470-530 (3-D): minmod-limited gradients of the coarse primitives
-  ATHK_HD void prolong_cell(int blk, int k, int j, int i) const {
+  ATHK_HD void prolong_cell(const Real *cprim, Real *fprim, int nv, int blk, int k, int j, int i) const {
     const int fk = (k - cg.cks) * 2 + g.ks, fj = (j - cg.cjs) * 2 + g.js, fi = (i - cg.cis) * 2 + g.is;
     const Real *cx1 = cxv + ((idx_t)blk * 3 + 0) * cg.CPG, *cx2 = cxv + ((idx_t)blk * 3 + 1) * cg.CPG,
                *cx3 = cxv + ((idx_t)blk * 3 + 2) * cg.CPG;
@@ -420,9 +445,9 @@ struct BoxOpPoint {
     const Real x1c = cx1[i], dx1m = x1c - cx1[i - 1], dx1p = cx1[i + 1] - x1c;
     const Real dx1fm = x1c - fx1[fi], dx1fp = fx1[fi + 1] - x1c;
     const idx_t cc = cidx(cg, k, j, i), fc = gidx(g, fk, fj, fi);
-    for (int n = 0; n < 5; ++n) {
-      const Real *cb = cw + ((idx_t)blk * 5 + n) * cg.csn + cc;
-      Real *fb = w + ((idx_t)blk * 5 + n) * g.sn + fc;
+    for (int n = 0; n < nv; ++n) {
+      const Real *cb = cprim + ((idx_t)blk * nv + n) * cg.csn + cc;
+      Real *fb = fprim + ((idx_t)blk * nv + n) * g.sn + fc;
       const Real ccval = cb[0];
       const Real gx1m = (ccval - cb[-1]) / dx1m;
       const Real gx1p = (cb[1] - ccval) / dx1p;
@@ -463,15 +488,14 @@ struct BoxOpPoint {
       o1 = 1; o2 = g.sj; o3 = g.sj + 1;
     }
     const Real tarea = a0 + a1 + a2 + a3;
-    const idx_t s = gidx(g, fk, fj, fi), d = gidx(g, k, j, i);
-    Real r[5];
-#pragma unroll
-    for (int n = 0; n < 5; ++n) {
-      const Real *f = flx[op.dir] + ((idx_t)sblk * 5 + n) * g.sn + s;
-      r[n] = (f[0] * a0 + f[o1] * a1 + f[o2] * a2 + f[o3] * a3) / tarea;
+    const idx_t so = gidx(g, fk, fj, fi), d = gidx(g, k, j, i);
+    const int nv = (op.pad == 1) ? ns : 5;
+    Real *fl = (op.pad == 1) ? sflx[op.dir] : flx[op.dir];
+    // (source and destination are faces of different blocks: no element is both read and written)
+    for (int n = 0; n < nv; ++n) {
+      const Real *f = fl + ((idx_t)sblk * nv + n) * g.sn + so;
+      fl[((idx_t)op.dst * nv + n) * g.sn + d] = (f[0] * a0 + f[o1] * a1 + f[o2] * a2 + f[o3] * a3) / tarea;
     }
-#pragma unroll
-    for (int n = 0; n < 5; ++n) flx[op.dir][((idx_t)op.dst * 5 + n) * g.sn + d] = r[n];
   }
 };
 

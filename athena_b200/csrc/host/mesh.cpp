@@ -184,11 +184,6 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
     }
   }
   if (multilevel) {
-    if (NSCALARS > 0) {
-      msg << "### FATAL ERROR in Mesh constructor" << std::endl
-          << "Static mesh refinement on the B200 path covers hydrodynamics and MHD; passive scalars are not refined";
-      ATHENA_ERROR(msg);
-    }
 
     if (NGHOST % 2 == 1) {   // prolongation fills 2*(cnghost-1) ghost cells: more than an odd NGHOST holds
       msg << "### FATAL ERROR in Mesh constructor" << std::endl

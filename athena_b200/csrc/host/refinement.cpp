@@ -550,6 +550,20 @@ void Mesh::SetupRefinement() {
       }
     }
   }
+  if (NSCALARS > 0) {
+    // passive scalars travel with the hydro variables (MeshRefinement::pvars_cc_: (s, coarse_s_), then
+    // (r, coarse_r_) for the prolongation, bvals_refine.cpp:560-575): every cell-centred box gets a twin
+    // acting on them (pad = 1); W(U) / U(W) boxes handle them in place.  The flux correction of
+    // s_flux is its own list (66): the scalar fluxes are formed after the hydro ones.
+    for (int list : {1, 2, 3, 5, 7}) {
+      const std::size_t n0 = ph[list].size();
+      for (std::size_t q = 0; q < n0; ++q) {
+        athk_box_op o = ph[list][q];
+        if (o.kind == 1 || o.kind == 2 || o.kind == 3 || o.kind == 5 || o.kind == 8) { o.pad = 1; ph[list].push_back(o); }
+      }
+    }
+    for (athk_box_op o : ph[0]) { o.pad = 1; ph[66].push_back(o); }
+  }
   if (MAGNETIC_FIELDS_ENABLED) SetupFieldRefinement(ph);
   for (int p = 0; p < ATHK_REFINE_NPHASES; ++p)
     AthkCheck(athk_refine_set_ops(athk, p, ph[p].data(), (int)ph[p].size()), who);

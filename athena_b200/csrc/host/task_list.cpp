@@ -101,6 +101,8 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   if (pm->multilevel)   // SEND/RECV_HYDFLX: fluxes on faces shared with finer blocks (:1757-1795)
     all([&](athk_ctx *a) { return athk_refine_run(a, 0, 0); });
   if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_calculate_scalar_fluxes(a, order); });  // CALC_SCLRFLX :2329-2340
+  if (NSCALARS > 0 && pm->multilevel)   // SEND/RECV_SCLRFLX (:2342-2374)
+    all([&](athk_ctx *a) { return athk_refine_run(a, 66, 0); });
   if (mhd) {
     all([&](athk_ctx *a) { return athk_compute_corner_e(a); });                                // CALC_FLDFLX
     all([&](athk_ctx *a) { return athk_send_flux_correction(a); });                            // SEND_FLDFLX

@@ -247,6 +247,9 @@ int athk_set_source_time(athk_ctx *ctx, double time);
  *         8 ApplyPhysicalBoundariesOnCoarseLevel (bvals_refine.cpp:445-530): the reflecting (src = 1) or
  *           outflow (src = 2) function on the coarse primitives, one ghost layer of direction dir copied
  *           from the active coarse cell so[dir]
+ * Passive scalars: a box of kind 1, 2, 3, 5, 7 or 8 with pad = 1 acts on s / coarse_s_ / r / coarse_r_ /
+ * s_flux instead of the hydro variables (MeshRefinement::pvars_cc_, bvals_refine.cpp:560-575); kinds 4
+ * and 6 convert them along with the hydro variables (eos/eos_scalars.cpp).
  * MHD (dir = component of the face field / of the edge EMF):
  *         9 SetBoundarySameLevel on a refined mesh (edge and corner neighbours also set the faces
  *           they share: bvals_fc.cpp:583-680): b[dst].dir box <- b[src].dir

@@ -208,6 +208,13 @@ CASES = {
                             bcs=["reflecting", "outflow", "outflow", "reflecting", "reflecting", "outflow"],
                             center=(-0.6, 0.5, -0.55)),
         (-1.0, -0.4, 0.3, 1.0, -1.0, -0.3, 1), (0.5, 1.0, -1.0, -0.6, 0.4, 1.0, 2))),
+    # ... with passive scalars (restriction of s, prolongation of r = s / rho, flux correction of s_flux)
+    "smr_kh_hydro_2scalars": ("kh_hydro_hllc_s2", "kh", False, lambda: refined(
+        refrun.kh_blocks(mesh=(16, 32, 16), block=(8, 8, 8), tlim=0.05, rst_dt=0.025, integrator="vl2", xorder=2,
+                         drho_rho0=0.5), (-0.2, 0.2, 0.3, 0.7, -0.1, 0.1, 1)), ["--nscalars=2"]),
+    "smr_kh_mhd_scalar_rk3": ("kh_mhd_hlld_s1", "kh", True, lambda: refined(
+        refrun.kh_blocks(mesh=(16, 32, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3", xorder=2,
+                         b0=0.5), (-0.5, 0.0, -0.7, -0.3, -0.25, 0.0, 1)), ["--nscalars=1"]),
     # ... with the isothermal EOS (NHYDRO = 4): hydro blast with walls, Orszag-Tang vortex (hlld_iso) refined
     # off-centre (its potential is sampled per level, as in the reference: the run is the comparison)
     "smr_iso_blast_hydro_walls": ("blast_iso_hydro_hlle", "blast", False, lambda: refined(iso(
@@ -370,7 +377,8 @@ def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
 
 
 @pytest.mark.parametrize("case,ncycle", [("smr_linwave_mhd_centre", 1), ("smr_linwave_mhd_two_levels_rk3", 0),
-                                         ("smr_blast_mhd_walls", 0), ("smr_linwave_mhd_ppm_two_regions", 0)])
+                                         ("smr_blast_mhd_walls", 0), ("smr_linwave_mhd_ppm_two_regions", 0),
+                                         ("smr_kh_mhd_scalar_rk3", 1)])
 def test_refinement_lists_do_not_depend_on_box_order(emul_binary, case, ncycle):
     """The boxes of one refinement list run concurrently on the device.  The harness library runs every
     list forwards and backwards from the same state (ATHK_REFINE_ORDER_CHECK, tests/emul/
