@@ -1123,6 +1123,23 @@ extern "C" int athk_refine_set_block_coords(athk_ctx *c, int lb, const double *x
   return ATHK_OK;
 }
 
+extern "C" int athk_refine_set_peers(athk_ctx *c, int n, athk_ctx *const *peers) {
+  if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_set_peers: call athk_refine_enable first");
+  if (n < 0 || n > ATHK_MAX_PEERS || (n > 0 && !peers)) return fail(ATHK_ERR_ARG, "refine_set_peers: %d contexts (0..%d)", n, ATHK_MAX_PEERS);
+  for (int r = 0; r < ATHK_MAX_PEERS; ++r) c->rf.peers[r] = nullptr;
+  for (int r = 0; r < n; ++r) {
+    athk_ctx *p = peers[r];
+    if (!p || p == c) continue;
+    if (!p->rf.on) return fail(ATHK_ERR_STATE, "refine_set_peers: context %d has no refinement buffers", r);
+    if (p->g.nx1 != c->g.nx1 || p->g.nx2 != c->g.nx2 || p->g.nx3 != c->g.nx3 || p->g.ng != c->g.ng ||
+        p->cfg.mhd != c->cfg.mhd || p->cfg.nscalars != c->cfg.nscalars || p->geo.PG != c->geo.PG)
+      return fail(ATHK_ERR_ARG, "refine_set_peers: context %d has another block shape or variable set", r);
+    c->rf.peers[r] = p;
+  }
+  c->rf.npeers = n;
+  return ATHK_OK;
+}
+
 extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *ops, int nops) {
   if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_set_ops: call athk_refine_enable first");
   cudaSetDevice(c->cfg.device);
@@ -1134,8 +1151,11 @@ extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *op
   long long maxvol = 0;
   for (int n = 0; n < nops; ++n) {   // every box must lie inside the array it addresses
     const athk_box_op &o = ops[n];
+    if (o.peer < 0 || o.peer > ATHK_MAX_PEERS || (o.peer > 0 && !c->rf.peers[o.peer - 1]))
+      return fail(ATHK_ERR_ARG, "refine_set_ops: box %d names GPU %d, which athk_refine_set_peers did not give", n, o.peer - 1);
+    const int src_nb = o.peer ? c->rf.peers[o.peer - 1]->g.nb : g.nb;
     if (o.kind < BOX_RESTRICT || o.kind > BOX_COARSE_BC_FC || o.dst < 0 || o.dst >= g.nb || o.src < 0 ||
-        (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.kind != BOX_COARSE_BC_FC && o.src >= g.nb))
+        (o.kind != BOX_COARSE_BC && o.kind != BOX_EMF_SCALE && o.kind != BOX_COARSE_BC_FC && o.src >= src_nb))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d has kind %d, blocks %d <- %d", n, o.kind, o.dst, o.src);
     if (o.kind < BOX_FC_COPY && o.pad != 0 && (o.pad != 1 || !c->cfg.nscalars))
       return fail(ATHK_ERR_ARG, "refine_set_ops: box %d (kind %d): variable set %d", n, o.kind, o.pad);
@@ -1204,6 +1224,14 @@ extern "C" int athk_refine_run(athk_ctx *c, int phase, int reg) {
                   ns, ns ? c->s[reg] : nullptr, c->r, c->rf.cs, c->rf.cr, {c->sflux[0], c->sflux[1], c->sflux[2]},
                   mhd ? 1 : 0, mhd ? c->b[reg] : nullptr, c->bcc, c->rf.cb, c->rf.cbcc, c->e, c->emfbuf, c->sf};
   if (mhd && !c->b[reg]) return fail(ATHK_ERR_ARG, "refine_run: field register %d not allocated", reg);
+  for (int q = 0; q <= ATHK_MAX_PEERS; ++q) {   // what the boxes read of their source blocks: own arrays, peers' arrays
+    const athk_ctx *p = (q == 0) ? c : c->rf.peers[q - 1];
+    PeerView &v = f.pv[q];
+    if (!p) { v = PeerView{}; continue; }
+    v.u = p->u[reg]; v.s = ns ? p->s[reg] : nullptr; v.b = mhd ? p->b[reg] : nullptr;
+    v.cu = p->rf.cu; v.cs = p->rf.cs; v.cb = p->rf.cb; v.emfbuf = p->emfbuf;
+    for (int d = 0; d < 3; ++d) { v.flx[d] = p->flux[d]; v.sflx[d] = p->sflux[d]; v.dxf[d] = p->geo.dxf[d]; }
+  }
 #ifdef ATHK_EMULATE
   // test harness only (tests/emul/athk_emul_refine_check.h): with ATHK_REFINE_ORDER_CHECK set, the list is also
   // run box by box in reverse order from the same state; any difference means two boxes of one list

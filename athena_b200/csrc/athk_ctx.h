@@ -91,6 +91,8 @@ struct athk_ctx {
     Real *cu = nullptr, *cw = nullptr, *xv = nullptr, *cxv = nullptr;
     Real *cb = nullptr, *cbcc = nullptr;   // MHD: coarse_b_, coarse_bcc_
     Real *cs = nullptr, *cr = nullptr;     // passive scalars: coarse_s_, coarse_r_
+    athk_ctx *peers[ATHK_MAX_PEERS] = {};   // contexts of the other GPUs of this process (athk_refine_set_peers)
+    int npeers = 0;
     BoxOp *ops[ATHK_REFINE_NPHASES] = {};
     int nops[ATHK_REFINE_NPHASES] = {};
     long long maxvol[ATHK_REFINE_NPHASES] = {};

@@ -59,7 +59,19 @@ struct BoxOp {   // == athk_box_op (include/athk.h)
   int lo[3], hi[3];   // destination box, inclusive, (i, j, k)
   int so[3];          // source origin (i, j, k) matching lo
   int pad;
+  int peer;           // 0: block src lives in this context; r + 1: in the context of GPU r (PeerView)
 };
+
+// What a box reads of its SOURCE block.  Entry 0 is the context itself; entry r + 1 the context of GPU r
+// of the same process, whose arrays the kernel reads over NVLink (peer access; athk_refine_set_peers).
+struct PeerView {
+  const Real *u, *s, *b;          // registers the exchange acts on
+  const Real *cu, *cs, *cb;       // coarse buffers
+  const Real *emfbuf;             // packed raw surface EMFs
+  const Real *flx[3], *sflx[3];
+  const Real *dxf[3];             // [nb][PG] cell widths of that context's blocks
+};
+enum { ATHK_MAX_PEERS = 8 };
 
 struct CoarseGrid {
   int cng;                       // cnghost
@@ -100,6 +112,7 @@ struct BoxOpPoint {
   Real *emf;               // [nb][3][sn]   edge EMFs
   const Real *emfbuf;      // [nb][per_block] packed raw surface EMFs (EmfPackPoint)
   EmfSurf sf;
+  PeerView pv[1 + ATHK_MAX_PEERS];
   ATHK_HD void operator()(int opi, idx_t e) const {
     const BoxOp op = ops[opi];
     const int n1 = op.hi[0] - op.lo[0] + 1, n2 = op.hi[1] - op.lo[1] + 1, n3 = op.hi[2] - op.lo[2] + 1;
@@ -116,7 +129,7 @@ struct BoxOpPoint {
       case BOX_FROM_FINER: {
         const idx_t so = cidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = gidx(g, k, j, i);
         const int nv = (op.pad == 1) ? ns : 5;
-        const Real *src = (op.pad == 1) ? cs : cu;
+        const Real *src = (op.pad == 1) ? pv[op.peer].cs : pv[op.peer].cu;
         Real *dst = (op.pad == 1) ? s : u;
         for (int n = 0; n < nv; ++n) dst[((idx_t)op.dst * nv + n) * g.sn + d] = src[((idx_t)op.src * nv + n) * cg.csn + so];
         break;
@@ -124,7 +137,7 @@ struct BoxOpPoint {
       case BOX_FROM_COARSER: {
         const idx_t so = gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di), d = cidx(cg, k, j, i);
         const int nv = (op.pad == 1) ? ns : 5;
-        const Real *src = (op.pad == 1) ? s : u;
+        const Real *src = (op.pad == 1) ? pv[op.peer].s : pv[op.peer].u;
         Real *dst = (op.pad == 1) ? cs : cu;
         for (int n = 0; n < nv; ++n) dst[((idx_t)op.dst * nv + n) * cg.csn + d] = src[((idx_t)op.src * nv + n) * g.sn + so];
         break;
@@ -218,20 +231,19 @@ struct BoxOpPoint {
       }
       case BOX_FC_COPY: {
         Real *bd = b + ((idx_t)op.dst * 3 + op.dir) * g.sn;
-        const Real *bs = b + ((idx_t)op.src * 3 + op.dir) * g.sn;
+        const Real *bs = pv[op.peer].b + ((idx_t)op.src * 3 + op.dir) * g.sn;
         bd[gidx(g, k, j, i)] = bs[gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
         break;
       }
       case BOX_FC_RESTRICT: restrict_face(op.dst, op.dir, k, j, i); break;
       case BOX_FC_FROM_FINER:
         b[((idx_t)op.dst * 3 + op.dir) * g.sn + gidx(g, k, j, i)] =
-            cb[((idx_t)op.src * 3 + op.dir) * cg.cfn + cfidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
+            pv[op.peer].cb[((idx_t)op.src * 3 + op.dir) * cg.cfn + cfidx(cg, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
         break;
-      case BOX_FC_FROM_COARSER: {
+      case BOX_FC_FROM_COARSER:
         cb[((idx_t)op.dst * 3 + op.dir) * cg.cfn + cfidx(cg, k, j, i)] =
-            b[((idx_t)op.src * 3 + op.dir) * g.sn + gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
+            pv[op.peer].b[((idx_t)op.src * 3 + op.dir) * g.sn + gidx(g, op.so[2] + dk, op.so[1] + dj, op.so[0] + di)];
         break;
-      }
       case BOX_FC_PROLONG_SHARED: prolong_shared_face(op.dst, op.dir, k, j, i); break;
       case BOX_FC_PROLONG_INTERNAL: prolong_internal(op.dst, k, j, i); break;
       case BOX_COARSE_BC_FC: {
@@ -386,8 +398,8 @@ struct BoxOpPoint {
     }
   }
   // raw (as computed by ComputeCornerE) surface EMF of a block from its packed surface buffer
-  ATHK_HD Real raw_emf(int blk, int comp, int k, int j, int i) const {
-    const Real *s = emfbuf + (idx_t)blk * sf.per_block();
+  ATHK_HD Real raw_emf(const Real *surf, int blk, int comp, int k, int j, int i) const {
+    const Real *s = surf + (idx_t)blk * sf.per_block();
     const int kk = k - g.ks, jj = j - g.js, ii = i - g.is;
     const bool ib = (i == g.is || i == g.ie + 1), jb = (j == g.js || j == g.je + 1);
     if (comp == 0) {
@@ -405,11 +417,12 @@ struct BoxOpPoint {
   ATHK_HD void emf_from_finer(const BoxOp &op, int k, int j, int i, int dk, int dj, int di) const {
     const int sblk = op.src, c = op.dir;
     const int fi = op.so[0] + 2 * di, fj = op.so[1] + 2 * dj, fk = op.so[2] + 2 * dk;
-    const Real *dx = geo.dxf[c] + sblk * geo.PG;
+    const Real *dx = pv[op.peer].dxf[c] + sblk * geo.PG;
     const int n = (c == 0) ? fi : (c == 1 ? fj : fk);
     const Real el1 = dx[n], el2 = dx[n + 1];
-    const Real v1 = raw_emf(sblk, c, fk, fj, fi);
-    const Real v2 = raw_emf(sblk, c, fk + (c == 2), fj + (c == 1), fi + (c == 0));
+    const Real *surf = pv[op.peer].emfbuf;
+    const Real v1 = raw_emf(surf, sblk, c, fk, fj, fi);
+    const Real v2 = raw_emf(surf, sblk, c, fk + (c == 2), fj + (c == 1), fi + (c == 0));
     emf[((idx_t)op.dst * 3 + c) * g.sn + gidx(g, k, j, i)] += (v1 * el1 + v2 * el2) / (el1 + el2);
   }
   // mesh_refinement.cpp:123-151 (3-D, Cartesian volumes dx1f*dx2f*dx3f, coordinates/cartesian.cpp)
@@ -471,7 +484,8 @@ struct BoxOpPoint {
   // flux_correction_cc.cpp:93-160 (restriction on the fine block) + :222-275 (set on the coarse one)
   ATHK_HD void flux_cell(const BoxOp &op, int k, int j, int i, int dk, int dj, int di) const {
     const int sblk = op.src;
-    const Real *dx1 = geo.dxf[0] + sblk * geo.PG, *dx2 = geo.dxf[1] + sblk * geo.PG, *dx3 = geo.dxf[2] + sblk * geo.PG;
+    const PeerView &sv = pv[op.peer];
+    const Real *dx1 = sv.dxf[0] + sblk * geo.PG, *dx2 = sv.dxf[1] + sblk * geo.PG, *dx3 = sv.dxf[2] + sblk * geo.PG;
     // fine cell of the source block under destination face (di,dj,dk)
     const int fi = op.so[0] + (op.dir == 0 ? 0 : 2 * di), fj = op.so[1] + (op.dir == 1 ? 0 : 2 * dj),
               fk = op.so[2] + (op.dir == 2 ? 0 : 2 * dk);
@@ -491,9 +505,10 @@ struct BoxOpPoint {
     const idx_t so = gidx(g, fk, fj, fi), d = gidx(g, k, j, i);
     const int nv = (op.pad == 1) ? ns : 5;
     Real *fl = (op.pad == 1) ? sflx[op.dir] : flx[op.dir];
+    const Real *fsrc = (op.pad == 1) ? sv.sflx[op.dir] : sv.flx[op.dir];
     // (source and destination are faces of different blocks: no element is both read and written)
     for (int n = 0; n < nv; ++n) {
-      const Real *f = fl + ((idx_t)sblk * nv + n) * g.sn + so;
+      const Real *f = fsrc + ((idx_t)sblk * nv + n) * g.sn + so;
       fl[((idx_t)op.dst * nv + n) * g.sn + d] = (f[0] * a0 + f[o1] * a1 + f[o2] * a2 + f[o3] * a3) / tarea;
     }
   }

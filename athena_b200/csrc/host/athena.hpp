@@ -199,7 +199,8 @@ class EquationOfState {   // eos/eos.hpp:32-181
 
 // bvals/bvals_interfaces.hpp:120-190 (NeighborBlock) -- what the refinement code needs of it
 struct NeighborBlock {
-  int gid, lid, level;
+  int gid, lid, level;   // global id; local id on the owning GPU's context
+  int rank = 0;          // which GPU owns it
   int ox1, ox2, ox3, fi1, fi2;
   int type;   // 0 face, 1 edge, 2 corner
   int fid;    // BoundaryFace of a face neighbour
@@ -311,7 +312,10 @@ class Mesh {   // mesh/mesh.hpp:206-447
   void BuildRefinedTree(ParameterInput *pin);
   void SearchAndSetNeighbors(MeshBlock *pmb);
   void SetupRefinement();
-  void SetupFieldRefinement(std::vector<athk_box_op> *lists);   // face-centred field + EMF correction boxes
+  // face-centred field + EMF correction boxes; lists[rank][list]
+  void SetupFieldRefinement(std::vector<std::vector<std::vector<athk_box_op>>> *lists);
+  void RunRefineList(int list);   // one box list on every GPU, ordered after everything enqueued so far on all of them
+  void SyncAll();
   const ProblemGeneratorEntry *pgen;
   bool fused_stage;
   // user history output (mesh.hpp: EnrollUserHistoryOutput)

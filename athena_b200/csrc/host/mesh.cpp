@@ -246,11 +246,6 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   // Mesh::CalculateLoadBalance (amr_loadbalance.cpp:73-131) for equal costs: contiguous Z-order
   // ranges, the remainder handed out from the last rank backwards
   ngpu = pin->GetOrAddInteger("mesh", "num_gpus", 1);
-  if (multilevel && ngpu != 1) {
-    msg << "### FATAL ERROR in Mesh constructor" << std::endl
-        << "Static mesh refinement runs on one GPU (<mesh> num_gpus = 1)";
-    ATHENA_ERROR(msg);
-  }
   if (ngpu < 1 || ngpu > nbtotal) {
     msg << "### FATAL ERROR in Mesh constructor" << std::endl
         << "<mesh> num_gpus = " << ngpu << " must be between 1 and the number of MeshBlocks (" << nbtotal << ")";
@@ -513,18 +508,20 @@ void Mesh::ExchangeGhosts() {
     // 2133-2160, bvals_refine.cpp:95): restrict the ghost-ghost zones, W(U) on the coarse buffer,
     // prolongate the primitives, U(W) on the new ghost zones (phases 3-6)
     const char *who = "Mesh::ExchangeGhosts";
-    AthkCheck(athk_refine_run(athk, 1, 0), who);
-    AthkCheck(athk_exchange_ghosts(athk, what & ~2, 0), who);
+    RunRefineList(1);
+    if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), who);
+    for (athk_ctx *a : ctx) AthkCheck(athk_exchange_ghosts(a, what & ~2, 0), who);
     // SETB_FLD on a refined mesh (refinement.cpp, SetupFieldRefinement): face, edge, corner neighbours in
     // turn (same level and from finer), then from coarser into the coarse buffer
-    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {8, 9, 10}) AthkCheck(athk_refine_run(athk, phase, 0), who);
-    AthkCheck(athk_refine_run(athk, 2, 0), who);
-    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {11, 64, 65}) AthkCheck(athk_refine_run(athk, phase, 0), who);
-    // (phase 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation;
-    //  12, 13 = shared and internal faces of the prolongated field, before U(W, bcc) of phase 6)
-    for (int phase : {3, 4, 7, 5}) AthkCheck(athk_refine_run(athk, phase, 0), who);
-    if (MAGNETIC_FIELDS_ENABLED) for (int phase : {12, 13}) AthkCheck(athk_refine_run(athk, phase, 0), who);
-    AthkCheck(athk_refine_run(athk, 6, 0), who);
+    if (MAGNETIC_FIELDS_ENABLED) for (int list : {8, 9, 10}) RunRefineList(list);
+    RunRefineList(2);
+    if (MAGNETIC_FIELDS_ENABLED) for (int list : {11, 64, 65}) RunRefineList(list);
+    // (list 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation;
+    //  12, 13 = shared and internal faces of the prolongated field, before U(W, bcc) of list 6)
+    for (int list : {3, 4, 7, 5}) RunRefineList(list);
+    if (MAGNETIC_FIELDS_ENABLED) for (int list : {12, 13}) RunRefineList(list);
+    RunRefineList(6);
+    if (ngpu > 1) SyncAll();   // nobody overwrites what another GPU's boxes still read
     return;
   }
   if (ngpu > 1) for (athk_ctx *a : ctx) AthkCheck(athk_remote_pack_ghosts(a, 0), "Mesh::ExchangeGhosts");

@@ -45,6 +45,26 @@ void Mesh::SetupRemoteLinks() {
     for (int lb = 0; lb < nblist[r]; ++lb) {
       const int n = nslist[r] + lb;
       const LogicalLocation &l = loclist[n];
+      if (multilevel) {
+        // refined mesh: the neighbours SearchAndSetNeighbors found (refinement.cpp); other levels are
+        // served by the box lists and only marked in the table
+        const MeshBlock *pmb = blocks_[n];
+        for (const NeighborBlock &nb : pmb->neighbor) {
+          int &entry = nbr[(std::size_t)lb * 27 + Slot(nb.ox1, nb.ox2, nb.ox3)];
+          if (nb.level != pmb->loc.level) {
+            entry = ATHK_NBR_REFINED;
+          } else if (nb.rank == r) {
+            entry = nb.lid;
+          } else {
+            entry = -(2 + (int)links[r].size());
+            Link k = {lb, nb.ox1, nb.ox2, nb.ox3, n, nb.gid, nb.rank, 0, 0, 0, 0, 0, 0};
+            k.gcount = athk_remote_ghost_count(ctx[r], nb.ox1, nb.ox2, nb.ox3);
+            k.ecount = athk_remote_emf_count(ctx[r], nb.ox1, nb.ox2, nb.ox3);
+            links[r].push_back(k);
+          }
+        }
+        continue;
+      }
       for (int o3 = -1; o3 <= 1; ++o3)
         for (int o2 = -1; o2 <= 1; ++o2)
           for (int o1 = -1; o1 <= 1; ++o1) {
@@ -127,8 +147,13 @@ void Mesh::SetupRemoteLinks() {
     AthkCheck(athk_p2p_alloc(ctx[r], 16 * std::max<long long>((long long)peers[r].size(), 8), &p, nullptr), who);
     fbuf[r] = static_cast<unsigned long long *>(p); p2p_allocs_[3 * r + 2] = p;
   }
-  for (int r = 0; r < ngpu; ++r)
-    for (int p : peers[r]) AthkCheck(athk_p2p_enable_peer(ctx[r], gpu_device0_ + p), who);
+  for (int r = 0; r < ngpu; ++r) {
+    if (multilevel) {   // boxes between levels read any GPU's blocks directly
+      for (int p = 0; p < ngpu; ++p) if (p != r) AthkCheck(athk_p2p_enable_peer(ctx[r], gpu_device0_ + p), who);
+    } else {
+      for (int p : peers[r]) AthkCheck(athk_p2p_enable_peer(ctx[r], gpu_device0_ + p), who);
+    }
+  }
   for (int r = 0; r < ngpu; ++r) {
     const std::vector<Link> &L = links[r];
     const int n = (int)L.size();

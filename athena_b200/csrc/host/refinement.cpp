@@ -222,7 +222,8 @@ void Mesh::SearchAndSetNeighbors(MeshBlock *pmb) {
             myox3 = ((loc.lx3 & 1LL) == 1LL) * 2 - 1;
   auto add = [&](MeshBlockTree *t, int o1, int o2, int o3, int type, int f1, int f2) {
     NeighborBlock nb;
-    nb.gid = t->gid_; nb.lid = t->gid_; nb.level = t->loc_.level;
+    nb.gid = t->gid_; nb.level = t->loc_.level;
+    nb.rank = ranklist[t->gid_]; nb.lid = t->gid_ - nslist[nb.rank];
     nb.ox1 = o1; nb.ox2 = o2; nb.ox3 = o3; nb.fi1 = f1; nb.fi2 = f2; nb.type = type;
     nb.fid = -1;
     if (type == 0) nb.fid = (o1 != 0) ? (o1 + 1) / 2 : ((o2 != 0) ? 2 + (o2 + 1) / 2 : 4 + (o3 + 1) / 2);
@@ -294,6 +295,12 @@ athk_box_op MakeOp(int kind, int dst, int src, int dir, const Box &d, int so1, i
   o.lo[0] = d.si; o.hi[0] = d.ei; o.lo[1] = d.sj; o.hi[1] = d.ej; o.lo[2] = d.sk; o.hi[2] = d.ek;
   o.so[0] = so1; o.so[1] = so2; o.so[2] = so3;
   o.pad = 0;
+  o.peer = 0;
+  return o;
+}
+// a box whose source block is the neighbour nb of a block on GPU `rank`
+athk_box_op FromNeighbor(athk_box_op o, const NeighborBlock &nb, int rank) {
+  o.peer = (nb.rank == rank) ? 0 : nb.rank + 1;
   return o;
 }
 }  // namespace
@@ -326,27 +333,27 @@ static void CoarseCellCentres(const MeshBlock *pmb, const Mesh *pm, int d, std::
 // neighbour table (same level: block index; other level: ATHK_NBR_REFINED) and the boxes per phase.
 void Mesh::SetupRefinement() {
   const char *who = "Mesh::SetupRefinement";
-  AthkCheck(athk_refine_enable(athk), who);
+  for (athk_ctx *a : ctx) AthkCheck(athk_refine_enable(a), who);
+  for (athk_ctx *a : ctx) AthkCheck(athk_refine_set_peers(a, ngpu, ctx.data()), who);
   const int ng = NGHOST, cng = (NGHOST + 1) / 2 + 1;
-  std::vector<int> nbr((std::size_t)nbtotal * 27, -1);
   for (int n = 0; n < nbtotal; ++n) {
     MeshBlock *pmb = blocks_[n];
     SearchAndSetNeighbors(pmb);
     std::vector<Real> cx[3];
     for (int d = 0; d < 3; ++d) CoarseCellCentres(pmb, this, d, &cx[d]);
-    AthkCheck(athk_refine_set_block_coords(athk, pmb->lid, pmb->pcoord->x1v.data(), pmb->pcoord->x2v.data(),
+    AthkCheck(athk_refine_set_block_coords(ctx_of(pmb), pmb->lid, pmb->pcoord->x1v.data(), pmb->pcoord->x2v.data(),
                                            pmb->pcoord->x3v.data(), cx[0].data(), cx[1].data(), cx[2].data()),
               who);
-    for (const NeighborBlock &nb : pmb->neighbor) {
-      int &e = nbr[(std::size_t)n * 27 + (nb.ox3 + 1) * 9 + (nb.ox2 + 1) * 3 + (nb.ox1 + 1)];
-      e = (nb.level == pmb->loc.level) ? nb.lid : ATHK_NBR_REFINED;
-    }
   }
-  AthkCheck(athk_set_neighbors(athk, nbr.data()), who);
+  // neighbour tables (same level: block index or remote link; other level: ATHK_NBR_REFINED), links and
+  // peer-to-peer buffers of the same-level messages between GPUs (multigpu.cpp)
+  SetupRemoteLinks();
 
-  std::vector<athk_box_op> ph[ATHK_REFINE_NPHASES];
+  // lists[rank][list]: the boxes of the MeshBlocks GPU `rank` owns
+  std::vector<std::vector<std::vector<athk_box_op>>> lists(ngpu, std::vector<std::vector<athk_box_op>>(ATHK_REFINE_NPHASES));
   for (int n = 0; n < nbtotal; ++n) {
     MeshBlock *pmb = blocks_[n];
+    std::vector<std::vector<athk_box_op>> &ph = lists[pmb->rank];
     const int t = pmb->lid, L = pmb->loc.level;
     const int is = pmb->is, ie = pmb->ie, js = pmb->js, je = pmb->je, ks = pmb->ks, ke = pmb->ke;
     const int nx1 = pmb->block_size.nx1, nx2 = pmb->block_size.nx2, nx3 = pmb->block_size.nx3;
@@ -412,7 +419,7 @@ void Mesh::SetupRefinement() {
                 << " disagree" << std::endl;
             ATHENA_ERROR(msg);
           }
-          ph[2].push_back(MakeOp(3, t, nb.lid, 0, d, s.si, s.sj, s.sk));
+          ph[2].push_back(FromNeighbor(MakeOp(3, t, nb.lid, 0, d, s.si, s.sj, s.sk), nb, pmb->rank));
         }
         // ---- phases 3-6: ProlongateBoundaries for this coarser neighbour (bvals_refine.cpp:151-260)
         const int nis = std::max(o1 - 1, -1), nie = std::min(o1 + 1, 1), njs = std::max(o2 - 1, -1),
@@ -523,7 +530,7 @@ void Mesh::SetupRefinement() {
               << " disagree" << std::endl;
           ATHENA_ERROR(msg);
         }
-        ph[2].push_back(MakeOp(2, t, nb.lid, 0, d, s.si, s.sj, s.sk));
+        ph[2].push_back(FromNeighbor(MakeOp(2, t, nb.lid, 0, d, s.si, s.sj, s.sk), nb, pmb->rank));
         // ---- phase 0: flux correction from this finer face neighbour (flux_correction_cc.cpp:222-275)
         if (nb.type == 0) {
           const int dir = nb.fid / 2, outer = nb.fid & 1;
@@ -545,12 +552,13 @@ void Mesh::SetupRefinement() {
             if (nb.fi2 == 0) fb.ej -= nx2 / 2; else fb.sj += nx2 / 2;
             so[2] = outer ? ks : ke + 1;
           }
-          ph[0].push_back(MakeOp(7, t, nb.lid, dir, fb, so[0], so[1], so[2]));
+          ph[0].push_back(FromNeighbor(MakeOp(7, t, nb.lid, dir, fb, so[0], so[1], so[2]), nb, pmb->rank));
         }
       }
     }
   }
-  if (NSCALARS > 0) {
+  if (NSCALARS > 0) for (int rk = 0; rk < ngpu; ++rk) {
+    std::vector<std::vector<athk_box_op>> &ph = lists[rk];
     // passive scalars travel with the hydro variables (MeshRefinement::pvars_cc_: (s, coarse_s_), then
     // (r, coarse_r_) for the prolongation, bvals_refine.cpp:560-575): every cell-centred box gets a twin
     // acting on them (pad = 1); W(U) / U(W) boxes handle them in place.  The flux correction of
@@ -564,9 +572,19 @@ void Mesh::SetupRefinement() {
     }
     for (athk_box_op o : ph[0]) { o.pad = 1; ph[66].push_back(o); }
   }
-  if (MAGNETIC_FIELDS_ENABLED) SetupFieldRefinement(ph);
-  for (int p = 0; p < ATHK_REFINE_NPHASES; ++p)
-    AthkCheck(athk_refine_set_ops(athk, p, ph[p].data(), (int)ph[p].size()), who);
+  if (MAGNETIC_FIELDS_ENABLED) SetupFieldRefinement(&lists);
+  for (int rk = 0; rk < ngpu; ++rk)
+    for (int p = 0; p < ATHK_REFINE_NPHASES; ++p)
+      AthkCheck(athk_refine_set_ops(ctx[rk], p, lists[rk][p].data(), (int)lists[rk][p].size()), who);
+}
+
+void Mesh::SyncAll() { for (athk_ctx *a : ctx) AthkCheck(athk_sync(a), "Mesh::SyncAll"); }
+
+// Boxes may read blocks of another GPU: with several GPUs every list starts after all GPUs have
+// finished what was enqueued before it (host-side; refined meshes are not the throughput path)
+void Mesh::RunRefineList(int list) {
+  if (ngpu > 1) SyncAll();
+  for (athk_ctx *a : ctx) AthkCheck(athk_refine_run(a, list, 0), "Mesh::RunRefineList");
 }
 
 //----------------------------------------------------------------------------------------
@@ -582,11 +600,12 @@ void Mesh::SetupRefinement() {
 //   3  (shared) RestrictGhostCellsOnSameLevel, 12 ProlongateSharedField, 13 ProlongateInternalField
 //   14 ClearCoarseFluxBoundary, 16 + slot SetFluxBoundaryFromFiner of the slot-th face / edge neighbour
 //      (accumulation order = neighbour order), 15 AverageFluxBoundary where finer EMFs were summed
-void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
+void Mesh::SetupFieldRefinement(std::vector<std::vector<std::vector<athk_box_op>>> *lists) {
   const char *who = "Mesh::SetupFieldRefinement";
   const int ng = NGHOST, cng = (NGHOST + 1) / 2 + 1;
   for (int n = 0; n < nbtotal; ++n) {
     MeshBlock *pmb = blocks_[n];
+    std::vector<std::vector<athk_box_op>> &ph = (*lists)[pmb->rank];
     const int t = pmb->lid, L = pmb->loc.level;
     const int s_[3] = {pmb->is, pmb->js, pmb->ks}, e_[3] = {pmb->ie, pmb->je, pmb->ke};
     const int nx[3] = {pmb->block_size.nx1, pmb->block_size.nx2, pmb->block_size.nx3};
@@ -638,8 +657,8 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
               else { lo[d] = s_[d] - ng; hi[d] = s_[d] - 1; }
             }
           }
-          ph[list_set].push_back(MakeOp(9, t, nb.lid, c, mk(lo, hi), lo[0] - o[0] * nx[0], lo[1] - o[1] * nx[1],
-                                        lo[2] - o[2] * nx[2]));
+          ph[list_set].push_back(FromNeighbor(MakeOp(9, t, nb.lid, c, mk(lo, hi), lo[0] - o[0] * nx[0],
+                                                     lo[1] - o[1] * nx[1], lo[2] - o[2] * nx[2]), nb, pmb->rank));
         }
       } else if (nb.level > L) {
         // ---- SetBoundaryFromFiner (bvals_fc.cpp:813-976) <- the finer block's restricted box
@@ -665,7 +684,7 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
                 << " disagree" << std::endl;
             ATHENA_ERROR(msg);
           }
-          ph[list_set].push_back(MakeOp(11, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
+          ph[list_set].push_back(FromNeighbor(MakeOp(11, t, nb.lid, c, d, sb.si, sb.sj, sb.sk), nb, pmb->rank));
         }
       } else {
         // ---- list 1: RestrictField for this coarser neighbour (LoadBoundaryBufferToCoarser)
@@ -719,7 +738,7 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
                 << " disagree (component " << c << ")" << std::endl;
             ATHENA_ERROR(msg);
           }
-          ph[nb.type == 0 ? 11 : 63 + nb.type].push_back(MakeOp(12, t, nb.lid, c, d, sb.si, sb.sj, sb.sk));
+          ph[nb.type == 0 ? 11 : 63 + nb.type].push_back(FromNeighbor(MakeOp(12, t, nb.lid, c, d, sb.si, sb.sj, sb.sk), nb, pmb->rank));
         }
         // ---- list 3: RestrictGhostCellsOnSameLevel, field part (bvals_refine.cpp:318-356)
         const int nlo[3] = {std::max(o[0] - 1, -1), std::max(o[1] - 1, -1), std::max(o[2] - 1, -1)};
@@ -842,20 +861,20 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
           const int i = outer ? ie + 1 : is, fi = outer ? is : ie + 1;
           if (nb.fi1 == 0) ju = js + h2 - 1; else jl = js + h2;
           if (nb.fi2 == 0) ku = ks + h3 - 1; else kl = ks + h3;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, kl, ku + 1}, fi, js, ks));
-          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{i, i, jl, ju + 1, kl, ku}, fi, js, ks));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, kl, ku + 1}, fi, js, ks), nb, pmb->rank));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 2, Box{i, i, jl, ju + 1, kl, ku}, fi, js, ks), nb, pmb->rank));
         } else if (dir == 1) {
           const int j = outer ? je + 1 : js, fj = outer ? js : je + 1;
           if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
           if (nb.fi2 == 0) ku = ks + h3 - 1; else kl = ks + h3;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, kl, ku + 1}, is, fj, ks));
-          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{il, iu + 1, j, j, kl, ku}, is, fj, ks));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, kl, ku + 1}, is, fj, ks), nb, pmb->rank));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 2, Box{il, iu + 1, j, j, kl, ku}, is, fj, ks), nb, pmb->rank));
         } else {
           const int k = outer ? ke + 1 : ks, fk = outer ? ks : ke + 1;
           if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
           if (nb.fi2 == 0) ju = js + h2 - 1; else jl = js + h2;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, jl, ju + 1, k, k}, is, js, fk));
-          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{il, iu + 1, jl, ju, k, k}, is, js, fk));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 0, Box{il, iu, jl, ju + 1, k, k}, is, js, fk), nb, pmb->rank));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 1, Box{il, iu + 1, jl, ju, k, k}, is, js, fk), nb, pmb->rank));
         }
       } else {
         int eid;
@@ -868,19 +887,19 @@ void Mesh::SetupFieldRefinement(std::vector<athk_box_op> *ph) {
           const int fi = (eid & 1) ? is : ie + 1, fj = (eid & 2) ? js : je + 1;
           int kl = ks, ku = ke;
           if (nb.fi1 == 0) ku = ks + h3 - 1; else kl = ks + h3;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 2, Box{i, i, j, j, kl, ku}, fi, fj, ks));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 2, Box{i, i, j, j, kl, ku}, fi, fj, ks), nb, pmb->rank));
         } else if (eid < 8) {
           const int i = (eid & 1) ? ie + 1 : is, k = (eid & 2) ? ke + 1 : ks;
           const int fi = (eid & 1) ? is : ie + 1, fk = (eid & 2) ? ks : ke + 1;
           int jl = js, ju = je;
           if (nb.fi1 == 0) ju = js + h2 - 1; else jl = js + h2;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, k, k}, fi, js, fk));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 1, Box{i, i, jl, ju, k, k}, fi, js, fk), nb, pmb->rank));
         } else {
           const int j = (eid & 1) ? je + 1 : js, k = (eid & 2) ? ke + 1 : ks;
           const int fj = (eid & 1) ? js : je + 1, fk = (eid & 2) ? ks : ke + 1;
           int il = is, iu = ie;
           if (nb.fi1 == 0) iu = is + h1 - 1; else il = is + h1;
-          ph[list].push_back(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, k, k}, is, fj, fk));
+          ph[list].push_back(FromNeighbor(MakeOp(16, t, nb.lid, 0, Box{il, iu, j, j, k, k}, is, fj, fk), nb, pmb->rank));
         }
       }
     }

@@ -98,11 +98,15 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
     if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_zero_register(a, 2, 1); });   // ps->s1.ZeroClear() :1628-1630
   }
   all([&](athk_ctx *a) { return athk_calculate_fluxes(a, order, dt, 0); });                    // CALC_HYDFLX
-  if (pm->multilevel)   // SEND/RECV_HYDFLX: fluxes on faces shared with finer blocks (:1757-1795)
-    all([&](athk_ctx *a) { return athk_refine_run(a, 0, 0); });
+  if (pm->multilevel) {   // SEND/RECV_HYDFLX: fluxes on faces shared with finer blocks (:1757-1795)
+    pm->RunRefineList(0);
+    if (pm->ngpu > 1) pm->SyncAll();
+  }
   if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_calculate_scalar_fluxes(a, order); });  // CALC_SCLRFLX :2329-2340
-  if (NSCALARS > 0 && pm->multilevel)   // SEND/RECV_SCLRFLX (:2342-2374)
-    all([&](athk_ctx *a) { return athk_refine_run(a, 66, 0); });
+  if (NSCALARS > 0 && pm->multilevel) {   // SEND/RECV_SCLRFLX (:2342-2374)
+    pm->RunRefineList(66);
+    if (pm->ngpu > 1) pm->SyncAll();
+  }
   if (mhd) {
     all([&](athk_ctx *a) { return athk_compute_corner_e(a); });                                // CALC_FLDFLX
     all([&](athk_ctx *a) { return athk_send_flux_correction(a); });                            // SEND_FLDFLX
@@ -110,9 +114,10 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
     all([&](athk_ctx *a) { return athk_recv_flux_correction(a); });                            // RECV_FLDFLX
     if (pm->multilevel) {   // ... from finer blocks (flux_correction_fc.cpp:1648-1680): clear, add neighbour by
                             // neighbour (lists 16..63, most of them empty), average
-      all([&](athk_ctx *a) { return athk_refine_run(a, 14, 0); });
-      for (int list = 16; list < 16 + 48; ++list) all([&](athk_ctx *a) { return athk_refine_run(a, list, 0); });
-      all([&](athk_ctx *a) { return athk_refine_run(a, 15, 0); });
+      pm->RunRefineList(14);
+      for (int list = 16; list < 16 + 48; ++list) pm->RunRefineList(list);
+      pm->RunRefineList(15);
+      if (pm->ngpu > 1) pm->SyncAll();
     }
   }
   // IntegrateHydro (:1797-1847)

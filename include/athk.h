@@ -277,6 +277,7 @@ typedef struct athk_box_op {
   int lo[3], hi[3];
   int so[3];
   int pad;
+  int peer;   /* 0: block src is a block of this context; r + 1: a block of GPU r's context (athk_refine_set_peers) */
 } athk_box_op;
 enum { ATHK_REFINE_NPHASES = 96 };
 /* allocates coarse_cons_ / coarse_prim_ (hydro/hydro.cpp:60-75): 2 x 5 x (nx/2 + 2 nghost)^3 per block;
@@ -286,6 +287,12 @@ int athk_refine_enable(athk_ctx *ctx);
  * nc? and nx?/2 + 2 nghost */
 int athk_refine_set_block_coords(athk_ctx *ctx, int lb, const double *x1v, const double *x2v, const double *x3v,
                                  const double *cx1v, const double *cx2v, const double *cx3v);
+/* Refined mesh over several GPUs of one process: peers[r] = the context of GPU r (n <= 8; the entry of
+ * the calling context itself is ignored).  A box whose source block lives on another GPU names it with
+ * peer = r + 1 and the kernel reads that context's arrays directly (peer access must be enabled,
+ * athk_p2p_enable_peer); the caller orders the lists across GPUs (athk_sync between dependent lists).
+ * Call before athk_refine_set_ops. */
+int athk_refine_set_peers(athk_ctx *ctx, int n, athk_ctx *const *peers);
 /* the boxes of one phase (0 .. ATHK_REFINE_NPHASES-1; their meaning is the host's), copied to the device */
 int athk_refine_set_ops(athk_ctx *ctx, int phase, const athk_box_op *ops, int nops);
 /* one launch over all boxes of the phase; reg = the conserved (and field) register the boxes act on */

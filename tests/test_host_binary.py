@@ -423,6 +423,14 @@ def test_host_partitions_blocks_over_gpus_emulated(emul_binary, ngpu, fused):
         del CASES["_mg"]
 
 
+@pytest.mark.parametrize("case,ngpu", [("smr_linwave_hydro_centre", 2), ("smr_linwave_mhd_two_levels_rk3", 3),
+                                       ("smr_kh_mhd_scalar_rk3", 4)])
+def test_host_partitions_refined_mesh_over_gpus_emulated(emul_binary, case, ngpu):
+    """Refined meshes over several GPUs: same-level messages through the remote links, boxes between
+    levels (and the field's same-level boxes) read the other context's arrays directly (athk_box_op.peer)."""
+    compare_with_reference(emul_binary, case, host_mesh_params={"num_gpus": ngpu})
+
+
 def _visible_gpus():
     try:
         import torch
@@ -432,7 +440,9 @@ def _visible_gpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,ngpu", [("mhd_blast", 2), ("kh_mhd_rk2_scalar", 2), ("mhd_blast", 8)])
+@pytest.mark.parametrize("case,ngpu", [("mhd_blast", 2), ("kh_mhd_rk2_scalar", 2), ("mhd_blast", 8),
+                                       ("smr_linwave_mhd_two_levels_rk3", 2), ("smr_blast_mhd_walls", 2),
+                                       ("smr_kh_mhd_scalar_rk3", 8)])
 def test_host_binary_on_several_gpus_reproduces_reference_files(cuda_lib, case, ngpu):
     if _visible_gpus() < ngpu:
         pytest.skip("needs %d GPUs" % ngpu)

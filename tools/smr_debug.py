@@ -17,6 +17,11 @@ def cases():
       "lw_2lev": ("linwave_mhd_hlld", "linear_wave", True, lambda: R(
           refrun.linwave_blocks(True, mesh=(24, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3"),
           (0.0, 0.6, 0.0, 0.5, 0.9, 1.5, 2))),
+      "walls": ("blast_mhd_hlld", "blast", True, lambda: R(
+          refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, radius=0.25,
+                              bcs=["reflecting", "outflow", "outflow", "reflecting", "reflecting", "outflow"],
+                              center=(-0.6, 0.5, -0.55)),
+          (-1.0, -0.4, 0.3, 1.0, -1.0, -0.3, 1), (0.5, 1.0, -1.0, -0.6, 0.4, 1.0, 2))),
       "blast": ("blast_mhd_hlld", "blast", True, lambda: R(
           refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.06, rst_dt=0.03, radius=0.25),
           (-0.3, 0.3, -0.3, 0.3, -0.3, 0.3, 1))),
@@ -30,6 +35,8 @@ def main():
         blocks["time"]["nlim"] = int(sys.argv[2])
     wd_ref, _ = refrun.run_reference(cfg, blocks)
     hb = {k: dict(v) for k, v in blocks.items()}
+    if os.environ.get("SMR_NGPU"):
+        hb["mesh"]["num_gpus"] = int(os.environ["SMR_NGPU"])
     wd, r = T.run_host(T.CUDA_BIN if os.environ.get("SMR_GPU") else T.EMUL_BIN, hb, prob, mhd)
     print("host rc", r.returncode)
     if r.returncode != 0:
