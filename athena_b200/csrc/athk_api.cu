@@ -731,7 +731,7 @@ static int weighted_ave(athk_ctx *c, Real *out, const Real *in1, const Real *in2
                         const double w[5]) {
   int mode;
   if (wa_mode(w, &mode))
-    return fail(ATHK_ERR_ARG, "weighted_ave: wght[3], wght[4] != 0 (3S*/ssprk5_4 registers) not implemented");
+    return fail(ATHK_ERR_ARG, "weighted_ave: wght[3], wght[4] != 0 (fourth and fifth input of MeshBlock::WeightedAve) not implemented");
   if (mode == -2) return ATHK_OK;
   const Grid &g = c->g;
   if ((mode == 0 || mode == 2 || mode == 4) && !in2) return fail(ATHK_ERR_ARG, "weighted_ave: in2 register not allocated");
@@ -756,6 +756,12 @@ extern "C" int athk_weighted_ave_cc(athk_ctx *c, int what, int out_reg, int in1_
   Real **regs = (what == 0) ? c->u : c->s;
   const int nvar = (what == 0) ? 5 : c->cfg.nscalars;
   if (what != 0 && what != 1) return fail(ATHK_ERR_ARG, "weighted_ave_cc: what must be 0 (u) or 1 (s)");
+  if (what == 1 && nvar == 0) return fail(ATHK_ERR_ARG, "weighted_ave_cc: the context has no passive scalars");
+  if (!regs[out_reg] && out_reg == 2) {
+    // the third register (u2 / s2 of the 3S* integrators, hydro.cpp:76-80) exists from its first use on
+    int rca = dev_alloc(&regs[2], cc_elems(c, nvar), c->stream);
+    if (rca) return rca;
+  }
   if (!regs[out_reg]) return fail(ATHK_ERR_ARG, "weighted_ave_cc: out register %d not allocated", out_reg);
   return weighted_ave(c, regs[out_reg], regs[in1_reg], regs[in2_reg], nvar, 0, wght);
 }

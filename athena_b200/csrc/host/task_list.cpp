@@ -35,6 +35,37 @@ TimeIntegratorTaskList::TimeIntegratorTaskList(ParameterInput *pin, Mesh *pm) {
     set(0, 1.0, 0.0, 1.0, 0.0, 1.0, 1.0, 0.0);
     set(1, 0.0, 0.25, 0.75, 0.0, 0.25, 0.5, 1.0);
     set(2, 0.0, TWO_3RD, ONE_3RD, 0.0, TWO_3RD, 1.0, 0.5);
+  } else if (integrator == "rk4" || integrator == "ssprk5_4") {
+    // RK4()4[2S] of Ketcheson (2010), time_integrator.cpp:607-735; SSPRK(5,4) of Gottlieb (2009) in
+    // 3S* form, :737-880 (its fourth stage also updates the third register, see DoTaskListOneStage)
+    if (integrator == "rk4") {
+      nstages = 4;
+      cfl_limit = 1.3925;
+      set(0, 1.0, 0.0, 1.0, 0.0, 1.193743905974738, 0.0, 0.0);
+      set(1, 0.217683334308543, 0.121098479554482, 0.721781678111411, 0.0, 0.099279895495783, 0.0, 0.0);
+      set(2, 1.065841341361089, -3.843833699660025, 2.121209265338722, 0.0, 1.131678018054042, 0.0, 0.0);
+      set(3, 0.0, 0.546370891121863, 0.198653035682705, 0.0, 0.310665766509336, 0.0, 0.0);
+    } else {
+      nstages = 5;
+      cfl_limit = 1.508;
+      set(0, 1.0, 0.0, 1.0, 0.0, 0.391752226571890, 0.0, 0.0);
+      set(1, 0.0, 0.555629506348765, 0.444370493651235, 0.0, 0.368410593050371, 0.0, 0.0);
+      set(2, 0.517231671970585, 0.379898148511597, 0.0, 0.620101851488403, 0.251891774271694, 0.0, 0.0);
+      set(3, 0.096059710526147, 0.821920045606868, 0.0, 0.178079954393132, 0.544974750228521, 0.0, 0.0);
+      set(4, 0.0, 0.386708617503268, 1.0, 1.0, 0.226007483236906, 0.0, 0.0);
+      pm->fused_stage = false;   // three registers: the operator sequence
+    }
+    // beginning / end of stage as fractions of dt (:722-735, :866-879)
+    Real temp = 0.0, temp_prev = 0.0;
+    stage_wghts[0].sbeta = 0.0;
+    for (int l = 0; l < nstages - 1; l++) {
+      temp_prev = temp;
+      temp = temp_prev + stage_wghts[l].delta * stage_wghts[l].sbeta;
+      stage_wghts[l].ebeta = stage_wghts[l].gamma_1 * temp_prev + stage_wghts[l].gamma_2 * temp +
+                             stage_wghts[l].gamma_3 * 0.0 + stage_wghts[l].beta;
+      stage_wghts[l + 1].sbeta = stage_wghts[l].ebeta;
+    }
+    stage_wghts[nstages - 1].ebeta = 1.0;
   } else {
     msg << "### FATAL ERROR in TimeIntegratorTaskList constructor" << std::endl
         << "integrator=" << integrator << " not valid time integrator" << std::endl;
@@ -92,10 +123,24 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
     }
     return;
   }
+  const bool ssprk = (integrator == "ssprk5_4");
   if (stage == 1) {   // StartupTaskList (:1608-1619)
+    const Real copy[5] = {0.0, 1.0, 0.0, 0.0, 0.0};   // u2 = u (:1612-1613, :1631-1632)
     all([&](athk_ctx *a) { return athk_zero_register(a, 0, 1); });
-    if (mhd) all([&](athk_ctx *a) { return athk_zero_register(a, 1, 1); });
-    if (NSCALARS > 0) all([&](athk_ctx *a) { return athk_zero_register(a, 2, 1); });   // ps->s1.ZeroClear() :1628-1630
+    if (ssprk) all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 0, 2, 0, 1, copy); });
+    if (mhd) {
+      all([&](athk_ctx *a) { return athk_zero_register(a, 1, 1); });
+      if (ssprk) {   // :1620-1626
+        std::stringstream msg;
+        msg << "### FATAL ERROR in TimeIntegratorTaskList::StartupTaskList\n"
+            << "integrator=" << integrator << " is currently incompatible with MHD." << std::endl;
+        ATHENA_ERROR(msg);
+      }
+    }
+    if (NSCALARS > 0) {
+      all([&](athk_ctx *a) { return athk_zero_register(a, 2, 1); });   // ps->s1.ZeroClear() :1628-1630
+      if (ssprk) all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 2, 0, 1, copy); });
+    }
   }
   all([&](athk_ctx *a) { return athk_calculate_fluxes(a, order, dt, 0); });                    // CALC_HYDFLX
   if (pm->multilevel) {   // SEND/RECV_HYDFLX: fluxes on faces shared with finer blocks (:1757-1795)
@@ -128,12 +173,23 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   if (swap) all([&](athk_ctx *a) { return athk_swap_registers(a, 0, 0, 1); });
   else all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 0, 0, 1, 2, w2); });
   all([&](athk_ctx *a) { return athk_add_flux_divergence(a, sw.beta * dt, 0); });
+  // the penultimate stage of SSPRK(5,4) also forms part of u^(n+1) in the third register (:1828-1841)
+  const Real neg[5] = {-1.0, 0.0, 0.0, 0.0, 0.0};
+  const Real wght_ssp = 0.063692468666290 * dt;
+  if (ssprk && stage == 4) {
+    all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 0, 2, 1, 2, neg); });
+    all([&](athk_ctx *a) { return athk_add_flux_divergence(a, wght_ssp, 2); });
+  }
   all([&](athk_ctx *a) { return athk_add_source_terms(a, sw.beta * dt); });                    // SRC_TERM :1890-1913
   if (NSCALARS > 0) {                                                                          // INT_SCLR :2376-2403
     all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 1, 0, 2, w1); });
     if (swap) all([&](athk_ctx *a) { return athk_swap_registers(a, 2, 0, 1); });
     else all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 0, 1, 2, w2); });
     all([&](athk_ctx *a) { return athk_add_scalar_flux_divergence(a, sw.beta * dt, 0); });
+    if (ssprk && stage == 4) {   // :2405-2416
+      all([&](athk_ctx *a) { return athk_weighted_ave_cc(a, 1, 2, 1, 2, neg); });
+      all([&](athk_ctx *a) { return athk_add_scalar_flux_divergence(a, wght_ssp, 2); });
+    }
   }
   if (mhd) {   // IntegrateField (:1853-1885)
     all([&](athk_ctx *a) { return athk_weighted_ave_fc(a, 1, 0, 2, w1); });

@@ -234,6 +234,13 @@ CASES = {
                           lambda: dict(refrun.linwave_blocks(False, mesh=(32, 16, 16), block=(16, 8, 8),
                                                              tlim=0.1, rst_dt=0.05, integrator="rk3"))),
     "mhd_blast": ("blast_mhd_hlld", "blast", True, blast_blocks),
+    # the reference's other integrators: RK4()4[2S] (four stages, two registers: fused stage) and
+    # SSPRK(5,4) (five stages, third register u2 / s2 and the extra update of its fourth stage)
+    "mhd_linwave_rk4": ("linwave_mhd_hlld", "linear_wave", True,
+                        lambda: dict(refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(16, 8, 8),
+                                                           tlim=0.05, rst_dt=0.02, integrator="rk4"))),
+    "kh_ssprk5_4_2scalars": ("kh_hydro_hllc_s2", "kh", False, lambda: refrun.kh_blocks(
+        mesh=(16, 16, 8), block=(8, 8, 8), tlim=0.04, rst_dt=0.015, integrator="ssprk5_4", xorder=2), ["--nscalars=2"]),
     # BASELINE configs[3] at parity size: KH + RK3 + PPM + HLLC + one passive scalar (row a10)
     "kh_rk3_ppm_scalar": ("kh_hydro_hllc_s1g3", "kh", False,
                           lambda: refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.03,
@@ -374,6 +381,15 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
+
+
+def test_ssprk5_4_refuses_magnetic_fields_like_the_reference(emul_binary):
+    # time_integrator.cpp:1620-1626: a fatal error at the first stage
+    blocks = refrun.linwave_blocks(True, mesh=(16, 8, 8), block=(8, 8, 8), tlim=0.05, integrator="ssprk5_4")
+    wd, r = run_host(emul_binary, blocks, "linear_wave", True)
+    shutil.rmtree(wd, ignore_errors=True)
+    assert r.returncode != 0
+    assert "integrator=ssprk5_4 is currently incompatible with MHD." in r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("case,ncycle", [("smr_linwave_mhd_centre", 1), ("smr_linwave_mhd_two_levels_rk3", 0),
