@@ -196,7 +196,7 @@ CASES = {
         refrun.linwave_blocks(True, mesh=(24, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3"),
         (0.0, 0.6, 0.0, 0.5, 0.9, 1.5, 2))),
     "smr_blast_mhd": ("blast_mhd_hlld", "blast", True, lambda: refined(
-        refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.06, rst_dt=0.03, radius=0.25),
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, radius=0.25),
         (-0.3, 0.3, -0.3, 0.3, -0.3, 0.3, 1))),
     "smr_linwave_mhd_ppm_two_regions": ("linwave_mhd_hlld_g4", "linear_wave", True, lambda: refined(
         refrun.linwave_blocks(True, mesh=(32, 16, 16), block=(8, 8, 8), tlim=0.04, rst_dt=0.02, integrator="rk3",
@@ -394,7 +394,7 @@ def test_ssprk5_4_refuses_magnetic_fields_like_the_reference(emul_binary):
 
 @pytest.mark.parametrize("case,ncycle", [("smr_linwave_mhd_centre", 1), ("smr_linwave_mhd_two_levels_rk3", 0),
                                          ("smr_blast_mhd_walls", 0), ("smr_linwave_mhd_ppm_two_regions", 0),
-                                         ("smr_kh_mhd_scalar_rk3", 1)])
+                                         ("smr_kh_mhd_scalar_rk3", 0)])
 def test_refinement_lists_do_not_depend_on_box_order(emul_binary, case, ncycle):
     """The boxes of one refinement list run concurrently on the device.  The harness library runs every
     list forwards and backwards from the same state (ATHK_REFINE_ORDER_CHECK, tests/emul/
@@ -439,8 +439,7 @@ def test_host_partitions_blocks_over_gpus_emulated(emul_binary, ngpu, fused):
         del CASES["_mg"]
 
 
-@pytest.mark.parametrize("case,ngpu", [("smr_linwave_hydro_centre", 2), ("smr_linwave_mhd_two_levels_rk3", 3),
-                                       ("smr_kh_mhd_scalar_rk3", 4)])
+@pytest.mark.parametrize("case,ngpu", [("smr_linwave_mhd_two_levels_rk3", 3), ("smr_kh_mhd_scalar_rk3", 4)])
 def test_host_partitions_refined_mesh_over_gpus_emulated(emul_binary, case, ngpu):
     """Refined meshes over several GPUs: same-level messages through the remote links, boxes between
     levels (and the field's same-level boxes) read the other context's arrays directly (athk_box_op.peer)."""
