@@ -80,14 +80,24 @@ ATHK_HD void scalar_face_flux_pair(const Grid &g, const Geom &geo, Real sfloor, 
     up_0 = q2 + cpv[n_dir] * d0;
     lo_p = q3 - cmv[n_dir + 1] * dp;
   } else {
+    // ComputeUpwindFlux takes ONE state per face: the cell upwind of it.  Only those cells are
+    // reconstructed (two of the three; cell n alone when both of its faces carry mass out of it);
+    // the states that would be discarded are never formed, the ones used are the same bits
     Real t;
-    ppm_cell(rb[-3 * s], rb[-2 * s], rb[-s], rb[0], rb[s], &up_m, &t);
-    ppm_cell(rb[-2 * s], rb[-s], rb[0], rb[s], rb[2 * s], &up_0, &lo_0);
-    ppm_cell(rb[-s], rb[0], rb[s], rb[2 * s], rb[3 * s], &t, &lo_p);
-    up_m = (up_m > sfloor) ? up_m : sfloor;   // ApplyPassiveScalarFloors (eos_scalars.cpp:161-173)
-    lo_0 = (lo_0 > sfloor) ? lo_0 : sfloor;
-    up_0 = (up_0 > sfloor) ? up_0 : sfloor;
-    lo_p = (lo_p > sfloor) ? lo_p : sfloor;
+    up_m = lo_0 = up_0 = lo_p = 0.0;
+    if (m_lo >= 0.0) {
+      ppm_cell(rb[-3 * s], rb[-2 * s], rb[-s], rb[0], rb[s], &up_m, &t);
+      up_m = (up_m > sfloor) ? up_m : sfloor;   // ApplyPassiveScalarFloors (eos_scalars.cpp:161-173)
+    }
+    if (!(m_lo >= 0.0) || m_hi >= 0.0) {
+      ppm_cell(rb[-2 * s], rb[-s], rb[0], rb[s], rb[2 * s], &up_0, &lo_0);
+      lo_0 = (lo_0 > sfloor) ? lo_0 : sfloor;
+      up_0 = (up_0 > sfloor) ? up_0 : sfloor;
+    }
+    if (!(m_hi >= 0.0)) {
+      ppm_cell(rb[-s], rb[0], rb[s], rb[2 * s], rb[3 * s], &t, &lo_p);
+      lo_p = (lo_p > sfloor) ? lo_p : sfloor;
+    }
   }
   *f_lo = (m_lo >= 0.0) ? m_lo * up_m : m_lo * lo_0;   // ComputeUpwindFlux
   *f_hi = (m_hi >= 0.0) ? m_hi * up_0 : m_hi * lo_p;
