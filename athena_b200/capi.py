@@ -96,6 +96,7 @@ PROTOTYPES = {
     "athk_refine_enable": (C.c_int, [_P]),
     "athk_refine_set_block_coords": (C.c_int, [_P, C.c_int] + [_D] * 6),
     "athk_refine_set_peers": (C.c_int, [_P, C.c_int, _P]),
+    "athk_refine_coarse_transfer": (C.c_int, [_P, C.c_int, C.c_int] + [_D] * 4),
     "athk_refine_set_ops": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "athk_refine_run": (C.c_int, [_P, C.c_int, C.c_int]),
     "athk_enroll_user_boundary": (C.c_int, [_P, C.c_int, _P, _P]),

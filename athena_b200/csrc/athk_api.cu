@@ -1146,6 +1146,38 @@ extern "C" int athk_refine_set_peers(athk_ctx *c, int n, athk_ctx *const *peers)
   return ATHK_OK;
 }
 
+extern "C" int athk_refine_coarse_transfer(athk_ctx *c, int lb, int to_device, double *cprim, double *cb1, double *cb2,
+                                           double *cb3) {
+  if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_coarse_transfer: call athk_refine_enable first");
+  cudaSetDevice(c->cfg.device);
+  if (lb < 0 || lb >= c->g.nb || !cprim) return fail(ATHK_ERR_ARG, "refine_coarse_transfer: block %d or null array", lb);
+  const CoarseGrid &cg = c->rf.cg;
+  CU(cudaStreamSynchronize(c->stream));
+  Real *dw = c->rf.cw + (size_t)lb * 5 * cg.csn;   // dense already: csj = cn1, csk = cn1 * cn2
+  if (to_device) CU(cudaMemcpy(dw, cprim, (size_t)5 * cg.csn * sizeof(Real), cudaMemcpyHostToDevice));
+  else CU(cudaMemcpy(cprim, dw, (size_t)5 * cg.csn * sizeof(Real), cudaMemcpyDeviceToHost));
+  double *hb[3] = {cb1, cb2, cb3};
+  if (c->cfg.mhd && (cb1 || cb2 || cb3)) {
+    // the device keeps every component in one (cn1+1, cn2+1, cn3+1) box: repack on the host
+    std::vector<Real> tmp((size_t)cg.cfn);
+    for (int d = 0; d < 3; ++d) {
+      if (!hb[d]) continue;
+      const int n1 = cg.cn1 + (d == 0), n2 = cg.cn2 + (d == 1), n3 = cg.cn3 + (d == 2);
+      Real *db = c->rf.cb + ((size_t)lb * 3 + d) * cg.cfn;
+      CU(cudaMemcpy(tmp.data(), db, (size_t)cg.cfn * sizeof(Real), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < n3; ++k)
+        for (int j = 0; j < n2; ++j)
+          for (int i = 0; i < n1; ++i) {
+            Real &dev = tmp[(size_t)cfidx(cg, k, j, i)];
+            double &host = hb[d][((size_t)k * n2 + j) * n1 + i];
+            if (to_device) dev = host; else host = dev;
+          }
+      if (to_device) CU(cudaMemcpy(db, tmp.data(), (size_t)cg.cfn * sizeof(Real), cudaMemcpyHostToDevice));
+    }
+  }
+  return ATHK_OK;
+}
+
 extern "C" int athk_refine_set_ops(athk_ctx *c, int phase, const athk_box_op *ops, int nops) {
   if (!c || !c->rf.on) return fail(ATHK_ERR_STATE, "refine_set_ops: call athk_refine_enable first");
   cudaSetDevice(c->cfg.device);

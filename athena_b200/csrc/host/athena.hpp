@@ -164,7 +164,8 @@ class MeshBlock;
 // Coordinates (coordinates/coordinates.hpp, cartesian.cpp): 1-D arrays, uniform Cartesian
 class Coordinates {
  public:
-  Coordinates(MeshBlock *pmb, Mesh *pm);
+  // coarse = the twin MeshRefinement::pcoarsec (coordinates.cpp:33-37, 108-160): nx/2 cells, same NGHOST
+  Coordinates(MeshBlock *pmb, Mesh *pm, bool coarse = false);
   AthenaArray<Real> x1f, x2f, x3f, x1v, x2v, x3v, dx1f, dx2f, dx3f, dx1v, dx2v, dx3v;
   Real GetCellVolume(int k, int j, int i) const { return dx1f(i) * dx2f(j) * dx3f(k); }
 };
@@ -248,6 +249,10 @@ class MeshBlock {   // mesh/mesh.hpp:75-200
   // static mesh refinement (bvals_base.hpp): neighbours in SearchAndSetNeighbors' order, their levels
   std::vector<NeighborBlock> neighbor;
   int nblevel[3][3][3];
+  // what a user-enrolled boundary function sees of the coarse buffer (built on first use)
+  Coordinates *pcoarsec = nullptr;
+  AthenaArray<Real> coarse_prim_;
+  FaceField coarse_b_;
   BoundaryFlag block_bcs[6] = {BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block,
                                BoundaryFlag::block, BoundaryFlag::block, BoundaryFlag::block};
 };
@@ -314,6 +319,12 @@ class Mesh {   // mesh/mesh.hpp:206-447
   void SetupRefinement();
   // face-centred field + EMF correction boxes; lists[rank][list]
   void SetupFieldRefinement(std::vector<std::vector<std::vector<athk_box_op>>> *lists);
+  // user-enrolled boundary functions on the coarse buffer (bvals_refine.cpp:445-530): which function, on
+  // which block, over which coarse index range (DispatchBoundaryFunctions' arguments, ngh = 1)
+  struct CoarseUserBC { int gid, face, il, iu, jl, ju, kl, ku; };
+  std::vector<CoarseUserBC> coarse_user_bcs_;
+  Real bc_time_ = 0.0, bc_dt_ = 0.0;   // as handed to athk_set_boundary_time
+  void ApplyUserBoundariesOnCoarseLevel();
   void RunRefineList(int list);   // one box list on every GPU, ordered after everything enqueued so far on all of them
   void SyncAll();
   const ProblemGeneratorEntry *pgen;

@@ -53,15 +53,16 @@ static std::uint64_t MortonKey(const LogicalLocation &l) {
 }
 
 //----------------------------------------------------------------------------------------
-Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm) {
+Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm, bool coarse) {
   const int ng = NGHOST;
+  const int cf = coarse ? 2 : 1;   // coordinates.cpp:108-160: a coarse cell spans two fine ones
   const RegionSize &ms = pm->mesh_size;
   const RegionSize &bs = pmb->block_size;
   struct Dir { AthenaArray<Real> *xf, *xv, *dxf, *dxv; int nx, nc; std::int64_t lx; Real bmin, bmax, mmin, mmax; int mnx; };
   Dir dirs[3] = {
-      {&x1f, &x1v, &dx1f, &dx1v, bs.nx1, pmb->ncells1, pmb->loc.lx1, bs.x1min, bs.x1max, ms.x1min, ms.x1max, ms.nx1},
-      {&x2f, &x2v, &dx2f, &dx2v, bs.nx2, pmb->ncells2, pmb->loc.lx2, bs.x2min, bs.x2max, ms.x2min, ms.x2max, ms.nx2},
-      {&x3f, &x3v, &dx3f, &dx3v, bs.nx3, pmb->ncells3, pmb->loc.lx3, bs.x3min, bs.x3max, ms.x3min, ms.x3max, ms.nx3}};
+      {&x1f, &x1v, &dx1f, &dx1v, bs.nx1 / cf, bs.nx1 / cf + 2 * ng, pmb->loc.lx1, bs.x1min, bs.x1max, ms.x1min, ms.x1max, ms.nx1},
+      {&x2f, &x2v, &dx2f, &dx2v, bs.nx2 / cf, bs.nx2 / cf + 2 * ng, pmb->loc.lx2, bs.x2min, bs.x2max, ms.x2min, ms.x2max, ms.nx2},
+      {&x3f, &x3v, &dx3f, &dx3v, bs.nx3 / cf, bs.nx3 / cf + 2 * ng, pmb->loc.lx3, bs.x3min, bs.x3max, ms.x3min, ms.x3max, ms.nx3}};
   for (Dir &d : dirs) {
     d.xf->NewAthenaArray(d.nc + 1);
     d.xv->NewAthenaArray(d.nc);
@@ -72,7 +73,7 @@ Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm) {
     // coordinates.cpp:143-152 (uniform mesh generator branch)
     const Real dx = (d.bmax - d.bmin) / (iu - il + 1);
     for (int i = il - ng; i <= iu + ng + 1; ++i) {
-      const std::int64_t noffset = static_cast<std::int64_t>(i - il + d.lx * d.nx);
+      const std::int64_t noffset = static_cast<std::int64_t>((i - il) * cf + d.lx * d.nx * cf);
       const Real rx = ComputeMeshGeneratorX(noffset, nrootmesh);
       (*d.xf)(i) = UniformMeshGenerator(rx, d.mmin, d.mmax);
     }
@@ -133,6 +134,7 @@ MeshBlock::MeshBlock(int igid, int ilid, LogicalLocation iloc, RegionSize bs, Me
   peos = new EquationOfState(pin);
 }
 MeshBlock::~MeshBlock() {
+  delete pcoarsec;
   delete pcoord; delete phydro; delete pfield; delete pscalars; delete peos;
 }
 void MeshBlock::ProblemGenerator(ParameterInput *pin) {
@@ -190,13 +192,6 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
           << "Mesh refinement needs an even number of ghost zones (nghost=" << NGHOST << ")";
       ATHENA_ERROR(msg);
     }
-    for (int n = 0; n < 6; ++n)
-      if (mesh_bcs[n] == BoundaryFlag::user) {
-        msg << "### FATAL ERROR in Mesh constructor" << std::endl
-            << "Static mesh refinement on the B200 path takes periodic, reflecting and outflow mesh boundaries "
-            << "(user-enrolled functions are not applied to the coarse buffer)";
-        ATHENA_ERROR(msg);
-      }
   }
   for (int n = 0; n < 6; ++n) {
     if (mesh_bcs[n] != BoundaryFlag::periodic && mesh_bcs[n] != BoundaryFlag::reflect &&
@@ -518,7 +513,9 @@ void Mesh::ExchangeGhosts() {
     if (MAGNETIC_FIELDS_ENABLED) for (int list : {11, 64, 65}) RunRefineList(list);
     // (list 7 = the physical boundary functions on the coarse primitives, between W(U) and prolongation;
     //  12, 13 = shared and internal faces of the prolongated field, before U(W, bcc) of list 6)
-    for (int list : {3, 4, 7, 5}) RunRefineList(list);
+    for (int list : {3, 4, 7}) RunRefineList(list);
+    ApplyUserBoundariesOnCoarseLevel();   // (host functions, like the fine level's: Mesh::EnrollUserBoundaryFunction)
+    RunRefineList(5);
     if (MAGNETIC_FIELDS_ENABLED) for (int list : {12, 13}) RunRefineList(list);
     RunRefineList(6);
     if (ngpu > 1) SyncAll();   // nobody overwrites what another GPU's boxes still read
@@ -548,6 +545,7 @@ void Mesh::Initialize(ParameterInput *pin) {
   ExchangeGhosts();
   for (athk_ctx *a : ctx) AthkCheck(athk_cons2prim(a, 0), "Mesh::Initialize");
   for (athk_ctx *a : ctx) AthkCheck(athk_set_boundary_time(a, time, 0.0), "Mesh::Initialize");
+  bc_time_ = time; bc_dt_ = 0.0;
   for (athk_ctx *a : ctx) AthkCheck(athk_apply_physical_boundaries(a), "Mesh::Initialize");   // mesh.cpp:1886-1891
   NewTimeStep();
 }

@@ -17,6 +17,7 @@
 //                                       CountFineEdges bvals/fc/bvals_fc.cpp:1129-1197
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "athena.hpp"
 
@@ -470,6 +471,14 @@ void Mesh::SetupRefinement() {
             if (off[d] != 0) continue;
             for (int side = 0; side < 2; ++side) {
               const BoundaryFlag bf = pmb->block_bcs[2 * d + side];
+              if (bf == BoundaryFlag::user) {   // DispatchBoundaryFunctions(..., cis, cie, sj, ej, sk, ek, 1, ...)
+                CoarseUserBC ub = {n, 2 * d + side, p.si, p.ei, p.sj, p.ej, p.sk, p.ek};
+                if (d == 0) { ub.il = clo[0]; ub.iu = chi[0]; }
+                if (d == 1) { ub.jl = clo[1]; ub.ju = chi[1]; }
+                if (d == 2) { ub.kl = clo[2]; ub.ku = chi[2]; }
+                coarse_user_bcs_.push_back(ub);
+                continue;
+              }
               if (bf != BoundaryFlag::reflect && bf != BoundaryFlag::outflow) continue;
               Box bb = p;
               int so[3] = {0, 0, 0};
@@ -576,6 +585,42 @@ void Mesh::SetupRefinement() {
   for (int rk = 0; rk < ngpu; ++rk)
     for (int p = 0; p < ATHK_REFINE_NPHASES; ++p)
       AthkCheck(athk_refine_set_ops(ctx[rk], p, lists[rk][p].data(), (int)lists[rk][p].size()), who);
+}
+
+// The user-enrolled boundary functions on coarse_prim_ / coarse_b_ with the coarse coordinates, one ghost
+// layer (bvals_refine.cpp:445-530 -> bvals.cpp:673-814).  The functions run on the host, as on the fine
+// level: the block's coarse arrays come to the host mirrors, every enrolled face touched by one of the
+// block's coarser neighbours is served in the reference's order, and the arrays go back.
+void Mesh::ApplyUserBoundariesOnCoarseLevel() {
+  const char *who = "Mesh::ApplyUserBoundariesOnCoarseLevel";
+  std::size_t q = 0;
+  while (q < coarse_user_bcs_.size()) {
+    const int gid = coarse_user_bcs_[q].gid;
+    MeshBlock *pmb = blocks_[gid];
+    athk_ctx *a = ctx_of(pmb);
+    const int ng = NGHOST;
+    const int cn1 = pmb->block_size.nx1 / 2 + 2 * ng, cn2 = pmb->block_size.nx2 / 2 + 2 * ng, cn3 = pmb->block_size.nx3 / 2 + 2 * ng;
+    if (pmb->pcoarsec == nullptr) {
+      pmb->pcoarsec = new Coordinates(pmb, this, true);
+      pmb->coarse_prim_.NewAthenaArray(5, cn3, cn2, cn1);   // (the device keeps five slots for every EOS)
+      if (MAGNETIC_FIELDS_ENABLED) {
+        pmb->coarse_b_.x1f.NewAthenaArray(cn3, cn2, cn1 + 1);
+        pmb->coarse_b_.x2f.NewAthenaArray(cn3, cn2 + 1, cn1);
+        pmb->coarse_b_.x3f.NewAthenaArray(cn3 + 1, cn2, cn1);
+      }
+    }
+    double *b1 = MAGNETIC_FIELDS_ENABLED ? pmb->coarse_b_.x1f.data() : nullptr;
+    double *b2 = MAGNETIC_FIELDS_ENABLED ? pmb->coarse_b_.x2f.data() : nullptr;
+    double *b3 = MAGNETIC_FIELDS_ENABLED ? pmb->coarse_b_.x3f.data() : nullptr;
+    AthkCheck(athk_refine_coarse_transfer(a, pmb->lid, 0, pmb->coarse_prim_.data(), b1, b2, b3), who);
+    for (; q < coarse_user_bcs_.size() && coarse_user_bcs_[q].gid == gid; ++q) {
+      const CoarseUserBC &t = coarse_user_bcs_[q];
+      if (BoundaryFunction_[t.face] == nullptr) continue;
+      BoundaryFunction_[t.face](pmb, pmb->pcoarsec, pmb->coarse_prim_, pmb->coarse_b_, bc_time_, bc_dt_, t.il, t.iu, t.jl,
+                                t.ju, t.kl, t.ku, 1);
+    }
+    AthkCheck(athk_refine_coarse_transfer(a, pmb->lid, 1, pmb->coarse_prim_.data(), b1, b2, b3), who);
+  }
 }
 
 void Mesh::SyncAll() { for (athk_ctx *a : ctx) AthkCheck(athk_sync(a), "Mesh::SyncAll"); }

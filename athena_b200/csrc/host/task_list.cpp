@@ -111,6 +111,8 @@ void TimeIntegratorTaskList::DoTaskListOneStage(Mesh *pm, int stage) {
   auto all = [&](auto &&fn) { for (athk_ctx *a : pm->ctx) AthkCheck(fn(a), who); };
   // what PhysicalBoundary hands to user-enrolled boundary functions (:2284-2287)
   all([&](athk_ctx *a) { return athk_set_boundary_time(a, pm->time + sw.ebeta * dt, sw.beta * dt); });
+  pm->bc_time_ = pm->time + sw.ebeta * dt;   // ... and Prolongation to ProlongateBoundaries (:2150-2153)
+  pm->bc_dt_ = sw.beta * dt;
   // ... and AddSourceTerms to user source functions: the time at the beginning of the stage (:1901-1903)
   all([&](athk_ctx *a) { return athk_set_source_time(a, pm->time + sw.sbeta * dt); });
   if (pm->fused_stage) {

@@ -293,6 +293,13 @@ int athk_refine_set_block_coords(athk_ctx *ctx, int lb, const double *x1v, const
  * athk_p2p_enable_peer); the caller orders the lists across GPUs (athk_sync between dependent lists).
  * Call before athk_refine_set_ops. */
 int athk_refine_set_peers(athk_ctx *ctx, int n, athk_ctx *const *peers);
+/* The coarse primitives and coarse field of local block lb in the reference's dense layouts
+ * (coarse_prim_ [5][cn3][cn2][cn1], coarse_b_.x1f [cn3][cn2][cn1+1], .x2f [cn3][cn2+1][cn1], .x3f
+ * [cn3+1][cn2][cn1] with cn = nx/2 + 2 nghost; the field pointers may be NULL), to the host
+ * (to_device = 0) or back: a user-enrolled boundary function acts on them between the coarse W(U) and
+ * the prolongation (bvals_refine.cpp:445-530).  Synchronous. */
+int athk_refine_coarse_transfer(athk_ctx *ctx, int lb, int to_device, double *coarse_prim, double *cb1, double *cb2,
+                                double *cb3);
 /* the boxes of one phase (0 .. ATHK_REFINE_NPHASES-1; their meaning is the host's), copied to the device */
 int athk_refine_set_ops(athk_ctx *ctx, int phase, const athk_box_op *ops, int nops);
 /* one launch over all boxes of the phase; reg = the conserved (and field) register the boxes act on */

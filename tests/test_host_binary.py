@@ -208,6 +208,11 @@ CASES = {
                             bcs=["reflecting", "outflow", "outflow", "reflecting", "reflecting", "outflow"],
                             center=(-0.6, 0.5, -0.55)),
         (-1.0, -0.4, 0.3, 1.0, -1.0, -0.3, 1), (0.5, 1.0, -1.0, -0.6, 0.4, 1.0, 2))),
+    # ... with a user-enrolled boundary function (the jet's inlet) acting on the coarse buffer too
+    "smr_jet_user_bc_hydro": ("jet_hydro_hllc", "jet", False, lambda: refined(
+        jet_blocks(False), (0.0, 1.0, 0.0, 2.0, -1.2, 0.5, 1))),
+    "smr_jet_user_bc_mhd_rk3": ("jet_mhd_hlld", "jet", True, lambda: refined(
+        jet_blocks(True, "rk3"), (0.0, 1.0, -2.0, 0.0, -0.5, 1.2, 1))),
     # ... with passive scalars (restriction of s, prolongation of r = s / rho, flux correction of s_flux)
     "smr_kh_hydro_2scalars": ("kh_hydro_hllc_s2", "kh", False, lambda: refined(
         refrun.kh_blocks(mesh=(16, 32, 16), block=(8, 8, 8), tlim=0.05, rst_dt=0.025, integrator="vl2", xorder=2,
