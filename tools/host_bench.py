@@ -64,8 +64,9 @@ def main():
     ap.add_argument("--cycles", type=int, default=30)
     ap.add_argument("--per-gpu", type=int, default=256)
     ap.add_argument("--block", type=int, default=64)
-    ap.add_argument("--config", default="blast", choices=["blast", "config0", "config1", "config3"],
-                    help="blast: the bench workload; config0/1/3: BASELINE.json configs[0], [1], [3] shapes")
+    ap.add_argument("--config", default="blast", choices=["blast", "config0", "config1", "config3", "smr"],
+                    help="blast: the bench workload; config0/1/3: BASELINE.json configs[0], [1], [3] shapes; "
+                         "smr: the MHD blast on a statically refined mesh (operator sequence + box lists)")
     a = ap.parse_args()
     if a.config == "config0":   # 3-D hydro linear wave 64^3, VL2+PLM+HLLC, single MeshBlock, tlim=1
         b = base("LinWave", "vl2", 2, 1.0, -1)
@@ -89,6 +90,17 @@ def main():
         b["problem"] = {"iprob": 4, "amp": 0.01, "vflow": 1.0, "vboost": 0.0, "drho_rho0": 0.0}
         return run_binary(b, ["--prob=kh", "--nghost=3", "--nscalars=1"], "BASELINE configs[3] shape: KH hydro %d^3, "
                           "RK3+PPM+HLLC + 1 passive scalar, %d^3 MeshBlocks" % (n, a.block), n ** 3, 1)
+    if a.config == "smr":   # MHD blast, 128^3 root mesh in 32^3 MeshBlocks, the central 2x2x2 root blocks refined once
+        b = base("Blast", "vl2", 2, 10.0, a.cycles)
+        b.update(mesh_block((128, 128, 128), (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), (32, 32, 32), num_gpus=a.gpus,
+                            refinement="static"))
+        b["refinement1"] = {"x1min": -0.4, "x1max": 0.4, "x2min": -0.4, "x2max": 0.4, "x3min": -0.4, "x3max": 0.4, "level": 1}
+        b["hydro"] = {"gamma": 1.666666666667, "iso_sound_speed": 0.4082482905}
+        b["problem"] = {"pamb": 0.1, "prat": 100.0, "radius": 0.1, "damb": 1.0, "drat": 1.0, "ramp": 0.0, "b0": 1.0,
+                        "angle": 30}
+        nblocks = 64 - 8 + 64
+        return run_binary(b, ["--prob=blast", "-b"], "MHD blast on a refined mesh: 128^3 root, 32^3 MeshBlocks, centre "
+                          "refined once (%d blocks), VL2+PLM+HLLD+CT" % nblocks, nblocks * 32 ** 3, a.gpus)
     # the bench workload: MHD blast, 256^3 zones per GPU in 64^3 MeshBlocks, weak-scaled
     f = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[a.gpus]
     mesh = tuple(a.per_gpu * x for x in f)
