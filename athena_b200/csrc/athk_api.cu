@@ -78,8 +78,14 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     return fail(ATHK_ERR_ARG, "athk_create: unknown eos %d", cfg->eos);
   if (cfg->eos == ATHK_EOS_ISOTHERMAL) {
     if (!(cfg->iso_sound_speed > 0.0)) return fail(ATHK_ERR_ARG, "athk_create: isothermal EOS needs iso_sound_speed > 0");
-    if (cfg->rsolver != (cfg->mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE))
-      return fail(ATHK_ERR_ARG, "athk_create: the isothermal EOS is implemented with rsolver HLLE (hydro) and HLLD (mhd)");
+    // hlle.cpp / hlld_iso.cpp have their own kernels; LLF, HLLE (MHD) and Roe (hydro) branch on the EOS
+    // inside the adiabatic kernels' flux functions (NON_BAROTROPIC_EOS == 0 branches of llf.cpp, llf_mhd.cpp,
+    // hlle_mhd.cpp, roe.cpp)
+    const bool ok = cfg->mhd ? (cfg->rsolver == ATHK_RS_HLLD || cfg->rsolver == ATHK_RS_HLLE || cfg->rsolver == ATHK_RS_LLF)
+                             : (cfg->rsolver == ATHK_RS_HLLE || cfg->rsolver == ATHK_RS_LLF || cfg->rsolver == ATHK_RS_ROE);
+    if (!ok)
+      return fail(ATHK_ERR_ARG, "athk_create: the isothermal EOS is implemented with rsolver HLLE, LLF, Roe (hydro) and "
+                                "HLLD, HLLE, LLF (mhd)");
     if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for the isothermal EOS");
   }
   if (cfg->arith == ATHK_ARITH_FAST && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_HLLD)
@@ -658,7 +664,7 @@ extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int
   int rc = check_order(c, order, "calculate_fluxes");
   if (rc) return rc;
   const bool mhd = c->cfg.mhd != 0;
-  if (c->eos.iso)
+  if (c->eos.iso && c->cfg.rsolver == (mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE))
     return mhd ? athk_flux3_rs<RS_HLLD_ISO, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLE_ISO, false>(c, order, dt_mesh, breg);
   switch (c->cfg.rsolver) {
     case ATHK_RS_ROE: return mhd ? athk_flux3_rs<RS_ROE, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_ROE, false>(c, order, dt_mesh, breg);
@@ -1554,7 +1560,7 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       for (int d = 0; d < 3; ++d) a.mf[d] = c->sflux[d];
       a.mf_bstride = (idx_t)ns * g.sn;
     }
-    if (c->eos.iso) {
+    if (c->eos.iso && c->cfg.rsolver == (mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE)) {
       rc = mhd ? athk_sweeps_rs<RS_HLLD_ISO, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLE_ISO, false, 0>(c, order, a);
     } else
     switch (c->cfg.rsolver) {

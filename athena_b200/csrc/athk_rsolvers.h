@@ -76,12 +76,19 @@ ATHK_HD void hydro_lr_fluxes(const EosParams &eos, const Real wl[5], const Real 
   fr[IVY] = mxr * wr[IVY];
   fl[IVZ] = mxl * wl[IVZ];
   fr[IVZ] = mxr * wr[IVZ];
-  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
-  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
-  fl[IVX] += wl[IPR];
-  fr[IVX] += wr[IPR];
-  fl[IEN] = (el + wl[IPR]) * wl[IVX];
-  fr[IEN] = (er + wr[IPR]) * wr[IVX];
+  Real el = 0.0, er = 0.0;
+  if (eos.iso) {   // NON_BAROTROPIC_EOS == 0 (llf.cpp:82-85, roe.cpp:112-115): no energy equation
+    fl[IVX] += (eos.iso_cs * eos.iso_cs) * wl[IDN];
+    fr[IVX] += (eos.iso_cs * eos.iso_cs) * wr[IDN];
+    fl[IEN] = fr[IEN] = 0.0;
+  } else {
+    el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
+    er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
+    fl[IVX] += wl[IPR];
+    fr[IVX] += wr[IPR];
+    fl[IEN] = (el + wl[IPR]) * wl[IVX];
+    fr[IEN] = (er + wr[IPR]) * wr[IVX];
+  }
   du[IDN] = wr[IDN] - wl[IDN];
   du[IVX] = wr[IDN] * wr[IVX] - wl[IDN] * wl[IVX];
   du[IVY] = wr[IDN] * wr[IVY] - wl[IDN] * wl[IVY];
@@ -93,15 +100,77 @@ ATHK_HD void hydro_lr_fluxes(const EosParams &eos, const Real wl[5], const Real 
 
 ATHK_HD void llf_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
   Real fl[5], fr[5], du[5], el, er;
-  Real cl = sound_speed(eos, wl[IDN], wl[IPR]);
-  Real cr = sound_speed(eos, wr[IDN], wr[IPR]);
+  Real cl = eos.iso ? eos.iso_cs : sound_speed(eos, wl[IDN], wl[IPR]);   // EquationOfState::SoundSpeed
+  Real cr = eos.iso ? eos.iso_cs : sound_speed(eos, wr[IDN], wr[IPR]);
   Real a = 0.5 * max_std((fabs(wl[IVX]) + cl), (fabs(wr[IVX]) + cr));
   hydro_lr_fluxes(eos, wl, wr, fl, fr, du, &el, &er);
 #pragma unroll
   for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - a * du[n];
 }
 
+// Roe for isothermal hydrodynamics: roe.cpp:43-175 with NON_BAROTROPIC_EOS == 0, RoeFlux :296-345
+// (four waves; NWAVE - 1 = 3 is the last eigenvalue)
+ATHK_HD void roe_iso_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real iso_cs = eos.iso_cs;
+  Real fl[5], fr[5], du[5], ev[4], el, er;
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  const Real v1 = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  const Real v2 = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  const Real v3 = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  hydro_lr_fluxes(eos, wl, wr, fl, fr, du, &el, &er);
+#pragma unroll
+  for (int n = 0; n < 4; ++n) f[n] = 0.5 * (fl[n] + fr[n]);
+  f[IEN] = 0.0;
+  int llf_flag = 0;
+  ev[0] = v1 - iso_cs;
+  ev[1] = v1;
+  ev[2] = v1;
+  ev[3] = v1 + iso_cs;
+  Real a[4];
+  a[0] = du[0] * (0.5 + 0.5 * v1 / iso_cs);
+  a[0] -= du[1] * 0.5 / iso_cs;
+  a[1] = du[0] * (-v2);
+  a[1] += du[2];
+  a[2] = du[0] * (-v3);
+  a[2] += du[3];
+  a[3] = du[0] * (0.5 - 0.5 * v1 / iso_cs);
+  a[3] += du[1] * 0.5 / iso_cs;
+  Real coeff[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) coeff[n] = -0.5 * fabs(ev[n]) * a[n];
+  Real dens = wl[IDN] + a[0];
+  if (dens < 0.0) llf_flag = 1;
+  dens += a[3];
+  if (dens < 0.0) llf_flag = 1;
+  f[0] += coeff[0];
+  f[0] += coeff[3];
+  f[1] += coeff[0] * (v1 - iso_cs);
+  f[1] += coeff[3] * (v1 + iso_cs);
+  f[2] += coeff[0] * v2;
+  f[2] += coeff[1];
+  f[2] += coeff[3] * v2;
+  f[3] += coeff[0] * v3;
+  f[3] += coeff[2];
+  f[3] += coeff[3] * v3;
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) f[n] = fl[n];
+  }
+  if (ev[3] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) f[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    Real am = 0.5 * max_std((fabs(wl[IVX]) + iso_cs), (fabs(wr[IVX]) + iso_cs));
+#pragma unroll
+    for (int n = 0; n < 4; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - am * du[n];
+  }
+}
+
 ATHK_HD void roe_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  if (eos.iso) { roe_iso_hydro_flux(eos, wl, wr, f); return; }
   const Real gm1 = eos.gm1;
   Real wroe[5], fl[5], fr[5], du[5], ev[5], el, er;
   Real sqrtdl = sqrt(wl[IDN]);
@@ -217,14 +286,21 @@ ATHK_HD void mhd_lr_fluxes(const EosParams &eos, const Real wl[7], const Real wr
   fr[IVY] = mxr * wr[IVY] - bxi * wr[IBY];
   fl[IVZ] = mxl * wl[IVZ] - bxi * wl[IBZ];
   fr[IVZ] = mxr * wr[IVZ] - bxi * wr[IBZ];
-  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
-  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
-  fl[IVX] += wl[IPR];
-  fr[IVX] += wr[IPR];
-  fl[IEN] = (el + wl[IPR] + pbl - bxi * bxi) * wl[IVX];
-  fr[IEN] = (er + wr[IPR] + pbr - bxi * bxi) * wr[IVX];
-  fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
-  fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  Real el = 0.0, er = 0.0;
+  if (eos.iso) {   // llf_mhd.cpp:106-109, roe_mhd.cpp:132-135
+    fl[IVX] += (eos.iso_cs * eos.iso_cs) * wl[IDN];
+    fr[IVX] += (eos.iso_cs * eos.iso_cs) * wr[IDN];
+    fl[IEN] = fr[IEN] = 0.0;
+  } else {
+    el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
+    er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
+    fl[IVX] += wl[IPR];
+    fr[IVX] += wr[IPR];
+    fl[IEN] = (el + wl[IPR] + pbl - bxi * bxi) * wl[IVX];
+    fr[IEN] = (er + wr[IPR] + pbr - bxi * bxi) * wr[IVX];
+    fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
+    fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  }
   fl[IBY] = wl[IBY] * wl[IVX] - bxi * wl[IVY];
   fr[IBY] = wr[IBY] * wr[IVX] - bxi * wr[IVY];
   fl[IBZ] = wl[IBZ] * wl[IVX] - bxi * wl[IVZ];
@@ -245,8 +321,8 @@ ATHK_HD void mhd_lr_fluxes(const EosParams &eos, const Real wl[7], const Real wr
 ATHK_HD void llf_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
                           Real f[7]) {
   Real fl[7], fr[7], du[7], el, er, pbl, pbr;
-  Real cfl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
-  Real cfr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  Real cfl = eos.iso ? fast_speed_iso(eos, wl[IDN], wl[IBY], wl[IBZ], bxi) : fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cfr = eos.iso ? fast_speed_iso(eos, wr[IDN], wr[IBY], wr[IBZ], bxi) : fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
   Real a = 0.5 * max_std((fabs(wl[IVX]) + cfl), (fabs(wr[IVX]) + cfr));
   mhd_lr_fluxes(eos, wl, wr, bxi, fl, fr, du, &el, &er, &pbl, &pbr);
 #pragma unroll
@@ -270,17 +346,26 @@ ATHK_HD void hlle_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr
   Real y = 0.5 * (wl[IDN] + wr[IDN]) / wroe[IDN];
   Real pbl = 0.5 * (bxi * bxi + sqr(wl[IBY]) + sqr(wl[IBZ]));
   Real pbr = 0.5 * (bxi * bxi + sqr(wr[IBY]) + sqr(wr[IBZ]));
-  Real el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
-  Real er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
-  Real hroe = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr;
-  Real cl = fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
-  Real cr = fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
+  Real el = 0.0, er = 0.0, hroe = 0.0;
+  if (!eos.iso) {
+    el = wl[IPR] / gm1 + 0.5 * wl[IDN] * (sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ])) + pbl;
+    er = wr[IPR] / gm1 + 0.5 * wr[IDN] * (sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ])) + pbr;
+    hroe = ((el + wl[IPR] + pbl) / sqrtdl + (er + wr[IPR] + pbr) / sqrtdr) * isdlpdr;
+  }
+  Real cl = eos.iso ? fast_speed_iso(eos, wl[IDN], wl[IBY], wl[IBZ], bxi) : fast_speed(eos, wl[IDN], wl[IPR], wl[IBY], wl[IBZ], bxi);
+  Real cr = eos.iso ? fast_speed_iso(eos, wr[IDN], wr[IBY], wr[IBZ], bxi) : fast_speed(eos, wr[IDN], wr[IPR], wr[IBY], wr[IBZ], bxi);
   Real btsq = sqr(wroe[IBY]) + sqr(wroe[IBZ]);
   Real vaxsq = bxi * bxi / wroe[IDN];
-  Real bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
-  Real hp = hroe - (vaxsq + btsq / wroe[IDN]);
-  Real vsq = sqr(wroe[IVX]) + sqr(wroe[IVY]) + sqr(wroe[IVZ]);
-  Real twid_asq = max_std((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 0.0);
+  Real bt_starsq, twid_asq;
+  if (eos.iso) {   // hlle_mhd.cpp:103-106
+    bt_starsq = btsq * y;
+    twid_asq = eos.iso_cs * eos.iso_cs + x;
+  } else {
+    bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+    Real hp = hroe - (vaxsq + btsq / wroe[IDN]);
+    Real vsq = sqr(wroe[IVX]) + sqr(wroe[IVY]) + sqr(wroe[IVZ]);
+    twid_asq = max_std((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 0.0);
+  }
   Real ct2 = bt_starsq / wroe[IDN];
   Real tsum = vaxsq + ct2 + twid_asq;
   Real tdif = vaxsq + ct2 - twid_asq;
@@ -301,12 +386,18 @@ ATHK_HD void hlle_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr
   fr[IVY] = wr[IDN] * wr[IVY] * vxr - bxi * wr[IBY];
   fl[IVZ] = wl[IDN] * wl[IVZ] * vxl - bxi * wl[IBZ];
   fr[IVZ] = wr[IDN] * wr[IVZ] * vxr - bxi * wr[IBZ];
-  fl[IVX] += wl[IPR];
-  fr[IVX] += wr[IPR];
-  fl[IEN] = el * vxl + wl[IVX] * (wl[IPR] + pbl - bxi * bxi);
-  fr[IEN] = er * vxr + wr[IVX] * (wr[IPR] + pbr - bxi * bxi);
-  fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
-  fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  if (eos.iso) {   // hlle_mhd.cpp:147-150
+    fl[IVX] += (eos.iso_cs * eos.iso_cs) * wl[IDN];
+    fr[IVX] += (eos.iso_cs * eos.iso_cs) * wr[IDN];
+    fl[IEN] = fr[IEN] = 0.0;
+  } else {
+    fl[IVX] += wl[IPR];
+    fr[IVX] += wr[IPR];
+    fl[IEN] = el * vxl + wl[IVX] * (wl[IPR] + pbl - bxi * bxi);
+    fr[IEN] = er * vxr + wr[IVX] * (wr[IPR] + pbr - bxi * bxi);
+    fl[IEN] -= bxi * (wl[IBY] * wl[IVY] + wl[IBZ] * wl[IVZ]);
+    fr[IEN] -= bxi * (wr[IBY] * wr[IVY] + wr[IBZ] * wr[IVZ]);
+  }
   fl[IBY] = wl[IBY] * vxl - bxi * wl[IVY];
   fr[IBY] = wr[IBY] * vxr - bxi * wr[IVY];
   fl[IBZ] = wl[IBZ] * vxl - bxi * wl[IVZ];

@@ -51,6 +51,10 @@ CONFIGS = {
     "usrsrc_hydro_hllc": dict(PROB="usrsrc", MHD=0, FLUX="hllc", PGEN="oracle"),   # oracle/pgen/usrsrc.cpp
     "usrsrc_mhd_hlld": dict(PROB="usrsrc", MHD=1, FLUX="hlld", PGEN="oracle"),
     "blast_iso_hydro_hlle": dict(PROB="blast", MHD=0, FLUX="hlle", EOS="isothermal"),
+    "blast_iso_hydro_llf": dict(PROB="blast", MHD=0, FLUX="llf", EOS="isothermal"),
+    "blast_iso_hydro_roe": dict(PROB="blast", MHD=0, FLUX="roe", EOS="isothermal"),
+    "ot_iso_mhd_hlle": dict(PROB="orszag_tang", MHD=1, FLUX="hlle", EOS="isothermal"),
+    "ot_iso_mhd_llf": dict(PROB="orszag_tang", MHD=1, FLUX="llf", EOS="isothermal"),
     "ot_iso_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld", EOS="isothermal"),   # (blast.cpp:208 writes
     # u(IEN) unguarded with -b: the reference's own blast problem cannot run isothermal MHD)
     "kh_iso_mhd_hlld_s1": dict(PROB="kh", MHD=1, FLUX="hlld", EOS="isothermal", NSCALARS=1),

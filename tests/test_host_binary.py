@@ -156,6 +156,19 @@ CASES = {
     "iso_kh_mhd_hlld_scalar": ("kh_iso_mhd_hlld_s1", "kh", True, lambda: iso(
         refrun.kh_blocks(mesh=(32, 32, 8), block=(16, 16, 8), tlim=0.1, rst_dt=0.05, integrator="vl2", xorder=2,
                          b0=0.5), 1.1), ["--eos=isothermal", "--nscalars=1"]),
+    # ... with the reference's other solvers for it: the NON_BAROTROPIC_EOS == 0 branches of llf.cpp, roe.cpp
+    # (four waves, LLF fallback), llf_mhd.cpp and hlle_mhd.cpp
+    "iso_blast_hydro_llf": ("blast_iso_hydro_llf", "blast", False, lambda: iso(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.1, rst_dt=0.05, b0=None, radius=0.3),
+        0.7, drat=8.0), ["--eos=isothermal", "--flux=llf"]),
+    "iso_blast_hydro_roe_rk3": ("blast_iso_hydro_roe", "blast", False, lambda: iso(
+        refrun.blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.1, rst_dt=0.05, b0=None, radius=0.3,
+                            integrator="rk3", bcs=["reflecting"] * 4 + ["outflow"] * 2, center=(0.5, 0.4, 0.3)),
+        0.7, drat=30.0), ["--eos=isothermal", "--flux=roe"]),
+    "iso_orszag_tang_hlle": ("ot_iso_mhd_hlle", "orszag_tang", True, lambda: iso(
+        refrun.ot_blocks(tlim=0.05, rst_dt=0.025), 0.9), ["--eos=isothermal", "--flux=hlle"]),
+    "iso_orszag_tang_llf_rk2": ("ot_iso_mhd_llf", "orszag_tang", True, lambda: iso(
+        refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk2"), 0.9), ["--eos=isothermal", "--flux=llf"]),
     "iso_orszag_tang_rk3": ("ot_iso_mhd_hlld", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk3"), 0.9), ["--eos=isothermal"]),
     # user-enrolled explicit source terms (SrcTermFunc, time-dependent) -- the reference
