@@ -317,6 +317,17 @@ class Mesh {   // mesh/mesh.hpp:206-447
   void BuildRefinedTree(ParameterInput *pin);
   void SearchAndSetNeighbors(MeshBlock *pmb);
   void SetupRefinement();
+  // The box lists (athk_refine_set_ops / athk_refine_run; include/athk.h), as the host numbers them:
+  //    0  flux correction of the hydro fluxes from finer faces      66  ... of the scalar fluxes
+  //    1  restriction for coarser neighbours (u, s, b)               2  cell-centred from finer / from coarser
+  //    3  restriction of same-level ghost zones (u, s, b)            4  W(U) on the coarse buffer
+  //    7  reflecting / outflow functions on the coarse buffer        5  prolongation of the primitives (w, r)
+  //    6  U(W) (+ bcc, s) on the prolongated ghost zones
+  //    8, 9, 10  field from same-level / finer face, edge, corner neighbours
+  //   11, 64, 65 field from coarser face, edge, corner neighbours
+  //   12  shared faces, 13 internal faces of the prolongated field
+  //   14  clear, 16..63 add (one list per face / edge neighbour slot), 15 average: EMFs from finer blocks
+  // Order of execution: Mesh::ExchangeGhosts (mesh.cpp), TimeIntegratorTaskList::DoTaskListOneStage.
   // face-centred field + EMF correction boxes; lists[rank][list]
   void SetupFieldRefinement(std::vector<std::vector<std::vector<athk_box_op>>> *lists);
   // user-enrolled boundary functions on the coarse buffer (bvals_refine.cpp:445-530): which function, on
