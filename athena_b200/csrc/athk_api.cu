@@ -80,12 +80,13 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     if (!(cfg->iso_sound_speed > 0.0)) return fail(ATHK_ERR_ARG, "athk_create: isothermal EOS needs iso_sound_speed > 0");
     // hlle.cpp / hlld_iso.cpp have their own kernels; LLF, HLLE (MHD) and Roe (hydro) branch on the EOS
     // inside the adiabatic kernels' flux functions (NON_BAROTROPIC_EOS == 0 branches of llf.cpp, llf_mhd.cpp,
-    // hlle_mhd.cpp, roe.cpp)
-    const bool ok = cfg->mhd ? (cfg->rsolver == ATHK_RS_HLLD || cfg->rsolver == ATHK_RS_HLLE || cfg->rsolver == ATHK_RS_LLF)
+    // hlle_mhd.cpp, roe.cpp, roe_mhd.cpp)
+    const bool ok = cfg->mhd ? (cfg->rsolver == ATHK_RS_HLLD || cfg->rsolver == ATHK_RS_HLLE || cfg->rsolver == ATHK_RS_LLF ||
+                                cfg->rsolver == ATHK_RS_ROE)
                              : (cfg->rsolver == ATHK_RS_HLLE || cfg->rsolver == ATHK_RS_LLF || cfg->rsolver == ATHK_RS_ROE);
     if (!ok)
       return fail(ATHK_ERR_ARG, "athk_create: the isothermal EOS is implemented with rsolver HLLE, LLF, Roe (hydro) and "
-                                "HLLD, HLLE, LLF (mhd)");
+                                "HLLD, HLLE, LLF, Roe (mhd)");
     if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for the isothermal EOS");
   }
   if (cfg->arith == ATHK_ARITH_FAST && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_HLLD)

@@ -410,8 +410,219 @@ ATHK_HD void hlle_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr
 
 // roe_mhd.cpp:43-210 with RoeFlux :245-470 (adiabatic branch).  The LLF fallback of the reference
 // leaves the induction components at their Roe values (roe_mhd.cpp:193-205); so does this.
+// Roe for isothermal MHD: roe_mhd.cpp:43-210 with NON_BAROTROPIC_EOS == 0 and RoeFlux's isothermal
+// eigensystem (:255-350, :496-640; six waves).  The reference's wave vector has no energy slot there
+// (IBY = 4, IBZ = 5); here the field components stay in slots 5 and 6 and slot 4 carries a zero flux.
+// As in the adiabatic solver the LLF fallback replaces the hydro components only (:186-197).
+ATHK_HD void roe_iso_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
+                              Real f[7]) {
+  const Real iso_cs = eos.iso_cs;
+  Real fl[7], fr[7], du[7], ev[6], el, er, pbl, pbr;
+  Real sqrtdl = sqrt(wl[IDN]);
+  Real sqrtdr = sqrt(wr[IDN]);
+  Real isdlpdr = 1.0 / (sqrtdl + sqrtdr);
+  const Real d = sqrtdl * sqrtdr;
+  const Real v1 = (sqrtdl * wl[IVX] + sqrtdr * wr[IVX]) * isdlpdr;
+  const Real v2 = (sqrtdl * wl[IVY] + sqrtdr * wr[IVY]) * isdlpdr;
+  const Real v3 = (sqrtdl * wl[IVZ] + sqrtdr * wr[IVZ]) * isdlpdr;
+  const Real b2 = (sqrtdr * wl[IBY] + sqrtdl * wr[IBY]) * isdlpdr;
+  const Real b3 = (sqrtdr * wl[IBZ] + sqrtdl * wr[IBZ]) * isdlpdr;
+  const Real b1 = bxi;
+  const Real x = 0.5 * (sqr(wl[IBY] - wr[IBY]) + sqr(wl[IBZ] - wr[IBZ])) / (sqr(sqrtdl + sqrtdr));
+  const Real y = 0.5 * (wl[IDN] + wr[IDN]) / d;
+  mhd_lr_fluxes(eos, wl, wr, bxi, fl, fr, du, &el, &er, &pbl, &pbr);
+#pragma unroll
+  for (int n = 0; n < 7; ++n) f[n] = 0.5 * (fl[n] + fr[n]);
+  f[IEN] = 0.0;
+  int llf_flag = 0;
+  {
+    Real di = 1.0 / d;
+    Real btsq = b2 * b2 + b3 * b3;
+    Real vaxsq = b1 * b1 * di;
+    Real bt_starsq = btsq * y;
+    Real twid_csq = (iso_cs * iso_cs) + x;
+    Real ct2 = bt_starsq * di;
+    Real tsum = vaxsq + ct2 + twid_csq;
+    Real tdif = vaxsq + ct2 - twid_csq;
+    Real cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_csq * ct2);
+    Real cfsq = 0.5 * (tsum + cf2_cs2);
+    Real cf = sqrt(cfsq);
+    Real cssq = twid_csq * vaxsq / cfsq;
+    Real cs = sqrt(cssq);
+    Real bt = sqrt(btsq);
+    Real bt_star = sqrt(bt_starsq);
+    Real bet2 = 0.0;
+    Real bet3 = 0.0;
+    if (bt != 0.0) {
+      bet2 = b2 / bt;
+      bet3 = b3 / bt;
+    }
+    Real bet2_star = bet2 / sqrt(y);
+    Real bet3_star = bet3 / sqrt(y);
+    Real bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star;
+    Real q2_star = 0.0;
+    Real q3_star = 0.0;
+    if (bet_starsq != 0.0) {
+      q2_star = bet2_star / bet_starsq;
+      q3_star = bet3_star / bet_starsq;
+    }
+    Real alpha_f, alpha_s;
+    if ((cfsq - cssq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else if ((twid_csq - cssq) <= 0.0) {
+      alpha_f = 0.0;
+      alpha_s = 1.0;
+    } else if ((cfsq - twid_csq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else {
+      alpha_f = sqrt((twid_csq - cssq) / (cfsq - cssq));
+      alpha_s = sqrt((cfsq - twid_csq) / (cfsq - cssq));
+    }
+    Real sqrtd = sqrt(d);
+    Real isqrtd = 1.0 / sqrtd;
+    Real s = sign_ath(b1);
+    Real twid_c = sqrt(twid_csq);
+    Real qf = cf * alpha_f * s;
+    Real qs = cs * alpha_s * s;
+    Real af_prime = twid_c * alpha_f * isqrtd;
+    Real as_prime = twid_c * alpha_s * isqrtd;
+    Real vqstr = (v2 * q2_star + v3 * q3_star);
+    Real vax = sqrt(vaxsq);
+    Real norm = 0.5 / twid_csq;
+    Real cff = norm * alpha_f * cf;
+    Real css = norm * alpha_s * cs;
+    Real qf_hat = qf * norm;
+    Real qs_hat = qs * norm;
+    Real af = norm * af_prime * d;
+    Real as = norm * as_prime * d;
+    Real afpb = norm * af_prime * bt_star;
+    Real aspb = norm * as_prime * bt_star;
+    (void)isqrtd;
+
+    ev[0] = v1 - cf;
+    ev[1] = v1 - vax;
+    ev[2] = v1 - cs;
+    ev[3] = v1 + cs;
+    ev[4] = v1 + vax;
+    ev[5] = v1 + cf;
+
+    // (du of the reference: 0..3 hydro, 4 = By, 5 = Bz)
+    const Real du4 = du[IBY], du5 = du[IBZ];
+    Real a[6];
+    a[0] = du[0] * (cff * (cf + v1) - qs_hat * vqstr - aspb);
+    a[0] -= du[1] * cff;
+    a[0] += du[2] * qs_hat * q2_star;
+    a[0] += du[3] * qs_hat * q3_star;
+    a[0] += du4 * as * q2_star;
+    a[0] += du5 * as * q3_star;
+
+    a[1] = du[0] * (v2 * bet3 - v3 * bet2);
+    a[1] -= du[2] * bet3;
+    a[1] += du[3] * bet2;
+    a[1] -= du4 * sqrtd * bet3 * s;
+    a[1] += du5 * sqrtd * bet2 * s;
+    a[1] *= 0.5;
+
+    a[2] = du[0] * (css * (cs + v1) + qf_hat * vqstr + afpb);
+    a[2] -= du[1] * css;
+    a[2] -= du[2] * qf_hat * q2_star;
+    a[2] -= du[3] * qf_hat * q3_star;
+    a[2] -= du4 * af * q2_star;
+    a[2] -= du5 * af * q3_star;
+
+    a[3] = du[0] * (css * (cs - v1) - qf_hat * vqstr + afpb);
+    a[3] += du[1] * css;
+    a[3] += du[2] * qf_hat * q2_star;
+    a[3] += du[3] * qf_hat * q3_star;
+    a[3] -= du4 * af * q2_star;
+    a[3] -= du5 * af * q3_star;
+
+    a[4] = du[0] * (v3 * bet2 - v2 * bet3);
+    a[4] += du[2] * bet3;
+    a[4] -= du[3] * bet2;
+    a[4] -= du4 * sqrtd * bet3 * s;
+    a[4] += du5 * sqrtd * bet2 * s;
+    a[4] *= 0.5;
+
+    a[5] = du[0] * (cff * (cf - v1) + qs_hat * vqstr - aspb);
+    a[5] += du[1] * cff;
+    a[5] -= du[2] * qs_hat * q2_star;
+    a[5] -= du[3] * qs_hat * q3_star;
+    a[5] += du4 * as * q2_star;
+    a[5] += du5 * as * q3_star;
+
+    Real coeff[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) coeff[n] = -0.5 * fabs(ev[n]) * a[n];
+
+    Real dens = wl[IDN] + a[0] * alpha_f;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[2] * alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3] * alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+
+    f[0] += coeff[0] * alpha_f;
+    f[0] += coeff[2] * alpha_s;
+    f[0] += coeff[3] * alpha_s;
+    f[0] += coeff[5] * alpha_f;
+
+    f[1] += coeff[0] * alpha_f * (v1 - cf);
+    f[1] += coeff[2] * alpha_s * (v1 - cs);
+    f[1] += coeff[3] * alpha_s * (v1 + cs);
+    f[1] += coeff[5] * alpha_f * (v1 + cf);
+
+    f[2] += coeff[0] * (alpha_f * v2 + qs * bet2_star);
+    f[2] -= coeff[1] * bet3;
+    f[2] += coeff[2] * (alpha_s * v2 - qf * bet2_star);
+    f[2] += coeff[3] * (alpha_s * v2 + qf * bet2_star);
+    f[2] += coeff[4] * bet3;
+    f[2] += coeff[5] * (alpha_f * v2 - qs * bet2_star);
+
+    f[3] += coeff[0] * (alpha_f * v3 + qs * bet3_star);
+    f[3] += coeff[1] * bet2;
+    f[3] += coeff[2] * (alpha_s * v3 - qf * bet3_star);
+    f[3] += coeff[3] * (alpha_s * v3 + qf * bet3_star);
+    f[3] -= coeff[4] * bet2;
+    f[3] += coeff[5] * (alpha_f * v3 - qs * bet3_star);
+
+    f[IBY] += coeff[0] * as_prime * bet2_star;
+    f[IBY] -= coeff[1] * bet3 * s / sqrtd;
+    f[IBY] -= coeff[2] * af_prime * bet2_star;
+    f[IBY] -= coeff[3] * af_prime * bet2_star;
+    f[IBY] -= coeff[4] * bet3 * s / sqrtd;
+    f[IBY] += coeff[5] * as_prime * bet2_star;
+
+    f[IBZ] += coeff[0] * as_prime * bet3_star;
+    f[IBZ] += coeff[1] * bet2 * s / sqrtd;
+    f[IBZ] -= coeff[2] * af_prime * bet3_star;
+    f[IBZ] -= coeff[3] * af_prime * bet3_star;
+    f[IBZ] += coeff[4] * bet2 * s / sqrtd;
+    f[IBZ] += coeff[5] * as_prime * bet3_star;
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) f[n] = fl[n];
+  }
+  if (ev[5] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) f[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    Real cfl = fast_speed_iso(eos, wl[IDN], wl[IBY], wl[IBZ], bxi);
+    Real cfr = fast_speed_iso(eos, wr[IDN], wr[IBY], wr[IBZ], bxi);
+    Real am = 0.5 * max_std((fabs(wl[IVX]) + cfl), (fabs(wr[IVX]) + cfr));
+#pragma unroll
+    for (int n = 0; n < 4; ++n) f[n] = 0.5 * (fl[n] + fr[n]) - am * du[n];
+  }
+  f[IEN] = 0.0;
+}
+
 ATHK_HD void roe_mhd_flux(const EosParams &eos, const Real wl[7], const Real wr[7], const Real bxi,
                           Real f[7]) {
+  if (eos.iso) { roe_iso_mhd_flux(eos, wl, wr, bxi, f); return; }
   const Real gm1 = eos.gm1;
   Real wroe[7], fl[7], fr[7], du[7], ev[7], el, er, pbl, pbr;
   Real sqrtdl = sqrt(wl[IDN]);

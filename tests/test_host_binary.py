@@ -169,6 +169,8 @@ CASES = {
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025), 0.9), ["--eos=isothermal", "--flux=hlle"]),
     "iso_orszag_tang_llf_rk2": ("ot_iso_mhd_llf", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk2"), 0.9), ["--eos=isothermal", "--flux=llf"]),
+    "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
+        refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
     "iso_orszag_tang_rk3": ("ot_iso_mhd_hlld", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk3"), 0.9), ["--eos=isothermal"]),
     # user-enrolled explicit source terms (SrcTermFunc, time-dependent) -- the reference
