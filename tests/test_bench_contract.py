@@ -63,4 +63,7 @@ def test_product_arm_line_has_every_contract_key(cuda_lib):
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = d["e2e"]
     assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    # the e2e number has several independent sets of MeshBlocks in flight; the one-set number stays beside it
+    assert e["pipeline"]["sets_in_flight"] == 3 and e["pipeline"]["added_sets_bit_identical"] is True
+    assert 0 < e["one_set_in_sequence"]["value"] < d["value"]
     assert "workload" in d["config"] and "sm_mhz" in d["clocks"]
