@@ -400,25 +400,7 @@ def run_ours(args):
     e2e_pipe = None
     nsets = max(1, args.e2e_sets)
     if world == 1 and nsets > 1 and args.per_gpu <= 320:
-        import threading
         import time as _time
-
-        # one set at a time owns each direction of the link (the DMA engines interleave the copies
-        # of concurrent streams, which drives the sets into lockstep: all copying in, then all
-        # copying out, each direction idle half of the time)
-        link_in, link_out = threading.Lock(), threading.Lock()
-
-        def lane_step(c, t, bufs):
-            with link_in:
-                for k in bufs:
-                    c.call("athk_upload_all", capi.ARRAYS[k], bufs[k].ctypes.data_as(dp), 1)
-                c.sync()
-            t.refresh_ghosts_and_primitives()
-            t.step()
-            with link_out:
-                for k in bufs:
-                    c.call("athk_download_all_async", capi.ARRAYS[k], bufs[k].ctypes.data_as(dp), 1)
-                c.sync()
 
         lanes = [(ctx, ti, anp, stream, ahost)]
         for _ in range(nsets - 1):
@@ -440,24 +422,11 @@ def run_ours(args):
         # direction of the link and leave the other idle)
         lag_s = ms_e2e / e2e_n * 1e-3 / nsets
 
-        def run_lanes(n_each):
-            errs = []
+        from athena_b200 import ensemble
+        ens = ensemble.HostSteppedEnsemble([ensemble.Member(ln[0], ln[1], ln[2], local_rank) for ln in lanes])
 
-            def work(n):
-                try:
-                    torch.cuda.set_device(local_rank)
-                    _time.sleep(n * lag_s)
-                    for _ in range(n_each):
-                        lane_step(lanes[n][0], lanes[n][1], lanes[n][2])
-                except Exception as ex:   # surfaced after join
-                    errs.append(ex)
-            ths = [threading.Thread(target=work, args=(n,)) for n in range(nsets)]
-            for th in ths:
-                th.start()
-            for th in ths:
-                th.join()
-            if errs:
-                raise errs[0]
+        def run_lanes(n_each):
+            ens.run(n_each, lag_s)
 
         def sync_lanes():
             for ln in lanes:
