@@ -42,7 +42,8 @@ class Config(C.Structure):
                 ("nblocks", C.c_int), ("mhd", C.c_int), ("nscalars", C.c_int),
                 ("rsolver", C.c_int), ("device", C.c_int), ("arith", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
-                ("sfloor", C.c_double), ("eos", C.c_int), ("iso_sound_speed", C.c_double)]
+                ("sfloor", C.c_double), ("eos", C.c_int), ("iso_sound_speed", C.c_double),
+                ("gamma_max", C.c_double)]
 
 
 class StageWghts(C.Structure):

@@ -74,8 +74,15 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   if (cfg->eos != ATHK_EOS_ISOTHERMAL && !(cfg->gamma > 1.0)) return fail(ATHK_ERR_ARG, "athk_create: gamma must be > 1");
   if (cfg->arith != ATHK_ARITH_STRICT && cfg->arith != ATHK_ARITH_FAST)
     return fail(ATHK_ERR_ARG, "athk_create: arith must be ATHK_ARITH_STRICT (0) or ATHK_ARITH_FAST (1)");
-  if (cfg->eos != ATHK_EOS_ADIABATIC && cfg->eos != ATHK_EOS_ISOTHERMAL)
+  if (cfg->eos != ATHK_EOS_ADIABATIC && cfg->eos != ATHK_EOS_ISOTHERMAL && cfg->eos != ATHK_EOS_ADIABATIC_SR)
     return fail(ATHK_ERR_ARG, "athk_create: unknown eos %d", cfg->eos);
+  if (cfg->eos == ATHK_EOS_ADIABATIC_SR) {   // configure.py -s
+    if (cfg->mhd) return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented for hydro only (mhd = 0)");
+    if (cfg->rsolver != ATHK_RS_HLLE)
+      return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented with rsolver HLLE (hlle_rel.cpp)");
+    if (cfg->nscalars) return fail(ATHK_ERR_ARG, "athk_create: no passive scalars with special relativity");
+    if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for special relativity");
+  }
   if (cfg->eos == ATHK_EOS_ISOTHERMAL) {
     if (!(cfg->iso_sound_speed > 0.0)) return fail(ATHK_ERR_ARG, "athk_create: isothermal EOS needs iso_sound_speed > 0");
     // hlle.cpp / hlld_iso.cpp have their own kernels; LLF, HLLE (MHD) and Roe (hydro) branch on the EOS
@@ -119,6 +126,8 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
                     cfg->sfloor > 0 ? cfg->sfloor : fmin_default);
   c->eos.iso = (cfg->eos == ATHK_EOS_ISOTHERMAL) ? 1 : 0;
   c->eos.iso_cs = cfg->iso_sound_speed;
+  c->eos.sr = (cfg->eos == ATHK_EOS_ADIABATIC_SR) ? 1 : 0;
+  c->eos.gamma_max = cfg->gamma_max > 0.0 ? cfg->gamma_max : 1000.0;
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
   c->dt_requested = c->dt_valid = false;
@@ -139,6 +148,8 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   int rc = 0;
   for (int r = 0; r < 3 && !rc; ++r) rc = dev_alloc(&c->u[r], r < 2 ? cc_elems(c, 5) : 0, st);
   if (!rc) rc = dev_alloc(&c->w, cc_elems(c, 5), st);
+  c->w_alt = nullptr;
+  if (!rc && c->eos.sr) rc = dev_alloc(&c->w_alt, cc_elems(c, 5), st);
   for (int d = 0; d < 3 && !rc; ++d) rc = dev_alloc(&c->flux[d], cc_elems(c, 5), st);
   const size_t mh = cfg->mhd ? 1 : 0;
   if (!rc) rc = dev_alloc(&c->bcc, mh * cc_elems(c, 3), st);
@@ -199,7 +210,7 @@ extern "C" void athk_destroy(athk_ctx *c) {
   cudaSetDevice(c->cfg.device);
   for (int r = 0; r < 3; ++r) { cudaFree(c->u[r]); cudaFree(c->b[r]); cudaFree(c->s[r]); }
   for (int d = 0; d < 3; ++d) { cudaFree(c->flux[d]); cudaFree(c->sflux[d]); }
-  cudaFree(c->w); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
+  cudaFree(c->w); cudaFree(c->w_alt); cudaFree(c->bcc); cudaFree(c->ef); cudaFree(c->wct); cudaFree(c->e);
   cudaFree(c->bcflags);
   cudaFree(c->d_floors);
   cudaFree(c->stage);
@@ -624,6 +635,9 @@ static int cons2prim_part(athk_ctx *c, int reg, int part) {
   Real *dt_out = nullptr;
   const bool fold = c->dt_requested && part != 2;   // the block dt is a property of the active zone
   if (part != 2) c->dt_valid = false;
+  if (c->eos.sr && part != 2) {   // ph->w.SwapAthenaArray(ph->w1): write the array of two calls ago
+    Real *t = c->w; c->w = c->w_alt; c->w_alt = t;
+  }
   if (fold) {
     int rc = fill_dt_blocks(c);
     if (rc) return rc;
@@ -1025,6 +1039,8 @@ extern "C" int athk_set_boundary_flags(athk_ctx *c, int lb, const int flags[6]) 
     if (flags[f] < ATHK_BC_NONE || flags[f] > ATHK_BC_USER)
       return fail(ATHK_ERR_ARG, "set_boundary_flags: face %d has unknown flag %d (reflecting, outflow, user or none)",
                   f, flags[f]);
+    if (c->eos.sr && flags[f] != ATHK_BC_NONE)
+      return fail(ATHK_ERR_ARG, "set_boundary_flags: physical boundaries are not implemented with special relativity");
     c->h_bcflags[(size_t)lb * 6 + f] = flags[f];
   }
   c->bc_dirty = true;
@@ -1093,6 +1109,7 @@ extern "C" int athk_refine_enable(athk_ctx *c) {
   if (!c) return fail(ATHK_ERR_ARG, "refine_enable: null context");
   cudaSetDevice(c->cfg.device);
   if (c->rf.on) return ATHK_OK;
+  if (c->eos.sr) return fail(ATHK_ERR_ARG, "refine_enable: mesh refinement is not implemented with special relativity");
   const Grid &g = c->g;
   if (g.nx1 % 2 || g.nx2 % 2 || g.nx3 % 2)   // mesh.cpp:340-346
     return fail(ATHK_ERR_ARG, "The size of MeshBlock must be divisible by 2 in order to use SMR or AMR.");
@@ -1376,12 +1393,15 @@ extern "C" int athk_set_block_floors(athk_ctx *c, int lb, double dfloor, double 
 
 extern "C" int athk_set_constant_acceleration(athk_ctx *c, double g1, double g2, double g3) {
   if (!c) return fail(ATHK_ERR_ARG, "set_constant_acceleration: null context");
+  if (c->eos.sr && (g1 != 0.0 || g2 != 0.0 || g3 != 0.0))
+    return fail(ATHK_ERR_ARG, "set_constant_acceleration: no source terms with special relativity");
   c->gacc[0] = g1; c->gacc[1] = g2; c->gacc[2] = g3;
   return ATHK_OK;
 }
 
 extern "C" int athk_enroll_user_source(athk_ctx *c, athk_src_fn fn, void *user) {
   if (!c) return fail(ATHK_ERR_ARG, "enroll_user_source: null context");
+  if (c->eos.sr && fn) return fail(ATHK_ERR_ARG, "enroll_user_source: no source terms with special relativity");
   c->user_src = fn;
   c->user_src_data = user;
   return ATHK_OK;

@@ -49,6 +49,7 @@ struct athk_ctx {
   // storage
   Real *u[3];       // hydro registers [nb][5][sn]
   Real *w;          // [nb][5][sn]
+  Real *w_alt;      // SR only: Hydro::w1, the array the next W(U) writes (swapped with w by every W(U))
   Real *bcc;        // [nb][3][sn]
   Real *b[3];       // field registers [nb][3][sn]
   Real *flux[3];    // [nb][5][sn]

@@ -143,7 +143,17 @@ struct Cons2PrimPoint {
       if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
       else cons2prim_mhd(eos_of_block(eos, blk), uc, bc1, bc2, bc3, wc);
     } else {
-      if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
+      if (eos.sr) {   // the output array still holds W of two calls ago: fallback state and first guess
+#pragma unroll
+        for (int n = 0; n < 5; ++n) wc[n] = wb[n * g.sn];
+        if (cons2prim_sr(eos_of_block(eos, blk), uc, wc)) {
+          ub[IM1 * g.sn] = uc[IM1];
+          ub[IM2 * g.sn] = uc[IM2];
+          ub[IM3 * g.sn] = uc[IM3];
+          ub[IDN * g.sn] = uc[IDN];
+          ub[IEN * g.sn] = uc[IEN];
+        }
+      } else if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
       else cons2prim_hydro(eos_of_block(eos, blk), uc, wc);
     }
     if (uc[IDN] != d0) ub[IDN * g.sn] = uc[IDN];
@@ -185,10 +195,12 @@ struct Cons2PrimPoint {
         dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b1, b2, bx))));
         }
       } else {
+        if (!eos.sr) {   // (SR: the cell widths themselves, new_blockdt.cpp:130)
         const Real cs = eos.iso ? eos.iso_cs : m.sqrt(m.div(eos.gamma * wc[IPR], wc[IDN]));
         dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + cs)));
         dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + cs)));
         dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + cs)));
+        }
       }
       dtcell = min_std(min_std(dt1, dt2), dt3);
       });
@@ -883,7 +895,7 @@ struct CellDt {
       bx = b3 + fabs(bf[2 * g.sn] - b3);
       cf = eos.iso ? fast_speed_iso(eos, d, b1, b2, bx) : fast_speed(eos, d, p, b1, b2, bx);
       dt3 /= max_std(0.0, (fabs(vz) + cf));
-    } else {
+    } else if (!eos.sr) {   // (SR: the cell widths themselves, maximum characteristic c = 1; new_blockdt.cpp:130)
       const Real cs = eos.iso ? eos.iso_cs : sound_speed(eos, d, p);
       dt1 /= max_std(0.0, (fabs(vx) + cs));
       dt2 /= max_std(0.0, (fabs(vy) + cs));

@@ -56,6 +56,10 @@ struct EosParams {
   // source) and the pressure slot of w is a dummy.
   int iso;
   Real iso_cs;
+  // special relativity (configure.py -s, hydro): eos/adiabatic_hydro_sr.cpp.  w holds (rho, u^1, u^2,
+  // u^3, pgas) with u^i the spatial components of the four-velocity; u holds (D, M^1, M^2, M^3, E).
+  int sr;
+  Real gamma_max;   // <hydro> gamma_max (velocity ceiling, default 1000)
 };
 
 // floors of block blk (uniform branch; a no-op unless per-block floors were set)
@@ -83,6 +87,8 @@ ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
   e.blk_floors = nullptr;
   e.iso = 0;
   e.iso_cs = 0.0;
+  e.sr = 0;
+  e.gamma_max = 1000.0;
   return e;
 }
 
@@ -137,6 +143,155 @@ ATHK_HD Real fast_speed_iso(const EosParams &eos, Real d, Real by, Real bz, Real
   Real qsq = vaxsq + ct2 + asq;
   Real tmp = vaxsq + ct2 - asq;
   return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
+}
+
+//----------------------------------------------------------------------------------------
+// Special-relativistic hydro (eos/adiabatic_hydro_sr.cpp).
+// std::isfinite without <cmath> differences between the two compilation passes
+ATHK_HD bool finite_ath(Real x) { return (x - x) == 0.0; }
+
+// ConservedToPrimitiveNormal (adiabatic_hydro_sr.cpp:303-411): fixed-point iteration on the gas
+// pressure with an Aitken step every third iteration (Newman & Hamlin 2014)
+ATHK_HD bool cons2prim_sr_normal(Real dd, Real ee, Real mm_sq, Real mm1, Real mm2, Real mm3, Real gamma_adi,
+                                 Real pgas_old, Real w[5], Real *p_gamma_lor) {
+  const int max_iterations = 15;
+  const Real tol = 1.0e-12;
+  const Real pgas_uniform_min = 1.0e-12;
+  const Real a_min = 1.0e-12;
+  const Real v_sq_max = 1.0 - 1.0e-12;
+  const Real rr_max = 1.0 - 1.0e-12;
+  Real pgas_min = -ee;
+  pgas_min = max_std(pgas_min, pgas_uniform_min);
+  // pgas[n % 3] of the reference kept in three scalars (p0, p1, p2): no dynamically indexed array
+  Real p0 = max_std(pgas_old, pgas_min), p1 = 0.0, p2 = 0.0;
+  Real result = 0.0;
+  int n;
+  for (n = 0; n < max_iterations; ++n) {
+    const int r = n % 3;
+    if (r != 2) {
+      const Real pin = (r == 0) ? p0 : p1;
+      Real a = ee + pin;
+      a = max_std(a, a_min);
+      Real v_sq = mm_sq / sqr(a);
+      v_sq = min_std(max_std(v_sq, 0.0), v_sq_max);
+      Real gamma_sq = 1.0 / (1.0 - v_sq);
+      Real gamma = sqrt(gamma_sq);
+      Real wgas = a / gamma_sq;
+      Real rho = dd / gamma;
+      Real pout = (gamma_adi - 1.0) / gamma_adi * (wgas - rho);
+      pout = max_std(pout, pgas_min);
+      if (r == 0) p1 = pout; else p2 = pout;
+      if (pout > pgas_min && fabs(pout - pin) < tol) { result = pout; break; }
+    } else {
+      Real rr = (p2 - p1) / (p1 - p0);
+      if (!finite_ath(rr) || fabs(rr) > rr_max) continue;
+      p0 = p1 + (p2 - p1) / (1.0 - rr);
+      p0 = max_std(p0, pgas_min);
+      if (p0 > pgas_min && fabs(p0 - p2) < tol) { result = p0; break; }
+    }
+  }
+  if (n == max_iterations) return false;
+  w[IPR] = result;   // (pgas[(n+1)%3]: the value the break left there)
+  if (!finite_ath(w[IPR])) return false;
+  Real a = ee + w[IPR];
+  a = max_std(a, a_min);
+  Real v_sq = mm_sq / sqr(a);
+  v_sq = min_std(max_std(v_sq, 0.0), v_sq_max);
+  Real gamma_sq = 1.0 / (1.0 - v_sq);
+  Real gamma = sqrt(gamma_sq);
+  w[IDN] = dd / gamma;
+  if (!finite_ath(w[IDN])) return false;
+  Real v1 = mm1 / a;
+  Real v2 = mm2 / a;
+  Real v3 = mm3 / a;
+  w[IVX] = gamma * v1;
+  w[IVY] = gamma * v2;
+  w[IVZ] = gamma * v3;
+  if (!finite_ath(w[IVX]) || !finite_ath(w[IVY]) || !finite_ath(w[IVZ])) return false;
+  *p_gamma_lor = gamma;
+  return true;
+}
+
+// EquationOfState::ConservedToPrimitive of one cell (adiabatic_hydro_sr.cpp:67-216).  On entry w[]
+// holds what the output array held before the call (the reference's fallback state and the
+// initial guess of the iteration); returns true when u[] was adjusted and has to be written back.
+ATHK_HD bool cons2prim_sr(const EosParams &eos, Real u[5], Real w[5]) {
+  const Real mm_sq_ee_sq_max = 1.0 - 1.0e-12;
+  const Real gamma_adi = eos.gamma;
+  Real dd = u[IDN], ee = u[IEN];
+  Real mm0 = sqr(u[IM1]) + sqr(u[IM2]) + sqr(u[IM3]);
+  Real mm1 = u[IM1], mm2 = u[IM2], mm3 = u[IM3];
+  bool fixed = false;
+  const Real dd_min = eos.dfloor;
+  if (dd < dd_min) { dd = dd_min; fixed = true; }
+  const Real ee_min = eos.dfloor + eos.pfloor / (gamma_adi - 1.0);
+  if (ee < ee_min) { ee = ee_min; fixed = true; }
+  const Real mm_sq_max = mm_sq_ee_sq_max * sqr(ee);
+  if (mm0 > mm_sq_max) {
+    const Real factor = sqrt(mm_sq_max / mm0);
+    mm0 = mm_sq_max;
+    mm1 *= factor;
+    mm2 *= factor;
+    mm3 *= factor;
+    fixed = true;
+  }
+  const Real rho_old = max_std(w[IDN], eos.dfloor);
+  const Real pgas_old = max_std(w[IPR], eos.pfloor);
+  const Real u1_old = w[IVX], u2_old = w[IVY], u3_old = w[IVZ];
+  Real gamma = 0.0;
+  bool success = cons2prim_sr_normal(dd, ee, mm0, mm1, mm2, mm3, gamma_adi, pgas_old, w, &gamma);
+  if (!success) {
+    w[IDN] = rho_old; w[IPR] = pgas_old; w[IVX] = u1_old; w[IVY] = u2_old; w[IVZ] = u3_old;
+    fixed = true;
+  }
+  const Real rho_add = max_std(eos.dfloor - w[IDN], 0.0);
+  const Real pgas_add = max_std(eos.pfloor - w[IPR], 0.0);
+  if (success && (rho_add > 0.0 || pgas_add > 0.0)) {
+    const Real wgas_add = rho_add + gamma_adi / (gamma_adi - 1.0) * pgas_add;
+    dd += rho_add * gamma;
+    ee += wgas_add * sqr(gamma) + pgas_add;
+    success = cons2prim_sr_normal(dd, ee, mm0, mm1, mm2, mm3, gamma_adi, pgas_old, w, &gamma);
+    if (!success) {
+      w[IDN] = rho_old; w[IPR] = pgas_old; w[IVX] = u1_old; w[IVY] = u2_old; w[IVZ] = u3_old;
+    }
+    fixed = true;
+  }
+  if (!success) gamma = sqrt(1.0 + sqr(w[IVX]) + sqr(w[IVY]) + sqr(w[IVZ]));
+  if (gamma > eos.gamma_max) {
+    const Real factor = sqrt((sqr(eos.gamma_max) - 1.0) / (sqr(gamma) - 1.0));
+    w[IVX] *= factor;
+    w[IVY] *= factor;
+    w[IVZ] *= factor;
+    fixed = true;
+  }
+  if (w[IDN] < eos.dfloor) { w[IDN] = eos.dfloor; fixed = true; }
+  if (w[IPR] < eos.pfloor) { w[IPR] = eos.pfloor; fixed = true; }
+  if (!success) {
+    w[IDN] = eos.dfloor;
+    w[IPR] = eos.pfloor;
+    w[IVX] = w[IVY] = w[IVZ] = 0.0;
+  }
+  if (fixed) {
+    const Real wgas = w[IDN] + gamma_adi / (gamma_adi - 1.0) * w[IPR];
+    gamma = sqrt(1.0 + sqr(w[IVX]) + sqr(w[IVY]) + sqr(w[IVZ]));
+    u[IDN] = w[IDN] * gamma;
+    u[IEN] = wgas * sqr(gamma) - w[IPR];
+    u[IM1] = wgas * gamma * w[IVX];
+    u[IM2] = wgas * gamma * w[IVY];
+    u[IM3] = wgas * gamma * w[IVZ];
+  }
+  return fixed;
+}
+
+// EquationOfState::SoundSpeedsSR (adiabatic_hydro_sr.cpp:271-281; Mignone & Bodo 2005 eq. 23)
+ATHK_HD void sound_speeds_sr(const EosParams &eos, Real rho_h, Real pgas, Real vx, Real gamma_lorentz_sq,
+                             Real *plambda_plus, Real *plambda_minus) {
+  Real cs_sq = eos.gamma * pgas / rho_h;
+  Real sigma_s = cs_sq / (gamma_lorentz_sq * (1.0 - cs_sq));
+  Real relative_speed = sqrt(sigma_s * (1.0 + sigma_s - sqr(vx)));
+  Real sigma_s_tmp = 1.0 / (1.0 + sigma_s);
+  *plambda_plus = sigma_s_tmp * (vx + relative_speed);
+  *plambda_minus = sigma_s_tmp * (vx - relative_speed);
 }
 
 // eos/adiabatic_hydro.cpp SoundSpeed ; eos/adiabatic_mhd.cpp:149-156 FastMagnetosonicSpeed

@@ -19,7 +19,66 @@ enum { RS_HLLC = 0, RS_HLLD = 1, RS_ROE = 2, RS_HLLE = 3, RS_LLF = 4,   // == en
        RS_HLLE_ISO = 5, RS_HLLD_ISO = 6 };   // isothermal EOS: hlle.cpp's barotropic branch, hlld_iso.cpp
 
 //----------------------------------------------------------------------------------------
+// HLLE for special-relativistic hydro: hlle_rel.cpp:94-286 (HLLETransforming with GENERAL_RELATIVITY
+// == 0: no frame transformation, interface velocity 0).  wl / wr: (rho, u^x, u^y, u^z, pgas) in the
+// sweep's rotated order, u^i the four-velocity's spatial part.
+ATHK_HD void hlle_sr_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  const Real gamma_adi = eos.gamma;
+  const Real gamma_prime = gamma_adi / (gamma_adi - 1.0);
+  const Real rho_l = wl[IDN], pgas_l = wl[IPR];
+  Real u_l[4];
+  u_l[0] = sqrt(1.0 + sqr(wl[IVX]) + sqr(wl[IVY]) + sqr(wl[IVZ]));
+  u_l[1] = wl[IVX]; u_l[2] = wl[IVY]; u_l[3] = wl[IVZ];
+  const Real rho_r = wr[IDN], pgas_r = wr[IPR];
+  Real u_r[4];
+  u_r[0] = sqrt(1.0 + sqr(wr[IVX]) + sqr(wr[IVY]) + sqr(wr[IVZ]));
+  u_r[1] = wr[IVX]; u_r[2] = wr[IVY]; u_r[3] = wr[IVZ];
+  Real lambda_p_l, lambda_m_l, lambda_p_r, lambda_m_r;
+  const Real wgas_l = rho_l + gamma_prime * pgas_l;
+  sound_speeds_sr(eos, wgas_l, pgas_l, u_l[1] / u_l[0], sqr(u_l[0]), &lambda_p_l, &lambda_m_l);
+  const Real wgas_r = rho_r + gamma_prime * pgas_r;
+  sound_speeds_sr(eos, wgas_r, pgas_r, u_r[1] / u_r[0], sqr(u_r[0]), &lambda_p_r, &lambda_m_r);
+  const Real lambda_l = min_std(lambda_m_l, lambda_m_r);
+  const Real lambda_r = max_std(lambda_p_l, lambda_p_r);
+  Real cons_l[5], flux_l[5], cons_r[5], flux_r[5];
+  cons_l[IDN] = rho_l * u_l[0];
+  cons_l[IEN] = wgas_l * u_l[0] * u_l[0] - pgas_l;
+  cons_l[IVX] = wgas_l * u_l[1] * u_l[0];
+  cons_l[IVY] = wgas_l * u_l[2] * u_l[0];
+  cons_l[IVZ] = wgas_l * u_l[3] * u_l[0];
+  flux_l[IDN] = rho_l * u_l[1];
+  flux_l[IEN] = wgas_l * u_l[0] * u_l[1];
+  flux_l[IVX] = wgas_l * u_l[1] * u_l[1] + pgas_l;
+  flux_l[IVY] = wgas_l * u_l[2] * u_l[1];
+  flux_l[IVZ] = wgas_l * u_l[3] * u_l[1];
+  cons_r[IDN] = rho_r * u_r[0];
+  cons_r[IEN] = wgas_r * u_r[0] * u_r[0] - pgas_r;
+  cons_r[IVX] = wgas_r * u_r[1] * u_r[0];
+  cons_r[IVY] = wgas_r * u_r[2] * u_r[0];
+  cons_r[IVZ] = wgas_r * u_r[3] * u_r[0];
+  flux_r[IDN] = rho_r * u_r[1];
+  flux_r[IEN] = wgas_r * u_r[0] * u_r[1];
+  flux_r[IVX] = wgas_r * u_r[1] * u_r[1] + pgas_r;
+  flux_r[IVY] = wgas_r * u_r[2] * u_r[1];
+  flux_r[IVZ] = wgas_r * u_r[3] * u_r[1];
+  const Real lambda_diff_inv = 1.0 / (lambda_r - lambda_l);
+  if (lambda_l >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = flux_l[n];
+  } else if (lambda_r <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = flux_r[n];
+  } else {
+#pragma unroll
+    for (int n = 0; n < 5; ++n)
+      f[n] = (lambda_r * flux_l[n] - lambda_l * flux_r[n] + lambda_l * lambda_r * (cons_r[n] - cons_l[n])) *
+             lambda_diff_inv;
+  }
+}
+
+//----------------------------------------------------------------------------------------
 ATHK_HD void hlle_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+  if (eos.sr) { hlle_sr_hydro_flux(eos, wl, wr, f); return; }
   const Real gm1 = eos.gm1;
   const Real igm1 = 1.0 / gm1;
   Real wroe[5], fl[5], fr[5];

@@ -53,6 +53,7 @@ struct Config {
   int nghost = 2;             // NGHOST
   int nscalars = 0;           // NSCALARS
   bool isothermal = false;    // --eos=isothermal: NON_BAROTROPIC_EOS == 0, NHYDRO == 4
+  bool sr = false;            // -s: RELATIVISTIC_DYNAMICS (special relativity, hydro)
   int nhydro() const { return isothermal ? 4 : 5; }
   int nwave() const { return nhydro() + (mhd ? 2 : 0); }
 };
@@ -62,6 +63,7 @@ extern Config g_config;
 #define NSCALARS (g_config.nscalars)
 #define NWAVE (g_config.nwave())
 #define NON_BAROTROPIC_EOS (!g_config.isothermal)
+#define RELATIVISTIC_DYNAMICS (g_config.sr)
 #define NHYDRO (g_config.nhydro())
 
 //----------------------------------------------------------------------------------------
@@ -191,11 +193,12 @@ class EquationOfState {   // eos/eos.hpp:32-181
   explicit EquationOfState(ParameterInput *pin);
   Real GetGamma() const { return gamma_; }
   Real GetIsoSoundSpeed() const { return iso_sound_speed_; }
+  Real GetGammaMax() const { return gamma_max_; }
   Real GetDensityFloor() const { return dfloor_; }
   Real GetPressureFloor() const { return pfloor_; }
   Real GetScalarFloor() const { return sfloor_; }
  private:
-  Real gamma_, dfloor_, pfloor_, sfloor_, iso_sound_speed_ = 0.0;
+  Real gamma_, dfloor_, pfloor_, sfloor_, iso_sound_speed_ = 0.0, gamma_max_ = 1000.0;
 };
 
 // bvals/bvals_interfaces.hpp:120-190 (NeighborBlock) -- what the refinement code needs of it

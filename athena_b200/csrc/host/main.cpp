@@ -33,6 +33,7 @@ void ShowConfig() {   // -c: what configure.py fixes in the reference is chosen 
             << "  Riemann solver:             "
             << (g_config.flux.empty() ? (g_config.mhd ? "hlld" : "hllc") : g_config.flux) << std::endl
             << "  Magnetic fields:            " << (g_config.mhd ? "ON" : "OFF") << std::endl
+            << "  Special relativity:         " << (g_config.sr ? "ON" : "OFF") << std::endl
             << "  Equation of state:          " << (g_config.isothermal ? "isothermal" : "adiabatic") << std::endl
             << "  Number of ghost cells:      " << g_config.nghost << std::endl
             << "  Number of scalars:          " << g_config.nscalars << std::endl
@@ -48,6 +49,7 @@ static void ParseConfigure(const std::string &s) {
   while (ss >> t) {
     if (t.compare(0, 7, "--prob=") == 0) g_config.problem = t.substr(7);
     else if (t == "-b") g_config.mhd = true;
+    else if (t == "-s") g_config.sr = true;
     else if (t.compare(0, 7, "--flux=") == 0) g_config.flux = t.substr(7);
     else if (t.compare(0, 9, "--nghost=") == 0) g_config.nghost = std::atoi(t.c_str() + 9);
     else if (t.compare(0, 6, "--eos=") == 0) {
@@ -89,10 +91,10 @@ int main(int argc, char *argv[]) {
                 << "  -n          parse input file and quit" << std::endl
                 << "  -c          show configuration and quit" << std::endl
                 << "  -t hh:mm:ss wall time limit for final output" << std::endl
-                << "  --prob=<pgen> [-b] [--eos=..] [--flux=..] [--nghost=n] [--nscalars=n]  configure-time choices "
+                << "  --prob=<pgen> [-b] [-s] [--eos=..] [--flux=..] [--nghost=n] [--nscalars=n]  configure-time choices "
                    "of the reference (default: the athinput's <comment> configure line)" << std::endl;
       return 0;
-    } else if (a.compare(0, 2, "--") == 0 || a == "-b") {
+    } else if (a.compare(0, 2, "--") == 0 || a == "-b" || a == "-s") {
       cfg_cmdline += a + " ";
       have_cfg = true;
     }

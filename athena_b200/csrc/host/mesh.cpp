@@ -116,6 +116,7 @@ EquationOfState::EquationOfState(ParameterInput *pin) {   // eos/adiabatic_*.cpp
   dfloor_ = pin->GetOrAddReal("hydro", "dfloor", std::sqrt(1024 * float_min));
   pfloor_ = pin->GetOrAddReal("hydro", "pfloor", std::sqrt(1024 * float_min));
   sfloor_ = pin->GetOrAddReal("hydro", "sfloor", std::sqrt(1024 * float_min));
+  if (RELATIVISTIC_DYNAMICS) gamma_max_ = pin->GetOrAddReal("hydro", "gamma_max", 1000.0);   // adiabatic_hydro_sr.cpp:40
 }
 
 MeshBlock::MeshBlock(int igid, int ilid, LogicalLocation iloc, RegionSize bs, Mesh *pm, ParameterInput *pin)
@@ -305,6 +306,14 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
                                ? (MAGNETIC_FIELDS_ENABLED ? "hlld" : (g_config.isothermal ? "hlle" : "hllc"))
                                : g_config.flux;
   cfg.eos = g_config.isothermal ? ATHK_EOS_ISOTHERMAL : ATHK_EOS_ADIABATIC;
+  if (RELATIVISTIC_DYNAMICS) {   // configure.py:391-409
+    if (g_config.isothermal) {
+      msg << "### FATAL ERROR in Mesh constructor" << std::endl << "Isothermal EOS is incompatible with relativity";
+      ATHENA_ERROR(msg);
+    }
+    cfg.eos = ATHK_EOS_ADIABATIC_SR;
+    cfg.gamma_max = blocks_[0]->peos->GetGammaMax();
+  }
   cfg.iso_sound_speed = g_config.isothermal ? blocks_[0]->peos->GetIsoSoundSpeed() : 0.0;
   if (flux == "hllc") cfg.rsolver = ATHK_RS_HLLC;
   else if (flux == "hlld") cfg.rsolver = ATHK_RS_HLLD;

@@ -62,6 +62,7 @@ static void BlastGenerator(MeshBlock *pmb, ParameterInput *pin) {
         u(IM2, k, j, i) = 0.0;
         u(IM3, k, j, i) = 0.0;
         if (NON_BAROTROPIC_EOS) u(IEN, k, j, i) = pres / gm1;
+        if (RELATIVISTIC_DYNAMICS) u(IEN, k, j, i) += den;   // blast.cpp:142-143
       }
   if (MAGNETIC_FIELDS_ENABLED) {
     FaceField &b = pmb->pfield->b;

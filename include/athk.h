@@ -43,7 +43,14 @@ enum athk_rsolver { ATHK_RS_HLLC = 0, ATHK_RS_HLLD = 1, ATHK_RS_ROE = 2, ATHK_RS
  * no energy equation; Riemann solvers HLLE for hydro (hlle.cpp, the reference's default) and HLLD
  * for MHD (hlld_iso.cpp).  Registers keep the adiabatic layout; the energy component stays zero and
  * upload / download of U, U1, U2, W move the NHYDRO = 4 components the reference has. */
-enum athk_eos { ATHK_EOS_ADIABATIC = 0, ATHK_EOS_ISOTHERMAL = 1 };
+enum athk_eos { ATHK_EOS_ADIABATIC = 0, ATHK_EOS_ISOTHERMAL = 1,
+                /* special-relativistic hydro (configure.py -s: eos/adiabatic_hydro_sr.cpp, hlle_rel.cpp):
+                 * w = (rho, u^1, u^2, u^3, pgas) with u^i the four-velocity's spatial components,
+                 * u = (D, M^1, M^2, M^3, E); rsolver HLLE, no magnetic fields, periodic uniform meshes;
+                 * the block time step is the smallest cell width (c = 1, new_blockdt.cpp:130).  W(U)
+                 * starts its iteration from W of two calls ago, like the reference's w / w1 swap
+                 * (time_integrator.cpp:2216-2269). */
+                ATHK_EOS_ADIABATIC_SR = 2 };
 
 /* ATHK_ARITH_STRICT: the reference's double-precision arithmetic operation by operation (no FMA
  * contraction, correctly rounded divisions and square roots): results identical to the CPU build.
@@ -65,6 +72,7 @@ typedef struct athk_config {
   double dfloor, pfloor, sfloor; /* floors; <=0 selects sqrt(1024*FLT_MIN) (eos.hpp:161) */
   int eos;             /* enum athk_eos: configure.py --eos                        */
   double iso_sound_speed; /* <hydro> iso_sound_speed (isothermal EOS)              */
+  double gamma_max;    /* <hydro> gamma_max (SR velocity ceiling); <=0 selects 1000 (eos.cpp)  */
 } athk_config;
 
 /* device-resident arrays addressable through upload/download */

@@ -38,6 +38,16 @@ def blast_blocks(n=32, blk=16, tlim=0.02):
     }
 
 
+def sr_blast_blocks(integrator="vl2", xorder=2):
+    b = blast_blocks(tlim=0.2)
+    b["output1"]["dt"] = 0.05
+    b["output2"]["dt"] = 0.1
+    b["time"].update(integrator=integrator, xorder=xorder)
+    b["problem"].update(prat=1.0e4, pamb=0.01)
+    del b["hydro"]["iso_sound_speed"]
+    return b
+
+
 def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     n = [8, 8, 8]
     n[shock_dir - 1] = 64
@@ -169,6 +179,12 @@ CASES = {
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025), 0.9), ["--eos=isothermal", "--flux=hlle"]),
     "iso_orszag_tang_llf_rk2": ("ot_iso_mhd_llf", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.05, rst_dt=0.025, integrator="rk2"), 0.9), ["--eos=isothermal", "--flux=llf"]),
+    # SURVEY 8(f).4, SR part: special-relativistic hydro (configure.py -s; adiabatic_hydro_sr.cpp's
+    # fixed-point W(U) started from W of two stages ago, hlle_rel.cpp, dt = cfl * min(dx)); a strong
+    # blast (pressure ratio 1e4), VL2 + PLM and RK3 + PLM
+    "sr_blast_hlle": ("blast_sr_hydro_hlle", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=hlle"]),
+    "sr_blast_hlle_rk3": ("blast_sr_hydro_hlle", "blast", False, lambda: sr_blast_blocks(
+        integrator="rk3"), ["-s", "--flux=hlle"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
     "iso_orszag_tang_rk3": ("ot_iso_mhd_hlld", "orszag_tang", True, lambda: iso(
@@ -397,7 +413,8 @@ def test_host_with_emulated_kernels_reproduces_reference_files(emul_binary, case
 
 @pytest.mark.parametrize("case", ["kh_rk3_ppm_scalar", "kh_vl2_plm_2scalars", "mhd_blast_roe",
                                   "blast_hydro_gravity_x3_reflect", "kh_mhd_gravity_all_axes", "jet_user_bc_mhd_rk3",
-                                  "user_source_mhd_vl2", "iso_kh_mhd_hlld_scalar", "iso_blast_hydro_reflecting_rk3"])
+                                  "user_source_mhd_vl2", "iso_kh_mhd_hlld_scalar", "iso_blast_hydro_reflecting_rk3",
+                                  "sr_blast_hlle"])
 def test_host_operator_sequence_reproduces_reference_files(emul_binary, case):
     # time/fused_stage=false: one C-ABI call per reference task instead of athk_stage()
     compare_with_reference(emul_binary, case, host_time_params={"fused_stage": "false"})
