@@ -13,6 +13,7 @@ ATHK_EXTERN_RS(athk::RS_LLF, false)
 ATHK_EXTERN_RS(athk::RS_LLF, true)
 ATHK_EXTERN_RS(athk::RS_HLLE_ISO, false)   // athk_rs_iso.cu
 ATHK_EXTERN_RS(athk::RS_HLLD_ISO, true)
+ATHK_EXTERN_RS(athk::RS_SR, false)         // athk_rs_sr.cu
 #ifndef ATHK_EMULATE
 ATHK_EXTERN_RS_FAST(athk::RS_HLLC, false)   // athk_fast.cu (--fmad=true)
 ATHK_EXTERN_RS_FAST(athk::RS_HLLD, true)
@@ -78,8 +79,9 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     return fail(ATHK_ERR_ARG, "athk_create: unknown eos %d", cfg->eos);
   if (cfg->eos == ATHK_EOS_ADIABATIC_SR) {   // configure.py -s
     if (cfg->mhd) return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented for hydro only (mhd = 0)");
-    if (cfg->rsolver != ATHK_RS_HLLE)
-      return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented with rsolver HLLE (hlle_rel.cpp)");
+    if (cfg->rsolver != ATHK_RS_HLLE && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_LLF)
+      return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented with rsolver HLLC, HLLE, LLF "
+                                "(hllc_rel.cpp, hlle_rel.cpp, llf_rel.cpp)");
     if (cfg->nscalars) return fail(ATHK_ERR_ARG, "athk_create: no passive scalars with special relativity");
     if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for special relativity");
   }
@@ -128,6 +130,7 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
   c->eos.iso_cs = cfg->iso_sound_speed;
   c->eos.sr = (cfg->eos == ATHK_EOS_ADIABATIC_SR) ? 1 : 0;
   c->eos.gamma_max = cfg->gamma_max > 0.0 ? cfg->gamma_max : 1000.0;
+  c->eos.sr_solver = cfg->rsolver;
   c->sf.nx1 = g.nx1; c->sf.nx2 = g.nx2; c->sf.nx3 = g.nx3;
   c->launches = 0;
   c->dt_requested = c->dt_valid = false;
@@ -679,6 +682,7 @@ extern "C" int athk_calculate_fluxes(athk_ctx *c, int order, double dt_mesh, int
   int rc = check_order(c, order, "calculate_fluxes");
   if (rc) return rc;
   const bool mhd = c->cfg.mhd != 0;
+  if (c->eos.sr) return athk_flux3_rs<RS_SR, false>(c, order, dt_mesh, breg);
   if (c->eos.iso && c->cfg.rsolver == (mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE))
     return mhd ? athk_flux3_rs<RS_HLLD_ISO, true>(c, order, dt_mesh, breg) : athk_flux3_rs<RS_HLLE_ISO, false>(c, order, dt_mesh, breg);
   switch (c->cfg.rsolver) {
@@ -1581,7 +1585,9 @@ extern "C" int athk_stage_phase(athk_ctx *c, int phase, int stage, int order,
       for (int d = 0; d < 3; ++d) a.mf[d] = c->sflux[d];
       a.mf_bstride = (idx_t)ns * g.sn;
     }
-    if (c->eos.iso && c->cfg.rsolver == (mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE)) {
+    if (c->eos.sr) {
+      rc = athk_sweeps_rs<RS_SR, false, 0>(c, order, a);
+    } else if (c->eos.iso && c->cfg.rsolver == (mhd ? ATHK_RS_HLLD : ATHK_RS_HLLE)) {
       rc = mhd ? athk_sweeps_rs<RS_HLLD_ISO, true, 0>(c, order, a) : athk_sweeps_rs<RS_HLLE_ISO, false, 0>(c, order, a);
     } else
     switch (c->cfg.rsolver) {

@@ -59,6 +59,7 @@ struct EosParams {
   // special relativity (configure.py -s, hydro): eos/adiabatic_hydro_sr.cpp.  w holds (rho, u^1, u^2,
   // u^3, pgas) with u^i the spatial components of the four-velocity; u holds (D, M^1, M^2, M^3, E).
   int sr;
+  int sr_solver;    // RS_HLLE, RS_HLLC or RS_LLF (hlle_rel.cpp, hllc_rel.cpp, llf_rel.cpp)
   Real gamma_max;   // <hydro> gamma_max (velocity ceiling, default 1000)
 };
 
@@ -88,6 +89,7 @@ ATHK_HD EosParams make_eos(Real gamma, Real dfloor, Real pfloor, Real sfloor) {
   e.iso = 0;
   e.iso_cs = 0.0;
   e.sr = 0;
+  e.sr_solver = 0;
   e.gamma_max = 1000.0;
   return e;
 }

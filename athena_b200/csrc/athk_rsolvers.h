@@ -16,13 +16,18 @@
 namespace athk {
 
 enum { RS_HLLC = 0, RS_HLLD = 1, RS_ROE = 2, RS_HLLE = 3, RS_LLF = 4,   // == enum athk_rsolver
-       RS_HLLE_ISO = 5, RS_HLLD_ISO = 6 };   // isothermal EOS: hlle.cpp's barotropic branch, hlld_iso.cpp
+       RS_HLLE_ISO = 5, RS_HLLD_ISO = 6,     // isothermal EOS: hlle.cpp's barotropic branch, hlld_iso.cpp
+       RS_SR = 7 };                          // special relativity: *_rel.cpp, chosen by eos.sr_solver
 
 //----------------------------------------------------------------------------------------
-// HLLE for special-relativistic hydro: hlle_rel.cpp:94-286 (HLLETransforming with GENERAL_RELATIVITY
-// == 0: no frame transformation, interface velocity 0).  wl / wr: (rho, u^x, u^y, u^z, pgas) in the
-// sweep's rotated order, u^i the four-velocity's spatial part.
-ATHK_HD void hlle_sr_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
+// Special-relativistic hydro (configure.py -s), GENERAL_RELATIVITY == 0: no frame transformation,
+// interface velocity 0.  wl / wr: (rho, u^x, u^y, u^z, pgas) in the sweep's rotated order, u^i the
+// four-velocity's spatial part.  eos.sr_solver selects
+//   HLLE  hlle_rel.cpp:94-286 (HLLETransforming)
+//   HLLC  hllc_rel.cpp:96-336 (HLLCTransforming; Mignone & Bodo 2005)
+//   LLF   llf_rel.cpp:93-215  (LLFTransforming)
+// which share the left / right states, their wave speeds (SoundSpeedsSR) and fluxes.
+ATHK_HD void sr_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
   const Real gamma_adi = eos.gamma;
   const Real gamma_prime = gamma_adi / (gamma_adi - 1.0);
   const Real rho_l = wl[IDN], pgas_l = wl[IPR];
@@ -61,24 +66,81 @@ ATHK_HD void hlle_sr_hydro_flux(const EosParams &eos, const Real wl[5], const Re
   flux_r[IVX] = wgas_r * u_r[1] * u_r[1] + pgas_r;
   flux_r[IVY] = wgas_r * u_r[2] * u_r[1];
   flux_r[IVZ] = wgas_r * u_r[3] * u_r[1];
-  const Real lambda_diff_inv = 1.0 / (lambda_r - lambda_l);
+  if (eos.sr_solver == RS_LLF) {
+    const Real lambda = max_std(lambda_r, -lambda_l);
+#pragma unroll
+    for (int n = 0; n < 5; ++n) f[n] = 0.5 * (flux_l[n] + flux_r[n] - lambda * (cons_r[n] - cons_l[n]));
+    return;
+  }
+  Real lambda_diff_inv = 1.0 / (lambda_r - lambda_l);
+  Real flux_hll[5];
+#pragma unroll
+  for (int n = 0; n < 5; ++n)
+    flux_hll[n] = (lambda_r * flux_l[n] - lambda_l * flux_r[n] + lambda_l * lambda_r * (cons_r[n] - cons_l[n])) *
+                  lambda_diff_inv;
+  if (eos.sr_solver == RS_HLLE) {
+    if (lambda_l >= 0.0) {
+#pragma unroll
+      for (int n = 0; n < 5; ++n) f[n] = flux_l[n];
+    } else if (lambda_r <= 0.0) {
+#pragma unroll
+      for (int n = 0; n < 5; ++n) f[n] = flux_r[n];
+    } else {
+#pragma unroll
+      for (int n = 0; n < 5; ++n) f[n] = flux_hll[n];
+    }
+    return;
+  }
+  // HLLC
+  Real cons_hll[5];
+#pragma unroll
+  for (int n = 0; n < 5; ++n)
+    cons_hll[n] = (lambda_r * cons_r[n] - lambda_l * cons_l[n] + flux_l[n] - flux_r[n]) * lambda_diff_inv;
+  Real lambda_star;
+  const Real b = -(cons_hll[IEN] + flux_hll[IVX]);
+  if (fabs(flux_hll[IEN]) > ATHK_TINY_NUMBER) {
+    lambda_star = -2.0 * cons_hll[IVX] / (b - sqrt(sqr(b) - 4.0 * flux_hll[IEN] * cons_hll[IVX]));
+  } else {
+    lambda_star = -cons_hll[IVX] / b;
+  }
+  const Real pgas_star = -flux_hll[IEN] * lambda_star + flux_hll[IVX];
   if (lambda_l >= 0.0) {
 #pragma unroll
     for (int n = 0; n < 5; ++n) f[n] = flux_l[n];
   } else if (lambda_r <= 0.0) {
 #pragma unroll
     for (int n = 0; n < 5; ++n) f[n] = flux_r[n];
-  } else {
+  } else if (lambda_star >= 0.0) {   // aL region (MB2005 16, 14)
+    Real cons_lstar[5];
+    const Real vx_l_ratio = u_l[1] / u_l[0];
+    lambda_diff_inv = 1.0 / (lambda_l - lambda_star);
 #pragma unroll
-    for (int n = 0; n < 5; ++n)
-      f[n] = (lambda_r * flux_l[n] - lambda_l * flux_r[n] + lambda_l * lambda_r * (cons_r[n] - cons_l[n])) *
-             lambda_diff_inv;
+    for (int n = 0; n < 5; ++n) cons_lstar[n] = cons_l[n] * (lambda_l - vx_l_ratio);
+    cons_lstar[IEN] += pgas_star * lambda_star - pgas_l * vx_l_ratio;
+    cons_lstar[IVX] += pgas_star - pgas_l;
+#pragma unroll
+    for (int n = 0; n < 5; ++n) {
+      cons_lstar[n] *= lambda_diff_inv;
+      f[n] = flux_l[n] + lambda_l * (cons_lstar[n] - cons_l[n]);
+    }
+  } else {                           // c region
+    Real cons_rstar[5];
+    const Real vx_r_ratio = u_r[1] / u_r[0];
+    lambda_diff_inv = 1.0 / (lambda_r - lambda_star);
+#pragma unroll
+    for (int n = 0; n < 5; ++n) cons_rstar[n] = cons_r[n] * (lambda_r - vx_r_ratio);
+    cons_rstar[IEN] += pgas_star * lambda_star - pgas_r * vx_r_ratio;
+    cons_rstar[IVX] += pgas_star - pgas_r;
+#pragma unroll
+    for (int n = 0; n < 5; ++n) {
+      cons_rstar[n] *= lambda_diff_inv;
+      f[n] = flux_r[n] + lambda_r * (cons_rstar[n] - cons_r[n]);
+    }
   }
 }
 
 //----------------------------------------------------------------------------------------
 ATHK_HD void hlle_hydro_flux(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
-  if (eos.sr) { hlle_sr_hydro_flux(eos, wl, wr, f); return; }
   const Real gm1 = eos.gm1;
   const Real igm1 = 1.0 / gm1;
   Real wroe[5], fl[5], fr[5];
@@ -1062,6 +1124,7 @@ constexpr int default_rsolver(bool mhd) { return mhd ? RS_HLLD : RS_HLLC; }
 template <int RS>
 ATHK_HD void hydro_riemann(const EosParams &eos, const Real wl[5], const Real wr[5], Real f[5]) {
   if (RS == RS_HLLE) hlle_hydro_flux(eos, wl, wr, f);
+  else if (RS == RS_SR) sr_hydro_flux(eos, wl, wr, f);
   else if (RS == RS_HLLE_ISO) hlle_iso_hydro_flux(eos, wl, wr, f);
   else if (RS == RS_ROE) roe_hydro_flux(eos, wl, wr, f);
   else if (RS == RS_LLF) llf_hydro_flux(eos, wl, wr, f);

@@ -56,6 +56,8 @@ CONFIGS = {
     "ot_iso_mhd_hlle": dict(PROB="orszag_tang", MHD=1, FLUX="hlle", EOS="isothermal"),
     "ot_iso_mhd_llf": dict(PROB="orszag_tang", MHD=1, FLUX="llf", EOS="isothermal"),
     "blast_sr_hydro_hlle": dict(PROB="blast", MHD=0, FLUX="hlle", SR=1),   # configure.py -s (SR part)
+    "blast_sr_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc", SR=1),   # (-s default flux)
+    "blast_sr_hydro_llf": dict(PROB="blast", MHD=0, FLUX="llf", SR=1),
     "ot_iso_mhd_roe": dict(PROB="orszag_tang", MHD=1, FLUX="roe", EOS="isothermal"),
     "ot_iso_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld", EOS="isothermal"),   # (blast.cpp:208 writes
     # u(IEN) unguarded with -b: the reference's own blast problem cannot run isothermal MHD)

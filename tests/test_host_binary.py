@@ -185,6 +185,10 @@ CASES = {
     "sr_blast_hlle": ("blast_sr_hydro_hlle", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=hlle"]),
     "sr_blast_hlle_rk3": ("blast_sr_hydro_hlle", "blast", False, lambda: sr_blast_blocks(
         integrator="rk3"), ["-s", "--flux=hlle"]),
+    "sr_blast_hllc": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_blast_blocks(), ["-s"]),   # -s default: hllc
+    "sr_blast_hllc_rk2": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_blast_blocks(integrator="rk2"),
+                          ["-s", "--flux=hllc"]),
+    "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
     "iso_orszag_tang_rk3": ("ot_iso_mhd_hlld", "orszag_tang", True, lambda: iso(
