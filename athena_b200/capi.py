@@ -15,13 +15,13 @@ ARRAYS = dict(
     U=0, U1=1, U2=2, W=3, BCC=4, B_X1F=5, B_X2F=6, B_X3F=7, B1_X1F=8, B1_X2F=9, B1_X3F=10,
     B2_X1F=11, B2_X2F=12, B2_X3F=13, FLUX_X1=14, FLUX_X2=15, FLUX_X3=16, E_X1E=17, E_X2E=18,
     E_X3E=19, E3_X1F=20, E2_X1F=21, E1_X2F=22, E3_X2F=23, E2_X3F=24, E1_X3F=25, WGHT_X1F=26,
-    WGHT_X2F=27, WGHT_X3F=28, S=29, S1=30, S2=31, R=32, SFLUX_X1=33, SFLUX_X2=34, SFLUX_X3=35)
+    WGHT_X2F=27, WGHT_X3F=28, S=29, S1=30, S2=31, R=32, SFLUX_X1=33, SFLUX_X2=34, SFLUX_X3=35, W1=36)
 RS_HLLC, RS_HLLD, RS_ROE, RS_HLLE, RS_LLF = range(5)
 ARITH_STRICT, ARITH_FAST = 0, 1
 
 # (nvar, a1, a2, a3): host shape = (nvar, nc3+a3, nc2+a2, nc1+a1); nvar None = nscalars
 SHAPES = {}
-for _n in ("U", "U1", "U2", "W"):
+for _n in ("U", "U1", "U2", "W", "W1"):
     SHAPES[_n] = (5, 0, 0, 0)
 SHAPES["BCC"] = (3, 0, 0, 0)
 for _p in ("B", "B1", "B2"):

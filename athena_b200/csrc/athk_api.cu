@@ -342,6 +342,7 @@ static bool describe(athk_ctx *c, int array, ArrDesc *d) {
     case ATHK_U: case ATHK_U1: case ATHK_U2:
       *d = {c->u[array - ATHK_U], 5, 0, c->eos.iso ? 4 : 5, 0, 0, 0}; break;
     case ATHK_W: *d = {c->w, 5, 0, c->eos.iso ? 4 : 5, 0, 0, 0}; break;
+    case ATHK_W1: if (!c->w_alt) return false; *d = {c->w_alt, 5, 0, 5, 0, 0, 0}; break;
     case ATHK_BCC: *d = {c->bcc, 3, 0, 3, 0, 0, 0}; break;
     case ATHK_B_X1F: case ATHK_B_X2F: case ATHK_B_X3F: {
       const int q = array - ATHK_B_X1F;
@@ -1043,8 +1044,6 @@ extern "C" int athk_set_boundary_flags(athk_ctx *c, int lb, const int flags[6]) 
     if (flags[f] < ATHK_BC_NONE || flags[f] > ATHK_BC_USER)
       return fail(ATHK_ERR_ARG, "set_boundary_flags: face %d has unknown flag %d (reflecting, outflow, user or none)",
                   f, flags[f]);
-    if (c->eos.sr && flags[f] != ATHK_BC_NONE)
-      return fail(ATHK_ERR_ARG, "set_boundary_flags: physical boundaries are not implemented with special relativity");
     c->h_bcflags[(size_t)lb * 6 + f] = flags[f];
   }
   c->bc_dirty = true;

@@ -129,6 +129,17 @@ struct PhysBCConsPoint {
     const Real w_d = wb[0], w_vx = wb[g.sn], w_vy = wb[2 * g.sn], w_vz = wb[3 * g.sn], w_p = wb[4 * g.sn];
     const Real igm1 = 1.0 / eos.gm1;
     Real *ub = u + (idx_t)blk * 5 * g.sn + c;
+    if (eos.sr) {   // EquationOfState::PrimitiveToConserved, adiabatic_hydro_sr.cpp:229-262
+      const Real gamma_prime = eos.gamma / (eos.gamma - 1.0);
+      const Real u0 = sqrt(1.0 + sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
+      const Real wgas_u0 = (w_d + gamma_prime * w_p) * u0;
+      ub[0] = w_d * u0;
+      ub[4 * g.sn] = wgas_u0 * u0 - w_p;
+      ub[g.sn] = wgas_u0 * w_vx;
+      ub[2 * g.sn] = wgas_u0 * w_vy;
+      ub[3 * g.sn] = wgas_u0 * w_vz;
+      return;
+    }
     ub[0] = w_d;
     ub[g.sn] = w_vx * w_d;
     ub[2 * g.sn] = w_vy * w_d;

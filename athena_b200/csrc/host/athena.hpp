@@ -176,6 +176,7 @@ class Hydro {   // hydro/hydro.hpp:32-122 (host mirrors only)
  public:
   explicit Hydro(MeshBlock *pmb);
   AthenaArray<Real> u, w;
+  AthenaArray<Real> w1;   // (RELATIVISTIC_DYNAMICS only: what a pgen leaves here seeds the second W(U))
 };
 class Field {   // field/field.hpp:30-75
  public:

@@ -89,6 +89,7 @@ Coordinates::Coordinates(MeshBlock *pmb, Mesh *pm, bool coarse) {
 Hydro::Hydro(MeshBlock *pmb) {
   u.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
   w.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+  if (RELATIVISTIC_DYNAMICS) w1.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
 }
 Field::Field(MeshBlock *pmb) {
   if (!MAGNETIC_FIELDS_ENABLED) return;
@@ -549,6 +550,13 @@ void Mesh::Initialize(ParameterInput *pin) {
       AthkCheck(athk_upload(a, ATHK_B_X3F, l, pmb->pfield->b.x3f.data()), "Mesh::Initialize");
     }
     if (NSCALARS > 0) AthkCheck(athk_upload(a, ATHK_S, l, pmb->pscalars->s.data()), "Mesh::Initialize");
+    if (RELATIVISTIC_DYNAMICS && !res_flag) {
+      // what the pgen left in w / w1 seeds the fixed-point W(U).  The first W(U) (below) writes Hydro::w
+      // (mesh.cpp:1833), the next one Hydro::w1 (time_integrator.cpp:2221); the device always writes the
+      // array ATHK_W1 names and then swaps the two names
+      AthkCheck(athk_upload(a, ATHK_W1, l, pmb->phydro->w.data()), "Mesh::Initialize");
+      AthkCheck(athk_upload(a, ATHK_W, l, pmb->phydro->w1.data()), "Mesh::Initialize");
+    }
   }
   for (athk_ctx *a : ctx) AthkCheck(athk_sync(a), "Mesh::Initialize");
   ExchangeGhosts();

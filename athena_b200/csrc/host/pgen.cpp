@@ -388,6 +388,74 @@ static void ShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
   }
 }
 
+// gr_shock_tube (pgen/gr_shock_tube.cpp:45-330, the special-relativistic hydro branch: Minkowski
+// coordinates, no fields): left / right states given by 3-velocities, stored as four-velocity
+// components in w AND w1 (both seed the fixed-point W(U)), then PrimitiveToConserved
+// (adiabatic_hydro_sr.cpp:229-262) on the active zone.
+static void GRShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
+  std::stringstream msg;
+  if (!RELATIVISTIC_DYNAMICS || MAGNETIC_FIELDS_ENABLED) {
+    msg << "### FATAL ERROR in Problem Generator" << std::endl
+        << "gr_shock_tube: the B200 host implements the special-relativistic hydro branch (configure with -s, no -b)";
+    ATHENA_ERROR(msg);
+  }
+  const Real gamma_adi = pmb->peos->GetGamma();
+  const Real gamma_prime = gamma_adi / (gamma_adi - 1.0);
+  const int shock_dir = pin->GetInteger("problem", "shock_dir");
+  const Real shock_pos = pin->GetReal("problem", "xshock");
+  Real min_bound = 0.0, max_bound = 0.0;
+  const RegionSize &ms = pmb->pmy_mesh->mesh_size;
+  switch (shock_dir) {
+    case 1: min_bound = ms.x1min; max_bound = ms.x1max; break;
+    case 2: min_bound = ms.x2min; max_bound = ms.x2max; break;
+    case 3: min_bound = ms.x3min; max_bound = ms.x3max; break;
+    default:
+      msg << "### FATAL ERROR in Problem Generator\n"
+          << "shock_dir=" << shock_dir << " must be either 1, 2, or 3" << std::endl;
+      ATHENA_ERROR(msg);
+  }
+  if (shock_pos < min_bound || shock_pos > max_bound) {
+    msg << "### FATAL ERROR in Problem Generator\n"
+        << "xshock=" << shock_pos << " lies outside x" << shock_dir << " domain for shkdir=" << shock_dir << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  const Real rho_left = pin->GetReal("problem", "dl"), pgas_left = pin->GetReal("problem", "pl");
+  const Real vx_left = pin->GetReal("problem", "ul"), vy_left = pin->GetReal("problem", "vl"),
+             vz_left = pin->GetReal("problem", "wl");
+  const Real rho_right = pin->GetReal("problem", "dr"), pgas_right = pin->GetReal("problem", "pr");
+  const Real vx_right = pin->GetReal("problem", "ur"), vy_right = pin->GetReal("problem", "vr"),
+             vz_right = pin->GetReal("problem", "wr");
+  Coordinates *pc = pmb->pcoord;
+  AthenaArray<Real> &u = pmb->phydro->u, &w = pmb->phydro->w, &w1 = pmb->phydro->w1;
+  for (int k = pmb->ks; k <= pmb->ke; ++k)
+    for (int j = pmb->js; j <= pmb->je; ++j)
+      for (int i = pmb->is; i <= pmb->ie; ++i) {
+        bool left_side = false;
+        switch (shock_dir) {
+          case 1: left_side = pc->x1v(i) < shock_pos; break;
+          case 2: left_side = pc->x2v(j) < shock_pos; break;
+          case 3: left_side = pc->x3v(k) < shock_pos; break;
+        }
+        const Real rho = left_side ? rho_left : rho_right, pgas = left_side ? pgas_left : pgas_right;
+        const Real vx = left_side ? vx_left : vx_right, vy = left_side ? vy_left : vy_right,
+                   vz = left_side ? vz_left : vz_right;
+        const Real ut = std::sqrt(1.0 / (1.0 - (SQR(vx) + SQR(vy) + SQR(vz))));
+        const Real ux = ut * vx, uy = ut * vy, uz = ut * vz;
+        w(IDN, k, j, i) = w1(IDN, k, j, i) = rho;
+        w(IPR, k, j, i) = w1(IPR, k, j, i) = pgas;
+        w(IVX, k, j, i) = w1(IM1, k, j, i) = ux;
+        w(IVY, k, j, i) = w1(IM2, k, j, i) = uy;
+        w(IVZ, k, j, i) = w1(IM3, k, j, i) = uz;
+        const Real u0 = std::sqrt(1.0 + SQR(ux) + SQR(uy) + SQR(uz));
+        const Real wgas_u0 = (rho + gamma_prime * pgas) * u0;
+        u(IDN, k, j, i) = rho * u0;
+        u(IEN, k, j, i) = wgas_u0 * u0 - pgas;
+        u(IM1, k, j, i) = wgas_u0 * ux;
+        u(IM2, k, j, i) = wgas_u0 * uy;
+        u(IM3, k, j, i) = wgas_u0 * uz;
+      }
+}
+
 // Errors against the exact solutions the reference tabulates (shock_tube.cpp:46-270): Sod's tube
 // for hydro, the Ryu & Jones 2a tube for MHD, both at t = tlim with the discontinuity at 0.  As in
 // the reference only the first MeshBlock is summed and its extents are what the row reports.
@@ -1266,6 +1334,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"orszag_tang", nullptr, OrszagTangGenerator, nullptr},
     {"kh", KHInitUserMeshData, KHGenerator, nullptr},
     {"shock_tube", nullptr, ShockTubeGenerator, ShockTubeErrors},
+    {"gr_shock_tube", nullptr, GRShockTubeGenerator, nullptr},
     {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
     {"field_loop", nullptr, FieldLoopGenerator, nullptr},
     {"jet", jet::JetInit, jet::JetGenerator, nullptr},

@@ -90,7 +90,9 @@ enum athk_array {
   ATHK_WGHT_X1F = 26, ATHK_WGHT_X2F = 27, ATHK_WGHT_X3F = 28, /* Field::wght                      */
   ATHK_S = 29, ATHK_S1 = 30, ATHK_S2 = 31, ATHK_R = 32, /* PassiveScalars::s,s1,s2,r              */
   ATHK_SFLUX_X1 = 33, ATHK_SFLUX_X2 = 34, ATHK_SFLUX_X3 = 35,
-  ATHK_NARRAYS = 36
+  ATHK_W1 = 36,   /* Hydro::w1 with ATHK_EOS_ADIABATIC_SR: the array the next W(U) writes -- what it holds
+                   * is that call's fallback state and first guess (a pgen may set it, gr_shock_tube.cpp) */
+  ATHK_NARRAYS = 37
 };
 
 /* time-integrator registers (u,b,s move together only if the caller says so) */

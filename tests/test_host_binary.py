@@ -48,6 +48,36 @@ def sr_blast_blocks(integrator="vl2", xorder=2):
     return b
 
 
+SR_TUBES = {   # inputs/hydro_sr/athinput.mb_N: (gamma, dl, pl, ul, vl, wl, dr, pr, ur, vr, wr)
+    1: (1.3333333333333333, 1.0, 1.0, 0.9, 0.0, 0.0, 1.0, 10.0, 0.0, 0.0, 0.0),
+    2: (1.6666666666666667, 1.0, 10.0, -0.6, 0.0, 0.0, 10.0, 20.0, 0.5, 0.0, 0.0),
+    4: (1.6666666666666667, 1.0, 1.0e3, 0.0, 0.0, 0.0, 1.0, 1.0e-2, 0.0, 0.0, 0.0),
+}
+
+
+def sr_tube_blocks(which, shock_dir, integrator="vl2"):
+    gam, dl, pl, ul, vl, wl, dr, pr, ur, vr, wr = SR_TUBES[which]
+    n = [8, 8, 8]
+    n[shock_dir - 1] = 64
+    blk = [8, 8, 8]
+    blk[shock_dir - 1] = 16
+    bc = ["periodic"] * 3
+    bc[shock_dir - 1] = "outflow"
+    return {
+        "job": {"problem_id": "srtube"},
+        "output1": {"file_type": "hst", "dt": 0.1, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": 0.2},
+        "time": {"cfl_number": 0.4, "nlim": -1, "tlim": 0.4, "integrator": integrator, "xorder": 2, "ncycle_out": 1},
+        "mesh": {"nx1": n[0], "x1min": -0.5, "x1max": 0.5, "ix1_bc": bc[0], "ox1_bc": bc[0],
+                 "nx2": n[1], "x2min": -0.5, "x2max": 0.5, "ix2_bc": bc[1], "ox2_bc": bc[1],
+                 "nx3": n[2], "x3min": -0.5, "x3max": 0.5, "ix3_bc": bc[2], "ox3_bc": bc[2], "num_threads": 1},
+        "meshblock": {"nx1": blk[0], "nx2": blk[1], "nx3": blk[2]},
+        "hydro": {"gamma": gam},
+        "problem": {"shock_dir": shock_dir, "xshock": 0.0, "dl": dl, "pl": pl, "ul": ul, "vl": vl, "wl": wl,
+                    "dr": dr, "pr": pr, "ur": ur, "vr": vr, "wr": wr},
+    }
+
+
 def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     n = [8, 8, 8]
     n[shock_dir - 1] = 64
@@ -188,6 +218,12 @@ CASES = {
     "sr_blast_hllc": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_blast_blocks(), ["-s"]),   # -s default: hllc
     "sr_blast_hllc_rk2": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_blast_blocks(integrator="rk2"),
                           ["-s", "--flux=hllc"]),
+    # the reference's own SR regression problems (tst/regression/scripts/tests/sr/hydro_shocks_*.py:
+    # inputs/hydro_sr/athinput.mb_1, mb_2, mb_4 -- Mignone & Bodo 2005 tubes, inflow at 0.9c, pressure ratio 1e5), as 3-D slabs with outflow walls along the tube: the pgen seeds w and w1, the walls
+    # go through the SR U(W) on the ghost slabs
+    "sr_tube_mb1_x1": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(1, 1), ["-s"]),
+    "sr_tube_mb2_x2": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(2, 2), ["-s"]),
+    "sr_tube_mb4_x3_rk3": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(4, 3, "rk3"), ["-s"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
