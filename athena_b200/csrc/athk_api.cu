@@ -82,7 +82,6 @@ extern "C" int athk_create(const athk_config *cfg, athk_ctx **out) {
     if (cfg->rsolver != ATHK_RS_HLLE && cfg->rsolver != ATHK_RS_HLLC && cfg->rsolver != ATHK_RS_LLF)
       return fail(ATHK_ERR_ARG, "athk_create: special relativity is implemented with rsolver HLLC, HLLE, LLF "
                                 "(hllc_rel.cpp, hlle_rel.cpp, llf_rel.cpp)");
-    if (cfg->nscalars) return fail(ATHK_ERR_ARG, "athk_create: no passive scalars with special relativity");
     if (cfg->arith == ATHK_ARITH_FAST) return fail(ATHK_ERR_ARG, "athk_create: no fast-arithmetic set for special relativity");
   }
   if (cfg->eos == ATHK_EOS_ISOTHERMAL) {

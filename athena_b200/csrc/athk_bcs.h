@@ -138,6 +138,10 @@ struct PhysBCConsPoint {
       ub[g.sn] = wgas_u0 * w_vx;
       ub[2 * g.sn] = wgas_u0 * w_vy;
       ub[3 * g.sn] = wgas_u0 * w_vz;
+      for (int n = 0; n < ns; ++n) {   // PassiveScalarPrimitiveToConserved: s = r * u(IDN), eos_scalars.cpp:96-112
+        const idx_t o = ((idx_t)blk * ns + n) * g.sn + c;
+        s[o] = r[o] * (w_d * u0);
+      }
       return;
     }
     ub[0] = w_d;

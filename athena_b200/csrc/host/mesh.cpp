@@ -350,8 +350,10 @@ Mesh::Mesh(ParameterInput *pin) : athk(nullptr) {
   // the 6-digit strings the first one stored (see ParameterInput::GetOrAddReal)
   for (int n = 0; n < nblocal; ++n) {
     const EquationOfState *pe = blocks_[n]->peos;
+    // (sfloor = 0, as the reference's SR inputs set it, is not expressible in athk_config, where <= 0
+    //  selects the default)
     if (pe->GetDensityFloor() != cfg.dfloor || pe->GetPressureFloor() != cfg.pfloor ||
-        pe->GetScalarFloor() != cfg.sfloor)
+        pe->GetScalarFloor() != cfg.sfloor || !(cfg.sfloor > 0.0))
       AthkCheck(athk_set_block_floors(ctx_of(blocks_[n]), blocks_[n]->lid, pe->GetDensityFloor(),
                                       pe->GetPressureFloor(), pe->GetScalarFloor()),
                 "Mesh constructor (athk_set_block_floors)");

@@ -453,6 +453,10 @@ static void GRShockTubeGenerator(MeshBlock *pmb, ParameterInput *pin) {
         u(IM1, k, j, i) = wgas_u0 * ux;
         u(IM2, k, j, i) = wgas_u0 * uy;
         u(IM3, k, j, i) = wgas_u0 * uz;
+        if (NSCALARS > 0) {   // (gr_shock_tube.cpp:211-213, then PassiveScalarPrimitiveToConserved)
+          pmb->pscalars->r(0, k, j, i) = left_side ? 0.0 : 1.0;
+          for (int n = 0; n < NSCALARS; ++n) pmb->pscalars->s(n, k, j, i) = pmb->pscalars->r(n, k, j, i) * u(IDN, k, j, i);
+        }
       }
 }
 

@@ -46,7 +46,7 @@ enum athk_rsolver { ATHK_RS_HLLC = 0, ATHK_RS_HLLD = 1, ATHK_RS_ROE = 2, ATHK_RS
 enum athk_eos { ATHK_EOS_ADIABATIC = 0, ATHK_EOS_ISOTHERMAL = 1,
                 /* special-relativistic hydro (configure.py -s: eos/adiabatic_hydro_sr.cpp, hlle_rel.cpp):
                  * w = (rho, u^1, u^2, u^3, pgas) with u^i the four-velocity's spatial components,
-                 * u = (D, M^1, M^2, M^3, E); rsolver HLLE, no magnetic fields, periodic uniform meshes;
+                 * u = (D, M^1, M^2, M^3, E); rsolver HLLC, HLLE or LLF, no magnetic fields, uniform meshes;
                  * the block time step is the smallest cell width (c = 1, new_blockdt.cpp:130).  W(U)
                  * starts its iteration from W of two calls ago, like the reference's w / w1 swap
                  * (time_integrator.cpp:2216-2269). */

@@ -55,7 +55,7 @@ SR_TUBES = {   # inputs/hydro_sr/athinput.mb_N: (gamma, dl, pl, ul, vl, wl, dr, 
 }
 
 
-def sr_tube_blocks(which, shock_dir, integrator="vl2"):
+def sr_tube_blocks(which, shock_dir, integrator="vl2", sfloor=None):
     gam, dl, pl, ul, vl, wl, dr, pr, ur, vr, wr = SR_TUBES[which]
     n = [8, 8, 8]
     n[shock_dir - 1] = 64
@@ -72,7 +72,7 @@ def sr_tube_blocks(which, shock_dir, integrator="vl2"):
                  "nx2": n[1], "x2min": -0.5, "x2max": 0.5, "ix2_bc": bc[1], "ox2_bc": bc[1],
                  "nx3": n[2], "x3min": -0.5, "x3max": 0.5, "ix3_bc": bc[2], "ox3_bc": bc[2], "num_threads": 1},
         "meshblock": {"nx1": blk[0], "nx2": blk[1], "nx3": blk[2]},
-        "hydro": {"gamma": gam},
+        "hydro": {"gamma": gam} if sfloor is None else {"gamma": gam, "sfloor": sfloor},
         "problem": {"shock_dir": shock_dir, "xshock": 0.0, "dl": dl, "pl": pl, "ul": ul, "vl": vl, "wl": wl,
                     "dr": dr, "pr": pr, "ur": ur, "vr": vr, "wr": wr},
     }
@@ -224,6 +224,8 @@ CASES = {
     "sr_tube_mb1_x1": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(1, 1), ["-s"]),
     "sr_tube_mb2_x2": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(2, 2), ["-s"]),
     "sr_tube_mb4_x3_rk3": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(4, 3, "rk3"), ["-s"]),
+    "sr_tube_mb2_x1_scalar_hlle_rk2": ("grtube_sr_hydro_hlle_s1", "gr_shock_tube", False, lambda: sr_tube_blocks(2, 1, "rk2", sfloor=0.0),
+                                       ["-s", "--flux=hlle", "--nscalars=1"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
