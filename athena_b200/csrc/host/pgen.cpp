@@ -1332,6 +1332,183 @@ void Generator(MeshBlock *pmb, ParameterInput *pin) {
 }  // namespace usrsrc
 
 //========================================================================================
+// gr_linear_wave (pgen/gr_linear_wave.cpp, the special-relativistic HYDRO branch: Minkowski
+// coordinates, no fields): a linear wave along x1 on a moving background -- InitUserMeshData
+// :76-433 (eigen-perturbations of Falle & Komissarov), ProblemGenerator :560-849 (w, w1 and u on
+// the whole box, ghost zones included), UserWorkAfterLoop :441-547 (L1 distance from the initial
+// state, appended to linearwave-errors.dat under problem/compute_error).
+namespace grlw {
+static Real amp, gamma_adi_red, rho, pgas, vx, vy, vz, u[4], delta_rho, delta_pgas, delta_u[4], delta_v[4], lambda;
+static bool compute_error;
+static std::vector<AthenaArray<Real>> initial;   // [lid](NHYDRO, k, j, i)
+
+static void Init(Mesh *pm, ParameterInput *pin) {
+  std::stringstream msg;
+  if (!RELATIVISTIC_DYNAMICS || MAGNETIC_FIELDS_ENABLED) {
+    msg << "### FATAL ERROR in Problem Generator" << std::endl
+        << "gr_linear_wave: the B200 host implements the special-relativistic hydro branch (configure with -s, no -b)";
+    ATHENA_ERROR(msg);
+  }
+  const int wave_flag = pin->GetInteger("problem", "wave_flag");
+  if (wave_flag < 0 || wave_flag > NWAVE - 1) {
+    msg << "### FATAL ERROR in Problem Generator\n"
+        << "wave_flag=" << wave_flag << " must be between 0 and " << NWAVE - 1 << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  amp = pin->GetReal("problem", "amp");
+  compute_error = pin->GetOrAddBoolean("problem", "compute_error", false);
+  const Real gamma_adi = pin->GetReal("hydro", "gamma");
+  gamma_adi_red = gamma_adi / (gamma_adi - 1.0);
+  rho = pin->GetReal("problem", "rho");
+  pgas = pin->GetReal("problem", "pgas");
+  vx = pin->GetReal("problem", "vx");
+  vy = pin->GetReal("problem", "vy");
+  vz = pin->GetReal("problem", "vz");
+  const Real v_sq = SQR(vx) + SQR(vy) + SQR(vz);
+  u[0] = 1.0 / std::sqrt(1.0 - v_sq);
+  u[1] = u[0] * vx;
+  u[2] = u[0] * vy;
+  u[3] = u[0] * vz;
+  const Real wgas = rho + gamma_adi_red * pgas;
+  const Real cs_sq = gamma_adi * pgas / wgas;
+  const Real cs = std::sqrt(cs_sq);
+  switch (wave_flag) {
+    case 1:
+      lambda = vx; delta_rho = 1.0; delta_pgas = 0.0;
+      delta_u[1] = delta_u[2] = delta_u[3] = 0.0;
+      break;
+    case 2:
+      lambda = vx; delta_rho = 0.0; delta_pgas = 0.0;
+      delta_u[1] = vx * vy / (1.0 - SQR(vx)); delta_u[2] = 1.0; delta_u[3] = 0.0;
+      break;
+    case 3:
+      lambda = vx; delta_rho = 0.0; delta_pgas = 0.0;
+      delta_u[1] = vx * vz / (1.0 - SQR(vx)); delta_u[2] = 0.0; delta_u[3] = 1.0;
+      break;
+    default: {
+      const Real delta = SQR(u[0]) * (1.0 - cs_sq) + cs_sq;
+      const Real v_minus_lambda_a = vx * cs_sq;
+      const Real v_minus_lambda_b = cs * std::sqrt(SQR(u[0]) * (1.0 - cs_sq) * (1.0 - SQR(vx)) + cs_sq);
+      Real v_minus_lambda;
+      if (wave_flag == 0) v_minus_lambda = (v_minus_lambda_a + v_minus_lambda_b) / delta;
+      else v_minus_lambda = (v_minus_lambda_a - v_minus_lambda_b) / delta;
+      lambda = vx - v_minus_lambda;
+      delta_rho = rho;
+      delta_pgas = wgas * cs_sq;
+      delta_u[1] = -cs_sq * u[1] - cs_sq / u[0] / v_minus_lambda;
+      delta_u[2] = -cs_sq * u[2];
+      delta_u[3] = -cs_sq * u[3];
+    }
+  }
+  delta_v[1] = (1.0 - SQR(vx)) * delta_u[1] - vx * vy * delta_u[2] - vx * vz * delta_u[3];
+  delta_v[2] = -vx * vy * delta_u[1] + (1.0 - SQR(vy)) * delta_u[2] - vy * vz * delta_u[3];
+  delta_v[3] = -vx * vz * delta_u[1] - vy * vz * delta_u[2] + (1.0 - SQR(vz)) * delta_u[3];
+  for (int i = 1; i < 4; ++i) delta_v[i] /= u[0];
+  Real perturbation_size = SQR(delta_rho) + SQR(delta_pgas);
+  for (int i = 1; i < 4; ++i) perturbation_size += SQR(delta_v[i]);
+  perturbation_size = std::sqrt(perturbation_size);
+  delta_rho /= perturbation_size;
+  delta_pgas /= perturbation_size;
+  for (int i = 1; i < 4; ++i) delta_v[i] /= perturbation_size;
+  initial.clear();
+  initial.resize(pm->nblocal);
+}
+
+static void Generator(MeshBlock *pmb, ParameterInput *pin) {
+  const int il = pmb->is - NGHOST, iu = pmb->ie + NGHOST;
+  int jl = pmb->js, ju = pmb->je, kl = pmb->ks, ku = pmb->ke;
+  if (pmb->block_size.nx2 > 1) { jl -= NGHOST; ju += NGHOST; }
+  if (pmb->block_size.nx3 > 1) { kl -= NGHOST; ku += NGHOST; }
+  const Real arg_min = pmb->pmy_mesh->mesh_size.x1min, arg_max = pmb->pmy_mesh->mesh_size.x1max;
+  const Real wavenumber = TWO_PI / (arg_max - arg_min);
+  AthenaArray<Real> &uu = pmb->phydro->u, &w = pmb->phydro->w, &w1 = pmb->phydro->w1;
+  for (int k = kl; k <= ku; ++k)
+    for (int j = jl; j <= ju; ++j)
+      for (int i = il; i <= iu; ++i) {
+        const Real t = 0.0, x = pmb->pcoord->x1v(i);
+        const Real local_amp = amp * std::sin(wavenumber * (x - lambda * t));
+        const Real rho_local = rho + local_amp * delta_rho;
+        const Real pgas_local = pgas + local_amp * delta_pgas;
+        const Real vx_mink = vx + local_amp * delta_v[1];
+        const Real vy_mink = vy + local_amp * delta_v[2];
+        const Real vz_mink = vz + local_amp * delta_v[3];
+        Real u_local[4];
+        u_local[0] = 1.0 / std::sqrt(1.0 - SQR(vx_mink) - SQR(vy_mink) - SQR(vz_mink));
+        u_local[1] = u_local[0] * vx_mink;
+        u_local[2] = u_local[0] * vy_mink;
+        u_local[3] = u_local[0] * vz_mink;
+        // (no field: b_local = 0, so the reference's b_sq_local is an exact 0 and its b terms vanish;
+        //  they are kept as written so that signed zeros and roundings follow)
+        Real b_local[4] = {0.0, 0.0, 0.0, 0.0}, b_local_low[4];
+        for (int mu = 0; mu < 4; ++mu) b_local_low[mu] = (mu == 0 ? -1.0 : 1.0) * b_local[mu];
+        Real b_sq_local = 0.0;
+        for (int mu = 0; mu < 4; ++mu) b_sq_local += b_local[mu] * b_local_low[mu];
+        const Real wtot_local = rho_local + gamma_adi_red * pgas_local + b_sq_local;
+        const Real ptot_local = pgas_local + 0.5 * b_sq_local;
+        w(IDN, k, j, i) = w1(IDN, k, j, i) = rho_local;
+        w(IPR, k, j, i) = w1(IPR, k, j, i) = pgas_local;
+        w(IVX, k, j, i) = w1(IVX, k, j, i) = u_local[1];
+        w(IVY, k, j, i) = w1(IVY, k, j, i) = u_local[2];
+        w(IVZ, k, j, i) = w1(IVZ, k, j, i) = u_local[3];
+        uu(IDN, k, j, i) = u_local[0] * rho_local;
+        uu(IEN, k, j, i) = wtot_local * u_local[0] * u_local[0] - b_local[0] * b_local[0] - ptot_local;
+        uu(IM1, k, j, i) = wtot_local * u_local[0] * u_local[1] - b_local[0] * b_local[1];
+        uu(IM2, k, j, i) = wtot_local * u_local[0] * u_local[2] - b_local[0] * b_local[2];
+        uu(IM3, k, j, i) = wtot_local * u_local[0] * u_local[3] - b_local[0] * b_local[3];
+      }
+  if (compute_error) {
+    if ((int)initial.size() <= pmb->lid) initial.resize(pmb->lid + 1);
+    AthenaArray<Real> &ini = initial[pmb->lid];
+    ini.NewAthenaArray(NHYDRO, pmb->ncells3, pmb->ncells2, pmb->ncells1);
+    for (int n = 0; n < NHYDRO; ++n)
+      for (int k = pmb->ks; k <= pmb->ke; ++k)
+        for (int j = pmb->js; j <= pmb->je; ++j)
+          for (int i = pmb->is; i <= pmb->ie; ++i) ini(n, k, j, i) = uu(n, k, j, i);
+  }
+  (void)pin;
+}
+
+static void Errors(Mesh *pm, ParameterInput *pin) {
+  if (!compute_error) return;
+  pm->DownloadAll();
+  Real errors[5 + 1] = {};
+  for (int b = 0; b < pm->nblocal; ++b) {
+    MeshBlock *pmb = pm->my_blocks(b);
+    const AthenaArray<Real> &ini = initial[pmb->lid];
+    for (int k = pmb->ks; k <= pmb->ke; ++k)
+      for (int j = pmb->js; j <= pmb->je; ++j)
+        for (int i = pmb->is; i <= pmb->ie; ++i) {
+          const Real vol = pmb->pcoord->GetCellVolume(k, j, i);
+          for (int n = 0; n < NHYDRO; ++n) errors[n] += std::abs(pmb->phydro->u(n, k, j, i) - ini(n, k, j, i)) * vol;
+          errors[NHYDRO] += vol;
+        }
+  }
+  for (int n = 0; n < NHYDRO; ++n) errors[n] /= errors[NHYDRO];
+  Real total_error = 0.0;
+  for (int n = 0; n < NHYDRO; ++n) total_error += SQR(errors[n]);
+  total_error = std::sqrt(total_error / NHYDRO);
+  const char *fname = "linearwave-errors.dat";
+  FILE *pfile = std::fopen(fname, "r");
+  const bool fresh = (pfile == nullptr);
+  if (pfile != nullptr) std::fclose(pfile);
+  pfile = std::fopen(fname, fresh ? "w" : "a");
+  if (pfile == nullptr) {
+    std::stringstream msg;
+    msg << "### FATAL ERROR in function [Mesh::UserWorkAfterLoop]\n"
+        << "Error output file could not be opened" << std::endl;
+    ATHENA_ERROR(msg);
+  }
+  if (fresh) std::fprintf(pfile, "# Nx1  Nx2  Nx3  Ncycle  RMS-Error  D  E  M1  M2  M3\n");
+  std::fprintf(pfile, "%d  %d  %d  %d  %e", pm->mesh_size.nx1, pm->mesh_size.nx2, pm->mesh_size.nx3, pm->ncycle,
+               total_error);
+  std::fprintf(pfile, "  %e  %e  %e  %e  %e", errors[IDN], errors[IEN], errors[IM1], errors[IM2], errors[IM3]);
+  std::fprintf(pfile, "\n");
+  std::fclose(pfile);
+  (void)pin;
+}
+}  // namespace grlw
+
+//========================================================================================
 static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"linear_wave", LinearWaveInit, LinearWaveGenerator, LinearWaveErrors},
     {"blast", nullptr, BlastGenerator, nullptr},
@@ -1339,6 +1516,7 @@ static const ProblemGeneratorEntry kProblemGenerators[] = {
     {"kh", KHInitUserMeshData, KHGenerator, nullptr},
     {"shock_tube", nullptr, ShockTubeGenerator, ShockTubeErrors},
     {"gr_shock_tube", nullptr, GRShockTubeGenerator, nullptr},
+    {"gr_linear_wave", grlw::Init, grlw::Generator, grlw::Errors},
     {"cpaw", cpaw::CpawInit, cpaw::CpawGenerator, cpaw::CpawErrors},
     {"field_loop", nullptr, FieldLoopGenerator, nullptr},
     {"jet", jet::JetInit, jet::JetGenerator, nullptr},

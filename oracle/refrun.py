@@ -59,6 +59,7 @@ CONFIGS = {
     "blast_sr_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc", SR=1),   # (-s default flux)
     "blast_sr_hydro_llf": dict(PROB="blast", MHD=0, FLUX="llf", SR=1),
     "grtube_sr_hydro_hlle_s1": dict(PROB="gr_shock_tube", MHD=0, FLUX="hlle", SR=1, NSCALARS=1),
+    "grlinwave_sr_hydro_hllc": dict(PROB="gr_linear_wave", MHD=0, FLUX="hllc", SR=1),   # inputs/hydro_sr/athinput.linear_wave
     "grtube_sr_hydro_hllc": dict(PROB="gr_shock_tube", MHD=0, FLUX="hllc", SR=1),   # inputs/hydro_sr/athinput.mb_*
     "ot_iso_mhd_roe": dict(PROB="orszag_tang", MHD=1, FLUX="roe", EOS="isothermal"),
     "ot_iso_mhd_hlld": dict(PROB="orszag_tang", MHD=1, FLUX="hlld", EOS="isothermal"),   # (blast.cpp:208 writes

@@ -78,6 +78,34 @@ def sr_tube_blocks(which, shock_dir, integrator="vl2", sfloor=None):
     }
 
 
+def sr_linwave_blocks(wave_flag, integrator="vl2"):
+    # wave speeds of hydro_convergence.py's wavespeeds_hydro() for this background; tlim = one period
+    gam, rho, pgas, vx, vy, vz = 4.0 / 3.0, 4.0, 1.0, 0.1, 0.3, -0.05
+    wgas = rho + gam / (gam - 1.0) * pgas
+    cs_sq = gam * pgas / wgas
+    v_sq = vx * vx + vy * vy + vz * vz
+    u0_sq = 1.0 / (1.0 - v_sq)
+    delta = u0_sq * (1.0 - cs_sq) + cs_sq
+    a, b = vx * cs_sq, (cs_sq * (u0_sq * (1.0 - cs_sq) * (1.0 - vx * vx) + cs_sq)) ** 0.5
+    lam = {0: vx - (a + b) / delta, 4: vx - (a - b) / delta}.get(wave_flag, vx)
+    tlim = float(1.0 / abs(lam))
+    if tlim > 4.0:
+        tlim = 4.0   # (entropy waves drift at vx = 0.1: a fraction of a period is enough for parity)
+    return {
+        "job": {"problem_id": "srwave"},
+        "output1": {"file_type": "hst", "dt": tlim / 2, "data_format": "%24.16e"},
+        "output2": {"file_type": "rst", "dt": tlim / 2},
+        "time": {"cfl_number": 0.8, "nlim": -1, "tlim": tlim, "integrator": integrator, "xorder": 2, "ncycle_out": 1},
+        "mesh": {"nx1": 64, "x1min": -0.5, "x1max": 0.5, "ix1_bc": "periodic", "ox1_bc": "periodic",
+                 "nx2": 8, "x2min": -0.5, "x2max": 0.5, "ix2_bc": "periodic", "ox2_bc": "periodic",
+                 "nx3": 8, "x3min": -0.5, "x3max": 0.5, "ix3_bc": "periodic", "ox3_bc": "periodic", "num_threads": 1},
+        "meshblock": {"nx1": 16, "nx2": 8, "nx3": 8},
+        "hydro": {"gamma": gam},
+        "problem": {"wave_flag": wave_flag, "amp": 1.0e-6, "compute_error": True, "rho": rho, "pgas": pgas,
+                    "vx": vx, "vy": vy, "vz": vz},
+    }
+
+
 def tube_error_blocks(mhd, shock_dir, integrator="vl2"):
     n = [8, 8, 8]
     n[shock_dir - 1] = 64
@@ -226,6 +254,11 @@ CASES = {
     "sr_tube_mb4_x3_rk3": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: sr_tube_blocks(4, 3, "rk3"), ["-s"]),
     "sr_tube_mb2_x1_scalar_hlle_rk2": ("grtube_sr_hydro_hlle_s1", "gr_shock_tube", False, lambda: sr_tube_blocks(2, 1, "rk2", sfloor=0.0),
                                        ["-s", "--flux=hlle", "--nscalars=1"]),
+    # tst/regression/scripts/tests/sr/hydro_convergence.py: linear waves on a moving background
+    # (rho 4, pgas 1, v = (0.1, 0.3, -0.05), gamma 4/3, amp 1e-6), one period, error row appended by
+    # UserWorkAfterLoop; a sound wave and an entropy (shear) wave
+    "sr_linwave_sound": ("grlinwave_sr_hydro_hllc", "gr_linear_wave", False, lambda: sr_linwave_blocks(0), ["-s"]),
+    "sr_linwave_shear_rk3": ("grlinwave_sr_hydro_hllc", "gr_linear_wave", False, lambda: sr_linwave_blocks(2, "rk3"), ["-s"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
