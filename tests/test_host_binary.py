@@ -551,6 +551,12 @@ def test_host_partitions_blocks_over_gpus_emulated(emul_binary, ngpu, fused):
         del CASES["_mg"]
 
 
+def test_host_partitions_sr_blocks_over_gpus_emulated(emul_binary):
+    # special relativity with the blocks of the tube split over three (emulated) GPUs: ghost messages
+    # carry (D, M, E), W(U) on the received ghosts starts from each GPU's own w / w1
+    compare_with_reference(emul_binary, "sr_tube_mb2_x2", host_mesh_params={"num_gpus": 3})
+
+
 @pytest.mark.parametrize("case,ngpu", [("smr_linwave_mhd_two_levels_rk3", 3), ("smr_kh_mhd_scalar_rk3", 4)])
 def test_host_partitions_refined_mesh_over_gpus_emulated(emul_binary, case, ngpu):
     """Refined meshes over several GPUs: same-level messages through the remote links, boxes between

@@ -64,9 +64,10 @@ def main():
     ap.add_argument("--cycles", type=int, default=30)
     ap.add_argument("--per-gpu", type=int, default=256)
     ap.add_argument("--block", type=int, default=64)
-    ap.add_argument("--config", default="blast", choices=["blast", "config0", "config1", "config3", "smr"],
+    ap.add_argument("--config", default="blast", choices=["blast", "config0", "config1", "config3", "smr", "sr"],
                     help="blast: the bench workload; config0/1/3: BASELINE.json configs[0], [1], [3] shapes; "
-                         "smr: the MHD blast on a statically refined mesh (operator sequence + box lists)")
+                         "smr: the MHD blast on a statically refined mesh (operator sequence + box lists); "
+                         "sr: special-relativistic hydro blast (-s, HLLC)")
     a = ap.parse_args()
     if a.config == "config0":   # 3-D hydro linear wave 64^3, VL2+PLM+HLLC, single MeshBlock, tlim=1
         b = base("LinWave", "vl2", 2, 1.0, -1)
@@ -90,6 +91,15 @@ def main():
         b["problem"] = {"iprob": 4, "amp": 0.01, "vflow": 1.0, "vboost": 0.0, "drho_rho0": 0.0}
         return run_binary(b, ["--prob=kh", "--nghost=3", "--nscalars=1"], "BASELINE configs[3] shape: KH hydro %d^3, "
                           "RK3+PPM+HLLC + 1 passive scalar, %d^3 MeshBlocks" % (n, a.block), n ** 3, 1)
+    if a.config == "sr":   # special-relativistic hydro blast (pressure ratio 1e4), VL2 + PLM + HLLC (hllc_rel.cpp)
+        n = a.per_gpu
+        b = base("Blast", "vl2", 2, 10.0, a.cycles)
+        b.update(mesh_block((n, n, n), (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), (a.block,) * 3))
+        b["hydro"] = {"gamma": 1.666666666667}
+        b["problem"] = {"pamb": 0.01, "prat": 1.0e4, "radius": 0.1, "damb": 1.0, "drat": 1.0, "ramp": 0.0, "b0": 0.0,
+                        "angle": 0}
+        return run_binary(b, ["--prob=blast", "-s"], "SR hydro blast %d^3, %d^3 MeshBlocks, VL2+PLM+HLLC (-s)" % (n, a.block),
+                          n ** 3, 1)
     if a.config == "smr":   # MHD blast, 128^3 root mesh in 32^3 MeshBlocks, the central 2x2x2 root blocks refined once
         b = base("Blast", "vl2", 2, 10.0, a.cycles)
         b.update(mesh_block((128, 128, 128), (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), (32, 32, 32), num_gpus=a.gpus,
