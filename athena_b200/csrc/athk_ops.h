@@ -80,7 +80,9 @@ struct ConstAccPoint {
 
 //========================================================================================
 // EquationOfState::ConservedToPrimitive for one cell (+ CalculateCellCenteredField for MHD)
-template <bool MHD>
+// (SR = true: special-relativistic hydro, its own instantiation so that the Newtonian kernels keep
+//  their register budget)
+template <bool MHD, bool SR = false>
 struct Cons2PrimPoint {
   Grid g;
   EosParams eos;
@@ -143,7 +145,7 @@ struct Cons2PrimPoint {
       if (eos.iso) cons2prim_iso(eos_of_block(eos, blk), uc, wc);
       else cons2prim_mhd(eos_of_block(eos, blk), uc, bc1, bc2, bc3, wc);
     } else {
-      if (eos.sr) {   // the output array still holds W of two calls ago: fallback state and first guess
+      if (SR) {   // the output array still holds W of two calls ago: fallback state and first guess
 #pragma unroll
         for (int n = 0; n < 5; ++n) wc[n] = wb[n * g.sn];
         if (cons2prim_sr(eos_of_block(eos, blk), uc, wc)) {
@@ -195,7 +197,7 @@ struct Cons2PrimPoint {
         dt3 = m.div(dt3, max_std(0.0, (fabs(wc[IVZ]) + fast_speed_m(m, eos, wc[IDN], wc[IPR], b1, b2, bx))));
         }
       } else {
-        if (!eos.sr) {   // (SR: the cell widths themselves, new_blockdt.cpp:130)
+        if (!SR) {   // (SR: the cell widths themselves, new_blockdt.cpp:130)
         const Real cs = eos.iso ? eos.iso_cs : m.sqrt(m.div(eos.gamma * wc[IPR], wc[IDN]));
         dt1 = m.div(dt1, max_std(0.0, (fabs(wc[IVX]) + cs)));
         dt2 = m.div(dt2, max_std(0.0, (fabs(wc[IVY]) + cs)));
