@@ -18,6 +18,7 @@ ARRAYS = dict(
     WGHT_X2F=27, WGHT_X3F=28, S=29, S1=30, S2=31, R=32, SFLUX_X1=33, SFLUX_X2=34, SFLUX_X3=35, W1=36)
 RS_HLLC, RS_HLLD, RS_ROE, RS_HLLE, RS_LLF = range(5)
 ARITH_STRICT, ARITH_FAST = 0, 1
+EOS_ADIABATIC, EOS_ISOTHERMAL, EOS_ADIABATIC_SR = 0, 1, 2
 
 # (nvar, a1, a2, a3): host shape = (nvar, nc3+a3, nc2+a2, nc1+a1); nvar None = nscalars
 SHAPES = {}

@@ -168,7 +168,7 @@ class Context:
     """One GPU context = the MeshBlocks of one rank."""
 
     def __init__(self, mesh, mhd, gamma, rsolver=None, nscalars=0, device=0, gids=None,
-                 rank_of=None, my_rank=0, lib=None, grav_acc=None, arith=0):
+                 rank_of=None, my_rank=0, lib=None, grav_acc=None, arith=0, eos=0, gamma_max=0.0):
         self.lib = lib if lib is not None else capi.load()
         self.mesh = mesh
         self.mhd = bool(mhd)
@@ -186,6 +186,8 @@ class Context:
         cfg.arith = arith      # capi.ARITH_STRICT (bit-exact, default) / capi.ARITH_FAST
         cfg.gamma = gamma
         cfg.dfloor = cfg.pfloor = cfg.sfloor = 0.0
+        cfg.eos = eos          # capi.EOS_ADIABATIC (default) / EOS_ISOTHERMAL needs iso_sound_speed / EOS_ADIABATIC_SR
+        cfg.gamma_max = gamma_max
         h = C.c_void_p()
         capi.check(self.lib, self.lib.athk_create(C.byref(cfg), C.byref(h)))
         self.h = h
