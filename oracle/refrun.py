@@ -57,6 +57,7 @@ CONFIGS = {
     "ot_iso_mhd_llf": dict(PROB="orszag_tang", MHD=1, FLUX="llf", EOS="isothermal"),
     "blast_sr_hydro_hlle": dict(PROB="blast", MHD=0, FLUX="hlle", SR=1),   # configure.py -s (SR part)
     "blast_sr_hydro_hllc": dict(PROB="blast", MHD=0, FLUX="hllc", SR=1),   # (-s default flux)
+    "blast_sr_hydro_hllc_g3": dict(PROB="blast", MHD=0, FLUX="hllc", SR=1, NGHOST=3),   # PPM
     "blast_sr_hydro_llf": dict(PROB="blast", MHD=0, FLUX="llf", SR=1),
     "grtube_sr_hydro_hlle_s1": dict(PROB="gr_shock_tube", MHD=0, FLUX="hlle", SR=1, NSCALARS=1),
     "grlinwave_sr_hydro_hllc": dict(PROB="gr_linear_wave", MHD=0, FLUX="hllc", SR=1),   # inputs/hydro_sr/athinput.linear_wave

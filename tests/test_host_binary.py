@@ -259,6 +259,8 @@ CASES = {
     # UserWorkAfterLoop; a sound wave and an entropy (shear) wave
     "sr_linwave_sound": ("grlinwave_sr_hydro_hllc", "gr_linear_wave", False, lambda: sr_linwave_blocks(0), ["-s"]),
     "sr_linwave_shear_rk3": ("grlinwave_sr_hydro_hllc", "gr_linear_wave", False, lambda: sr_linwave_blocks(2, "rk3"), ["-s"]),
+    "sr_blast_hllc_rk3_ppm": ("blast_sr_hydro_hllc_g3", "blast", False, lambda: sr_blast_blocks(integrator="rk3", xorder=3),
+                              ["-s", "--nghost=3"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
