@@ -55,6 +55,14 @@ SR_TUBES = {   # inputs/hydro_sr/athinput.mb_N: (gamma, dl, pl, ul, vl, wl, dr, 
 }
 
 
+def sr_walls_blocks():
+    b = refrun.blast_blocks(mesh=(32, 32, 32), block=(16, 16, 16), tlim=0.6, rst_dt=0.3, b0=None, radius=0.3,
+                            integrator="vl2", bcs=["reflecting"] * 4 + ["outflow"] * 2, center=(0.5, 0.4, 0.3))
+    b["problem"].update(prat=1.0e3, pamb=0.01)
+    b["hydro"].pop("iso_sound_speed", None)
+    return b
+
+
 def sr_tube_blocks(which, shock_dir, integrator="vl2", sfloor=None):
     gam, dl, pl, ul, vl, wl, dr, pr, ur, vr, wr = SR_TUBES[which]
     n = [8, 8, 8]
@@ -261,6 +269,9 @@ CASES = {
     "sr_linwave_shear_rk3": ("grlinwave_sr_hydro_hllc", "gr_linear_wave", False, lambda: sr_linwave_blocks(2, "rk3"), ["-s"]),
     "sr_blast_hllc_rk3_ppm": ("blast_sr_hydro_hllc_g3", "blast", False, lambda: sr_blast_blocks(integrator="rk3", xorder=3),
                               ["-s", "--nghost=3"]),
+    # SR blast off-centre in a box with four reflecting and two outflow walls (primitives mirrored / copied,
+    # then the SR U(W) on the ghost slabs)
+    "sr_blast_hllc_reflecting": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_walls_blocks(), ["-s"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
