@@ -39,9 +39,13 @@ def fp64_peak():
 
 def committed_traffic():
     """Whole-cycle and per-kernel DRAM bytes from the committed ncu launch list of this bench
-    (profiles/r2_cycle_traffic.json, made by tools/ncu_launch_list.py --json)."""
-    p = os.path.join(ROOT, "profiles", "r2_cycle_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else None
+    (profiles/r5_cycle_traffic.json -- the library as it stands at the end of round 2; r2_cycle_traffic.json is
+    the same capture from the middle of the round -- made by tools/ncu_launch_list.py)."""
+    for name in ("r5_cycle_traffic.json", "r2_cycle_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return None
 # algorithmic bytes per zone of ONE launch of the named kernel (DESIGN.md, kernel table)
 DOMINANT_ALG_BYTES = {"sweep_x1": 31 * 8, "sweep_x2": 16 * 8, "sweep_x3": 16 * 8}
 
