@@ -588,7 +588,7 @@ def _visible_gpus():
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,ngpu", [("mhd_blast", 2), ("kh_mhd_rk2_scalar", 2), ("mhd_blast", 8),
                                        ("smr_linwave_mhd_two_levels_rk3", 2), ("smr_blast_mhd_walls", 2),
-                                       ("smr_kh_mhd_scalar_rk3", 8)])
+                                       ("smr_kh_mhd_scalar_rk3", 8), ("sr_tube_mb2_x2", 2), ("sr_blast_hllc_reflecting", 2)])
 def test_host_binary_on_several_gpus_reproduces_reference_files(cuda_lib, case, ngpu):
     if _visible_gpus() < ngpu:
         pytest.skip("needs %d GPUs" % ngpu)
