@@ -272,6 +272,9 @@ CASES = {
     # SR blast off-centre in a box with four reflecting and two outflow walls (primitives mirrored / copied,
     # then the SR U(W) on the ghost slabs)
     "sr_blast_hllc_reflecting": ("blast_sr_hydro_hllc", "blast", False, lambda: sr_walls_blocks(), ["-s"]),
+    # .tab / .vtk dumps of an SR run (primitives = four-velocity components, taken from the array W(U) wrote last)
+    "sr_tube_mb2_x1_tab_vtk": ("grtube_sr_hydro_hllc", "gr_shock_tube", False, lambda: with_data_dumps(
+        sr_tube_blocks(2, 1), "prim", "cons", "prim"), ["-s"]),
     "sr_blast_llf": ("blast_sr_hydro_llf", "blast", False, lambda: sr_blast_blocks(), ["-s", "--flux=llf"]),
     "iso_orszag_tang_roe": ("ot_iso_mhd_roe", "orszag_tang", True, lambda: iso(
         refrun.ot_blocks(tlim=0.08, rst_dt=0.04), 0.6), ["--eos=isothermal", "--flux=roe"]),
