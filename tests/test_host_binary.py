@@ -917,6 +917,42 @@ def test_restart_resumes_bitwise(emul_binary, case):
     check_restart(emul_binary, case)
 
 
+def check_sr_restart(binary, case="sr_blast_hllc"):
+    """Special relativity: a checkpoint holds U only, so after -r the fixed-point W(U) starts cold (w = w1 = 0,
+    restart.cpp writes w / w1 under GENERAL_RELATIVITY only) and the reference's own restarted run is not its
+    continuous run bit for bit.  What must hold: both codes, restarted from the same checkpoint, end identically."""
+    cfg, prob, mhd, mk = CASES[case][:4]
+    extra = CASES[case][4]
+    if not refrun.have_ref(cfg):
+        pytest.skip("reference binary oracle/_ref/athena_%s not built" % cfg)
+    dirs = []
+    try:
+        wd_ref, _ = refrun.run_reference(cfg, mk())
+        dirs.append(wd_ref)
+        mid = sorted(glob.glob(wd_ref + "/*.00001.rst"))[0]
+        wd_a, wd_b = tempfile.mkdtemp(prefix="athref_"), tempfile.mkdtemp(prefix="athhost_")
+        dirs += [wd_a, wd_b]
+        r = subprocess.run([refrun.ref_binary(cfg), "-r", mid, "-d", wd_a], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS="1"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        r = subprocess.run([binary, "-r", mid, "-d", wd_b, "--prob=" + prob] + list(extra), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rst_equal(refrun.read_rst(glob.glob(wd_a + "/*.final.rst")[0]), refrun.read_rst(glob.glob(wd_b + "/*.final.rst")[0]))
+    finally:
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
+
+
+def test_sr_restart_matches_the_reference_restarted_from_the_same_checkpoint(emul_binary):
+    check_sr_restart(emul_binary)
+
+
+@pytest.mark.gpu
+def test_sr_restart_matches_the_reference_restarted_from_the_same_checkpoint_on_gpu(cuda_lib):
+    check_sr_restart(CUDA_BIN)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", RESTART_CASES)
 def test_restart_resumes_bitwise_on_gpu(cuda_lib, case):
