@@ -1173,7 +1173,7 @@ ATHK_HD void with_math(F &&body) {
   }
 #endif
 #if ATHK_SL_MATH && defined(__CUDA_ARCH__)
-  if (RS == RS_HLLC || RS == RS_HLLD) {
+  if (RS == RS_HLLC || RS == RS_HLLD || RS == RS_SR) {   // (RS_SR: reconstruction and flux divergence; its solvers keep the compiler's operations)
     MathSL m;
     body(m);
     if (!m.ok()) {
