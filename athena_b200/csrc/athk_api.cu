@@ -655,13 +655,14 @@ static int cons2prim_part(athk_ctx *c, int reg, int part) {
     else LAUNCH_NAMED(c, "athk_cons2prim",
                       launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f));
   } else if (c->eos.sr) {
+    // (the fixed-point iteration wants ~100 registers: 4 CTAs per SM instead of the streaming kernels' 8 / 6)
     Cons2PrimPoint<false, true> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo,
                                ns ? c->s[reg] : nullptr, c->r, ns};
     if (part == 2) LAUNCH_NAMED(c, "athk_cons2prim", launch_shell(c->stream, g.nb, rall, rin, f));
     else if (fold) LAUNCH_NAMED(c, "athk_cons2prim_dt",
-                                launch_points_min<6>(c->stream, g.nb, part == 1 ? rin : rall, f, dt_out));
+                                launch_points_min<4>(c->stream, g.nb, part == 1 ? rin : rall, f, dt_out));
     else LAUNCH_NAMED(c, "athk_cons2prim",
-                      launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f));
+                      launch_points_occ<4>(c->stream, g.nb, part == 1 ? rin : rall, f));
   } else {
     Cons2PrimPoint<false> f = {g, c->eos, c->u[reg], nullptr, c->w, nullptr, c->nbr, dt_out, c->geo,
                                ns ? c->s[reg] : nullptr, c->r, ns};
