@@ -624,6 +624,9 @@ extern "C" int athk_request_block_dt(athk_ctx *c) {
 
 // part 0: whole box; 1: active zone only (needs no ghost data: can run under the inter-GPU ghost
 // transfer); 2: ghost shell only.
+#ifndef ATHK_C2PDT_MINB
+#define ATHK_C2PDT_MINB 6   // CTAs per SM of the MHD W(U) + block-dt kernel (development knob)
+#endif
 static int cons2prim_part(athk_ctx *c, int reg, int part);
 extern "C" int athk_cons2prim(athk_ctx *c, int reg) { return cons2prim_part(c, reg, 0); }
 
@@ -651,7 +654,7 @@ static int cons2prim_part(athk_ctx *c, int reg, int part) {
                               ns ? c->s[reg] : nullptr, c->r, ns};
     if (part == 2) LAUNCH_NAMED(c, "athk_cons2prim", launch_shell(c->stream, g.nb, rall, rin, f));
     else if (fold) LAUNCH_NAMED(c, "athk_cons2prim_dt",
-                                launch_points_min<6>(c->stream, g.nb, part == 1 ? rin : rall, f, dt_out));
+                                launch_points_min<ATHK_C2PDT_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f, dt_out));
     else LAUNCH_NAMED(c, "athk_cons2prim",
                       launch_points_occ<ATHK_STREAM_MINB>(c->stream, g.nb, part == 1 ? rin : rall, f));
   } else if (c->eos.sr) {
